@@ -1,0 +1,618 @@
+// a6/a7: 2DGS rasterisation forward + backward, 3 colour channels, packed.
+//
+// Reference behaviour: GSF/csrc/RasterizeToPixels2DGSFwd.cu:19-473 and
+// GSF/csrc/RasterizeToPixels2DGSBwd.cu:16-709 (host glue GSF/csrc/Rasterization.cpp:324-612).
+// Per pixel, front to back over the tile's depth-sorted splats:
+//   h_u = px*M_w - M_u ; h_v = py*M_w - M_v ; zeta = h_u x h_v ; (u,v) = zeta.xy / zeta.z
+//   depth = u*M_w.x + v*M_w.y + M_w.z ; alpha = min(0.999, o*exp(-(u^2+v^2)/2))
+//   skip if zeta.z == 0, depth < 0.05, alpha < 1/255 ; stop when T*(1-alpha) <= 1e-4
+//
+// B200-first design
+//   * one 64-byte render record per visible splat (M[9], opacity, rgb[3], normal[3]) packed once per
+//     call; a tile's CTA gathers the records of its depth-sorted list with per-record TMA bulk copies
+//     (cp.async.bulk, mbarrier complete_tx) into a 2-stage shared-memory ring, so the per-pixel loop
+//     only touches shared memory (the reference re-reads colours/normals from global memory per
+//     (pixel, splat) and issues one float atomic per (pixel, splat) for the visibilities);
+//   * a warp owns an 8x4 pixel block; per-splat reductions (visibility forward, the 16-float gradient
+//     record backward) are warp-shuffle reductions: backward uses a 16-shuffle butterfly instead of the
+//     reference's 16 x 5 cg::reduce shuffles, accumulates the tile's 8 warps in shared memory and
+//     issues ONE 64-byte RED per (tile, splat) instead of 16 atomics per (warp, splat);
+//   * v_densify is a well-defined post-pass instead of the reference's racy read (Bwd.cu:699-706).
+#include "common.cuh"
+
+namespace gssdf {
+
+constexpr int kRasterThreads = 256;
+constexpr int kBatch = 256;  // splats per shared-memory stage
+constexpr float kNearN = 0.05f, kFarN = 100.f;  // hard-coded in the reference (Fwd.cu:368-369)
+constexpr float kAlphaThreshold = 1.f / 255.f;  // GSF/include/Common.h:53
+
+// ---------------------------------------------------------------------------------------------
+// record packing
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_records_kernel(const gssdf_counts *counts, const float *__restrict__ ray_transforms,
+                    const float *__restrict__ colors, const float *__restrict__ opacities,
+                    const float *__restrict__ normals, float4 *__restrict__ rec, float *__restrict__ zero_a,
+                    int zero_a_stride) {
+    const int nnz = counts->nnz;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    const float *M = ray_transforms + 9 * (int64_t)i;
+    const float *c = colors + 3 * (int64_t)i;
+    const float *n = normals + 3 * (int64_t)i;
+    float4 *r = rec + 4 * (int64_t)i;
+    r[0] = make_float4(M[0], M[1], M[2], M[3]);
+    r[1] = make_float4(M[4], M[5], M[6], M[7]);
+    r[2] = make_float4(M[8], opacities[i], c[0], c[1]);
+    r[3] = make_float4(c[2], n[0], n[1], n[2]);
+    if (zero_a) {
+        for (int k = 0; k < zero_a_stride; ++k) zero_a[(int64_t)i * zero_a_stride + k] = 0.f;
+    }
+}
+
+struct TileInfo {
+    int cam, tile, rs, re;
+    int tx, ty;
+};
+
+__device__ __forceinline__ TileInfo tile_info(int C, int tw, int th, const int32_t *offsets, const gssdf_counts *counts) {
+    TileInfo t;
+    const int n_tiles = tw * th;
+    const int bin = blockIdx.x;
+    t.cam = bin / n_tiles;
+    t.tile = bin % n_tiles;
+    t.ty = t.tile / tw;
+    t.tx = t.tile % tw;
+    const int n_isects = counts->n_isects;
+    t.rs = min(offsets[bin], n_isects);
+    t.re = (bin == C * n_tiles - 1) ? n_isects : min(offsets[bin + 1], n_isects);
+    return t;
+}
+
+// thread -> pixel: warp w owns the 8x4 block (w & 1, w >> 1) of the 16x16 tile
+__device__ __forceinline__ void pixel_of_thread(int &lx, int &ly) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    lx = (warp & 1) * 8 + (lane & 7);
+    ly = (warp >> 1) * 4 + (lane >> 3);
+}
+
+struct __align__(16) Stage {
+    float4 rec[kBatch * 4];  // 16 KB
+    int ids[kBatch];         // packed splat index of each record
+    float acc[kBatch];       // per-splat tile accumulator (visibility)
+};
+
+// issue the gather of batch [start, start+n) (n <= kBatch) into `st`; every thread arrives once
+__device__ __forceinline__ void issue_batch(Stage &st, uint64_t *bar, const float4 *__restrict__ rec,
+                                            const int32_t *__restrict__ flatten_ids, int start, int n) {
+    const int t = threadIdx.x;
+    if (t < n) {
+        const int g = flatten_ids[start + t];
+        st.ids[t] = g;
+        st.acc[t] = 0.f;
+        bulk_g2s(&st.rec[t * 4], rec + 4 * (int64_t)g, 64, bar);
+        mbar_arrive_expect_tx(bar, 64);
+    } else {
+        mbar_arrive(bar);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRasterThreads)
+raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restrict__ rec, int tw, int th) {
+    __shared__ Stage s_stage[2];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const TileInfo ti = tile_info(a.C, tw, th, a.offsets, a.counts);
+    const int W = a.image_width, H = a.image_height;
+    int lx, ly;
+    pixel_of_thread(lx, ly);
+    const int i = ti.ty * kTile + ly, j = ti.tx * kTile + lx;
+    const bool inside = i < H && j < W;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const int64_t pix = ((int64_t)ti.cam * H + i) * W + j;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], kRasterThreads);
+        mbar_init(&s_bar[1], kRasterThreads);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int n_total = ti.re - ti.rs;
+    const int nb = (n_total + kBatch - 1) / kBatch;
+    if (nb > 0) issue_batch(s_stage[0], &s_bar[0], rec, a.flatten_ids, ti.rs, min(kBatch, n_total));
+    if (nb > 1) issue_batch(s_stage[1], &s_bar[1], rec, a.flatten_ids, ti.rs + kBatch, min(kBatch, n_total - kBatch));
+
+    float T = 1.f;
+    float pc0 = 0.f, pc1 = 0.f, pc2 = 0.f, pn0 = 0.f, pn1 = 0.f, pn2 = 0.f;
+    float dout = 0.f, M1 = 0.f, M2 = 0.f, distort = 0.f, median_depth = 0.f;
+    int cur_idx = 0, median_idx = 0;
+    bool done = !inside;
+    int waited = 0;  // batches whose barrier has been consumed
+
+    for (int b = 0; b < nb; ++b) {
+        Stage &st = s_stage[b & 1];
+        mbar_wait(&s_bar[b & 1], (b >> 1) & 1);
+        waited = b + 1;
+        const int start = ti.rs + b * kBatch;
+        const int bn = min(kBatch, ti.re - start);
+        for (int t = 0; t < bn; ++t) {
+            if (__all_sync(0xffffffffu, done)) break;
+            const float4 r0 = st.rec[t * 4 + 0], r1 = st.rec[t * 4 + 1], r2 = st.rec[t * 4 + 2], r3 = st.rec[t * 4 + 3];
+            // M rows: u = (r0.x r0.y r0.z) v = (r0.w r1.x r1.y) w = (r1.z r1.w r2.x)
+            const float hux = px * r1.z - r0.x, huy = px * r1.w - r0.y, huz = px * r2.x - r0.z;
+            const float hvx = py * r1.z - r0.w, hvy = py * r1.w - r1.x, hvz = py * r2.x - r1.y;
+            const float rcx = huy * hvz - huz * hvy, rcy = huz * hvx - hux * hvz, rcz = hux * hvy - huy * hvx;
+            bool ok = !done && rcz != 0.f;
+            const float inv_rcz = __fdividef(1.f, rcz);
+            const float sx = rcx * inv_rcz, sy = rcy * inv_rcz;
+            const float sigma = 0.5f * (sx * sx + sy * sy);
+            const float depth = sx * r1.z + sy * r1.w + r2.x;
+            ok = ok && !(depth < kNearN);
+            const float alpha = fminf(0.999f, r2.y * __expf(-sigma));
+            ok = ok && !(sigma < 0.f || alpha < kAlphaThreshold);
+            const float next_T = T * (1.f - alpha);
+            if (ok && next_T <= 1e-4f) { done = true; ok = false; }
+            float vis = 0.f;
+            if (ok) {
+                vis = alpha * T;
+                pc0 += r2.z * vis; pc1 += r2.w * vis; pc2 += r3.x * vis;
+                dout += depth * vis;
+                pn0 += r3.y * vis; pn1 += r3.z * vis; pn2 += r3.w * vis;
+                const float A = 1.f - T;
+                const float m = kFarN / (kFarN - kNearN) * (1.f - kNearN / depth);
+                distort += (m * m * A + M1 - 2.f * m * M2) * vis;
+                M1 += m * m * vis;
+                M2 += m * vis;
+                if (T > 0.5f) { median_depth = depth; median_idx = start + t; }
+                cur_idx = start + t;
+                T = next_T;
+            }
+            if (__any_sync(0xffffffffu, ok)) {
+                const float v = warp_sum(vis);
+                if (lane == 0) atomicAdd(&st.acc[t], v);
+            }
+        }
+        const int n_done = __syncthreads_count(done);
+        // flush this batch's visibilities: one RED per (tile, splat)
+        if (threadIdx.x < bn) {
+            const float v = st.acc[threadIdx.x];
+            if (v != 0.f) atomicAdd(a.visibilities + st.ids[threadIdx.x], v);
+        }
+        if (n_done == kRasterThreads) break;
+        __syncthreads();  // stage b&1 fully consumed -> refill with batch b+2
+        if (b + 2 < nb) {
+            const int s2 = ti.rs + (b + 2) * kBatch;
+            issue_batch(st, &s_bar[b & 1], rec, a.flatten_ids, s2, min(kBatch, ti.re - s2));
+        }
+    }
+    // never leave the CTA with a bulk copy in flight into its shared memory
+    {
+        const int issued = min(nb, waited + 1);
+        for (int b = waited; b < issued; ++b) mbar_wait(&s_bar[b & 1], (b >> 1) & 1);
+    }
+
+    if (inside) {
+        a.render_depths[pix] = dout;
+        a.render_alphas[pix] = 1.f - T;
+        reinterpret_cast<float2 *>(a.render_Ts)[pix] = make_float2(M1, M2);
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        if (a.backgrounds) { b0 = a.backgrounds[3 * ti.cam]; b1 = a.backgrounds[3 * ti.cam + 1]; b2 = a.backgrounds[3 * ti.cam + 2]; }
+        a.render_colors[3 * pix] = pc0 + T * b0;
+        a.render_colors[3 * pix + 1] = pc1 + T * b1;
+        a.render_colors[3 * pix + 2] = pc2 + T * b2;
+        a.render_normals[3 * pix] = pn0;
+        a.render_normals[3 * pix + 1] = pn1;
+        a.render_normals[3 * pix + 2] = pn2;
+        a.last_ids[pix] = cur_idx;
+        a.render_distort[pix] = distort;
+        a.render_median[pix] = median_depth;
+        a.median_ids[pix] = median_idx;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) BwdStage {
+    float4 rec[kBatch * 4];
+    int ids[kBatch];
+    float grad[kBatch * 16];  // per-splat tile gradient record: rgb[3] n[3] u[3] v[3] w[3] opacity
+    float gabs[kBatch * 2];
+};
+
+__device__ __forceinline__ void issue_batch_bwd(BwdStage &st, uint64_t *bar, const float4 *__restrict__ rec,
+                                                const int32_t *__restrict__ flatten_ids, int last, int n) {
+    // batch covers sorted indices last, last-1, ..., last-n+1 (slot t <-> index last - t)
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) st.grad[k * kBatch + t] = 0.f;  // [16][kBatch] transposed zero-fill (conflict-free)
+    st.gabs[t] = 0.f;
+    st.gabs[kBatch + t] = 0.f;
+    if (t < n) {
+        const int g = flatten_ids[last - t];
+        st.ids[t] = g;
+        bulk_g2s(&st.rec[t * 4], rec + 4 * (int64_t)g, 64, bar);
+        mbar_arrive_expect_tx(bar, 64);
+    } else {
+        mbar_arrive(bar);
+    }
+}
+
+template <bool ABS>
+__global__ void __launch_bounds__(kRasterThreads)
+raster2dgs_bwd_kernel(const gssdf_raster2dgs_bwd_args a, const float4 *__restrict__ rec, float *__restrict__ vrec,
+                      int tw, int th) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    BwdStage *s_stage = reinterpret_cast<BwdStage *>(s_raw);
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const TileInfo ti = tile_info(a.C, tw, th, a.offsets, a.counts);
+    const int n_total = ti.re - ti.rs;
+    if (n_total <= 0) return;
+    const int W = a.image_width, H = a.image_height;
+    int lx, ly;
+    pixel_of_thread(lx, ly);
+    const int i = ti.ty * kTile + ly, j = ti.tx * kTile + lx;
+    const bool inside = i < H && j < W;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const int64_t pix = inside ? ((int64_t)ti.cam * H + i) * W + j : 0;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], kRasterThreads);
+        mbar_init(&s_bar[1], kRasterThreads);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const float T_final = inside ? 1.f - a.render_alphas[pix] : 1.f;
+    float T = T_final;
+    float bc0 = 0.f, bc1 = 0.f, bc2 = 0.f, bn0 = 0.f, bn1 = 0.f, bn2 = 0.f, bd = 0.f;
+    const int bin_final = inside ? a.last_ids[pix] : -1;
+    const int median_idx = inside ? a.median_ids[pix] : -1;
+    float vc0 = 0.f, vc1 = 0.f, vc2 = 0.f, vd = 0.f, va = 0.f, vn0 = 0.f, vn1 = 0.f, vn2 = 0.f, v_median = 0.f;
+    if (inside) {
+        vc0 = a.v_render_colors[3 * pix]; vc1 = a.v_render_colors[3 * pix + 1]; vc2 = a.v_render_colors[3 * pix + 2];
+        vd = a.v_render_depths[pix];
+        va = a.v_render_alphas[pix];
+        vn0 = a.v_render_normals[3 * pix]; vn1 = a.v_render_normals[3 * pix + 1]; vn2 = a.v_render_normals[3 * pix + 2];
+        v_median = a.v_render_median[pix];
+    }
+    float bgdot = 0.f;
+    if (a.backgrounds)
+        bgdot = a.backgrounds[3 * ti.cam] * vc0 + a.backgrounds[3 * ti.cam + 1] * vc1 + a.backgrounds[3 * ti.cam + 2] * vc2;
+
+    // pixels that never composited anything keep last_ids == 0 (Fwd.cu:209,463); index 0 only
+    // exists in the first non-empty tile, elsewhere nothing is <= bin_final.
+    const int warp_bin_final = warp_max_i(bin_final);
+
+    // process sorted indices re-1 ... rs in batches of kBatch, back to front
+    const int nb = (n_total + kBatch - 1) / kBatch;
+    issue_batch_bwd(s_stage[0], &s_bar[0], rec, a.flatten_ids, ti.re - 1, min(kBatch, n_total));
+    if (nb > 1) issue_batch_bwd(s_stage[1], &s_bar[1], rec, a.flatten_ids, ti.re - 1 - kBatch, min(kBatch, n_total - kBatch));
+
+    for (int b = 0; b < nb; ++b) {
+        BwdStage &st = s_stage[b & 1];
+        mbar_wait(&s_bar[b & 1], (b >> 1) & 1);
+        const int last = ti.re - 1 - b * kBatch;  // sorted index held by slot 0
+        const int bn = min(kBatch, last - ti.rs + 1);
+        // skip the slots behind every pixel of this warp's last contributor (Bwd.cu:333)
+        for (int t = max(0, last - warp_bin_final); t < bn; ++t) {
+            const int idx = last - t;
+            const float4 r0 = st.rec[t * 4 + 0], r1 = st.rec[t * 4 + 1], r2 = st.rec[t * 4 + 2], r3 = st.rec[t * 4 + 3];
+            const float hux = px * r1.z - r0.x, huy = px * r1.w - r0.y, huz = px * r2.x - r0.z;
+            const float hvx = py * r1.z - r0.w, hvy = py * r1.w - r1.x, hvz = py * r2.x - r1.y;
+            const float rcx = huy * hvz - huz * hvy, rcy = huz * hvx - hux * hvz, rcz = hux * hvy - huy * hvx;
+            bool valid = inside && idx <= bin_final && rcz != 0.f;
+            const float inv_rcz = __fdividef(1.f, rcz);
+            const float sx = rcx * inv_rcz, sy = rcy * inv_rcz;
+            const float sigma = 0.5f * (sx * sx + sy * sy);
+            const float depth = sx * r1.z + sy * r1.w + r2.x;
+            valid = valid && !(depth < kNearN);
+            const float opac = r2.y;
+            const float vis = __expf(-sigma);
+            const float alpha = fminf(0.999f, opac * vis);
+            valid = valid && !(sigma < 0.f || alpha < kAlphaThreshold);
+            if (!__any_sync(0xffffffffu, valid)) continue;
+
+            float g[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) g[k] = 0.f;
+            if (valid) {
+                float v_depth = (idx == median_idx) ? v_median : 0.f;
+                const float ra = __fdividef(1.f, 1.f - alpha);
+                T *= ra;
+                const float fac = alpha * T;
+                g[0] = fac * vc0; g[1] = fac * vc1; g[2] = fac * vc2;
+                g[3] = fac * vn0; g[4] = fac * vn1; g[5] = fac * vn2;
+                float v_alpha = (r2.z * T - bc0 * ra) * vc0 + (r2.w * T - bc1 * ra) * vc1 + (r3.x * T - bc2 * ra) * vc2;
+                v_alpha += (r3.y * T - bn0 * ra) * vn0 + (r3.z * T - bn1 * ra) * vn1 + (r3.w * T - bn2 * ra) * vn2;
+                v_alpha += T_final * ra * va;
+                v_alpha += -T_final * ra * bgdot;
+                v_alpha += (depth * T - bd * ra) * vd;
+                if (opac * vis <= 0.999f) {
+                    v_depth += fac * vd;
+                    const float v_G = opac * v_alpha;
+                    const float vsx = v_G * -vis * sx + v_depth * r1.z;
+                    const float vsy = v_G * -vis * sy + v_depth * r1.w;
+                    const float vsxz = vsx * inv_rcz, vsyz = vsy * inv_rcz;
+                    const float vrx = vsxz, vry = vsyz, vrz = -(vsxz * sx + vsyz * sy);
+                    // v_h_u = h_v x v_rc ; v_h_v = v_rc x h_u
+                    const float vhux = hvy * vrz - hvz * vry, vhuy = hvz * vrx - hvx * vrz, vhuz = hvx * vry - hvy * vrx;
+                    const float vhvx = vry * huz - vrz * huy, vhvy = vrz * hux - vrx * huz, vhvz = vrx * huy - vry * hux;
+                    g[6] = -vhux; g[7] = -vhuy; g[8] = -vhuz;
+                    g[9] = -vhvx; g[10] = -vhvy; g[11] = -vhvz;
+                    g[12] = px * vhux + py * vhvx + v_depth * sx;
+                    g[13] = px * vhuy + py * vhvy + v_depth * sy;
+                    g[14] = px * vhuz + py * vhvz + v_depth;
+                    g[15] = vis * v_alpha;
+                }
+                bc0 += r2.z * fac; bc1 += r2.w * fac; bc2 += r3.x * fac;
+                bd += depth * fac;
+                bn0 += r3.y * fac; bn1 += r3.z * fac; bn2 += r3.w * fac;
+            }
+            // butterfly reduction of the 16-float record over the 32 lanes: 8+4+2+1+1 shuffles
+            float h8[8], h4[4], h2[2], h1;
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float send = b4 ? g[k] : g[k + 8], keep = b4 ? g[k + 8] : g[k];
+                h8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float send = b3 ? h8[k] : h8[k + 4], keep = b3 ? h8[k + 4] : h8[k];
+                h4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float send = b2 ? h4[k] : h4[k + 2], keep = b2 ? h4[k + 2] : h4[k];
+                h2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            {
+                const float send = b1 ? h2[0] : h2[1], keep = b1 ? h2[1] : h2[0];
+                h1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            h1 += __shfl_xor_sync(0xffffffffu, h1, 1);
+            const int comp = lane >> 1;  // gradient component held by this lane pair
+            if ((lane & 1) == 0) atomicAdd(&st.grad[comp * kBatch + t], h1);
+            if (ABS) {
+                // |sum over the warp's 8x4 pixel block of dL/dM_u.z (resp. M_v.z)| * M_w.z
+                if (lane == 16) atomicAdd(&st.gabs[t], fabsf(h1 * r2.x));           // comp 8  = u.z
+                if (lane == 22) atomicAdd(&st.gabs[kBatch + t], fabsf(h1 * r2.x));  // comp 11 = v.z
+            }
+        }
+        __syncthreads();
+        // flush: one 64-byte RED burst per (tile, splat); 16 consecutive threads cover one record
+        for (int e = threadIdx.x; e < bn * 16; e += kRasterThreads) {
+            const int t = e >> 4, k = e & 15;
+            const float v = st.grad[k * kBatch + t];
+            if (v != 0.f) atomicAdd(vrec + 16 * (int64_t)st.ids[t] + k, v);
+        }
+        if (ABS) {
+            for (int e = threadIdx.x; e < bn * 2; e += kRasterThreads) {
+                const int t = e >> 1, k = e & 1;
+                const float v = st.gabs[k * kBatch + t];
+                if (v != 0.f) atomicAdd(a.v_means2d_abs + 2 * (int64_t)st.ids[t] + k, v);
+            }
+        }
+        __syncthreads();
+        if (b + 2 < nb) {
+            const int l2 = ti.re - 1 - (b + 2) * kBatch;
+            issue_batch_bwd(st, &s_bar[b & 1], rec, a.flatten_ids, l2, min(kBatch, l2 - ti.rs + 1));
+        }
+    }
+}
+
+// v_rec[nnz,16] -> the reference's separate gradient tensors (+ v_densify post-pass)
+__global__ void __launch_bounds__(256)
+raster_bwd_finalize_kernel(const gssdf_raster2dgs_bwd_args a, const float4 *__restrict__ vrec) {
+    const int nnz = a.counts->nnz;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    const float4 g0 = vrec[4 * (int64_t)i], g1 = vrec[4 * (int64_t)i + 1], g2 = vrec[4 * (int64_t)i + 2], g3 = vrec[4 * (int64_t)i + 3];
+    float *vc = a.v_colors + 3 * (int64_t)i;
+    vc[0] = g0.x; vc[1] = g0.y; vc[2] = g0.z;
+    float *vn = a.v_normals + 3 * (int64_t)i;
+    vn[0] = g0.w; vn[1] = g1.x; vn[2] = g1.y;
+    float *vm = a.v_ray_transforms + 9 * (int64_t)i;
+    vm[0] = g1.z; vm[1] = g1.w; vm[2] = g2.x;
+    vm[3] = g2.y; vm[4] = g2.z; vm[5] = g2.w;
+    vm[6] = g3.x; vm[7] = g3.y; vm[8] = g3.z;
+    a.v_opacities[i] = g3.w;
+    if (a.v_means2d) { a.v_means2d[2 * (int64_t)i] = 0.f; a.v_means2d[2 * (int64_t)i + 1] = 0.f; }
+    if (a.v_densify) {
+        const float mz = a.ray_transforms[9 * (int64_t)i + 8];
+        a.v_densify[2 * (int64_t)i] = g2.x * mz;
+        a.v_densify[2 * (int64_t)i + 1] = g2.w * mz;
+    }
+}
+
+// a8 -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cam_rot(const float *viewmats, int cam, float R[9]) {
+    const float *v = viewmats + 16 * cam;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) R[r * 3 + c] = v[r * 4 + c];
+}
+
+__global__ void __launch_bounds__(256) render_post_fwd_kernel(const gssdf_render_post_fwd_args a) {
+    const int64_t P = (int64_t)a.image_width * a.image_height;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P * a.C) return;
+    const int cam = (int)(p / P);
+    float R[9];
+    cam_rot(a.viewmats, cam, R);
+    const float al = a.render_alphas[p], d = a.render_depths[p];
+    // (render_depths / render_alphas).nan_to_num(): nan -> 0, +-inf -> +-FLT_MAX
+    float ed = d / al;
+    if (isnan(ed)) ed = 0.f;
+    else if (isinf(ed)) ed = ed > 0 ? 3.402823466e38f : -3.402823466e38f;
+    reinterpret_cast<float4 *>(a.out_colors)[p] =
+        make_float4(a.render_colors[3 * p], a.render_colors[3 * p + 1], a.render_colors[3 * p + 2], ed);
+    // n_world = n_cam * inverse(V)[:3,:3]^T = n_cam * R  (R_c2w^T == R for a rigid world->camera V)
+    const float n0 = a.render_normals[3 * p], n1 = a.render_normals[3 * p + 1], n2 = a.render_normals[3 * p + 2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) a.out_normals[3 * p + c] = n0 * R[c] + n1 * R[3 + c] + n2 * R[6 + c];
+}
+
+__global__ void __launch_bounds__(256) render_post_bwd_kernel(const gssdf_render_post_bwd_args a) {
+    const int64_t P = (int64_t)a.image_width * a.image_height;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P * a.C) return;
+    const int cam = (int)(p / P);
+    float R[9];
+    cam_rot(a.viewmats, cam, R);
+    const float4 vo = reinterpret_cast<const float4 *>(a.v_out_colors)[p];
+    a.v_render_colors[3 * p] = vo.x; a.v_render_colors[3 * p + 1] = vo.y; a.v_render_colors[3 * p + 2] = vo.z;
+    const float al = a.render_alphas[p], d = a.render_depths[p];
+    const float ed = d / al;
+    float vdep = 0.f, val = a.v_alphas_in ? a.v_alphas_in[p] : 0.f;
+    if (!(isnan(ed) || isinf(ed))) {  // nan_to_num passes gradient only through finite values
+        vdep = vo.w / al;
+        val += -vo.w * d / (al * al);
+    }
+    a.v_render_depths[p] = vdep;
+    a.v_render_alphas[p] = val;
+    const float g0 = a.v_out_normals[3 * p], g1 = a.v_out_normals[3 * p + 1], g2 = a.v_out_normals[3 * p + 2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) a.v_render_normals[3 * p + r] = g0 * R[r * 3] + g1 * R[r * 3 + 1] + g2 * R[r * 3 + 2];
+}
+
+// f-1 (minimal): L1 photometric + depth loss and its cotangent in one pass
+__global__ void __launch_bounds__(256) l1_loss_kernel(const gssdf_l1_loss_args a, int64_t n_pix) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float part = 0.f;
+    if (p < n_pix) {
+        const float4 o = reinterpret_cast<const float4 *>(a.out_colors)[p];
+        const float4 g = reinterpret_cast<const float4 *>(a.gt)[p];
+        const float sr = a.w_rgb / (3.f * (float)n_pix), sd = a.w_depth / (float)n_pix;
+        const float d0 = o.x - g.x, d1 = o.y - g.y, d2 = o.z - g.z, d3 = o.w - g.w;
+        part = sr * (fabsf(d0) + fabsf(d1) + fabsf(d2)) + sd * fabsf(d3);
+        auto sgn = [](float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); };
+        reinterpret_cast<float4 *>(a.v_out_colors)[p] = make_float4(sr * sgn(d0), sr * sgn(d1), sr * sgn(d2), sd * sgn(d3));
+    }
+    part = warp_sum(part);
+    __shared__ float s_part[8];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += s_part[w];
+        atomicAdd(a.loss_out, s);
+    }
+}
+
+}  // namespace gssdf
+
+using namespace gssdf;
+
+extern "C" int gssdf_l1_loss(const gssdf_l1_loss_args *a, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "l1_loss: null args");
+    GSSDF_REQUIRE(a->C > 0 && a->image_width > 0 && a->image_height > 0, GSSDF_EINVAL, "l1_loss: bad image size");
+    GSSDF_REQUIRE(a->out_colors && a->gt && a->loss_out && a->v_out_colors, GSSDF_EINVAL, "l1_loss: null pointer");
+    const int64_t n = (int64_t)a->C * a->image_width * a->image_height;
+    l1_loss_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(*a, n);
+    GSSDF_LAUNCH_OK("l1_loss_kernel");
+    return GSSDF_OK;
+}
+
+extern "C" size_t gssdf_raster2dgs_workspace_bytes(int32_t cap) { return align_up((size_t)(cap > 0 ? cap : 1) * 64, 256); }
+extern "C" size_t gssdf_raster2dgs_bwd_workspace_bytes(int32_t cap) { return 2 * align_up((size_t)(cap > 0 ? cap : 1) * 64, 256); }
+
+static int check_raster_common(const char *who, int C, int W, int H, int tile_size, int channels) {
+    GSSDF_REQUIRE(C > 0 && W > 0 && H > 0, GSSDF_EINVAL, "%s: C, width, height must be positive", who);
+    GSSDF_REQUIRE(tile_size == kTile, GSSDF_EUNSUPPORTED, "%s: tile_size %d unsupported (GS-SDF renders with 16)", who, tile_size);
+    GSSDF_REQUIRE(channels == 3, channels <= 0 || channels > 512 ? GSSDF_EINVAL : GSSDF_EUNSUPPORTED,
+                  "%s: Unsupported number of color channels: %d", who, channels);
+    return GSSDF_OK;
+}
+
+extern "C" int gssdf_raster2dgs_fwd(const gssdf_raster2dgs_fwd_args *a, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "raster2dgs_fwd: null args");
+    int rc = check_raster_common("raster2dgs_fwd", a->C, a->image_width, a->image_height, a->tile_size, a->channels);
+    if (rc) return rc;
+    GSSDF_REQUIRE(a->counts && a->offsets && a->render_colors && a->render_depths && a->render_alphas && a->render_normals &&
+                      a->render_distort && a->render_median && a->render_Ts && a->last_ids && a->median_ids,
+                  GSSDF_EINVAL, "raster2dgs_fwd: null output / counts / offsets");
+    GSSDF_REQUIRE(a->cap == 0 || (a->ray_transforms && a->colors && a->opacities && a->normals && a->flatten_ids && a->visibilities),
+                  GSSDF_EINVAL, "raster2dgs_fwd: null splat input");
+    GSSDF_REQUIRE(a->cap == 0 || (a->workspace && a->workspace_bytes >= gssdf_raster2dgs_workspace_bytes(a->cap)), GSSDF_ENOMEM,
+                  "raster2dgs_fwd: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tw = cdiv(a->image_width, kTile), th = cdiv(a->image_height, kTile);
+    float4 *rec = reinterpret_cast<float4 *>(a->workspace);
+    if (a->cap > 0) {
+        pack_records_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(a->counts, a->ray_transforms, a->colors, a->opacities, a->normals,
+                                                              rec, a->visibilities, 1);
+        GSSDF_LAUNCH_OK("pack_records_kernel");
+    }
+    raster2dgs_fwd_kernel<<<a->C * tw * th, kRasterThreads, 0, st>>>(*a, rec, tw, th);
+    GSSDF_LAUNCH_OK("raster2dgs_fwd_kernel");
+    return GSSDF_OK;
+}
+
+extern "C" int gssdf_raster2dgs_bwd(const gssdf_raster2dgs_bwd_args *a, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "raster2dgs_bwd: null args");
+    int rc = check_raster_common("raster2dgs_bwd", a->C, a->image_width, a->image_height, a->tile_size, a->channels);
+    if (rc) return rc;
+    GSSDF_REQUIRE(a->v_render_distort == nullptr, GSSDF_EUNSUPPORTED,
+                  "raster2dgs_bwd: distortion-loss cotangent is outside the GS-SDF path (distloss=false)");
+    if (a->cap == 0) return GSSDF_OK;  // nothing to do (Bwd.cu:770-773)
+    GSSDF_REQUIRE(a->counts && a->offsets && a->flatten_ids && a->ray_transforms && a->colors && a->opacities && a->normals &&
+                      a->render_alphas && a->last_ids && a->median_ids && a->v_render_colors && a->v_render_depths &&
+                      a->v_render_alphas && a->v_render_normals && a->v_render_median,
+                  GSSDF_EINVAL, "raster2dgs_bwd: null input");
+    GSSDF_REQUIRE(a->v_ray_transforms && a->v_colors && a->v_opacities && a->v_normals, GSSDF_EINVAL, "raster2dgs_bwd: null output");
+    GSSDF_REQUIRE(a->workspace && a->workspace_bytes >= gssdf_raster2dgs_bwd_workspace_bytes(a->cap), GSSDF_ENOMEM,
+                  "raster2dgs_bwd: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tw = cdiv(a->image_width, kTile), th = cdiv(a->image_height, kTile);
+    float4 *rec = reinterpret_cast<float4 *>(a->workspace);
+    float4 *vrec = reinterpret_cast<float4 *>(reinterpret_cast<char *>(a->workspace) + align_up((size_t)a->cap * 64, 256));
+    pack_records_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(a->counts, a->ray_transforms, a->colors, a->opacities, a->normals, rec,
+                                                          reinterpret_cast<float *>(vrec), 16);
+    GSSDF_LAUNCH_OK("pack_records_kernel");
+    const size_t smem = 2 * sizeof(BwdStage);
+    if (a->v_means2d_abs) {
+        GSSDF_CUDA_OK(cudaMemsetAsync(a->v_means2d_abs, 0, (size_t)a->cap * 2 * sizeof(float), st));
+        GSSDF_CUDA_OK(cudaFuncSetAttribute(raster2dgs_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        raster2dgs_bwd_kernel<true><<<a->C * tw * th, kRasterThreads, smem, st>>>(*a, rec, reinterpret_cast<float *>(vrec), tw, th);
+    } else {
+        GSSDF_CUDA_OK(cudaFuncSetAttribute(raster2dgs_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        raster2dgs_bwd_kernel<false><<<a->C * tw * th, kRasterThreads, smem, st>>>(*a, rec, reinterpret_cast<float *>(vrec), tw, th);
+    }
+    GSSDF_LAUNCH_OK("raster2dgs_bwd_kernel");
+    raster_bwd_finalize_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, vrec);
+    GSSDF_LAUNCH_OK("raster_bwd_finalize_kernel");
+    return GSSDF_OK;
+}
+
+extern "C" int gssdf_render_post_fwd(const gssdf_render_post_fwd_args *a, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "render_post_fwd: null args");
+    GSSDF_REQUIRE(a->C > 0 && a->image_width > 0 && a->image_height > 0, GSSDF_EINVAL, "render_post_fwd: bad image size");
+    GSSDF_REQUIRE(a->viewmats && a->render_colors && a->render_depths && a->render_alphas && a->render_normals && a->out_colors &&
+                      a->out_normals,
+                  GSSDF_EINVAL, "render_post_fwd: null pointer");
+    const int64_t n = (int64_t)a->C * a->image_width * a->image_height;
+    render_post_fwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(*a);
+    GSSDF_LAUNCH_OK("render_post_fwd_kernel");
+    return GSSDF_OK;
+}
+
+extern "C" int gssdf_render_post_bwd(const gssdf_render_post_bwd_args *a, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "render_post_bwd: null args");
+    GSSDF_REQUIRE(a->C > 0 && a->image_width > 0 && a->image_height > 0, GSSDF_EINVAL, "render_post_bwd: bad image size");
+    GSSDF_REQUIRE(a->viewmats && a->render_depths && a->render_alphas && a->v_out_colors && a->v_out_normals && a->v_render_colors &&
+                      a->v_render_depths && a->v_render_alphas && a->v_render_normals,
+                  GSSDF_EINVAL, "render_post_bwd: null pointer");
+    const int64_t n = (int64_t)a->C * a->image_width * a->image_height;
+    render_post_bwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(*a);
+    GSSDF_LAUNCH_OK("render_post_bwd_kernel");
+    return GSSDF_OK;
+}

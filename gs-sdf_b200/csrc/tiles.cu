@@ -1,0 +1,282 @@
+// a5: tile intersection keys + sort + per-tile offsets (bit-exact target).
+//
+// Reference behaviour: gsplat::intersect_tile / intersect_offset
+//   GSF/csrc/Intersect.cpp:15-145, kernels GSF/csrc/IntersectTile.cu:24-115 (tile AABB, key
+//   layout :96-109), :209-255 (offsets), CUB radix sort :294-337.
+// The reference emits (key = cam|tile|depth_bits, value = packed index) per intersection in
+// packed-index order, radix-sorts all n_isects pairs over 42-48 key bits (6 global passes) and
+// derives per-tile offsets from the sorted keys, with two host syncs in between.
+//
+// B200-first method (same bits out, ~8x less HBM traffic, no host sync):
+//   1. tile_count   : per splat tile rect -> tiles_per_gauss + per-(camera,tile) histogram
+//   2. scan         : exclusive scan of the histogram == isect_offsets, total == n_isects
+//   3. tile_scatter : every intersection is written into its tile's bin as the unique 64-bit key
+//                     (depth_bits << 32 | packed index)
+//   4. tile_sort    : one CTA per tile sorts its bin in shared memory (all-ascending bitonic
+//                     network); since the key is unique, ascending order IS the reference order
+//                     (sorted by depth bits, ties in emission = packed-index order).
+#include "common.cuh"
+
+namespace gssdf {
+
+struct TileGeom {
+    int tile_size, tw, th, n_tiles;
+    uint32_t tile_n_bits;
+};
+
+// IntersectTile.cu:54-76. (uint32_t)floor(x) saturates on the GPU; negative -> 0.
+__device__ __forceinline__ bool tile_rect(const gssdf_tile_encode_args &a, const TileGeom &g, int idx, uint32_t &x0,
+                                          uint32_t &y0, uint32_t &x1, uint32_t &y1) {
+    const int2 rad = reinterpret_cast<const int2 *>(a.radii)[idx];
+    const float radius_x = (float)rad.x, radius_y = (float)rad.y;
+    if (radius_x <= 0 || radius_y <= 0) return false;
+    const float2 m = reinterpret_cast<const float2 *>(a.means2d)[idx];
+    const float ts = (float)g.tile_size;
+    const float trx = __fdiv_rn(radius_x, ts), try_ = __fdiv_rn(radius_y, ts);
+    const float tx = __fdiv_rn(m.x, ts), ty = __fdiv_rn(m.y, ts);
+    x0 = min(__float2uint_rz(floorf(tx - trx)), (uint32_t)g.tw);
+    y0 = min(__float2uint_rz(floorf(ty - try_)), (uint32_t)g.th);
+    x1 = min(__float2uint_rz(ceilf(tx + trx)), (uint32_t)g.tw);
+    y1 = min(__float2uint_rz(ceilf(ty + try_)), (uint32_t)g.th);
+    return true;
+}
+
+// Visit every tile of every splat's rect. Small rects are walked by their own thread; rects with
+// >= 32 tiles are walked cooperatively by the warp (a screen-filling splat touches ~8k tiles).
+template <typename F>
+__device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, int idx,
+                                              F &&f) {
+    const uint32_t w = has ? x1 - x0 : 0, h = has ? y1 - y0 : 0;
+    const uint32_t cnt = w * h;
+    const bool big = cnt >= 32;
+    if (has && !big) {
+        for (uint32_t y = y0; y < y1; ++y)
+            for (uint32_t x = x0; x < x1; ++x) f(idx, x, y);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, big);
+    const int lane = threadIdx.x & 31;
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+        const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bcnt = __shfl_sync(0xffffffffu, cnt, src);
+        const int bidx = __shfl_sync(0xffffffffu, idx, src);
+        for (uint32_t t = lane; t < bcnt; t += 32) f(bidx, bx0 + t % bw, by0 + t / bw);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist) {
+    const int nnz = a.counts->nnz;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = idx < nnz;
+    uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    const bool has = in && tile_rect(a, g, idx, x0, y0, x1, y1);
+    if (in && a.tiles_per_gauss) a.tiles_per_gauss[idx] = has ? (int32_t)((y1 - y0) * (x1 - x0)) : 0;
+    for_each_tile(has, x0, y0, x1, y1, idx, [&](int i, uint32_t x, uint32_t y) {
+        const int64_t cid = a.camera_ids ? a.camera_ids[i] : 0;
+        atomicAdd(hist + cid * g.n_tiles + y * g.tw + x, 1);
+    });
+}
+
+// exclusive scan of hist[n] -> offsets[n] (int32 output tensor) and bin_start[n+1]; hist is left
+// intact (the scatter pass counts it down). Single CTA.
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(const int32_t *__restrict__ hist, int32_t *__restrict__ offsets, int32_t *__restrict__ bin_start,
+                 int n, gssdf_counts *counts, int64_t isect_cap) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry, s_max;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_carry = 0; s_max = 0; }
+    __syncthreads();
+    int local_max = 0;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int v = i < n ? hist[i] : 0;
+        local_max = max(local_max, v);
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int incl = x + (warp > 0 ? s_warp[warp - 1] : 0) + s_carry;
+        if (i < n) { offsets[i] = incl - v; bin_start[i] = incl - v; }
+        __syncthreads();
+        if (tid == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    local_max = warp_max_i(local_max);
+    if (lane == 0) atomicMax(&s_max, local_max);
+    __syncthreads();
+    if (tid == 0) {
+        const int total = s_carry;
+        bin_start[n] = total;
+        counts->n_isects = (int32_t)min((int64_t)total, isect_cap);
+        counts->isect_overflow = (int64_t)total > isect_cap ? 1 : 0;
+        counts->max_tile_count = s_max;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tile_scatter_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist,
+                    const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys) {
+    const int nnz = a.counts->nnz;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = idx < nnz;
+    uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    const bool has = in && tile_rect(a, g, idx, x0, y0, x1, y1);
+    const int64_t cap = a.isect_cap;
+    for_each_tile(has, x0, y0, x1, y1, idx, [&](int i, uint32_t x, uint32_t y) {
+        const int64_t cid = a.camera_ids ? a.camera_ids[i] : 0;
+        const int64_t bin = cid * g.n_tiles + y * g.tw + x;
+        const int slot = atomicSub(hist + bin, 1) - 1;  // fills the bin back to front
+        const int64_t pos = (int64_t)bin_start[bin] + slot;
+        if (pos < cap)
+            keys[pos] = ((unsigned long long)__float_as_uint(a.depths[i]) << 32) | (unsigned long long)(uint32_t)i;
+    });
+}
+
+// All-ascending bitonic network over v[0..n) (virtual +inf padding beyond n): flip step then
+// half-cleaners. Works on shared or global memory; one CTA.
+template <int THREADS>
+__device__ __forceinline__ void bitonic_sort(unsigned long long *v, int n) {
+    int lP = 0;
+    while ((1 << lP) < n) ++lP;
+    const int half = (1 << lP) >> 1;
+    for (int lk = 1; lk <= lP; ++lk) {
+        const int k = 1 << lk, hk = k >> 1;
+        for (int p = threadIdx.x; p < half; p += THREADS) {  // flip
+            const int i = ((p >> (lk - 1)) << lk) | (p & (hk - 1));
+            const int l = i ^ (k - 1);
+            if (l < n) {
+                const unsigned long long a = v[i], b = v[l];
+                if (a > b) { v[i] = b; v[l] = a; }
+            }
+        }
+        __syncthreads();
+        for (int lj = lk - 2; lj >= 0; --lj) {
+            const int j = 1 << lj;
+            for (int p = threadIdx.x; p < half; p += THREADS) {
+                const int i = ((p >> lj) << (lj + 1)) | (p & (j - 1));
+                const int l = i + j;
+                if (l < n) {
+                    const unsigned long long a = v[i], b = v[l];
+                    if (a > b) { v[i] = b; v[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// One CTA per (camera, tile) bin with LO < n <= HI intersections (n > S only in the last tier:
+// sorted in place in global memory).
+template <int S, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+tile_sort_kernel(const TileGeom g, const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys,
+                 int lo, int hi, int64_t isect_cap, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
+    extern __shared__ __align__(16) unsigned long long s_keys[];
+    const int bin = blockIdx.x;
+    const int64_t rs = min((int64_t)bin_start[bin], isect_cap), re = min((int64_t)bin_start[bin + 1], isect_cap);
+    const int n = (int)(re - rs);
+    if (n <= lo || n > hi) return;
+    unsigned long long *v;
+    if (n <= S) {
+        for (int i = threadIdx.x; i < n; i += THREADS) s_keys[i] = keys[rs + i];
+        v = s_keys;
+    } else {
+        v = keys + rs;  // rare: bin larger than shared memory
+    }
+    __syncthreads();
+    bitonic_sort<THREADS>(v, n);
+    const int cid = bin / g.n_tiles, tile = bin % g.n_tiles;
+    const long long hi_bits = ((long long)cid << (32 + g.tile_n_bits)) | ((long long)tile << 32);
+    for (int i = threadIdx.x; i < n; i += THREADS) {
+        const unsigned long long k = v[i];
+        flatten_ids[rs + i] = (int32_t)(uint32_t)(k & 0xffffffffull);
+        if (isect_ids) isect_ids[rs + i] = hi_bits | (long long)(k >> 32);
+    }
+}
+
+}  // namespace gssdf
+
+using namespace gssdf;
+
+static TileGeom make_geom(int W, int H, int tile_size) {
+    TileGeom g;
+    g.tile_size = tile_size;
+    g.tw = (W + tile_size - 1) / tile_size;
+    g.th = (H + tile_size - 1) / tile_size;
+    g.n_tiles = g.tw * g.th;
+    uint32_t b = 0;  // floor(log2(n_tiles)) + 1 (IntersectTile.cu:151)
+    while ((1u << b) <= (uint32_t)g.n_tiles) ++b;
+    g.tile_n_bits = b;
+    return g;
+}
+
+extern "C" size_t gssdf_tile_encode_workspace_bytes(int32_t C, int32_t W, int32_t H, int32_t tile_size, int64_t isect_cap) {
+    if (tile_size <= 0) return 0;
+    const TileGeom g = make_geom(W, H, tile_size);
+    const size_t bins = (size_t)(C > 0 ? C : 1) * g.n_tiles;
+    return align_up(bins * 4, 256) + align_up((bins + 1) * 4, 256) + align_up((size_t)(isect_cap > 0 ? isect_cap : 1) * 8, 256);
+}
+
+extern "C" int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "tile_encode: null args");
+    GSSDF_REQUIRE(a->C > 0 && a->image_width > 0 && a->image_height > 0 && a->tile_size > 0, GSSDF_EINVAL,
+                  "tile_encode: n_cameras, image size and tile_size must be positive");
+    GSSDF_REQUIRE(a->counts && a->offsets, GSSDF_EINVAL, "tile_encode: counts and offsets are required");
+    const TileGeom g = make_geom(a->image_width, a->image_height, a->tile_size);
+    uint32_t cam_bits = 0;
+    while ((1u << cam_bits) <= (uint32_t)a->C) ++cam_bits;
+    GSSDF_REQUIRE(g.tile_n_bits + cam_bits <= 32, GSSDF_EINVAL, "tile_encode: tile_n_bits + cam_n_bits > 32");
+    const int bins = a->C * g.n_tiles;
+    GSSDF_REQUIRE(a->workspace && a->workspace_bytes >= gssdf_tile_encode_workspace_bytes(a->C, a->image_width,
+                                                                                         a->image_height, a->tile_size,
+                                                                                         a->isect_cap),
+                  GSSDF_ENOMEM, "tile_encode: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = reinterpret_cast<char *>(a->workspace);
+    int32_t *hist = reinterpret_cast<int32_t *>(ws);
+    ws += align_up((size_t)bins * 4, 256);
+    int32_t *bin_start = reinterpret_cast<int32_t *>(ws);
+    ws += align_up((size_t)(bins + 1) * 4, 256);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws);
+
+    GSSDF_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)bins * 4, st));
+    if (a->cap > 0) {
+        GSSDF_REQUIRE(a->means2d && a->radii && a->depths && a->flatten_ids, GSSDF_EINVAL, "tile_encode: null input/output");
+        tile_count_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist);
+        GSSDF_LAUNCH_OK("tile_count_kernel");
+    }
+    tile_scan_kernel<<<1, 1024, 0, st>>>(hist, a->offsets, bin_start, bins, a->counts, a->isect_cap);
+    GSSDF_LAUNCH_OK("tile_scan_kernel");
+    if (a->cap == 0 || a->isect_cap == 0) return GSSDF_OK;
+    tile_scatter_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist, bin_start, keys);
+    GSSDF_LAUNCH_OK("tile_scatter_kernel");
+
+    constexpr int S0 = 2048, S1 = 8192, S2 = 28672;
+    GSSDF_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<S1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1 * 8));
+    GSSDF_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<S2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2 * 8));
+    tile_sort_kernel<S0, 256><<<bins, 256, S0 * 8, st>>>(g, bin_start, keys, 0, S0, a->isect_cap, a->isect_ids, a->flatten_ids);
+    GSSDF_LAUNCH_OK("tile_sort_kernel<2048>");
+    tile_sort_kernel<S1, 512><<<bins, 512, S1 * 8, st>>>(g, bin_start, keys, S0, S1, a->isect_cap, a->isect_ids, a->flatten_ids);
+    GSSDF_LAUNCH_OK("tile_sort_kernel<8192>");
+    tile_sort_kernel<S2, 1024><<<bins, 1024, S2 * 8, st>>>(g, bin_start, keys, S1, 0x7fffffff, a->isect_cap, a->isect_ids,
+                                                          a->flatten_ids);
+    GSSDF_LAUNCH_OK("tile_sort_kernel<28672>");
+    return GSSDF_OK;
+}

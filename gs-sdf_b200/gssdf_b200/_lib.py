@@ -1,0 +1,101 @@
+"""ctypes binding of libgssdf_b200.so generated from include/gssdf_b200.h (the single source of truth).
+
+The library is the product: if it is missing or fails to load this module raises -- there is no
+CPU or PyTorch fallback anywhere in the package.
+"""
+import ctypes as C
+import os
+import re
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(_PKG))
+HEADER = os.path.join(ROOT, "include", "gssdf_b200.h")
+SO_PATH = os.path.join(os.path.dirname(_PKG), "libgssdf_b200.so")
+
+_SCALARS = {"int32_t": C.c_int32, "int64_t": C.c_int64, "uint32_t": C.c_uint32, "float": C.c_float,
+            "size_t": C.c_size_t, "int": C.c_int, "double": C.c_double}
+
+
+def _strip_comments(src):
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return re.sub(r"//[^\n]*", "", src)
+
+
+def parse_header(path=HEADER):
+    """Returns ({struct_name: [(field, ctype)]}, {func_name: (restype, n_args)})."""
+    src = _strip_comments(open(path).read())
+    structs = {}
+    for m in re.finditer(r"typedef\s+struct\s+(\w+)\s*\{(.*?)\}\s*(\w+)\s*;", src, flags=re.S):
+        name, body = m.group(3), m.group(2)
+        fields = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            decl = decl.replace("const ", "")
+            base, rest = decl.split(" ", 1)
+            for item in rest.split(","):
+                item = item.strip()
+                arr = re.match(r"(\w+)\[(\d+)\]$", item)
+                if item.startswith("*"):
+                    fields.append((item.lstrip("* "), C.c_void_p))
+                elif arr:
+                    fields.append((arr.group(1), _SCALARS[base] * int(arr.group(2))))
+                else:
+                    fields.append((item, _SCALARS[base]))
+        structs[name] = fields
+    funcs = {}
+    for m in re.finditer(r"^\s*(const char \*|int|size_t)\s*(gssdf_\w+)\s*\(([^)]*)\)\s*;", src, flags=re.M):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3)
+        funcs[name] = (ret, args)
+    return structs, funcs
+
+
+_STRUCT_FIELDS, FUNCS = parse_header()
+STRUCTS = {}
+for _n, _f in _STRUCT_FIELDS.items():
+    STRUCTS[_n] = type(_n, (C.Structure,), {"_fields_": _f})
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                f"{SO_PATH} not found: build it with `python gs-sdf_b200/build.py` (nvcc, sm_100a). "
+                "gssdf_b200 has no CPU/PyTorch fallback.")
+        L = C.CDLL(SO_PATH)
+        for name, (ret, _args) in FUNCS.items():
+            fn = getattr(L, name)  # raises AttributeError if a declared symbol is not exported
+            fn.restype = {"int": C.c_int, "size_t": C.c_size_t, "const char *": C.c_char_p}[ret]
+        _lib = L
+    return _lib
+
+
+class GssdfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gssdf_b200 error {code}: {msg}")
+        self.code = code
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().gssdf_last_error().decode()
+        if rc == -1:
+            raise ValueError(f"gssdf_b200: {msg}")  # reference: TORCH_CHECK / std::invalid_argument
+        raise GssdfError(rc, msg)
+
+
+def make_args(struct_name, **kw):
+    S = STRUCTS[struct_name]
+    a = S()
+    names = {f[0] for f in S._fields_}
+    for k, v in kw.items():
+        if k not in names:
+            raise KeyError(f"{struct_name} has no field {k}")
+        if hasattr(v, "data_ptr"):  # torch tensor
+            v = v.data_ptr() if v.numel() > 0 else (v.data_ptr() or None)
+        setattr(a, k, v)
+    return a

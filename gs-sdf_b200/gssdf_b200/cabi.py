@@ -1,0 +1,165 @@
+"""Thin functional layer: torch tensors (device memory + streams only) -> C ABI calls.
+
+One function per entry point of include/gssdf_b200.h. Nothing here computes: every function fills an
+args struct with raw device pointers and calls libgssdf_b200.so on torch's current CUDA stream.
+"""
+import torch
+
+from . import _lib
+from ._lib import check, lib, make_args
+
+COUNTS_INTS = 8  # sizeof(gssdf_counts) / 4
+NNZ, N_ISECTS, NNZ_OVERFLOW, ISECT_OVERFLOW, MAX_TILE = 0, 1, 2, 3, 4
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, dtype, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError(f"gssdf_b200: {name} must be a CUDA tensor")  # CHECK_CUDA (GSF/include/Common.h:12)
+    if not t.is_contiguous():
+        raise ValueError(f"gssdf_b200: {name} must be contiguous")  # CHECK_CONTIGUOUS (:13)
+    if t.dtype != dtype:
+        raise ValueError(f"gssdf_b200: {name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def new_counts(device, nnz=0, n_isects=0):
+    c = torch.zeros(COUNTS_INTS, dtype=torch.int32, device=device)
+    if nnz or n_isects:
+        c[:2] = torch.tensor([nnz, n_isects], dtype=torch.int32)
+    return c
+
+
+class Workspace:
+    """Grow-only device scratch buffer (the library itself never allocates)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    def get(self, nbytes):
+        nbytes = max(int(nbytes), 256)
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+def project2dgs_fwd(means, quats, scales, viewmats, Ks, W, H, near, far, radius_clip, randns, cap, out, counts, ws,
+                    opacities=None):
+    """out: dict of capacity-sized tensors (camera_ids, gaussian_ids, radii, means2d, depths, ray_transforms,
+    normals, samples, sample_weights, indptr)."""
+    N, Cn = means.shape[0], viewmats.shape[0]
+    f32 = torch.float32
+    for n_, t in (("means", means), ("quats", quats), ("scales", scales), ("viewmats", viewmats), ("Ks", Ks)):
+        _req(t, f32, n_)
+    need = lib().gssdf_project2dgs_workspace_bytes(N, Cn)
+    w = ws.get(need)
+    a = make_args("gssdf_project2dgs_fwd_args", N=N, C=Cn, means=means, quats=quats, scales=scales, viewmats=viewmats,
+                  Ks=Ks, image_width=W, image_height=H, near_plane=near, far_plane=far, radius_clip=radius_clip,
+                  randns=_req(randns, f32, "randns"), opacities=_req(opacities, f32, "opacities"),
+                  pt_opacities=out.get("pt_opacities") if opacities is not None else None, cap=cap,
+                  camera_ids=out["camera_ids"],
+                  gaussian_ids=out["gaussian_ids"], radii=out["radii"], means2d=out["means2d"], depths=out["depths"],
+                  ray_transforms=out["ray_transforms"], normals=out["normals"], samples=out.get("samples"),
+                  sample_weights=out.get("sample_weights"), indptr=out.get("indptr"), counts=counts, workspace=w,
+                  workspace_bytes=w.numel())
+    check(lib().gssdf_project2dgs_fwd(_lib.C.byref(a), _stream()))
+
+
+def project2dgs_bwd(means, quats, scales, viewmats, Ks, W, H, cap, counts, camera_ids, gaussian_ids, ray_transforms,
+                    randns, v_means2d, v_depths, v_ray_transforms, v_normals, v_samples, v_means, v_quats, v_scales,
+                    v_pt_opacities=None, v_opacities=None):
+    a = make_args("gssdf_project2dgs_bwd_args", N=means.shape[0], C=viewmats.shape[0], means=means, quats=quats,
+                  scales=scales, viewmats=viewmats, Ks=Ks, image_width=W, image_height=H, cap=cap, counts=counts,
+                  camera_ids=camera_ids, gaussian_ids=gaussian_ids, ray_transforms=ray_transforms, randns=randns,
+                  v_means2d=v_means2d, v_depths=v_depths, v_ray_transforms=v_ray_transforms, v_normals=v_normals,
+                  v_samples=v_samples, v_means=v_means, v_quats=v_quats, v_scales=v_scales,
+                  v_pt_opacities=v_pt_opacities, v_opacities=v_opacities)
+    check(lib().gssdf_project2dgs_bwd(_lib.C.byref(a), _stream()))
+
+
+def view_colors_fwd(viewmats, means, sh, sh_degree, cap, counts, camera_ids, gaussian_ids, radii, colors):
+    a = make_args("gssdf_view_colors_fwd_args", N=means.shape[0], C=viewmats.shape[0], K=sh.shape[1],
+                  sh_degree=sh_degree, viewmats=viewmats, means=means, sh=sh, cap=cap, counts=counts,
+                  camera_ids=camera_ids, gaussian_ids=gaussian_ids, radii=radii, colors=colors)
+    check(lib().gssdf_view_colors_fwd(_lib.C.byref(a), _stream()))
+
+
+def view_colors_bwd(viewmats, means, sh, sh_degree, cap, counts, camera_ids, gaussian_ids, radii, colors, v_colors,
+                    v_sh, v_means):
+    a = make_args("gssdf_view_colors_bwd_args", N=means.shape[0], C=viewmats.shape[0], K=sh.shape[1],
+                  sh_degree=sh_degree, viewmats=viewmats, means=means, sh=sh, cap=cap, counts=counts,
+                  camera_ids=camera_ids, gaussian_ids=gaussian_ids, radii=radii, colors=colors, v_colors=v_colors,
+                  v_sh=v_sh, v_means=v_means)
+    check(lib().gssdf_view_colors_bwd(_lib.C.byref(a), _stream()))
+
+
+def tile_encode(Cn, W, H, tile_size, cap, counts, means2d, radii, depths, camera_ids, isect_cap, tiles_per_gauss,
+                isect_ids, flatten_ids, offsets, ws):
+    need = lib().gssdf_tile_encode_workspace_bytes(Cn, W, H, tile_size, isect_cap)
+    w = ws.get(need)
+    a = make_args("gssdf_tile_encode_args", C=Cn, image_width=W, image_height=H, tile_size=tile_size, cap=cap,
+                  counts=counts, means2d=means2d, radii=radii, depths=depths, camera_ids=camera_ids, isect_cap=isect_cap,
+                  tiles_per_gauss=tiles_per_gauss, isect_ids=isect_ids, flatten_ids=flatten_ids, offsets=offsets,
+                  workspace=w, workspace_bytes=w.numel())
+    check(lib().gssdf_tile_encode(_lib.C.byref(a), _stream()))
+
+
+def raster2dgs_fwd(Cn, W, H, tile_size, channels, cap, counts, means2d, ray_transforms, colors, opacities, normals,
+                   backgrounds, offsets, flatten_ids, out, ws):
+    need = lib().gssdf_raster2dgs_workspace_bytes(cap)
+    w = ws.get(need)
+    a = make_args("gssdf_raster2dgs_fwd_args", C=Cn, image_width=W, image_height=H, tile_size=tile_size,
+                  channels=channels, cap=cap, counts=counts, means2d=means2d, ray_transforms=ray_transforms,
+                  colors=colors, opacities=opacities, normals=normals, backgrounds=backgrounds, offsets=offsets,
+                  flatten_ids=flatten_ids, render_colors=out["render_colors"], render_depths=out["render_depths"],
+                  render_alphas=out["render_alphas"], render_normals=out["render_normals"],
+                  render_distort=out["render_distort"], render_median=out["render_median"], render_Ts=out["render_Ts"],
+                  last_ids=out["last_ids"], median_ids=out["median_ids"], visibilities=out["visibilities"], workspace=w,
+                  workspace_bytes=w.numel())
+    check(lib().gssdf_raster2dgs_fwd(_lib.C.byref(a), _stream()))
+
+
+def raster2dgs_bwd(Cn, W, H, tile_size, channels, cap, counts, means2d, ray_transforms, colors, opacities, normals,
+                   backgrounds, offsets, flatten_ids, render_alphas, render_Ts, last_ids, median_ids, v_render_colors,
+                   v_render_depths, v_render_alphas, v_render_normals, v_render_median, out, ws, v_render_distort=None):
+    need = lib().gssdf_raster2dgs_bwd_workspace_bytes(cap)
+    w = ws.get(need)
+    a = make_args("gssdf_raster2dgs_bwd_args", C=Cn, image_width=W, image_height=H, tile_size=tile_size,
+                  channels=channels, cap=cap, counts=counts, means2d=means2d, ray_transforms=ray_transforms,
+                  colors=colors, opacities=opacities, normals=normals, backgrounds=backgrounds, offsets=offsets,
+                  flatten_ids=flatten_ids, render_alphas=render_alphas, render_Ts=render_Ts, last_ids=last_ids,
+                  median_ids=median_ids, v_render_colors=v_render_colors, v_render_depths=v_render_depths,
+                  v_render_alphas=v_render_alphas, v_render_normals=v_render_normals, v_render_distort=v_render_distort,
+                  v_render_median=v_render_median, v_means2d=out.get("v_means2d"), v_means2d_abs=out.get("v_means2d_abs"),
+                  v_ray_transforms=out["v_ray_transforms"], v_colors=out["v_colors"], v_opacities=out["v_opacities"],
+                  v_normals=out["v_normals"], v_densify=out.get("v_densify"), workspace=w, workspace_bytes=w.numel())
+    check(lib().gssdf_raster2dgs_bwd(_lib.C.byref(a), _stream()))
+
+
+def render_post_fwd(Cn, W, H, viewmats, render_colors, render_depths, render_alphas, render_normals, out_colors,
+                    out_normals):
+    a = make_args("gssdf_render_post_fwd_args", C=Cn, image_width=W, image_height=H, viewmats=viewmats,
+                  render_colors=render_colors, render_depths=render_depths, render_alphas=render_alphas,
+                  render_normals=render_normals, out_colors=out_colors, out_normals=out_normals)
+    check(lib().gssdf_render_post_fwd(_lib.C.byref(a), _stream()))
+
+
+def render_post_bwd(Cn, W, H, viewmats, render_depths, render_alphas, v_out_colors, v_out_normals, v_alphas_in,
+                    v_render_colors, v_render_depths, v_render_alphas, v_render_normals):
+    a = make_args("gssdf_render_post_bwd_args", C=Cn, image_width=W, image_height=H, viewmats=viewmats,
+                  render_depths=render_depths, render_alphas=render_alphas, v_out_colors=v_out_colors,
+                  v_out_normals=v_out_normals, v_alphas_in=v_alphas_in, v_render_colors=v_render_colors,
+                  v_render_depths=v_render_depths, v_render_alphas=v_render_alphas, v_render_normals=v_render_normals)
+    check(lib().gssdf_render_post_bwd(_lib.C.byref(a), _stream()))
+
+
+def l1_loss(Cn, W, H, out_colors, gt, w_rgb, w_depth, loss_out, v_out_colors):
+    a = make_args("gssdf_l1_loss_args", C=Cn, image_width=W, image_height=H, out_colors=out_colors, gt=gt, w_rgb=w_rgb,
+                  w_depth=w_depth, loss_out=loss_out, v_out_colors=v_out_colors)
+    check(lib().gssdf_l1_loss(_lib.C.byref(a), _stream()))

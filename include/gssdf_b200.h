@@ -1,0 +1,313 @@
+/*
+ * gssdf_b200 -- C ABI of the B200-native GS-SDF hot path (libgssdf_b200.so).
+ *
+ * Every entry point replaces one host function of the reference's gsplat fork / tcnn binding
+ * (the functions the reference's libtorch wrappers `gsplat_cpp` and `tcnn_binding` call) and is
+ * what a reference-side binding would bind instead. Reference paths are relative to
+ * /root/reference; GSF = submodules/gsplat_cpp/submodules/gsplat/gsplat/cuda,
+ * GSC = submodules/gsplat_cpp/gsplat_cpp, TB = submodules/tcnn_binding/tcnn_binding.
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers unless named host_*; plain C types only (no torch types);
+ *  - inputs are borrowed for the duration of the call on `stream`; outputs are caller-allocated
+ *    (the reference's host functions at::empty/zeros them: GSF/csrc/Projection.cpp:720-729,
+ *    GSF/csrc/Rasterization.cpp:360-382);
+ *  - data-dependent sizes (nnz visible splats, n_isects tile intersections) never force a host
+ *    sync: the caller passes a capacity, the library writes the true count to a device counter
+ *    (`gssdf_counts`) and truncates writes at the capacity; later stages read the counter on the
+ *    device. The reference blocks the host three times per render instead
+ *    (Projection.cpp:714, Intersect.cpp:78, GSC/rasterize_to_pixels.cpp:252);
+ *  - every function returns GSSDF_OK (0) or a negative GSSDF_E* code; gssdf_last_error() gives a
+ *    thread-local message. The libtorch shim maps codes back to c10::Error / std::invalid_argument
+ *    like the reference's TORCH_CHECK / CHECK_INPUT (GSF/include/Common.h:12-17);
+ *  - empty inputs (N==0, nnz==0, n_isects==0) are legal no-ops
+ *    (GSF/csrc/Projection2DGSPacked.cu:258-261, RasterizeToPixels2DGSBwd.cu:770-773);
+ *  - no allocation and no global mutable state inside the library except a thread-local error
+ *    string: re-entrant from any thread, any stream, any device (the current device is honoured).
+ */
+#ifndef GSSDF_B200_H
+#define GSSDF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *gssdf_stream_t; /* == cudaStream_t */
+
+enum {
+    GSSDF_OK = 0,
+    GSSDF_EINVAL = -1,       /* bad argument (null pointer, bad shape, unsupported channel count) */
+    GSSDF_ECUDA = -2,        /* a CUDA runtime call / kernel launch failed */
+    GSSDF_EUNSUPPORTED = -3, /* feature of the reference op outside the GS-SDF path */
+    GSSDF_ENOMEM = -4        /* workspace too small */
+};
+
+const char *gssdf_last_error(void);
+/* "gssdf_b200 <ver> sm_100a" */
+const char *gssdf_version(void);
+
+/* Device-side counters shared by the stages of one render. Zeroed by gssdf_project2dgs_fwd. */
+typedef struct gssdf_counts {
+    int32_t nnz;            /* visible (camera, splat) pairs found by the projection            */
+    int32_t n_isects;       /* tile intersections found by tile_encode                          */
+    int32_t nnz_overflow;   /* 1 if nnz exceeded the capacity given to project2dgs_fwd          */
+    int32_t isect_overflow; /* 1 if n_isects exceeded the capacity given to tile_encode         */
+    int32_t max_tile_count; /* largest number of intersections in one tile (diagnostic)        */
+    int32_t reserved[3];
+} gssdf_counts;
+
+/* ------------------------------------------------------------------------------------------
+ * a2  projection forward.  Replaces gsplat::projection_2dgs_packed_fwd
+ *     (GSF/csrc/Projection.cpp:654-774, kernel GSF/csrc/Projection2DGSPacked.cu:18-217) as
+ *     called by FullyFusedProjectionPacked2DGS::forward (GSC/fully_fused_projection.cpp:171-197).
+ *     randns[cap,2] ~ N(0,1) is an INPUT indexed by packed index (the reference draws it on the
+ *     host after its first sync, Projection.cpp:728); sample_weights = exp(-|randn|^2/2)
+ *     (GSC/fully_fused_projection.cpp:193) is produced here too.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gssdf_project2dgs_fwd_args {
+    int32_t N, C;
+    const float *means;    /* [N,3] */
+    const float *quats;    /* [N,4] (w,x,y,z) */
+    const float *scales;   /* [N,3] */
+    const float *viewmats; /* [C,4,4] row-major world->camera */
+    const float *Ks;       /* [C,3,3] */
+    int32_t image_width, image_height;
+    float near_plane, far_plane, radius_clip;
+    const float *randns; /* [cap,2] or NULL (=> samples = means, weights = 1) */
+    const float *opacities; /* [N] or NULL: fuses `opacities.index({gaussian_ids})` (neural_gaussian.cpp:193) */
+    int32_t cap;         /* capacity (rows) of every packed output; C*N always suffices */
+    /* packed outputs, rows [0,nnz) valid, order (camera, splat) ascending like the reference */
+    int64_t *camera_ids;    /* [cap] */
+    int64_t *gaussian_ids;  /* [cap] */
+    int32_t *radii;         /* [cap,2] */
+    float *means2d;         /* [cap,2] */
+    float *depths;          /* [cap] */
+    float *ray_transforms;  /* [cap,3,3] */
+    float *normals;         /* [cap,3] */
+    float *samples;         /* [cap,3] or NULL */
+    float *sample_weights;  /* [cap,1] or NULL */
+    float *pt_opacities;    /* [cap] or NULL (requires opacities) */
+    int32_t *indptr;        /* [C+1] or NULL */
+    gssdf_counts *counts;   /* device; zeroed then counts->nnz (+overflow flag) written */
+    void *workspace;        /* device scratch, >= gssdf_project2dgs_workspace_bytes(N, C) */
+    size_t workspace_bytes;
+} gssdf_project2dgs_fwd_args;
+size_t gssdf_project2dgs_workspace_bytes(int32_t N, int32_t C);
+int gssdf_project2dgs_fwd(const gssdf_project2dgs_fwd_args *a, gssdf_stream_t stream);
+
+/* a3  projection backward.  Replaces gsplat::projection_2dgs_packed_bwd
+ *     (Projection.cpp:776-865, kernel Projection2DGSPacked.cu:298-501, VJP Projection2DGS.cuh:10-90),
+ *     dense layout (sparse_grad=false), no v_viewmats (GS-SDF poses carry no grad).
+ *     v_* outputs [N,*] are ACCUMULATED INTO: the caller zero-fills them (the reference does,
+ *     Projection.cpp:828-830) or passes live .grad buffers. Any v_* input may be NULL (= zeros). */
+typedef struct gssdf_project2dgs_bwd_args {
+    int32_t N, C;
+    const float *means, *quats, *scales, *viewmats, *Ks;
+    int32_t image_width, image_height;
+    int32_t cap;                  /* rows allocated in the packed arrays */
+    const gssdf_counts *counts;   /* device: nnz */
+    const int64_t *camera_ids, *gaussian_ids;
+    const float *ray_transforms;  /* [cap,3,3] */
+    const float *randns;          /* [cap,2] or NULL */
+    const float *v_means2d;       /* [cap,2] */
+    const float *v_depths;        /* [cap] */
+    const float *v_ray_transforms;/* [cap,3,3] */
+    const float *v_normals;       /* [cap,3] */
+    const float *v_samples;       /* [cap,3] */
+    const float *v_pt_opacities;  /* [cap] or NULL: backward of the fused opacity gather */
+    float *v_opacities;           /* [N] += (required iff v_pt_opacities) */
+    float *v_means;               /* [N,3] += */
+    float *v_quats;               /* [N,4] += */
+    float *v_scales;              /* [N,3] += (z component untouched, like the reference) */
+} gssdf_project2dgs_bwd_args;
+int gssdf_project2dgs_bwd(const gssdf_project2dgs_bwd_args *a, gssdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a4  view-dependent colour.  Replaces gsplat_cpp::get_view_colors (GSC/rendering.cpp:11-47):
+ *     dirs = means[gid] - cam_centre[cid]; SH (gsplat::spherical_harmonics_fwd,
+ *     GSF/csrc/SphericalHarmonicsCUDA.cu:374-399) with mask min(radii)>0; clamp_min(c+0.5, 0).
+ *     The [nnz,K,3] gathers the reference materialises are fused away.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gssdf_view_colors_fwd_args {
+    int32_t N, C, K;        /* K = SH bases stored per splat */
+    int32_t sh_degree;      /* degree to evaluate, (sh_degree+1)^2 <= K, <= 4 */
+    const float *viewmats;  /* [C,4,4] */
+    const float *means;     /* [N,3] */
+    const float *sh;        /* [N,K,3] */
+    int32_t cap;
+    const gssdf_counts *counts;
+    const int64_t *camera_ids, *gaussian_ids; /* [cap] */
+    const int32_t *radii;   /* [cap,2] */
+    float *colors;          /* [cap,3] */
+} gssdf_view_colors_fwd_args;
+int gssdf_view_colors_fwd(const gssdf_view_colors_fwd_args *a, gssdf_stream_t stream);
+
+/* a4 backward: v_colors[cap,3] -> v_sh[N,K,3] += , v_means[N,3] += (through dirs).
+ * Replaces SphericalHarmonics::backward (GSC/spherical_harmonics.hpp:24-45,
+ * SphericalHarmonicsCUDA.cu:448-485) + the ATen clamp/index backward around it. */
+typedef struct gssdf_view_colors_bwd_args {
+    int32_t N, C, K, sh_degree;
+    const float *viewmats, *means, *sh;
+    int32_t cap;
+    const gssdf_counts *counts;
+    const int64_t *camera_ids, *gaussian_ids;
+    const int32_t *radii;
+    const float *colors;    /* [cap,3] forward output (clamp mask) */
+    const float *v_colors;  /* [cap,3] */
+    float *v_sh;            /* [N,K,3] += */
+    float *v_means;         /* [N,3] += or NULL */
+} gssdf_view_colors_bwd_args;
+int gssdf_view_colors_bwd(const gssdf_view_colors_bwd_args *a, gssdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a5  tile keys + sort + offsets.  Replaces gsplat_cpp::tile_encode (GSC/rendering.cpp:49-63) =
+ *     gsplat::intersect_tile (GSF/csrc/Intersect.cpp:15-127; kernels IntersectTile.cu:24-115;
+ *     CUB radix sort IntersectTile.cu:294-337) + gsplat::intersect_offset (Intersect.cpp:129-145,
+ *     IntersectTile.cu:209-255).  Outputs are BIT-EXACT with the reference:
+ *       isect_ids[i]  = cid << (32+tile_n_bits) | tile_id << 32 | float_bits(depth)  (sorted)
+ *       flatten_ids[i]= packed splat index, ties in emission order
+ *       offsets[c,ty,tx] = first i of that tile (== n_isects for trailing empty tiles)
+ *     Method (B200-first, no 6-pass global radix sort): per-tile histogram -> scan (= offsets) ->
+ *     binned scatter -> per-tile shared-memory sort of the unique key (depth_bits, packed index).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gssdf_tile_encode_args {
+    int32_t C;
+    int32_t image_width, image_height, tile_size;
+    int32_t cap;                 /* rows of the packed arrays */
+    gssdf_counts *counts;        /* reads nnz, writes n_isects / isect_overflow / max_tile_count */
+    const float *means2d;        /* [cap,2] */
+    const int32_t *radii;        /* [cap,2] */
+    const float *depths;         /* [cap] */
+    const int64_t *camera_ids;   /* [cap] */
+    int64_t isect_cap;           /* capacity of isect_ids / flatten_ids */
+    int32_t *tiles_per_gauss;    /* [cap] or NULL */
+    int64_t *isect_ids;          /* [isect_cap] or NULL (the raster stages do not need it) */
+    int32_t *flatten_ids;        /* [isect_cap] */
+    int32_t *offsets;            /* [C, tile_h, tile_w] */
+    void *workspace;             /* >= gssdf_tile_encode_workspace_bytes(...) */
+    size_t workspace_bytes;
+} gssdf_tile_encode_args;
+size_t gssdf_tile_encode_workspace_bytes(int32_t C, int32_t image_width, int32_t image_height,
+                                         int32_t tile_size, int64_t isect_cap);
+int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a6  rasterise forward.  Replaces gsplat::rasterize_to_pixels_2dgs_fwd
+ *     (GSF/csrc/Rasterization.cpp:324-452, kernel RasterizeToPixels2DGSFwd.cu:19-473), packed,
+ *     3 colour channels (GS-SDF renders RGB; other CDIM -> GSSDF_EUNSUPPORTED), masks == NULL.
+ *     visibilities is zero-filled by this call. render_Ts holds (M1,M2) per pixel at [pix*2]
+ *     (the reference's [pix],[pix+1] indexing, Fwd.cu:450-451, races between neighbours).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gssdf_raster2dgs_fwd_args {
+    int32_t C, image_width, image_height, tile_size;
+    int32_t channels;            /* must be 3 */
+    int32_t cap;
+    const gssdf_counts *counts;  /* nnz, n_isects */
+    const float *means2d;        /* [cap,2] (unused by the 2DGS kernel; kept for ABI parity) */
+    const float *ray_transforms; /* [cap,3,3] */
+    const float *colors;         /* [cap,3] */
+    const float *opacities;      /* [cap] */
+    const float *normals;        /* [cap,3] */
+    const float *backgrounds;    /* [C,3] or NULL */
+    const int32_t *offsets;      /* [C,tile_h,tile_w] */
+    const int32_t *flatten_ids;  /* [n_isects] */
+    float *render_colors;        /* [C,H,W,3] */
+    float *render_depths;        /* [C,H,W,1] sum vis*depth (NOT divided by alpha) */
+    float *render_alphas;        /* [C,H,W,1] */
+    float *render_normals;       /* [C,H,W,3] */
+    float *render_distort;       /* [C,H,W,1] */
+    float *render_median;        /* [C,H,W,1] */
+    float *render_Ts;            /* [C,H,W,2] saved for backward */
+    int32_t *last_ids;           /* [C,H,W]   saved for backward */
+    int32_t *median_ids;         /* [C,H,W]   saved for backward */
+    float *visibilities;         /* [cap,1] */
+    void *workspace;             /* >= gssdf_raster2dgs_workspace_bytes(cap) : packed 64-B records */
+    size_t workspace_bytes;
+} gssdf_raster2dgs_fwd_args;
+size_t gssdf_raster2dgs_workspace_bytes(int32_t cap);
+int gssdf_raster2dgs_fwd(const gssdf_raster2dgs_fwd_args *a, gssdf_stream_t stream);
+
+/* a7  rasterise backward.  Replaces gsplat::rasterize_to_pixels_2dgs_bwd
+ *     (Rasterization.cpp:462-612, kernel RasterizeToPixels2DGSBwd.cu:16-709).
+ *     Outputs [cap,*] are OVERWRITTEN for rows [0,nnz) (the reference zero-inits then atomically
+ *     accumulates). v_means2d is identically zero on this path (Bwd.cu:441,686-688).
+ *     v_densify[g] = (v_ray_transforms[g][0][2], v_ray_transforms[g][1][2]) * ray_transforms[g][2][2]
+ *     computed AFTER the accumulation (the reference reads the partially accumulated value
+ *     non-atomically, Bwd.cu:699-706). v_render_distort must be NULL (GS-SDF: distloss=false). */
+typedef struct gssdf_raster2dgs_bwd_args {
+    int32_t C, image_width, image_height, tile_size, channels, cap;
+    const gssdf_counts *counts;
+    const float *means2d, *ray_transforms, *colors, *opacities, *normals, *backgrounds;
+    const int32_t *offsets, *flatten_ids;
+    const float *render_alphas;  /* [C,H,W,1] */
+    const float *render_Ts;      /* [C,H,W,2] */
+    const int32_t *last_ids, *median_ids;
+    const float *v_render_colors;  /* [C,H,W,3] */
+    const float *v_render_depths;  /* [C,H,W,1] */
+    const float *v_render_alphas;  /* [C,H,W,1] */
+    const float *v_render_normals; /* [C,H,W,3] */
+    const float *v_render_distort; /* must be NULL */
+    const float *v_render_median;  /* [C,H,W,1] */
+    float *v_means2d;         /* [cap,2] (zeros) or NULL */
+    float *v_means2d_abs;     /* [cap,2] or NULL: sum over (tile quadrant, splat) of |sum_px dL/dM[.][2]| * M[2][2] */
+    float *v_ray_transforms;  /* [cap,3,3] */
+    float *v_colors;          /* [cap,3] */
+    float *v_opacities;       /* [cap] */
+    float *v_normals;         /* [cap,3] */
+    float *v_densify;         /* [cap,2] */
+    void *workspace;          /* >= gssdf_raster2dgs_bwd_workspace_bytes(cap) */
+    size_t workspace_bytes;
+} gssdf_raster2dgs_bwd_args;
+size_t gssdf_raster2dgs_bwd_workspace_bytes(int32_t cap);
+int gssdf_raster2dgs_bwd(const gssdf_raster2dgs_bwd_args *a, gssdf_stream_t stream);
+
+/* a8  image post-ops of rasterization_2dgs_sdf (include/neural_gaussian/neural_gaussian.cpp:229-240):
+ *     expected depth = nan_to_num(D / alpha); out_colors = cat(rgb, ED); normals -> world
+ *     (n_w = n_c * R_c2w^T). One fused pass instead of ~5 ATen kernels; backward likewise. */
+typedef struct gssdf_render_post_fwd_args {
+    int32_t C, image_width, image_height;
+    const float *viewmats;       /* [C,4,4] */
+    const float *render_colors;  /* [C,H,W,3] */
+    const float *render_depths;  /* [C,H,W,1] */
+    const float *render_alphas;  /* [C,H,W,1] */
+    const float *render_normals; /* [C,H,W,3] camera space */
+    float *out_colors;           /* [C,H,W,4] rgb + expected depth */
+    float *out_normals;          /* [C,H,W,3] world space */
+} gssdf_render_post_fwd_args;
+int gssdf_render_post_fwd(const gssdf_render_post_fwd_args *a, gssdf_stream_t stream);
+
+typedef struct gssdf_render_post_bwd_args {
+    int32_t C, image_width, image_height;
+    const float *viewmats;
+    const float *render_depths, *render_alphas;
+    const float *v_out_colors;   /* [C,H,W,4] */
+    const float *v_out_normals;  /* [C,H,W,3] */
+    const float *v_alphas_in;    /* [C,H,W,1] direct cotangent of alpha or NULL */
+    float *v_render_colors;      /* [C,H,W,3] */
+    float *v_render_depths;      /* [C,H,W,1] */
+    float *v_render_alphas;      /* [C,H,W,1] */
+    float *v_render_normals;     /* [C,H,W,3] */
+} gssdf_render_post_bwd_args;
+int gssdf_render_post_bwd(const gssdf_render_post_bwd_args *a, gssdf_stream_t stream);
+
+/* f-1 (minimal)  photometric + depth L1 loss on the post-processed render and its cotangent:
+ *     loss = w_rgb * mean|rgb - gt_rgb| + w_depth * mean|ED - gt_depth|   (loss::rgb_loss,
+ *     include/optimizer/loss.cpp:22-30; L1 on depth as in neural_mapping.cpp:243-266's depth terms).
+ *     loss_out[0] += loss (device float, caller zeroes); v_out_colors[C,H,W,4] is overwritten. */
+typedef struct gssdf_l1_loss_args {
+    int32_t C, image_width, image_height;
+    const float *out_colors; /* [C,H,W,4] */
+    const float *gt;         /* [C,H,W,4] */
+    float w_rgb, w_depth;
+    float *loss_out;         /* device float[1], += */
+    float *v_out_colors;     /* [C,H,W,4] */
+} gssdf_l1_loss_args;
+int gssdf_l1_loss(const gssdf_l1_loss_args *a, gssdf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSSDF_B200_H */

@@ -1,0 +1,205 @@
+"""ctypes/numpy front-end of liboracle (TEST INFRASTRUCTURE ONLY).
+
+Each function mirrors one reference op of the splat path and cites it in oracle/splat_oracle.c /
+splat_oracle_impl.inc. `prec` selects the fp32 restatement ("f32") or the fp64 arbiter ("f64").
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libgssdf_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("splat_oracle.c", "splat_oracle_impl.inc", "sdf_oracle.c", "Makefile")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s))
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libgssdf_oracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = C.CDLL(so)
+        _LIB.oracle_project2dgs_fwd_f32.restype = C.c_int64
+        _LIB.oracle_project2dgs_fwd_f64.restype = C.c_int64
+        _LIB.oracle_isect_tiles.restype = C.c_int64
+        _LIB.oracle_tile_n_bits.restype = C.c_uint32
+    return _LIB
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "oracle buffers must be contiguous"
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _acc(prec):
+    return np.float32 if prec == "f32" else np.float64
+
+
+def project2dgs_fwd(means, quats, scales, viewmats, Ks, W, H, near=0.01, far=1e10, radius_clip=0.0,
+                    randns=None, prec="f32"):
+    """gsplat::projection_2dgs_packed_fwd (Projection.cpp:654-774)."""
+    means, quats, scales, viewmats, Ks = map(_f32, (means, quats, scales, viewmats, Ks))
+    N, Cn = means.shape[0], viewmats.shape[0]
+    cap = N * Cn
+    randns = _f32(randns) if randns is not None else np.zeros((cap, 2), np.float32)
+    o = dict(camera_ids=np.zeros(cap, np.int64), gaussian_ids=np.zeros(cap, np.int64),
+             radii=np.zeros((cap, 2), np.int32), means2d=np.zeros((cap, 2), np.float32),
+             depths=np.zeros(cap, np.float32), ray_transforms=np.zeros((cap, 3, 3), np.float32),
+             normals=np.zeros((cap, 3), np.float32), samples=np.zeros((cap, 3), np.float32),
+             indptr=np.zeros(Cn + 1, np.int32))
+    fn = getattr(lib(), "oracle_project2dgs_fwd_" + prec)
+    nnz = fn(C.c_int64(N), C.c_int64(Cn), _p(means), _p(quats), _p(scales), _p(viewmats), _p(Ks),
+             C.c_int(W), C.c_int(H), C.c_float(near), C.c_float(far), C.c_float(radius_clip),
+             _p(randns), C.c_int64(cap), _p(o["camera_ids"]), _p(o["gaussian_ids"]), _p(o["radii"]),
+             _p(o["means2d"]), _p(o["depths"]), _p(o["ray_transforms"]), _p(o["normals"]),
+             _p(o["samples"]), _p(o["indptr"]))
+    for k in list(o):
+        if k != "indptr":
+            o[k] = o[k][:nnz].copy()
+    o["randns"] = randns[:nnz].copy()
+    o["sample_weights"] = np.exp(-0.5 * (o["randns"].astype(np.float64) ** 2).sum(-1, keepdims=True)).astype(np.float32)
+    o["nnz"] = int(nnz)
+    return o
+
+
+def project2dgs_bwd(means, quats, scales, viewmats, Ks, camera_ids, gaussian_ids, ray_transforms, randns,
+                    v_means2d, v_depths, v_ray_transforms, v_normals, v_samples, prec="f32"):
+    """gsplat::projection_2dgs_packed_bwd (Projection.cpp:776-865), dense layout, no v_viewmats."""
+    means, quats, scales, viewmats, Ks = map(_f32, (means, quats, scales, viewmats, Ks))
+    N = means.shape[0]
+    nnz = len(camera_ids)
+    acc = _acc(prec)
+    v_means, v_quats, v_scales = np.zeros((N, 3), acc), np.zeros((N, 4), acc), np.zeros((N, 3), acc)
+    fn = getattr(lib(), "oracle_project2dgs_bwd_" + prec)
+    args = [_f32(x) for x in (ray_transforms, randns, v_means2d, v_depths, v_ray_transforms, v_normals, v_samples)]
+    cid = np.ascontiguousarray(camera_ids, np.int64)
+    gid = np.ascontiguousarray(gaussian_ids, np.int64)
+    fn(C.c_int64(nnz), _p(means), _p(quats), _p(scales), _p(viewmats), _p(Ks), _p(cid), _p(gid),
+       _p(args[0]), _p(args[1]), _p(args[2]), _p(args[3]), _p(args[4]), _p(args[5]), _p(args[6]),
+       _p(v_means), _p(v_quats), _p(v_scales))
+    return dict(v_means=v_means, v_quats=v_quats, v_scales=v_scales)
+
+
+def sh_fwd(degree, dirs, coeffs, masks=None, prec="f32"):
+    """gsplat::spherical_harmonics_fwd (SphericalHarmonics.cpp:15-43)."""
+    dirs, coeffs = _f32(dirs), _f32(coeffs)
+    n, K = dirs.shape[0], coeffs.shape[1]
+    colors = np.zeros((n, 3), np.float32)
+    m = None if masks is None else np.ascontiguousarray(masks, np.uint8)
+    getattr(lib(), "oracle_sh_fwd_" + prec)(C.c_int64(n), C.c_int(K), C.c_int(degree), _p(dirs), _p(coeffs), _p(m), _p(colors))
+    return colors
+
+
+def sh_bwd(degree, dirs, coeffs, v_colors, masks=None, prec="f32"):
+    """gsplat::spherical_harmonics_bwd (SphericalHarmonics.cpp:45-80)."""
+    dirs, coeffs, v_colors = _f32(dirs), _f32(coeffs), _f32(v_colors)
+    n, K = dirs.shape[0], coeffs.shape[1]
+    v_coeffs, v_dirs = np.zeros((n, K, 3), np.float32), np.zeros((n, 3), np.float32)
+    m = None if masks is None else np.ascontiguousarray(masks, np.uint8)
+    getattr(lib(), "oracle_sh_bwd_" + prec)(C.c_int64(n), C.c_int(K), C.c_int(degree), _p(dirs), _p(coeffs), _p(m),
+                                           _p(v_colors), _p(v_coeffs), _p(v_dirs))
+    return v_coeffs, v_dirs
+
+
+def view_colors_fwd(viewmats, means, radii, coeffs, camera_ids, gaussian_ids, degree, prec="f32"):
+    """gsplat_cpp::get_view_colors (gsplat_cpp/rendering.cpp:11-47), SH branch. Returns (colors, dirs)."""
+    viewmats, means, coeffs = _f32(viewmats), _f32(means), _f32(coeffs)
+    nnz, K = len(gaussian_ids), coeffs.shape[1]
+    radii = np.ascontiguousarray(radii, np.int32)
+    cid, gid = np.ascontiguousarray(camera_ids, np.int64), np.ascontiguousarray(gaussian_ids, np.int64)
+    colors, dirs = np.zeros((nnz, 3), np.float32), np.zeros((nnz, 3), np.float32)
+    getattr(lib(), "oracle_view_colors_fwd_" + prec)(C.c_int64(nnz), C.c_int(K), C.c_int(degree), _p(viewmats), _p(means),
+                                                    _p(radii), _p(coeffs), _p(cid), _p(gid), _p(colors), _p(dirs))
+    return colors, dirs
+
+
+def isect_tiles(means2d, radii, depths, camera_ids, n_cameras, tile_size, tile_width, tile_height, sort=True):
+    """gsplat::intersect_tile (Intersect.cpp:15-127), packed. Returns tiles_per_gauss, isect_ids, flatten_ids."""
+    means2d, depths = _f32(means2d), _f32(depths)
+    radii = np.ascontiguousarray(radii, np.int32)
+    nnz = means2d.shape[0]
+    cid = np.ascontiguousarray(camera_ids, np.int64) if camera_ids is not None else np.zeros(nnz, np.int64)
+    tpg = np.zeros(nnz, np.int32)
+    L = lib()
+    n = L.oracle_isect_tiles(C.c_int64(nnz), C.c_int64(n_cameras), _p(means2d), _p(radii), _p(depths), _p(cid),
+                             C.c_uint32(tile_size), C.c_uint32(tile_width), C.c_uint32(tile_height), C.c_int(int(sort)),
+                             C.c_int64(0), _p(tpg), None, None)
+    ids, flat = np.zeros(n, np.int64), np.zeros(n, np.int32)
+    L.oracle_isect_tiles(C.c_int64(nnz), C.c_int64(n_cameras), _p(means2d), _p(radii), _p(depths), _p(cid),
+                         C.c_uint32(tile_size), C.c_uint32(tile_width), C.c_uint32(tile_height), C.c_int(int(sort)),
+                         C.c_int64(n), _p(tpg), _p(ids), _p(flat))
+    return tpg, ids, flat
+
+
+def isect_offsets(isect_ids, n_cameras, tile_width, tile_height):
+    """gsplat::intersect_offset (Intersect.cpp:129-145)."""
+    ids = np.ascontiguousarray(isect_ids, np.int64)
+    off = np.zeros((n_cameras, tile_height, tile_width), np.int32)
+    lib().oracle_isect_offsets(C.c_int64(len(ids)), _p(ids), C.c_uint32(n_cameras), C.c_uint32(tile_width),
+                               C.c_uint32(tile_height), _p(off))
+    return off
+
+
+def raster2dgs_fwd(ray_transforms, colors, opacities, normals, W, H, tile_size, tile_offsets, flatten_ids,
+                   backgrounds=None, prec="f32"):
+    """gsplat::rasterize_to_pixels_2dgs_fwd (Rasterization.cpp:324-452), CDIM=3, packed, no masks."""
+    rt, colors, opac, normals = map(_f32, (ray_transforms, colors, opacities, normals))
+    off = np.ascontiguousarray(tile_offsets, np.int32)
+    flat = np.ascontiguousarray(flatten_ids, np.int32)
+    Cn = off.shape[0]
+    nnz = opac.shape[0]
+    bg = _f32(backgrounds)
+    o = dict(render_colors=np.zeros((Cn, H, W, 3), np.float32), render_depths=np.zeros((Cn, H, W, 1), np.float32),
+             render_alphas=np.zeros((Cn, H, W, 1), np.float32), render_Ts=np.zeros((Cn, H, W, 2), np.float32),
+             render_normals=np.zeros((Cn, H, W, 3), np.float32), render_distort=np.zeros((Cn, H, W, 1), np.float32),
+             render_median=np.zeros((Cn, H, W, 1), np.float32), last_ids=np.zeros((Cn, H, W), np.int32),
+             median_ids=np.zeros((Cn, H, W), np.int32), visibilities=np.zeros((nnz, 1), _acc(prec)))
+    getattr(lib(), "oracle_raster2dgs_fwd_" + prec)(
+        C.c_int(Cn), C.c_int(W), C.c_int(H), C.c_int(tile_size), C.c_int64(len(flat)), _p(rt), _p(colors), _p(opac),
+        _p(normals), _p(bg), _p(off), _p(flat), _p(o["render_colors"]), _p(o["render_depths"]), _p(o["render_alphas"]),
+        _p(o["render_Ts"]), _p(o["render_normals"]), _p(o["render_distort"]), _p(o["render_median"]),
+        _p(o["last_ids"]), _p(o["median_ids"]), _p(o["visibilities"]))
+    return o
+
+
+def raster2dgs_bwd(ray_transforms, colors, opacities, normals, W, H, tile_size, tile_offsets, flatten_ids,
+                   render_alphas, render_Ts, last_ids, median_ids, v_render_colors, v_render_depths, v_render_alphas,
+                   v_render_normals, v_render_median, v_render_distort=None, backgrounds=None, prec="f32"):
+    """gsplat::rasterize_to_pixels_2dgs_bwd (Rasterization.cpp:462-612), CDIM=3."""
+    rt, colors, opac, normals = map(_f32, (ray_transforms, colors, opacities, normals))
+    off = np.ascontiguousarray(tile_offsets, np.int32)
+    flat = np.ascontiguousarray(flatten_ids, np.int32)
+    Cn, nnz = off.shape[0], opac.shape[0]
+    acc = _acc(prec)
+    o = dict(v_ray_transforms=np.zeros((nnz, 3, 3), acc), v_colors=np.zeros((nnz, 3), acc),
+             v_opacities=np.zeros(nnz, acc), v_normals=np.zeros((nnz, 3), acc))
+    a = [_f32(x) for x in (render_alphas, render_Ts, v_render_colors, v_render_depths, v_render_alphas,
+                           v_render_normals, v_render_distort, v_render_median)]
+    li, mi = np.ascontiguousarray(last_ids, np.int32), np.ascontiguousarray(median_ids, np.int32)
+    bg = _f32(backgrounds)
+    getattr(lib(), "oracle_raster2dgs_bwd_" + prec)(
+        C.c_int(Cn), C.c_int(W), C.c_int(H), C.c_int(tile_size), C.c_int64(len(flat)), _p(rt), _p(colors), _p(opac),
+        _p(normals), _p(bg), _p(off), _p(flat), _p(a[0]), _p(a[1]), _p(li), _p(mi), _p(a[2]), _p(a[3]), _p(a[4]),
+        _p(a[5]), _p(a[6]), _p(a[7]), _p(o["v_ray_transforms"]), _p(o["v_colors"]), _p(o["v_opacities"]),
+        _p(o["v_normals"]))
+    vd = np.zeros((nnz, 2), acc)
+    getattr(lib(), "oracle_densify_from_vrt_" + prec)(C.c_int64(nnz), _p(rt), _p(o["v_ray_transforms"]), _p(vd))
+    o["v_densify"] = vd
+    o["v_means2d"] = np.zeros((nnz, 2), acc)
+    return o

