@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- train-step/s (and Mrays/s) of the GS-SDF splat hot path on B200 (BASELINE.json metric).
+
+A "step" is one pass of the hot path (SURVEY.md section 3.2 [B]+[D], rows a2-a8 of section 8a) over one
+camera per rank: projection -> SH colour -> tile keys/sort/offsets -> rasterise -> post-ops -> L1 loss ->
+backward of all of it to {means, quats, scales, opacities, SH}; with N > 1 ranks (image-batch data parallel,
+replicated splat state) the flat gradient is all-reduced over NCCL every step.
+
+  value : whole-job steps/s with every input already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same through the public API with HOST buffers: per step the camera (viewmat, K) and the
+          ground-truth image are copied from pinned host memory and the loss is read back (D2H)
+  roofline     : dominant kernel (raster backward): algorithmic bytes / CUDA-event time
+  cpu_baseline : the CPU oracle port on this box's host cores, on a bounded 1/16 sample of the workload
+
+`--impl reference` times the reference's own CPU path: GS-SDF has none (every op CHECK_CUDAs),
+so this arm runs the oracle port (oracle/, the CPU restatement of the reference kernels) with all host
+threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "gs-sdf_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (W, H, N splats, SH degree, isect capacity)
+    "1080p-1M": (1920, 1080, 1_000_000, 3, 40_000_000),   # the config BASELINE.json's metric is quoted on (c4 per GPU)
+    "c2": (1200, 680, 500_000, 3, 24_000_000),
+    "c3": (1920, 1080, 2_000_000, 3, 60_000_000),
+    "c1": (256, 256, 50_000, 0, 4_000_000),
+    "tiny": (320, 192, 20_000, 3, 2_000_000),
+}
+CPU_SAMPLE_DIV = 4  # the CPU sample is the workload at 1/4 resolution per axis and 1/16 of the splats (1/16 of the work)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def summary(self):
+        self._stop_evt.set()
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_oracle_step(O, S, sc, V, K, W, H, deg, rn, gt):
+    """One hot-path step on the CPU oracle port (fp32 restatement, OpenMP)."""
+    p = O.project2dgs_fwd(sc["means"], sc["quats"], sc["scales"], V, K, W, H, S.NEAR, S.FAR, 0.0, rn, "f32")
+    col, dirs = O.view_colors_fwd(V, sc["means"], p["radii"], sc["sh"], p["camera_ids"], p["gaussian_ids"], deg, "f32")
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    _, ids, flat = O.isect_tiles(p["means2d"], p["radii"], p["depths"], p["camera_ids"], 1, 16, tw, th)
+    off = O.isect_offsets(ids, 1, tw, th)
+    op = sc["opacities"][p["gaussian_ids"]]
+    r = O.raster2dgs_fwd(p["ray_transforms"], col, op, p["normals"], W, H, 16, off, flat, None, "f32")
+    ed = np.nan_to_num(r["render_depths"] / r["render_alphas"])
+    out = np.concatenate([r["render_colors"], ed], -1)
+    d = out - gt
+    npx = W * H
+    loss = np.abs(d[..., :3]).sum() / (3 * npx) + 0.1 * np.abs(d[..., 3:]).sum() / npx
+    v_out = np.sign(d) * np.array([1 / (3 * npx)] * 3 + [0.1 / npx], np.float32)
+    fin = np.isfinite(r["render_depths"] / np.where(r["render_alphas"] == 0, np.nan, r["render_alphas"]))
+    v_dep = np.where(fin, v_out[..., 3:] / np.where(fin, r["render_alphas"], 1), 0).astype(np.float32)
+    v_alp = np.where(fin, -v_out[..., 3:] * r["render_depths"] / np.where(fin, r["render_alphas"], 1) ** 2, 0).astype(np.float32)
+    z3 = np.zeros((1, H, W, 3), np.float32)
+    rb = O.raster2dgs_bwd(p["ray_transforms"], col, op, p["normals"], W, H, 16, off, flat, r["render_alphas"], r["render_Ts"],
+                          r["last_ids"], r["median_ids"], np.ascontiguousarray(v_out[..., :3]), v_dep, v_alp, z3,
+                          np.zeros((1, H, W, 1), np.float32), None, None, "f32")
+    vcm = rb["v_colors"] * (col > 0)
+    O.sh_bwd(deg, dirs, sc["sh"][p["gaussian_ids"]], vcm, None, "f32")
+    O.project2dgs_bwd(sc["means"], sc["quats"], sc["scales"], V, K, p["camera_ids"], p["gaussian_ids"], p["ray_transforms"],
+                      p["randns"], rb["v_means2d"], np.zeros(p["nnz"], np.float32), rb["v_ray_transforms"], rb["v_normals"],
+                      np.zeros((p["nnz"], 3), np.float32), "f32")
+    return float(loss), p["nnz"], len(flat)
+
+
+def run_cpu_sample(workload, steps, warmup, budget_s=25.0):
+    """Times the oracle port on a bounded sample: the workload at 1/4 linear resolution with 1/16 of the splats
+    (same screen coverage per splat, 1/16 of every unit count); returns full-workload-equivalent steps/s."""
+    from gssdf_b200 import scene as S
+    from oracle import oracle as O
+    O.build()
+    W, H, N, deg, _ = WORKLOADS[workload]
+    Ws, Hs, Ns = max(W // CPU_SAMPLE_DIV, 16), max(H // CPU_SAMPLE_DIV, 16), max(N // CPU_SAMPLE_DIV ** 2, 64)
+    # 1/16 of the splats, each 4x larger in world space: same pixel footprint per splat at 1/4 resolution, hence the
+    # same per-tile depth complexity as the full workload and 1/16 of its nnz, n_isects, tiles and pixels
+    sc = S.box_scene(Ns, deg, seed=0, scale_mult=math.sqrt(1.0e6 / N) * CPU_SAMPLE_DIV)
+    V, K = S.cameras([0], Ws, Hs)
+    rn = S.randns(Ns)
+    gt = np.random.default_rng(3).random((1, Hs, Ws, 4), dtype=np.float32)
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    for _ in range(max(1, min(warmup, 1))):
+        cpu_oracle_step(O, S, sc, V, K, Ws, Hs, deg, rn, gt)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(max(steps, 1)):
+        _, nnz, I = cpu_oracle_step(O, S, sc, V, K, Ws, Hs, deg, rn, gt)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / done
+    frac = (Ws * Hs) / float(W * H)
+    value = (1.0 / dt) * frac  # sample steps/s scaled by the work fraction = full-workload-equivalent steps/s
+    return dict(value=value, unit="step/s", cores=cores, kind="port",
+                sample=f"{done} oracle steps (C, OpenMP, fp32) of the workload at 1/{CPU_SAMPLE_DIV} linear resolution "
+                       f"({Ws}x{Hs}, {Ns} splats, nnz={nnz}, n_isects={I}): {dt * 1e3:.0f} ms each; value = sample steps/s x {frac:.4f}"), W, H
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="1080p-1M", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    W, H, N, deg, isect_cap = WORKLOADS[args.workload]
+    cfg = {"workload": f"{args.workload}: {W}x{H}, {N} splats, SH deg {deg}, synthetic box scene seed 0 (SURVEY 8d), tile 16, packed, "
+                       f"1 camera/rank/step", "timing": "CUDA events; inputs (232 B/splat state + images) exceed the 126 MB L2, no flush",
+           "parallelism": f"image-parallel dp{world}, replicated splats, NCCL all-reduce of the flat gradient" if world > 1 else "single GPU"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb, _, _ = run_cpu_sample(args.workload, max(args.steps, 1), args.warmup)
+        line = {"impl": "reference", "metric": "train_steps_per_s", "value": cb["value"], "unit": "step/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "step/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "mrays_per_s": cb["value"] * W * H / 1e6,
+                "note": "GS-SDF has no CPU implementation of this path (SURVEY 0.5); this arm is the oracle port of the reference kernels"}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    from gssdf_b200 import render
+    from gssdf_b200 import scene as S
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    sc_np = S.box_scene(N, deg, seed=0)  # replicated state: identical on every rank
+    sc = {k: t(v) for k, v in sc_np.items()}
+    K_sh = (deg + 1) ** 2
+    R = render.SplatRenderer(N, K_sh, 1, W, H, dev, isect_cap=isect_cap, sh_degree=deg)
+    n_cams = 8
+    cams = [S.camera(rank * n_cams + i, W, H) for i in range(n_cams)]  # rank r renders its own images
+    # ground truth: the same scene rendered with perturbed colours, produced once on the device
+    sc_gt = dict(sc)
+    sc_gt["sh"] = sc["sh"] + 0.1 * torch.randn(sc["sh"].shape, device=dev, generator=torch.Generator(dev).manual_seed(3))
+    gts = []
+    randn_buf = torch.empty(N, 2, device=dev)
+    for V, Kc in cams:
+        R.forward(sc_gt["means"], sc_gt["quats"], sc_gt["scales"], sc_gt["opacities"], sc_gt["sh"], t(V[None]), t(Kc[None]))
+        gts.append(R.out_colors.clone())
+    torch.cuda.synchronize()
+    dev_cams = [(t(V[None]), t(Kc[None])) for V, Kc in cams]
+    host_cams = [(torch.from_numpy(V[None].copy()).pin_memory(), torch.from_numpy(Kc[None].copy()).pin_memory()) for V, Kc in cams]
+    host_gts = [g.cpu().pin_memory() for g in gts]
+    h_V, h_K, h_gt = torch.empty(1, 4, 4, device=dev), torch.empty(1, 3, 3, device=dev), torch.empty(1, H, W, 4, device=dev)
+    loss_host = torch.empty(1).pin_memory()
+
+    def step_resident(i):
+        V, Kc = dev_cams[i % n_cams]
+        randn_buf.normal_()  # the reference draws randns on the device every render (Projection.cpp:728)
+        loss = R.step(sc, V, Kc, gts[i % n_cams], randn_buf)
+        if world > 1:
+            dist.all_reduce(R.flat_grad)  # sum; the optimiser scales by 1/world (losses are means)
+        return loss
+
+    def step_e2e(i):
+        hv, hk = host_cams[i % n_cams]
+        h_V.copy_(hv, non_blocking=True)
+        h_K.copy_(hk, non_blocking=True)
+        h_gt.copy_(host_gts[i % n_cams], non_blocking=True)
+        randn_buf.normal_()
+        loss = R.step(sc, h_V, h_K, h_gt, randn_buf)
+        if world > 1:
+            dist.all_reduce(R.flat_grad)
+        loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the loss every step (neural_mapping.cpp:505-514)
+        return float(loss_host[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, sampler=None):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.start()
+        ev0.record()
+        for i in range(steps):
+            fn(i)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            tm = torch.tensor([ms], device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms = float(tm[0])
+        return ms
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    cnt = R.read_counts()
+    assert not cnt["nnz_overflow"] and not cnt["isect_overflow"], f"capacity overflow: {cnt}"
+    # the timed region; the library records one CUDA-event pair per step around each raster kernel
+    mk = lambda: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    prof_f, prof_b = [mk() for _ in range(args.steps)], [mk() for _ in range(args.steps)]
+    for e0, e1 in prof_f + prof_b:
+        e0.record(); e1.record()  # creates the cudaEvent_t handles
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.start()
+    ev0.record()
+    for i in range(args.steps):
+        R.prof_fwd, R.prof_bwd = prof_f[i], prof_b[i]
+        step_resident(i)
+    ev1.record()
+    barrier()
+    fwd_ms = [a.elapsed_time(b) for a, b in prof_f]
+    bwd_ms = [a.elapsed_time(b) for a, b in prof_b]
+    R.prof_fwd = R.prof_bwd = None
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        tm = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms_total = float(tm[0])
+    clocks = sampler.summary() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * 1e3 / ms_step  # images (train steps of one camera) per second over the whole job
+
+    # end-to-end through the public API with host buffers
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = world * 1e3 / ms_e2e
+    h2d = 16 * 4 + 9 * 4 + H * W * 4 * 4
+    d2h = 4
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        nnz, I, P = cnt["nnz"], cnt["n_isects"], W * H
+        alg_bwd = 148 * I + 64 * P + 8 * nnz   # raster_bwd = 76 I + 64 P + 72 I + 8 nnz
+        alg_fwd = 76 * I + 56 * P + 4 * nnz
+        t_bwd = float(np.mean(bwd_ms)) * 1e-3
+        t_fwd = float(np.mean(fwd_ms)) * 1e-3
+        achieved = alg_bwd / t_bwd / 1e9
+        line = {"metric": "train_steps_per_s", "value": value, "unit": "step/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfg, "mrays_per_s": value * P / 1e6, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "step/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e},
+                "gpu_launches": args.steps * render.SplatRenderer.KERNELS_PER_STEP,
+                "roofline": {"kernel": "raster2dgs_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                             "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
+                             "algorithmic_bytes": alg_bwd, "kernel_ms": t_bwd * 1e3,
+                             "raster_fwd": {"achieved": alg_fwd / t_fwd / 1e9, "frac": alg_fwd / t_fwd / 1e9 / pk["hbm_gbs"],
+                                            "kernel_ms": t_fwd * 1e3, "algorithmic_bytes": alg_fwd}},
+                "counts": cnt}
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _, _ = run_cpu_sample(args.workload, 3, 1)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -552,8 +552,10 @@ extern "C" int gssdf_raster2dgs_fwd(const gssdf_raster2dgs_fwd_args *a, gssdf_st
                                                               rec, a->visibilities, 1);
         GSSDF_LAUNCH_OK("pack_records_kernel");
     }
+    if (a->prof_start) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_start, st));
     raster2dgs_fwd_kernel<<<a->C * tw * th, kRasterThreads, 0, st>>>(*a, rec, tw, th);
     GSSDF_LAUNCH_OK("raster2dgs_fwd_kernel");
+    if (a->prof_stop) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_stop, st));
     return GSSDF_OK;
 }
 
@@ -579,6 +581,7 @@ extern "C" int gssdf_raster2dgs_bwd(const gssdf_raster2dgs_bwd_args *a, gssdf_st
                                                           reinterpret_cast<float *>(vrec), 16);
     GSSDF_LAUNCH_OK("pack_records_kernel");
     const size_t smem = 2 * sizeof(BwdStage);
+    if (a->prof_start) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_start, st));
     if (a->v_means2d_abs) {
         GSSDF_CUDA_OK(cudaMemsetAsync(a->v_means2d_abs, 0, (size_t)a->cap * 2 * sizeof(float), st));
         GSSDF_CUDA_OK(cudaFuncSetAttribute(raster2dgs_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -588,6 +591,7 @@ extern "C" int gssdf_raster2dgs_bwd(const gssdf_raster2dgs_bwd_args *a, gssdf_st
         raster2dgs_bwd_kernel<false><<<a->C * tw * th, kRasterThreads, smem, st>>>(*a, rec, reinterpret_cast<float *>(vrec), tw, th);
     }
     GSSDF_LAUNCH_OK("raster2dgs_bwd_kernel");
+    if (a->prof_stop) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_stop, st));
     raster_bwd_finalize_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, vrec);
     GSSDF_LAUNCH_OK("raster_bwd_finalize_kernel");
     return GSSDF_OK;

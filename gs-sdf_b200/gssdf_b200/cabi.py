@@ -111,7 +111,7 @@ def tile_encode(Cn, W, H, tile_size, cap, counts, means2d, radii, depths, camera
 
 
 def raster2dgs_fwd(Cn, W, H, tile_size, channels, cap, counts, means2d, ray_transforms, colors, opacities, normals,
-                   backgrounds, offsets, flatten_ids, out, ws):
+                   backgrounds, offsets, flatten_ids, out, ws, prof=None):
     need = lib().gssdf_raster2dgs_workspace_bytes(cap)
     w = ws.get(need)
     a = make_args("gssdf_raster2dgs_fwd_args", C=Cn, image_width=W, image_height=H, tile_size=tile_size,
@@ -121,13 +121,15 @@ def raster2dgs_fwd(Cn, W, H, tile_size, channels, cap, counts, means2d, ray_tran
                   render_alphas=out["render_alphas"], render_normals=out["render_normals"],
                   render_distort=out["render_distort"], render_median=out["render_median"], render_Ts=out["render_Ts"],
                   last_ids=out["last_ids"], median_ids=out["median_ids"], visibilities=out["visibilities"], workspace=w,
-                  workspace_bytes=w.numel())
+                  workspace_bytes=w.numel(), prof_start=prof[0].cuda_event if prof else None,
+                  prof_stop=prof[1].cuda_event if prof else None)
     check(lib().gssdf_raster2dgs_fwd(_lib.C.byref(a), _stream()))
 
 
 def raster2dgs_bwd(Cn, W, H, tile_size, channels, cap, counts, means2d, ray_transforms, colors, opacities, normals,
                    backgrounds, offsets, flatten_ids, render_alphas, render_Ts, last_ids, median_ids, v_render_colors,
-                   v_render_depths, v_render_alphas, v_render_normals, v_render_median, out, ws, v_render_distort=None):
+                   v_render_depths, v_render_alphas, v_render_normals, v_render_median, out, ws, v_render_distort=None,
+                   prof=None):
     need = lib().gssdf_raster2dgs_bwd_workspace_bytes(cap)
     w = ws.get(need)
     a = make_args("gssdf_raster2dgs_bwd_args", C=Cn, image_width=W, image_height=H, tile_size=tile_size,
@@ -138,7 +140,8 @@ def raster2dgs_bwd(Cn, W, H, tile_size, channels, cap, counts, means2d, ray_tran
                   v_render_alphas=v_render_alphas, v_render_normals=v_render_normals, v_render_distort=v_render_distort,
                   v_render_median=v_render_median, v_means2d=out.get("v_means2d"), v_means2d_abs=out.get("v_means2d_abs"),
                   v_ray_transforms=out["v_ray_transforms"], v_colors=out["v_colors"], v_opacities=out["v_opacities"],
-                  v_normals=out["v_normals"], v_densify=out.get("v_densify"), workspace=w, workspace_bytes=w.numel())
+                  v_normals=out["v_normals"], v_densify=out.get("v_densify"), workspace=w, workspace_bytes=w.numel(),
+                  prof_start=prof[0].cuda_event if prof else None, prof_stop=prof[1].cuda_event if prof else None)
     check(lib().gssdf_raster2dgs_bwd(_lib.C.byref(a), _stream()))
 
 

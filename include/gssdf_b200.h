@@ -226,6 +226,7 @@ typedef struct gssdf_raster2dgs_fwd_args {
     float *visibilities;         /* [cap,1] */
     void *workspace;             /* >= gssdf_raster2dgs_workspace_bytes(cap) : packed 64-B records */
     size_t workspace_bytes;
+    void *prof_start, *prof_stop; /* optional cudaEvent_t recorded around the main raster kernel (NULL = off) */
 } gssdf_raster2dgs_fwd_args;
 size_t gssdf_raster2dgs_workspace_bytes(int32_t cap);
 int gssdf_raster2dgs_fwd(const gssdf_raster2dgs_fwd_args *a, gssdf_stream_t stream);
@@ -260,6 +261,7 @@ typedef struct gssdf_raster2dgs_bwd_args {
     float *v_densify;         /* [cap,2] */
     void *workspace;          /* >= gssdf_raster2dgs_bwd_workspace_bytes(cap) */
     size_t workspace_bytes;
+    void *prof_start, *prof_stop; /* optional cudaEvent_t recorded around the main raster kernel (NULL = off) */
 } gssdf_raster2dgs_bwd_args;
 size_t gssdf_raster2dgs_bwd_workspace_bytes(int32_t cap);
 int gssdf_raster2dgs_bwd(const gssdf_raster2dgs_bwd_args *a, gssdf_stream_t stream);
