@@ -17,7 +17,14 @@
 //     record backward) are warp-shuffle reductions: backward uses a 16-shuffle butterfly instead of the
 //     reference's 16 x 5 cg::reduce shuffles, accumulates the tile's 8 warps in shared memory and
 //     issues ONE 64-byte RED per (tile, splat) instead of 16 atomics per (warp, splat);
-//   * v_densify is a well-defined post-pass instead of the reference's racy read (Bwd.cu:699-706).
+//   * v_densify is a well-defined post-pass instead of the reference's racy read (Bwd.cu:699-706);
+//   * exact sub-tile culling: alpha >= 1/255 needs u^2+v^2 <= rho^2 = 2 ln(255 o), and the pixel set
+//     {zeta_x^2 + zeta_y^2 <= rho^2 zeta_z^2} (zeta = px*(Mv x Mw) + py*(Mw x Mu) + Mu x Mv is LINEAR in the pixel)
+//     is a conic. Its ellipse (centre + 2x2 form, computed once per splat in fp64, inflated by a safety margin)
+//     rides in the record; per (tile, splat) one thread tests the ellipse against the 8 warp blocks (exact
+//     minimum of the quadratic over a rectangle) and each warp only evaluates the splats whose ellipse
+//     touches its 8x4 pixels. Every culled (pixel, splat) pair is one the reference skips (alpha < 1/255),
+//     so results are unchanged; on the 1080p/1M workload 96% of the (warp, splat) iterations were such no-ops.
 #include "common.cuh"
 
 namespace gssdf {
@@ -26,6 +33,8 @@ constexpr int kRasterThreads = 256;
 constexpr int kBatch = 256;  // splats per shared-memory stage
 constexpr float kNearN = 0.05f, kFarN = 100.f;  // hard-coded in the reference (Fwd.cu:368-369)
 constexpr float kAlphaThreshold = 1.f / 255.f;  // GSF/include/Common.h:53
+constexpr int kRecF4 = 6;                        // record = 6 float4 = 96 B: 16 render floats + ellipse (cx, cy, a, b, c) + pad
+constexpr int kRecBytes = kRecF4 * 16;
 
 // ---------------------------------------------------------------------------------------------
 // record packing
@@ -41,11 +50,43 @@ pack_records_kernel(const gssdf_counts *counts, const float *__restrict__ ray_tr
     const float *M = ray_transforms + 9 * (int64_t)i;
     const float *c = colors + 3 * (int64_t)i;
     const float *n = normals + 3 * (int64_t)i;
-    float4 *r = rec + 4 * (int64_t)i;
+    float4 *r = rec + kRecF4 * (int64_t)i;
+    const float opac = opacities[i];
     r[0] = make_float4(M[0], M[1], M[2], M[3]);
     r[1] = make_float4(M[4], M[5], M[6], M[7]);
-    r[2] = make_float4(M[8], opacities[i], c[0], c[1]);
+    r[2] = make_float4(M[8], opac, c[0], c[1]);
     r[3] = make_float4(c[2], n[0], n[1], n[2]);
+    // contributing region {alpha >= 1/255} as an ellipse (p-c)^T A (p-c) <= 1, or A = 0 (no culling possible)
+    float ecx = 0.f, ecy = 0.f, ea = 0.f, eb = 0.f, ec = 0.f;
+    const double lg = log(255.0 * (double)opac);
+    if (!(lg > 0.0)) {  // o * exp(-sigma) < 1/255 everywhere (also catches NaN opacities conservatively? no: NaN -> no cull)
+        if (opac == opac) { ecx = ecy = 1e15f; ea = ec = 1e30f; }
+    } else {
+        const double rho2 = 2.0 * lg * 1.002 + 1e-6;  // safety margin on the cut-off radius
+        const double u0 = M[0], u1 = M[1], u2 = M[2], v0 = M[3], v1 = M[4], v2 = M[5], w0 = M[6], w1 = M[7], w2 = M[8];
+        // zeta = px * A + py * B + Cc
+        const double A0 = v1 * w2 - v2 * w1, A1 = v2 * w0 - v0 * w2, A2 = v0 * w1 - v1 * w0;  // Mv x Mw
+        const double B0 = w1 * u2 - w2 * u1, B1 = w2 * u0 - w0 * u2, B2 = w0 * u1 - w1 * u0;  // Mw x Mu
+        const double C0 = u1 * v2 - u2 * v1, C1 = u2 * v0 - u0 * v2, C2 = u0 * v1 - u1 * v0;  // Mu x Mv
+        // Q(p) = q00 x^2 + 2 q01 x y + q11 y^2 + 2 q02 x + 2 q12 y + q22
+        const double q00 = A0 * A0 + A1 * A1 - rho2 * A2 * A2, q01 = A0 * B0 + A1 * B1 - rho2 * A2 * B2;
+        const double q11 = B0 * B0 + B1 * B1 - rho2 * B2 * B2, q02 = A0 * C0 + A1 * C1 - rho2 * A2 * C2;
+        const double q12 = B0 * C0 + B1 * C1 - rho2 * B2 * C2, q22 = C0 * C0 + C1 * C1 - rho2 * C2 * C2;
+        const double det = q00 * q11 - q01 * q01;
+        if (q00 > 0.0 && det > 1e-30 * q00 * q00 + 1e-300) {
+            const double cx = -(q11 * q02 - q01 * q12) / det, cy = -(q00 * q12 - q01 * q02) / det;
+            const double k = q22 + q02 * cx + q12 * cy;
+            if (k < 0.0 && isfinite(cx) && isfinite(cy)) {
+                const double sc = -1.0 / (k * 1.004);  // inflate the ellipse by ~0.2 % in radius
+                const double fa = q00 * sc, fb = q01 * sc, fc = q11 * sc;
+                if (isfinite(fa) && isfinite(fb) && isfinite(fc) && fabs(cx) < 1e9 && fabs(cy) < 1e9) {
+                    ecx = (float)cx; ecy = (float)cy; ea = (float)fa * 0.9999f; eb = (float)fb; ec = (float)fc * 0.9999f;
+                }
+            }
+        }
+    }
+    r[4] = make_float4(ecx, ecy, ea, eb);
+    r[5] = make_float4(ec, 0.f, 0.f, 0.f);
     if (zero_a) {
         for (int k = 0; k < zero_a_stride; ++k) zero_a[(int64_t)i * zero_a_stride + k] = 0.f;
     }
@@ -78,10 +119,43 @@ __device__ __forceinline__ void pixel_of_thread(int &lx, int &ly) {
 }
 
 struct __align__(16) Stage {
-    float4 rec[kBatch * 4];  // 16 KB
-    int ids[kBatch];         // packed splat index of each record
-    float acc[kBatch];       // per-splat tile accumulator (visibility)
+    float4 rec[kBatch * kRecF4];  // 24 KB
+    int ids[kBatch];              // packed splat index of each record
+    float acc[kBatch];            // per-splat tile accumulator (visibility)
+    unsigned char mask[kBatch];   // bit w: the splat's ellipse touches warp w's 8x4 pixel block
 };
+
+// minimum over the rectangle [x0,x1]x[y0,y1] (relative to the centre) of a dx^2 + 2 b dx dy + c dy^2 is <= 1 ?
+__device__ __forceinline__ bool ellipse_hits_rect(float a, float b, float c, float dx0, float dx1, float dy0, float dy1) {
+    if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) return true;
+    float q = 3.0e38f;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const float dx = e ? dx1 : dx0;
+        const float dy = fminf(fmaxf(-b * dx / c, dy0), dy1);  // NaN (c == 0: culling disabled) falls through to dy0/dy1
+        q = fminf(q, a * dx * dx + 2.f * b * dx * dy + c * dy * dy);
+        const float ey = e ? dy1 : dy0;
+        const float ex = fminf(fmaxf(-b * ey / a, dx0), dx1);
+        q = fminf(q, a * ex * ex + 2.f * b * ex * ey + c * ey * ey);
+    }
+    return q <= 1.f;
+}
+
+// 8-bit warp mask of record t for the tile whose first pixel centre is (ox, oy)
+__device__ __forceinline__ unsigned cull_mask(const float4 *rec_t, float ox, float oy) {
+    const float4 e0 = rec_t[4];
+    const float ec = rec_t[5].x;
+    const float cx = e0.x, cy = e0.y, a = e0.z, b = e0.w;
+    const float m = 0.05f;  // margin in pixels
+    if (!ellipse_hits_rect(a, b, ec, ox - m - cx, ox + 15.f + m - cx, oy - m - cy, oy + 15.f + m - cy)) return 0u;
+    unsigned mask = 0u;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const float x0 = ox + (w & 1) * 8.f, y0 = oy + (w >> 1) * 4.f;
+        if (ellipse_hits_rect(a, b, ec, x0 - m - cx, x0 + 7.f + m - cx, y0 - m - cy, y0 + 3.f + m - cy)) mask |= 1u << w;
+    }
+    return mask;
+}
 
 // issue the gather of batch [start, start+n) (n <= kBatch) into `st`; every thread arrives once
 __device__ __forceinline__ void issue_batch(Stage &st, uint64_t *bar, const float4 *__restrict__ rec,
@@ -91,8 +165,8 @@ __device__ __forceinline__ void issue_batch(Stage &st, uint64_t *bar, const floa
         const int g = flatten_ids[start + t];
         st.ids[t] = g;
         st.acc[t] = 0.f;
-        bulk_g2s(&st.rec[t * 4], rec + 4 * (int64_t)g, 64, bar);
-        mbar_arrive_expect_tx(bar, 64);
+        bulk_g2s(&st.rec[t * kRecF4], rec + kRecF4 * (int64_t)g, kRecBytes, bar);
+        mbar_arrive_expect_tx(bar, kRecBytes);
     } else {
         mbar_arrive(bar);
     }
@@ -103,7 +177,8 @@ __device__ __forceinline__ void issue_batch(Stage &st, uint64_t *bar, const floa
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRasterThreads)
 raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restrict__ rec, int tw, int th) {
-    __shared__ Stage s_stage[2];
+    extern __shared__ __align__(16) unsigned char s_raw_fwd[];
+    Stage *s_stage = reinterpret_cast<Stage *>(s_raw_fwd);
     __shared__ __align__(8) uint64_t s_bar[2];
     const TileInfo ti = tile_info(a.C, tw, th, a.offsets, a.counts);
     const int W = a.image_width, H = a.image_height;
@@ -140,9 +215,18 @@ raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restric
         waited = b + 1;
         const int start = ti.rs + b * kBatch;
         const int bn = min(kBatch, ti.re - start);
-        for (int t = 0; t < bn; ++t) {
+        if (threadIdx.x < bn)
+            st.mask[threadIdx.x] = (unsigned char)cull_mask(&st.rec[threadIdx.x * kRecF4], ti.tx * kTile + 0.5f, ti.ty * kTile + 0.5f);
+        __syncthreads();
+        const int warp_id = threadIdx.x >> 5;
+        for (int t0 = 0; t0 < bn; t0 += 32) {
+          if (__all_sync(0xffffffffu, done)) break;
+          unsigned todo = __ballot_sync(0xffffffffu, (t0 + lane < bn) && ((st.mask[t0 + lane] >> warp_id) & 1));
+          while (todo) {
+            const int t = t0 + __ffs(todo) - 1;
+            todo &= todo - 1;
             if (__all_sync(0xffffffffu, done)) break;
-            const float4 r0 = st.rec[t * 4 + 0], r1 = st.rec[t * 4 + 1], r2 = st.rec[t * 4 + 2], r3 = st.rec[t * 4 + 3];
+            const float4 r0 = st.rec[t * kRecF4 + 0], r1 = st.rec[t * kRecF4 + 1], r2 = st.rec[t * kRecF4 + 2], r3 = st.rec[t * kRecF4 + 3];
             // M rows: u = (r0.x r0.y r0.z) v = (r0.w r1.x r1.y) w = (r1.z r1.w r2.x)
             const float hux = px * r1.z - r0.x, huy = px * r1.w - r0.y, huz = px * r2.x - r0.z;
             const float hvx = py * r1.z - r0.w, hvy = py * r1.w - r1.x, hvz = py * r2.x - r1.y;
@@ -176,6 +260,7 @@ raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restric
                 const float v = warp_sum(vis);
                 if (lane == 0) atomicAdd(&st.acc[t], v);
             }
+          }
         }
         const int n_done = __syncthreads_count(done);
         // flush this batch's visibilities: one RED per (tile, splat)
@@ -219,8 +304,9 @@ raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restric
 // backward
 // ---------------------------------------------------------------------------------------------
 struct __align__(16) BwdStage {
-    float4 rec[kBatch * 4];
+    float4 rec[kBatch * kRecF4];
     int ids[kBatch];
+    unsigned char mask[kBatch];
     float grad[kBatch * 16];  // per-splat tile gradient record: rgb[3] n[3] u[3] v[3] w[3] opacity
     float gabs[kBatch * 2];
 };
@@ -236,8 +322,8 @@ __device__ __forceinline__ void issue_batch_bwd(BwdStage &st, uint64_t *bar, con
     if (t < n) {
         const int g = flatten_ids[last - t];
         st.ids[t] = g;
-        bulk_g2s(&st.rec[t * 4], rec + 4 * (int64_t)g, 64, bar);
-        mbar_arrive_expect_tx(bar, 64);
+        bulk_g2s(&st.rec[t * kRecF4], rec + kRecF4 * (int64_t)g, kRecBytes, bar);
+        mbar_arrive_expect_tx(bar, kRecBytes);
     } else {
         mbar_arrive(bar);
     }
@@ -300,10 +386,19 @@ raster2dgs_bwd_kernel(const gssdf_raster2dgs_bwd_args a, const float4 *__restric
         mbar_wait(&s_bar[b & 1], (b >> 1) & 1);
         const int last = ti.re - 1 - b * kBatch;  // sorted index held by slot 0
         const int bn = min(kBatch, last - ti.rs + 1);
+        if (threadIdx.x < bn)
+            st.mask[threadIdx.x] = (unsigned char)cull_mask(&st.rec[threadIdx.x * kRecF4], ti.tx * kTile + 0.5f, ti.ty * kTile + 0.5f);
+        __syncthreads();
+        const int warp_id = threadIdx.x >> 5;
         // skip the slots behind every pixel of this warp's last contributor (Bwd.cu:333)
-        for (int t = max(0, last - warp_bin_final); t < bn; ++t) {
+        const int t_begin = max(0, last - warp_bin_final);
+        for (int t0 = t_begin & ~31; t0 < bn; t0 += 32) {
+          unsigned todo = __ballot_sync(0xffffffffu, (t0 + lane < bn) && (t0 + lane >= t_begin) && ((st.mask[t0 + lane] >> warp_id) & 1));
+          while (todo) {
+            const int t = t0 + __ffs(todo) - 1;
+            todo &= todo - 1;
             const int idx = last - t;
-            const float4 r0 = st.rec[t * 4 + 0], r1 = st.rec[t * 4 + 1], r2 = st.rec[t * 4 + 2], r3 = st.rec[t * 4 + 3];
+            const float4 r0 = st.rec[t * kRecF4 + 0], r1 = st.rec[t * kRecF4 + 1], r2 = st.rec[t * kRecF4 + 2], r3 = st.rec[t * kRecF4 + 3];
             const float hux = px * r1.z - r0.x, huy = px * r1.w - r0.y, huz = px * r2.x - r0.z;
             const float hvx = py * r1.z - r0.w, hvy = py * r1.w - r1.x, hvz = py * r2.x - r1.y;
             const float rcx = huy * hvz - huz * hvy, rcy = huz * hvx - hux * hvz, rcz = hux * hvy - huy * hvx;
@@ -385,6 +480,7 @@ raster2dgs_bwd_kernel(const gssdf_raster2dgs_bwd_args a, const float4 *__restric
                 if (lane == 16) atomicAdd(&st.gabs[t], fabsf(h1 * r2.x));           // comp 8  = u.z
                 if (lane == 22) atomicAdd(&st.gabs[kBatch + t], fabsf(h1 * r2.x));  // comp 11 = v.z
             }
+          }
         }
         __syncthreads();
         // flush: one 64-byte RED burst per (tile, splat); 16 consecutive threads cover one record
@@ -522,8 +618,10 @@ extern "C" int gssdf_l1_loss(const gssdf_l1_loss_args *a, gssdf_stream_t stream)
     return GSSDF_OK;
 }
 
-extern "C" size_t gssdf_raster2dgs_workspace_bytes(int32_t cap) { return align_up((size_t)(cap > 0 ? cap : 1) * 64, 256); }
-extern "C" size_t gssdf_raster2dgs_bwd_workspace_bytes(int32_t cap) { return 2 * align_up((size_t)(cap > 0 ? cap : 1) * 64, 256); }
+extern "C" size_t gssdf_raster2dgs_workspace_bytes(int32_t cap) { return align_up((size_t)(cap > 0 ? cap : 1) * kRecBytes, 256); }
+extern "C" size_t gssdf_raster2dgs_bwd_workspace_bytes(int32_t cap) {
+    return align_up((size_t)(cap > 0 ? cap : 1) * kRecBytes, 256) + align_up((size_t)(cap > 0 ? cap : 1) * 64, 256);
+}
 
 static int check_raster_common(const char *who, int C, int W, int H, int tile_size, int channels) {
     GSSDF_REQUIRE(C > 0 && W > 0 && H > 0, GSSDF_EINVAL, "%s: C, width, height must be positive", who);
@@ -553,7 +651,8 @@ extern "C" int gssdf_raster2dgs_fwd(const gssdf_raster2dgs_fwd_args *a, gssdf_st
         GSSDF_LAUNCH_OK("pack_records_kernel");
     }
     if (a->prof_start) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_start, st));
-    raster2dgs_fwd_kernel<<<a->C * tw * th, kRasterThreads, 0, st>>>(*a, rec, tw, th);
+    GSSDF_CUDA_OK(cudaFuncSetAttribute(raster2dgs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(Stage))));
+    raster2dgs_fwd_kernel<<<a->C * tw * th, kRasterThreads, 2 * sizeof(Stage), st>>>(*a, rec, tw, th);
     GSSDF_LAUNCH_OK("raster2dgs_fwd_kernel");
     if (a->prof_stop) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_stop, st));
     return GSSDF_OK;
@@ -576,7 +675,7 @@ extern "C" int gssdf_raster2dgs_bwd(const gssdf_raster2dgs_bwd_args *a, gssdf_st
     cudaStream_t st = (cudaStream_t)stream;
     const int tw = cdiv(a->image_width, kTile), th = cdiv(a->image_height, kTile);
     float4 *rec = reinterpret_cast<float4 *>(a->workspace);
-    float4 *vrec = reinterpret_cast<float4 *>(reinterpret_cast<char *>(a->workspace) + align_up((size_t)a->cap * 64, 256));
+    float4 *vrec = reinterpret_cast<float4 *>(reinterpret_cast<char *>(a->workspace) + align_up((size_t)a->cap * kRecBytes, 256));
     pack_records_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(a->counts, a->ray_transforms, a->colors, a->opacities, a->normals, rec,
                                                           reinterpret_cast<float *>(vrec), 16);
     GSSDF_LAUNCH_OK("pack_records_kernel");
