@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256)
 pack_records_kernel(const gssdf_counts *counts, const float *__restrict__ ray_transforms,
                     const float *__restrict__ colors, const float *__restrict__ opacities,
                     const float *__restrict__ normals, float4 *__restrict__ rec, float *__restrict__ zero_a,
-                    int zero_a_stride) {
+                    int zero_a_stride, float extent) {
     const int nnz = counts->nnz;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnz) return;
@@ -56,11 +56,13 @@ pack_records_kernel(const gssdf_counts *counts, const float *__restrict__ ray_tr
     r[1] = make_float4(M[4], M[5], M[6], M[7]);
     r[2] = make_float4(M[8], opac, c[0], c[1]);
     r[3] = make_float4(c[2], n[0], n[1], n[2]);
-    // contributing region {alpha >= 1/255} as an ellipse (p-c)^T A (p-c) <= 1, or A = 0 (no culling possible)
-    float ecx = 0.f, ecy = 0.f, ea = 0.f, eb = 0.f, ec = 0.f;
+    // contributing region {alpha >= 1/255} = {Q(p) <= 0}, Q a conic in the pixel (see file header). Stored as six
+    // coefficients normalised so that every term is <= 1 in magnitude over the image (fp32-safe evaluation).
+    // all zeros = "cannot cull" (Q == 0 everywhere -> always hit); (0,..,0,1) = never contributes.
+    double q[6] = {0, 0, 0, 0, 0, 0};
     const double lg = log(255.0 * (double)opac);
-    if (!(lg > 0.0)) {  // o * exp(-sigma) < 1/255 everywhere (also catches NaN opacities conservatively? no: NaN -> no cull)
-        if (opac == opac) { ecx = ecy = 1e15f; ea = ec = 1e30f; }
+    if (!(lg > 0.0)) {
+        if (opac == opac) q[5] = 1.0;  // o * exp(-sigma) < 1/255 everywhere
     } else {
         const double rho2 = 2.0 * lg * 1.002 + 1e-6;  // safety margin on the cut-off radius
         const double u0 = M[0], u1 = M[1], u2 = M[2], v0 = M[3], v1 = M[4], v2 = M[5], w0 = M[6], w1 = M[7], w2 = M[8];
@@ -68,25 +70,23 @@ pack_records_kernel(const gssdf_counts *counts, const float *__restrict__ ray_tr
         const double A0 = v1 * w2 - v2 * w1, A1 = v2 * w0 - v0 * w2, A2 = v0 * w1 - v1 * w0;  // Mv x Mw
         const double B0 = w1 * u2 - w2 * u1, B1 = w2 * u0 - w0 * u2, B2 = w0 * u1 - w1 * u0;  // Mw x Mu
         const double C0 = u1 * v2 - u2 * v1, C1 = u2 * v0 - u0 * v2, C2 = u0 * v1 - u1 * v0;  // Mu x Mv
-        // Q(p) = q00 x^2 + 2 q01 x y + q11 y^2 + 2 q02 x + 2 q12 y + q22
-        const double q00 = A0 * A0 + A1 * A1 - rho2 * A2 * A2, q01 = A0 * B0 + A1 * B1 - rho2 * A2 * B2;
-        const double q11 = B0 * B0 + B1 * B1 - rho2 * B2 * B2, q02 = A0 * C0 + A1 * C1 - rho2 * A2 * C2;
-        const double q12 = B0 * C0 + B1 * C1 - rho2 * B2 * C2, q22 = C0 * C0 + C1 * C1 - rho2 * C2 * C2;
-        const double det = q00 * q11 - q01 * q01;
-        if (q00 > 0.0 && det > 1e-30 * q00 * q00 + 1e-300) {
-            const double cx = -(q11 * q02 - q01 * q12) / det, cy = -(q00 * q12 - q01 * q02) / det;
-            const double k = q22 + q02 * cx + q12 * cy;
-            if (k < 0.0 && isfinite(cx) && isfinite(cy)) {
-                const double sc = -1.0 / (k * 1.004);  // inflate the ellipse by ~0.2 % in radius
-                const double fa = q00 * sc, fb = q01 * sc, fc = q11 * sc;
-                if (isfinite(fa) && isfinite(fb) && isfinite(fc) && fabs(cx) < 1e9 && fabs(cy) < 1e9) {
-                    ecx = (float)cx; ecy = (float)cy; ea = (float)fa * 0.9999f; eb = (float)fb; ec = (float)fc * 0.9999f;
-                }
-            }
+        // Q(p) = q0 x^2 + 2 q1 x y + q2 y^2 + 2 q3 x + 2 q4 y + q5
+        q[0] = A0 * A0 + A1 * A1 - rho2 * A2 * A2; q[1] = A0 * B0 + A1 * B1 - rho2 * A2 * B2;
+        q[2] = B0 * B0 + B1 * B1 - rho2 * B2 * B2; q[3] = A0 * C0 + A1 * C1 - rho2 * A2 * C2;
+        q[4] = B0 * C0 + B1 * C1 - rho2 * B2 * C2; q[5] = C0 * C0 + C1 * C1 - rho2 * C2 * C2;
+        const double X = extent;
+        const double sc = fmax(fmax(fmax(fabs(q[0]), 2.0 * fabs(q[1])), fabs(q[2])) * X * X,
+                               fmax(fmax(2.0 * fabs(q[3]), 2.0 * fabs(q[4])) * X, fabs(q[5])));
+        if (sc > 0.0 && isfinite(sc)) {
+#pragma unroll
+            for (int e = 0; e < 6; ++e) q[e] /= sc;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 6; ++e) q[e] = 0.0;
         }
     }
-    r[4] = make_float4(ecx, ecy, ea, eb);
-    r[5] = make_float4(ec, 0.f, 0.f, 0.f);
+    r[4] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
+    r[5] = make_float4((float)q[4], (float)q[5], 0.f, 0.f);
     if (zero_a) {
         for (int k = 0; k < zero_a_stride; ++k) zero_a[(int64_t)i * zero_a_stride + k] = 0.f;
     }
@@ -125,34 +125,59 @@ struct __align__(16) Stage {
     unsigned char mask[kBatch];   // bit w: the splat's ellipse touches warp w's 8x4 pixel block
 };
 
-// minimum over the rectangle [x0,x1]x[y0,y1] (relative to the centre) of a dx^2 + 2 b dx dy + c dy^2 is <= 1 ?
-__device__ __forceinline__ bool ellipse_hits_rect(float a, float b, float c, float dx0, float dx1, float dy0, float dy1) {
-    if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) return true;
-    float q = 3.0e38f;
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        const float dx = e ? dx1 : dx0;
-        const float dy = fminf(fmaxf(-b * dx / c, dy0), dy1);  // NaN (c == 0: culling disabled) falls through to dy0/dy1
-        q = fminf(q, a * dx * dx + 2.f * b * dx * dy + c * dy * dy);
-        const float ey = e ? dy1 : dy0;
-        const float ex = fminf(fmaxf(-b * ey / a, dx0), dx1);
-        q = fminf(q, a * ex * ex + 2.f * b * ex * ey + c * ey * ey);
-    }
-    return q <= 1.f;
+// Conic in tile-local pixel coordinates: Q(x,y) = a x^2 + 2 b x y + c y^2 + 2 d x + 2 e y + f
+struct Conic { float a, b, c, d, e, f; };
+
+__device__ __forceinline__ float conic_eval(const Conic &q, float x, float y) {
+    return (q.a * x + 2.f * (q.b * y + q.d)) * x + (q.c * y + 2.f * q.e) * y + q.f;
 }
 
-// 8-bit warp mask of record t for the tile whose first pixel centre is (ox, oy)
+// minimum of Q over the rectangle [x0,x1] x [y0,y1] (any conic type): corners, edge critical points, interior
+// critical point. Exact up to fp32 rounding, which the caller's tolerance absorbs.
+__device__ __forceinline__ float conic_min_rect(const Conic &q, float x0, float x1, float y0, float y1) {
+    float m = fminf(fminf(conic_eval(q, x0, y0), conic_eval(q, x1, y0)), fminf(conic_eval(q, x0, y1), conic_eval(q, x1, y1)));
+    if (q.c > 0.f) {  // edges x = const: minimise over y
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const float xe = s ? x1 : x0;
+            const float ys = -(q.b * xe + q.e) / q.c;
+            if (ys > y0 && ys < y1) m = fminf(m, conic_eval(q, xe, ys));
+        }
+    }
+    if (q.a > 0.f) {  // edges y = const: minimise over x
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const float ye = s ? y1 : y0;
+            const float xs = -(q.b * ye + q.d) / q.a;
+            if (xs > x0 && xs < x1) m = fminf(m, conic_eval(q, xs, ye));
+        }
+    }
+    const float det = q.a * q.c - q.b * q.b;
+    if (q.a > 0.f && det > 0.f) {  // interior minimum (ellipse centre)
+        const float cx = -(q.c * q.d - q.b * q.e) / det, cy = -(q.a * q.e - q.b * q.d) / det;
+        if (cx > x0 && cx < x1 && cy > y0 && cy < y1) m = fminf(m, conic_eval(q, cx, cy));
+    }
+    return m;
+}
+
+// 8-bit warp mask of record t for the tile whose first pixel centre is (ox, oy) (global pixel coordinates)
 __device__ __forceinline__ unsigned cull_mask(const float4 *rec_t, float ox, float oy) {
-    const float4 e0 = rec_t[4];
-    const float ec = rec_t[5].x;
-    const float cx = e0.x, cy = e0.y, a = e0.z, b = e0.w;
+    const float4 g0 = rec_t[4], g1 = rec_t[5];
+    // shift the conic to tile-local coordinates (x = ox + x')
+    Conic q;
+    q.a = g0.x; q.b = g0.y; q.c = g0.z;
+    q.d = g0.x * ox + g0.y * oy + g0.w;
+    q.e = g0.y * ox + g0.z * oy + g1.x;
+    q.f = (g0.x * ox + 2.f * (g0.y * oy + g0.w)) * ox + (g0.z * oy + 2.f * g1.x) * oy + g1.y;
+    // every term of the normalised form is <= 1 over the image: fp32 evaluation error < ~1e-6
+    const float tol = 4e-6f;
     const float m = 0.05f;  // margin in pixels
-    if (!ellipse_hits_rect(a, b, ec, ox - m - cx, ox + 15.f + m - cx, oy - m - cy, oy + 15.f + m - cy)) return 0u;
+    if (!(conic_min_rect(q, -m, 15.f + m, -m, 15.f + m) <= tol)) return 0u;
     unsigned mask = 0u;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-        const float x0 = ox + (w & 1) * 8.f, y0 = oy + (w >> 1) * 4.f;
-        if (ellipse_hits_rect(a, b, ec, x0 - m - cx, x0 + 7.f + m - cx, y0 - m - cy, y0 + 3.f + m - cy)) mask |= 1u << w;
+        const float x0 = (w & 1) * 8.f, y0 = (w >> 1) * 4.f;
+        if (conic_min_rect(q, x0 - m, x0 + 7.f + m, y0 - m, y0 + 3.f + m) <= tol) mask |= 1u << w;
     }
     return mask;
 }
@@ -647,7 +672,7 @@ extern "C" int gssdf_raster2dgs_fwd(const gssdf_raster2dgs_fwd_args *a, gssdf_st
     float4 *rec = reinterpret_cast<float4 *>(a->workspace);
     if (a->cap > 0) {
         pack_records_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(a->counts, a->ray_transforms, a->colors, a->opacities, a->normals,
-                                                              rec, a->visibilities, 1);
+                                                              rec, a->visibilities, 1, (float)max(a->image_width, a->image_height));
         GSSDF_LAUNCH_OK("pack_records_kernel");
     }
     if (a->prof_start) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_start, st));
@@ -677,7 +702,7 @@ extern "C" int gssdf_raster2dgs_bwd(const gssdf_raster2dgs_bwd_args *a, gssdf_st
     float4 *rec = reinterpret_cast<float4 *>(a->workspace);
     float4 *vrec = reinterpret_cast<float4 *>(reinterpret_cast<char *>(a->workspace) + align_up((size_t)a->cap * kRecBytes, 256));
     pack_records_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(a->counts, a->ray_transforms, a->colors, a->opacities, a->normals, rec,
-                                                          reinterpret_cast<float *>(vrec), 16);
+                                                          reinterpret_cast<float *>(vrec), 16, (float)max(a->image_width, a->image_height));
     GSSDF_LAUNCH_OK("pack_records_kernel");
     const size_t smem = 2 * sizeof(BwdStage);
     if (a->prof_start) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_start, st));

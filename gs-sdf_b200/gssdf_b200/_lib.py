@@ -25,6 +25,7 @@ def parse_header(path=HEADER):
     """Returns ({struct_name: [(field, ctype)]}, {func_name: (restype, n_args)})."""
     src = _strip_comments(open(path).read())
     structs = {}
+    ctypes_structs = {}
     for m in re.finditer(r"typedef\s+struct\s+(\w+)\s*\{(.*?)\}\s*(\w+)\s*;", src, flags=re.S):
         name, body = m.group(3), m.group(2)
         fields = []
@@ -41,20 +42,20 @@ def parse_header(path=HEADER):
                     fields.append((item.lstrip("* "), C.c_void_p))
                 elif arr:
                     fields.append((arr.group(1), _SCALARS[base] * int(arr.group(2))))
+                elif base in ctypes_structs:  # nested struct by value
+                    fields.append((item, ctypes_structs[base]))
                 else:
                     fields.append((item, _SCALARS[base]))
         structs[name] = fields
+        ctypes_structs[name] = type(name, (C.Structure,), {"_fields_": fields})
     funcs = {}
-    for m in re.finditer(r"^\s*(const char \*|int|size_t)\s*(gssdf_\w+)\s*\(([^)]*)\)\s*;", src, flags=re.M):
+    for m in re.finditer(r"^\s*(const char \*|int64_t|int|size_t)\s*(gssdf_\w+)\s*\(([^)]*)\)\s*;", src, flags=re.M):
         ret, name, args = m.group(1).strip(), m.group(2), m.group(3)
         funcs[name] = (ret, args)
-    return structs, funcs
+    return structs, funcs, ctypes_structs
 
 
-_STRUCT_FIELDS, FUNCS = parse_header()
-STRUCTS = {}
-for _n, _f in _STRUCT_FIELDS.items():
-    STRUCTS[_n] = type(_n, (C.Structure,), {"_fields_": _f})
+_STRUCT_FIELDS, FUNCS, STRUCTS = parse_header()
 
 _lib = None
 
@@ -69,7 +70,7 @@ def lib():
         L = C.CDLL(SO_PATH)
         for name, (ret, _args) in FUNCS.items():
             fn = getattr(L, name)  # raises AttributeError if a declared symbol is not exported
-            fn.restype = {"int": C.c_int, "size_t": C.c_size_t, "const char *": C.c_char_p}[ret]
+            fn.restype = {"int": C.c_int, "int64_t": C.c_int64, "size_t": C.c_size_t, "const char *": C.c_char_p}[ret]
         _lib = L
     return _lib
 
@@ -97,5 +98,7 @@ def make_args(struct_name, **kw):
             raise KeyError(f"{struct_name} has no field {k}")
         if hasattr(v, "data_ptr"):  # torch tensor
             v = v.data_ptr() if v.numel() > 0 else (v.data_ptr() or None)
+        elif isinstance(v, (list, tuple)):
+            v = type(getattr(a, k))(*v)
         setattr(a, k, v)
     return a

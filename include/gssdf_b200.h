@@ -309,6 +309,59 @@ typedef struct gssdf_l1_loss_args {
 } gssdf_l1_loss_args;
 int gssdf_l1_loss(const gssdf_l1_loss_args *a, gssdf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * a9-a12  SDF branch: multiresolution hash-grid encoding + decoder MLP, first order.
+ *     Replaces LocalMap::get_sdf (include/neural_net/local_map.cpp:87-103) = EncodingMap::encoding
+ *     (encoding_map.cpp:31-60) -> TCNNEncoding::forward (TB/tcnn_binding.cpp:26-58; kernel_grid,
+ *     TCNN/include/tiny-cuda-nn/encodings/grid.h:49-212) -> torch::nn::Sequential decoder
+ *     (local_map.cpp:29-42), and its autograd backward (kernel_grid_backward / _backward_input,
+ *     grid.h:215-349; Linear/ReLU backward). One fused kernel per direction: the [n,32] features and the
+ *     [n,64] hidden activations never touch HBM (the reference round-trips 256 B/point/layer).
+ *     The fp16 rounding points of tiny-cuda-nn are reproduced (table -> half, per-corner __hfma2,
+ *     dL/dy -> half, x128 loss scale); the table gradient is accumulated in fp32 (the reference uses
+ *     non-deterministic fp16 atomics). The fp16 shadow of the table is refreshed by
+ *     gssdf_sdf_table_to_half once per optimiser step (the reference re-casts 61 MB on EVERY forward).
+ *     Decoder parameters: torch::nn::Linear order, row-major W[out,in] then bias, layer after layer.
+ *     Double backward (analytic eikonal through the encoding, grid.h:352-667) is not part of this ABI
+ *     yet: the numerical-gradient regulariser (LocalMap::get_gradient numerical branch,
+ *     local_map.cpp:110-147) is expressed with these two calls on the 6 offset points.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gssdf_sdf_net {
+    int32_t n_levels, n_features_per_level, log2_hashmap_size, base_resolution; /* 16, 2, 19, 32 */
+    float per_level_scale;                                                      /* 2.0 */
+    int32_t hidden_dim;   /* 64 (or 32) */
+    int32_t n_hidden;     /* geo_num_layer: number of hidden->hidden Linear layers (3) */
+    const void *table_half; /* [gssdf_sdf_table_params] fp16 */
+    const float *mlp;       /* [gssdf_sdf_mlp_params] fp32 */
+    float origin[3];        /* world -> unit cube: x01 = (x - origin) * inv_size + 0.5 (SubMap::xyz_to_zp1_pts, */
+    float inv_size;         /*   include/neural_net/sub_map.cpp:82-97); inv_size == 0 -> x is already in [0,1]^3 */
+} gssdf_sdf_net;
+int64_t gssdf_sdf_table_params(const gssdf_sdf_net *net);
+int64_t gssdf_sdf_mlp_params(const gssdf_sdf_net *net);
+int gssdf_sdf_table_to_half(const float *table_f32, void *table_f16, int64_t n, gssdf_stream_t stream);
+
+typedef struct gssdf_sdf_fwd_args {
+    gssdf_sdf_net net;
+    int64_t n;
+    const float *x;   /* [n,3] */
+    float *sdf;       /* [n] decoder output 0 */
+    float *y1;        /* [n] decoder output 1 (raw; isigma = 1 + softplus_100(y1) * k_bce_isigma stays in the caller) */
+    float *feat;      /* [n, L*F] encoding (fp16-exact values) or NULL */
+} gssdf_sdf_fwd_args;
+int gssdf_sdf_fwd(const gssdf_sdf_fwd_args *a, gssdf_stream_t stream);
+
+typedef struct gssdf_sdf_bwd_args {
+    gssdf_sdf_net net;
+    int64_t n;
+    const float *x;      /* [n,3] */
+    const float *v_sdf;  /* [n] */
+    const float *v_y1;   /* [n] or NULL */
+    float *table_grad;   /* [table_params] fp32 +=  or NULL */
+    float *mlp_grad;     /* [mlp_params]  fp32 +=  or NULL */
+    float *v_x;          /* [n,3] overwritten, or NULL */
+} gssdf_sdf_bwd_args;
+int gssdf_sdf_bwd(const gssdf_sdf_bwd_args *a, gssdf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

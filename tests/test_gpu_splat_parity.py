@@ -334,7 +334,7 @@ def test_kernels_vs_reference_cuda_goldens(oracle):
                             _t(ct["v_render_colors"], dev), _t(ct["v_render_depths"], dev), _t(ct["v_render_alphas"], dev),
                             _t(ct["v_render_normals"], dev), _t(ct["v_render_median"], dev), go, cabi.Workspace(dev))
         for k in ("v_ray_transforms", "v_colors", "v_opacities", "v_normals"):
-            noise = rel_l2(d[k + "_run2"], d[k])
+            noise = rel_l2(d[k + "_run2"], d[k]) if (k + "_run2") in d else 0.0
             err = rel_l2(_np(go[k]), d[k])
             assert err <= max(3 * noise, 2e-4), f"raster bwd {k}: rel L2 {err:.2e} vs reference (its run-to-run spread {noise:.2e})"
         assert rel_l2(_np(go["v_densify"]), d["v_densify"]) < 5e-2
