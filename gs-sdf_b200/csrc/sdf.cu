@@ -1,0 +1,589 @@
+// a9-a12 (first order): fused multiresolution hash-grid encoding + SDF decoder MLP, forward and backward.
+//
+// Reference behaviour (TCNN = submodules/tcnn_binding/submodules/tiny-cuda-nn, TB = submodules/tcnn_binding/tcnn_binding):
+//   LocalMap::get_sdf                 include/neural_net/local_map.cpp:87-103
+//   EncodingMap::encoding             include/neural_net/encoding_map.cpp:31-60  (Grid/Hash, L16 F2 T2^19, base 32, x2, Linear)
+//   TCNNModule::forward/backward      TB/tcnn_binding.cpp:26-58,94-149 (table -> half per call, half output, x128 loss scale)
+//   kernel_grid / _backward / _backward_input   TCNN/include/tiny-cuda-nn/encodings/grid.h:49-349
+//   hash / index / scale helpers      TCNN/include/tiny-cuda-nn/common_device.h:631-655,690-718,842-855
+//   decoder torch::nn::Sequential     local_map.cpp:29-42 (Linear+ReLU x (1+geo_num_layer), Linear -> 2)
+//
+// B200-first design: ONE kernel per direction. A CTA owns a tile of points; the 32 encoded features and
+// every 64-wide hidden activation live in shared memory only (the reference writes/reads [n,32] half +
+// [n,64] fp32 per layer through HBM and launches >= 12 kernels per get_sdf). The fp16 table (30.5 MB) is
+// L2-resident on B200 (126 MB L2); the fp32 master is cast to its fp16 shadow once per optimiser step, not on
+// every forward. The backward kernel is persistent (grid = k x SMs): decoder weight gradients are accumulated
+// in REGISTERS across all tiles of a CTA and flushed once (a few million REDs per call instead of 15 k per tile).
+// tiny-cuda-nn's fp16 rounding points are reproduced: table in half, per-corner __hfma2 accumulation,
+// dL/dy -> half, x128, per-corner half product. Deviation: the table gradient accumulates in fp32 RED
+// (the reference: fp16 atomics). MLP arithmetic is fp32 FMA on the CUDA cores in this round (the tcgen05
+// path is the next step).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace gssdf {
+
+constexpr int kSdfThreads = 256;
+constexpr int kMaxLevels = 16;
+constexpr int kFeat = 32;  // n_levels * n_features_per_level supported by the fused kernels (16 x 2)
+
+struct GridGeom {
+    int L;
+    uint32_t offset[kMaxLevels + 1];  // in table entries (x F for params)
+    float scale[kMaxLevels];
+    uint32_t res[kMaxLevels];
+};
+
+static inline float h_grid_scale(uint32_t level, float log2_pls, uint32_t base) { return exp2f(level * log2_pls) * base - 1.0f; }
+
+static GridGeom make_grid(const gssdf_sdf_net &net) {  // grid.h:692-716
+    GridGeom g;
+    g.L = net.n_levels;
+    uint32_t off = 0;
+    const float l2 = log2f(net.per_level_scale);
+    for (int i = 0; i < net.n_levels && i < kMaxLevels; ++i) {
+        g.scale[i] = h_grid_scale(i, l2, net.base_resolution);
+        g.res[i] = (uint32_t)ceilf(g.scale[i]) + 1;
+        const uint32_t max_params = 0xffffffffu / 2;
+        uint32_t p = powf((float)g.res[i], 3) > (float)max_params ? max_params : g.res[i] * g.res[i] * g.res[i];
+        p = (p + 7u) / 8u * 8u;
+        const uint32_t cap = 1u << net.log2_hashmap_size;
+        if (p > cap) p = cap;
+        g.offset[i] = off;
+        off += p;
+    }
+    g.offset[net.n_levels] = off;
+    return g;
+}
+
+__device__ __forceinline__ uint32_t grid_index(uint32_t hashmap_size, uint32_t res, uint32_t x, uint32_t y, uint32_t z) {
+    // common_device.h:690-707 with the coherent prime hash (:650-655)
+    uint32_t stride = 1, index = 0;
+    if (stride <= hashmap_size) { index += x * stride; stride *= res; }
+    if (stride <= hashmap_size) { index += y * stride; stride *= res; }
+    if (stride <= hashmap_size) { index += z * stride; stride *= res; }
+    if (hashmap_size < stride) index = x ^ (y * 2654435761u) ^ (z * 805459861u);
+    return index % hashmap_size;
+}
+
+struct LevelPos {
+    float pos[3];
+    uint32_t pg[3];
+};
+
+__device__ __forceinline__ LevelPos level_pos(const float x[3], float scale) {  // pos_fract, common_device.h:842-855
+    LevelPos p;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float v = fmaf(scale, x[d], 0.5f);
+        const float t = floorf(v);
+        p.pg[d] = (uint32_t)(int)t;
+        p.pos[d] = v - t;
+    }
+    return p;
+}
+
+// one (point, level): the two features, accumulated exactly like kernel_grid<__half>: result = hfma2((half)w, val, result)
+__device__ __forceinline__ float2 encode_level(const __half2 *__restrict__ table, const GridGeom &g, int lvl, const float x[3]) {
+    const __half2 *t = table + g.offset[lvl];
+    const uint32_t hs = g.offset[lvl + 1] - g.offset[lvl];
+    const LevelPos p = level_pos(x, g.scale[lvl]);
+    __half2 vals[8];
+    float w[8];
+#pragma unroll
+    for (int idx = 0; idx < 8; ++idx) {  // issue the 8 gathers first (independent loads in flight)
+        float wt = 1.f;
+        uint32_t c[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if ((idx & (1 << d)) == 0) { wt *= 1.f - p.pos[d]; c[d] = p.pg[d]; }
+            else { wt *= p.pos[d]; c[d] = p.pg[d] + 1; }
+        }
+        w[idx] = wt;
+        vals[idx] = __ldg(t + grid_index(hs, g.res[lvl], c[0], c[1], c[2]));
+    }
+    __half2 r = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+    for (int idx = 0; idx < 8; ++idx) r = __hfma2(__float2half2_rn(w[idx]), vals[idx], r);
+    return __half22float2(r);
+}
+
+// backward of one (point, level): scatter the table gradient (optional) and return dL/dx contribution (optional)
+__device__ __forceinline__ void encode_level_bwd(const __half2 *__restrict__ table, float *__restrict__ table_grad, const GridGeom &g,
+                                                 int lvl, const float x[3], float g0, float g1, bool want_dx, float dx[3]) {
+    const uint32_t hs = g.offset[lvl + 1] - g.offset[lvl];
+    const LevelPos p = level_pos(x, g.scale[lvl]);
+    // binding rounding points: dL/dy -> half, x128 in half (TB/tcnn_binding.cpp:133)
+    const __half2 gh = __hmul2(__floats2half2_rn(g0, g1), __float2half2_rn(128.f));
+    if (table_grad) {
+        float *tg = table_grad + 2 * (size_t)g.offset[lvl];
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) {
+            float wt = 1.f;
+            uint32_t c[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if ((idx & (1 << d)) == 0) { wt *= 1.f - p.pos[d]; c[d] = p.pg[d]; }
+                else { wt *= p.pos[d]; c[d] = p.pg[d] + 1; }
+            }
+            const float2 v = __half22float2(__hmul2(__float2half2_rn(wt), gh));  // (GRAD_T)weight * grad, grid.h:247
+            const size_t e = 2 * (size_t)grid_index(hs, g.res[lvl], c[0], c[1], c[2]);
+            if (v.x != 0.f) atomicAdd(tg + e, v.x * (1.f / 128.f));
+            if (v.y != 0.f) atomicAdd(tg + e + 1, v.y * (1.f / 128.f));
+        }
+    }
+    if (want_dx) {  // dy_dx (grid.h:170-211) folded with kernel_grid_backward_input (:323-349)
+        const __half2 *t = table + g.offset[lvl];
+        const float2 ghf = __half22float2(gh);
+#pragma unroll
+        for (int gd = 0; gd < 3; ++gd) {
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int idx = 0; idx < 4; ++idx) {
+                float wt = g.scale[lvl];
+                uint32_t c[3];
+#pragma unroll
+                for (int nd = 0; nd < 2; ++nd) {
+                    const int d = nd >= gd ? nd + 1 : nd;
+                    if ((idx & (1 << nd)) == 0) { wt *= 1.f - p.pos[d]; c[d] = p.pg[d]; }
+                    else { wt *= p.pos[d]; c[d] = p.pg[d] + 1; }
+                }
+                c[gd] = p.pg[gd];
+                const float2 l = __half22float2(__ldg(t + grid_index(hs, g.res[lvl], c[0], c[1], c[2])));
+                c[gd] = p.pg[gd] + 1;
+                const float2 r = __half22float2(__ldg(t + grid_index(hs, g.res[lvl], c[0], c[1], c[2])));
+                acc0 += wt * (r.x - l.x);
+                acc1 += wt * (r.y - l.y);
+            }
+            dx[gd] = (ghf.x * acc0 + ghf.y * acc1) * (1.f / 128.f);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) table_to_half_kernel(const float *__restrict__ in, __half *__restrict__ out, int64_t n) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4 *>(in + i);
+        reinterpret_cast<__half2 *>(out + i)[0] = __floats2half2_rn(v.x, v.y);
+        reinterpret_cast<__half2 *>(out + i)[1] = __floats2half2_rn(v.z, v.w);
+    } else {
+        for (int64_t k = i; k < n; ++k) out[k] = __float2half_rn(in[k]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory MLP pieces. Activations: s_act[p][HID + 1] (row padded). Weights of one layer are
+// staged transposed and padded: s_w[k][HID + 4]  (k = input index), bias in s_b[HID].
+// ---------------------------------------------------------------------------------------------
+template <int HID>
+struct MlpShape {
+    static constexpr int AP = HID + 4;   // activation row pitch (float4 aligned)
+    static constexpr int WP = HID + 4;   // transposed-weight row pitch (float4 aligned)
+};
+
+// stage W[out=O][in=K] (row-major, global) transposed into s_w[k][WP]; bias into s_b
+template <int HID>
+__device__ __forceinline__ void stage_weights(const float *__restrict__ W, int O, int K, float *s_w, float *s_b) {
+    constexpr int WP = MlpShape<HID>::WP;
+    for (int e = threadIdx.x; e < O * K; e += kSdfThreads) {
+        const int o = e / K, k = e % K;
+        s_w[k * WP + o] = __ldg(W + e);
+    }
+    for (int o = threadIdx.x; o < O; o += kSdfThreads) s_b[o] = __ldg(W + (size_t)O * K + o);
+}
+
+// stage W[out=O][in=K] as is: s_w[o * K + k]
+__device__ __forceinline__ void stage_weights_plain(const float *__restrict__ W, int O, int K, float *s_w) {
+    for (int e = threadIdx.x; e < O * K; e += kSdfThreads) s_w[e] = __ldg(W + e);
+}
+
+// out[p][o] = act(sum_k in[p][k] * W[o][k] + b[o]) for a tile of TM points, O == HID outputs
+template <int HID, int TM, bool RELU>
+__device__ __forceinline__ void dense_layer(const float *s_in, int K, const float *s_w, const float *s_b, float *s_out) {
+    constexpr int AP = MlpShape<HID>::AP, WP = MlpShape<HID>::WP;
+    constexpr int TX = HID / 4, TY = kSdfThreads / TX, PPT = TM / TY;
+    static_assert(PPT >= 1 && PPT * TY == TM, "tile shape");
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    float acc[PPT][4];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[j][q] = s_b[tx * 4 + q];
+    for (int k = 0; k < K; ++k) {
+        const float4 w = *reinterpret_cast<const float4 *>(s_w + k * WP + tx * 4);
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const float a = s_in[(ty * PPT + j) * AP + k];
+            acc[j][0] = fmaf(a, w.x, acc[j][0]);
+            acc[j][1] = fmaf(a, w.y, acc[j][1]);
+            acc[j][2] = fmaf(a, w.z, acc[j][2]);
+            acc[j][3] = fmaf(a, w.w, acc[j][3]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < PPT; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float v = acc[j][q];
+            if (RELU) v = fmaxf(v, 0.f);
+            s_out[(ty * PPT + j) * AP + tx * 4 + q] = v;
+        }
+}
+
+__device__ __forceinline__ void load_x(const gssdf_sdf_net &net, const float *__restrict__ x, int64_t i, float out[3]) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float v = __ldg(x + 3 * i + d);
+        out[d] = net.inv_size != 0.f ? (v - net.origin[d]) * net.inv_size + 0.5f : v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int HID>
+__global__ void __launch_bounds__(kSdfThreads)
+sdf_fwd_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
+    constexpr int TM = 128;
+    constexpr int AP = MlpShape<HID>::AP, WP = MlpShape<HID>::WP;
+    extern __shared__ __align__(16) float s_mem[];
+    float *s_a = s_mem;                 // [TM][AP]
+    float *s_b2 = s_a + TM * AP;        // [TM][AP]
+    float *s_w = s_b2 + TM * AP;        // [max(K)][WP]
+    float *s_bias = s_w + 64 * WP;      // [HID]
+    const int64_t base = (int64_t)blockIdx.x * TM;
+    const int tm = (int)min((int64_t)TM, a.n - base);
+    const __half2 *table = reinterpret_cast<const __half2 *>(a.net.table_half);
+    // 1. encode: (point, level) tasks; consecutive threads -> consecutive points of one level
+    for (int task = threadIdx.x; task < TM * g.L; task += kSdfThreads) {
+        const int p = task % TM, lvl = task / TM;
+        float2 f = make_float2(0.f, 0.f);
+        if (p < tm) {
+            float x[3];
+            load_x(a.net, a.x, base + p, x);
+            f = encode_level(table, g, lvl, x);
+            if (a.feat) { a.feat[(base + p) * kFeat + 2 * lvl] = f.x; a.feat[(base + p) * kFeat + 2 * lvl + 1] = f.y; }
+        }
+        s_a[p * AP + 2 * lvl] = f.x;
+        s_a[p * AP + 2 * lvl + 1] = f.y;
+    }
+    // 2. hidden layers
+    const float *W = a.net.mlp;
+    int K = kFeat;
+    float *in = s_a, *out = s_b2;
+    for (int l = 0; l < 1 + a.net.n_hidden; ++l) {
+        __syncthreads();
+        stage_weights<HID>(W, HID, K, s_w, s_bias);
+        __syncthreads();
+        dense_layer<HID, TM, true>(in, K, s_w, s_bias, out);
+        W += (size_t)HID * K + HID;
+        K = HID;
+        float *t = in; in = out; out = t;
+    }
+    __syncthreads();
+    // 3. output layer HID -> 2 : one thread per (point, output)
+    {
+        const int p = threadIdx.x >> 1, o = threadIdx.x & 1;
+        if (p < tm) {
+            float s = __ldg(W + 2 * HID + o);
+            const float *w = W + o * HID;
+#pragma unroll 8
+            for (int k = 0; k < HID; ++k) s = fmaf(in[p * AP + k], __ldg(w + k), s);
+            if (o == 0) a.sdf[base + p] = s;
+            else if (a.y1) a.y1[base + p] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward (persistent): recompute forward for a 64-point tile keeping every activation in shared memory,
+// back-propagate, accumulate dW in registers across tiles, scatter table grads, write v_x.
+// ---------------------------------------------------------------------------------------------
+template <int HID>
+__global__ void __launch_bounds__(kSdfThreads)
+sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
+    constexpr int TM = 64;
+    constexpr int AP = MlpShape<HID>::AP, WP = MlpShape<HID>::WP;
+    constexpr int NL = 5;  // up to 1 + 4 hidden activations kept
+    extern __shared__ __align__(16) float s_mem[];
+    float *s_feat = s_mem;                       // [TM][kFeat+1]
+    float *s_act = s_feat + TM * (kFeat + 1);    // [NL][TM][AP]
+    float *s_g = s_act + NL * TM * AP;           // [TM][AP] current gradient
+    float *s_g2 = s_g + TM * AP;                 // [TM][AP] next gradient
+    float *s_w = s_g2 + TM * AP;                 // [64][WP]
+    float *s_bias = s_w + 64 * WP;               // [HID]
+    float *s_dx = s_bias + HID;                  // [TM][3]
+    const int nh = 1 + a.net.n_hidden;           // number of HID-wide layers
+    const __half2 *table = reinterpret_cast<const __half2 *>(a.net.table_half);
+
+    // register accumulators of the weight gradients: thread owns rows o = tx*4..+3? -> use [4][KPT] blocks:
+    // layer l (HID x K): thread (ox = t % 16 -> outputs ox*HID/16.., kx = t / 16 -> inputs kx*K/16..)
+    constexpr int OB = HID / 16;     // outputs per thread
+    float dW0[OB][kFeat / 16];       // first layer: HID x 32
+    float dWh[4][OB][HID / 16];      // hidden layers: HID x HID
+    float dB[NL][OB];                // biases (only threads with kx == 0 use them)
+#pragma unroll
+    for (int i = 0; i < OB; ++i) {
+#pragma unroll
+        for (int j = 0; j < kFeat / 16; ++j) dW0[i][j] = 0.f;
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+#pragma unroll
+            for (int j = 0; j < HID / 16; ++j) dWh[l][i][j] = 0.f;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) dB[l][i] = 0.f;
+    }
+    float dWout = 0.f, dBout = 0.f;  // output layer: thread t < 2*HID owns W_out[t / HID][t % HID]; t < 2 owns b_out[t]
+    const int ox = threadIdx.x % 16, kx = threadIdx.x / 16;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * TM;
+        const int tm = (int)min((int64_t)TM, a.n - base);
+        __syncthreads();
+        // 1. encode
+        for (int task = threadIdx.x; task < TM * g.L; task += kSdfThreads) {
+            const int p = task % TM, lvl = task / TM;
+            float2 f = make_float2(0.f, 0.f);
+            if (p < tm) {
+                float x[3];
+                load_x(a.net, a.x, base + p, x);
+                f = encode_level(table, g, lvl, x);
+            }
+            s_feat[p * (kFeat + 1) + 2 * lvl] = f.x;
+            s_feat[p * (kFeat + 1) + 2 * lvl + 1] = f.y;
+        }
+        // 2. forward, keeping activations. dense_layer expects pitch AP for its input: copy features into s_g (scratch)
+        __syncthreads();
+        for (int e = threadIdx.x; e < TM * kFeat; e += kSdfThreads) s_g[(e / kFeat) * AP + e % kFeat] = s_feat[(e / kFeat) * (kFeat + 1) + e % kFeat];
+        const float *W = a.net.mlp;
+        {
+            int K = kFeat;
+            const float *in = s_g;
+            for (int l = 0; l < nh; ++l) {
+                __syncthreads();
+                stage_weights<HID>(W, HID, K, s_w, s_bias);
+                __syncthreads();
+                dense_layer<HID, TM, true>(in, K, s_w, s_bias, s_act + l * TM * AP);
+                W += (size_t)HID * K + HID;
+                K = HID;
+                in = s_act + l * TM * AP;
+            }
+        }
+        __syncthreads();
+        // 3. output layer backward: g_last[p][k] = (v_sdf W_out[0][k] + v_y1 W_out[1][k]) * relu'(a_last)
+        const float *Wout = W;  // [2][HID] then bias[2]
+        const float *a_last = s_act + (nh - 1) * TM * AP;
+        for (int e = threadIdx.x; e < TM * HID; e += kSdfThreads) {
+            const int p = e / HID, k = e % HID;
+            float gv = 0.f;
+            if (p < tm) {
+                const float v0 = __ldg(a.v_sdf + base + p), v1 = a.v_y1 ? __ldg(a.v_y1 + base + p) : 0.f;
+                gv = v0 * __ldg(Wout + k) + v1 * __ldg(Wout + HID + k);
+                if (!(a_last[p * AP + k] > 0.f)) gv = 0.f;
+            }
+            s_g[p * AP + k] = gv;
+        }
+        if (a.mlp_grad && threadIdx.x < 2 * HID) {  // dW_out, db_out
+            const int o = threadIdx.x / HID, k = threadIdx.x % HID;
+            float s = 0.f, sb = 0.f;
+            for (int p = 0; p < tm; ++p) {
+                const float v = o == 0 ? __ldg(a.v_sdf + base + p) : (a.v_y1 ? __ldg(a.v_y1 + base + p) : 0.f);
+                s = fmaf(v, a_last[p * AP + k], s);
+                sb += v;
+            }
+            dWout += s;
+            if (k == 0) dBout += sb;
+        }
+        __syncthreads();
+        // 4. hidden layers, last to first. gcur holds dL/d(pre-activation of layer l) (ReLU mask already applied).
+        //    The loop is fully unrolled with a compile-time layer index so the dW accumulators stay in registers.
+        float *gcur = s_g, *gnext = s_g2;
+#pragma unroll
+        for (int l = 4; l >= 0; --l) {
+            if (l < nh) {
+                const int K = l == 0 ? kFeat : HID;
+                const float *Wl = a.net.mlp;
+                for (int q = 0; q < l; ++q) Wl += (size_t)HID * (q == 0 ? kFeat : HID) + HID;
+                const float *a_prev = l == 0 ? nullptr : s_act + (l - 1) * TM * AP;
+                // 4a. dW_l[o][k] += sum_p g[p][o] * a_prev[p][k] ; thread owns an OB x (K/16) block
+                if (a.mlp_grad) {
+                    for (int p = 0; p < tm; ++p) {
+                        float gv[OB];
+#pragma unroll
+                        for (int i = 0; i < OB; ++i) gv[i] = gcur[p * AP + ox * OB + i];
+                        if (l == 0) {
+#pragma unroll
+                            for (int j = 0; j < kFeat / 16; ++j) {
+                                const float av = s_feat[p * (kFeat + 1) + kx * (kFeat / 16) + j];
+#pragma unroll
+                                for (int i = 0; i < OB; ++i) dW0[i][j] = fmaf(gv[i], av, dW0[i][j]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < HID / 16; ++j) {
+                                const float av = a_prev[p * AP + kx * (HID / 16) + j];
+#pragma unroll
+                                for (int i = 0; i < OB; ++i) dWh[l > 0 ? l - 1 : 0][i][j] = fmaf(gv[i], av, dWh[l > 0 ? l - 1 : 0][i][j]);
+                            }
+                        }
+                        if (kx == 0) {
+#pragma unroll
+                            for (int i = 0; i < OB; ++i) dB[l][i] += gv[i];
+                        }
+                    }
+                }
+                // 4b. g_prev[p][k] = sum_o g[p][o] W_l[o][k] (* relu'(a_prev)); W_l staged as is (consecutive k -> no conflicts)
+                __syncthreads();
+                stage_weights_plain(Wl, HID, K, s_w);
+                __syncthreads();
+                for (int e = threadIdx.x; e < TM * K; e += kSdfThreads) {
+                    const int p = e / K, k = e % K;
+                    float sacc = 0.f;
+#pragma unroll 8
+                    for (int o = 0; o < HID; ++o) sacc = fmaf(gcur[p * AP + o], s_w[o * K + k], sacc);
+                    if (l > 0 && !(a_prev[p * AP + k] > 0.f)) sacc = 0.f;
+                    gnext[p * AP + k] = sacc;
+                }
+                __syncthreads();
+                float *t = gcur; gcur = gnext; gnext = t;
+            }
+        }
+        // 5. gcur[p][0..31] = dL/dfeat -> table gradient + dL/dx
+        for (int e = threadIdx.x; e < TM * 3; e += kSdfThreads) s_dx[e] = 0.f;
+        __syncthreads();
+        for (int task = threadIdx.x; task < TM * g.L; task += kSdfThreads) {
+            const int p = task % TM, lvl = task / TM;
+            if (p < tm) {
+                float x[3], dx[3] = {0.f, 0.f, 0.f};
+                load_x(a.net, a.x, base + p, x);
+                encode_level_bwd(table, a.table_grad, g, lvl, x, gcur[p * AP + 2 * lvl], gcur[p * AP + 2 * lvl + 1], a.v_x != nullptr, dx);
+                if (a.v_x) {
+                    atomicAdd(&s_dx[p * 3 + 0], dx[0]);
+                    atomicAdd(&s_dx[p * 3 + 1], dx[1]);
+                    atomicAdd(&s_dx[p * 3 + 2], dx[2]);
+                }
+            }
+        }
+        __syncthreads();
+        if (a.v_x)
+            for (int e = threadIdx.x; e < tm * 3; e += kSdfThreads)
+                a.v_x[base * 3 + e] = s_dx[e] * (a.net.inv_size != 0.f ? a.net.inv_size : 1.f);
+    }
+    // flush the register-resident weight gradients (one RED per parameter per CTA)
+    if (a.mlp_grad) {
+        float *G = a.mlp_grad;
+#pragma unroll
+        for (int l = 0; l < 5; ++l) {
+            if (l < nh) {
+                const int K = l == 0 ? kFeat : HID;
+                const int KB = K / 16;
+#pragma unroll
+                for (int i = 0; i < OB; ++i) {
+                    const int o = ox * OB + i;
+                    if (l == 0) {
+#pragma unroll
+                        for (int j = 0; j < kFeat / 16; ++j) atomicAdd(G + (size_t)o * K + kx * KB + j, dW0[i][j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < HID / 16; ++j) atomicAdd(G + (size_t)o * K + kx * KB + j, dWh[l > 0 ? l - 1 : 0][i][j]);
+                    }
+                    if (kx == 0) atomicAdd(G + (size_t)HID * K + o, dB[l][i]);
+                }
+                G += (size_t)HID * K + HID;
+            }
+        }
+        if (threadIdx.x < 2 * HID) atomicAdd(G + threadIdx.x, dWout);
+        if (threadIdx.x < 2 * HID && threadIdx.x % HID == 0) atomicAdd(G + 2 * HID + threadIdx.x / HID, dBout);
+    }
+}
+
+template <int HID>
+static size_t fwd_smem() { return sizeof(float) * (2 * 128 * MlpShape<HID>::AP + 64 * MlpShape<HID>::WP + HID); }
+template <int HID>
+static size_t bwd_smem() {
+    return sizeof(float) * (64 * (kFeat + 1) + 5 * 64 * MlpShape<HID>::AP + 2 * 64 * MlpShape<HID>::AP + 64 * MlpShape<HID>::WP + HID + 64 * 3);
+}
+
+}  // namespace gssdf
+
+using namespace gssdf;
+
+static int check_net(const char *who, const gssdf_sdf_net &net) {
+    GSSDF_REQUIRE(net.n_levels == 16 && net.n_features_per_level == 2, GSSDF_EUNSUPPORTED,
+                  "%s: the fused SDF kernels support n_levels 16 x n_features_per_level 2 (config/base.yaml:8-9), got %d x %d", who,
+                  net.n_levels, net.n_features_per_level);
+    GSSDF_REQUIRE(net.hidden_dim == 64 || net.hidden_dim == 32, GSSDF_EUNSUPPORTED, "%s: hidden_dim %d not in {32, 64}", who, net.hidden_dim);
+    GSSDF_REQUIRE(net.n_hidden >= 0 && net.n_hidden <= 4, GSSDF_EUNSUPPORTED, "%s: n_hidden %d not in [0,4]", who, net.n_hidden);
+    GSSDF_REQUIRE(net.log2_hashmap_size >= 8 && net.log2_hashmap_size <= 24 && net.base_resolution > 0 && net.per_level_scale > 1.f,
+                  GSSDF_EINVAL, "%s: bad grid configuration", who);
+    GSSDF_REQUIRE(net.table_half && net.mlp, GSSDF_EINVAL, "%s: table_half and mlp must be non-null", who);
+    return GSSDF_OK;
+}
+
+extern "C" int64_t gssdf_sdf_table_params(const gssdf_sdf_net *net) {
+    if (!net || net->n_levels <= 0 || net->n_levels > kMaxLevels) return -1;
+    const GridGeom g = make_grid(*net);
+    return (int64_t)g.offset[net->n_levels] * net->n_features_per_level;
+}
+
+extern "C" int64_t gssdf_sdf_mlp_params(const gssdf_sdf_net *net) {
+    if (!net) return -1;
+    const int64_t in = (int64_t)net->n_levels * net->n_features_per_level, h = net->hidden_dim;
+    return (in * h + h) + (int64_t)net->n_hidden * (h * h + h) + (2 * h + 2);
+}
+
+extern "C" int gssdf_sdf_table_to_half(const float *table_f32, void *table_f16, int64_t n, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(n >= 0, GSSDF_EINVAL, "sdf_table_to_half: negative size");
+    if (n == 0) return GSSDF_OK;
+    GSSDF_REQUIRE(table_f32 && table_f16, GSSDF_EINVAL, "sdf_table_to_half: null pointer");
+    table_to_half_kernel<<<cdiv(cdiv(n, 4), 256), 256, 0, (cudaStream_t)stream>>>(table_f32, reinterpret_cast<__half *>(table_f16), n);
+    GSSDF_LAUNCH_OK("table_to_half_kernel");
+    return GSSDF_OK;
+}
+
+extern "C" int gssdf_sdf_fwd(const gssdf_sdf_fwd_args *a, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "sdf_fwd: null args");
+    int rc = check_net("sdf_fwd", a->net);
+    if (rc) return rc;
+    GSSDF_REQUIRE(a->n >= 0, GSSDF_EINVAL, "sdf_fwd: negative n");
+    if (a->n == 0) return GSSDF_OK;
+    GSSDF_REQUIRE(a->x && a->sdf, GSSDF_EINVAL, "sdf_fwd: x and sdf must be non-null");
+    const GridGeom g = make_grid(a->net);
+    const int grid = cdiv(a->n, 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->net.hidden_dim == 64) {
+        GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
+        sdf_fwd_kernel<64><<<grid, kSdfThreads, fwd_smem<64>(), st>>>(*a, g);
+    } else {
+        GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<32>()));
+        sdf_fwd_kernel<32><<<grid, kSdfThreads, fwd_smem<32>(), st>>>(*a, g);
+    }
+    GSSDF_LAUNCH_OK("sdf_fwd_kernel");
+    return GSSDF_OK;
+}
+
+extern "C" int gssdf_sdf_bwd(const gssdf_sdf_bwd_args *a, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "sdf_bwd: null args");
+    int rc = check_net("sdf_bwd", a->net);
+    if (rc) return rc;
+    GSSDF_REQUIRE(a->n >= 0, GSSDF_EINVAL, "sdf_bwd: negative n");
+    if (a->n == 0) return GSSDF_OK;
+    GSSDF_REQUIRE(a->x && a->v_sdf, GSSDF_EINVAL, "sdf_bwd: x and v_sdf must be non-null");
+    const GridGeom g = make_grid(a->net);
+    const int64_t n_tiles = (a->n + 63) / 64;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sms * 1);  // persistent: one CTA per SM (176 KB of shared memory each)
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->net.hidden_dim == 64) {
+        GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<64>()));
+        sdf_bwd_kernel<64><<<grid, kSdfThreads, bwd_smem<64>(), st>>>(*a, g, n_tiles);
+    } else {
+        GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<32>()));
+        sdf_bwd_kernel<32><<<grid, kSdfThreads, bwd_smem<32>(), st>>>(*a, g, n_tiles);
+    }
+    GSSDF_LAUNCH_OK("sdf_bwd_kernel");
+    return GSSDF_OK;
+}

@@ -166,3 +166,36 @@ def l1_loss(Cn, W, H, out_colors, gt, w_rgb, w_depth, loss_out, v_out_colors):
     a = make_args("gssdf_l1_loss_args", C=Cn, image_width=W, image_height=H, out_colors=out_colors, gt=gt, w_rgb=w_rgb,
                   w_depth=w_depth, loss_out=loss_out, v_out_colors=v_out_colors)
     check(lib().gssdf_l1_loss(_lib.C.byref(a), _stream()))
+
+
+# ---- SDF branch -------------------------------------------------------------------------------
+def sdf_net(table_half, mlp, n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=2.0,
+            hidden_dim=64, n_hidden=3, origin=(0.0, 0.0, 0.0), inv_size=0.0):
+    return make_args("gssdf_sdf_net", n_levels=n_levels, n_features_per_level=n_features, log2_hashmap_size=log2_hashmap_size,
+                     base_resolution=base_resolution, per_level_scale=per_level_scale, hidden_dim=hidden_dim, n_hidden=n_hidden,
+                     table_half=table_half, mlp=mlp, origin=list(origin), inv_size=inv_size)
+
+
+def sdf_table_params(net):
+    return int(lib().gssdf_sdf_table_params(_lib.C.byref(net)))
+
+
+def sdf_mlp_params(net):
+    return int(lib().gssdf_sdf_mlp_params(_lib.C.byref(net)))
+
+
+def sdf_table_to_half(table_f32, table_f16):
+    check(lib().gssdf_sdf_table_to_half(_lib.C.c_void_p(table_f32.data_ptr()), _lib.C.c_void_p(table_f16.data_ptr()),
+                                        _lib.C.c_int64(table_f32.numel()), _stream()))
+
+
+def sdf_fwd(net, x, sdf, y1=None, feat=None):
+    a = make_args("gssdf_sdf_fwd_args", n=x.shape[0], x=x, sdf=sdf, y1=y1, feat=feat)
+    a.net = net
+    check(lib().gssdf_sdf_fwd(_lib.C.byref(a), _stream()))
+
+
+def sdf_bwd(net, x, v_sdf, v_y1=None, table_grad=None, mlp_grad=None, v_x=None):
+    a = make_args("gssdf_sdf_bwd_args", n=x.shape[0], x=x, v_sdf=v_sdf, v_y1=v_y1, table_grad=table_grad, mlp_grad=mlp_grad, v_x=v_x)
+    a.net = net
+    check(lib().gssdf_sdf_bwd(_lib.C.byref(a), _stream()))

@@ -203,3 +203,73 @@ def raster2dgs_bwd(ray_transforms, colors, opacities, normals, W, H, tile_size, 
     o["v_densify"] = vd
     o["v_means2d"] = np.zeros((nnz, 2), acc)
     return o
+
+
+# ---- SDF branch (oracle/sdf_oracle.c) ---------------------------------------------------------
+def grid_setup(L=16, F=2, log2_hashmap=19, base_res=32, per_level_scale=2.0):
+    off = np.zeros(L + 1, np.uint32)
+    lib().oracle_grid_setup.restype = C.c_int64
+    n = lib().oracle_grid_setup(C.c_int(L), C.c_int(F), C.c_int(log2_hashmap), C.c_int(base_res), C.c_float(per_level_scale), _p(off))
+    return int(n), off
+
+
+def f32_to_f16_bits(x):
+    x = _f32(x).reshape(-1)
+    out = np.zeros(x.shape, np.uint16)
+    lib().oracle_f32_to_f16_bits(C.c_int64(len(x)), _p(x), _p(out))
+    return out
+
+
+def hashgrid_fwd(x, table, L=16, F=2, log2_hashmap=19, base_res=32, per_level_scale=2.0, want_dy_dx=False):
+    x, table = _f32(x), _f32(table)
+    n = x.shape[0]
+    feat = np.zeros((n, L * F), np.float32)
+    dy = np.zeros((n, L * F, 3), np.float32) if want_dy_dx else None
+    lib().oracle_hashgrid_fwd(C.c_int64(n), _p(x), _p(table), C.c_int(L), C.c_int(F), C.c_int(log2_hashmap), C.c_int(base_res),
+                              C.c_float(per_level_scale), _p(feat), _p(dy))
+    return (feat, dy) if want_dy_dx else feat
+
+
+def hashgrid_bwd(x, dL_dfeat, n_params, dy_dx=None, L=16, F=2, log2_hashmap=19, base_res=32, per_level_scale=2.0, want_table=True):
+    x, g = _f32(x), _f32(dL_dfeat)
+    n = x.shape[0]
+    tg = np.zeros(n_params, np.float64) if want_table else None
+    dx = np.zeros((n, 3), np.float32) if dy_dx is not None else None
+    lib().oracle_hashgrid_bwd(C.c_int64(n), _p(x), _p(g), C.c_int(L), C.c_int(F), C.c_int(log2_hashmap), C.c_int(base_res),
+                              C.c_float(per_level_scale), _p(_f32(dy_dx)) if dy_dx is not None else None, _p(tg), _p(dx))
+    return tg, dx
+
+
+def mlp_fwd(inp, widths, params):
+    inp, params = _f32(inp), _f32(params)
+    n = inp.shape[0]
+    w = np.ascontiguousarray(widths, np.int32)
+    out = np.zeros((n, widths[-1]), np.float64)
+    lib().oracle_mlp_fwd(C.c_int64(n), _p(inp), C.c_int(len(widths) - 1), _p(w), _p(params), None, _p(out))
+    return out
+
+
+def mlp_bwd(inp, widths, params, d_out):
+    inp, params = _f32(inp), _f32(params)
+    n = inp.shape[0]
+    w = np.ascontiguousarray(widths, np.int32)
+    d_out = np.ascontiguousarray(d_out, np.float64)
+    d_in = np.zeros((n, widths[0]), np.float64)
+    d_params = np.zeros(params.shape, np.float64)
+    lib().oracle_mlp_bwd(C.c_int64(n), _p(inp), C.c_int(len(widths) - 1), _p(w), _p(params), _p(d_out), _p(d_in), _p(d_params))
+    return d_in, d_params
+
+
+def sdf_fwd(x, table, mlp_params, hidden=64, n_hidden=3, **grid):
+    feat = hashgrid_fwd(x, table, **grid)
+    widths = [feat.shape[1]] + [hidden] * (1 + n_hidden) + [2]
+    y = mlp_fwd(feat, widths, mlp_params)
+    return y[:, 0], y[:, 1], feat
+
+
+def sdf_bwd(x, table, mlp_params, v_sdf, v_y1, hidden=64, n_hidden=3, **grid):
+    feat, dy = hashgrid_fwd(x, table, want_dy_dx=True, **grid)
+    widths = [feat.shape[1]] + [hidden] * (1 + n_hidden) + [2]
+    d_feat, d_mlp = mlp_bwd(feat, widths, mlp_params, np.stack([v_sdf, v_y1], 1))
+    tg, dx = hashgrid_bwd(x, d_feat.astype(np.float32), len(table), dy, **grid)
+    return tg, d_mlp, dx

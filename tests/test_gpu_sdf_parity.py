@@ -1,0 +1,89 @@
+"""GPU parity of the SDF branch (fused hash-grid + decoder MLP, first order) vs the CPU oracle.
+Features are compared EXACTLY (they are fp16 values produced with the same rounding points); the fp32 MLP
+outputs and all gradients at 1e-4 relative to the fp64 oracle chain (with an fp32 absolute floor)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from helpers import assert_close_frac  # noqa: E402
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _mlp(rng, hidden, n_hidden, in_dim=32):
+    dims = [in_dim] + [hidden] * (1 + n_hidden) + [2]
+    ps = []
+    for k, o in zip(dims[:-1], dims[1:]):
+        b = 1 / np.sqrt(k)
+        ps += [rng.uniform(-b, b, o * k), rng.uniform(-b, b, o)]
+    return np.concatenate(ps).astype(np.float32)
+
+
+@pytest.mark.parametrize("n,hidden,n_hidden", [(5000, 64, 3), (777, 32, 1), (130, 64, 0)])
+def test_sdf_fwd_bwd(oracle, n, hidden, n_hidden):
+    from gssdf_b200 import cabi
+    dev = _dev()
+    rng = np.random.default_rng(n)
+    n_params, _ = oracle.grid_setup()
+    table = rng.uniform(-0.5, 0.5, n_params).astype(np.float32)  # U(-0.5,0.5) for parity
+    mlp = _mlp(rng, hidden, n_hidden)
+    x = rng.uniform(0.02, 0.98, (n, 3)).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    tab, half = t(table), torch.empty(n_params, dtype=torch.float16, device=dev)
+    cabi.sdf_table_to_half(tab, half)
+    assert np.array_equal(half.cpu().numpy().view(np.uint16), oracle.f32_to_f16_bits(table))
+    net = cabi.sdf_net(half, t(mlp), hidden_dim=hidden, n_hidden=n_hidden)
+    assert cabi.sdf_table_params(net) == n_params and cabi.sdf_mlp_params(net) == len(mlp)
+    sdf, y1, feat = torch.empty(n, device=dev), torch.empty(n, device=dev), torch.empty(n, 32, device=dev)
+    cabi.sdf_fwd(net, t(x), sdf, y1, feat)
+    r_sdf, r_y1, r_feat = oracle.sdf_fwd(x, table, mlp, hidden, n_hidden)
+    assert np.array_equal(feat.cpu().numpy(), r_feat), "hash-grid features must be bit-identical (fp16 rounding points)"
+    assert_close_frac(sdf.cpu().numpy(), r_sdf, 1e-4, 1e-5, 0.0, "sdf")
+    assert_close_frac(y1.cpu().numpy(), r_y1, 1e-4, 1e-5, 0.0, "y1")
+    # backward
+    v_sdf, v_y1 = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    tg, mg, vx = torch.zeros(n_params, device=dev), torch.zeros(len(mlp), device=dev), torch.empty(n, 3, device=dev)
+    cabi.sdf_bwd(net, t(x), t(v_sdf), t(v_y1), tg, mg, vx)
+    r_tg, r_mg, r_vx = oracle.sdf_bwd(x, table, mlp, v_sdf, v_y1, hidden, n_hidden)
+    assert_close_frac(mg.cpu().numpy(), r_mg, 1e-4, 1e-5 * np.abs(r_mg).max(), 0.0, "mlp grad")
+    # the cotangent reaching the encoding is rounded to fp16 (x128) in both; an fp32-vs-fp64 difference of the MLP
+    # backward can flip that rounding by one fp16 ulp (2^-11 relative) on isolated entries
+    assert_close_frac(tg.cpu().numpy(), r_tg, 2e-3, 1e-5 * np.abs(r_tg).max(), 1e-3, "table grad")
+    assert np.linalg.norm(tg.cpu().numpy() - r_tg) <= 2e-4 * np.linalg.norm(r_tg)
+    assert_close_frac(vx.cpu().numpy(), r_vx, 2e-3, 1e-4 * np.abs(r_vx).max(), 1e-3, "v_x")
+    assert np.linalg.norm(vx.cpu().numpy() - r_vx) <= 5e-4 * np.linalg.norm(r_vx)
+
+
+def test_sdf_mirror_api_autograd_and_numerical_gradient(oracle):
+    from gssdf_b200 import sdf as sdfmod
+    dev = _dev()
+    net = sdfmod.SdfNet(dev, map_size=14.0, origin=(0.5, -0.25, 0.1))
+    with torch.no_grad():
+        net.params_.uniform_(-0.5, 0.5)
+    xyz = (torch.rand(3000, 3, device=dev) - 0.5) * 10 + torch.tensor([0.5, -0.25, 0.1], device=dev)
+    xyz.requires_grad_(True)
+    sdf, isigma = net.get_sdf(xyz)
+    assert sdf.shape == (3000, 1) and isigma.shape == (3000, 1) and (isigma >= 1).all()
+    (sdf.square().sum() + isigma.sum()).backward()
+    assert net.params_.grad is not None and net.decoder_.grad is not None and xyz.grad is not None
+    assert torch.isfinite(net.params_.grad).all() and net.params_.grad.abs().sum() > 0
+    x01 = ((xyz.detach().cpu().numpy() - np.array([0.5, -0.25, 0.1], np.float32)) / 14.0 + 0.5).astype(np.float32)
+    r_sdf, _, _ = oracle.sdf_fwd(x01, net.params_.detach().cpu().numpy(), net.decoder_.detach().cpu().numpy())
+    assert_close_frac(sdf.detach().cpu().numpy()[:, 0], r_sdf, 2e-4, 2e-5, 2e-3, "sdf (world coords)")  # x01 rounding differs by an ulp
+    g = net.get_gradient_numerical(xyz.detach(), 0.05)
+    assert g.shape == (3000, 3) and torch.isfinite(g).all()
+
+
+def test_sdf_error_conventions():
+    from gssdf_b200 import cabi
+    dev = _dev()
+    z = torch.zeros(16, device=dev)
+    with pytest.raises(Exception, match="n_levels 16"):
+        cabi.sdf_fwd(cabi.sdf_net(z.half(), z, n_levels=8), torch.zeros(4, 3, device=dev), torch.zeros(4, device=dev))
+    cabi.sdf_fwd(cabi.sdf_net(z.half(), z), torch.zeros(0, 3, device=dev), torch.zeros(0, device=dev))  # n == 0: legal no-op

@@ -1,0 +1,101 @@
+"""CPU checks of the SDF oracle (oracle/sdf_oracle.c): fp16 emulation against numpy's IEEE binary16, grid
+geometry against the numbers SURVEY.md section 8a quotes from tiny-cuda-nn (15 269 888 parameters), the restated
+backward against finite differences. tiny-cuda-nn ships no tests, so this is the only pin (parity UNPINNED
+against reference outputs, see the file header)."""
+import numpy as np
+import pytest
+
+
+def _net(rng, hidden=64, n_hidden=3, in_dim=32):
+    dims = [in_dim] + [hidden] * (1 + n_hidden) + [2]
+    ps = []
+    for k, o in zip(dims[:-1], dims[1:]):
+        b = 1 / np.sqrt(k)
+        ps += [rng.uniform(-b, b, o * k), rng.uniform(-b, b, o)]
+    return np.concatenate(ps).astype(np.float32), dims
+
+
+def test_half_emulation_matches_ieee(oracle):
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(200000) * 10.0 ** rng.integers(-9, 6, 200000)).astype(np.float32)
+    x = np.concatenate([x, np.array([0, -0.0, 65504, 65519.9, 65520, 1e-8, 2.98e-8, 2.99e-8, 6e-8, 6.1e-5, np.inf, -np.inf], np.float32)])
+    with np.errstate(over="ignore"):
+        assert np.array_equal(oracle.f32_to_f16_bits(x), x.astype(np.float16).view(np.uint16))
+
+
+def test_grid_geometry(oracle):
+    n, off = oracle.grid_setup()  # config/base.yaml:8-10 + encoding_map.cpp:15-23
+    assert n == 15269888 and list(off[:4]) == [0, 32768, 32768 + 262144, 32768 + 262144 + 524288] and off[-1] == 7634944
+
+
+def test_hashgrid_forward_is_trilinear_and_fp16(oracle):
+    rng = np.random.default_rng(1)
+    n_params, _ = oracle.grid_setup()
+    table = rng.uniform(-0.5, 0.5, n_params).astype(np.float32)
+    x = rng.uniform(0.05, 0.95, (300, 3)).astype(np.float32)
+    feat, dy = oracle.hashgrid_fwd(x, table, want_dy_dx=True)
+    assert np.array_equal(feat, feat.astype(np.float16).astype(np.float32))  # outputs are fp16-exact
+    assert np.abs(feat).max() <= 0.5 + 1e-3 and np.abs(feat).mean() > 0.05
+    # level 0 is a dense 32^3 grid (scale 31): compare with an independent numpy trilinear interpolation
+    t0 = table[: 32768 * 2].astype(np.float16).astype(np.float64).reshape(32, 32, 32, 2)  # [z][y][x][f]
+    pos = x.astype(np.float64) * 31 + 0.5
+    i0 = np.floor(pos).astype(int)
+    fr = pos - i0
+    ref = np.zeros((len(x), 2))
+    for c in range(8):
+        o = [(c >> d) & 1 for d in range(3)]
+        w = np.prod([fr[:, d] if o[d] else 1 - fr[:, d] for d in range(3)], 0)
+        ref += w[:, None] * t0[(i0[:, 2] + o[2]) % 32, (i0[:, 1] + o[1]) % 32, (i0[:, 0] + o[0]) % 32]
+    np.testing.assert_allclose(feat[:, :2], ref, atol=2e-3)  # fp16 accumulation of 8 terms
+    # dy_dx vs finite differences of the (fp16-rounded) forward at the coarse levels
+    eps = 2e-3
+    for d in range(3):
+        xp, xm = x.copy(), x.copy()
+        xp[:, d] += eps
+        xm[:, d] -= eps
+        fd = (oracle.hashgrid_fwd(xp, table) - oracle.hashgrid_fwd(xm, table)) / (xp[:, d] - xm[:, d])[:, None]
+        same_cell = np.floor(xp * 31 + 0.5)[:, d] == np.floor(xm * 31 + 0.5)[:, d]
+        np.testing.assert_allclose(dy[same_cell][:, :2, d], fd[same_cell][:, :2], atol=0.3, rtol=5e-2)
+
+
+@pytest.mark.parametrize("hidden,n_hidden", [(64, 3), (32, 1)])
+def test_mlp_backward_is_derivative(oracle, hidden, n_hidden):
+    rng = np.random.default_rng(2)
+    params, dims = _net(rng, hidden, n_hidden)
+    x = rng.standard_normal((40, 32)).astype(np.float32)
+    v = rng.standard_normal((40, 2))
+    d_in, d_p = oracle.mlp_bwd(x, dims, params, v)
+    loss = lambda xx, pp: float((oracle.mlp_fwd(xx, dims, pp) * v).sum())
+    for trial in range(3):
+        # a random direction over all 14 k parameters has norm ~120, so the step must be tiny for the ReLU network to
+        # stay in one linear region; use the realised fp32 step in the analytic side
+        eps = 1e-6
+        dp = rng.standard_normal(params.shape)
+        pp, pm = (params + eps * dp).astype(np.float32), (params - eps * dp).astype(np.float32)
+        fd = (loss(x, pp) - loss(x, pm)) / (2 * eps)
+        an = float((d_p * ((pp.astype(np.float64) - pm.astype(np.float64)) / (2 * eps))).sum())
+        assert abs(fd - an) <= 2e-3 * max(abs(fd), 1), (fd, an)
+        dx = rng.standard_normal(x.shape)
+        eps = 1e-5
+        xp, xm = (x + eps * dx).astype(np.float32), (x - eps * dx).astype(np.float32)
+        fd = (loss(xp, params) - loss(xm, params)) / (2 * eps)
+        an = float((d_in * ((xp.astype(np.float64) - xm.astype(np.float64)) / (2 * eps))).sum())
+        assert abs(fd - an) <= 2e-3 * max(abs(fd), 1), (fd, an)
+
+
+def test_sdf_chain_table_gradient(oracle):
+    """table gradient of the chained oracle: sum over the table equals the sum of weights x cotangent (partition of unity),
+    and only touched entries are non-zero."""
+    rng = np.random.default_rng(3)
+    n_params, off = oracle.grid_setup()
+    table = rng.uniform(-0.5, 0.5, n_params).astype(np.float32)
+    params, dims = _net(rng)
+    x = rng.uniform(0.05, 0.95, (200, 3)).astype(np.float32)
+    tg, d_mlp, dx = oracle.sdf_bwd(x, table, params, np.ones(200), np.zeros(200))
+    feat = oracle.hashgrid_fwd(x, table)
+    d_feat, _ = oracle.mlp_bwd(feat, dims, params, np.stack([np.ones(200), np.zeros(200)], 1))
+    per_level = tg.reshape(-1, 2)
+    for lvl in (0, 1, 5, 15):
+        seg = per_level[off[lvl]:off[lvl + 1]].sum(0)
+        np.testing.assert_allclose(seg, d_feat[:, 2 * lvl:2 * lvl + 2].sum(0), rtol=3e-3, atol=3e-4)  # fp16 rounding of w and g
+    assert (tg != 0).sum() <= 200 * 16 * 8 * 2 and np.isfinite(dx).all() and np.abs(dx).max() > 0
