@@ -37,5 +37,42 @@ def build(verbose=False, force=False):
     return OUT
 
 
+SHIM_OUT = os.path.join(HERE, "gssdf_shim.so")
+
+
+def build_shim(force=False):
+    """libtorch shim (gs-sdf_b200/shim/) + its pybind harness -> gssdf_shim.so, linked against libgssdf_b200.so."""
+    import sysconfig
+
+    import torch
+    srcs = [os.path.join(HERE, "shim", f) for f in ("gsplat_cpp_shim.cpp", "py_binding.cpp")]
+    deps = srcs + [os.path.join(HERE, "shim", "include", "gsplat_cpp", h) for h in ("fully_fused_projection.h", "rasterize_to_pixels.h", "rendering.h")]
+    deps.append(os.path.join(HERE, "..", "include", "gssdf_b200.h"))
+    if not force and os.path.exists(SHIM_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(SHIM_OUT) for d in deps):
+        return SHIM_OUT
+    tdir = os.path.dirname(torch.__file__)
+    inc = [f"-I{os.path.join(HERE, 'shim', 'include')}", f"-I{tdir}/include", f"-I{tdir}/include/torch/csrc/api/include",
+           "-I/usr/local/cuda/include", f"-I{sysconfig.get_paths()['include']}"]
+    flags = ["-std=c++17", "-O2", "-fPIC", "-w", "-D_GLIBCXX_USE_CXX11_ABI=1", "-DTORCH_EXTENSION_NAME=gssdf_shim", "-DTORCH_API_INCLUDE_EXTENSION_H"]
+    objs, procs = [], []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    for s_ in srcs:
+        o = os.path.join(HERE, "build", os.path.basename(s_) + ".o")
+        objs.append(o)
+        procs.append((s_, subprocess.Popen(["/usr/bin/g++"] + flags + inc + ["-c", s_, "-o", o], stdout=subprocess.PIPE,
+                                           stderr=subprocess.STDOUT, text=True)))
+    for s_, p in procs:
+        out, _ = p.communicate()
+        if p.returncode:
+            sys.stderr.write(out)
+            raise RuntimeError("g++ failed on " + s_)
+    subprocess.check_call(["/usr/bin/g++", "-shared", "-o", SHIM_OUT] + objs +
+                          [f"-L{HERE}", "-l:libgssdf_b200.so", f"-L{tdir}/lib", "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda",
+                           "-ltorch_python", "-L/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{tdir}/lib", "-Wl,-rpath,$ORIGIN"])
+    return SHIM_OUT
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    if "--shim" in sys.argv:
+        print(build_shim(force="-f" in sys.argv))

@@ -235,7 +235,7 @@ __device__ __forceinline__ void load_x(const gssdf_sdf_net &net, const float *__
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         const float v = __ldg(x + 3 * i + d);
-        out[d] = net.inv_size != 0.f ? (v - net.origin[d]) * net.inv_size + 0.5f : v;
+        out[d] = net.inv_size != 0.f ? __fmaf_rn(v - net.origin[d], net.inv_size, 0.5f) : v;
     }
 }
 

@@ -38,7 +38,8 @@ def test_sdf_fwd_bwd(oracle, n, hidden, n_hidden):
     tab, half = t(table), torch.empty(n_params, dtype=torch.float16, device=dev)
     cabi.sdf_table_to_half(tab, half)
     assert np.array_equal(half.cpu().numpy().view(np.uint16), oracle.f32_to_f16_bits(table))
-    net = cabi.sdf_net(half, t(mlp), hidden_dim=hidden, n_hidden=n_hidden)
+    mlp_t = t(mlp)  # keep alive: the net struct only holds raw pointers
+    net = cabi.sdf_net(half, mlp_t, hidden_dim=hidden, n_hidden=n_hidden)
     assert cabi.sdf_table_params(net) == n_params and cabi.sdf_mlp_params(net) == len(mlp)
     sdf, y1, feat = torch.empty(n, device=dev), torch.empty(n, device=dev), torch.empty(n, 32, device=dev)
     cabi.sdf_fwd(net, t(x), sdf, y1, feat)
@@ -73,7 +74,9 @@ def test_sdf_mirror_api_autograd_and_numerical_gradient(oracle):
     (sdf.square().sum() + isigma.sum()).backward()
     assert net.params_.grad is not None and net.decoder_.grad is not None and xyz.grad is not None
     assert torch.isfinite(net.params_.grad).all() and net.params_.grad.abs().sum() > 0
-    x01 = ((xyz.detach().cpu().numpy() - np.array([0.5, -0.25, 0.1], np.float32)) / 14.0 + 0.5).astype(np.float32)
+    # same arithmetic as the kernel: fma(x - origin, inv_size, 0.5) in fp32 (the fp16 grid amplifies 1-ulp input changes)
+    d32 = (xyz.detach().cpu().numpy() - np.array([0.5, -0.25, 0.1], np.float32)).astype(np.float32)
+    x01 = (d32.astype(np.float64) * np.float64(np.float32(1.0 / 14.0)) + 0.5).astype(np.float32)
     r_sdf, _, _ = oracle.sdf_fwd(x01, net.params_.detach().cpu().numpy(), net.decoder_.detach().cpu().numpy())
     assert_close_frac(sdf.detach().cpu().numpy()[:, 0], r_sdf, 2e-4, 2e-5, 2e-3, "sdf (world coords)")  # x01 rounding differs by an ulp
     g = net.get_gradient_numerical(xyz.detach(), 0.05)
