@@ -1,0 +1,48 @@
+"""Image-batch data parallelism for the GS-SDF step: splat/SDF state replicated, rank r renders its
+own camera, ONE all-reduce of the flat gradient per step, densification statistics reduced so that every replica makes
+identical grow/prune decisions. torch.distributed is plumbing (NCCL over NVLink on GPUs, gloo in the CPU tests).
+
+Reference behaviour being parallelised: one image per step drawn from a per-epoch torch::randperm(train_num)
+(include/neural_mapping/neural_mapping.cpp:208-225); densification state grad2d/count (sum) and vis/radii (max)
+(include/neural_gaussian/neural_gaussian.cpp:660-679).
+"""
+import torch
+import torch.distributed as dist
+
+
+def epoch_permutation(n_train, epoch, seed=0):
+    """Rank-shared permutation of the training images for one epoch (same generator seed on every rank)."""
+    g = torch.Generator(device="cpu").manual_seed(seed * 1_000_003 + epoch)
+    return torch.randperm(n_train, generator=g)
+
+
+def image_for_rank(step, rank, world, n_train, seed=0):
+    """Image index rank `rank` renders at global step `step`: perm[(step * world + rank) mod n_train] of the epoch's permutation.
+    Within an epoch no image is rendered twice and ranks never collide (world <= n_train)."""
+    per_epoch = max(n_train // world, 1)
+    epoch, i = divmod(step, per_epoch)
+    perm = epoch_permutation(n_train, epoch, seed)
+    return int(perm[(i * world + rank) % n_train])
+
+
+def allreduce_flat_grad(flat_grad, world=None, average=True):
+    """Sum (or mean) the flat gradient buffer over ranks in place: the path's only data exchange."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return flat_grad
+    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+    if average:
+        flat_grad.div_(world or dist.get_world_size())
+    return flat_grad
+
+
+def allreduce_densify_state(state):
+    """state: dict with 'grad2d', 'count' (summed over ranks) and 'vis', 'radii' (max over ranks); in place."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return state
+    for k in ("grad2d", "count"):
+        if k in state:
+            dist.all_reduce(state[k], op=dist.ReduceOp.SUM)
+    for k in ("vis", "radii"):
+        if k in state:
+            dist.all_reduce(state[k], op=dist.ReduceOp.MAX)
+    return state

@@ -1,0 +1,54 @@
+"""world_size-2 gloo test (CPU) of the data-parallel host logic: disjoint image assignment from a rank-shared
+permutation, flat-gradient all-reduce, densification-state reduction (sum / max)."""
+import os
+import socket
+
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.multiprocessing as mp  # noqa: E402
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    from gssdf_b200 import parallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    imgs = [parallel.image_for_rank(s, rank, world, 10, seed=3) for s in range(12)]
+    flat = torch.full((1000,), float(rank + 1))
+    parallel.allreduce_flat_grad(flat, world, average=True)
+    st = dict(grad2d=torch.arange(5.0) * (rank + 1), count=torch.ones(5), vis=torch.tensor([0.1, 0.9]) if rank == 0 else torch.tensor([0.5, 0.2]),
+              radii=torch.tensor([float(rank)]))
+    parallel.allreduce_densify_state(st)
+    out.put((rank, imgs, float(flat[0]), st["grad2d"].tolist(), st["count"].tolist(), st["vis"].tolist(), st["radii"].tolist()))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_host_logic_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, im0, f0, g0, c0, v0, rad0), (r1, im1, f1, g1, c1, v1, rad1) = res
+    # same epoch permutation on both ranks, disjoint images inside an epoch (5 steps x 2 ranks = the 10 images once each)
+    assert sorted(im0[:5] + im1[:5]) == list(range(10)) and sorted(im0[5:10] + im1[5:10]) == list(range(10))
+    assert f0 == f1 == 1.5  # mean of 1 and 2
+    assert g0 == g1 == [0.0, 3.0, 6.0, 9.0, 12.0] and c0 == c1 == [2.0] * 5
+    assert v0 == v1 == pytest.approx([0.5, 0.9]) and rad0 == rad1 == [1.0]
+
+
+def test_single_process_is_identity():
+    from gssdf_b200 import parallel
+    t = torch.ones(4)
+    assert parallel.allreduce_flat_grad(t) is t and (t == 1).all()
+    assert sorted(parallel.image_for_rank(s, 0, 1, 7) for s in range(7)) == list(range(7))
