@@ -1,10 +1,12 @@
 #!/usr/bin/env python
 """bench.py -- train-step/s (and Mrays/s) of the GS-SDF splat hot path on B200 (BASELINE.json metric).
 
-A "step" is one pass of the hot path (SURVEY.md section 3.2 [B]+[D], rows a2-a8 of section 8a) over one
-camera per rank: projection -> SH colour -> tile keys/sort/offsets -> rasterise -> post-ops -> L1 loss ->
-backward of all of it to {means, quats, scales, opacities, SH}; with N > 1 ranks (image-batch data parallel,
-replicated splat state) the flat gradient is all-reduced over NCCL every step.
+A "step" is one pass of the hot path (SURVEY.md section 3.2 [A]-[D], rows a2-a12 of section 8a) over one
+camera per rank: SDF stage on 32768 ray samples (hash-grid + MLP at the point and its 6 numerical-gradient
+offsets, BCE + eikonal, backward) -> projection -> SH colour -> tile keys/sort/offsets -> rasterise -> post-ops
+-> GS<->SDF coupling on the visible splats' stochastic samples (7 SDF evaluations each, backward incl. d/d sample)
+-> L1 loss -> backward of the render to {means, quats, scales, opacities, SH}; with N > 1 ranks (image-batch data
+parallel, replicated state) the flat gradient (splats + hash table + decoder) is all-reduced over NCCL every step.
 
   value : whole-job steps/s with every input already resident in HBM (CUDA events, max over ranks)
   e2e   : the same through the public API with HOST buffers: per step the camera (viewmat, K) and the
@@ -108,7 +110,18 @@ def cpu_oracle_step(O, S, sc, V, K, W, H, deg, rn, gt):
     O.project2dgs_bwd(sc["means"], sc["quats"], sc["scales"], V, K, p["camera_ids"], p["gaussian_ids"], p["ray_transforms"],
                       p["randns"], rb["v_means2d"], np.zeros(p["nnz"], np.float32), rb["v_ray_transforms"], rb["v_normals"],
                       np.zeros((p["nnz"], 3), np.float32), "f32")
-    return float(loss), p["nnz"], len(flat)
+    return float(loss), p["nnz"], len(flat), p, r
+
+
+def cpu_oracle_sdf(O, pts, table, mlp, hidden, n_hidden, gt=None, weights=None, delta=0.1):
+    """SDF stage on the oracle port: 7 evaluations per point, losses, backward (table + decoder + d/dx of the base point)."""
+    n = len(pts)
+    offs = np.array([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float32) * np.float32(delta)
+    x01 = (((pts[None] + offs[:, None]).reshape(-1, 3)) / 14.0 + 0.5).astype(np.float32)
+    sdf, y1, _ = O.sdf_fwd(x01, table, mlp, hidden, n_hidden)
+    loss, vs, vy = O.sdf_losses(sdf, y1, n, 7, gt, weights, 10.0, 1.0 if gt is not None else 0.0, 0.1, 1e-3, delta)
+    O.sdf_bwd(x01, table, mlp, vs, vy, hidden, n_hidden)
+    return loss
 
 
 def run_cpu_sample(workload, steps, warmup, budget_s=25.0):
@@ -127,12 +140,31 @@ def run_cpu_sample(workload, steps, warmup, budget_s=25.0):
     gt = np.random.default_rng(3).random((1, Hs, Ws, 4), dtype=np.float32)
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    rng = np.random.default_rng(5)
+    n_table, _ = O.grid_setup()
+    table = rng.uniform(-1e-4, 1e-4, n_table).astype(np.float32)
+    hidden, n_hidden = (32, 1) if workload == "c1" else (64, 3)
+    dims = [32] + [hidden] * (1 + n_hidden) + [2]
+    mlp = np.concatenate([np.concatenate([rng.uniform(-1, 1, o * k) / np.sqrt(k), rng.uniform(-1, 1, o) / np.sqrt(k)])
+                          for k, o in zip(dims[:-1], dims[1:])]).astype(np.float32)
+    n_ray = 32768 // CPU_SAMPLE_DIV ** 2
+    ray = (rng.uniform(-1, 1, (n_ray, 3)) * (S.BOX + 0.3)).astype(np.float32)
+    ray_gt = np.clip((S.BOX - np.abs(ray)).min(1), -0.3, 0.3).astype(np.float32)
+
+    def full_step():
+        cpu_oracle_sdf(O, ray, table, mlp, hidden, n_hidden, gt=ray_gt)
+        loss, nnz, I, p, r = cpu_oracle_step(O, S, sc, V, K, Ws, Hs, deg, rn, gt)
+        vis = np.asarray(r["visibilities"], np.float32)[:, 0]
+        w = np.where(vis > 0.1, p["sample_weights"][:, 0] * vis, 0).astype(np.float32)
+        cpu_oracle_sdf(O, p["samples"], table, mlp, hidden, n_hidden, weights=w)
+        return loss, nnz, I
+
     for _ in range(max(1, min(warmup, 1))):
-        cpu_oracle_step(O, S, sc, V, K, Ws, Hs, deg, rn, gt)
+        full_step()
     t0 = time.perf_counter()
     done = 0
     for _ in range(max(steps, 1)):
-        _, nnz, I = cpu_oracle_step(O, S, sc, V, K, Ws, Hs, deg, rn, gt)
+        _, nnz, I = full_step()
         done += 1
         if time.perf_counter() - t0 > budget_s:
             break
@@ -141,7 +173,7 @@ def run_cpu_sample(workload, steps, warmup, budget_s=25.0):
     value = (1.0 / dt) * frac  # sample steps/s scaled by the work fraction = full-workload-equivalent steps/s
     return dict(value=value, unit="step/s", cores=cores, kind="port",
                 sample=f"{done} oracle steps (C, OpenMP, fp32) of the workload at 1/{CPU_SAMPLE_DIV} linear resolution "
-                       f"({Ws}x{Hs}, {Ns} splats, nnz={nnz}, n_isects={I}): {dt * 1e3:.0f} ms each; value = sample steps/s x {frac:.4f}"), W, H
+                       f"({Ws}x{Hs}, {Ns} splats, nnz={nnz}, n_isects={I}, {n_ray}+{nnz} SDF points x7): {dt * 1e3:.0f} ms each; value = sample steps/s x {frac:.4f}"), W, H
 
 
 def main():
@@ -189,7 +221,22 @@ def main():
     sc_np = S.box_scene(N, deg, seed=0)  # replicated state: identical on every rank
     sc = {k: t(v) for k, v in sc_np.items()}
     K_sh = (deg + 1) ** 2
-    R = render.SplatRenderer(N, K_sh, 1, W, H, dev, isect_cap=isect_cap, sh_degree=deg)
+    sdf_cfg = dict(n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=2.0,
+                   hidden_dim=32 if args.workload == "c1" else 64, n_hidden=1 if args.workload == "c1" else 3)
+    n_ray = 32768  # config/base.yaml:23 batch_pt_num
+    G = render.GsSdfStep(N, K_sh, W, H, dev, isect_cap, sdf_cfg, n_ray_samples=n_ray, sh_degree=deg, origin=(0.0, 0.0, 0.0), map_size=14.0)
+    R = G.R
+    gen = torch.Generator(dev).manual_seed(5)
+    table = (torch.rand(G.n_table, device=dev, generator=gen) * 2 - 1) * 1e-4  # tcnn grid init U(+-1e-4) (grid.h:1059-1062)
+    mlp_chunks, dims = [], [32] + [sdf_cfg["hidden_dim"]] * (1 + sdf_cfg["n_hidden"]) + [2]
+    for k_, o_ in zip(dims[:-1], dims[1:]):  # torch::nn::Linear default init
+        b_ = 1.0 / math.sqrt(k_)
+        mlp_chunks += [(torch.rand(o_ * k_, device=dev, generator=gen) * 2 - 1) * b_, (torch.rand(o_, device=dev, generator=gen) * 2 - 1) * b_]
+    mlp = torch.cat(mlp_chunks)
+    # ray samples: points within +-0.3 m of the box walls, ground-truth SDF = distance to the nearest wall (inside positive)
+    box = torch.tensor(S.BOX, device=dev, dtype=torch.float32)
+    ray_xyz = (torch.rand(n_ray, 3, device=dev, generator=gen) * 2 - 1) * (box + 0.3)
+    ray_gt = (box - ray_xyz.abs()).min(dim=1).values.clamp(-0.3, 0.3).contiguous()
     n_cams = 8
     cams = [S.camera(rank * n_cams + i, W, H) for i in range(n_cams)]  # rank r renders its own images
     # ground truth: the same scene rendered with perturbed colours, produced once on the device
@@ -210,9 +257,9 @@ def main():
     def step_resident(i):
         V, Kc = dev_cams[i % n_cams]
         randn_buf.normal_()  # the reference draws randns on the device every render (Projection.cpp:728)
-        loss = R.step(sc, V, Kc, gts[i % n_cams], randn_buf)
+        loss, _sdf_loss = G.step(sc, table, mlp, V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf)
         if world > 1:
-            dist.all_reduce(R.flat_grad)  # sum; the optimiser scales by 1/world (losses are means)
+            dist.all_reduce(G.flat_grad)  # splat + hash-table + decoder gradients; the optimiser scales by 1/world
         return loss
 
     def step_e2e(i):
@@ -221,9 +268,9 @@ def main():
         h_K.copy_(hk, non_blocking=True)
         h_gt.copy_(host_gts[i % n_cams], non_blocking=True)
         randn_buf.normal_()
-        loss = R.step(sc, h_V, h_K, h_gt, randn_buf)
+        loss, _sdf_loss = G.step(sc, table, mlp, h_V, h_K, h_gt, ray_xyz, ray_gt, randn_buf)
         if world > 1:
-            dist.all_reduce(R.flat_grad)
+            dist.all_reduce(G.flat_grad)
         loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the loss every step (neural_mapping.cpp:505-514)
         return float(loss_host[0])
@@ -304,7 +351,7 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": cfg, "mrays_per_s": value * P / 1e6, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "step/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
-                "gpu_launches": args.steps * render.SplatRenderer.KERNELS_PER_STEP,
+                "gpu_launches": args.steps * render.GsSdfStep.KERNELS_PER_STEP,
                 "roofline": {"kernel": "raster2dgs_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
                              "algorithmic_bytes": alg_bwd, "kernel_ms": t_bwd * 1e3,

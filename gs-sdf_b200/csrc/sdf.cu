@@ -231,10 +231,15 @@ __device__ __forceinline__ void dense_layer(const float *s_in, int K, const floa
         }
 }
 
-__device__ __forceinline__ void load_x(const gssdf_sdf_net &net, const float *__restrict__ x, int64_t i, float out[3]) {
+// evaluation index gi = variant * n + base point; variants 1..6 = +x,-x,+y,-y,+z,-z offsets by delta (local_map.cpp:112-121)
+__device__ __forceinline__ void load_x(const gssdf_sdf_net &net, const float *__restrict__ x, int64_t gi, int64_t n, float delta,
+                                       float out[3]) {
+    const int64_t i = gi % n;
+    const int var = (int)(gi / n);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        const float v = __ldg(x + 3 * i + d);
+        float v = __ldg(x + 3 * i + d);
+        if (var > 0 && (var - 1) / 2 == d) v += ((var - 1) & 1) ? -delta : delta;
         out[d] = net.inv_size != 0.f ? __fmaf_rn(v - net.origin[d], net.inv_size, 0.5f) : v;
     }
 }
@@ -252,16 +257,19 @@ sdf_fwd_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
     float *s_b2 = s_a + TM * AP;        // [TM][AP]
     float *s_w = s_b2 + TM * AP;        // [max(K)][WP]
     float *s_bias = s_w + 64 * WP;      // [HID]
+    const int64_t n_eval = a.n * max(a.n_variants, 1);
     const int64_t base = (int64_t)blockIdx.x * TM;
-    const int tm = (int)min((int64_t)TM, a.n - base);
+    const int tm = (int)min((int64_t)TM, n_eval - base);
+    const int64_t n_live = a.n_live ? min((int64_t)*a.n_live, a.n) : a.n;
+    if (base % a.n >= n_live && base % a.n + TM <= a.n) return;  // whole tile beyond the live rows
     const __half2 *table = reinterpret_cast<const __half2 *>(a.net.table_half);
     // 1. encode: (point, level) tasks; consecutive threads -> consecutive points of one level
     for (int task = threadIdx.x; task < TM * g.L; task += kSdfThreads) {
         const int p = task % TM, lvl = task / TM;
         float2 f = make_float2(0.f, 0.f);
-        if (p < tm) {
+        if (p < tm && (base + p) % a.n < n_live) {
             float x[3];
-            load_x(a.net, a.x, base + p, x);
+            load_x(a.net, a.x, base + p, a.n, a.delta, x);
             f = encode_level(table, g, lvl, x);
             if (a.feat) { a.feat[(base + p) * kFeat + 2 * lvl] = f.x; a.feat[(base + p) * kFeat + 2 * lvl + 1] = f.y; }
         }
@@ -285,7 +293,7 @@ sdf_fwd_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
     // 3. output layer HID -> 2 : one thread per (point, output)
     {
         const int p = threadIdx.x >> 1, o = threadIdx.x & 1;
-        if (p < tm) {
+        if (p < tm && (base + p) % a.n < n_live) {
             float s = __ldg(W + 2 * HID + o);
             const float *w = W + o * HID;
 #pragma unroll 8
@@ -315,6 +323,8 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
     float *s_bias = s_w + 64 * WP;               // [HID]
     float *s_dx = s_bias + HID;                  // [TM][3]
     const int nh = 1 + a.net.n_hidden;           // number of HID-wide layers
+    const int64_t n_eval = a.n * max(a.n_variants, 1);
+    const int64_t n_live = a.n_live ? min((int64_t)*a.n_live, a.n) : a.n;
     const __half2 *table = reinterpret_cast<const __half2 *>(a.net.table_half);
 
     // register accumulators of the weight gradients: thread owns rows o = tx*4..+3? -> use [4][KPT] blocks:
@@ -339,15 +349,17 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * TM;
-        const int tm = (int)min((int64_t)TM, a.n - base);
+        const int tm = (int)min((int64_t)TM, n_eval - base);
+        if (base % a.n >= n_live && base % a.n + TM <= a.n) continue;  // whole tile beyond the live rows (uniform per CTA)
+#define LIVE(p_) ((p_) < tm && (base + (p_)) % a.n < n_live)
         __syncthreads();
         // 1. encode
         for (int task = threadIdx.x; task < TM * g.L; task += kSdfThreads) {
             const int p = task % TM, lvl = task / TM;
             float2 f = make_float2(0.f, 0.f);
-            if (p < tm) {
+            if (LIVE(p)) {
                 float x[3];
-                load_x(a.net, a.x, base + p, x);
+                load_x(a.net, a.x, base + p, a.n, a.delta, x);
                 f = encode_level(table, g, lvl, x);
             }
             s_feat[p * (kFeat + 1) + 2 * lvl] = f.x;
@@ -377,7 +389,7 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
         for (int e = threadIdx.x; e < TM * HID; e += kSdfThreads) {
             const int p = e / HID, k = e % HID;
             float gv = 0.f;
-            if (p < tm) {
+            if (LIVE(p)) {
                 const float v0 = __ldg(a.v_sdf + base + p), v1 = a.v_y1 ? __ldg(a.v_y1 + base + p) : 0.f;
                 gv = v0 * __ldg(Wout + k) + v1 * __ldg(Wout + HID + k);
                 if (!(a_last[p * AP + k] > 0.f)) gv = 0.f;
@@ -388,6 +400,7 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
             const int o = threadIdx.x / HID, k = threadIdx.x % HID;
             float s = 0.f, sb = 0.f;
             for (int p = 0; p < tm; ++p) {
+                if (!LIVE(p)) continue;
                 const float v = o == 0 ? __ldg(a.v_sdf + base + p) : (a.v_y1 ? __ldg(a.v_y1 + base + p) : 0.f);
                 s = fmaf(v, a_last[p * AP + k], s);
                 sb += v;
@@ -454,11 +467,12 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
         __syncthreads();
         for (int task = threadIdx.x; task < TM * g.L; task += kSdfThreads) {
             const int p = task % TM, lvl = task / TM;
-            if (p < tm) {
+            if (LIVE(p)) {
                 float x[3], dx[3] = {0.f, 0.f, 0.f};
-                load_x(a.net, a.x, base + p, x);
-                encode_level_bwd(table, a.table_grad, g, lvl, x, gcur[p * AP + 2 * lvl], gcur[p * AP + 2 * lvl + 1], a.v_x != nullptr, dx);
-                if (a.v_x) {
+                load_x(a.net, a.x, base + p, a.n, a.delta, x);
+                const bool want_dx = a.v_x != nullptr && base + p < a.n;  // only variant 0 carries a gradient to x
+                encode_level_bwd(table, a.table_grad, g, lvl, x, gcur[p * AP + 2 * lvl], gcur[p * AP + 2 * lvl + 1], want_dx, dx);
+                if (want_dx) {
                     atomicAdd(&s_dx[p * 3 + 0], dx[0]);
                     atomicAdd(&s_dx[p * 3 + 1], dx[1]);
                     atomicAdd(&s_dx[p * 3 + 2], dx[2]);
@@ -468,7 +482,8 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
         __syncthreads();
         if (a.v_x)
             for (int e = threadIdx.x; e < tm * 3; e += kSdfThreads)
-                a.v_x[base * 3 + e] = s_dx[e] * (a.net.inv_size != 0.f ? a.net.inv_size : 1.f);
+                if (base + e / 3 < n_live) a.v_x[base * 3 + e] = s_dx[e] * (a.net.inv_size != 0.f ? a.net.inv_size : 1.f);
+#undef LIVE
     }
     // flush the register-resident weight gradients (one RED per parameter per CTA)
     if (a.mlp_grad) {
@@ -495,6 +510,76 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
         }
         if (threadIdx.x < 2 * HID) atomicAdd(G + threadIdx.x, dWout);
         if (threadIdx.x < 2 * HID && threadIdx.x % HID == 0) atomicAdd(G + 2 * HID + threadIdx.x / HID, dBout);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused SDF losses + cotangents (loss.cpp:7-11,49-83)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sdf_loss_kernel(const gssdf_sdf_loss_args a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = a.n;  // layout stride
+    const int64_t nl = a.n_live ? min((int64_t)*a.n_live, n) : n;  // live rows; the means are over them
+    float part = 0.f;
+    if (i < nl) {
+        const float s = a.sdf[i];
+        float v_s = 0.f, v_y = 0.f;
+        if (a.gt_sdf) {
+            const float y = a.y1 ? a.y1[i] : 0.f;
+            const float by = 100.f * y;
+            const float sp = by > 20.f ? y : log1pf(expf(by)) * 0.01f;  // torch softplus(beta=100, threshold=20)
+            const float raw = 1.f + sp * a.bce_isigma;
+            const bool capped = raw > 500.f;
+            const float isg = capped ? 500.f : raw;
+            const float z = -s * isg;
+            const float gt = a.gt_sdf[i];
+            const float tz = -gt * isg;
+            const float tsig = 1.f / (1.f + expf(-tz));
+            const bool tcl = tsig < 1e-7f || tsig > 1.f - 1e-7f;
+            const float t = fminf(fmaxf(tsig, 1e-7f), 1.f - 1e-7f);
+            const float bce = fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z)));
+            const float w = a.bce_weight / (float)nl;
+            part += w * bce;
+            const float dz = (1.f / (1.f + expf(-z)) - t) * w;  // d/dz
+            const float dt = -z * w;                             // d/dt (the reference's target is not detached)
+            v_s += dz * -isg;
+            float d_isg = dz * -s + (tcl ? 0.f : dt * tsig * (1.f - tsig) * -gt);
+            if (!capped) v_y += d_isg * a.bce_isigma * (by > 20.f ? 1.f : 1.f / (1.f + expf(-by)));
+        }
+        if (a.weights) {
+            float w = a.weights[i] * a.gs_sdf_weight;
+            if (a.visibilities) {
+                const float vis = a.visibilities[i];
+                w = vis > a.visible_thr ? w * vis : 0.f;
+            }
+            part += 0.5f * w * s * s;
+            v_s += w * s;
+        }
+        if (a.n_variants == 7) {
+            const float inv2d = 0.5f / a.delta;
+            const float gx = (a.sdf[n + i] - a.sdf[2 * n + i]) * inv2d, gy = (a.sdf[3 * n + i] - a.sdf[4 * n + i]) * inv2d;
+            const float gz = (a.sdf[5 * n + i] - a.sdf[6 * n + i]) * inv2d;
+            const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
+            const float w = a.eikonal_weight / (float)nl;
+            part += w * (nrm - 1.f) * (nrm - 1.f);
+            const float c = nrm > 0.f ? 2.f * (nrm - 1.f) / nrm * w * inv2d : 0.f;
+            a.v_sdf[n + i] = c * gx; a.v_sdf[2 * n + i] = -c * gx;
+            a.v_sdf[3 * n + i] = c * gy; a.v_sdf[4 * n + i] = -c * gy;
+            a.v_sdf[5 * n + i] = c * gz; a.v_sdf[6 * n + i] = -c * gz;
+            if (a.v_y1)
+                for (int v = 1; v < 7; ++v) a.v_y1[v * n + i] = 0.f;
+        }
+        a.v_sdf[i] = v_s;
+        if (a.v_y1) a.v_y1[i] = v_y;
+    }
+    part = warp_sum(part);
+    __shared__ float s_part[8];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += s_part[w];
+        if (t != 0.f) atomicAdd(a.loss_out, t);
     }
 }
 
@@ -550,7 +635,8 @@ extern "C" int gssdf_sdf_fwd(const gssdf_sdf_fwd_args *a, gssdf_stream_t stream)
     if (a->n == 0) return GSSDF_OK;
     GSSDF_REQUIRE(a->x && a->sdf, GSSDF_EINVAL, "sdf_fwd: x and sdf must be non-null");
     const GridGeom g = make_grid(a->net);
-    const int grid = cdiv(a->n, 128);
+    GSSDF_REQUIRE(a->n_variants == 0 || a->n_variants == 1 || a->n_variants == 7, GSSDF_EINVAL, "sdf_fwd: n_variants must be 1 or 7");
+    const int grid = cdiv(a->n * (a->n_variants > 1 ? a->n_variants : 1), 128);
     cudaStream_t st = (cudaStream_t)stream;
     if (a->net.hidden_dim == 64) {
         GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
@@ -571,7 +657,8 @@ extern "C" int gssdf_sdf_bwd(const gssdf_sdf_bwd_args *a, gssdf_stream_t stream)
     if (a->n == 0) return GSSDF_OK;
     GSSDF_REQUIRE(a->x && a->v_sdf, GSSDF_EINVAL, "sdf_bwd: x and v_sdf must be non-null");
     const GridGeom g = make_grid(a->net);
-    const int64_t n_tiles = (a->n + 63) / 64;
+    GSSDF_REQUIRE(a->n_variants == 0 || a->n_variants == 1 || a->n_variants == 7, GSSDF_EINVAL, "sdf_bwd: n_variants must be 1 or 7");
+    const int64_t n_tiles = (a->n * (a->n_variants > 1 ? a->n_variants : 1) + 63) / 64;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -585,5 +672,17 @@ extern "C" int gssdf_sdf_bwd(const gssdf_sdf_bwd_args *a, gssdf_stream_t stream)
         sdf_bwd_kernel<32><<<grid, kSdfThreads, bwd_smem<32>(), st>>>(*a, g, n_tiles);
     }
     GSSDF_LAUNCH_OK("sdf_bwd_kernel");
+    return GSSDF_OK;
+}
+
+extern "C" int gssdf_sdf_loss(const gssdf_sdf_loss_args *a, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "sdf_loss: null args");
+    GSSDF_REQUIRE(a->n >= 0, GSSDF_EINVAL, "sdf_loss: negative n");
+    if (a->n == 0) return GSSDF_OK;
+    GSSDF_REQUIRE(a->n_variants == 1 || a->n_variants == 7, GSSDF_EINVAL, "sdf_loss: n_variants must be 1 or 7");
+    GSSDF_REQUIRE(a->sdf && a->v_sdf && a->loss_out, GSSDF_EINVAL, "sdf_loss: sdf, v_sdf, loss_out must be non-null");
+    GSSDF_REQUIRE(a->n_variants == 1 || a->delta > 0.f, GSSDF_EINVAL, "sdf_loss: delta must be positive");
+    sdf_loss_kernel<<<cdiv(a->n, 256), 256, 0, (cudaStream_t)stream>>>(*a);
+    GSSDF_LAUNCH_OK("sdf_loss_kernel");
     return GSSDF_OK;
 }

@@ -189,13 +189,23 @@ def sdf_table_to_half(table_f32, table_f16):
                                         _lib.C.c_int64(table_f32.numel()), _stream()))
 
 
-def sdf_fwd(net, x, sdf, y1=None, feat=None):
-    a = make_args("gssdf_sdf_fwd_args", n=x.shape[0], x=x, sdf=sdf, y1=y1, feat=feat)
+def sdf_fwd(net, x, sdf, y1=None, feat=None, n_variants=1, delta=0.0, n_live=None):
+    a = make_args("gssdf_sdf_fwd_args", n=x.shape[0], x=x, sdf=sdf, y1=y1, feat=feat, n_variants=n_variants, delta=delta, n_live=n_live)
     a.net = net
     check(lib().gssdf_sdf_fwd(_lib.C.byref(a), _stream()))
 
 
-def sdf_bwd(net, x, v_sdf, v_y1=None, table_grad=None, mlp_grad=None, v_x=None):
-    a = make_args("gssdf_sdf_bwd_args", n=x.shape[0], x=x, v_sdf=v_sdf, v_y1=v_y1, table_grad=table_grad, mlp_grad=mlp_grad, v_x=v_x)
+def sdf_bwd(net, x, v_sdf, v_y1=None, table_grad=None, mlp_grad=None, v_x=None, n_variants=1, delta=0.0, n_live=None):
+    a = make_args("gssdf_sdf_bwd_args", n=x.shape[0], x=x, v_sdf=v_sdf, v_y1=v_y1, table_grad=table_grad, mlp_grad=mlp_grad, v_x=v_x,
+                  n_variants=n_variants, delta=delta, n_live=n_live)
     a.net = net
     check(lib().gssdf_sdf_bwd(_lib.C.byref(a), _stream()))
+
+
+def sdf_loss(n, n_variants, sdf, y1, gt_sdf, weights, bce_isigma, bce_weight, eikonal_weight, gs_sdf_weight, delta, loss_out, v_sdf, v_y1,
+             visibilities=None, visible_thr=0.0, n_live=None):
+    a = make_args("gssdf_sdf_loss_args", n=n, n_variants=n_variants, sdf=sdf, y1=y1, gt_sdf=gt_sdf, weights=weights,
+                  visibilities=visibilities, visible_thr=visible_thr, n_live=n_live,
+                  bce_isigma=bce_isigma, bce_weight=bce_weight, eikonal_weight=eikonal_weight, gs_sdf_weight=gs_sdf_weight,
+                  delta=delta, loss_out=loss_out, v_sdf=v_sdf, v_y1=v_y1)
+    check(lib().gssdf_sdf_loss(_lib.C.byref(a), _stream()))

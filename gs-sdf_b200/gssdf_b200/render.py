@@ -75,10 +75,12 @@ class SplatRenderer:
         return self.out_colors, self.out_normals
 
     # -- loss + backward -----------------------------------------------------------------------
-    def backward(self, means, quats, scales, opacities, sh, viewmats, Ks, gt, randns=None, w_rgb=1.0, w_depth=0.1):
+    def backward(self, means, quats, scales, opacities, sh, viewmats, Ks, gt, randns=None, w_rgb=1.0, w_depth=0.1, v_samples=None,
+                 zero_grads=True):
         C, W, H, cap = self.C, self.W, self.H, self.cap
         self.loss.zero_()
-        self.flat_grad.zero_()
+        if zero_grads:
+            self.flat_grad.zero_()
         cabi.l1_loss(C, W, H, self.out_colors, gt, w_rgb, w_depth, self.loss, self.v_out_colors)
         cabi.render_post_bwd(C, W, H, viewmats, self.r["render_depths"], self.r["render_alphas"], self.v_out_colors,
                              self.v_out_normals, None, self.v_r["colors"], self.v_r["depths"], self.v_r["alphas"],
@@ -92,7 +94,7 @@ class SplatRenderer:
                              self.p["gaussian_ids"], self.p["radii"], self.colors, self.g["v_colors"], self.v_sh, self.v_means)
         cabi.project2dgs_bwd(means, quats, scales, viewmats, Ks, W, H, cap, self.counts, self.p["camera_ids"],
                              self.p["gaussian_ids"], self.p["ray_transforms"], randns, None, None, self.g["v_ray_transforms"],
-                             self.g["v_normals"], None, self.v_means, self.v_quats, self.v_scales,
+                             self.g["v_normals"], v_samples, self.v_means, self.v_quats, self.v_scales,
                              v_pt_opacities=self.g["v_opacities"], v_opacities=self.v_opac)
         return self.loss
 
@@ -107,3 +109,81 @@ class SplatRenderer:
     def read_counts(self):
         c = self.counts.cpu().tolist()
         return dict(nnz=c[0], n_isects=c[1], nnz_overflow=c[2], isect_overflow=c[3], max_tile_count=c[4])
+
+
+class GsSdfStep:
+    """One full GS-SDF hot-path step (SURVEY.md section 3.2 [A]-[D]) with zero host synchronisation:
+
+      [A] SDF on ray samples   : get_sdf(x) + 6-offset numerical gradient -> BCE + eikonal -> backward to table / decoder
+      [B] render               : SplatRenderer.forward (projection -> SH -> tiles -> raster -> post-ops)
+      [C] GS<->SDF coupling    : get_sdf(splat samples) (+ numerical eikonal) -> 0.5 sum w sdf^2, w = sample_weight * visibility
+                                 (vis > visible_thr); its gradient w.r.t. the samples flows into the projection backward
+      [D] backward             : L1 photometric/depth loss -> raster bwd -> SH bwd -> projection bwd
+    All gradients land in ONE flat buffer [splat grads | table grad | decoder grad] (single all-reduce under data parallelism).
+    The eikonal terms use the numerical-gradient branch of LocalMap::get_gradient (local_map.cpp:110-133); the analytic
+    double-backward through the encoding is not implemented yet.
+    """
+
+    def __init__(self, N, K, W, H, device, isect_cap, sdf_net_cfg, n_ray_samples=32768, sh_degree=3, origin=(0.0, 0.0, 0.0),
+                 map_size=14.0, bce_sigma=0.1, delta=None, eikonal_weight=0.1, gs_sdf_weight=1e-3, visible_thr=0.1):
+        self.R = SplatRenderer(N, K, 1, W, H, device, isect_cap, sh_degree=sh_degree)
+        self.dev, self.N, self.n_ray = device, N, n_ray_samples
+        self.cfg = dict(sdf_net_cfg)
+        self.origin, self.inv_size = tuple(origin), 1.0 / map_size
+        self.bce_isigma, self.delta = 1.0 / bce_sigma, (delta if delta is not None else bce_sigma)  # k_sample_std = k_bce_sigma
+        self.eik_w, self.gs_sdf_w, self.vis_thr = eikonal_weight, gs_sdf_weight, visible_thr
+        f32 = dict(dtype=torch.float32, device=device)
+        probe = cabi.sdf_net(torch.zeros(1, **f32), torch.zeros(1, **f32), **self.cfg)
+        self.n_table, self.n_mlp = cabi.sdf_table_params(probe), cabi.sdf_mlp_params(probe)
+        self.table_half = torch.empty(self.n_table, dtype=torch.float16, device=device)
+        # flat gradient: [splat | table | mlp]
+        n_splat = self.R.flat_grad.numel()
+        self.flat_grad = torch.zeros(n_splat + self.n_table + self.n_mlp, **f32)
+        self._rebind_splat_grads(n_splat)
+        self.table_grad = self.flat_grad[n_splat:n_splat + self.n_table]
+        self.mlp_grad = self.flat_grad[n_splat + self.n_table:]
+        e = lambda *s: torch.empty(*s, **f32)
+        self.ray_sdf, self.ray_y1, self.ray_vs, self.ray_vy = e(7 * n_ray_samples), e(7 * n_ray_samples), e(7 * n_ray_samples), e(7 * n_ray_samples)
+        cap = self.R.cap
+        self.gs_sdf, self.gs_y1, self.gs_vs, self.gs_vy = e(7 * cap), e(7 * cap), e(7 * cap), e(7 * cap)
+        self.v_samples = e(cap, 3)
+        self.sdf_loss = torch.zeros(1, **f32)
+
+    KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 7  # + table cast + 2 x (sdf fwd, sdf loss, sdf bwd)
+
+    def _rebind_splat_grads(self, n_splat):
+        R, N, K = self.R, self.R.N, self.R.K
+        R.flat_grad = self.flat_grad[:n_splat]
+        o = [0, N * 3, N * 7, N * 10, N * 11, N * 11 + N * K * 3]
+        fg = R.flat_grad
+        R.v_means, R.v_quats, R.v_scales = fg[o[0]:o[1]].view(N, 3), fg[o[1]:o[2]].view(N, 4), fg[o[2]:o[3]].view(N, 3)
+        R.v_opac, R.v_sh = fg[o[3]:o[4]], fg[o[4]:o[5]].view(N, K, 3)
+
+    def refresh_table(self, table_f32):
+        cabi.sdf_table_to_half(table_f32, self.table_half)
+
+    def step(self, scene, table_f32, mlp, viewmats, Ks, gt_image, ray_xyz, ray_gt_sdf, randns=None):
+        R, n_ray, cap = self.R, self.n_ray, self.R.cap
+        # fp32 master -> fp16 shadow once per step (the optimiser moved the master; the reference casts on EVERY forward)
+        cabi.sdf_table_to_half(table_f32, self.table_half)
+        net = cabi.sdf_net(self.table_half, mlp, origin=self.origin, inv_size=self.inv_size, **self.cfg)
+        self.flat_grad.zero_()
+        self.sdf_loss.zero_()
+        # [A] SDF stage on the ray samples
+        cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, self.ray_y1, None, n_variants=7, delta=self.delta)
+        cabi.sdf_loss(n_ray, 7, self.ray_sdf, self.ray_y1, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.delta, self.sdf_loss,
+                      self.ray_vs, self.ray_vy)
+        cabi.sdf_bwd(net, ray_xyz, self.ray_vs, self.ray_vy, self.table_grad, self.mlp_grad, None, n_variants=7, delta=self.delta)
+        # [B] render
+        R.forward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, randns)
+        # [C] coupling on the stochastic splat samples (rows < nnz, counted on the device)
+        samples, n_live = R.p["samples"], R.counts  # counts[0] == nnz
+        cabi.sdf_fwd(net, samples, self.gs_sdf, self.gs_y1, None, n_variants=7, delta=self.delta, n_live=n_live)
+        cabi.sdf_loss(cap, 7, self.gs_sdf, self.gs_y1, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w, self.delta,
+                      self.sdf_loss, self.gs_vs, self.gs_vy, visibilities=R.r["visibilities"], visible_thr=self.vis_thr, n_live=n_live)
+        cabi.sdf_bwd(net, samples, self.gs_vs, self.gs_vy, self.table_grad, self.mlp_grad, self.v_samples, n_variants=7, delta=self.delta,
+                     n_live=n_live)
+        # [D] photometric loss + backward of the render, with the coupling gradient entering through the samples
+        loss = R.backward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, gt_image, randns,
+                          v_samples=self.v_samples, zero_grads=False)
+        return loss, self.sdf_loss

@@ -342,11 +342,16 @@ int gssdf_sdf_table_to_half(const float *table_f32, void *table_f16, int64_t n, 
 
 typedef struct gssdf_sdf_fwd_args {
     gssdf_sdf_net net;
-    int64_t n;
+    int64_t n;        /* number of base points */
     const float *x;   /* [n,3] */
-    float *sdf;       /* [n] decoder output 0 */
-    float *y1;        /* [n] decoder output 1 (raw; isigma = 1 + softplus_100(y1) * k_bce_isigma stays in the caller) */
-    float *feat;      /* [n, L*F] encoding (fp16-exact values) or NULL */
+    int32_t n_variants; /* 1, or 7: the base point + the six offsets +-delta e_k of LocalMap::get_gradient's numerical branch
+                           (local_map.cpp:112-121: +x,-x,+y,-y,+z,-z); evaluation v*n + i is variant v of point i. 0 == 1 */
+    float delta;      /* offset in the units of x */
+    const int32_t *n_live; /* device int32 or NULL: only base points i < min(n, *n_live) are evaluated (e.g. &counts->nnz for
+                              the splat samples); the layout stride stays n */
+    float *sdf;       /* [n_variants*n] decoder output 0 */
+    float *y1;        /* [n_variants*n] decoder output 1 (raw; isigma = 1 + softplus_100(y1) * k_bce_isigma) or NULL */
+    float *feat;      /* [n_variants*n, L*F] encoding (fp16-exact values) or NULL */
 } gssdf_sdf_fwd_args;
 int gssdf_sdf_fwd(const gssdf_sdf_fwd_args *a, gssdf_stream_t stream);
 
@@ -354,13 +359,36 @@ typedef struct gssdf_sdf_bwd_args {
     gssdf_sdf_net net;
     int64_t n;
     const float *x;      /* [n,3] */
-    const float *v_sdf;  /* [n] */
-    const float *v_y1;   /* [n] or NULL */
+    int32_t n_variants;  /* as in the forward */
+    float delta;
+    const int32_t *n_live; /* as in the forward */
+    const float *v_sdf;  /* [n_variants*n] */
+    const float *v_y1;   /* [n_variants*n] or NULL */
     float *table_grad;   /* [table_params] fp32 +=  or NULL */
     float *mlp_grad;     /* [mlp_params]  fp32 +=  or NULL */
-    float *v_x;          /* [n,3] overwritten, or NULL */
+    float *v_x;          /* [n,3] overwritten with the gradient through variant 0 (the base point), or NULL */
 } gssdf_sdf_bwd_args;
 int gssdf_sdf_bwd(const gssdf_sdf_bwd_args *a, gssdf_stream_t stream);
+
+/* SDF losses and their cotangents in one pass (include/optimizer/loss.cpp:7-11,49-83, neural_mapping.cpp:106-136,443-460):
+ *   bce     : mean BCE-with-logits(-sdf*isigma, clamp(sigmoid(-gt*isigma),1e-7,1-1e-7)), isigma = min(1+softplus_100(y1)*k, 500)
+ *   eikonal : mean (|g|-1)^2 with the 6-offset numerical gradient g (k_numerical_grad branch of sdf_regularization)
+ *   gs_sdf  : 0.5 * sum w * sdf^2   (w = samples_weights * visibility, 0 where the sample is masked out)
+ * loss_out[0] += bce_weight*bce + eikonal_weight*eikonal + gs_sdf_weight*gs_sdf; v_* are overwritten. */
+typedef struct gssdf_sdf_loss_args {
+    int64_t n;
+    int32_t n_variants;      /* 1 or 7 (layout of sdf / v_sdf as in gssdf_sdf_fwd) */
+    const float *sdf, *y1;   /* [n_variants*n] */
+    const float *gt_sdf;     /* [n] or NULL (no BCE term) */
+    const float *weights;    /* [n] or NULL (no gs-sdf term) */
+    const float *visibilities; /* [n] or NULL: w = weights * vis where vis > visible_thr else 0 (neural_mapping.cpp:428-432) */
+    float visible_thr;
+    const int32_t *n_live;   /* device int32 or NULL: rows >= *n_live are ignored; means are over min(n, *n_live) */
+    float bce_isigma, bce_weight, eikonal_weight, gs_sdf_weight, delta;
+    float *loss_out;         /* device float[1] += */
+    float *v_sdf, *v_y1;     /* [n_variants*n] */
+} gssdf_sdf_loss_args;
+int gssdf_sdf_loss(const gssdf_sdf_loss_args *a, gssdf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -273,3 +273,46 @@ def sdf_bwd(x, table, mlp_params, v_sdf, v_y1, hidden=64, n_hidden=3, **grid):
     d_feat, d_mlp = mlp_bwd(feat, widths, mlp_params, np.stack([v_sdf, v_y1], 1))
     tg, dx = hashgrid_bwd(x, d_feat.astype(np.float32), len(table), dy, **grid)
     return tg, d_mlp, dx
+
+
+def sdf_losses(sdf, y1, n, n_variants, gt_sdf=None, weights=None, bce_isigma=1.0, bce_weight=1.0, eikonal_weight=0.1,
+               gs_sdf_weight=1e-3, delta=0.05):
+    """numpy (fp64) restatement of loss::sdf_loss / eikonal_loss / gs_sdf_loss (include/optimizer/loss.cpp:7-11,49-83) with the
+    numerical 6-offset gradient of LocalMap::get_gradient (local_map.cpp:110-133); returns (loss, v_sdf, v_y1)."""
+    s = np.asarray(sdf, np.float64).reshape(n_variants, n)
+    y = np.asarray(y1, np.float64).reshape(n_variants, n)
+    v_s, v_y = np.zeros_like(s), np.zeros_like(y)
+    loss = 0.0
+    if gt_sdf is not None:
+        gt = np.asarray(gt_sdf, np.float64)
+        by = 100.0 * y[0]
+        sp = np.where(by > 20, y[0], np.log1p(np.exp(np.minimum(by, 20))) / 100.0)
+        raw = 1 + sp * bce_isigma
+        capped = raw > 500
+        isg = np.minimum(raw, 500)
+        z = -s[0] * isg
+        tsig = 1 / (1 + np.exp(gt * isg))
+        tcl = (tsig < 1e-7) | (tsig > 1 - 1e-7)
+        t = np.clip(tsig, 1e-7, 1 - 1e-7)
+        bce = np.maximum(z, 0) - z * t + np.log1p(np.exp(-np.abs(z)))
+        w = bce_weight / n
+        loss += w * bce.sum()
+        dz = (1 / (1 + np.exp(-z)) - t) * w
+        dt = -z * w
+        v_s[0] += dz * -isg
+        d_isg = dz * -s[0] + np.where(tcl, 0, dt * tsig * (1 - tsig) * -gt)
+        v_y[0] += np.where(capped, 0, d_isg * bce_isigma * np.where(by > 20, 1.0, 1 / (1 + np.exp(-by))))
+    if weights is not None:
+        w = np.asarray(weights, np.float64) * gs_sdf_weight
+        loss += 0.5 * (w * s[0] ** 2).sum()
+        v_s[0] += w * s[0]
+    if n_variants == 7:
+        g = np.stack([s[1] - s[2], s[3] - s[4], s[5] - s[6]], 1) * (0.5 / delta)
+        nrm = np.linalg.norm(g, axis=1)
+        w = eikonal_weight / n
+        loss += w * ((nrm - 1) ** 2).sum()
+        c = np.where(nrm > 0, 2 * (nrm - 1) / np.maximum(nrm, 1e-300) * w * 0.5 / delta, 0)
+        for k in range(3):
+            v_s[1 + 2 * k] = c * g[:, k]
+            v_s[2 + 2 * k] = -c * g[:, k]
+    return loss, v_s.reshape(-1), v_y.reshape(-1)

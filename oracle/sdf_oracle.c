@@ -247,27 +247,38 @@ void oracle_mlp_bwd(int64_t n, const float *in, int n_layers, const int *widths,
     size_t po = 0;
     int ao = 0;
     for (int l = 0; l < n_layers; ++l) { poff[l] = po; aoff[l] = ao; po += (size_t)widths[l + 1] * widths[l] + widths[l + 1]; ao += widths[l + 1]; }
-    for (int64_t i = 0; i < n; ++i) {
-        double g[256], gp[256];
-        for (int o = 0; o < widths[n_layers]; ++o) g[o] = d_out[i * widths[n_layers] + o];
-        for (int l = n_layers - 1; l >= 0; --l) {
-            int K = widths[l], O = widths[l + 1];
-            const float *Wm = params + poff[l];
-            if (l < n_layers - 1)
-                for (int o = 0; o < O; ++o) if (!(acts[i * acts_stride + aoff[l] + o] > 0)) g[o] = 0; /* ReLU' */
-            for (int k = 0; k < K; ++k) gp[k] = 0;
-            for (int o = 0; o < O; ++o) {
-                for (int k = 0; k < K; ++k) {
-                    double a_k = l == 0 ? (double)in[i * widths[0] + k] : acts[i * acts_stride + aoff[l - 1] + k];
-                    if (d_params) d_params[poff[l] + (size_t)o * K + k] += g[o] * a_k;
-                    gp[k] += (double)Wm[o * K + k] * g[o];
+    size_t n_par = po;
+#pragma omp parallel
+    {
+        double *dp_local = d_params ? (double *)calloc(n_par, sizeof(double)) : NULL; /* per-thread partial sums */
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < n; ++i) {
+            double g[256], gp[256];
+            for (int o = 0; o < widths[n_layers]; ++o) g[o] = d_out[i * widths[n_layers] + o];
+            for (int l = n_layers - 1; l >= 0; --l) {
+                int K = widths[l], O = widths[l + 1];
+                const float *Wm = params + poff[l];
+                if (l < n_layers - 1)
+                    for (int o = 0; o < O; ++o) if (!(acts[i * acts_stride + aoff[l] + o] > 0)) g[o] = 0; /* ReLU' */
+                for (int k = 0; k < K; ++k) gp[k] = 0;
+                for (int o = 0; o < O; ++o) {
+                    for (int k = 0; k < K; ++k) {
+                        double a_k = l == 0 ? (double)in[i * widths[0] + k] : acts[i * acts_stride + aoff[l - 1] + k];
+                        if (dp_local) dp_local[poff[l] + (size_t)o * K + k] += g[o] * a_k;
+                        gp[k] += (double)Wm[o * K + k] * g[o];
+                    }
+                    if (dp_local) dp_local[poff[l] + (size_t)O * K + o] += g[o];
                 }
-                if (d_params) d_params[poff[l] + (size_t)O * K + o] += g[o];
+                for (int k = 0; k < K; ++k) g[k] = gp[k];
             }
-            for (int k = 0; k < K; ++k) g[k] = gp[k];
+            if (d_in)
+                for (int k = 0; k < widths[0]; ++k) d_in[i * widths[0] + k] = g[k];
         }
-        if (d_in)
-            for (int k = 0; k < widths[0]; ++k) d_in[i * widths[0] + k] = g[k];
+        if (dp_local) {
+#pragma omp critical
+            for (size_t q = 0; q < n_par; ++q) d_params[q] += dp_local[q];
+            free(dp_local);
+        }
     }
     free(acts);
     free(out);

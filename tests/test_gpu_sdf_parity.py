@@ -90,3 +90,45 @@ def test_sdf_error_conventions():
     with pytest.raises(Exception, match="n_levels 16"):
         cabi.sdf_fwd(cabi.sdf_net(z.half(), z, n_levels=8), torch.zeros(4, 3, device=dev), torch.zeros(4, device=dev))
     cabi.sdf_fwd(cabi.sdf_net(z.half(), z), torch.zeros(0, 3, device=dev), torch.zeros(0, device=dev))  # n == 0: legal no-op
+
+
+def test_sdf_variants_and_losses(oracle):
+    """7-variant evaluation (base + 6 numerical-gradient offsets) and the fused loss kernel vs numpy fp64."""
+    from gssdf_b200 import cabi
+    dev = _dev()
+    rng = np.random.default_rng(11)
+    n, delta = 2000, 0.01
+    n_params, _ = oracle.grid_setup()
+    table = rng.uniform(-0.5, 0.5, n_params).astype(np.float32)
+    mlp = _mlp(rng, 64, 3)
+    x = rng.uniform(0.05, 0.95, (n, 3)).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    tab, half, mlp_t, xt = t(table), torch.empty(n_params, dtype=torch.float16, device=dev), t(mlp), t(x)
+    cabi.sdf_table_to_half(tab, half)
+    net = cabi.sdf_net(half, mlp_t)
+    sdf, y1 = torch.empty(7 * n, device=dev), torch.empty(7 * n, device=dev)
+    cabi.sdf_fwd(net, xt, sdf, y1, None, n_variants=7, delta=delta)
+    offs = np.array([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float32) * np.float32(delta)
+    pts = (x[None] + offs[:, None]).reshape(-1, 3).astype(np.float32)
+    r_sdf, r_y1, _ = oracle.sdf_fwd(pts, table, mlp)
+    assert_close_frac(sdf.cpu().numpy(), r_sdf, 1e-4, 1e-5, 0.0, "sdf x7")
+    # losses (ray-sample flavour: bce + eikonal ; splat-sample flavour: gs_sdf + eikonal)
+    gt = (rng.standard_normal(n) * 0.05).astype(np.float32)
+    w = rng.uniform(0, 1, n).astype(np.float32)
+    for kw in (dict(gt_sdf=gt, weights=None), dict(gt_sdf=None, weights=w)):
+        loss = torch.zeros(1, device=dev)
+        v_s, v_y = torch.empty(7 * n, device=dev), torch.empty(7 * n, device=dev)
+        cabi.sdf_loss(n, 7, sdf, y1, t(kw["gt_sdf"]) if kw["gt_sdf"] is not None else None,
+                      t(kw["weights"]) if kw["weights"] is not None else None, 10.0, 1.0, 0.1, 1e-3, delta, loss, v_s, v_y)
+        r_loss, r_vs, r_vy = oracle.sdf_losses(sdf.cpu().numpy(), y1.cpu().numpy(), n, 7, kw["gt_sdf"], kw["weights"], 10.0, 1.0, 0.1,
+                                               1e-3, delta)
+        assert abs(float(loss) - r_loss) <= 1e-4 * abs(r_loss) + 1e-7
+        assert_close_frac(v_s.cpu().numpy(), r_vs, 1e-3, 1e-5 * np.abs(r_vs).max(), 0.0, "v_sdf")
+        assert_close_frac(v_y.cpu().numpy(), r_vy, 1e-3, 1e-5 * max(np.abs(r_vy).max(), 1e-12), 0.0, "v_y1")
+    # backward through all 7 variants: gradient to x only through variant 0
+    tg, mg, vx = torch.zeros(n_params, device=dev), torch.zeros(len(mlp), device=dev), torch.empty(n, 3, device=dev)
+    cabi.sdf_bwd(net, xt, v_s, v_y, tg, mg, vx, n_variants=7, delta=delta)
+    r_tg, r_mg, r_vx = oracle.sdf_bwd(pts, table, mlp, v_s.cpu().numpy(), v_y.cpu().numpy())
+    assert_close_frac(mg.cpu().numpy(), r_mg, 1e-4, 1e-5 * np.abs(r_mg).max(), 0.0, "mlp grad x7")
+    assert np.linalg.norm(tg.cpu().numpy() - r_tg) <= 3e-4 * np.linalg.norm(r_tg)
+    assert np.linalg.norm(vx.cpu().numpy() - r_vx[:n]) <= 1e-3 * np.linalg.norm(r_vx[:n])
