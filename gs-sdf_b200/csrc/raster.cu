@@ -33,8 +33,9 @@ constexpr int kRasterThreads = 256;
 constexpr int kBatch = 256;  // splats per shared-memory stage
 constexpr float kNearN = 0.05f, kFarN = 100.f;  // hard-coded in the reference (Fwd.cu:368-369)
 constexpr float kAlphaThreshold = 1.f / 255.f;  // GSF/include/Common.h:53
-constexpr int kRecF4 = 6;                        // record = 6 float4 = 96 B: 16 render floats + ellipse (cx, cy, a, b, c) + pad
+constexpr int kRecF4 = 4;                        // render record = 4 float4 = 64 B: M[9], opacity, rgb[3], normal[3]
 constexpr int kRecBytes = kRecF4 * 16;
+constexpr int kConicF4 = 2;                      // culling conic = 6 normalised coefficients (+2 pad) = 32 B per visible splat
 
 // ---------------------------------------------------------------------------------------------
 // record packing
@@ -42,8 +43,8 @@ constexpr int kRecBytes = kRecF4 * 16;
 __global__ void __launch_bounds__(256)
 pack_records_kernel(const gssdf_counts *counts, const float *__restrict__ ray_transforms,
                     const float *__restrict__ colors, const float *__restrict__ opacities,
-                    const float *__restrict__ normals, float4 *__restrict__ rec, float *__restrict__ zero_a,
-                    int zero_a_stride, float extent) {
+                    const float *__restrict__ normals, float4 *__restrict__ rec, float4 *__restrict__ conic,
+                    float *__restrict__ zero_a, int zero_a_stride, float extent) {
     const int nnz = counts->nnz;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnz) return;
@@ -85,8 +86,8 @@ pack_records_kernel(const gssdf_counts *counts, const float *__restrict__ ray_tr
             for (int e = 0; e < 6; ++e) q[e] = 0.0;
         }
     }
-    r[4] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
-    r[5] = make_float4((float)q[4], (float)q[5], 0.f, 0.f);
+    conic[kConicF4 * (int64_t)i] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
+    conic[kConicF4 * (int64_t)i + 1] = make_float4((float)q[4], (float)q[5], 0.f, 0.f);
     if (zero_a) {
         for (int k = 0; k < zero_a_stride; ++k) zero_a[(int64_t)i * zero_a_stride + k] = 0.f;
     }
@@ -119,10 +120,10 @@ __device__ __forceinline__ void pixel_of_thread(int &lx, int &ly) {
 }
 
 struct __align__(16) Stage {
-    float4 rec[kBatch * kRecF4];  // 24 KB
+    float4 rec[kBatch * kRecF4];  // 16 KB
     int ids[kBatch];              // packed splat index of each record
+    int meta[kBatch];             // (index in the tile's sorted list << 8) | warp mask (bit w: the conic touches warp w's 8x4 block)
     float acc[kBatch];            // per-splat tile accumulator (visibility)
-    unsigned char mask[kBatch];   // bit w: the splat's ellipse touches warp w's 8x4 pixel block
 };
 
 // Conic in tile-local pixel coordinates: Q(x,y) = a x^2 + 2 b x y + c y^2 + 2 d x + 2 e y + f
@@ -161,8 +162,7 @@ __device__ __forceinline__ float conic_min_rect(const Conic &q, float x0, float 
 }
 
 // 8-bit warp mask of record t for the tile whose first pixel centre is (ox, oy) (global pixel coordinates)
-__device__ __forceinline__ unsigned cull_mask(const float4 *rec_t, float ox, float oy) {
-    const float4 g0 = rec_t[4], g1 = rec_t[5];
+__device__ __forceinline__ unsigned cull_mask(const float4 g0, const float4 g1, float ox, float oy) {
     // shift the conic to tile-local coordinates (x = ox + x')
     Conic q;
     q.a = g0.x; q.b = g0.y; q.c = g0.z;
@@ -182,15 +182,55 @@ __device__ __forceinline__ unsigned cull_mask(const float4 *rec_t, float ox, flo
     return mask;
 }
 
-// issue the gather of batch [start, start+n) (n <= kBatch) into `st`; every thread arrives once
+// ---------------------------------------------------------------------------------------------
+// culling pass: one CTA per tile walks the tile's sorted list once, tests every splat's conic against the tile and its
+// 8 warp blocks, and writes the survivors IN ORDER into clist[rs .. rs + ccount[tile]) as (packed index, (list position << 8) |
+// warp mask). Forward and backward then iterate the (much shorter) culled lists; nothing they skip can contribute.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRasterThreads)
+tile_cull_kernel(int C, int tw, int th, const int32_t *__restrict__ offsets, const gssdf_counts *counts,
+                 const int32_t *__restrict__ flatten_ids, const float4 *__restrict__ conic, int2 *__restrict__ clist,
+                 int32_t *__restrict__ ccount) {
+    __shared__ int s_wc[kRasterThreads / 32];
+    const TileInfo ti = tile_info(C, tw, th, offsets, counts);
+    const float ox = ti.tx * kTile + 0.5f, oy = ti.ty * kTile + 0.5f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int count = 0;
+    for (int c0 = ti.rs; c0 < ti.re; c0 += kRasterThreads) {
+        const int idx = c0 + threadIdx.x;
+        int g = 0;
+        unsigned mask = 0u;
+        if (idx < ti.re) {
+            g = flatten_ids[idx];
+            mask = cull_mask(__ldg(conic + kConicF4 * (int64_t)g), __ldg(conic + kConicF4 * (int64_t)g + 1), ox, oy);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, mask != 0u);
+        if (lane == 0) s_wc[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kRasterThreads / 32; ++w) {
+            const int c = s_wc[w];
+            if (w < warp) before += c;
+            total += c;
+        }
+        if (mask != 0u) clist[ti.rs + count + before + __popc(bal & ((1u << lane) - 1u))] = make_int2(g, ((idx - ti.rs) << 8) | (int)mask);
+        count += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ccount[blockIdx.x] = count;
+}
+
+// issue the gather of culled-list entries [start, start+n) (n <= kBatch) into `st`; every thread arrives once
 __device__ __forceinline__ void issue_batch(Stage &st, uint64_t *bar, const float4 *__restrict__ rec,
-                                            const int32_t *__restrict__ flatten_ids, int start, int n) {
+                                            const int2 *__restrict__ clist, int start, int n) {
     const int t = threadIdx.x;
     if (t < n) {
-        const int g = flatten_ids[start + t];
-        st.ids[t] = g;
+        const int2 e = clist[start + t];
+        st.ids[t] = e.x;
+        st.meta[t] = e.y;
         st.acc[t] = 0.f;
-        bulk_g2s(&st.rec[t * kRecF4], rec + kRecF4 * (int64_t)g, kRecBytes, bar);
+        bulk_g2s(&st.rec[t * kRecF4], rec + kRecF4 * (int64_t)e.x, kRecBytes, bar);
         mbar_arrive_expect_tx(bar, kRecBytes);
     } else {
         mbar_arrive(bar);
@@ -201,7 +241,8 @@ __device__ __forceinline__ void issue_batch(Stage &st, uint64_t *bar, const floa
 // forward
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRasterThreads)
-raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restrict__ rec, int tw, int th) {
+raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restrict__ rec, const int2 *__restrict__ clist,
+                      const int32_t *__restrict__ ccount, int tw, int th) {
     extern __shared__ __align__(16) unsigned char s_raw_fwd[];
     Stage *s_stage = reinterpret_cast<Stage *>(s_raw_fwd);
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -222,10 +263,11 @@ raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restric
     }
     __syncthreads();
 
-    const int n_total = ti.re - ti.rs;
+    const int n_total = ccount[blockIdx.x];  // culled list length; entries live at clist[rs ..)
+    const int c_end = ti.rs + n_total;
     const int nb = (n_total + kBatch - 1) / kBatch;
-    if (nb > 0) issue_batch(s_stage[0], &s_bar[0], rec, a.flatten_ids, ti.rs, min(kBatch, n_total));
-    if (nb > 1) issue_batch(s_stage[1], &s_bar[1], rec, a.flatten_ids, ti.rs + kBatch, min(kBatch, n_total - kBatch));
+    if (nb > 0) issue_batch(s_stage[0], &s_bar[0], rec, clist, ti.rs, min(kBatch, n_total));
+    if (nb > 1) issue_batch(s_stage[1], &s_bar[1], rec, clist, ti.rs + kBatch, min(kBatch, n_total - kBatch));
 
     float T = 1.f;
     float pc0 = 0.f, pc1 = 0.f, pc2 = 0.f, pn0 = 0.f, pn1 = 0.f, pn2 = 0.f;
@@ -239,18 +281,18 @@ raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restric
         mbar_wait(&s_bar[b & 1], (b >> 1) & 1);
         waited = b + 1;
         const int start = ti.rs + b * kBatch;
-        const int bn = min(kBatch, ti.re - start);
-        if (threadIdx.x < bn)
-            st.mask[threadIdx.x] = (unsigned char)cull_mask(&st.rec[threadIdx.x * kRecF4], ti.tx * kTile + 0.5f, ti.ty * kTile + 0.5f);
-        __syncthreads();
+        const int bn = min(kBatch, c_end - start);
         const int warp_id = threadIdx.x >> 5;
         for (int t0 = 0; t0 < bn; t0 += 32) {
           if (__all_sync(0xffffffffu, done)) break;
-          unsigned todo = __ballot_sync(0xffffffffu, (t0 + lane < bn) && ((st.mask[t0 + lane] >> warp_id) & 1));
+          const int my_meta = (t0 + lane < bn) ? st.meta[t0 + lane] : 0;
+          unsigned todo = __ballot_sync(0xffffffffu, (my_meta >> warp_id) & 1);
           while (todo) {
-            const int t = t0 + __ffs(todo) - 1;
+            const int src = __ffs(todo) - 1;
+            const int t = t0 + src;
             todo &= todo - 1;
             if (__all_sync(0xffffffffu, done)) break;
+            const int sorted_idx = ti.rs + (__shfl_sync(0xffffffffu, my_meta, src) >> 8);  // position in the reference's sorted list
             const float4 r0 = st.rec[t * kRecF4 + 0], r1 = st.rec[t * kRecF4 + 1], r2 = st.rec[t * kRecF4 + 2], r3 = st.rec[t * kRecF4 + 3];
             // M rows: u = (r0.x r0.y r0.z) v = (r0.w r1.x r1.y) w = (r1.z r1.w r2.x)
             const float hux = px * r1.z - r0.x, huy = px * r1.w - r0.y, huz = px * r2.x - r0.z;
@@ -277,8 +319,8 @@ raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restric
                 distort += (m * m * A + M1 - 2.f * m * M2) * vis;
                 M1 += m * m * vis;
                 M2 += m * vis;
-                if (T > 0.5f) { median_depth = depth; median_idx = start + t; }
-                cur_idx = start + t;
+                if (T > 0.5f) { median_depth = depth; median_idx = sorted_idx; }
+                cur_idx = sorted_idx;
                 T = next_T;
             }
             if (__any_sync(0xffffffffu, ok)) {
@@ -297,7 +339,7 @@ raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restric
         __syncthreads();  // stage b&1 fully consumed -> refill with batch b+2
         if (b + 2 < nb) {
             const int s2 = ti.rs + (b + 2) * kBatch;
-            issue_batch(st, &s_bar[b & 1], rec, a.flatten_ids, s2, min(kBatch, ti.re - s2));
+            issue_batch(st, &s_bar[b & 1], rec, clist, s2, min(kBatch, c_end - s2));
         }
     }
     // never leave the CTA with a bulk copy in flight into its shared memory
@@ -331,23 +373,24 @@ raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restric
 struct __align__(16) BwdStage {
     float4 rec[kBatch * kRecF4];
     int ids[kBatch];
-    unsigned char mask[kBatch];
+    int meta[kBatch];
     float grad[kBatch * 16];  // per-splat tile gradient record: rgb[3] n[3] u[3] v[3] w[3] opacity
     float gabs[kBatch * 2];
 };
 
 __device__ __forceinline__ void issue_batch_bwd(BwdStage &st, uint64_t *bar, const float4 *__restrict__ rec,
-                                                const int32_t *__restrict__ flatten_ids, int last, int n) {
-    // batch covers sorted indices last, last-1, ..., last-n+1 (slot t <-> index last - t)
+                                                const int2 *__restrict__ clist, int last, int n) {
+    // batch covers culled-list entries last, last-1, ..., last-n+1 (slot t <-> entry last - t): back to front
     const int t = threadIdx.x;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) st.grad[k * kBatch + t] = 0.f;  // [16][kBatch] transposed zero-fill (conflict-free)
+    for (int k = 0; k < 16; ++k) st.grad[k * kBatch + t] = 0.f;  // flat, conflict-free zero-fill of the [kBatch][16] records
     st.gabs[t] = 0.f;
     st.gabs[kBatch + t] = 0.f;
     if (t < n) {
-        const int g = flatten_ids[last - t];
-        st.ids[t] = g;
-        bulk_g2s(&st.rec[t * kRecF4], rec + kRecF4 * (int64_t)g, kRecBytes, bar);
+        const int2 e = clist[last - t];
+        st.ids[t] = e.x;
+        st.meta[t] = e.y;
+        bulk_g2s(&st.rec[t * kRecF4], rec + kRecF4 * (int64_t)e.x, kRecBytes, bar);
         mbar_arrive_expect_tx(bar, kRecBytes);
     } else {
         mbar_arrive(bar);
@@ -356,14 +399,15 @@ __device__ __forceinline__ void issue_batch_bwd(BwdStage &st, uint64_t *bar, con
 
 template <bool ABS>
 __global__ void __launch_bounds__(kRasterThreads)
-raster2dgs_bwd_kernel(const gssdf_raster2dgs_bwd_args a, const float4 *__restrict__ rec, float *__restrict__ vrec,
-                      int tw, int th) {
+raster2dgs_bwd_kernel(const gssdf_raster2dgs_bwd_args a, const float4 *__restrict__ rec, const int2 *__restrict__ clist,
+                      const int32_t *__restrict__ ccount, float *__restrict__ vrec, int tw, int th) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     BwdStage *s_stage = reinterpret_cast<BwdStage *>(s_raw);
     __shared__ __align__(8) uint64_t s_bar[2];
     const TileInfo ti = tile_info(a.C, tw, th, a.offsets, a.counts);
-    const int n_total = ti.re - ti.rs;
+    const int n_total = ccount[blockIdx.x];  // culled list length
     if (n_total <= 0) return;
+    const int c_last = ti.rs + n_total - 1;
     const int W = a.image_width, H = a.image_height;
     int lx, ly;
     pixel_of_thread(lx, ly);
@@ -403,26 +447,24 @@ raster2dgs_bwd_kernel(const gssdf_raster2dgs_bwd_args a, const float4 *__restric
 
     // process sorted indices re-1 ... rs in batches of kBatch, back to front
     const int nb = (n_total + kBatch - 1) / kBatch;
-    issue_batch_bwd(s_stage[0], &s_bar[0], rec, a.flatten_ids, ti.re - 1, min(kBatch, n_total));
-    if (nb > 1) issue_batch_bwd(s_stage[1], &s_bar[1], rec, a.flatten_ids, ti.re - 1 - kBatch, min(kBatch, n_total - kBatch));
+    issue_batch_bwd(s_stage[0], &s_bar[0], rec, clist, c_last, min(kBatch, n_total));
+    if (nb > 1) issue_batch_bwd(s_stage[1], &s_bar[1], rec, clist, c_last - kBatch, min(kBatch, n_total - kBatch));
 
     for (int b = 0; b < nb; ++b) {
         BwdStage &st = s_stage[b & 1];
         mbar_wait(&s_bar[b & 1], (b >> 1) & 1);
-        const int last = ti.re - 1 - b * kBatch;  // sorted index held by slot 0
+        const int last = c_last - b * kBatch;  // culled-list entry held by slot 0
         const int bn = min(kBatch, last - ti.rs + 1);
-        if (threadIdx.x < bn)
-            st.mask[threadIdx.x] = (unsigned char)cull_mask(&st.rec[threadIdx.x * kRecF4], ti.tx * kTile + 0.5f, ti.ty * kTile + 0.5f);
-        __syncthreads();
         const int warp_id = threadIdx.x >> 5;
-        // skip the slots behind every pixel of this warp's last contributor (Bwd.cu:333)
-        const int t_begin = max(0, last - warp_bin_final);
-        for (int t0 = t_begin & ~31; t0 < bn; t0 += 32) {
-          unsigned todo = __ballot_sync(0xffffffffu, (t0 + lane < bn) && (t0 + lane >= t_begin) && ((st.mask[t0 + lane] >> warp_id) & 1));
+        for (int t0 = 0; t0 < bn; t0 += 32) {
+          const int my_meta = (t0 + lane < bn) ? st.meta[t0 + lane] : 0;
+          // skip the entries behind every pixel of this warp's last contributor (Bwd.cu:333) and those culled for this warp
+          unsigned todo = __ballot_sync(0xffffffffu, ((my_meta >> warp_id) & 1) && (ti.rs + (my_meta >> 8) <= warp_bin_final));
           while (todo) {
-            const int t = t0 + __ffs(todo) - 1;
+            const int src = __ffs(todo) - 1;
+            const int t = t0 + src;
             todo &= todo - 1;
-            const int idx = last - t;
+            const int idx = ti.rs + (__shfl_sync(0xffffffffu, my_meta, src) >> 8);  // position in the reference's sorted list
             const float4 r0 = st.rec[t * kRecF4 + 0], r1 = st.rec[t * kRecF4 + 1], r2 = st.rec[t * kRecF4 + 2], r3 = st.rec[t * kRecF4 + 3];
             const float hux = px * r1.z - r0.x, huy = px * r1.w - r0.y, huz = px * r2.x - r0.z;
             const float hvx = py * r1.z - r0.w, hvy = py * r1.w - r1.x, hvz = py * r2.x - r1.y;
@@ -499,7 +541,7 @@ raster2dgs_bwd_kernel(const gssdf_raster2dgs_bwd_args a, const float4 *__restric
             }
             h1 += __shfl_xor_sync(0xffffffffu, h1, 1);
             const int comp = lane >> 1;  // gradient component held by this lane pair
-            if ((lane & 1) == 0) atomicAdd(&st.grad[comp * kBatch + t], h1);
+            if ((lane & 1) == 0) atomicAdd(&st.grad[t * 16 + comp], h1);  // 16 consecutive words: conflict-free
             if (ABS) {
                 // |sum over the warp's 8x4 pixel block of dL/dM_u.z (resp. M_v.z)| * M_w.z
                 if (lane == 16) atomicAdd(&st.gabs[t], fabsf(h1 * r2.x));           // comp 8  = u.z
@@ -511,7 +553,7 @@ raster2dgs_bwd_kernel(const gssdf_raster2dgs_bwd_args a, const float4 *__restric
         // flush: one 64-byte RED burst per (tile, splat); 16 consecutive threads cover one record
         for (int e = threadIdx.x; e < bn * 16; e += kRasterThreads) {
             const int t = e >> 4, k = e & 15;
-            const float v = st.grad[k * kBatch + t];
+            const float v = st.grad[e];
             if (v != 0.f) atomicAdd(vrec + 16 * (int64_t)st.ids[t] + k, v);
         }
         if (ABS) {
@@ -523,8 +565,8 @@ raster2dgs_bwd_kernel(const gssdf_raster2dgs_bwd_args a, const float4 *__restric
         }
         __syncthreads();
         if (b + 2 < nb) {
-            const int l2 = ti.re - 1 - (b + 2) * kBatch;
-            issue_batch_bwd(st, &s_bar[b & 1], rec, a.flatten_ids, l2, min(kBatch, l2 - ti.rs + 1));
+            const int l2 = c_last - (b + 2) * kBatch;
+            issue_batch_bwd(st, &s_bar[b & 1], rec, clist, l2, min(kBatch, l2 - ti.rs + 1));
         }
     }
 }
@@ -643,9 +685,36 @@ extern "C" int gssdf_l1_loss(const gssdf_l1_loss_args *a, gssdf_stream_t stream)
     return GSSDF_OK;
 }
 
-extern "C" size_t gssdf_raster2dgs_workspace_bytes(int32_t cap) { return align_up((size_t)(cap > 0 ? cap : 1) * kRecBytes, 256); }
-extern "C" size_t gssdf_raster2dgs_bwd_workspace_bytes(int32_t cap) {
-    return align_up((size_t)(cap > 0 ? cap : 1) * kRecBytes, 256) + align_up((size_t)(cap > 0 ? cap : 1) * 64, 256);
+struct RasterWs {
+    float4 *rec;
+    float4 *conic;
+    int2 *clist;
+    int32_t *ccount;
+    float4 *vrec;
+    size_t fwd_bytes, bwd_bytes;
+};
+
+static RasterWs carve_ws(void *base, int C, int W, int H, int cap, int64_t isect_cap) {
+    const size_t n = (size_t)(cap > 0 ? cap : 1), I = (size_t)(isect_cap > 0 ? isect_cap : 1);
+    const size_t tiles = (size_t)(C > 0 ? C : 1) * cdiv(W > 0 ? W : 1, kTile) * cdiv(H > 0 ? H : 1, kTile);
+    char *p = reinterpret_cast<char *>(base);
+    RasterWs w;
+    size_t off = 0;
+    w.rec = reinterpret_cast<float4 *>(p + off); off += align_up(n * kRecBytes, 256);
+    w.conic = reinterpret_cast<float4 *>(p + off); off += align_up(n * kConicF4 * 16, 256);
+    w.clist = reinterpret_cast<int2 *>(p + off); off += align_up(I * sizeof(int2), 256);
+    w.ccount = reinterpret_cast<int32_t *>(p + off); off += align_up(tiles * sizeof(int32_t), 256);
+    w.fwd_bytes = off;
+    w.vrec = reinterpret_cast<float4 *>(p + off); off += align_up(n * 64, 256);
+    w.bwd_bytes = off;
+    return w;
+}
+
+extern "C" size_t gssdf_raster2dgs_workspace_bytes(int32_t C, int32_t W, int32_t H, int32_t cap, int64_t isect_cap) {
+    return carve_ws(nullptr, C, W, H, cap, isect_cap).fwd_bytes;
+}
+extern "C" size_t gssdf_raster2dgs_bwd_workspace_bytes(int32_t C, int32_t W, int32_t H, int32_t cap, int64_t isect_cap) {
+    return carve_ws(nullptr, C, W, H, cap, isect_cap).bwd_bytes;
 }
 
 static int check_raster_common(const char *who, int C, int W, int H, int tile_size, int channels) {
@@ -653,6 +722,22 @@ static int check_raster_common(const char *who, int C, int W, int H, int tile_si
     GSSDF_REQUIRE(tile_size == kTile, GSSDF_EUNSUPPORTED, "%s: tile_size %d unsupported (GS-SDF renders with 16)", who, tile_size);
     GSSDF_REQUIRE(channels == 3, channels <= 0 || channels > 512 ? GSSDF_EINVAL : GSSDF_EUNSUPPORTED,
                   "%s: Unsupported number of color channels: %d", who, channels);
+    return GSSDF_OK;
+}
+
+// pack the render records + culling conics, then build the culled per-tile lists
+static int pack_and_cull(const char *who, const RasterWs &w, const gssdf_counts *counts, int C, int W, int H, int cap,
+                         const float *ray_transforms, const float *colors, const float *opacities, const float *normals,
+                         const int32_t *offsets, const int32_t *flatten_ids, float *zero_a, int zero_stride, cudaStream_t st) {
+    const int tw = cdiv(W, kTile), th = cdiv(H, kTile);
+    if (cap > 0) {
+        pack_records_kernel<<<cdiv(cap, 256), 256, 0, st>>>(counts, ray_transforms, colors, opacities, normals, w.rec, w.conic, zero_a,
+                                                           zero_stride, (float)max(W, H));
+        GSSDF_LAUNCH_OK("pack_records_kernel");
+    }
+    tile_cull_kernel<<<C * tw * th, kRasterThreads, 0, st>>>(C, tw, th, offsets, counts, flatten_ids, w.conic, w.clist, w.ccount);
+    GSSDF_LAUNCH_OK("tile_cull_kernel");
+    (void)who;
     return GSSDF_OK;
 }
 
@@ -665,19 +750,19 @@ extern "C" int gssdf_raster2dgs_fwd(const gssdf_raster2dgs_fwd_args *a, gssdf_st
                   GSSDF_EINVAL, "raster2dgs_fwd: null output / counts / offsets");
     GSSDF_REQUIRE(a->cap == 0 || (a->ray_transforms && a->colors && a->opacities && a->normals && a->flatten_ids && a->visibilities),
                   GSSDF_EINVAL, "raster2dgs_fwd: null splat input");
-    GSSDF_REQUIRE(a->cap == 0 || (a->workspace && a->workspace_bytes >= gssdf_raster2dgs_workspace_bytes(a->cap)), GSSDF_ENOMEM,
-                  "raster2dgs_fwd: workspace too small");
+    GSSDF_REQUIRE(a->isect_cap >= 0, GSSDF_EINVAL, "raster2dgs_fwd: negative isect_cap");
+    GSSDF_REQUIRE(a->workspace && a->workspace_bytes >= gssdf_raster2dgs_workspace_bytes(a->C, a->image_width, a->image_height, a->cap,
+                                                                                         a->isect_cap),
+                  GSSDF_ENOMEM, "raster2dgs_fwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int tw = cdiv(a->image_width, kTile), th = cdiv(a->image_height, kTile);
-    float4 *rec = reinterpret_cast<float4 *>(a->workspace);
-    if (a->cap > 0) {
-        pack_records_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(a->counts, a->ray_transforms, a->colors, a->opacities, a->normals,
-                                                              rec, a->visibilities, 1, (float)max(a->image_width, a->image_height));
-        GSSDF_LAUNCH_OK("pack_records_kernel");
-    }
-    if (a->prof_start) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_start, st));
+    const RasterWs w = carve_ws(a->workspace, a->C, a->image_width, a->image_height, a->cap, a->isect_cap);
+    rc = pack_and_cull("raster2dgs_fwd", w, a->counts, a->C, a->image_width, a->image_height, a->cap, a->ray_transforms, a->colors,
+                       a->opacities, a->normals, a->offsets, a->flatten_ids, a->visibilities, 1, st);
+    if (rc) return rc;
     GSSDF_CUDA_OK(cudaFuncSetAttribute(raster2dgs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(Stage))));
-    raster2dgs_fwd_kernel<<<a->C * tw * th, kRasterThreads, 2 * sizeof(Stage), st>>>(*a, rec, tw, th);
+    if (a->prof_start) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_start, st));
+    raster2dgs_fwd_kernel<<<a->C * tw * th, kRasterThreads, 2 * sizeof(Stage), st>>>(*a, w.rec, w.clist, w.ccount, tw, th);
     GSSDF_LAUNCH_OK("raster2dgs_fwd_kernel");
     if (a->prof_stop) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_stop, st));
     return GSSDF_OK;
@@ -695,28 +780,32 @@ extern "C" int gssdf_raster2dgs_bwd(const gssdf_raster2dgs_bwd_args *a, gssdf_st
                       a->v_render_alphas && a->v_render_normals && a->v_render_median,
                   GSSDF_EINVAL, "raster2dgs_bwd: null input");
     GSSDF_REQUIRE(a->v_ray_transforms && a->v_colors && a->v_opacities && a->v_normals, GSSDF_EINVAL, "raster2dgs_bwd: null output");
-    GSSDF_REQUIRE(a->workspace && a->workspace_bytes >= gssdf_raster2dgs_bwd_workspace_bytes(a->cap), GSSDF_ENOMEM,
-                  "raster2dgs_bwd: workspace too small");
+    GSSDF_REQUIRE(a->isect_cap >= 0, GSSDF_EINVAL, "raster2dgs_bwd: negative isect_cap");
+    GSSDF_REQUIRE(a->workspace && a->workspace_bytes >= gssdf_raster2dgs_bwd_workspace_bytes(a->C, a->image_width, a->image_height,
+                                                                                             a->cap, a->isect_cap),
+                  GSSDF_ENOMEM, "raster2dgs_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int tw = cdiv(a->image_width, kTile), th = cdiv(a->image_height, kTile);
-    float4 *rec = reinterpret_cast<float4 *>(a->workspace);
-    float4 *vrec = reinterpret_cast<float4 *>(reinterpret_cast<char *>(a->workspace) + align_up((size_t)a->cap * kRecBytes, 256));
-    pack_records_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(a->counts, a->ray_transforms, a->colors, a->opacities, a->normals, rec,
-                                                          reinterpret_cast<float *>(vrec), 16, (float)max(a->image_width, a->image_height));
-    GSSDF_LAUNCH_OK("pack_records_kernel");
+    const RasterWs w = carve_ws(a->workspace, a->C, a->image_width, a->image_height, a->cap, a->isect_cap);
+    if (!a->reuse_fwd) {
+        rc = pack_and_cull("raster2dgs_bwd", w, a->counts, a->C, a->image_width, a->image_height, a->cap, a->ray_transforms, a->colors,
+                           a->opacities, a->normals, a->offsets, a->flatten_ids, nullptr, 0, st);
+        if (rc) return rc;
+    }
+    GSSDF_CUDA_OK(cudaMemsetAsync(w.vrec, 0, (size_t)a->cap * 64, st));
     const size_t smem = 2 * sizeof(BwdStage);
+    if (a->v_means2d_abs) GSSDF_CUDA_OK(cudaMemsetAsync(a->v_means2d_abs, 0, (size_t)a->cap * 2 * sizeof(float), st));
     if (a->prof_start) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_start, st));
     if (a->v_means2d_abs) {
-        GSSDF_CUDA_OK(cudaMemsetAsync(a->v_means2d_abs, 0, (size_t)a->cap * 2 * sizeof(float), st));
         GSSDF_CUDA_OK(cudaFuncSetAttribute(raster2dgs_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        raster2dgs_bwd_kernel<true><<<a->C * tw * th, kRasterThreads, smem, st>>>(*a, rec, reinterpret_cast<float *>(vrec), tw, th);
+        raster2dgs_bwd_kernel<true><<<a->C * tw * th, kRasterThreads, smem, st>>>(*a, w.rec, w.clist, w.ccount, reinterpret_cast<float *>(w.vrec), tw, th);
     } else {
         GSSDF_CUDA_OK(cudaFuncSetAttribute(raster2dgs_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        raster2dgs_bwd_kernel<false><<<a->C * tw * th, kRasterThreads, smem, st>>>(*a, rec, reinterpret_cast<float *>(vrec), tw, th);
+        raster2dgs_bwd_kernel<false><<<a->C * tw * th, kRasterThreads, smem, st>>>(*a, w.rec, w.clist, w.ccount, reinterpret_cast<float *>(w.vrec), tw, th);
     }
     GSSDF_LAUNCH_OK("raster2dgs_bwd_kernel");
     if (a->prof_stop) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_stop, st));
-    raster_bwd_finalize_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, vrec);
+    raster_bwd_finalize_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, w.vrec);
     GSSDF_LAUNCH_OK("raster_bwd_finalize_kernel");
     return GSSDF_OK;
 }

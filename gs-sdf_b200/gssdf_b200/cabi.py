@@ -111,13 +111,14 @@ def tile_encode(Cn, W, H, tile_size, cap, counts, means2d, radii, depths, camera
 
 
 def raster2dgs_fwd(Cn, W, H, tile_size, channels, cap, counts, means2d, ray_transforms, colors, opacities, normals,
-                   backgrounds, offsets, flatten_ids, out, ws, prof=None):
-    need = lib().gssdf_raster2dgs_workspace_bytes(cap)
+                   backgrounds, offsets, flatten_ids, out, ws, prof=None, isect_cap=None):
+    isect_cap = int(flatten_ids.shape[0]) if isect_cap is None else int(isect_cap)
+    need = lib().gssdf_raster2dgs_workspace_bytes(Cn, W, H, cap, _lib.C.c_int64(isect_cap))
     w = ws.get(need)
     a = make_args("gssdf_raster2dgs_fwd_args", C=Cn, image_width=W, image_height=H, tile_size=tile_size,
                   channels=channels, cap=cap, counts=counts, means2d=means2d, ray_transforms=ray_transforms,
                   colors=colors, opacities=opacities, normals=normals, backgrounds=backgrounds, offsets=offsets,
-                  flatten_ids=flatten_ids, render_colors=out["render_colors"], render_depths=out["render_depths"],
+                  flatten_ids=flatten_ids, isect_cap=isect_cap, render_colors=out["render_colors"], render_depths=out["render_depths"],
                   render_alphas=out["render_alphas"], render_normals=out["render_normals"],
                   render_distort=out["render_distort"], render_median=out["render_median"], render_Ts=out["render_Ts"],
                   last_ids=out["last_ids"], median_ids=out["median_ids"], visibilities=out["visibilities"], workspace=w,
@@ -129,13 +130,15 @@ def raster2dgs_fwd(Cn, W, H, tile_size, channels, cap, counts, means2d, ray_tran
 def raster2dgs_bwd(Cn, W, H, tile_size, channels, cap, counts, means2d, ray_transforms, colors, opacities, normals,
                    backgrounds, offsets, flatten_ids, render_alphas, render_Ts, last_ids, median_ids, v_render_colors,
                    v_render_depths, v_render_alphas, v_render_normals, v_render_median, out, ws, v_render_distort=None,
-                   prof=None):
-    need = lib().gssdf_raster2dgs_bwd_workspace_bytes(cap)
+                   prof=None, isect_cap=None, reuse_fwd=False):
+    isect_cap = int(flatten_ids.shape[0]) if isect_cap is None else int(isect_cap)
+    need = lib().gssdf_raster2dgs_bwd_workspace_bytes(Cn, W, H, cap, _lib.C.c_int64(isect_cap))
     w = ws.get(need)
     a = make_args("gssdf_raster2dgs_bwd_args", C=Cn, image_width=W, image_height=H, tile_size=tile_size,
                   channels=channels, cap=cap, counts=counts, means2d=means2d, ray_transforms=ray_transforms,
                   colors=colors, opacities=opacities, normals=normals, backgrounds=backgrounds, offsets=offsets,
-                  flatten_ids=flatten_ids, render_alphas=render_alphas, render_Ts=render_Ts, last_ids=last_ids,
+                  flatten_ids=flatten_ids, isect_cap=isect_cap, reuse_fwd=int(bool(reuse_fwd)), render_alphas=render_alphas,
+                  render_Ts=render_Ts, last_ids=last_ids,
                   median_ids=median_ids, v_render_colors=v_render_colors, v_render_depths=v_render_depths,
                   v_render_alphas=v_render_alphas, v_render_normals=v_render_normals, v_render_distort=v_render_distort,
                   v_render_median=v_render_median, v_means2d=out.get("v_means2d"), v_means2d_abs=out.get("v_means2d_abs"),

@@ -56,6 +56,9 @@ class SplatRenderer:
         self.v_scales, self.v_opac, self.v_sh = fg[o[2]:o[3]].view(N, 3), fg[o[3]:o[4]], fg[o[4]:o[5]].view(N, K, 3)
         self.loss = torch.zeros(1, **f32)
         self.ws = cabi.Workspace(device)
+        # dedicated raster workspace (records, conics, culled lists | gradient records): the backward reuses the forward's part
+        self.raster_ws = cabi.Workspace(device)
+        self.raster_ws.get(cabi.lib().gssdf_raster2dgs_bwd_workspace_bytes(C, W, H, cap, cabi._lib.C.c_int64(self.isect_cap)))
         self.prof_fwd = self.prof_bwd = None  # optional (start, stop) torch.cuda.Event pairs around the raster kernels
 
     # -- forward ------------------------------------------------------------------------------
@@ -68,8 +71,8 @@ class SplatRenderer:
         cabi.tile_encode(C, W, H, self.tile, cap, self.counts, self.p["means2d"], self.p["radii"], self.p["depths"],
                          self.p["camera_ids"], self.isect_cap, None, None, self.flatten_ids, self.offsets, self.ws)
         cabi.raster2dgs_fwd(C, W, H, self.tile, 3, cap, self.counts, self.p["means2d"], self.p["ray_transforms"], self.colors,
-                            self.p["pt_opacities"], self.p["normals"], None, self.offsets, self.flatten_ids, self.r, self.ws,
-                            prof=self.prof_fwd)
+                            self.p["pt_opacities"], self.p["normals"], None, self.offsets, self.flatten_ids, self.r, self.raster_ws,
+                            prof=self.prof_fwd, isect_cap=self.isect_cap)
         cabi.render_post_fwd(C, W, H, viewmats, self.r["render_colors"], self.r["render_depths"], self.r["render_alphas"],
                              self.r["render_normals"], self.out_colors, self.out_normals)
         return self.out_colors, self.out_normals
@@ -89,7 +92,7 @@ class SplatRenderer:
                             self.p["pt_opacities"], self.p["normals"], None, self.offsets, self.flatten_ids,
                             self.r["render_alphas"], self.r["render_Ts"], self.r["last_ids"], self.r["median_ids"],
                             self.v_r["colors"], self.v_r["depths"], self.v_r["alphas"], self.v_r["normals"],
-                            self.v_r["median"], self.g, self.ws, prof=self.prof_bwd)
+                            self.v_r["median"], self.g, self.raster_ws, prof=self.prof_bwd, isect_cap=self.isect_cap, reuse_fwd=True)
         cabi.view_colors_bwd(viewmats, means, sh, self.sh_degree, cap, self.counts, self.p["camera_ids"],
                              self.p["gaussian_ids"], self.p["radii"], self.colors, self.g["v_colors"], self.v_sh, self.v_means)
         cabi.project2dgs_bwd(means, quats, scales, viewmats, Ks, W, H, cap, self.counts, self.p["camera_ids"],

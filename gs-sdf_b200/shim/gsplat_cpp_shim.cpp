@@ -161,8 +161,8 @@ struct ViewColors : public torch::autograd::Function<ViewColors> {
 // ---------------------------------------------------------------------------------------------
 struct Raster2DGS : public torch::autograd::Function<Raster2DGS> {
     static tensor_list forward(AutogradContext *ctx, const Tensor &means2d, const Tensor &rt, const Tensor &colors, const Tensor &opac,
-                               const Tensor &normals, const Tensor &densify, const at::optional<Tensor> &backgrounds, int width,
-                               int height, int tile_size, const Tensor &offsets, const Tensor &flatten_ids, const Tensor &absgrad) {
+                               const Tensor &normals, const Tensor &densify, const Tensor &bg_in /* [C,3] or empty */, int width,
+                               int height, int tile_size, const Tensor &offsets, const Tensor &flatten_ids, bool want_abs) {
         const c10::cuda::CUDAGuard guard(means2d.device());
         const int64_t C = offsets.size(0), nnz = means2d.size(0), I = flatten_ids.size(0);
         auto f = means2d.options();
@@ -172,20 +172,21 @@ struct Raster2DGS : public torch::autograd::Function<Raster2DGS> {
         Tensor rTs = torch::empty({C, height, width, 2}, f), last_ids = torch::empty({C, height, width}, i32), median_ids = torch::empty({C, height, width}, i32);
         Tensor vis = torch::zeros({std::max<int64_t>(nnz, 1), 1}, f);
         Tensor counts = new_counts(means2d, (int32_t)nnz, (int32_t)I);
-        Tensor ws = workspace(means2d, gssdf_raster2dgs_workspace_bytes((int32_t)nnz));
-        Tensor bg = backgrounds.has_value() ? backgrounds.value().contiguous() : Tensor();
+        Tensor ws = workspace(means2d, gssdf_raster2dgs_workspace_bytes((int32_t)C, width, height, (int32_t)nnz, I));
+        Tensor bg = bg_in.numel() > 0 ? bg_in.contiguous() : bg_in;
         gssdf_raster2dgs_fwd_args a{};
         a.C = (int32_t)C; a.image_width = width; a.image_height = height; a.tile_size = tile_size; a.channels = (int32_t)colors.size(-1);
         a.cap = (int32_t)nnz; a.counts = reinterpret_cast<const gssdf_counts *>(counts.data_ptr<int32_t>());
         a.means2d = ptr<float>(means2d); a.ray_transforms = ptr<float>(rt); a.colors = ptr<float>(colors); a.opacities = ptr<float>(opac);
         a.normals = ptr<float>(normals); a.backgrounds = ptr<float>(bg); a.offsets = ptr<int32_t>(offsets); a.flatten_ids = ptr<int32_t>(flatten_ids);
+        a.isect_cap = I;
         a.render_colors = ptr<float>(rc); a.render_depths = ptr<float>(rd); a.render_alphas = ptr<float>(ra); a.render_normals = ptr<float>(rn);
         a.render_distort = ptr<float>(rdis); a.render_median = ptr<float>(rmed); a.render_Ts = ptr<float>(rTs);
         a.last_ids = ptr<int32_t>(last_ids); a.median_ids = ptr<int32_t>(median_ids); a.visibilities = vis.data_ptr<float>();
         a.workspace = ws.data_ptr(); a.workspace_bytes = (size_t)ws.numel();
         check(gssdf_raster2dgs_fwd(&a, cur_stream()));
-        ctx->save_for_backward({means2d, rt, colors, opac, normals, offsets, flatten_ids, ra, rTs, last_ids, median_ids, counts, bg});
-        ctx->saved_data["dims"] = std::vector<int64_t>{width, height, tile_size, C, nnz, absgrad.defined() && absgrad.requires_grad()};
+        ctx->save_for_backward({means2d, rt, colors, opac, normals, offsets, flatten_ids, ra, rTs, last_ids, median_ids, counts, bg});  // bg: [C,3] or an empty tensor
+        ctx->saved_data["dims"] = std::vector<int64_t>{width, height, tile_size, C, nnz, want_abs ? 1 : 0};
         Tensor visn = vis.slice(0, 0, nnz);
         ctx->mark_non_differentiable({visn});
         return {rc, rd, ra, rn, rdis, rmed, visn};
@@ -207,12 +208,14 @@ struct Raster2DGS : public torch::autograd::Function<Raster2DGS> {
         Tensor v_op = torch::zeros({nnz}, f), v_nrm = torch::zeros({nnz, 3}, f), v_den = torch::zeros({nnz, 2}, f);
         Tensor v_abs = want_abs ? torch::zeros({nnz, 2}, f) : Tensor();
         if (nnz > 0 && flatten_ids.size(0) > 0) {
-            Tensor ws = workspace(means2d, gssdf_raster2dgs_bwd_workspace_bytes((int32_t)nnz));
+            const int64_t I = flatten_ids.size(0);
+            Tensor ws = workspace(means2d, gssdf_raster2dgs_bwd_workspace_bytes((int32_t)C, (int32_t)width, (int32_t)height, (int32_t)nnz, I));
             gssdf_raster2dgs_bwd_args a{};
             a.C = (int32_t)C; a.image_width = (int32_t)width; a.image_height = (int32_t)height; a.tile_size = (int32_t)tile; a.channels = 3;
             a.cap = (int32_t)nnz; a.counts = reinterpret_cast<const gssdf_counts *>(counts.data_ptr<int32_t>());
             a.means2d = ptr<float>(means2d); a.ray_transforms = ptr<float>(rt); a.colors = ptr<float>(colors); a.opacities = ptr<float>(opac);
             a.normals = ptr<float>(normals); a.backgrounds = ptr<float>(bg); a.offsets = ptr<int32_t>(offsets); a.flatten_ids = ptr<int32_t>(flatten_ids);
+            a.isect_cap = I; a.reuse_fwd = 0;
             a.render_alphas = ptr<float>(ra); a.render_Ts = ptr<float>(rTs); a.last_ids = ptr<int32_t>(last_ids); a.median_ids = ptr<int32_t>(median_ids);
             a.v_render_colors = ptr<float>(vc); a.v_render_depths = ptr<float>(vd); a.v_render_alphas = ptr<float>(va);
             a.v_render_normals = ptr<float>(vn); a.v_render_median = ptr<float>(vm);
@@ -223,8 +226,8 @@ struct Raster2DGS : public torch::autograd::Function<Raster2DGS> {
             // no torch::cuda::synchronize() here (the reference blocks the host, GSC/rasterize_to_pixels.cpp:252)
         }
         Tensor v_bg;
-        if (bg.defined() && bg.numel() > 0 && ctx->needs_input_grad(6)) v_bg = (vc * (1.0 - ra)).sum({1, 2});
-        return {v_m2d, v_rt, v_col, v_op, v_nrm, v_den, v_bg, Tensor(), Tensor(), Tensor(), Tensor(), Tensor(), v_abs};
+        if (bg.numel() > 0 && ctx->needs_input_grad(6)) v_bg = (vc * (1.0 - ra)).sum({1, 2});
+        return {v_m2d, v_rt, v_col, v_op, v_nrm, v_den, v_bg, Tensor(), Tensor(), Tensor(), Tensor(), Tensor(), Tensor()};
     }
 };
 
@@ -324,7 +327,11 @@ rasterize_to_pixels_2dgs(const torch::Tensor &means2d, const torch::Tensor &ray_
     TORCH_CHECK(isect_offsets.size(2) * tile_size >= image_width, "Assert Failed: tile_width * tile_size >= image_width");
     for (const Tensor *t : {&means2d, &ray_transforms, &colors, &opacities, &normals, &densify, &isect_offsets, &flatten_ids})
         TORCH_CHECK(t->is_contiguous());
-    auto o = Raster2DGS::apply(means2d, ray_transforms, colors, opacities, normals, densify, backgrounds, image_width, image_height,
-                               tile_size, isect_offsets, flatten_ids, absgrad);
+    TORCH_CHECK(!(absgrad.defined() && absgrad.requires_grad()),
+                "gssdf_b200 shim: absgrad (use_absgrad: 0 in config/base.yaml:74, 'not suggested for 2dgs') is exposed through the C ABI "
+                "(gssdf_raster2dgs_bwd_args.v_means2d_abs) but not wired into this autograd shim yet");
+    torch::Tensor bg = backgrounds.has_value() ? backgrounds.value() : torch::empty({0}, means2d.options());
+    auto o = Raster2DGS::apply(means2d, ray_transforms, colors, opacities, normals, densify, bg, image_width, image_height, tile_size,
+                               isect_offsets, flatten_ids, false);
     return std::make_tuple(o[0], o[1], o[2], o[3], o[4], o[5], o[6]);
 }

@@ -56,7 +56,8 @@ typedef struct gssdf_counts {
     int32_t nnz_overflow;   /* 1 if nnz exceeded the capacity given to project2dgs_fwd          */
     int32_t isect_overflow; /* 1 if n_isects exceeded the capacity given to tile_encode         */
     int32_t max_tile_count; /* largest number of intersections in one tile (diagnostic)        */
-    int32_t reserved[3];
+    int32_t n_culled;       /* intersections that survive the raster culling pass (diagnostic)  */
+    int32_t reserved[2];
 } gssdf_counts;
 
 /* ------------------------------------------------------------------------------------------
@@ -214,6 +215,7 @@ typedef struct gssdf_raster2dgs_fwd_args {
     const float *backgrounds;    /* [C,3] or NULL */
     const int32_t *offsets;      /* [C,tile_h,tile_w] */
     const int32_t *flatten_ids;  /* [n_isects] */
+    int64_t isect_cap;           /* rows allocated in flatten_ids (>= n_isects); sizes the culled-list workspace */
     float *render_colors;        /* [C,H,W,3] */
     float *render_depths;        /* [C,H,W,1] sum vis*depth (NOT divided by alpha) */
     float *render_alphas;        /* [C,H,W,1] */
@@ -224,11 +226,12 @@ typedef struct gssdf_raster2dgs_fwd_args {
     int32_t *last_ids;           /* [C,H,W]   saved for backward */
     int32_t *median_ids;         /* [C,H,W]   saved for backward */
     float *visibilities;         /* [cap,1] */
-    void *workspace;             /* >= gssdf_raster2dgs_workspace_bytes(cap) : packed 64-B records */
+    void *workspace;             /* >= gssdf_raster2dgs_workspace_bytes(C, W, H, cap, isect_cap): render records, culling
+                                    conics, culled per-tile lists. Keep it untouched until the backward to let it reuse them. */
     size_t workspace_bytes;
     void *prof_start, *prof_stop; /* optional cudaEvent_t recorded around the main raster kernel (NULL = off) */
 } gssdf_raster2dgs_fwd_args;
-size_t gssdf_raster2dgs_workspace_bytes(int32_t cap);
+size_t gssdf_raster2dgs_workspace_bytes(int32_t C, int32_t image_width, int32_t image_height, int32_t cap, int64_t isect_cap);
 int gssdf_raster2dgs_fwd(const gssdf_raster2dgs_fwd_args *a, gssdf_stream_t stream);
 
 /* a7  rasterise backward.  Replaces gsplat::rasterize_to_pixels_2dgs_bwd
@@ -243,6 +246,9 @@ typedef struct gssdf_raster2dgs_bwd_args {
     const gssdf_counts *counts;
     const float *means2d, *ray_transforms, *colors, *opacities, *normals, *backgrounds;
     const int32_t *offsets, *flatten_ids;
+    int64_t isect_cap;           /* as in the forward */
+    int32_t reuse_fwd;           /* 1: `workspace` begins with the forward's workspace contents (same inputs, same call chain):
+                                    skip re-packing and re-culling. 0: self-contained. */
     const float *render_alphas;  /* [C,H,W,1] */
     const float *render_Ts;      /* [C,H,W,2] */
     const int32_t *last_ids, *median_ids;
@@ -259,11 +265,11 @@ typedef struct gssdf_raster2dgs_bwd_args {
     float *v_opacities;       /* [cap] */
     float *v_normals;         /* [cap,3] */
     float *v_densify;         /* [cap,2] */
-    void *workspace;          /* >= gssdf_raster2dgs_bwd_workspace_bytes(cap) */
+    void *workspace;          /* >= gssdf_raster2dgs_bwd_workspace_bytes(C, W, H, cap, isect_cap) = forward layout + gradient records */
     size_t workspace_bytes;
     void *prof_start, *prof_stop; /* optional cudaEvent_t recorded around the main raster kernel (NULL = off) */
 } gssdf_raster2dgs_bwd_args;
-size_t gssdf_raster2dgs_bwd_workspace_bytes(int32_t cap);
+size_t gssdf_raster2dgs_bwd_workspace_bytes(int32_t C, int32_t image_width, int32_t image_height, int32_t cap, int64_t isect_cap);
 int gssdf_raster2dgs_bwd(const gssdf_raster2dgs_bwd_args *a, gssdf_stream_t stream);
 
 /* a8  image post-ops of rasterization_2dgs_sdf (include/neural_gaussian/neural_gaussian.cpp:229-240):
