@@ -423,8 +423,13 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
                 if (a.mlp_grad) {
                     for (int p = 0; p < tm; ++p) {
                         float gv[OB];
+                        if (OB == 4) {
+                            const float4 g4 = *reinterpret_cast<const float4 *>(gcur + p * AP + ox * 4);
+                            gv[0] = g4.x; gv[1] = g4.y; gv[OB - 2] = g4.z; gv[OB - 1] = g4.w;
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < OB; ++i) gv[i] = gcur[p * AP + ox * OB + i];
+                            for (int i = 0; i < OB; ++i) gv[i] = gcur[p * AP + ox * OB + i];
+                        }
                         if (l == 0) {
 #pragma unroll
                             for (int j = 0; j < kFeat / 16; ++j) {
@@ -433,12 +438,18 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
                                 for (int i = 0; i < OB; ++i) dW0[i][j] = fmaf(gv[i], av, dW0[i][j]);
                             }
                         } else {
+                            float avv[HID / 16];
+                            if (HID / 16 == 4) {
+                                const float4 a4 = *reinterpret_cast<const float4 *>(a_prev + p * AP + kx * 4);
+                                avv[0] = a4.x; avv[1] = a4.y; avv[HID / 16 - 2] = a4.z; avv[HID / 16 - 1] = a4.w;
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < HID / 16; ++j) {
-                                const float av = a_prev[p * AP + kx * (HID / 16) + j];
-#pragma unroll
-                                for (int i = 0; i < OB; ++i) dWh[l > 0 ? l - 1 : 0][i][j] = fmaf(gv[i], av, dWh[l > 0 ? l - 1 : 0][i][j]);
+                                for (int j = 0; j < HID / 16; ++j) avv[j] = a_prev[p * AP + kx * (HID / 16) + j];
                             }
+#pragma unroll
+                            for (int j = 0; j < HID / 16; ++j)
+#pragma unroll
+                                for (int i = 0; i < OB; ++i) dWh[l > 0 ? l - 1 : 0][i][j] = fmaf(gv[i], avv[j], dWh[l > 0 ? l - 1 : 0][i][j]);
                         }
                         if (kx == 0) {
 #pragma unroll
@@ -450,13 +461,35 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
                 __syncthreads();
                 stage_weights_plain(Wl, HID, K, s_w);
                 __syncthreads();
-                for (int e = threadIdx.x; e < TM * K; e += kSdfThreads) {
-                    const int p = e / K, k = e % K;
-                    float sacc = 0.f;
-#pragma unroll 8
-                    for (int o = 0; o < HID; ++o) sacc = fmaf(gcur[p * AP + o], s_w[o * K + k], sacc);
-                    if (l > 0 && !(a_prev[p * AP + k] > 0.f)) sacc = 0.f;
-                    gnext[p * AP + k] = sacc;
+                {
+                    // register tile: 4 points x 4 inputs per thread; (TM/4) x (K/4) tiles over 256 threads
+                    const int KT = K / 4;                 // 16 (K = 64) or 8 (K = 32)
+                    for (int tile = threadIdx.x; tile < (TM / 4) * KT; tile += kSdfThreads) {
+                        const int k0 = (tile % KT) * 4, p0 = (tile / KT) * 4;
+                        float acc[4][4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+                        for (int o = 0; o < HID; ++o) {
+                            const float4 w4 = *reinterpret_cast<const float4 *>(s_w + o * K + k0);
+                            const float g0 = gcur[(p0 + 0) * AP + o], g1 = gcur[(p0 + 1) * AP + o], g2 = gcur[(p0 + 2) * AP + o],
+                                        g3 = gcur[(p0 + 3) * AP + o];
+                            acc[0][0] = fmaf(g0, w4.x, acc[0][0]); acc[0][1] = fmaf(g0, w4.y, acc[0][1]); acc[0][2] = fmaf(g0, w4.z, acc[0][2]); acc[0][3] = fmaf(g0, w4.w, acc[0][3]);
+                            acc[1][0] = fmaf(g1, w4.x, acc[1][0]); acc[1][1] = fmaf(g1, w4.y, acc[1][1]); acc[1][2] = fmaf(g1, w4.z, acc[1][2]); acc[1][3] = fmaf(g1, w4.w, acc[1][3]);
+                            acc[2][0] = fmaf(g2, w4.x, acc[2][0]); acc[2][1] = fmaf(g2, w4.y, acc[2][1]); acc[2][2] = fmaf(g2, w4.z, acc[2][2]); acc[2][3] = fmaf(g2, w4.w, acc[2][3]);
+                            acc[3][0] = fmaf(g3, w4.x, acc[3][0]); acc[3][1] = fmaf(g3, w4.y, acc[3][1]); acc[3][2] = fmaf(g3, w4.z, acc[3][2]); acc[3][3] = fmaf(g3, w4.w, acc[3][3]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float v = acc[i][j];
+                                if (l > 0 && !(a_prev[(p0 + i) * AP + k0 + j] > 0.f)) v = 0.f;
+                                gnext[(p0 + i) * AP + k0 + j] = v;
+                            }
+                    }
                 }
                 __syncthreads();
                 float *t = gcur; gcur = gnext; gnext = t;

@@ -61,7 +61,8 @@ __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0
         const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
         const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bcnt = __shfl_sync(0xffffffffu, cnt, src);
         const int bidx = __shfl_sync(0xffffffffu, idx, src);
-        for (uint32_t t = lane; t < bcnt; t += 32) f(bidx, bx0 + t % bw, by0 + t / bw);
+#pragma unroll 4
+        for (uint32_t t = lane; t < bcnt; t += 32) f(bidx, bx0 + t % bw, by0 + t / bw);  // unrolled: 4 atomics in flight per lane
     }
 }
 

@@ -129,6 +129,7 @@ def test_sdf_variants_and_losses(oracle):
     tg, mg, vx = torch.zeros(n_params, device=dev), torch.zeros(len(mlp), device=dev), torch.empty(n, 3, device=dev)
     cabi.sdf_bwd(net, xt, v_s, v_y, tg, mg, vx, n_variants=7, delta=delta)
     r_tg, r_mg, r_vx = oracle.sdf_bwd(pts, table, mlp, v_s.cpu().numpy(), v_y.cpu().numpy())
-    assert_close_frac(mg.cpu().numpy(), r_mg, 1e-4, 5e-5 * np.abs(r_mg).max(), 0.0, "mlp grad x7")  # fp32 sums over 14 k points
+    assert_close_frac(mg.cpu().numpy(), r_mg, 1e-4, 5e-5 * np.abs(r_mg).max(), 1e-3, "mlp grad x7")  # fp32 sums over 14 k points
+    assert np.linalg.norm(mg.cpu().numpy() - r_mg) <= 1e-4 * np.linalg.norm(r_mg)
     assert np.linalg.norm(tg.cpu().numpy() - r_tg) <= 3e-4 * np.linalg.norm(r_tg)
     assert np.linalg.norm(vx.cpu().numpy() - r_vx[:n]) <= 1e-3 * np.linalg.norm(r_vx[:n])
