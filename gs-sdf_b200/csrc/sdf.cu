@@ -183,26 +183,27 @@ struct MlpShape {
 };
 
 // stage W[out=O][in=K] (row-major, global) transposed into s_w[k][WP]; bias into s_b
-template <int HID>
+template <int HID, int THREADS = kSdfThreads>
 __device__ __forceinline__ void stage_weights(const float *__restrict__ W, int O, int K, float *s_w, float *s_b) {
     constexpr int WP = MlpShape<HID>::WP;
-    for (int e = threadIdx.x; e < O * K; e += kSdfThreads) {
+    for (int e = threadIdx.x; e < O * K; e += THREADS) {
         const int o = e / K, k = e % K;
         s_w[k * WP + o] = __ldg(W + e);
     }
-    for (int o = threadIdx.x; o < O; o += kSdfThreads) s_b[o] = __ldg(W + (size_t)O * K + o);
+    for (int o = threadIdx.x; o < O; o += THREADS) s_b[o] = __ldg(W + (size_t)O * K + o);
 }
 
 // stage W[out=O][in=K] as is: s_w[o * K + k]
+template <int THREADS = kSdfThreads>
 __device__ __forceinline__ void stage_weights_plain(const float *__restrict__ W, int O, int K, float *s_w) {
-    for (int e = threadIdx.x; e < O * K; e += kSdfThreads) s_w[e] = __ldg(W + e);
+    for (int e = threadIdx.x; e < O * K; e += THREADS) s_w[e] = __ldg(W + e);
 }
 
 // out[p][o] = act(sum_k in[p][k] * W[o][k] + b[o]) for a tile of TM points, O == HID outputs
-template <int HID, int TM, bool RELU>
+template <int HID, int TM, bool RELU, int THREADS = kSdfThreads>
 __device__ __forceinline__ void dense_layer(const float *s_in, int K, const float *s_w, const float *s_b, float *s_out) {
     constexpr int AP = MlpShape<HID>::AP, WP = MlpShape<HID>::WP;
-    constexpr int TX = HID / 4, TY = kSdfThreads / TX, PPT = TM / TY;
+    constexpr int TX = HID / 4, TY = THREADS / TX, PPT = TM / TY;
     static_assert(PPT >= 1 && PPT * TY == TM, "tile shape");
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     float acc[PPT][4];
@@ -308,8 +309,10 @@ sdf_fwd_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
 // backward (persistent): recompute forward for a 64-point tile keeping every activation in shared memory,
 // back-propagate, accumulate dW in registers across tiles, scatter table grads, write v_x.
 // ---------------------------------------------------------------------------------------------
+constexpr int kSdfBwdThreads = 512;
+
 template <int HID>
-__global__ void __launch_bounds__(kSdfThreads)
+__global__ void __launch_bounds__(kSdfBwdThreads)
 sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
     constexpr int TM = 64;
     constexpr int AP = MlpShape<HID>::AP, WP = MlpShape<HID>::WP;
@@ -330,17 +333,20 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
     // register accumulators of the weight gradients: thread owns rows o = tx*4..+3? -> use [4][KPT] blocks:
     // layer l (HID x K): thread (ox = t % 16 -> outputs ox*HID/16.., kx = t / 16 -> inputs kx*K/16..)
     constexpr int OB = HID / 16;     // outputs per thread
-    float dW0[OB][kFeat / 16];       // first layer: HID x 32
-    float dWh[4][OB][HID / 16];      // hidden layers: HID x HID
+    constexpr int KX = kSdfBwdThreads / 16;  // thread columns over the input dimension
+    constexpr int KB0 = kFeat / KX, KBH = HID / KX;  // inputs per thread (first / hidden layers)
+    static_assert(KB0 >= 1 && KBH >= 1, "thread tiling");
+    float dW0[OB][KB0];              // first layer: HID x 32
+    float dWh[4][OB][KBH];           // hidden layers: HID x HID
     float dB[NL][OB];                // biases (only threads with kx == 0 use them)
 #pragma unroll
     for (int i = 0; i < OB; ++i) {
 #pragma unroll
-        for (int j = 0; j < kFeat / 16; ++j) dW0[i][j] = 0.f;
+        for (int j = 0; j < KB0; ++j) dW0[i][j] = 0.f;
 #pragma unroll
         for (int l = 0; l < 4; ++l)
 #pragma unroll
-            for (int j = 0; j < HID / 16; ++j) dWh[l][i][j] = 0.f;
+            for (int j = 0; j < KBH; ++j) dWh[l][i][j] = 0.f;
 #pragma unroll
         for (int l = 0; l < NL; ++l) dB[l][i] = 0.f;
     }
@@ -354,7 +360,7 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
 #define LIVE(p_) ((p_) < tm && (base + (p_)) % a.n < n_live)
         __syncthreads();
         // 1. encode
-        for (int task = threadIdx.x; task < TM * g.L; task += kSdfThreads) {
+        for (int task = threadIdx.x; task < TM * g.L; task += kSdfBwdThreads) {
             const int p = task % TM, lvl = task / TM;
             float2 f = make_float2(0.f, 0.f);
             if (LIVE(p)) {
@@ -367,16 +373,16 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
         }
         // 2. forward, keeping activations. dense_layer expects pitch AP for its input: copy features into s_g (scratch)
         __syncthreads();
-        for (int e = threadIdx.x; e < TM * kFeat; e += kSdfThreads) s_g[(e / kFeat) * AP + e % kFeat] = s_feat[(e / kFeat) * (kFeat + 1) + e % kFeat];
+        for (int e = threadIdx.x; e < TM * kFeat; e += kSdfBwdThreads) s_g[(e / kFeat) * AP + e % kFeat] = s_feat[(e / kFeat) * (kFeat + 1) + e % kFeat];
         const float *W = a.net.mlp;
         {
             int K = kFeat;
             const float *in = s_g;
             for (int l = 0; l < nh; ++l) {
                 __syncthreads();
-                stage_weights<HID>(W, HID, K, s_w, s_bias);
+                stage_weights<HID, kSdfBwdThreads>(W, HID, K, s_w, s_bias);
                 __syncthreads();
-                dense_layer<HID, TM, true>(in, K, s_w, s_bias, s_act + l * TM * AP);
+                dense_layer<HID, TM, true, kSdfBwdThreads>(in, K, s_w, s_bias, s_act + l * TM * AP);
                 W += (size_t)HID * K + HID;
                 K = HID;
                 in = s_act + l * TM * AP;
@@ -386,7 +392,7 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
         // 3. output layer backward: g_last[p][k] = (v_sdf W_out[0][k] + v_y1 W_out[1][k]) * relu'(a_last)
         const float *Wout = W;  // [2][HID] then bias[2]
         const float *a_last = s_act + (nh - 1) * TM * AP;
-        for (int e = threadIdx.x; e < TM * HID; e += kSdfThreads) {
+        for (int e = threadIdx.x; e < TM * HID; e += kSdfBwdThreads) {
             const int p = e / HID, k = e % HID;
             float gv = 0.f;
             if (LIVE(p)) {
@@ -432,22 +438,22 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
                         }
                         if (l == 0) {
 #pragma unroll
-                            for (int j = 0; j < kFeat / 16; ++j) {
-                                const float av = s_feat[p * (kFeat + 1) + kx * (kFeat / 16) + j];
+                            for (int j = 0; j < KB0; ++j) {
+                                const float av = s_feat[p * (kFeat + 1) + kx * KB0 + j];
 #pragma unroll
                                 for (int i = 0; i < OB; ++i) dW0[i][j] = fmaf(gv[i], av, dW0[i][j]);
                             }
                         } else {
-                            float avv[HID / 16];
-                            if (HID / 16 == 4) {
-                                const float4 a4 = *reinterpret_cast<const float4 *>(a_prev + p * AP + kx * 4);
-                                avv[0] = a4.x; avv[1] = a4.y; avv[HID / 16 - 2] = a4.z; avv[HID / 16 - 1] = a4.w;
+                            float avv[KBH];
+                            if (KBH == 2) {
+                                const float2 a2 = *reinterpret_cast<const float2 *>(a_prev + p * AP + kx * 2);
+                                avv[0] = a2.x; avv[KBH - 1] = a2.y;
                             } else {
 #pragma unroll
-                                for (int j = 0; j < HID / 16; ++j) avv[j] = a_prev[p * AP + kx * (HID / 16) + j];
+                                for (int j = 0; j < KBH; ++j) avv[j] = a_prev[p * AP + kx * KBH + j];
                             }
 #pragma unroll
-                            for (int j = 0; j < HID / 16; ++j)
+                            for (int j = 0; j < KBH; ++j)
 #pragma unroll
                                 for (int i = 0; i < OB; ++i) dWh[l > 0 ? l - 1 : 0][i][j] = fmaf(gv[i], avv[j], dWh[l > 0 ? l - 1 : 0][i][j]);
                         }
@@ -459,12 +465,12 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
                 }
                 // 4b. g_prev[p][k] = sum_o g[p][o] W_l[o][k] (* relu'(a_prev)); W_l staged as is (consecutive k -> no conflicts)
                 __syncthreads();
-                stage_weights_plain(Wl, HID, K, s_w);
+                stage_weights_plain<kSdfBwdThreads>(Wl, HID, K, s_w);
                 __syncthreads();
                 {
                     // register tile: 4 points x 4 inputs per thread; (TM/4) x (K/4) tiles over 256 threads
                     const int KT = K / 4;                 // 16 (K = 64) or 8 (K = 32)
-                    for (int tile = threadIdx.x; tile < (TM / 4) * KT; tile += kSdfThreads) {
+                    for (int tile = threadIdx.x; tile < (TM / 4) * KT; tile += kSdfBwdThreads) {
                         const int k0 = (tile % KT) * 4, p0 = (tile / KT) * 4;
                         float acc[4][4];
 #pragma unroll
@@ -496,9 +502,9 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
             }
         }
         // 5. gcur[p][0..31] = dL/dfeat -> table gradient + dL/dx
-        for (int e = threadIdx.x; e < TM * 3; e += kSdfThreads) s_dx[e] = 0.f;
+        for (int e = threadIdx.x; e < TM * 3; e += kSdfBwdThreads) s_dx[e] = 0.f;
         __syncthreads();
-        for (int task = threadIdx.x; task < TM * g.L; task += kSdfThreads) {
+        for (int task = threadIdx.x; task < TM * g.L; task += kSdfBwdThreads) {
             const int p = task % TM, lvl = task / TM;
             if (LIVE(p)) {
                 float x[3], dx[3] = {0.f, 0.f, 0.f};
@@ -514,7 +520,7 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
         }
         __syncthreads();
         if (a.v_x)
-            for (int e = threadIdx.x; e < tm * 3; e += kSdfThreads)
+            for (int e = threadIdx.x; e < tm * 3; e += kSdfBwdThreads)
                 if (base + e / 3 < n_live) a.v_x[base * 3 + e] = s_dx[e] * (a.net.inv_size != 0.f ? a.net.inv_size : 1.f);
 #undef LIVE
     }
@@ -525,16 +531,16 @@ sdf_bwd_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
         for (int l = 0; l < 5; ++l) {
             if (l < nh) {
                 const int K = l == 0 ? kFeat : HID;
-                const int KB = K / 16;
+                const int KB = K / KX;
 #pragma unroll
                 for (int i = 0; i < OB; ++i) {
                     const int o = ox * OB + i;
                     if (l == 0) {
 #pragma unroll
-                        for (int j = 0; j < kFeat / 16; ++j) atomicAdd(G + (size_t)o * K + kx * KB + j, dW0[i][j]);
+                        for (int j = 0; j < KB0; ++j) atomicAdd(G + (size_t)o * K + kx * KB + j, dW0[i][j]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < HID / 16; ++j) atomicAdd(G + (size_t)o * K + kx * KB + j, dWh[l > 0 ? l - 1 : 0][i][j]);
+                        for (int j = 0; j < KBH; ++j) atomicAdd(G + (size_t)o * K + kx * KB + j, dWh[l > 0 ? l - 1 : 0][i][j]);
                     }
                     if (kx == 0) atomicAdd(G + (size_t)HID * K + o, dB[l][i]);
                 }
@@ -699,10 +705,10 @@ extern "C" int gssdf_sdf_bwd(const gssdf_sdf_bwd_args *a, gssdf_stream_t stream)
     cudaStream_t st = (cudaStream_t)stream;
     if (a->net.hidden_dim == 64) {
         GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<64>()));
-        sdf_bwd_kernel<64><<<grid, kSdfThreads, bwd_smem<64>(), st>>>(*a, g, n_tiles);
+        sdf_bwd_kernel<64><<<grid, kSdfBwdThreads, bwd_smem<64>(), st>>>(*a, g, n_tiles);
     } else {
         GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<32>()));
-        sdf_bwd_kernel<32><<<grid, kSdfThreads, bwd_smem<32>(), st>>>(*a, g, n_tiles);
+        sdf_bwd_kernel<32><<<grid, kSdfBwdThreads, bwd_smem<32>(), st>>>(*a, g, n_tiles);
     }
     GSSDF_LAUNCH_OK("sdf_bwd_kernel");
     return GSSDF_OK;
