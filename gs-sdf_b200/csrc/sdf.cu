@@ -18,6 +18,7 @@
 // dL/dy -> half, x128, per-corner half product. Deviation: the table gradient accumulates in fp32 RED
 // (the reference: fp16 atomics). MLP arithmetic is fp32 FMA on the CUDA cores in this round (the tcgen05
 // path is the next step).
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -633,6 +634,8 @@ static size_t bwd_smem() {
 
 using namespace gssdf;
 
+extern "C" int gssdf_sdf_fwd_tc_launch(const gssdf_sdf_fwd_args *a, const gssdf::GridGeom *g, gssdf_stream_t stream);
+
 static int check_net(const char *who, const gssdf_sdf_net &net) {
     GSSDF_REQUIRE(net.n_levels == 16 && net.n_features_per_level == 2, GSSDF_EUNSUPPORTED,
                   "%s: the fused SDF kernels support n_levels 16 x n_features_per_level 2 (config/base.yaml:8-9), got %d x %d", who,
@@ -675,6 +678,11 @@ extern "C" int gssdf_sdf_fwd(const gssdf_sdf_fwd_args *a, gssdf_stream_t stream)
     GSSDF_REQUIRE(a->x && a->sdf, GSSDF_EINVAL, "sdf_fwd: x and sdf must be non-null");
     const GridGeom g = make_grid(a->net);
     GSSDF_REQUIRE(a->n_variants == 0 || a->n_variants == 1 || a->n_variants == 7, GSSDF_EINVAL, "sdf_fwd: n_variants must be 1 or 7");
+    if (a->net.mlp_mode == 1) {
+        GSSDF_REQUIRE(a->net.hidden_dim == 64, GSSDF_EUNSUPPORTED, "sdf_fwd: the tcgen05 decoder needs hidden_dim 64");
+        return gssdf_sdf_fwd_tc_launch(a, &g, stream);
+    }
+    GSSDF_REQUIRE(a->net.mlp_mode == 0, GSSDF_EINVAL, "sdf_fwd: mlp_mode must be 0 or 1");
     const int grid = cdiv(a->n * (a->n_variants > 1 ? a->n_variants : 1), 128);
     cudaStream_t st = (cudaStream_t)stream;
     if (a->net.hidden_dim == 64) {
@@ -723,5 +731,224 @@ extern "C" int gssdf_sdf_loss(const gssdf_sdf_loss_args *a, gssdf_stream_t strea
     GSSDF_REQUIRE(a->n_variants == 1 || a->delta > 0.f, GSSDF_EINVAL, "sdf_loss: delta must be positive");
     sdf_loss_kernel<<<cdiv(a->n, 256), 256, 0, (cudaStream_t)stream>>>(*a);
     GSSDF_LAUNCH_OK("sdf_loss_kernel");
+    return GSSDF_OK;
+}
+
+// =============================================================================================
+// tcgen05 forward: the decoder's dense 64-wide layers on the 5th-generation tensor cores.
+//
+// One CTA = 128 points = one UMMA M=128 tile. Per layer D[128 x 64] (fp32, TMEM) = A[128 x K] * W^T[K x 64], issued by ONE
+// thread as tcgen05.mma.cta_group::1.kind::f16 (bf16 inputs, fp32 accumulate), N = 64, K = 16 per instruction.
+// fp32 parity: both operands are split x = hi + mid (two bf16 terms, 16 significant bits) and three products are
+// accumulated, hi*hi + hi*mid + mid*hi (error ~2^-16 relative; the hash-grid features are fp16 values, for which the
+// split is exact). Operands live in shared memory in the canonical K-major no-swizzle layout (8 x 16-byte core
+// matrices; LBO = 128 B between K-adjacent cores, SBO = 1024 B between 8-row groups); the epilogue reads the
+// accumulator with tcgen05.ld (32 lanes x 32 columns per warp), adds the bias, applies ReLU in registers and writes the next
+// layer's A operand straight back into the canonical layout -- activations never leave the SM.
+// =============================================================================================
+namespace gssdf {
+
+constexpr int kTcThreads = 256;
+constexpr uint32_t kLBO = 128, kSBO = 1024;  // bytes
+
+__device__ __forceinline__ uint32_t canon_off(int r, int k) {  // byte offset of bf16 element (row r, col k)
+    return (uint32_t)((r >> 3) * kSBO + (k >> 3) * kLBO + (r & 7) * 16 + (k & 7) * 2);
+}
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+    d |= (uint64_t)(kLBO >> 4) << 16;               // leading (K-direction) byte offset, bits [16,30)
+    d |= (uint64_t)(kSBO >> 4) << 32;               // stride (M/N-direction) byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+    return d;                                       // base_offset 0, lbo_mode 0, layout_type 0 = no swizzle
+}
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &mid) {
+    hi = __float2bfloat16_rn(x);
+    mid = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+    for (int it = 0; it < (1 << 24); ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(kTcThreads)
+sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
+    constexpr int TM = 128, HID = 64;
+    extern __shared__ __align__(1024) unsigned char s_tc[];
+    unsigned char *sA_hi = s_tc;                  // 16 KB : [128 x 64] bf16 canonical
+    unsigned char *sA_mid = sA_hi + 16384;        // 16 KB
+    unsigned char *sW_hi = sA_mid + 16384;        // 8 KB  : [64 x 64] bf16 canonical
+    unsigned char *sW_mid = sW_hi + 8192;         // 8 KB
+    float *s_bias = reinterpret_cast<float *>(sW_mid + 8192);  // [64]
+    float *s_wout = s_bias + 64;                  // [2][64] + [2]
+    float *s_part = s_wout + 130 + 2;             // [2 halves][128][2]
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_eval = a.n * max(a.n_variants, 1);
+    const int64_t base = (int64_t)blockIdx.x * TM;
+    const int tm = (int)min((int64_t)TM, n_eval - base);
+    const int64_t n_live = a.n_live ? min((int64_t)*a.n_live, a.n) : a.n;
+    if (base % a.n >= n_live && base % a.n + TM <= a.n) return;  // whole tile beyond the live rows (CTA-uniform)
+
+    if (warp == 0) {  // TMEM: 64 fp32 columns x 128 lanes for the accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(64));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        mbar_init(&s_mbar, 1);
+        fence_mbar_init();
+    }
+    // 1. hash-grid encode -> A (layer 0 input, K = 32), split into bf16 hi/mid (exact: features are fp16 values)
+    const __half2 *table = reinterpret_cast<const __half2 *>(a.net.table_half);
+    for (int task = tid; task < TM * g.L; task += kTcThreads) {
+        const int p = task % TM, lvl = task / TM;
+        float2 f = make_float2(0.f, 0.f);
+        if (p < tm && (base + p) % a.n < n_live) {
+            float x[3];
+            load_x(a.net, a.x, base + p, a.n, a.delta, x);
+            f = encode_level(table, g, lvl, x);
+            if (a.feat) { a.feat[(base + p) * kFeat + 2 * lvl] = f.x; a.feat[(base + p) * kFeat + 2 * lvl + 1] = f.y; }
+        }
+        __nv_bfloat16 h0, m0, h1, m1;
+        split_bf16(f.x, h0, m0);
+        split_bf16(f.y, h1, m1);
+        const uint32_t off = canon_off(p, 2 * lvl);
+        *reinterpret_cast<__nv_bfloat162 *>(sA_hi + off) = __halves2bfloat162(h0, h1);
+        *reinterpret_cast<__nv_bfloat162 *>(sA_mid + off) = __halves2bfloat162(m0, m1);
+    }
+    // output layer parameters (HID -> 2) for the CUDA-core tail
+    const int nh = 1 + a.net.n_hidden;
+    {
+        const float *Wo = a.net.mlp + ((size_t)HID * kFeat + HID) + (size_t)a.net.n_hidden * ((size_t)HID * HID + HID);
+        for (int e = tid; e < 2 * HID + 2; e += kTcThreads) s_wout[e] = __ldg(Wo + e);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = s_tmem;
+    // instruction descriptor: D = F32, A = B = BF16, both K-major, N = 64, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+    const float *W = a.net.mlp;
+    int K = kFeat;
+    bool ok = true;
+    for (int l = 0; l < nh; ++l) {
+        // 2. stage W_l [64 x K] (row-major fp32, global) as bf16 hi/mid in the canonical layout; bias
+        for (int e = tid; e < HID * K; e += kTcThreads) {
+            const int o = e / K, k = e % K;
+            __nv_bfloat16 hi, mid;
+            split_bf16(__ldg(W + e), hi, mid);
+            const uint32_t off = canon_off(o, k);
+            *reinterpret_cast<__nv_bfloat16 *>(sW_hi + off) = hi;
+            *reinterpret_cast<__nv_bfloat16 *>(sW_mid + off) = mid;
+        }
+        if (tid < HID) s_bias[tid] = __ldg(W + (size_t)HID * K + tid);
+        fence_proxy_async();  // generic-proxy smem writes (A from the previous epilogue / encode, W) -> visible to the tensor core
+        __syncthreads();
+        // 3. one thread issues the MMAs: 3 bf16 products per 16-wide K step
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint32_t aH = smem_u32(sA_hi), aM = smem_u32(sA_mid), wH = smem_u32(sW_hi), wM = smem_u32(sW_mid);
+            uint32_t acc = 0;
+            for (int ks = 0; ks < K / 16; ++ks) {
+                const uint32_t ko = ks * 2 * kLBO;
+                umma_bf16(tmem, make_smem_desc(aH + ko), make_smem_desc(wH + ko), idesc, acc); acc = 1;
+                umma_bf16(tmem, make_smem_desc(aH + ko), make_smem_desc(wM + ko), idesc, acc);
+                umma_bf16(tmem, make_smem_desc(aM + ko), make_smem_desc(wH + ko), idesc, acc);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_mbar)) : "memory");
+        }
+        // 4. wait for the accumulator
+        ok = mbar_wait_bounded(&s_mbar, (uint32_t)(l & 1));
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        // 5. epilogue: warp w owns TMEM lanes 32*(w%4).. and columns 32*(w/4)..
+        const int q = warp & 3, h = warp >> 2;
+        const int row = 32 * q + lane;
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * h);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+            "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float act[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) act[j] = fmaxf(__uint_as_float(v[j]) + s_bias[32 * h + j], 0.f);
+        if (l < nh - 1) {
+            // next layer's A operand: row `row`, columns 32h .. 32h+31 -> four 16-byte stores per split
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                __nv_bfloat16 hi[8], mid[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split_bf16(act[jj * 8 + e], hi[e], mid[e]);
+                const uint32_t off = canon_off(row, 32 * h + jj * 8);
+                *reinterpret_cast<uint4 *>(sA_hi + off) = *reinterpret_cast<uint4 *>(hi);
+                *reinterpret_cast<uint4 *>(sA_mid + off) = *reinterpret_cast<uint4 *>(mid);
+            }
+        } else {
+            float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                p0 = fmaf(act[j], s_wout[32 * h + j], p0);
+                p1 = fmaf(act[j], s_wout[HID + 32 * h + j], p1);
+            }
+            s_part[(h * TM + row) * 2] = p0;
+            s_part[(h * TM + row) * 2 + 1] = p1;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");  // TMEM reads done before the next layer's MMA overwrites D
+        W += (size_t)HID * K + HID;
+        K = HID;
+    }
+    __syncthreads();
+    if (ok && tid < TM) {
+        const int p = tid;
+        if (p < tm && (base + p) % a.n < n_live) {
+            a.sdf[base + p] = s_part[p * 2] + s_part[(TM + p) * 2] + s_wout[2 * HID];
+            if (a.y1) a.y1[base + p] = s_part[p * 2 + 1] + s_part[(TM + p) * 2 + 1] + s_wout[2 * HID + 1];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(64));
+    if (!ok) __trap();  // the accumulator never arrived: fail loudly instead of hanging
+}
+
+}  // namespace gssdf
+
+extern "C" int gssdf_sdf_fwd_tc_launch(const gssdf_sdf_fwd_args *a, const gssdf::GridGeom *g, gssdf_stream_t stream) {
+    using namespace gssdf;
+    const size_t smem = 16384 * 2 + 8192 * 2 + sizeof(float) * (64 + 132 + 2 * 128 * 2) + 1024;
+    GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = cdiv(a->n * (a->n_variants > 1 ? a->n_variants : 1), 128);
+    sdf_fwd_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(*a, *g);
+    GSSDF_LAUNCH_OK("sdf_fwd_tc_kernel");
     return GSSDF_OK;
 }

@@ -173,10 +173,10 @@ def l1_loss(Cn, W, H, out_colors, gt, w_rgb, w_depth, loss_out, v_out_colors):
 
 # ---- SDF branch -------------------------------------------------------------------------------
 def sdf_net(table_half, mlp, n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=2.0,
-            hidden_dim=64, n_hidden=3, origin=(0.0, 0.0, 0.0), inv_size=0.0):
+            hidden_dim=64, n_hidden=3, origin=(0.0, 0.0, 0.0), inv_size=0.0, mlp_mode=0):
     return make_args("gssdf_sdf_net", n_levels=n_levels, n_features_per_level=n_features, log2_hashmap_size=log2_hashmap_size,
                      base_resolution=base_resolution, per_level_scale=per_level_scale, hidden_dim=hidden_dim, n_hidden=n_hidden,
-                     table_half=table_half, mlp=mlp, origin=list(origin), inv_size=inv_size)
+                     table_half=table_half, mlp=mlp, origin=list(origin), inv_size=inv_size, mlp_mode=mlp_mode)
 
 
 def sdf_table_params(net):

@@ -341,6 +341,10 @@ typedef struct gssdf_sdf_net {
     const float *mlp;       /* [gssdf_sdf_mlp_params] fp32 */
     float origin[3];        /* world -> unit cube: x01 = (x - origin) * inv_size + 0.5 (SubMap::xyz_to_zp1_pts, */
     float inv_size;         /*   include/neural_net/sub_map.cpp:82-97); inv_size == 0 -> x is already in [0,1]^3 */
+    int32_t mlp_mode;       /* forward decoder arithmetic: 0 = fp32 FMA on the CUDA cores (bit-for-bit the fp32 reference order
+                               up to summation order); 1 = 5th-gen tensor cores: tcgen05.mma kind::f16 on a 2-term bf16 split
+                               of both operands (hi*hi + hi*mid + mid*hi, fp32 accumulation in TMEM; ~2^-16 relative),
+                               hidden_dim 64 only */
 } gssdf_sdf_net;
 int64_t gssdf_sdf_table_params(const gssdf_sdf_net *net);
 int64_t gssdf_sdf_mlp_params(const gssdf_sdf_net *net);

@@ -136,3 +136,30 @@ def test_sdf_variants_and_losses(oracle):
     # backward flips whole quanta -> the comparison is only meaningful at the ~1e-3 level
     assert np.linalg.norm(tg.cpu().numpy() - r_tg) <= 2e-3 * np.linalg.norm(r_tg)
     assert np.linalg.norm(vx.cpu().numpy() - r_vx[:n]) <= 2e-3 * np.linalg.norm(r_vx[:n])
+
+
+@pytest.mark.parametrize("n,n_hidden,variants", [(5000, 3, 1), (1000, 1, 7), (130, 0, 1)])
+def test_sdf_fwd_tensor_core_path(oracle, n, n_hidden, variants):
+    """mlp_mode=1: decoder on the 5th-gen tensor cores (tcgen05.mma, bf16 hi/mid split, fp32 accumulate in TMEM).
+    Features stay bit-exact; sdf/y1 within 1e-4 relative (+ 3e-5 of the output scale) of the fp64 oracle."""
+    from gssdf_b200 import cabi
+    dev = _dev()
+    rng = np.random.default_rng(n + 1)
+    n_params, _ = oracle.grid_setup()
+    table = rng.uniform(-0.5, 0.5, n_params).astype(np.float32)
+    mlp = _mlp(rng, 64, n_hidden)
+    x = rng.uniform(0.02, 0.98, (n, 3)).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    tab, half, mlp_t, xt = t(table), torch.empty(n_params, dtype=torch.float16, device=dev), t(mlp), t(x)
+    cabi.sdf_table_to_half(tab, half)
+    net = cabi.sdf_net(half, mlp_t, hidden_dim=64, n_hidden=n_hidden, mlp_mode=1)
+    delta = 0.01
+    sdf, y1, feat = torch.empty(variants * n, device=dev), torch.empty(variants * n, device=dev), torch.empty(variants * n, 32, device=dev)
+    cabi.sdf_fwd(net, xt, sdf, y1, feat, n_variants=variants, delta=delta)
+    torch.cuda.synchronize()
+    offs = np.array([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float32)[:variants] * np.float32(delta)
+    pts = (x[None] + offs[:, None]).reshape(-1, 3).astype(np.float32)
+    r_sdf, r_y1, r_feat = oracle.sdf_fwd(pts, table, mlp, 64, n_hidden)
+    assert np.array_equal(feat.cpu().numpy(), r_feat)
+    assert_close_frac(sdf.cpu().numpy(), r_sdf, 1e-4, 3e-5 * np.abs(r_sdf).max(), 0.0, "sdf (tcgen05)")
+    assert_close_frac(y1.cpu().numpy(), r_y1, 1e-4, 3e-5 * np.abs(r_y1).max(), 0.0, "y1 (tcgen05)")
