@@ -16,151 +16,12 @@
 // in REGISTERS across all tiles of a CTA and flushed once (a few million REDs per call instead of 15 k per tile).
 // tiny-cuda-nn's fp16 rounding points are reproduced: table in half, per-corner __hfma2 accumulation,
 // dL/dy -> half, x128, per-corner half product. Deviation: the table gradient accumulates in fp32 RED
-// (the reference: fp16 atomics). MLP arithmetic is fp32 FMA on the CUDA cores in this round (the tcgen05
-// path is the next step).
+// (the reference: fp16 atomics). This file: decoder arithmetic as fp32 FMA on the CUDA cores (mlp_mode 0); the tcgen05
+// kernels (mlp_mode 1) are in sdf_tc.cu.
 #include <cuda_bf16.h>
-#include <cuda_fp16.h>
-
-#include "common.cuh"
+#include "sdf_grid.cuh"
 
 namespace gssdf {
-
-constexpr int kSdfThreads = 256;
-constexpr int kMaxLevels = 16;
-constexpr int kFeat = 32;  // n_levels * n_features_per_level supported by the fused kernels (16 x 2)
-
-struct GridGeom {
-    int L;
-    uint32_t offset[kMaxLevels + 1];  // in table entries (x F for params)
-    float scale[kMaxLevels];
-    uint32_t res[kMaxLevels];
-};
-
-static inline float h_grid_scale(uint32_t level, float log2_pls, uint32_t base) { return exp2f(level * log2_pls) * base - 1.0f; }
-
-static GridGeom make_grid(const gssdf_sdf_net &net) {  // grid.h:692-716
-    GridGeom g;
-    g.L = net.n_levels;
-    uint32_t off = 0;
-    const float l2 = log2f(net.per_level_scale);
-    for (int i = 0; i < net.n_levels && i < kMaxLevels; ++i) {
-        g.scale[i] = h_grid_scale(i, l2, net.base_resolution);
-        g.res[i] = (uint32_t)ceilf(g.scale[i]) + 1;
-        const uint32_t max_params = 0xffffffffu / 2;
-        uint32_t p = powf((float)g.res[i], 3) > (float)max_params ? max_params : g.res[i] * g.res[i] * g.res[i];
-        p = (p + 7u) / 8u * 8u;
-        const uint32_t cap = 1u << net.log2_hashmap_size;
-        if (p > cap) p = cap;
-        g.offset[i] = off;
-        off += p;
-    }
-    g.offset[net.n_levels] = off;
-    return g;
-}
-
-__device__ __forceinline__ uint32_t grid_index(uint32_t hashmap_size, uint32_t res, uint32_t x, uint32_t y, uint32_t z) {
-    // common_device.h:690-707 with the coherent prime hash (:650-655)
-    uint32_t stride = 1, index = 0;
-    if (stride <= hashmap_size) { index += x * stride; stride *= res; }
-    if (stride <= hashmap_size) { index += y * stride; stride *= res; }
-    if (stride <= hashmap_size) { index += z * stride; stride *= res; }
-    if (hashmap_size < stride) index = x ^ (y * 2654435761u) ^ (z * 805459861u);
-    return index % hashmap_size;
-}
-
-struct LevelPos {
-    float pos[3];
-    uint32_t pg[3];
-};
-
-__device__ __forceinline__ LevelPos level_pos(const float x[3], float scale) {  // pos_fract, common_device.h:842-855
-    LevelPos p;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        const float v = fmaf(scale, x[d], 0.5f);
-        const float t = floorf(v);
-        p.pg[d] = (uint32_t)(int)t;
-        p.pos[d] = v - t;
-    }
-    return p;
-}
-
-// one (point, level): the two features, accumulated exactly like kernel_grid<__half>: result = hfma2((half)w, val, result)
-__device__ __forceinline__ float2 encode_level(const __half2 *__restrict__ table, const GridGeom &g, int lvl, const float x[3]) {
-    const __half2 *t = table + g.offset[lvl];
-    const uint32_t hs = g.offset[lvl + 1] - g.offset[lvl];
-    const LevelPos p = level_pos(x, g.scale[lvl]);
-    __half2 vals[8];
-    float w[8];
-#pragma unroll
-    for (int idx = 0; idx < 8; ++idx) {  // issue the 8 gathers first (independent loads in flight)
-        float wt = 1.f;
-        uint32_t c[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            if ((idx & (1 << d)) == 0) { wt *= 1.f - p.pos[d]; c[d] = p.pg[d]; }
-            else { wt *= p.pos[d]; c[d] = p.pg[d] + 1; }
-        }
-        w[idx] = wt;
-        vals[idx] = __ldg(t + grid_index(hs, g.res[lvl], c[0], c[1], c[2]));
-    }
-    __half2 r = __floats2half2_rn(0.f, 0.f);
-#pragma unroll
-    for (int idx = 0; idx < 8; ++idx) r = __hfma2(__float2half2_rn(w[idx]), vals[idx], r);
-    return __half22float2(r);
-}
-
-// backward of one (point, level): scatter the table gradient (optional) and return dL/dx contribution (optional)
-__device__ __forceinline__ void encode_level_bwd(const __half2 *__restrict__ table, float *__restrict__ table_grad, const GridGeom &g,
-                                                 int lvl, const float x[3], float g0, float g1, bool want_dx, float dx[3]) {
-    const uint32_t hs = g.offset[lvl + 1] - g.offset[lvl];
-    const LevelPos p = level_pos(x, g.scale[lvl]);
-    // binding rounding points: dL/dy -> half, x128 in half (TB/tcnn_binding.cpp:133)
-    const __half2 gh = __hmul2(__floats2half2_rn(g0, g1), __float2half2_rn(128.f));
-    if (table_grad) {
-        float *tg = table_grad + 2 * (size_t)g.offset[lvl];
-#pragma unroll
-        for (int idx = 0; idx < 8; ++idx) {
-            float wt = 1.f;
-            uint32_t c[3];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                if ((idx & (1 << d)) == 0) { wt *= 1.f - p.pos[d]; c[d] = p.pg[d]; }
-                else { wt *= p.pos[d]; c[d] = p.pg[d] + 1; }
-            }
-            const float2 v = __half22float2(__hmul2(__float2half2_rn(wt), gh));  // (GRAD_T)weight * grad, grid.h:247
-            const size_t e = 2 * (size_t)grid_index(hs, g.res[lvl], c[0], c[1], c[2]);
-            if (v.x != 0.f) atomicAdd(tg + e, v.x * (1.f / 128.f));
-            if (v.y != 0.f) atomicAdd(tg + e + 1, v.y * (1.f / 128.f));
-        }
-    }
-    if (want_dx) {  // dy_dx (grid.h:170-211) folded with kernel_grid_backward_input (:323-349)
-        const __half2 *t = table + g.offset[lvl];
-        const float2 ghf = __half22float2(gh);
-#pragma unroll
-        for (int gd = 0; gd < 3; ++gd) {
-            float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-            for (int idx = 0; idx < 4; ++idx) {
-                float wt = g.scale[lvl];
-                uint32_t c[3];
-#pragma unroll
-                for (int nd = 0; nd < 2; ++nd) {
-                    const int d = nd >= gd ? nd + 1 : nd;
-                    if ((idx & (1 << nd)) == 0) { wt *= 1.f - p.pos[d]; c[d] = p.pg[d]; }
-                    else { wt *= p.pos[d]; c[d] = p.pg[d] + 1; }
-                }
-                c[gd] = p.pg[gd];
-                const float2 l = __half22float2(__ldg(t + grid_index(hs, g.res[lvl], c[0], c[1], c[2])));
-                c[gd] = p.pg[gd] + 1;
-                const float2 r = __half22float2(__ldg(t + grid_index(hs, g.res[lvl], c[0], c[1], c[2])));
-                acc0 += wt * (r.x - l.x);
-                acc1 += wt * (r.y - l.y);
-            }
-            dx[gd] = (ghf.x * acc0 + ghf.y * acc1) * (1.f / 128.f);
-        }
-    }
-}
 
 __global__ void __launch_bounds__(256) table_to_half_kernel(const float *__restrict__ in, __half *__restrict__ out, int64_t n) {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -234,21 +95,6 @@ __device__ __forceinline__ void dense_layer(const float *s_in, int K, const floa
 }
 
 // evaluation index gi = variant * n + base point; variants 1..6 = +x,-x,+y,-y,+z,-z offsets by delta (local_map.cpp:112-121)
-__device__ __forceinline__ void load_x(const gssdf_sdf_net &net, const float *__restrict__ x, int64_t gi, int64_t n, float delta,
-                                       float out[3]) {
-    const int64_t i = gi % n;
-    const int var = (int)(gi / n);
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        float v = __ldg(x + 3 * i + d);
-        if (var > 0 && (var - 1) / 2 == d) v += ((var - 1) & 1) ? -delta : delta;
-        out[d] = net.inv_size != 0.f ? __fmaf_rn(v - net.origin[d], net.inv_size, 0.5f) : v;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// forward
-// ---------------------------------------------------------------------------------------------
 template <int HID>
 __global__ void __launch_bounds__(kSdfThreads)
 sdf_fwd_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
@@ -635,6 +481,7 @@ static size_t bwd_smem() {
 using namespace gssdf;
 
 extern "C" int gssdf_sdf_fwd_tc_launch(const gssdf_sdf_fwd_args *a, const gssdf::GridGeom *g, gssdf_stream_t stream);
+extern "C" int gssdf_sdf_bwd_tc_launch(const gssdf_sdf_bwd_args *a, const gssdf::GridGeom *g, gssdf_stream_t stream);
 
 static int check_net(const char *who, const gssdf_sdf_net &net) {
     GSSDF_REQUIRE(net.n_levels == 16 && net.n_features_per_level == 2, GSSDF_EUNSUPPORTED,
@@ -703,8 +550,14 @@ extern "C" int gssdf_sdf_bwd(const gssdf_sdf_bwd_args *a, gssdf_stream_t stream)
     GSSDF_REQUIRE(a->n >= 0, GSSDF_EINVAL, "sdf_bwd: negative n");
     if (a->n == 0) return GSSDF_OK;
     GSSDF_REQUIRE(a->x && a->v_sdf, GSSDF_EINVAL, "sdf_bwd: x and v_sdf must be non-null");
+    GSSDF_REQUIRE(((uintptr_t)a->table_grad & 7) == 0, GSSDF_EINVAL, "sdf_bwd: table_grad must be 8-byte aligned");
     const GridGeom g = make_grid(a->net);
     GSSDF_REQUIRE(a->n_variants == 0 || a->n_variants == 1 || a->n_variants == 7, GSSDF_EINVAL, "sdf_bwd: n_variants must be 1 or 7");
+    if (a->net.mlp_mode == 1) {
+        GSSDF_REQUIRE(a->net.hidden_dim == 64, GSSDF_EUNSUPPORTED, "sdf_bwd: the tcgen05 decoder needs hidden_dim 64");
+        return gssdf_sdf_bwd_tc_launch(a, &g, stream);
+    }
+    GSSDF_REQUIRE(a->net.mlp_mode == 0, GSSDF_EINVAL, "sdf_bwd: mlp_mode must be 0 or 1");
     const int64_t n_tiles = (a->n * (a->n_variants > 1 ? a->n_variants : 1) + 63) / 64;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -734,221 +587,3 @@ extern "C" int gssdf_sdf_loss(const gssdf_sdf_loss_args *a, gssdf_stream_t strea
     return GSSDF_OK;
 }
 
-// =============================================================================================
-// tcgen05 forward: the decoder's dense 64-wide layers on the 5th-generation tensor cores.
-//
-// One CTA = 128 points = one UMMA M=128 tile. Per layer D[128 x 64] (fp32, TMEM) = A[128 x K] * W^T[K x 64], issued by ONE
-// thread as tcgen05.mma.cta_group::1.kind::f16 (bf16 inputs, fp32 accumulate), N = 64, K = 16 per instruction.
-// fp32 parity: both operands are split x = hi + mid (two bf16 terms, 16 significant bits) and three products are
-// accumulated, hi*hi + hi*mid + mid*hi (error ~2^-16 relative; the hash-grid features are fp16 values, for which the
-// split is exact). Operands live in shared memory in the canonical K-major no-swizzle layout (8 x 16-byte core
-// matrices; LBO = 128 B between K-adjacent cores, SBO = 1024 B between 8-row groups); the epilogue reads the
-// accumulator with tcgen05.ld (32 lanes x 32 columns per warp), adds the bias, applies ReLU in registers and writes the next
-// layer's A operand straight back into the canonical layout -- activations never leave the SM.
-// =============================================================================================
-namespace gssdf {
-
-constexpr int kTcThreads = 256;
-constexpr uint32_t kLBO = 128, kSBO = 1024;  // bytes
-
-__device__ __forceinline__ uint32_t canon_off(int r, int k) {  // byte offset of bf16 element (row r, col k)
-    return (uint32_t)((r >> 3) * kSBO + (k >> 3) * kLBO + (r & 7) * 16 + (k & 7) * 2);
-}
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, bits [0,14)
-    d |= (uint64_t)(kLBO >> 4) << 16;               // leading (K-direction) byte offset, bits [16,30)
-    d |= (uint64_t)(kSBO >> 4) << 32;               // stride (M/N-direction) byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-    return d;                                       // base_offset 0, lbo_mode 0, layout_type 0 = no swizzle
-}
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &mid) {
-    hi = __float2bfloat16_rn(x);
-    mid = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
-    for (int it = 0; it < (1 << 24); ++it) {
-        uint32_t ok;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (ok) return true;
-    }
-    return false;
-}
-
-__global__ void __launch_bounds__(kTcThreads)
-sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
-    constexpr int TM = 128, HID = 64;
-    extern __shared__ __align__(1024) unsigned char s_tc[];
-    unsigned char *sA_hi = s_tc;                  // 16 KB : [128 x 64] bf16 canonical
-    unsigned char *sA_mid = sA_hi + 16384;        // 16 KB
-    unsigned char *sW_hi = sA_mid + 16384;        // 8 KB  : [64 x 64] bf16 canonical
-    unsigned char *sW_mid = sW_hi + 8192;         // 8 KB
-    float *s_bias = reinterpret_cast<float *>(sW_mid + 8192);  // [64]
-    float *s_wout = s_bias + 64;                  // [2][64] + [2]
-    float *s_part = s_wout + 130 + 2;             // [2 halves][128][2]
-    __shared__ __align__(8) uint64_t s_mbar;
-    __shared__ uint32_t s_tmem;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t n_eval = a.n * max(a.n_variants, 1);
-    const int64_t base = (int64_t)blockIdx.x * TM;
-    const int tm = (int)min((int64_t)TM, n_eval - base);
-    const int64_t n_live = a.n_live ? min((int64_t)*a.n_live, a.n) : a.n;
-    if (base % a.n >= n_live && base % a.n + TM <= a.n) return;  // whole tile beyond the live rows (CTA-uniform)
-
-    if (warp == 0) {  // TMEM: 64 fp32 columns x 128 lanes for the accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(64));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    if (tid == 0) {
-        mbar_init(&s_mbar, 1);
-        fence_mbar_init();
-    }
-    // 1. hash-grid encode -> A (layer 0 input, K = 32), split into bf16 hi/mid (exact: features are fp16 values)
-    const __half2 *table = reinterpret_cast<const __half2 *>(a.net.table_half);
-    for (int task = tid; task < TM * g.L; task += kTcThreads) {
-        const int p = task % TM, lvl = task / TM;
-        float2 f = make_float2(0.f, 0.f);
-        if (p < tm && (base + p) % a.n < n_live) {
-            float x[3];
-            load_x(a.net, a.x, base + p, a.n, a.delta, x);
-            f = encode_level(table, g, lvl, x);
-            if (a.feat) { a.feat[(base + p) * kFeat + 2 * lvl] = f.x; a.feat[(base + p) * kFeat + 2 * lvl + 1] = f.y; }
-        }
-        __nv_bfloat16 h0, m0, h1, m1;
-        split_bf16(f.x, h0, m0);
-        split_bf16(f.y, h1, m1);
-        const uint32_t off = canon_off(p, 2 * lvl);
-        *reinterpret_cast<__nv_bfloat162 *>(sA_hi + off) = __halves2bfloat162(h0, h1);
-        *reinterpret_cast<__nv_bfloat162 *>(sA_mid + off) = __halves2bfloat162(m0, m1);
-    }
-    // output layer parameters (HID -> 2) for the CUDA-core tail
-    const int nh = 1 + a.net.n_hidden;
-    {
-        const float *Wo = a.net.mlp + ((size_t)HID * kFeat + HID) + (size_t)a.net.n_hidden * ((size_t)HID * HID + HID);
-        for (int e = tid; e < 2 * HID + 2; e += kTcThreads) s_wout[e] = __ldg(Wo + e);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint32_t tmem = s_tmem;
-    // instruction descriptor: D = F32, A = B = BF16, both K-major, N = 64, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-
-    const float *W = a.net.mlp;
-    int K = kFeat;
-    bool ok = true;
-    for (int l = 0; l < nh; ++l) {
-        // 2. stage W_l [64 x K] (row-major fp32, global) as bf16 hi/mid in the canonical layout; bias
-        for (int e = tid; e < HID * K; e += kTcThreads) {
-            const int o = e / K, k = e % K;
-            __nv_bfloat16 hi, mid;
-            split_bf16(__ldg(W + e), hi, mid);
-            const uint32_t off = canon_off(o, k);
-            *reinterpret_cast<__nv_bfloat16 *>(sW_hi + off) = hi;
-            *reinterpret_cast<__nv_bfloat16 *>(sW_mid + off) = mid;
-        }
-        if (tid < HID) s_bias[tid] = __ldg(W + (size_t)HID * K + tid);
-        fence_proxy_async();  // generic-proxy smem writes (A from the previous epilogue / encode, W) -> visible to the tensor core
-        __syncthreads();
-        // 3. one thread issues the MMAs: 3 bf16 products per 16-wide K step
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t aH = smem_u32(sA_hi), aM = smem_u32(sA_mid), wH = smem_u32(sW_hi), wM = smem_u32(sW_mid);
-            uint32_t acc = 0;
-            for (int ks = 0; ks < K / 16; ++ks) {
-                const uint32_t ko = ks * 2 * kLBO;
-                umma_bf16(tmem, make_smem_desc(aH + ko), make_smem_desc(wH + ko), idesc, acc); acc = 1;
-                umma_bf16(tmem, make_smem_desc(aH + ko), make_smem_desc(wM + ko), idesc, acc);
-                umma_bf16(tmem, make_smem_desc(aM + ko), make_smem_desc(wH + ko), idesc, acc);
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_mbar)) : "memory");
-        }
-        // 4. wait for the accumulator
-        ok = mbar_wait_bounded(&s_mbar, (uint32_t)(l & 1));
-        if (!ok) break;
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        // 5. epilogue: warp w owns TMEM lanes 32*(w%4).. and columns 32*(w/4)..
-        const int q = warp & 3, h = warp >> 2;
-        const int row = 32 * q + lane;
-        uint32_t v[32];
-        const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * h);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
-            "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float act[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) act[j] = fmaxf(__uint_as_float(v[j]) + s_bias[32 * h + j], 0.f);
-        if (l < nh - 1) {
-            // next layer's A operand: row `row`, columns 32h .. 32h+31 -> four 16-byte stores per split
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                __nv_bfloat16 hi[8], mid[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) split_bf16(act[jj * 8 + e], hi[e], mid[e]);
-                const uint32_t off = canon_off(row, 32 * h + jj * 8);
-                *reinterpret_cast<uint4 *>(sA_hi + off) = *reinterpret_cast<uint4 *>(hi);
-                *reinterpret_cast<uint4 *>(sA_mid + off) = *reinterpret_cast<uint4 *>(mid);
-            }
-        } else {
-            float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                p0 = fmaf(act[j], s_wout[32 * h + j], p0);
-                p1 = fmaf(act[j], s_wout[HID + 32 * h + j], p1);
-            }
-            s_part[(h * TM + row) * 2] = p0;
-            s_part[(h * TM + row) * 2 + 1] = p1;
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;");  // TMEM reads done before the next layer's MMA overwrites D
-        W += (size_t)HID * K + HID;
-        K = HID;
-    }
-    __syncthreads();
-    if (ok && tid < TM) {
-        const int p = tid;
-        if (p < tm && (base + p) % a.n < n_live) {
-            a.sdf[base + p] = s_part[p * 2] + s_part[(TM + p) * 2] + s_wout[2 * HID];
-            if (a.y1) a.y1[base + p] = s_part[p * 2 + 1] + s_part[(TM + p) * 2 + 1] + s_wout[2 * HID + 1];
-        }
-    }
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(64));
-    if (!ok) __trap();  // the accumulator never arrived: fail loudly instead of hanging
-}
-
-}  // namespace gssdf
-
-extern "C" int gssdf_sdf_fwd_tc_launch(const gssdf_sdf_fwd_args *a, const gssdf::GridGeom *g, gssdf_stream_t stream) {
-    using namespace gssdf;
-    const size_t smem = 16384 * 2 + 8192 * 2 + sizeof(float) * (64 + 132 + 2 * 128 * 2) + 1024;
-    GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = cdiv(a->n * (a->n_variants > 1 ? a->n_variants : 1), 128);
-    sdf_fwd_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(*a, *g);
-    GSSDF_LAUNCH_OK("sdf_fwd_tc_kernel");
-    return GSSDF_OK;
-}

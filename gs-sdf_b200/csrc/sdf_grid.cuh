@@ -1,0 +1,165 @@
+// Multiresolution hash-grid geometry + per-(point, level) encode / backward helpers shared by the CUDA-core kernels
+// (sdf.cu) and the tcgen05 kernels (sdf_tc.cu). Reference: TCNN/include/tiny-cuda-nn/encodings/grid.h:49-349,
+// common_device.h:631-655,690-718,842-855; TB/tcnn_binding.cpp:94-149 for the fp16 rounding points.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace gssdf {
+
+constexpr int kSdfThreads = 256;
+constexpr int kMaxLevels = 16;
+constexpr int kFeat = 32;  // n_levels * n_features_per_level supported by the fused kernels (16 x 2)
+
+struct GridGeom {
+    int L;
+    uint32_t offset[kMaxLevels + 1];  // in table entries (x F for params)
+    float scale[kMaxLevels];
+    uint32_t res[kMaxLevels];
+};
+
+static inline float h_grid_scale(uint32_t level, float log2_pls, uint32_t base) { return exp2f(level * log2_pls) * base - 1.0f; }
+
+static GridGeom make_grid(const gssdf_sdf_net &net) {  // grid.h:692-716
+    GridGeom g;
+    g.L = net.n_levels;
+    uint32_t off = 0;
+    const float l2 = log2f(net.per_level_scale);
+    for (int i = 0; i < net.n_levels && i < kMaxLevels; ++i) {
+        g.scale[i] = h_grid_scale(i, l2, net.base_resolution);
+        g.res[i] = (uint32_t)ceilf(g.scale[i]) + 1;
+        const uint32_t max_params = 0xffffffffu / 2;
+        uint32_t p = powf((float)g.res[i], 3) > (float)max_params ? max_params : g.res[i] * g.res[i] * g.res[i];
+        p = (p + 7u) / 8u * 8u;
+        const uint32_t cap = 1u << net.log2_hashmap_size;
+        if (p > cap) p = cap;
+        g.offset[i] = off;
+        off += p;
+    }
+    g.offset[net.n_levels] = off;
+    return g;
+}
+
+__device__ __forceinline__ uint32_t grid_index(uint32_t hashmap_size, uint32_t res, uint32_t x, uint32_t y, uint32_t z) {
+    // common_device.h:690-707 with the coherent prime hash (:650-655)
+    uint32_t stride = 1, index = 0;
+    if (stride <= hashmap_size) { index += x * stride; stride *= res; }
+    if (stride <= hashmap_size) { index += y * stride; stride *= res; }
+    if (stride <= hashmap_size) { index += z * stride; stride *= res; }
+    if (hashmap_size < stride) index = x ^ (y * 2654435761u) ^ (z * 805459861u);
+    return index % hashmap_size;
+}
+
+struct LevelPos {
+    float pos[3];
+    uint32_t pg[3];
+};
+
+__device__ __forceinline__ LevelPos level_pos(const float x[3], float scale) {  // pos_fract, common_device.h:842-855
+    LevelPos p;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float v = fmaf(scale, x[d], 0.5f);
+        const float t = floorf(v);
+        p.pg[d] = (uint32_t)(int)t;
+        p.pos[d] = v - t;
+    }
+    return p;
+}
+
+// one (point, level): the two features, accumulated exactly like kernel_grid<__half>: result = hfma2((half)w, val, result)
+__device__ __forceinline__ float2 encode_level(const __half2 *__restrict__ table, const GridGeom &g, int lvl, const float x[3]) {
+    const __half2 *t = table + g.offset[lvl];
+    const uint32_t hs = g.offset[lvl + 1] - g.offset[lvl];
+    const LevelPos p = level_pos(x, g.scale[lvl]);
+    __half2 vals[8];
+    float w[8];
+#pragma unroll
+    for (int idx = 0; idx < 8; ++idx) {  // issue the 8 gathers first (independent loads in flight)
+        float wt = 1.f;
+        uint32_t c[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if ((idx & (1 << d)) == 0) { wt *= 1.f - p.pos[d]; c[d] = p.pg[d]; }
+            else { wt *= p.pos[d]; c[d] = p.pg[d] + 1; }
+        }
+        w[idx] = wt;
+        vals[idx] = __ldg(t + grid_index(hs, g.res[lvl], c[0], c[1], c[2]));
+    }
+    __half2 r = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+    for (int idx = 0; idx < 8; ++idx) r = __hfma2(__float2half2_rn(w[idx]), vals[idx], r);
+    return __half22float2(r);
+}
+
+// backward of one (point, level): scatter the table gradient (optional) and return dL/dx contribution (optional)
+__device__ __forceinline__ void encode_level_bwd(const __half2 *__restrict__ table, float *__restrict__ table_grad, const GridGeom &g,
+                                                 int lvl, const float x[3], float g0, float g1, bool want_dx, float dx[3]) {
+    const uint32_t hs = g.offset[lvl + 1] - g.offset[lvl];
+    const LevelPos p = level_pos(x, g.scale[lvl]);
+    // binding rounding points: dL/dy -> half, x128 in half (TB/tcnn_binding.cpp:133)
+    const __half2 gh = __hmul2(__floats2half2_rn(g0, g1), __float2half2_rn(128.f));
+    if (table_grad) {
+        float *tg = table_grad + 2 * (size_t)g.offset[lvl];
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) {
+            float wt = 1.f;
+            uint32_t c[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if ((idx & (1 << d)) == 0) { wt *= 1.f - p.pos[d]; c[d] = p.pg[d]; }
+                else { wt *= p.pos[d]; c[d] = p.pg[d] + 1; }
+            }
+            const float2 v = __half22float2(__hmul2(__float2half2_rn(wt), gh));  // (GRAD_T)weight * grad, grid.h:247
+            const size_t e = 2 * (size_t)grid_index(hs, g.res[lvl], c[0], c[1], c[2]);
+            // one 8-byte vector RED per corner (red.global.add.v2.f32, sm_90+); table_grad is 8-byte aligned (checked on the host)
+            if (v.x != 0.f || v.y != 0.f) atomicAdd(reinterpret_cast<float2 *>(tg + e), make_float2(v.x * (1.f / 128.f), v.y * (1.f / 128.f)));
+        }
+    }
+    if (want_dx) {  // dy_dx (grid.h:170-211) folded with kernel_grid_backward_input (:323-349)
+        const __half2 *t = table + g.offset[lvl];
+        const float2 ghf = __half22float2(gh);
+#pragma unroll
+        for (int gd = 0; gd < 3; ++gd) {
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int idx = 0; idx < 4; ++idx) {
+                float wt = g.scale[lvl];
+                uint32_t c[3];
+#pragma unroll
+                for (int nd = 0; nd < 2; ++nd) {
+                    const int d = nd >= gd ? nd + 1 : nd;
+                    if ((idx & (1 << nd)) == 0) { wt *= 1.f - p.pos[d]; c[d] = p.pg[d]; }
+                    else { wt *= p.pos[d]; c[d] = p.pg[d] + 1; }
+                }
+                c[gd] = p.pg[gd];
+                const float2 l = __half22float2(__ldg(t + grid_index(hs, g.res[lvl], c[0], c[1], c[2])));
+                c[gd] = p.pg[gd] + 1;
+                const float2 r = __half22float2(__ldg(t + grid_index(hs, g.res[lvl], c[0], c[1], c[2])));
+                acc0 += wt * (r.x - l.x);
+                acc1 += wt * (r.y - l.y);
+            }
+            dx[gd] = (ghf.x * acc0 + ghf.y * acc1) * (1.f / 128.f);
+        }
+    }
+}
+
+__device__ __forceinline__ void load_x(const gssdf_sdf_net &net, const float *__restrict__ x, int64_t gi, int64_t n, float delta,
+                                       float out[3]) {
+    const int64_t i = gi % n;
+    const int var = (int)(gi / n);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float v = __ldg(x + 3 * i + d);
+        if (var > 0 && (var - 1) / 2 == d) v += ((var - 1) & 1) ? -delta : delta;
+        out[d] = net.inv_size != 0.f ? __fmaf_rn(v - net.origin[d], net.inv_size, 0.5f) : v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+
+}  // namespace gssdf

@@ -173,10 +173,12 @@ def l1_loss(Cn, W, H, out_colors, gt, w_rgb, w_depth, loss_out, v_out_colors):
 
 # ---- SDF branch -------------------------------------------------------------------------------
 def sdf_net(table_half, mlp, n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=2.0,
-            hidden_dim=64, n_hidden=3, origin=(0.0, 0.0, 0.0), inv_size=0.0, mlp_mode=0):
+            hidden_dim=64, n_hidden=3, origin=(0.0, 0.0, 0.0), inv_size=0.0, mlp_mode=0, mlp_packed=None):
+    """The struct holds RAW pointers: the caller keeps table_half / mlp / mlp_packed alive."""
     return make_args("gssdf_sdf_net", n_levels=n_levels, n_features_per_level=n_features, log2_hashmap_size=log2_hashmap_size,
                      base_resolution=base_resolution, per_level_scale=per_level_scale, hidden_dim=hidden_dim, n_hidden=n_hidden,
-                     table_half=table_half, mlp=mlp, origin=list(origin), inv_size=inv_size, mlp_mode=mlp_mode)
+                     table_half=table_half, mlp=mlp, origin=list(origin), inv_size=inv_size, mlp_mode=mlp_mode,
+                     mlp_packed=mlp_packed)
 
 
 def sdf_table_params(net):
@@ -185,6 +187,16 @@ def sdf_table_params(net):
 
 def sdf_mlp_params(net):
     return int(lib().gssdf_sdf_mlp_params(_lib.C.byref(net)))
+
+
+def sdf_mlp_packed_bytes(net):
+    return int(lib().gssdf_sdf_mlp_packed_bytes(_lib.C.byref(net)))
+
+
+def sdf_mlp_pack(net, packed):
+    """Pre-split the hidden layers' weights (bf16 hi/mid/lo, operand layout) for mlp_mode=1; `packed` = uint8 device tensor."""
+    assert packed.numel() * packed.element_size() >= sdf_mlp_packed_bytes(net)
+    check(lib().gssdf_sdf_mlp_pack(_lib.C.byref(net), _lib.C.c_void_p(packed.data_ptr()), _stream()))
 
 
 def sdf_table_to_half(table_f32, table_f16):

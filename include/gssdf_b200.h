@@ -341,14 +341,23 @@ typedef struct gssdf_sdf_net {
     const float *mlp;       /* [gssdf_sdf_mlp_params] fp32 */
     float origin[3];        /* world -> unit cube: x01 = (x - origin) * inv_size + 0.5 (SubMap::xyz_to_zp1_pts, */
     float inv_size;         /*   include/neural_net/sub_map.cpp:82-97); inv_size == 0 -> x is already in [0,1]^3 */
-    int32_t mlp_mode;       /* forward decoder arithmetic: 0 = fp32 FMA on the CUDA cores (bit-for-bit the fp32 reference order
-                               up to summation order); 1 = 5th-gen tensor cores: tcgen05.mma kind::f16 on a 2-term bf16 split
-                               of both operands (hi*hi + hi*mid + mid*hi, fp32 accumulation in TMEM; ~2^-16 relative),
-                               hidden_dim 64 only */
+    int32_t mlp_mode;       /* decoder arithmetic (forward and backward):
+                               0 = fp32 FMA on the CUDA cores;
+                               1 = 5th-gen tensor cores (hidden_dim 64 only): tcgen05.mma kind::f16 on bf16 splits of both operands
+                                   with fp32 accumulation in TMEM. Forward / forward-recompute: 3-term split (24 significant bits,
+                                   6 products -> fp32-grade pre-activations, so ReLU decisions match the fp32 path); backward
+                                   GEMMs: 2-term split, 4 products (~2^-17 relative). Needs mlp_packed. */
+    const void *mlp_packed; /* mode 1 only: [gssdf_sdf_mlp_packed_bytes] the hidden layers' weights pre-split into bf16 hi/mid/lo in
+                               the shared-memory operand layout (gssdf_sdf_mlp_pack; refresh after every optimiser step, like
+                               table_half); 16-byte aligned. NULL in mode 0 */
 } gssdf_sdf_net;
 int64_t gssdf_sdf_table_params(const gssdf_sdf_net *net);
 int64_t gssdf_sdf_mlp_params(const gssdf_sdf_net *net);
 int gssdf_sdf_table_to_half(const float *table_f32, void *table_f16, int64_t n, gssdf_stream_t stream);
+/* mode-1 weight image: (1 + n_hidden) x 24 KiB, each = 8 groups of 8 output rows x [hi | mid | lo] x 8 column groups x (8 rows x 16 B).
+   One small kernel; net->mlp is read, net->mlp_packed is ignored. */
+int64_t gssdf_sdf_mlp_packed_bytes(const gssdf_sdf_net *net);
+int gssdf_sdf_mlp_pack(const gssdf_sdf_net *net, void *packed, gssdf_stream_t stream);
 
 typedef struct gssdf_sdf_fwd_args {
     gssdf_sdf_net net;

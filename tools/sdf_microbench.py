@@ -1,0 +1,46 @@
+import sys, numpy as np, torch
+sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/gs-sdf_b200"); sys.path.insert(0, "/root/repo/tests")
+from oracle import oracle as O
+from gssdf_b200 import cabi
+O.build()
+dev = torch.device("cuda:0")
+def _mlp(rng, hidden, n_hidden, in_dim=32):
+    dims = [in_dim] + [hidden] * (1 + n_hidden) + [2]; ps = []
+    for k, o in zip(dims[:-1], dims[1:]):
+        b = 1 / np.sqrt(k); ps += [rng.uniform(-b, b, o * k), rng.uniform(-b, b, o)]
+    return np.concatenate(ps).astype(np.float32)
+n, n_hidden = 40000, 3
+rng = np.random.default_rng(7 * n + 3)
+n_params, _ = O.grid_setup()
+table = rng.uniform(-0.5, 0.5, n_params).astype(np.float32); mlp = _mlp(rng, 64, n_hidden)
+x = rng.uniform(0.02, 0.98, (n, 3)).astype(np.float32)
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+tab, half, mlp_t, xt = t(table), torch.empty(n_params, dtype=torch.float16, device=dev), t(mlp), t(x)
+cabi.sdf_table_to_half(tab, half)
+v_sdf, v_y1 = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+r_tg, r_mg, r_vx = O.sdf_bwd(x, table, mlp, v_sdf, v_y1, 64, n_hidden)
+sizes = [("W0", 64*32), ("b0", 64)] + sum([[(f"W{i}", 64*64), (f"b{i}", 64)] for i in range(1, 1+n_hidden)], []) + [("Wo", 128), ("bo", 2)]
+for mode in (0, 1):
+    probe = cabi.sdf_net(half, mlp_t, hidden_dim=64, n_hidden=n_hidden)
+    packed = torch.empty(cabi.sdf_mlp_packed_bytes(probe), dtype=torch.uint8, device=dev)
+    cabi.sdf_mlp_pack(probe, packed)
+    net = cabi.sdf_net(half, mlp_t, hidden_dim=64, n_hidden=n_hidden, mlp_mode=mode, mlp_packed=packed if mode else None)
+    tg, mg, vx = torch.zeros(n_params, device=dev), torch.zeros(len(mlp), device=dev), torch.empty(n, 3, device=dev)
+    cabi.sdf_bwd(net, xt, t(v_sdf), t(v_y1), tg, mg, vx); torch.cuda.synchronize()
+    m = mg.cpu().numpy(); o = 0
+    print("mode", mode, "L2 rel", np.linalg.norm(m - r_mg) / np.linalg.norm(r_mg))
+    for name, sz in sizes:
+        d = np.abs(m[o:o+sz] - r_mg[o:o+sz]); print(f"  {name}: max|ref| {np.abs(r_mg[o:o+sz]).max():.3e} max err {d.max():.3e} at {d.argmax()}"); o += sz
+    # timing
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xb = torch.rand(229376, 3, device=dev) * 0.96 + 0.02; vb = torch.randn(229376, device=dev)
+    vxb = torch.empty(229376, 3, device=dev)
+    for _ in range(3): cabi.sdf_bwd(net, xb, vb, vb, tg, mg, vxb)
+    s.record()
+    for _ in range(10): cabi.sdf_bwd(net, xb, vb, vb, tg, mg, vxb)
+    e.record(); torch.cuda.synchronize(); print("  bwd 229376 pts ms", s.elapsed_time(e) / 10)
+    sd = torch.empty(229376, device=dev)
+    for _ in range(3): cabi.sdf_fwd(net, xb, sd, sd.clone(), None)
+    s.record()
+    for _ in range(10): cabi.sdf_fwd(net, xb, sd, None, None)
+    e.record(); torch.cuda.synchronize(); print("  fwd 229376 pts ms", s.elapsed_time(e) / 10)
