@@ -43,13 +43,17 @@ static GridGeom make_grid(const gssdf_sdf_net &net) {  // grid.h:692-716
 }
 
 __device__ __forceinline__ uint32_t grid_index(uint32_t hashmap_size, uint32_t res, uint32_t x, uint32_t y, uint32_t z) {
-    // common_device.h:690-707 with the coherent prime hash (:650-655)
+    // common_device.h:690-707 with the coherent prime hash (:650-655). The reference ends with `index % hashmap_size`. For a
+    // hashed level hashmap_size == 2^log2_hashmap_size (make_grid: res^3 exceeded the cap) -> a mask; for a dense level the
+    // index only reaches hashmap_size on the far faces of the unit cube (corner coordinate == res) or for points outside
+    // it -> the division runs on that rare branch only. Same values as the reference everywhere.
     uint32_t stride = 1, index = 0;
     if (stride <= hashmap_size) { index += x * stride; stride *= res; }
     if (stride <= hashmap_size) { index += y * stride; stride *= res; }
     if (stride <= hashmap_size) { index += z * stride; stride *= res; }
-    if (hashmap_size < stride) index = x ^ (y * 2654435761u) ^ (z * 805459861u);
-    return index % hashmap_size;
+    if (hashmap_size < stride) return (x ^ (y * 2654435761u) ^ (z * 805459861u)) & (hashmap_size - 1u);
+    if (index >= hashmap_size) index %= hashmap_size;
+    return index;
 }
 
 struct LevelPos {

@@ -28,6 +28,8 @@ namespace gssdf {
 
 constexpr int kFwdTcThreads = 256;   // forward: one 128-point tile per CTA, several CTAs per SM
 constexpr int kBwdTcThreads = 512;   // backward: persistent, one CTA per SM
+constexpr int kLevels = 16;          // check_net: the fused kernels support 16 levels x 2 features
+static_assert(128 * kLevels == 4 * kBwdTcThreads, "encode batches assume 4 tasks per thread");
 constexpr uint32_t kWImg = 24576;    // bytes of one layer's packed weight image
 constexpr uint32_t kGW = 3072;       // weight image: bytes per 8 output rows (hi | mid | lo)
 constexpr uint32_t kGA = 2048;       // activations / gradients: bytes per 8 points (hi | mid)
@@ -261,21 +263,29 @@ sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
         }
         for (int e = tid; e < 2 * HID + 2; e += kFwdTcThreads) s_wout[e] = __ldg(W + e);
     }
-    // 1. encode: 128 points x 16 levels -> features (global, optional) + A operand of layer 0
-    for (int task = tid; task < TM * g.L; task += kFwdTcThreads) {
-        const int p = task % TM, lvl = task / TM;
-        float2 f = make_float2(0.f, 0.f);
-        if (p < tm && (base + p) % a.n < n_live) {
+    // 1. encode: 128 points x 16 levels -> features (global, optional) + A operand of layer 0. Branch-free batches of 4 (point,
+    //    level) tasks per thread so that 32 table gathers are in flight before the first one is consumed.
+    for (int t0 = 0; t0 < TM * kLevels; t0 += 4 * kFwdTcThreads) {
+        float2 f[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int task = t0 + i * kFwdTcThreads + tid, p = task % TM, lvl = task / TM;
             float x[3];
-            load_x(a.net, a.x, base + p, a.n, a.delta, x);
-            f = encode_level(table, g, lvl, x);
-            if (a.feat) *reinterpret_cast<float2 *>(a.feat + (base + p) * kFeat + 2 * lvl) = f;
+            load_x(a.net, a.x, min(base + p, n_eval - 1), a.n, a.delta, x);
+            f[i] = encode_level(table, g, lvl, x);
         }
-        __nv_bfloat16 h0, m0, h1, m1;
-        split2(f.x, h0, m0);
-        split2(f.y, h1, m1);
-        *reinterpret_cast<__nv_bfloat162 *>(sF + off_feat(p, 2 * lvl, 0)) = __halves2bfloat162(h0, h1);
-        *reinterpret_cast<__nv_bfloat162 *>(sF + off_feat(p, 2 * lvl, 1)) = __halves2bfloat162(m0, m1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int task = t0 + i * kFwdTcThreads + tid, p = task % TM, lvl = task / TM;
+            const bool live = p < tm && (base + p) % a.n < n_live;
+            if (!live) f[i] = make_float2(0.f, 0.f);
+            if (live && a.feat) *reinterpret_cast<float2 *>(a.feat + (base + p) * kFeat + 2 * lvl) = f[i];
+            __nv_bfloat16 h0, m0, h1, m1;
+            split2(f[i].x, h0, m0);
+            split2(f[i].y, h1, m1);
+            *reinterpret_cast<__nv_bfloat162 *>(sF + off_feat(p, 2 * lvl, 0)) = __halves2bfloat162(h0, h1);
+            *reinterpret_cast<__nv_bfloat162 *>(sF + off_feat(p, 2 * lvl, 1)) = __halves2bfloat162(m0, m1);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -400,20 +410,26 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles)
             mbar_arrive_expect_tx(&s_mbar[1], kWImg);
             bulk_g2s(sW, wimg, kWImg, &s_mbar[1]);
         }
-        // ---- 1. encode -> a_0, seeds
-        for (int task = tid; task < TM * g.L; task += NT) {
-            const int p = task % TM, lvl = task / TM;
-            float2 f = make_float2(0.f, 0.f);
-            if (LIVE_TC(p)) {
+        // ---- 1. encode -> a_0, seeds (4 tasks per thread, branch-free: 32 gathers in flight)
+        {
+            float2 f[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int task = i * NT + tid, p = task % TM, lvl = task / TM;
                 float x[3];
-                load_x(a.net, a.x, base + p, a.n, a.delta, x);
-                f = encode_level(table, g, lvl, x);
+                load_x(a.net, a.x, min(base + p, n_eval - 1), a.n, a.delta, x);
+                f[i] = encode_level(table, g, lvl, x);
             }
-            __nv_bfloat16 h0, m0, h1, m1;
-            split2(f.x, h0, m0);
-            split2(f.y, h1, m1);
-            *reinterpret_cast<__nv_bfloat162 *>(sF + off_feat(p, 2 * lvl, 0)) = __halves2bfloat162(h0, h1);
-            *reinterpret_cast<__nv_bfloat162 *>(sF + off_feat(p, 2 * lvl, 1)) = __halves2bfloat162(m0, m1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int task = i * NT + tid, p = task % TM, lvl = task / TM;
+                if (!LIVE_TC(p)) f[i] = make_float2(0.f, 0.f);
+                __nv_bfloat16 h0, m0, h1, m1;
+                split2(f[i].x, h0, m0);
+                split2(f[i].y, h1, m1);
+                *reinterpret_cast<__nv_bfloat162 *>(sF + off_feat(p, 2 * lvl, 0)) = __halves2bfloat162(h0, h1);
+                *reinterpret_cast<__nv_bfloat162 *>(sF + off_feat(p, 2 * lvl, 1)) = __halves2bfloat162(m0, m1);
+            }
         }
         if (tid < TM) {
             const bool lv = LIVE_TC(tid);

@@ -128,7 +128,7 @@ class GsSdfStep:
     """
 
     def __init__(self, N, K, W, H, device, isect_cap, sdf_net_cfg, n_ray_samples=32768, sh_degree=3, origin=(0.0, 0.0, 0.0),
-                 map_size=14.0, bce_sigma=0.1, delta=None, eikonal_weight=0.1, gs_sdf_weight=1e-3, visible_thr=0.1):
+                 map_size=14.0, bce_sigma=0.1, delta=None, eikonal_weight=0.1, gs_sdf_weight=1e-3, visible_thr=0.1, mlp_mode=None):
         self.R = SplatRenderer(N, K, 1, W, H, device, isect_cap, sh_degree=sh_degree)
         self.dev, self.N, self.n_ray = device, N, n_ray_samples
         self.cfg = dict(sdf_net_cfg)
@@ -139,12 +139,17 @@ class GsSdfStep:
         probe = cabi.sdf_net(torch.zeros(1, **f32), torch.zeros(1, **f32), **self.cfg)
         self.n_table, self.n_mlp = cabi.sdf_table_params(probe), cabi.sdf_mlp_params(probe)
         self.table_half = torch.empty(self.n_table, dtype=torch.float16, device=device)
-        # flat gradient: [splat | table | mlp]
+        # decoder arithmetic: tensor cores (tcgen05, sdf_tc.cu) wherever the configuration allows it, else fp32 CUDA cores
+        tc_ok = self.cfg.get("hidden_dim", 64) == 64 and self.cfg.get("n_hidden", 3) <= 3
+        self.mlp_mode = (1 if tc_ok else 0) if mlp_mode is None else int(mlp_mode)
+        self.mlp_packed = torch.empty(cabi.sdf_mlp_packed_bytes(probe), dtype=torch.uint8, device=device) if self.mlp_mode == 1 else None
+        # flat gradient: [splat | (pad to an even offset: the table gradient takes 8-byte vector REDs) | table | mlp]
         n_splat = self.R.flat_grad.numel()
-        self.flat_grad = torch.zeros(n_splat + self.n_table + self.n_mlp, **f32)
+        t0 = (n_splat + 1) // 2 * 2
+        self.flat_grad = torch.zeros(t0 + self.n_table + self.n_mlp, **f32)
         self._rebind_splat_grads(n_splat)
-        self.table_grad = self.flat_grad[n_splat:n_splat + self.n_table]
-        self.mlp_grad = self.flat_grad[n_splat + self.n_table:]
+        self.table_grad = self.flat_grad[t0:t0 + self.n_table]
+        self.mlp_grad = self.flat_grad[t0 + self.n_table:]
         e = lambda *s: torch.empty(*s, **f32)
         self.ray_sdf, self.ray_y1, self.ray_vs, self.ray_vy = e(7 * n_ray_samples), e(7 * n_ray_samples), e(7 * n_ray_samples), e(7 * n_ray_samples)
         cap = self.R.cap
@@ -152,7 +157,7 @@ class GsSdfStep:
         self.v_samples = e(cap, 3)
         self.sdf_loss = torch.zeros(1, **f32)
 
-    KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 7  # + table cast + 2 x (sdf fwd, sdf loss, sdf bwd)
+    KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 8  # + table cast + decoder weight image + 2 x (sdf fwd, sdf loss, sdf bwd)
 
     def _rebind_splat_grads(self, n_splat):
         R, N, K = self.R, self.R.N, self.R.K
@@ -169,7 +174,10 @@ class GsSdfStep:
         R, n_ray, cap = self.R, self.n_ray, self.R.cap
         # fp32 master -> fp16 shadow once per step (the optimiser moved the master; the reference casts on EVERY forward)
         cabi.sdf_table_to_half(table_f32, self.table_half)
-        net = cabi.sdf_net(self.table_half, mlp, origin=self.origin, inv_size=self.inv_size, **self.cfg)
+        if self.mlp_mode == 1:  # bf16 hi/mid/lo weight image for the tensor-core decoder, also once per step
+            cabi.sdf_mlp_pack(cabi.sdf_net(self.table_half, mlp, **self.cfg), self.mlp_packed)
+        net = cabi.sdf_net(self.table_half, mlp, origin=self.origin, inv_size=self.inv_size, mlp_mode=self.mlp_mode,
+                           mlp_packed=self.mlp_packed, **self.cfg)
         self.flat_grad.zero_()
         self.sdf_loss.zero_()
         # [A] SDF stage on the ray samples

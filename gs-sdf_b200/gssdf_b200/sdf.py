@@ -45,7 +45,7 @@ class SdfNet(torch.nn.Module):
     """EncodingMap (hash grid, tcnn fp16 semantics) + LocalMap decoder (Linear/ReLU) evaluated by the fused kernels."""
 
     def __init__(self, device, n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=2.0,
-                 hidden_dim=64, geo_num_layer=3, origin=(0.0, 0.0, 0.0), map_size=0.0, bce_isigma=1.0, seed=1337):
+                 hidden_dim=64, geo_num_layer=3, origin=(0.0, 0.0, 0.0), map_size=0.0, bce_isigma=1.0, seed=1337, mlp_mode=None):
         super().__init__()
         self.cfg = dict(n_levels=n_levels, n_features=n_features, log2_hashmap_size=log2_hashmap_size, base_resolution=base_resolution,
                         per_level_scale=per_level_scale, hidden_dim=hidden_dim, n_hidden=geo_num_layer)
@@ -66,6 +66,10 @@ class SdfNet(torch.nn.Module):
         assert self.decoder_.numel() == n_mlp
         self._half = torch.empty(n_table, dtype=torch.float16, device=device)
         self._half_version = None
+        # decoder arithmetic: tcgen05 tensor cores where supported (hidden 64, <= 3 hidden->hidden layers), else fp32 CUDA cores
+        self.mlp_mode = (1 if hidden_dim == 64 and geo_num_layer <= 3 else 0) if mlp_mode is None else int(mlp_mode)
+        self._packed = torch.empty(cabi.sdf_mlp_packed_bytes(probe), dtype=torch.uint8, device=device) if self.mlp_mode == 1 else None
+        self._packed_version = None
 
     def get_out_dim(self):
         return self.cfg["n_levels"] * self.cfg["n_features"]
@@ -78,7 +82,11 @@ class SdfNet(torch.nn.Module):
     def _net(self, table, mlp):
         if self._half_version != self.params_._version:
             self.refresh_half()
-        return cabi.sdf_net(self._half, mlp.detach(), origin=self.origin, inv_size=self.inv_size, **self.cfg)
+        if self.mlp_mode == 1 and self._packed_version != self.decoder_._version:
+            cabi.sdf_mlp_pack(cabi.sdf_net(self._half, mlp.detach(), **self.cfg), self._packed)
+            self._packed_version = self.decoder_._version
+        return cabi.sdf_net(self._half, mlp.detach(), origin=self.origin, inv_size=self.inv_size, mlp_mode=self.mlp_mode,
+                            mlp_packed=self._packed, **self.cfg)
 
     def get_sdf(self, xyz):
         sdf, y1 = _SdfFunction.apply(xyz.contiguous(), self.params_, self.decoder_, self)

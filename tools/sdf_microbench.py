@@ -31,16 +31,20 @@ for mode in (0, 1):
     print("mode", mode, "L2 rel", np.linalg.norm(m - r_mg) / np.linalg.norm(r_mg))
     for name, sz in sizes:
         d = np.abs(m[o:o+sz] - r_mg[o:o+sz]); print(f"  {name}: max|ref| {np.abs(r_mg[o:o+sz]).max():.3e} max err {d.max():.3e} at {d.argmax()}"); o += sz
-    # timing
+    # timing on the two shapes of the training step (bench.py 1080p-1M): ray samples 32768 x 7 variants (no dL/dx) and splat
+    # samples 152864 x 7 variants (dL/dx through variant 0)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    xb = torch.rand(229376, 3, device=dev) * 0.96 + 0.02; vb = torch.randn(229376, device=dev)
-    vxb = torch.empty(229376, 3, device=dev)
-    for _ in range(3): cabi.sdf_bwd(net, xb, vb, vb, tg, mg, vxb)
-    s.record()
-    for _ in range(10): cabi.sdf_bwd(net, xb, vb, vb, tg, mg, vxb)
-    e.record(); torch.cuda.synchronize(); print("  bwd 229376 pts ms", s.elapsed_time(e) / 10)
-    sd = torch.empty(229376, device=dev)
-    for _ in range(3): cabi.sdf_fwd(net, xb, sd, sd.clone(), None)
-    s.record()
-    for _ in range(10): cabi.sdf_fwd(net, xb, sd, None, None)
-    e.record(); torch.cuda.synchronize(); print("  fwd 229376 pts ms", s.elapsed_time(e) / 10)
+    for name, nb, want_vx in (("ray 32768x7", 32768, False), ("splat 152864x7", 152864, True)):
+        xb = torch.rand(nb, 3, device=dev) * 0.96 + 0.02
+        vb = torch.randn(7 * nb, device=dev) * 1e-3
+        vxb = torch.empty(nb, 3, device=dev) if want_vx else None
+        sd, y1 = torch.empty(7 * nb, device=dev), torch.empty(7 * nb, device=dev)
+        for _ in range(3): cabi.sdf_bwd(net, xb, vb, vb, tg, mg, vxb, n_variants=7, delta=0.01)
+        s.record()
+        for _ in range(10): cabi.sdf_bwd(net, xb, vb, vb, tg, mg, vxb, n_variants=7, delta=0.01)
+        e.record(); torch.cuda.synchronize(); tb = s.elapsed_time(e) / 10
+        for _ in range(3): cabi.sdf_fwd(net, xb, sd, y1, None, n_variants=7, delta=0.01)
+        s.record()
+        for _ in range(10): cabi.sdf_fwd(net, xb, sd, y1, None, n_variants=7, delta=0.01)
+        e.record(); torch.cuda.synchronize(); tf = s.elapsed_time(e) / 10
+        print(f"  {name}: fwd {tf:.3f} ms  bwd {tb:.3f} ms")
