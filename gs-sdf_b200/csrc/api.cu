@@ -15,3 +15,4 @@ void set_error(const char *fmt, ...) {
 
 extern "C" const char *gssdf_last_error(void) { return gssdf::g_err; }
 extern "C" const char *gssdf_version(void) { return "gssdf_b200 0.1 sm_100a"; }
+extern "C" int32_t gssdf_abi_revision(void) { return GSSDF_ABI_REVISION; }

@@ -26,6 +26,7 @@
 //     touches its 8x4 pixels. Every culled (pixel, splat) pair is one the reference skips (alpha < 1/255),
 //     so results are unchanged; on the 1080p/1M workload 96% of the (warp, splat) iterations were such no-ops.
 #include "common.cuh"
+#include "conic.cuh"
 
 namespace gssdf {
 
@@ -35,7 +36,6 @@ constexpr float kNearN = 0.05f, kFarN = 100.f;  // hard-coded in the reference (
 constexpr float kAlphaThreshold = 1.f / 255.f;  // GSF/include/Common.h:53
 constexpr int kRecF4 = 4;                        // render record = 4 float4 = 64 B: M[9], opacity, rgb[3], normal[3]
 constexpr int kRecBytes = kRecF4 * 16;
-constexpr int kConicF4 = 2;                      // culling conic = 6 normalised coefficients (+2 pad) = 32 B per visible splat
 
 // ---------------------------------------------------------------------------------------------
 // record packing
@@ -57,40 +57,26 @@ pack_records_kernel(const gssdf_counts *counts, const float *__restrict__ ray_tr
     r[1] = make_float4(M[4], M[5], M[6], M[7]);
     r[2] = make_float4(M[8], opac, c[0], c[1]);
     r[3] = make_float4(c[2], n[0], n[1], n[2]);
-    // contributing region {alpha >= 1/255} = {Q(p) <= 0}, Q a conic in the pixel (see file header). Stored as six
-    // coefficients normalised so that every term is <= 1 in magnitude over the image (fp32-safe evaluation).
-    // all zeros = "cannot cull" (Q == 0 everywhere -> always hit); (0,..,0,1) = never contributes.
-    double q[6] = {0, 0, 0, 0, 0, 0};
-    const double lg = log(255.0 * (double)opac);
-    if (!(lg > 0.0)) {
-        if (opac == opac) q[5] = 1.0;  // o * exp(-sigma) < 1/255 everywhere
-    } else {
-        const double rho2 = 2.0 * lg * 1.002 + 1e-6;  // safety margin on the cut-off radius
-        const double u0 = M[0], u1 = M[1], u2 = M[2], v0 = M[3], v1 = M[4], v2 = M[5], w0 = M[6], w1 = M[7], w2 = M[8];
-        // zeta = px * A + py * B + Cc
-        const double A0 = v1 * w2 - v2 * w1, A1 = v2 * w0 - v0 * w2, A2 = v0 * w1 - v1 * w0;  // Mv x Mw
-        const double B0 = w1 * u2 - w2 * u1, B1 = w2 * u0 - w0 * u2, B2 = w0 * u1 - w1 * u0;  // Mw x Mu
-        const double C0 = u1 * v2 - u2 * v1, C1 = u2 * v0 - u0 * v2, C2 = u0 * v1 - u1 * v0;  // Mu x Mv
-        // Q(p) = q0 x^2 + 2 q1 x y + q2 y^2 + 2 q3 x + 2 q4 y + q5
-        q[0] = A0 * A0 + A1 * A1 - rho2 * A2 * A2; q[1] = A0 * B0 + A1 * B1 - rho2 * A2 * B2;
-        q[2] = B0 * B0 + B1 * B1 - rho2 * B2 * B2; q[3] = A0 * C0 + A1 * C1 - rho2 * A2 * C2;
-        q[4] = B0 * C0 + B1 * C1 - rho2 * B2 * C2; q[5] = C0 * C0 + C1 * C1 - rho2 * C2 * C2;
-        const double X = extent;
-        const double sc = fmax(fmax(fmax(fabs(q[0]), 2.0 * fabs(q[1])), fabs(q[2])) * X * X,
-                               fmax(fmax(2.0 * fabs(q[3]), 2.0 * fabs(q[4])) * X, fabs(q[5])));
-        if (sc > 0.0 && isfinite(sc)) {
-#pragma unroll
-            for (int e = 0; e < 6; ++e) q[e] /= sc;
-        } else {
-#pragma unroll
-            for (int e = 0; e < 6; ++e) q[e] = 0.0;
-        }
-    }
-    conic[kConicF4 * (int64_t)i] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
-    conic[kConicF4 * (int64_t)i + 1] = make_float4((float)q[4], (float)q[5], 0.f, 0.f);
+    float q[6];
+    uint32_t rect[2];
+    splat_conic(M, opac, extent, q, rect);
+    conic[kConicF4 * (int64_t)i] = make_float4(q[0], q[1], q[2], q[3]);
+    conic[kConicF4 * (int64_t)i + 1] = make_float4(q[4], q[5], __uint_as_float(rect[0]), __uint_as_float(rect[1]));
     if (zero_a) {
         for (int k = 0; k < zero_a_stride; ++k) zero_a[(int64_t)i * zero_a_stride + k] = 0.f;
     }
+}
+
+__global__ void __launch_bounds__(256)
+splat_conics_kernel(const gssdf_counts *counts, const float *__restrict__ ray_transforms, const float *__restrict__ opacities,
+                    float4 *__restrict__ conic, float extent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts->nnz) return;
+    float q[6];
+    uint32_t rect[2];
+    splat_conic(ray_transforms + 9 * (int64_t)i, opacities[i], extent, q, rect);  // identical to pack_records_kernel's
+    conic[kConicF4 * (int64_t)i] = make_float4(q[0], q[1], q[2], q[3]);
+    conic[kConicF4 * (int64_t)i + 1] = make_float4(q[4], q[5], __uint_as_float(rect[0]), __uint_as_float(rect[1]));
 }
 
 struct TileInfo {
@@ -125,62 +111,6 @@ struct __align__(16) Stage {
     int meta[kBatch];             // (index in the tile's sorted list << 8) | warp mask (bit w: the conic touches warp w's 8x4 block)
     float acc[kBatch];            // per-splat tile accumulator (visibility)
 };
-
-// Conic in tile-local pixel coordinates: Q(x,y) = a x^2 + 2 b x y + c y^2 + 2 d x + 2 e y + f
-struct Conic { float a, b, c, d, e, f; };
-
-__device__ __forceinline__ float conic_eval(const Conic &q, float x, float y) {
-    return (q.a * x + 2.f * (q.b * y + q.d)) * x + (q.c * y + 2.f * q.e) * y + q.f;
-}
-
-// minimum of Q over the rectangle [x0,x1] x [y0,y1] (any conic type): corners, edge critical points, interior
-// critical point. Exact up to fp32 rounding, which the caller's tolerance absorbs.
-__device__ __forceinline__ float conic_min_rect(const Conic &q, float x0, float x1, float y0, float y1) {
-    float m = fminf(fminf(conic_eval(q, x0, y0), conic_eval(q, x1, y0)), fminf(conic_eval(q, x0, y1), conic_eval(q, x1, y1)));
-    if (q.c > 0.f) {  // edges x = const: minimise over y
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const float xe = s ? x1 : x0;
-            const float ys = -(q.b * xe + q.e) / q.c;
-            if (ys > y0 && ys < y1) m = fminf(m, conic_eval(q, xe, ys));
-        }
-    }
-    if (q.a > 0.f) {  // edges y = const: minimise over x
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const float ye = s ? y1 : y0;
-            const float xs = -(q.b * ye + q.d) / q.a;
-            if (xs > x0 && xs < x1) m = fminf(m, conic_eval(q, xs, ye));
-        }
-    }
-    const float det = q.a * q.c - q.b * q.b;
-    if (q.a > 0.f && det > 0.f) {  // interior minimum (ellipse centre)
-        const float cx = -(q.c * q.d - q.b * q.e) / det, cy = -(q.a * q.e - q.b * q.d) / det;
-        if (cx > x0 && cx < x1 && cy > y0 && cy < y1) m = fminf(m, conic_eval(q, cx, cy));
-    }
-    return m;
-}
-
-// 8-bit warp mask of record t for the tile whose first pixel centre is (ox, oy) (global pixel coordinates)
-__device__ __forceinline__ unsigned cull_mask(const float4 g0, const float4 g1, float ox, float oy) {
-    // shift the conic to tile-local coordinates (x = ox + x')
-    Conic q;
-    q.a = g0.x; q.b = g0.y; q.c = g0.z;
-    q.d = g0.x * ox + g0.y * oy + g0.w;
-    q.e = g0.y * ox + g0.z * oy + g1.x;
-    q.f = (g0.x * ox + 2.f * (g0.y * oy + g0.w)) * ox + (g0.z * oy + 2.f * g1.x) * oy + g1.y;
-    // every term of the normalised form is <= 1 over the image: fp32 evaluation error < ~1e-6
-    const float tol = 4e-6f;
-    const float m = 0.05f;  // margin in pixels
-    if (!(conic_min_rect(q, -m, 15.f + m, -m, 15.f + m) <= tol)) return 0u;
-    unsigned mask = 0u;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        const float x0 = (w & 1) * 8.f, y0 = (w >> 1) * 4.f;
-        if (conic_min_rect(q, x0 - m, x0 + 7.f + m, y0 - m, y0 + 3.f + m) <= tol) mask |= 1u << w;
-    }
-    return mask;
-}
 
 // ---------------------------------------------------------------------------------------------
 // culling pass: one CTA per tile walks the tile's sorted list once, tests every splat's conic against the tile and its
@@ -726,6 +656,19 @@ static int check_raster_common(const char *who, int C, int W, int H, int tile_si
 }
 
 // pack the render records + culling conics, then build the culled per-tile lists
+extern "C" int gssdf_splat_conics(const gssdf_splat_conics_args *a, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "splat_conics: null args");
+    GSSDF_REQUIRE(a->cap >= 0 && a->image_width > 0 && a->image_height > 0, GSSDF_EINVAL, "splat_conics: bad sizes");
+    if (a->cap == 0) return GSSDF_OK;
+    GSSDF_REQUIRE(a->counts && a->ray_transforms && a->opacities && a->conics, GSSDF_EINVAL, "splat_conics: null pointer");
+    GSSDF_REQUIRE(((uintptr_t)a->conics & 15) == 0, GSSDF_EINVAL, "splat_conics: conics must be 16-byte aligned");
+    splat_conics_kernel<<<cdiv(a->cap, 256), 256, 0, (cudaStream_t)stream>>>(a->counts, a->ray_transforms, a->opacities,
+                                                                            reinterpret_cast<float4 *>(a->conics),
+                                                                            (float)max(a->image_width, a->image_height));
+    GSSDF_LAUNCH_OK("splat_conics_kernel");
+    return GSSDF_OK;
+}
+
 static int pack_and_cull(const char *who, const RasterWs &w, const gssdf_counts *counts, int C, int W, int H, int cap,
                          const float *ray_transforms, const float *colors, const float *opacities, const float *normals,
                          const int32_t *offsets, const int32_t *flatten_ids, float *zero_a, int zero_stride, cudaStream_t st) {

@@ -16,6 +16,7 @@
 //                     network); since the key is unique, ascending order IS the reference order
 //                     (sorted by depth bits, ties in emission = packed-index order).
 #include "common.cuh"
+#include "conic.cuh"
 
 namespace gssdf {
 
@@ -41,11 +42,24 @@ __device__ __forceinline__ bool tile_rect(const gssdf_tile_encode_args &a, const
     return true;
 }
 
+// culled mode: intersect the reference rect with the conservative tile rectangle of the splat's exact footprint (conic.cuh)
+__device__ __forceinline__ bool shrink_rect(const gssdf_tile_encode_args &a, int idx, uint32_t &x0, uint32_t &y0, uint32_t &x1, uint32_t &y1) {
+    if (!a.conics) return true;
+    const float4 g1 = __ldg(reinterpret_cast<const float4 *>(a.conics) + kConicF4 * (int64_t)idx + 1);
+    const uint32_t rx = __float_as_uint(g1.z), ry = __float_as_uint(g1.w);
+    x0 = max(x0, rx & 0xffffu); x1 = min(x1, rx >> 16);
+    y0 = max(y0, ry & 0xffffu); y1 = min(y1, ry >> 16);
+    return x0 < x1 && y0 < y1;
+}
+
 // Visit every tile of every splat's rect. Small rects are walked by their own thread; rects with
 // >= 32 tiles are walked cooperatively by the warp (a screen-filling splat touches ~8k tiles).
+// Culled mode (conic != NULL): the cooperative walk first tests 8x8-tile super-blocks against the splat's conic (same
+// min-over-rectangle routine, looser tolerance -> a superset of the per-tile test), and only descends into the ones it touches.
+// f(i, x, y) still applies the exact per-tile test, so the set of visited (splat, tile) pairs that pass is unchanged.
 template <typename F>
 __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, int idx,
-                                              F &&f) {
+                                              const float4 *__restrict__ conic, F &&f) {
     const uint32_t w = has ? x1 - x0 : 0, h = has ? y1 - y0 : 0;
     const uint32_t cnt = w * h;
     const bool big = cnt >= 32;
@@ -61,8 +75,33 @@ __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0
         const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
         const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bcnt = __shfl_sync(0xffffffffu, cnt, src);
         const int bidx = __shfl_sync(0xffffffffu, idx, src);
+        if (conic && bcnt >= 256) {
+            const uint32_t bh = bcnt / bw, sw = (bw + 7) >> 3, sh = (bh + 7) >> 3, nsb = sw * sh;
+            const float4 g0 = __ldg(conic + kConicF4 * (int64_t)bidx), g1 = __ldg(conic + kConicF4 * (int64_t)bidx + 1);
+            for (uint32_t s0 = 0; s0 < nsb; s0 += 32) {
+                const uint32_t sb = s0 + lane;
+                bool hit = false;
+                if (sb < nsb) {
+                    const uint32_t sx = (sb % sw) * 8, sy = (sb / sw) * 8;
+                    const uint32_t ex = min(sx + 8, bw), ey = min(sy + 8, bh);
+                    hit = rect_hit(g0, g1, (bx0 + sx) * 16.f + 0.5f, (by0 + sy) * 16.f + 0.5f, (ex - sx) * 16.f - 1.f, (ey - sy) * 16.f - 1.f, 1e-4f);
+                }
+                unsigned hm = __ballot_sync(0xffffffffu, hit);
+                while (hm) {
+                    const uint32_t sb2 = s0 + (__ffs(hm) - 1);
+                    hm &= hm - 1;
+                    const uint32_t sx = (sb2 % sw) * 8, sy = (sb2 / sw) * 8;
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const uint32_t x = sx + (lane & 7), y = sy + (lane >> 3) + 4 * t;
+                        if (x < bw && y < bh) f(bidx, bx0 + x, by0 + y);
+                    }
+                }
+            }
+        } else {
 #pragma unroll 4
-        for (uint32_t t = lane; t < bcnt; t += 32) f(bidx, bx0 + t % bw, by0 + t / bw);  // unrolled: 4 atomics in flight per lane
+            for (uint32_t t = lane; t < bcnt; t += 32) f(bidx, bx0 + t % bw, by0 + t / bw);  // unrolled: 4 atomics in flight per lane
+        }
     }
 }
 
@@ -72,11 +111,16 @@ tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__r
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = idx < nnz;
     uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    const bool has = in && tile_rect(a, g, idx, x0, y0, x1, y1);
-    if (in && a.tiles_per_gauss) a.tiles_per_gauss[idx] = has ? (int32_t)((y1 - y0) * (x1 - x0)) : 0;
-    for_each_tile(has, x0, y0, x1, y1, idx, [&](int i, uint32_t x, uint32_t y) {
+    bool has = in && tile_rect(a, g, idx, x0, y0, x1, y1);
+    has = has && shrink_rect(a, idx, x0, y0, x1, y1);
+    if (in && a.tiles_per_gauss && !a.conics) a.tiles_per_gauss[idx] = has ? (int32_t)((y1 - y0) * (x1 - x0)) : 0;
+    const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
+    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) {
+        if (conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f))
+            return;
         const int64_t cid = a.camera_ids ? a.camera_ids[i] : 0;
         atomicAdd(hist + cid * g.n_tiles + y * g.tw + x, 1);
+        if (conic && a.tiles_per_gauss) atomicAdd(a.tiles_per_gauss + i, 1);  // culled mode: count the survivors
     });
 }
 
@@ -138,9 +182,13 @@ tile_scatter_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *_
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = idx < nnz;
     uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    const bool has = in && tile_rect(a, g, idx, x0, y0, x1, y1);
+    bool has = in && tile_rect(a, g, idx, x0, y0, x1, y1);
+    has = has && shrink_rect(a, idx, x0, y0, x1, y1);
     const int64_t cap = a.isect_cap;
-    for_each_tile(has, x0, y0, x1, y1, idx, [&](int i, uint32_t x, uint32_t y) {
+    const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
+    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) {
+        if (conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f))
+            return;  // the same test, on the same inputs, as in tile_count_kernel
         const int64_t cid = a.camera_ids ? a.camera_ids[i] : 0;
         const int64_t bin = cid * g.n_tiles + y * g.tw + x;
         const int slot = atomicSub(hist + bin, 1) - 1;  // fills the bin back to front
@@ -257,7 +305,10 @@ extern "C" int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t
     ws += align_up((size_t)(bins + 1) * 4, 256);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws);
 
+    GSSDF_REQUIRE(!a->conics || (a->tile_size == 16 && ((uintptr_t)a->conics & 15) == 0), GSSDF_EINVAL,
+                  "tile_encode: footprint culling (conics) needs tile_size 16 and a 16-byte aligned conic array");
     GSSDF_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)bins * 4, st));
+    if (a->conics && a->tiles_per_gauss && a->cap > 0) GSSDF_CUDA_OK(cudaMemsetAsync(a->tiles_per_gauss, 0, (size_t)a->cap * 4, st));
     if (a->cap > 0) {
         GSSDF_REQUIRE(a->means2d && a->radii && a->depths && a->flatten_ids, GSSDF_EINVAL, "tile_encode: null input/output");
         tile_count_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist);

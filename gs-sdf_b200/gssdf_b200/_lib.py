@@ -49,7 +49,7 @@ def parse_header(path=HEADER):
         structs[name] = fields
         ctypes_structs[name] = type(name, (C.Structure,), {"_fields_": fields})
     funcs = {}
-    for m in re.finditer(r"^\s*(const char \*|int64_t|int|size_t)\s*(gssdf_\w+)\s*\(([^)]*)\)\s*;", src, flags=re.M):
+    for m in re.finditer(r"^\s*(const char \*|int64_t|int32_t|int|size_t)\s*(gssdf_\w+)\s*\(([^)]*)\)\s*;", src, flags=re.M):
         ret, name, args = m.group(1).strip(), m.group(2), m.group(3)
         funcs[name] = (ret, args)
     return structs, funcs, ctypes_structs
@@ -70,7 +70,11 @@ def lib():
         L = C.CDLL(SO_PATH)
         for name, (ret, _args) in FUNCS.items():
             fn = getattr(L, name)  # raises AttributeError if a declared symbol is not exported
-            fn.restype = {"int": C.c_int, "int64_t": C.c_int64, "size_t": C.c_size_t, "const char *": C.c_char_p}[ret]
+            fn.restype = {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "size_t": C.c_size_t, "const char *": C.c_char_p}[ret]
+        m = re.search(r"#define\s+GSSDF_ABI_REVISION\s+(\d+)", open(HEADER).read())
+        if m and L.gssdf_abi_revision() != int(m.group(1)):
+            raise RuntimeError(f"{SO_PATH} was built against ABI revision {L.gssdf_abi_revision()}, the header says {m.group(1)}: "
+                               "rebuild with `python gs-sdf_b200/build.py`")
         _lib = L
     return _lib
 

@@ -100,14 +100,22 @@ def view_colors_bwd(viewmats, means, sh, sh_degree, cap, counts, camera_ids, gau
 
 
 def tile_encode(Cn, W, H, tile_size, cap, counts, means2d, radii, depths, camera_ids, isect_cap, tiles_per_gauss,
-                isect_ids, flatten_ids, offsets, ws):
+                isect_ids, flatten_ids, offsets, ws, conics=None):
+    """conics=None: reference-identical lists. conics=[cap,8] (splat_conics): pairs whose exact footprint misses the tile are dropped
+    before the sort (fused step; renders unchanged)."""
     need = lib().gssdf_tile_encode_workspace_bytes(Cn, W, H, tile_size, isect_cap)
     w = ws.get(need)
     a = make_args("gssdf_tile_encode_args", C=Cn, image_width=W, image_height=H, tile_size=tile_size, cap=cap,
                   counts=counts, means2d=means2d, radii=radii, depths=depths, camera_ids=camera_ids, isect_cap=isect_cap,
                   tiles_per_gauss=tiles_per_gauss, isect_ids=isect_ids, flatten_ids=flatten_ids, offsets=offsets,
-                  workspace=w, workspace_bytes=w.numel())
+                  workspace=w, workspace_bytes=w.numel(), conics=conics)
     check(lib().gssdf_tile_encode(_lib.C.byref(a), _stream()))
+
+
+def splat_conics(cap, W, H, counts, ray_transforms, opacities, conics):
+    a = make_args("gssdf_splat_conics_args", cap=cap, image_width=W, image_height=H, counts=counts, ray_transforms=ray_transforms,
+                  opacities=opacities, conics=conics)
+    check(lib().gssdf_splat_conics(_lib.C.byref(a), _stream()))
 
 
 def raster2dgs_fwd(Cn, W, H, tile_size, channels, cap, counts, means2d, ray_transforms, colors, opacities, normals,

@@ -16,7 +16,7 @@ from . import cabi
 
 
 class SplatRenderer:
-    def __init__(self, N, K, C, W, H, device, isect_cap, tile_size=16, near=0.05, far=300.0, sh_degree=3):
+    def __init__(self, N, K, C, W, H, device, isect_cap, tile_size=16, near=0.05, far=300.0, sh_degree=3, presort_cull=True):
         self.N, self.K, self.C, self.W, self.H, self.tile = N, K, C, W, H, tile_size
         self.near, self.far, self.sh_degree = near, far, sh_degree
         self.dev = device
@@ -32,6 +32,8 @@ class SplatRenderer:
                       radii=e(cap, 2, **i32), means2d=e(cap, 2), depths=e(cap), ray_transforms=e(cap, 3, 3), normals=e(cap, 3),
                       samples=e(cap, 3), sample_weights=e(cap, 1), pt_opacities=e(cap), indptr=e(C + 1, **i32))
         self.colors = e(cap, 3)
+        self.presort_cull = bool(presort_cull) and tile_size == 16
+        self.conics = e(cap, 8) if self.presort_cull else None
         self.flatten_ids = e(self.isect_cap, **i32)
         self.offsets = e(C, self.th, self.tw, **i32)
         self.r = dict(render_colors=e(C, H, W, 3), render_depths=e(C, H, W, 1), render_alphas=e(C, H, W, 1),
@@ -68,8 +70,12 @@ class SplatRenderer:
                              self.counts, self.ws, opacities=opacities)
         cabi.view_colors_fwd(viewmats, means, sh, self.sh_degree, cap, self.counts, self.p["camera_ids"],
                              self.p["gaussian_ids"], self.p["radii"], self.colors)
+        conics = None
+        if self.presort_cull:  # exact footprint test BEFORE the sort: ~4x fewer keys to scatter / sort / cull
+            cabi.splat_conics(cap, W, H, self.counts, self.p["ray_transforms"], self.p["pt_opacities"], self.conics)
+            conics = self.conics
         cabi.tile_encode(C, W, H, self.tile, cap, self.counts, self.p["means2d"], self.p["radii"], self.p["depths"],
-                         self.p["camera_ids"], self.isect_cap, None, None, self.flatten_ids, self.offsets, self.ws)
+                         self.p["camera_ids"], self.isect_cap, None, None, self.flatten_ids, self.offsets, self.ws, conics=conics)
         cabi.raster2dgs_fwd(C, W, H, self.tile, 3, cap, self.counts, self.p["means2d"], self.p["ray_transforms"], self.colors,
                             self.p["pt_opacities"], self.p["normals"], None, self.offsets, self.flatten_ids, self.r, self.raster_ws,
                             prof=self.prof_fwd, isect_cap=self.isect_cap)
@@ -107,7 +113,7 @@ class SplatRenderer:
                              randns)
 
     # kernels launched by one step() (fwd: 3+1+6+2+1, bwd: 1+1+3+1+1 ; memsets not counted)
-    KERNELS_PER_STEP = 20
+    KERNELS_PER_STEP = 21
 
     def read_counts(self):
         c = self.counts.cpu().tolist()

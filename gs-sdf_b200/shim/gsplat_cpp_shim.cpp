@@ -25,6 +25,9 @@ using torch::autograd::tensor_list;
 inline gssdf_stream_t cur_stream() { return reinterpret_cast<gssdf_stream_t>(at::cuda::getCurrentCUDAStream().stream()); }
 
 inline void check(int rc) {
+    static const bool abi_ok = gssdf_abi_revision() == GSSDF_ABI_REVISION;  // argument structs grow between revisions
+    TORCH_CHECK(abi_ok, "gssdf_b200 shim was compiled against ABI revision ", GSSDF_ABI_REVISION, " but libgssdf_b200.so is revision ",
+                gssdf_abi_revision(), ": rebuild the shim");
     if (rc == GSSDF_OK) return;
     if (rc == GSSDF_EINVAL) throw std::invalid_argument(gssdf_last_error());
     TORCH_CHECK(false, "gssdf_b200 error ", rc, ": ", gssdf_last_error());

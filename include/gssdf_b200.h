@@ -48,6 +48,9 @@ enum {
 const char *gssdf_last_error(void);
 /* "gssdf_b200 <ver> sm_100a" */
 const char *gssdf_version(void);
+/* Argument structs grow between revisions: a binding compiled against this header must see the same number from the library. */
+#define GSSDF_ABI_REVISION 4
+int32_t gssdf_abi_revision(void);
 
 /* Device-side counters shared by the stages of one render. Zeroed by gssdf_project2dgs_fwd. */
 typedef struct gssdf_counts {
@@ -190,9 +193,26 @@ typedef struct gssdf_tile_encode_args {
     int32_t *offsets;            /* [C, tile_h, tile_w] */
     void *workspace;             /* >= gssdf_tile_encode_workspace_bytes(...) */
     size_t workspace_bytes;
+    const float *conics;         /* NULL: reference-identical lists (every tile of the splat's radius AABB).
+                                    [cap,8] from gssdf_splat_conics (tile_size must be 16): a (splat, tile) pair is dropped BEFORE the
+                                    sort when the splat's exact alpha >= 1/255 footprint misses the tile. tiles_per_gauss / offsets /
+                                    flatten_ids / n_isects then describe the culled lists: per tile a subset of the reference's list in
+                                    the same order; every render output is unchanged (the dropped pairs cannot pass the kernel's
+                                    alpha test anywhere in the tile). Used by the fused training step. */
 } gssdf_tile_encode_args;
 size_t gssdf_tile_encode_workspace_bytes(int32_t C, int32_t image_width, int32_t image_height,
                                          int32_t tile_size, int64_t isect_cap);
+/* Per-splat footprint conic for exact culling (no reference counterpart; derived from the alpha test of
+   RasterizeToPixels2DGSFwd.cu): conics[i] = 6 normalised coefficients of Q(p) = zeta_x^2 + zeta_y^2 - 2 ln(255 o) zeta_z^2 (+ 2 pad). */
+typedef struct gssdf_splat_conics_args {
+    int32_t cap;
+    int32_t image_width, image_height;
+    const gssdf_counts *counts;  /* nnz */
+    const float *ray_transforms; /* [cap,3,3] */
+    const float *opacities;      /* [cap] (per packed row) */
+    float *conics;               /* [cap,8] */
+} gssdf_splat_conics_args;
+int gssdf_splat_conics(const gssdf_splat_conics_args *a, gssdf_stream_t stream);
 int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

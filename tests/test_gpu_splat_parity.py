@@ -242,7 +242,7 @@ def test_async_renderer_matches_mirror_api(oracle):
     sc, V, K = small_scene(N, W, H, deg)
     rn = S.randns(N)
     tsc = {k: _t(v, dev) for k, v in sc.items()}
-    R = render.SplatRenderer(N, (deg + 1) ** 2, 1, W, H, dev, isect_cap=200000, sh_degree=deg)
+    R = render.SplatRenderer(N, (deg + 1) ** 2, 1, W, H, dev, isect_cap=200000, sh_degree=deg, presort_cull=False)
     gt = torch.rand(1, H, W, 4, device=dev)
     loss = R.step(tsc, _t(V, dev), _t(K, dev), gt, _t(rn, dev))
     cnt = R.read_counts()
@@ -259,6 +259,45 @@ def test_async_renderer_matches_mirror_api(oracle):
     for name, g in [("means", R.v_means), ("quats", R.v_quats), ("scales", R.v_scales), ("opacities", R.v_opac), ("sh", R.v_sh)]:
         ref = leaves[name].grad
         torch.testing.assert_close(g, ref, rtol=2e-3, atol=2e-5 * float(ref.abs().max()), msg=lambda m: f"{name}: {m}")
+
+
+@pytest.mark.parametrize("N,W,H,scale", [(4000, 160, 96, 6.0), (1500, 320, 200, 25.0)])
+def test_presort_footprint_cull_is_exact(oracle, N, W, H, scale):
+    """Fused-step option: (splat, tile) pairs whose exact alpha >= 1/255 footprint misses the tile are dropped BEFORE the sort.
+    Per tile the culled list must be a sub-sequence of the reference list (same order), every image must be BIT-identical to the
+    un-culled run, and the gradients equal up to atomic summation order."""
+    from gssdf_b200 import render
+    dev = _dev()
+    deg = 3
+    sc, V, K = small_scene(N, W, H, deg, scale_mult=scale)
+    rn = S.randns(N)
+    tsc = {k: _t(v, dev) for k, v in sc.items()}
+    gt = torch.rand(1, H, W, 4, device=dev)
+    runs = []
+    for cull in (False, True):
+        R = render.SplatRenderer(N, (deg + 1) ** 2, 1, W, H, dev, isect_cap=400000, sh_degree=deg, presort_cull=cull)
+        loss = R.step(tsc, _t(V, dev), _t(K, dev), gt, _t(rn, dev))
+        torch.cuda.synchronize()
+        cnt = R.read_counts()
+        assert cnt["isect_overflow"] == 0
+        runs.append(dict(R=R, loss=float(loss[0]), cnt=cnt, off=_np(R.offsets).ravel(), flat=_np(R.flatten_ids)[:cnt["n_isects"]],
+                         grad=R.flat_grad.clone()))
+    a, b = runs
+    assert b["cnt"]["n_isects"] < a["cnt"]["n_isects"] and b["cnt"]["nnz"] == a["cnt"]["nnz"]
+    for k in ("render_colors", "render_depths", "render_alphas", "render_normals", "render_median"):
+        assert torch.equal(a["R"].r[k], b["R"].r[k]), k
+    # per-splat visibility is a float atomic sum over tiles: same terms, different order
+    torch.testing.assert_close(a["R"].r["visibilities"], b["R"].r["visibilities"], rtol=1e-5, atol=1e-6)
+    assert torch.equal(a["R"].out_colors, b["R"].out_colors)
+    assert a["loss"] == b["loss"]
+    torch.testing.assert_close(b["grad"], a["grad"], rtol=1e-4, atol=1e-6 * float(a["grad"].abs().max()))
+    n_t = len(a["off"])
+    for t in range(n_t):  # sub-sequence check
+        ra = a["flat"][a["off"][t]:(a["off"][t + 1] if t + 1 < n_t else a["cnt"]["n_isects"])]
+        rb = b["flat"][b["off"][t]:(b["off"][t + 1] if t + 1 < n_t else b["cnt"]["n_isects"])]
+        pos = {int(g): i for i, g in enumerate(ra)}
+        idx = [pos[int(g)] for g in rb]  # KeyError -> not a subset
+        assert idx == sorted(idx), f"tile {t}: order changed"
 
 
 def test_error_conventions():
