@@ -53,34 +53,74 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / clock-event (throttle) reasons DURING the timed region, sampled in-process through NVML every 5 ms
+    (nvidia-smi queries the same counters but takes ~100 ms per call); falls back to nvidia-smi when pynvml is unusable."""
 
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, index):
+    def __init__(self, index, pci_bus_id=None):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.sm, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode()) if pci_bus_id else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _sample_nvml(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = int(get(self.h))
+        self.reasons |= {n for n, b in self.BITS.items() if bits & b}
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            r = [x.strip() for x in out.split(",")]
+            self.sm.append(float(r[0]))
+            self.max_mhz = max(self.max_mhz or 0.0, float(r[1]))
+            self.reasons |= {n for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6])
+                             if v.lower().startswith("active")}
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self._sample_nvml() if self.h is not None else self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.005 if self.h is not None else 0.2)
 
     def summary(self):
         self._stop_evt.set()
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": "nvml" if self.h is not None else "nvidia-smi"}
+
+
+def pci_bus_id():
+    """NVML-style bus id of the current CUDA device (robust to CUDA_VISIBLE_DEVICES remapping)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(torch.cuda.current_device())
+        return f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+    except Exception:
+        return None
+
+
+def ncu_traffic(kernel):
+    """Measured DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r1_traffic.json), or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        return d.get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def cpu_oracle_step(O, S, sc, V, K, W, H, deg, rn, gt):
@@ -184,6 +224,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p-1M", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--distinct-cameras", action="store_true", help="N>1: rank r renders its own camera poses (adds load imbalance)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,7 +267,7 @@ def main():
     n_ray = 32768  # config/base.yaml:23 batch_pt_num
     G = render.GsSdfStep(N, K_sh, W, H, dev, isect_cap, sdf_cfg, n_ray_samples=n_ray, sh_degree=deg, origin=(0.0, 0.0, 0.0), map_size=14.0)
     R = G.R
-    gen = torch.Generator(dev).manual_seed(5)
+    gen = torch.Generator(dev).manual_seed(5)  # replicated parameters: same on every rank
     table = (torch.rand(G.n_table, device=dev, generator=gen) * 2 - 1) * 1e-4  # tcnn grid init U(+-1e-4) (grid.h:1059-1062)
     mlp_chunks, dims = [], [32] + [sdf_cfg["hidden_dim"]] * (1 + sdf_cfg["n_hidden"]) + [2]
     for k_, o_ in zip(dims[:-1], dims[1:]):  # torch::nn::Linear default init
@@ -235,10 +276,15 @@ def main():
     mlp = torch.cat(mlp_chunks)
     # ray samples: points within +-0.3 m of the box walls, ground-truth SDF = distance to the nearest wall (inside positive)
     box = torch.tensor(S.BOX, device=dev, dtype=torch.float32)
-    ray_xyz = (torch.rand(n_ray, 3, device=dev, generator=gen) * 2 - 1) * (box + 0.3)
+    gen_r = torch.Generator(dev).manual_seed(50 + rank)  # each rank draws its own share of the ray batch
+    ray_xyz = (torch.rand(n_ray, 3, device=dev, generator=gen_r) * 2 - 1) * (box + 0.3)
     ray_gt = (box - ray_xyz.abs()).min(dim=1).values.clamp(-0.3, 0.3).contiguous()
     n_cams = 8
-    cams = [S.camera(rank * n_cams + i, W, H) for i in range(n_cams)]  # rank r renders its own images
+    # weak scaling = identical work per GPU: every rank renders camera[step % 8] of the SAME pose set (rank-specific stochastic
+    # splat samples and SDF ray samples); --distinct-cameras gives rank r its own poses, which adds load imbalance between ranks
+    cam0 = rank * n_cams if args.distinct_cameras else 0
+    cams = [S.camera(cam0 + i, W, H) for i in range(n_cams)]
+    torch.manual_seed(1234 + rank)  # randns stream
     # ground truth: the same scene rendered with perturbed colours, produced once on the device
     sc_gt = dict(sc)
     sc_gt["sh"] = sc["sh"] + 0.1 * torch.randn(sc["sh"].shape, device=dev, generator=torch.Generator(dev).manual_seed(3))
@@ -254,12 +300,25 @@ def main():
     h_V, h_K, h_gt = torch.empty(1, 4, 4, device=dev), torch.empty(1, 3, 3, device=dev), torch.empty(1, H, W, 4, device=dev)
     loss_host = torch.empty(1).pin_memory()
 
+    n_splat_grad = R.flat_grad.numel()
+    pending = []
+
+    def reduce_sdf_grads(g):  # hash-table + decoder gradients are final after [C]: reduce them under the render backward
+        pending.append(dist.all_reduce(g, async_op=True))
+
+    def reduce_rest():
+        dist.all_reduce(G.flat_grad[:n_splat_grad])  # splat gradients; the optimiser scales by 1/world
+        while pending:
+            pending.pop().wait()
+
+    hook = reduce_sdf_grads if world > 1 else None
+
     def step_resident(i):
         V, Kc = dev_cams[i % n_cams]
         randn_buf.normal_()  # the reference draws randns on the device every render (Projection.cpp:728)
-        loss, _sdf_loss = G.step(sc, table, mlp, V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf)
+        loss, _sdf_loss = G.step(sc, table, mlp, V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook)
         if world > 1:
-            dist.all_reduce(G.flat_grad)  # splat + hash-table + decoder gradients; the optimiser scales by 1/world
+            reduce_rest()
         return loss
 
     def step_e2e(i):
@@ -268,9 +327,9 @@ def main():
         h_K.copy_(hk, non_blocking=True)
         h_gt.copy_(host_gts[i % n_cams], non_blocking=True)
         randn_buf.normal_()
-        loss, _sdf_loss = G.step(sc, table, mlp, h_V, h_K, h_gt, ray_xyz, ray_gt, randn_buf)
+        loss, _sdf_loss = G.step(sc, table, mlp, h_V, h_K, h_gt, ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook)
         if world > 1:
-            dist.all_reduce(G.flat_grad)
+            reduce_rest()
         loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the loss every step (neural_mapping.cpp:505-514)
         return float(loss_host[0])
@@ -307,7 +366,7 @@ def main():
     for e0, e1 in prof_f + prof_b:
         e0.record(); e1.record()  # creates the cudaEvent_t handles
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, pci_bus_id()) if rank == 0 else None
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
@@ -340,9 +399,12 @@ def main():
 
     if rank == 0:
         pk, pk_kind = peaks()
-        nnz, I, P = cnt["nnz"], cnt["n_isects"], W * H
+        # SURVEY 8d quotes the algorithmic bytes per REFERENCE intersection (every tile of a splat's radius AABB): I_ref. The fused
+        # step drops the pairs whose exact footprint misses the tile before the sort, so the kernels only walk I_kept of them.
+        nnz, I_kept, I, P = cnt["nnz"], cnt["n_isects"], max(cnt["n_isects_aabb"], cnt["n_isects"]), W * H
         alg_bwd = 148 * I + 64 * P + 8 * nnz   # raster_bwd = 76 I + 64 P + 72 I + 8 nnz
         alg_fwd = 76 * I + 56 * P + 4 * nnz
+        alg_bwd_kept = 148 * I_kept + 64 * P + 8 * nnz
         t_bwd = float(np.mean(bwd_ms)) * 1e-3
         t_fwd = float(np.mean(fwd_ms)) * 1e-3
         achieved = alg_bwd / t_bwd / 1e9
@@ -353,8 +415,12 @@ def main():
                         "ms_per_step": ms_e2e},
                 "gpu_launches": args.steps * render.GsSdfStep.KERNELS_PER_STEP,
                 "roofline": {"kernel": "raster2dgs_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                             "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
+                             "frac": achieved / pk["hbm_gbs"], "traffic": ncu_traffic("raster2dgs_bwd_kernel"), "peak_source": pk_kind,
                              "algorithmic_bytes": alg_bwd, "kernel_ms": t_bwd * 1e3,
+                             "units": {"I_reference": I, "I_after_exact_culling": I_kept, "P": P, "nnz": nnz},
+                             "achieved_on_kept_intersections": alg_bwd_kept / t_bwd / 1e9,
+                             "note": "algorithmic bytes per SURVEY 8d are counted on the reference's intersections; after exact "
+                                     "culling the kernel is issue/latency-bound, not HBM-bound (see profiles/)",
                              "raster_fwd": {"achieved": alg_fwd / t_fwd / 1e9, "frac": alg_fwd / t_fwd / 1e9 / pk["hbm_gbs"],
                                             "kernel_ms": t_fwd * 1e3, "algorithmic_bytes": alg_fwd}},
                 "counts": cnt}

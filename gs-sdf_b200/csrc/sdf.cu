@@ -20,6 +20,7 @@
 // kernels (mlp_mode 1) are in sdf_tc.cu.
 #include <cuda_bf16.h>
 #include "sdf_grid.cuh"
+#include "sdf_loss.cuh"
 
 namespace gssdf {
 
@@ -408,55 +409,18 @@ __global__ void __launch_bounds__(256) sdf_loss_kernel(const gssdf_sdf_loss_args
     const int64_t nl = a.n_live ? min((int64_t)*a.n_live, n) : n;  // live rows; the means are over them
     float part = 0.f;
     if (i < nl) {
-        const float s = a.sdf[i];
-        float v_s = 0.f, v_y = 0.f;
-        if (a.gt_sdf) {
-            const float y = a.y1 ? a.y1[i] : 0.f;
-            const float by = 100.f * y;
-            const float sp = by > 20.f ? y : log1pf(expf(by)) * 0.01f;  // torch softplus(beta=100, threshold=20)
-            const float raw = 1.f + sp * a.bce_isigma;
-            const bool capped = raw > 500.f;
-            const float isg = capped ? 500.f : raw;
-            const float z = -s * isg;
-            const float gt = a.gt_sdf[i];
-            const float tz = -gt * isg;
-            const float tsig = 1.f / (1.f + expf(-tz));
-            const bool tcl = tsig < 1e-7f || tsig > 1.f - 1e-7f;
-            const float t = fminf(fmaxf(tsig, 1e-7f), 1.f - 1e-7f);
-            const float bce = fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z)));
-            const float w = a.bce_weight / (float)nl;
-            part += w * bce;
-            const float dz = (1.f / (1.f + expf(-z)) - t) * w;  // d/dz
-            const float dt = -z * w;                             // d/dt (the reference's target is not detached)
-            v_s += dz * -isg;
-            float d_isg = dz * -s + (tcl ? 0.f : dt * tsig * (1.f - tsig) * -gt);
-            if (!capped) v_y += d_isg * a.bce_isigma * (by > 20.f ? 1.f : 1.f / (1.f + expf(-by)));
+        SdfLossCfg cfg{a.bce_isigma, a.bce_weight, a.eikonal_weight, a.gs_sdf_weight, a.delta, a.visible_thr};
+        float s[7], v_s[7], v_y = 0.f;
+        const int V = a.n_variants == 7 ? 7 : 1;
+        for (int v = 0; v < V; ++v) s[v] = a.sdf[v * n + i];
+        part = sdf_point_loss(cfg, (float)nl, V, s, a.y1 ? a.y1[i] : 0.f, a.gt_sdf != nullptr, a.gt_sdf ? a.gt_sdf[i] : 0.f,
+                              a.weights != nullptr, a.weights ? a.weights[i] : 0.f, a.visibilities != nullptr,
+                              a.visibilities ? a.visibilities[i] : 0.f, v_s, v_y);
+        for (int v = 0; v < V; ++v) a.v_sdf[v * n + i] = v_s[v];
+        if (a.v_y1) {
+            a.v_y1[i] = v_y;
+            for (int v = 1; v < V; ++v) a.v_y1[v * n + i] = 0.f;
         }
-        if (a.weights) {
-            float w = a.weights[i] * a.gs_sdf_weight;
-            if (a.visibilities) {
-                const float vis = a.visibilities[i];
-                w = vis > a.visible_thr ? w * vis : 0.f;
-            }
-            part += 0.5f * w * s * s;
-            v_s += w * s;
-        }
-        if (a.n_variants == 7) {
-            const float inv2d = 0.5f / a.delta;
-            const float gx = (a.sdf[n + i] - a.sdf[2 * n + i]) * inv2d, gy = (a.sdf[3 * n + i] - a.sdf[4 * n + i]) * inv2d;
-            const float gz = (a.sdf[5 * n + i] - a.sdf[6 * n + i]) * inv2d;
-            const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
-            const float w = a.eikonal_weight / (float)nl;
-            part += w * (nrm - 1.f) * (nrm - 1.f);
-            const float c = nrm > 0.f ? 2.f * (nrm - 1.f) / nrm * w * inv2d : 0.f;
-            a.v_sdf[n + i] = c * gx; a.v_sdf[2 * n + i] = -c * gx;
-            a.v_sdf[3 * n + i] = c * gy; a.v_sdf[4 * n + i] = -c * gy;
-            a.v_sdf[5 * n + i] = c * gz; a.v_sdf[6 * n + i] = -c * gz;
-            if (a.v_y1)
-                for (int v = 1; v < 7; ++v) a.v_y1[v * n + i] = 0.f;
-        }
-        a.v_sdf[i] = v_s;
-        if (a.v_y1) a.v_y1[i] = v_y;
     }
     part = warp_sum(part);
     __shared__ float s_part[8];

@@ -23,6 +23,7 @@
 // Weights are pre-split once per optimiser step (gssdf_sdf_mlp_pack) into that layout (G = 3072: hi | mid | lo) and fetched per
 // layer with one 24 KiB cp.async.bulk (TMA) issued by the MMA thread; completion on an mbarrier.
 #include "sdf_grid.cuh"
+#include "sdf_loss.cuh"
 
 namespace gssdf {
 
@@ -346,8 +347,19 @@ sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
 // ---------------------------------------------------------------------------------------------
 constexpr size_t kBwdTcSmem = 16 * kGA0 + 3 * 16 * kGA + 16 * kGA + 16 * kGL + kWImg + sizeof(float) * (5 * 64 + 132 + 256 + 384 + 4 * 192) + 1024;
 
+// FUSED = false: gssdf_sdf_bwd (cotangents v_sdf / v_y1 come from memory; evaluation index = variant * n + point).
+// FUSED = true : gssdf_sdf_train (forward -> losses -> backward in one pass, nothing but the gradients leaves the SM). A tile
+//                holds PT = 128 / V whole points with their V variants in consecutive rows (row = j * V + v; 18 points x 7 variants
+//                + 2 idle rows), so the per-point losses (BCE, 6-offset eikonal, GS<->SDF coupling) see all of a point's evaluations.
+struct TcLossArgs {
+    const float *gt_sdf, *weights, *visibilities;
+    SdfLossCfg cfg;
+    float *loss_out;
+};
+
+template <bool FUSED>
 __global__ void __launch_bounds__(kBwdTcThreads)
-sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles) {
+sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeom g, int64_t n_tiles) {
     constexpr int TM = 128, HID = 64, NT = kBwdTcThreads;
     extern __shared__ __align__(1024) unsigned char s_tc[];
     unsigned char *sF = s_tc;                    // 16 KB a_0: encoded features hi/mid (off_feat); rows 64-127 of its stacked view alias
@@ -371,6 +383,8 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles)
     const int64_t n_live = a.n_live ? min((int64_t)*a.n_live, a.n) : a.n;
     const __half2 *table = reinterpret_cast<const __half2 *>(a.net.table_half);
     const unsigned char *wimg = reinterpret_cast<const unsigned char *>(a.net.mlp_packed);
+    const int V = max(a.n_variants, 1), PT = FUSED ? TM / V : TM;
+    float loss_acc = 0.f;
 
     if (warp == 0) {  // TMEM: D (64 columns) + one 64-column weight-gradient accumulator per hidden layer -> 512-column allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(512));
@@ -400,10 +414,22 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles)
     float dwo0 = 0.f, dwo1 = 0.f, dbo = 0.f;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
-        const int64_t base = tile * TM;
+        const int64_t base = FUSED ? tile * PT : tile * TM;  // first point (FUSED) / first evaluation index of the tile
         const int tm = (int)min((int64_t)TM, n_eval - base);
-        if (base % a.n >= n_live && base % a.n + TM <= a.n) continue;  // CTA-uniform
-#define LIVE_TC(p_) ((p_) < tm && (base + (p_)) % a.n < n_live)
+        if (FUSED ? base >= n_live : (base % a.n >= n_live && base % a.n + TM <= a.n)) continue;  // CTA-uniform
+        // row -> (evaluation index gi, live, is the base variant)
+        auto row_gi = [&](int p) -> int64_t {
+            if (!FUSED) return min(base + p, n_eval - 1);
+            const int j = p / V, v = p - j * V;
+            return (int64_t)v * a.n + min(base + j, a.n - 1);
+        };
+        auto row_live = [&](int p) -> bool {
+            if (!FUSED) return p < tm && (base + p) % a.n < n_live;
+            const int j = p / V;
+            return j < PT && base + j < n_live;
+        };
+        auto row_is_base = [&](int p) -> bool { return FUSED ? (p % V) == 0 : base + p < a.n; };
+#define LIVE_TC(p_) row_live(p_)
         __syncthreads();  // everything of the previous tile (sL/sW as dL/dfeat, s_dx, s_seed) has been consumed
         if (tid == 0) {
             fence_proxy_async();
@@ -417,7 +443,7 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles)
             for (int i = 0; i < 4; ++i) {
                 const int task = i * NT + tid, p = task % TM, lvl = task / TM;
                 float x[3];
-                load_x(a.net, a.x, min(base + p, n_eval - 1), a.n, a.delta, x);
+                load_x(a.net, a.x, row_gi(p), a.n, a.delta, x);
                 f[i] = encode_level(table, g, lvl, x);
             }
 #pragma unroll
@@ -431,7 +457,7 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles)
                 *reinterpret_cast<__nv_bfloat162 *>(sF + off_feat(p, 2 * lvl, 1)) = __halves2bfloat162(m0, m1);
             }
         }
-        if (tid < TM) {
+        if (!FUSED && tid < TM) {
             const bool lv = LIVE_TC(tid);
             s_seed[2 * tid] = lv ? __ldg(a.v_sdf + base + tid) : 0.f;
             s_seed[2 * tid + 1] = (lv && a.v_y1) ? __ldg(a.v_y1 + base + tid) : 0.f;
@@ -463,9 +489,43 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles)
             unsigned char *dst = (l < nh - 1) ? sAct + l * 16 * kGA : sG;
             store8(dst, l < nh - 1 ? sL : nullptr, row, col0, act);
             store8(dst, l < nh - 1 ? sL : nullptr, row, col0 + 8, act + 8);
+            if (FUSED && l == nh - 1) {  // output layer (64 -> 2): this thread's 16-column share of both dot products
+                float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    p0 = fmaf(act[j], s_wout[col0 + j], p0);
+                    p1 = fmaf(act[j], s_wout[HID + col0 + j], p1);
+                }
+                float *s_part = s_dx;  // [4 column quarters][128][2] over s_dx + s_col (both idle here)
+                s_part[(cq * TM + row) * 2] = p0;
+                s_part[(cq * TM + row) * 2 + 1] = p1;
+            }
             tc_fence_before();
         }
         if (!ok) break;
+        if (FUSED) {  // ---- 2b. network outputs -> per-point losses -> cotangent seeds
+            float *s_part = s_dx, *s_out = reinterpret_cast<float *>(sL);  // sL is idle after the last forward layer
+            __syncthreads();
+            if (tid < TM) {
+                s_out[2 * tid] = s_part[tid * 2] + s_part[(TM + tid) * 2] + s_part[(2 * TM + tid) * 2] + s_part[(3 * TM + tid) * 2] + s_wout[2 * HID];
+                s_out[2 * tid + 1] = s_part[tid * 2 + 1] + s_part[(TM + tid) * 2 + 1] + s_part[(2 * TM + tid) * 2 + 1] +
+                                     s_part[(3 * TM + tid) * 2 + 1] + s_wout[2 * HID + 1];
+                s_seed[2 * tid] = 0.f;
+                s_seed[2 * tid + 1] = 0.f;
+            }
+            __syncthreads();
+            if (tid < PT && base + tid < n_live) {
+                const int64_t i = base + tid;
+                float sv[7], v_s[7], v_y;
+                for (int v = 0; v < V; ++v) sv[v] = s_out[2 * (tid * V + v)];
+                loss_acc += sdf_point_loss(lo.cfg, (float)n_live, V, sv, s_out[2 * tid * V + 1], lo.gt_sdf != nullptr,
+                                           lo.gt_sdf ? __ldg(lo.gt_sdf + i) : 0.f, lo.weights != nullptr, lo.weights ? __ldg(lo.weights + i) : 0.f,
+                                           lo.visibilities != nullptr, lo.visibilities ? __ldg(lo.visibilities + i) : 0.f, v_s, v_y);
+                for (int v = 0; v < V; ++v) s_seed[2 * (tid * V + v)] = v_s[v];
+                s_seed[2 * tid * V + 1] = v_y;
+            }
+            __syncthreads();
+        }
         // ---- 3. output layer backward (CUDA cores, in place on sG): every thread touches only its own (row, 16 columns)
         {
             float an[16], gl[16];
@@ -579,8 +639,8 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles)
                 const int p = task % TM, lvl = task / TM;
                 if (LIVE_TC(p)) {
                     float x[3], dx[3] = {0.f, 0.f, 0.f};
-                    load_x(a.net, a.x, base + p, a.n, a.delta, x);
-                    const bool want_dx = a.v_x != nullptr && base + p < a.n;
+                    load_x(a.net, a.x, row_gi(p), a.n, a.delta, x);
+                    const bool want_dx = a.v_x != nullptr && row_is_base(p);
                     encode_level_bwd(table, a.table_grad, g, lvl, x, gf[p * 33 + 2 * lvl], gf[p * 33 + 2 * lvl + 1], want_dx, dx);
                     if (want_dx) {
                         atomicAdd(&s_dx[p * 3 + 0], dx[0]);
@@ -591,9 +651,18 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles)
             }
         }
         __syncthreads();
-        if (a.v_x)
-            for (int e = tid; e < tm * 3; e += NT)
-                if (base + e / 3 < n_live) a.v_x[base * 3 + e] = s_dx[e] * (a.net.inv_size != 0.f ? a.net.inv_size : 1.f);
+        if (a.v_x) {
+            const float sc = a.net.inv_size != 0.f ? a.net.inv_size : 1.f;
+            if (FUSED) {
+                for (int e = tid; e < PT * 3; e += NT) {
+                    const int j = e / 3, d = e - 3 * j;
+                    if (base + j < n_live) a.v_x[(base + j) * 3 + d] = s_dx[(j * V) * 3 + d] * sc;
+                }
+            } else {
+                for (int e = tid; e < tm * 3; e += NT)
+                    if (base + e / 3 < n_live) a.v_x[base * 3 + e] = s_dx[e] * sc;
+            }
+        }
         first_tile = false;
 #undef LIVE_TC
     }
@@ -622,6 +691,10 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const GridGeom g, int64_t n_tiles)
         if (tid < HID) atomicAdd(G + tid, dwo0);
         else if (tid < 2 * HID) atomicAdd(G + tid, dwo1);
         else if (tid < 2 * HID + 2) atomicAdd(G + tid, dbo);
+    }
+    if (FUSED && lo.loss_out) {
+        loss_acc = warp_sum(loss_acc);
+        if (lane == 0 && loss_acc != 0.f) atomicAdd(lo.loss_out, loss_acc);
     }
     __syncthreads();
     tc_fence_before();
@@ -677,13 +750,44 @@ extern "C" int gssdf_sdf_fwd_tc_launch(const gssdf_sdf_fwd_args *a, const gssdf:
 extern "C" int gssdf_sdf_bwd_tc_launch(const gssdf_sdf_bwd_args *a, const gssdf::GridGeom *g, gssdf_stream_t stream) {
     int rc = check_tc("sdf_bwd", a->net);
     if (rc) return rc;
-    GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdTcSmem));
+    GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdTcSmem));
     const int64_t n_tiles = (a->n * (a->n_variants > 1 ? a->n_variants : 1) + 127) / 128;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sms);
-    sdf_bwd_tc_kernel<<<grid, kBwdTcThreads, kBwdTcSmem, (cudaStream_t)stream>>>(*a, *g, n_tiles);
+    sdf_bwd_tc_kernel<false><<<grid, kBwdTcThreads, kBwdTcSmem, (cudaStream_t)stream>>>(*a, TcLossArgs{}, *g, n_tiles);
     GSSDF_LAUNCH_OK("sdf_bwd_tc_kernel");
+    return GSSDF_OK;
+}
+
+extern "C" int gssdf_sdf_train(const gssdf_sdf_train_args *t, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(t != nullptr, GSSDF_EINVAL, "sdf_train: null args");
+    GSSDF_REQUIRE(t->net.mlp_mode == 1, GSSDF_EUNSUPPORTED, "sdf_train: the fused forward+loss+backward kernel exists for mlp_mode 1 only "
+                  "(use gssdf_sdf_fwd + gssdf_sdf_loss + gssdf_sdf_bwd otherwise)");
+    GSSDF_REQUIRE(t->net.n_levels == 16 && t->net.n_features_per_level == 2, GSSDF_EUNSUPPORTED, "sdf_train: 16 levels x 2 features only");
+    int rc = check_tc("sdf_train", t->net);
+    if (rc) return rc;
+    GSSDF_REQUIRE(t->n >= 0, GSSDF_EINVAL, "sdf_train: negative n");
+    if (t->n == 0) return GSSDF_OK;
+    GSSDF_REQUIRE(t->x && t->net.table_half && t->net.mlp, GSSDF_EINVAL, "sdf_train: x, table_half, mlp must be non-null");
+    GSSDF_REQUIRE(t->n_variants == 1 || t->n_variants == 7, GSSDF_EINVAL, "sdf_train: n_variants must be 1 or 7");
+    GSSDF_REQUIRE(t->n_variants == 1 || t->delta > 0.f, GSSDF_EINVAL, "sdf_train: delta must be positive");
+    GSSDF_REQUIRE(((uintptr_t)t->table_grad & 7) == 0, GSSDF_EINVAL, "sdf_train: table_grad must be 8-byte aligned");
+    gssdf_sdf_bwd_args a{};
+    a.net = t->net; a.n = t->n; a.x = t->x; a.n_variants = t->n_variants; a.delta = t->delta; a.n_live = t->n_live;
+    a.table_grad = t->table_grad; a.mlp_grad = t->mlp_grad; a.v_x = t->v_x;
+    TcLossArgs lo{t->gt_sdf, t->weights, t->visibilities,
+                  SdfLossCfg{t->bce_isigma, t->bce_weight, t->eikonal_weight, t->gs_sdf_weight, t->delta, t->visible_thr}, t->loss_out};
+    const GridGeom g = make_grid(t->net);
+    GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdTcSmem));
+    const int pt = 128 / t->n_variants;
+    const int64_t n_tiles = (t->n + pt - 1) / pt;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sms);
+    sdf_bwd_tc_kernel<true><<<grid, kBwdTcThreads, kBwdTcSmem, (cudaStream_t)stream>>>(a, lo, g, n_tiles);
+    GSSDF_LAUNCH_OK("sdf_train_kernel");
     return GSSDF_OK;
 }

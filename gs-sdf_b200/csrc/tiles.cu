@@ -42,6 +42,12 @@ __device__ __forceinline__ bool tile_rect(const gssdf_tile_encode_args &a, const
     return true;
 }
 
+__device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // culled mode: intersect the reference rect with the conservative tile rectangle of the splat's exact footprint (conic.cuh)
 __device__ __forceinline__ bool shrink_rect(const gssdf_tile_encode_args &a, int idx, uint32_t &x0, uint32_t &y0, uint32_t &x1, uint32_t &y1) {
     if (!a.conics) return true;
@@ -112,6 +118,13 @@ tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__r
     const bool in = idx < nnz;
     uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     bool has = in && tile_rect(a, g, idx, x0, y0, x1, y1);
+    {   // reference intersection count (diagnostic): one atomic per warp
+        const unsigned area = warp_sum_u(has ? (x1 - x0) * (y1 - y0) : 0u);
+        if ((threadIdx.x & 31) == 0 && area) {
+            const int old = atomicAdd(&a.counts->n_isects_aabb, (int)min(area, 0x3fffffffu));
+            if (old < 0 || old + (int)min(area, 0x3fffffffu) < 0) a.counts->n_isects_aabb = 0x7fffffff;  // saturate
+        }
+    }
     has = has && shrink_rect(a, idx, x0, y0, x1, y1);
     if (in && a.tiles_per_gauss && !a.conics) a.tiles_per_gauss[idx] = has ? (int32_t)((y1 - y0) * (x1 - x0)) : 0;
     const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
@@ -308,6 +321,7 @@ extern "C" int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t
     GSSDF_REQUIRE(!a->conics || (a->tile_size == 16 && ((uintptr_t)a->conics & 15) == 0), GSSDF_EINVAL,
                   "tile_encode: footprint culling (conics) needs tile_size 16 and a 16-byte aligned conic array");
     GSSDF_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)bins * 4, st));
+    GSSDF_CUDA_OK(cudaMemsetAsync(&a->counts->n_isects_aabb, 0, 4, st));
     if (a->conics && a->tiles_per_gauss && a->cap > 0) GSSDF_CUDA_OK(cudaMemsetAsync(a->tiles_per_gauss, 0, (size_t)a->cap * 4, st));
     if (a->cap > 0) {
         GSSDF_REQUIRE(a->means2d && a->radii && a->depths && a->flatten_ids, GSSDF_EINVAL, "tile_encode: null input/output");

@@ -117,7 +117,7 @@ class SplatRenderer:
 
     def read_counts(self):
         c = self.counts.cpu().tolist()
-        return dict(nnz=c[0], n_isects=c[1], nnz_overflow=c[2], isect_overflow=c[3], max_tile_count=c[4])
+        return dict(nnz=c[0], n_isects=c[1], nnz_overflow=c[2], isect_overflow=c[3], max_tile_count=c[4], n_isects_aabb=c[6])
 
 
 class GsSdfStep:
@@ -163,7 +163,7 @@ class GsSdfStep:
         self.v_samples = e(cap, 3)
         self.sdf_loss = torch.zeros(1, **f32)
 
-    KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 8  # + table cast + decoder weight image + 2 x (sdf fwd, sdf loss, sdf bwd)
+    KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 4  # + table cast + decoder weight image + 2 fused sdf train kernels (mlp_mode 1)
 
     def _rebind_splat_grads(self, n_splat):
         R, N, K = self.R, self.R.N, self.R.K
@@ -176,7 +176,9 @@ class GsSdfStep:
     def refresh_table(self, table_f32):
         cabi.sdf_table_to_half(table_f32, self.table_half)
 
-    def step(self, scene, table_f32, mlp, viewmats, Ks, gt_image, ray_xyz, ray_gt_sdf, randns=None):
+    def step(self, scene, table_f32, mlp, viewmats, Ks, gt_image, ray_xyz, ray_gt_sdf, randns=None, on_sdf_grads_ready=None):
+        """on_sdf_grads_ready(table_and_mlp_grad): called once the hash-table / decoder gradients are final (after [C]) so a
+        data-parallel caller can start reducing them while the render backward [D] is still running."""
         R, n_ray, cap = self.R, self.n_ray, self.R.cap
         # fp32 master -> fp16 shadow once per step (the optimiser moved the master; the reference casts on EVERY forward)
         cabi.sdf_table_to_half(table_f32, self.table_half)
@@ -186,20 +188,31 @@ class GsSdfStep:
                            mlp_packed=self.mlp_packed, **self.cfg)
         self.flat_grad.zero_()
         self.sdf_loss.zero_()
-        # [A] SDF stage on the ray samples
-        cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, self.ray_y1, None, n_variants=7, delta=self.delta)
-        cabi.sdf_loss(n_ray, 7, self.ray_sdf, self.ray_y1, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.delta, self.sdf_loss,
-                      self.ray_vs, self.ray_vy)
-        cabi.sdf_bwd(net, ray_xyz, self.ray_vs, self.ray_vy, self.table_grad, self.mlp_grad, None, n_variants=7, delta=self.delta)
+        # [A] SDF stage on the ray samples (tensor-core mode: forward + losses + backward fused in one kernel)
+        if self.mlp_mode == 1:
+            cabi.sdf_train(net, ray_xyz, 7, self.delta, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.sdf_loss,
+                           self.table_grad, self.mlp_grad, None)
+        else:
+            cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, self.ray_y1, None, n_variants=7, delta=self.delta)
+            cabi.sdf_loss(n_ray, 7, self.ray_sdf, self.ray_y1, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.delta, self.sdf_loss,
+                          self.ray_vs, self.ray_vy)
+            cabi.sdf_bwd(net, ray_xyz, self.ray_vs, self.ray_vy, self.table_grad, self.mlp_grad, None, n_variants=7, delta=self.delta)
         # [B] render
         R.forward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, randns)
         # [C] coupling on the stochastic splat samples (rows < nnz, counted on the device)
         samples, n_live = R.p["samples"], R.counts  # counts[0] == nnz
-        cabi.sdf_fwd(net, samples, self.gs_sdf, self.gs_y1, None, n_variants=7, delta=self.delta, n_live=n_live)
-        cabi.sdf_loss(cap, 7, self.gs_sdf, self.gs_y1, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w, self.delta,
-                      self.sdf_loss, self.gs_vs, self.gs_vy, visibilities=R.r["visibilities"], visible_thr=self.vis_thr, n_live=n_live)
-        cabi.sdf_bwd(net, samples, self.gs_vs, self.gs_vy, self.table_grad, self.mlp_grad, self.v_samples, n_variants=7, delta=self.delta,
-                     n_live=n_live)
+        if self.mlp_mode == 1:
+            cabi.sdf_train(net, samples, 7, self.delta, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
+                           self.sdf_loss, self.table_grad, self.mlp_grad, self.v_samples, visibilities=R.r["visibilities"],
+                           visible_thr=self.vis_thr, n_live=n_live)
+        else:
+            cabi.sdf_fwd(net, samples, self.gs_sdf, self.gs_y1, None, n_variants=7, delta=self.delta, n_live=n_live)
+            cabi.sdf_loss(cap, 7, self.gs_sdf, self.gs_y1, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w, self.delta,
+                          self.sdf_loss, self.gs_vs, self.gs_vy, visibilities=R.r["visibilities"], visible_thr=self.vis_thr, n_live=n_live)
+            cabi.sdf_bwd(net, samples, self.gs_vs, self.gs_vy, self.table_grad, self.mlp_grad, self.v_samples, n_variants=7, delta=self.delta,
+                         n_live=n_live)
+        if on_sdf_grads_ready is not None:
+            on_sdf_grads_ready(self.flat_grad[self.table_grad.storage_offset():])
         # [D] photometric loss + backward of the render, with the coupling gradient entering through the samples
         loss = R.backward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, gt_image, randns,
                           v_samples=self.v_samples, zero_grads=False)

@@ -49,7 +49,7 @@ const char *gssdf_last_error(void);
 /* "gssdf_b200 <ver> sm_100a" */
 const char *gssdf_version(void);
 /* Argument structs grow between revisions: a binding compiled against this header must see the same number from the library. */
-#define GSSDF_ABI_REVISION 4
+#define GSSDF_ABI_REVISION 5
 int32_t gssdf_abi_revision(void);
 
 /* Device-side counters shared by the stages of one render. Zeroed by gssdf_project2dgs_fwd. */
@@ -60,7 +60,9 @@ typedef struct gssdf_counts {
     int32_t isect_overflow; /* 1 if n_isects exceeded the capacity given to tile_encode         */
     int32_t max_tile_count; /* largest number of intersections in one tile (diagnostic)        */
     int32_t n_culled;       /* intersections that survive the raster culling pass (diagnostic)  */
-    int32_t reserved[2];
+    int32_t n_isects_aabb;  /* the REFERENCE's intersection count (every tile of each radius AABB, saturating), also when tile_encode
+                               culls with conics: the unit the algorithmic-bytes figures of SURVEY 8d are quoted in */
+    int32_t reserved[1];
 } gssdf_counts;
 
 /* ------------------------------------------------------------------------------------------
@@ -428,6 +430,28 @@ typedef struct gssdf_sdf_loss_args {
     float *v_sdf, *v_y1;     /* [n_variants*n] */
 } gssdf_sdf_loss_args;
 int gssdf_sdf_loss(const gssdf_sdf_loss_args *a, gssdf_stream_t stream);
+
+/* gssdf_sdf_fwd + gssdf_sdf_loss + gssdf_sdf_bwd in ONE persistent kernel (mlp_mode 1 only): per 128-row tile encode -> decoder ->
+ * per-point losses -> backward -> table / decoder gradients (+ dL/dx of the base point). Same arithmetic as the three separate
+ * calls (same loss function, same forward, same backward); nothing but gradients and the scalar loss leaves the SM. */
+typedef struct gssdf_sdf_train_args {
+    gssdf_sdf_net net;       /* mlp_mode must be 1 */
+    int64_t n;               /* base points */
+    const float *x;          /* [n,3] */
+    int32_t n_variants;      /* 1 or 7 */
+    float delta;
+    const int32_t *n_live;   /* device int32 or NULL */
+    const float *gt_sdf;     /* [n] or NULL   (as in gssdf_sdf_loss_args) */
+    const float *weights;    /* [n] or NULL */
+    const float *visibilities; /* [n] or NULL */
+    float visible_thr;
+    float bce_isigma, bce_weight, eikonal_weight, gs_sdf_weight;
+    float *loss_out;         /* device float[1] += */
+    float *table_grad;       /* [table_params] fp32 += or NULL; 8-byte aligned */
+    float *mlp_grad;         /* [mlp_params]  fp32 += or NULL */
+    float *v_x;              /* [n,3] overwritten (rows < n_live) or NULL */
+} gssdf_sdf_train_args;
+int gssdf_sdf_train(const gssdf_sdf_train_args *a, gssdf_stream_t stream);
 
 #ifdef __cplusplus
 }

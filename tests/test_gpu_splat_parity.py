@@ -287,9 +287,10 @@ def test_presort_footprint_cull_is_exact(oracle, N, W, H, scale):
     for k in ("render_colors", "render_depths", "render_alphas", "render_normals", "render_median"):
         assert torch.equal(a["R"].r[k], b["R"].r[k]), k
     # per-splat visibility is a float atomic sum over tiles: same terms, different order
-    torch.testing.assert_close(a["R"].r["visibilities"], b["R"].r["visibilities"], rtol=1e-5, atol=1e-6)
+    nnz = a["cnt"]["nnz"]  # rows >= nnz of the capacity buffers are undefined
+    torch.testing.assert_close(a["R"].r["visibilities"][:nnz], b["R"].r["visibilities"][:nnz], rtol=1e-5, atol=1e-5)
     assert torch.equal(a["R"].out_colors, b["R"].out_colors)
-    assert a["loss"] == b["loss"]
+    assert abs(a["loss"] - b["loss"]) <= 2e-6 * abs(a["loss"])  # the L1 reduction uses float atomics: same terms, any order
     torch.testing.assert_close(b["grad"], a["grad"], rtol=1e-4, atol=1e-6 * float(a["grad"].abs().max()))
     n_t = len(a["off"])
     for t in range(n_t):  # sub-sequence check
