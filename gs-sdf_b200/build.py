@@ -74,5 +74,5 @@ def build_shim(force=False):
 
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
-    if "--shim" in sys.argv:
+    if "--no-shim" not in sys.argv:  # the shim embeds the argument-struct layouts: always keep it in step with the header
         print(build_shim(force="-f" in sys.argv))
