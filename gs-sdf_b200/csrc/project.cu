@@ -146,6 +146,13 @@ project2dgs_fwd_kernel(const gssdf_project2dgs_fwd_args a, int32_t *__restrict__
     const int rows = min((int64_t)kProjThreads, (int64_t)a.N - row0);
     stage_rows3(a.means, row0, rows, s_means);
     stage_rows3(a.scales, row0, rows, s_scales);
+    if (a.mean_offsets || a.raw_params) {  // a1 fused: activations applied while staging (no activated copies in HBM)
+        __syncthreads();
+        for (int e = threadIdx.x; e < rows * 3; e += blockDim.x) {
+            if (a.mean_offsets) s_means[e] += __ldg(a.mean_offsets + row0 * 3 + e);
+            if (a.raw_params) s_scales[e] = expf(s_scales[e]);
+        }
+    }
     __syncthreads();
     const int tid = threadIdx.x;
     const int64_t gid = row0 + tid;
@@ -201,7 +208,10 @@ project2dgs_fwd_kernel(const gssdf_project2dgs_fwd_args a, int32_t *__restrict__
         for (int k = 0; k < 3; ++k) a.samples[3 * i + k] = o.RSw0[k] * r0 + o.RSw1[k] * r1 + s_means[tid * 3 + k];
     }
     if (a.sample_weights) a.sample_weights[i] = expf(-0.5f * (r0 * r0 + r1 * r1));
-    if (a.pt_opacities) a.pt_opacities[i] = __ldg(a.opacities + gid);
+    if (a.pt_opacities) {
+        const float o_raw = __ldg(a.opacities + gid);
+        a.pt_opacities[i] = a.raw_params ? 1.f / (1.f + expf(-o_raw)) : o_raw;
+    }
 }
 
 // Single-CTA exclusive scan of the per-block counts; writes offs[0..n] (offs[n] = total) and the
@@ -283,12 +293,17 @@ project2dgs_bwd_kernel(const gssdf_project2dgs_bwd_args a) {
     const int64_t gid = a.gaussian_ids[i];
     const Cam cam = load_cam(a.viewmats, a.Ks, cid);
     const float *R = cam.R;
-    const float mw[3] = {a.means[3 * gid], a.means[3 * gid + 1], a.means[3 * gid + 2]};
+    float mw[3] = {a.means[3 * gid], a.means[3 * gid + 1], a.means[3 * gid + 2]};
+    if (a.mean_offsets) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) mw[k] += a.mean_offsets[3 * gid + k];
+    }
     float mc[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) mc[r] = R[r * 3] * mw[0] + R[r * 3 + 1] * mw[1] + R[r * 3 + 2] * mw[2] + cam.t[r];
     const float4 quat = __ldg(reinterpret_cast<const float4 *>(a.quats) + gid);
-    const float s0 = a.scales[3 * gid], s1 = a.scales[3 * gid + 1];
+    float s0 = a.scales[3 * gid], s1 = a.scales[3 * gid + 1];
+    if (a.raw_params) { s0 = expf(s0); s1 = expf(s1); }
     const float *rt = a.ray_transforms + 9 * (int64_t)i;
     float G[9];
 #pragma unroll
@@ -357,9 +372,13 @@ project2dgs_bwd_kernel(const gssdf_project2dgs_bwd_args a) {
     for (int k = 0; k < 3; ++k) atomicAdd(a.v_means + 3 * gid + k, vmean[k]);
 #pragma unroll
     for (int k = 0; k < 4; ++k) atomicAdd(a.v_quats + 4 * gid + k, vq[k]);
-    atomicAdd(a.v_scales + 3 * gid, vs0);
-    atomicAdd(a.v_scales + 3 * gid + 1, vs1);
-    if (a.v_pt_opacities) atomicAdd(a.v_opacities + gid, a.v_pt_opacities[i]);
+    atomicAdd(a.v_scales + 3 * gid, a.raw_params ? vs0 * s0 : vs0);       // d/d log s = s * d/ds
+    atomicAdd(a.v_scales + 3 * gid + 1, a.raw_params ? vs1 * s1 : vs1);
+    if (a.v_pt_opacities) {
+        float v = a.v_pt_opacities[i];
+        if (a.raw_params) { const float o = a.pt_opacities[i]; v *= o * (1.f - o); }  // sigmoid'
+        atomicAdd(a.v_opacities + gid, v);
+    }
 }
 
 }  // namespace gssdf
@@ -417,6 +436,8 @@ extern "C" int gssdf_project2dgs_bwd(const gssdf_project2dgs_bwd_args *a, gssdf_
     GSSDF_REQUIRE(a->v_means && a->v_quats && a->v_scales, GSSDF_EINVAL, "project2dgs_bwd: v_means/v_quats/v_scales required");
     GSSDF_REQUIRE(aligned16(a->quats), GSSDF_EINVAL, "project2dgs_bwd: quats must be 16-byte aligned");
     GSSDF_REQUIRE(!a->v_pt_opacities || a->v_opacities, GSSDF_EINVAL, "project2dgs_bwd: v_pt_opacities requires v_opacities");
+    GSSDF_REQUIRE(!(a->raw_params && a->v_pt_opacities) || a->pt_opacities, GSSDF_EINVAL,
+                  "project2dgs_bwd: raw_params with v_pt_opacities needs the forward's pt_opacities");
     project2dgs_bwd_kernel<<<cdiv(a->cap, 256), 256, 0, (cudaStream_t)stream>>>(*a);
     GSSDF_LAUNCH_OK("project2dgs_bwd_kernel");
     return GSSDF_OK;

@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(256) view_colors_fwd_kernel(const gssdf_view_c
     if (rad.x > 0 && rad.y > 0) {
         float cc[3];
         cam_centre(a.viewmats, (int)a.camera_ids[i], cc);
-        const float dx = a.means[3 * g] - cc[0], dy = a.means[3 * g + 1] - cc[1], dz = a.means[3 * g + 2] - cc[2];
+        float dx = a.means[3 * g] - cc[0], dy = a.means[3 * g + 1] - cc[1], dz = a.means[3 * g + 2] - cc[2];
+        if (a.mean_offsets) { dx += a.mean_offsets[3 * g]; dy += a.mean_offsets[3 * g + 1]; dz += a.mean_offsets[3 * g + 2]; }
         float x = 0.f, y = 0.f, z = 0.f;
         if (DEG >= 1) {
             const float inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
@@ -118,12 +119,15 @@ __global__ void __launch_bounds__(256) view_colors_fwd_kernel(const gssdf_view_c
         }
         float b[KU];
         sh_bases<DEG>(x, y, z, b);
-        const float *co = a.sh + (size_t)g * a.K * 3;
+        // coefficients of basis k: one [N,K,3] array, or features_dc [N,1,3] + features_rest [N,K-1,3] (a1 fused)
+        const float *co = a.sh_rest ? a.sh + (size_t)g * 3 : a.sh + (size_t)g * a.K * 3;
+        const float *cr = a.sh_rest ? a.sh_rest + (size_t)g * (a.K - 1) * 3 - 3 : co;
 #pragma unroll
         for (int k = 0; k < KU; ++k) {
-            out[0] += b[k] * __ldg(co + 3 * k);
-            out[1] += b[k] * __ldg(co + 3 * k + 1);
-            out[2] += b[k] * __ldg(co + 3 * k + 2);
+            const float *c = k == 0 ? co : cr + 3 * k;
+            out[0] += b[k] * __ldg(c);
+            out[1] += b[k] * __ldg(c + 1);
+            out[2] += b[k] * __ldg(c + 2);
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) out[c] = fmaxf(out[c] + 0.5f, 0.f);
@@ -152,7 +156,8 @@ __global__ void __launch_bounds__(256) view_colors_bwd_kernel(const gssdf_view_c
     }
     float cc[3];
     cam_centre(a.viewmats, (int)a.camera_ids[i], cc);
-    const float dx = a.means[3 * g] - cc[0], dy = a.means[3 * g + 1] - cc[1], dz = a.means[3 * g + 2] - cc[2];
+    float dx = a.means[3 * g] - cc[0], dy = a.means[3 * g + 1] - cc[1], dz = a.means[3 * g + 2] - cc[2];
+    if (a.mean_offsets) { dx += a.mean_offsets[3 * g]; dy += a.mean_offsets[3 * g + 1]; dz += a.mean_offsets[3 * g + 2]; }
     float x = 0.f, y = 0.f, z = 0.f, inorm = 1.f;
     if (DEG >= 1) {
         inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
@@ -160,16 +165,21 @@ __global__ void __launch_bounds__(256) view_colors_bwd_kernel(const gssdf_view_c
     }
     float b[KU];
     sh_bases<DEG>(x, y, z, b);
-    float *vsh = a.v_sh + (size_t)g * a.K * 3;
-    const float *co = a.sh + (size_t)g * a.K * 3;
+    const bool split = a.sh_rest != nullptr;
+    float *vsh = split ? a.v_sh + (size_t)g * 3 : a.v_sh + (size_t)g * a.K * 3;
+    float *vsr = split ? a.v_sh_rest + (size_t)g * (a.K - 1) * 3 - 3 : vsh;
+    const float *co = split ? a.sh + (size_t)g * 3 : a.sh + (size_t)g * a.K * 3;
+    const float *cr = split ? a.sh_rest + (size_t)g * (a.K - 1) * 3 - 3 : co;
     float w[KU];
 #pragma unroll
     for (int k = 0; k < KU; ++k) {
+        float *v = k == 0 ? vsh : vsr + 3 * k;
+        const float *c = k == 0 ? co : cr + 3 * k;
         // unique (camera, splat) pairs: conflict-free for C == 1, RED for C > 1
-        atomicAdd(vsh + 3 * k, b[k] * vc[0]);
-        atomicAdd(vsh + 3 * k + 1, b[k] * vc[1]);
-        atomicAdd(vsh + 3 * k + 2, b[k] * vc[2]);
-        w[k] = __ldg(co + 3 * k) * vc[0] + __ldg(co + 3 * k + 1) * vc[1] + __ldg(co + 3 * k + 2) * vc[2];
+        atomicAdd(v, b[k] * vc[0]);
+        atomicAdd(v + 1, b[k] * vc[1]);
+        atomicAdd(v + 2, b[k] * vc[2]);
+        w[k] = __ldg(c) * vc[0] + __ldg(c + 1) * vc[1] + __ldg(c + 2) * vc[2];
     }
     if (DEG >= 1 && a.v_means) {
         float vx, vy, vz;
@@ -214,6 +224,7 @@ extern "C" int gssdf_view_colors_bwd(const gssdf_view_colors_bwd_args *a, gssdf_
     GSSDF_REQUIRE(a->viewmats && a->means && a->sh && a->counts && a->camera_ids && a->gaussian_ids && a->radii &&
                       a->colors && a->v_colors && a->v_sh,
                   GSSDF_EINVAL, "view_colors_bwd: null pointer");
+    GSSDF_REQUIRE(!a->sh_rest || (a->v_sh_rest && a->K >= 2), GSSDF_EINVAL, "view_colors_bwd: sh_rest needs v_sh_rest and K >= 2");
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = cdiv(a->cap, 256);
     switch (a->sh_degree) {

@@ -50,7 +50,7 @@ class Workspace:
 
 
 def project2dgs_fwd(means, quats, scales, viewmats, Ks, W, H, near, far, radius_clip, randns, cap, out, counts, ws,
-                    opacities=None):
+                    opacities=None, mean_offsets=None, raw_params=False):
     """out: dict of capacity-sized tensors (camera_ids, gaussian_ids, radii, means2d, depths, ray_transforms,
     normals, samples, sample_weights, indptr)."""
     N, Cn = means.shape[0], viewmats.shape[0]
@@ -67,35 +67,41 @@ def project2dgs_fwd(means, quats, scales, viewmats, Ks, W, H, near, far, radius_
                   gaussian_ids=out["gaussian_ids"], radii=out["radii"], means2d=out["means2d"], depths=out["depths"],
                   ray_transforms=out["ray_transforms"], normals=out["normals"], samples=out.get("samples"),
                   sample_weights=out.get("sample_weights"), indptr=out.get("indptr"), counts=counts, workspace=w,
-                  workspace_bytes=w.numel())
+                  workspace_bytes=w.numel(), mean_offsets=_req(mean_offsets, f32, "mean_offsets"), raw_params=int(bool(raw_params)))
     check(lib().gssdf_project2dgs_fwd(_lib.C.byref(a), _stream()))
 
 
 def project2dgs_bwd(means, quats, scales, viewmats, Ks, W, H, cap, counts, camera_ids, gaussian_ids, ray_transforms,
                     randns, v_means2d, v_depths, v_ray_transforms, v_normals, v_samples, v_means, v_quats, v_scales,
-                    v_pt_opacities=None, v_opacities=None):
+                    v_pt_opacities=None, v_opacities=None, mean_offsets=None, raw_params=False, pt_opacities=None):
     a = make_args("gssdf_project2dgs_bwd_args", N=means.shape[0], C=viewmats.shape[0], means=means, quats=quats,
                   scales=scales, viewmats=viewmats, Ks=Ks, image_width=W, image_height=H, cap=cap, counts=counts,
                   camera_ids=camera_ids, gaussian_ids=gaussian_ids, ray_transforms=ray_transforms, randns=randns,
                   v_means2d=v_means2d, v_depths=v_depths, v_ray_transforms=v_ray_transforms, v_normals=v_normals,
                   v_samples=v_samples, v_means=v_means, v_quats=v_quats, v_scales=v_scales,
-                  v_pt_opacities=v_pt_opacities, v_opacities=v_opacities)
+                  v_pt_opacities=v_pt_opacities, v_opacities=v_opacities, mean_offsets=mean_offsets, raw_params=int(bool(raw_params)),
+                  pt_opacities=pt_opacities)
     check(lib().gssdf_project2dgs_bwd(_lib.C.byref(a), _stream()))
 
 
-def view_colors_fwd(viewmats, means, sh, sh_degree, cap, counts, camera_ids, gaussian_ids, radii, colors):
-    a = make_args("gssdf_view_colors_fwd_args", N=means.shape[0], C=viewmats.shape[0], K=sh.shape[1],
+def view_colors_fwd(viewmats, means, sh, sh_degree, cap, counts, camera_ids, gaussian_ids, radii, colors, mean_offsets=None,
+                    sh_rest=None):
+    """sh_rest given: `sh` is features_dc [N,1,3], sh_rest features_rest [N,K-1,3] (no concatenated copy)."""
+    K = sh.shape[1] + (sh_rest.shape[1] if sh_rest is not None else 0)
+    a = make_args("gssdf_view_colors_fwd_args", N=means.shape[0], C=viewmats.shape[0], K=K,
                   sh_degree=sh_degree, viewmats=viewmats, means=means, sh=sh, cap=cap, counts=counts,
-                  camera_ids=camera_ids, gaussian_ids=gaussian_ids, radii=radii, colors=colors)
+                  camera_ids=camera_ids, gaussian_ids=gaussian_ids, radii=radii, colors=colors, mean_offsets=mean_offsets,
+                  sh_rest=sh_rest)
     check(lib().gssdf_view_colors_fwd(_lib.C.byref(a), _stream()))
 
 
 def view_colors_bwd(viewmats, means, sh, sh_degree, cap, counts, camera_ids, gaussian_ids, radii, colors, v_colors,
-                    v_sh, v_means):
-    a = make_args("gssdf_view_colors_bwd_args", N=means.shape[0], C=viewmats.shape[0], K=sh.shape[1],
+                    v_sh, v_means, mean_offsets=None, sh_rest=None, v_sh_rest=None):
+    K = sh.shape[1] + (sh_rest.shape[1] if sh_rest is not None else 0)
+    a = make_args("gssdf_view_colors_bwd_args", N=means.shape[0], C=viewmats.shape[0], K=K,
                   sh_degree=sh_degree, viewmats=viewmats, means=means, sh=sh, cap=cap, counts=counts,
                   camera_ids=camera_ids, gaussian_ids=gaussian_ids, radii=radii, colors=colors, v_colors=v_colors,
-                  v_sh=v_sh, v_means=v_means)
+                  v_sh=v_sh, v_means=v_means, mean_offsets=mean_offsets, sh_rest=sh_rest, v_sh_rest=v_sh_rest)
     check(lib().gssdf_view_colors_bwd(_lib.C.byref(a), _stream()))
 
 

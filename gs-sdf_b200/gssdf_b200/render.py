@@ -64,12 +64,15 @@ class SplatRenderer:
         self.prof_fwd = self.prof_bwd = None  # optional (start, stop) torch.cuda.Event pairs around the raster kernels
 
     # -- forward ------------------------------------------------------------------------------
-    def forward(self, means, quats, scales, opacities, sh, viewmats, Ks, randns=None):
+    def forward(self, means, quats, scales, opacities, sh, viewmats, Ks, randns=None, raw=None):
+        """raw = dict(offsets=[N,3], sh_rest=[N,K-1,3]) switches to the RAW parameters of NeuralGS (row a1 fused into the kernels):
+        means = anchors, scales = log-scales, opacities = logits, sh = features_dc; no activated copies are materialised."""
         C, W, H, cap = self.C, self.W, self.H, self.cap
+        off, rest = (raw["offsets"], raw["sh_rest"]) if raw else (None, None)
         cabi.project2dgs_fwd(means, quats, scales, viewmats, Ks, W, H, self.near, self.far, 0.0, randns, cap, self.p,
-                             self.counts, self.ws, opacities=opacities)
+                             self.counts, self.ws, opacities=opacities, mean_offsets=off, raw_params=raw is not None)
         cabi.view_colors_fwd(viewmats, means, sh, self.sh_degree, cap, self.counts, self.p["camera_ids"],
-                             self.p["gaussian_ids"], self.p["radii"], self.colors)
+                             self.p["gaussian_ids"], self.p["radii"], self.colors, mean_offsets=off, sh_rest=rest)
         conics = None
         if self.presort_cull:  # exact footprint test BEFORE the sort: ~4x fewer keys to scatter / sort / cull
             cabi.splat_conics(cap, W, H, self.counts, self.p["ray_transforms"], self.p["pt_opacities"], self.conics)
@@ -85,8 +88,13 @@ class SplatRenderer:
 
     # -- loss + backward -----------------------------------------------------------------------
     def backward(self, means, quats, scales, opacities, sh, viewmats, Ks, gt, randns=None, w_rgb=1.0, w_depth=0.1, v_samples=None,
-                 zero_grads=True):
+                 zero_grads=True, raw=None):
+        """With raw parameters the flat gradient holds dL/d(offsets|quats|log-scales|logits|features_dc|features_rest); the SH segment
+        keeps its [N,K,3] size, laid out as dc [N,1,3] followed by rest [N,K-1,3]."""
         C, W, H, cap = self.C, self.W, self.H, self.cap
+        off, rest = (raw["offsets"], raw["sh_rest"]) if raw else (None, None)
+        N, K = self.N, self.K
+        v_sh, v_rest = (self.v_sh.view(-1)[:N * 3].view(N, 1, 3), self.v_sh.view(-1)[N * 3:].view(N, K - 1, 3)) if raw else (self.v_sh, None)
         self.loss.zero_()
         if zero_grads:
             self.flat_grad.zero_()
@@ -100,17 +108,20 @@ class SplatRenderer:
                             self.v_r["colors"], self.v_r["depths"], self.v_r["alphas"], self.v_r["normals"],
                             self.v_r["median"], self.g, self.raster_ws, prof=self.prof_bwd, isect_cap=self.isect_cap, reuse_fwd=True)
         cabi.view_colors_bwd(viewmats, means, sh, self.sh_degree, cap, self.counts, self.p["camera_ids"],
-                             self.p["gaussian_ids"], self.p["radii"], self.colors, self.g["v_colors"], self.v_sh, self.v_means)
+                             self.p["gaussian_ids"], self.p["radii"], self.colors, self.g["v_colors"], v_sh, self.v_means,
+                             mean_offsets=off, sh_rest=rest, v_sh_rest=v_rest)
         cabi.project2dgs_bwd(means, quats, scales, viewmats, Ks, W, H, cap, self.counts, self.p["camera_ids"],
                              self.p["gaussian_ids"], self.p["ray_transforms"], randns, None, None, self.g["v_ray_transforms"],
                              self.g["v_normals"], v_samples, self.v_means, self.v_quats, self.v_scales,
-                             v_pt_opacities=self.g["v_opacities"], v_opacities=self.v_opac)
+                             v_pt_opacities=self.g["v_opacities"], v_opacities=self.v_opac, mean_offsets=off,
+                             raw_params=raw is not None, pt_opacities=self.p["pt_opacities"])
         return self.loss
 
     def step(self, scene, viewmats, Ks, gt, randns=None):
-        self.forward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, randns)
+        raw = scene.get("raw")
+        self.forward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, randns, raw=raw)
         return self.backward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, gt,
-                             randns)
+                             randns, raw=raw)
 
     # kernels launched by one step() (fwd: 3+1+6+2+1, bwd: 1+1+3+1+1 ; memsets not counted)
     KERNELS_PER_STEP = 21
@@ -198,7 +209,8 @@ class GsSdfStep:
                           self.ray_vs, self.ray_vy)
             cabi.sdf_bwd(net, ray_xyz, self.ray_vs, self.ray_vy, self.table_grad, self.mlp_grad, None, n_variants=7, delta=self.delta)
         # [B] render
-        R.forward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, randns)
+        R.forward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, randns,
+                  raw=scene.get("raw"))
         # [C] coupling on the stochastic splat samples (rows < nnz, counted on the device)
         samples, n_live = R.p["samples"], R.counts  # counts[0] == nnz
         if self.mlp_mode == 1:
@@ -215,5 +227,5 @@ class GsSdfStep:
             on_sdf_grads_ready(self.flat_grad[self.table_grad.storage_offset():])
         # [D] photometric loss + backward of the render, with the coupling gradient entering through the samples
         loss = R.backward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, gt_image, randns,
-                          v_samples=self.v_samples, zero_grads=False)
+                          v_samples=self.v_samples, zero_grads=False, raw=scene.get("raw"))
         return loss, self.sdf_loss

@@ -49,7 +49,7 @@ const char *gssdf_last_error(void);
 /* "gssdf_b200 <ver> sm_100a" */
 const char *gssdf_version(void);
 /* Argument structs grow between revisions: a binding compiled against this header must see the same number from the library. */
-#define GSSDF_ABI_REVISION 5
+#define GSSDF_ABI_REVISION 6
 int32_t gssdf_abi_revision(void);
 
 /* Device-side counters shared by the stages of one render. Zeroed by gssdf_project2dgs_fwd. */
@@ -100,6 +100,9 @@ typedef struct gssdf_project2dgs_fwd_args {
     gssdf_counts *counts;   /* device; zeroed then counts->nnz (+overflow flag) written */
     void *workspace;        /* device scratch, >= gssdf_project2dgs_workspace_bytes(N, C) */
     size_t workspace_bytes;
+    /* a1 fused (NeuralGS::generate_gaussian, neural_gaussian.cpp:463-492): read the RAW parameters instead of activated copies */
+    const float *mean_offsets; /* [N,3] or NULL: means := means (anchors) + mean_offsets            (get_xyz)     */
+    int32_t raw_params;        /* 1: scales := exp(scales) (get_scale), pt_opacities := sigmoid(opacities) (get_opacity(training)) */
 } gssdf_project2dgs_fwd_args;
 size_t gssdf_project2dgs_workspace_bytes(int32_t N, int32_t C);
 int gssdf_project2dgs_fwd(const gssdf_project2dgs_fwd_args *a, gssdf_stream_t stream);
@@ -128,6 +131,11 @@ typedef struct gssdf_project2dgs_bwd_args {
     float *v_means;               /* [N,3] += */
     float *v_quats;               /* [N,4] += */
     float *v_scales;              /* [N,3] += (z component untouched, like the reference) */
+    /* a1 fused: same meaning as in the forward; the gradients then refer to the RAW parameters (v_scales = dL/d log-scale,
+       v_opacities = dL/d logit via pt_opacities = sigmoid(raw); v_means = dL/d offsets = dL/d anchors) */
+    const float *mean_offsets;
+    int32_t raw_params;
+    const float *pt_opacities;    /* [cap] activated opacities from the forward (required iff raw_params && v_pt_opacities) */
 } gssdf_project2dgs_bwd_args;
 int gssdf_project2dgs_bwd(const gssdf_project2dgs_bwd_args *a, gssdf_stream_t stream);
 
@@ -148,6 +156,10 @@ typedef struct gssdf_view_colors_fwd_args {
     const int64_t *camera_ids, *gaussian_ids; /* [cap] */
     const int32_t *radii;   /* [cap,2] */
     float *colors;          /* [cap,3] */
+    /* a1 fused: */
+    const float *mean_offsets; /* [N,3] or NULL: means := means + mean_offsets */
+    const float *sh_rest;      /* [N,K-1,3] or NULL. Non-NULL: `sh` is features_dc [N,1,3] and the bases k >= 1 are read here
+                                  (the reference concatenates 192 MB per step, neural_gaussian.cpp:488) */
 } gssdf_view_colors_fwd_args;
 int gssdf_view_colors_fwd(const gssdf_view_colors_fwd_args *a, gssdf_stream_t stream);
 
@@ -165,6 +177,10 @@ typedef struct gssdf_view_colors_bwd_args {
     const float *v_colors;  /* [cap,3] */
     float *v_sh;            /* [N,K,3] += */
     float *v_means;         /* [N,3] += or NULL */
+    /* a1 fused: */
+    const float *mean_offsets;
+    const float *sh_rest;      /* as in the forward */
+    float *v_sh_rest;          /* [N,K-1,3] += (required iff sh_rest; v_sh is then [N,1,3]) */
 } gssdf_view_colors_bwd_args;
 int gssdf_view_colors_bwd(const gssdf_view_colors_bwd_args *a, gssdf_stream_t stream);
 

@@ -280,3 +280,47 @@ def test_sdf_train_fused_equals_separate_calls(oracle, case):
         # layer) flips whole quanta -> table grad / v_x agree at the 1e-3 level only (same effect as in test_sdf_variants_and_losses)
         tol = 2e-5 if name == "mlp grad" else 2e-3
         assert np.linalg.norm(a_ - b_) <= tol * np.linalg.norm(a_), f"{name}: {np.linalg.norm(a_ - b_) / np.linalg.norm(a_):.2e}"
+
+
+def test_full_step_tensor_core_equals_cuda_core_path():
+    """GsSdfStep ([A] SDF on rays, [B] render, [C] GS<->SDF coupling, [D] backward) with the fused tcgen05 SDF kernels (mlp_mode 1)
+    vs the three-call fp32 CUDA-core path (mlp_mode 0): losses and every segment of the flat gradient agree."""
+    import math
+    from gssdf_b200 import render, scene as S
+    dev = _dev()
+    N, W, H, deg = 3000, 160, 96, 2
+    sc = S.box_scene(N, deg, seed=0, scale_mult=6.0)
+    V, K = S.cameras([0], W, H)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    tsc = {k: t(v) for k, v in sc.items()}
+    cfg = dict(n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=2.0, hidden_dim=64, n_hidden=3)
+    gen = torch.Generator(dev).manual_seed(5)
+    n_ray = 4096
+    outs = []
+    for mode in (0, 1):
+        G = render.GsSdfStep(N, (deg + 1) ** 2, W, H, dev, 300000, cfg, n_ray_samples=n_ray, sh_degree=deg, map_size=14.0, mlp_mode=mode)
+        gen.manual_seed(5)
+        table = (torch.rand(G.n_table, device=dev, generator=gen) * 2 - 1) * 0.1
+        chunks, dims = [], [32, 64, 64, 64, 64, 2]
+        for k_, o_ in zip(dims[:-1], dims[1:]):
+            b_ = 1.0 / math.sqrt(k_)
+            chunks += [(torch.rand(o_ * k_, device=dev, generator=gen) * 2 - 1) * b_, (torch.rand(o_, device=dev, generator=gen) * 2 - 1) * b_]
+        mlp = torch.cat(chunks)
+        box = torch.tensor(S.BOX, device=dev, dtype=torch.float32)
+        ray_xyz = (torch.rand(n_ray, 3, device=dev, generator=gen) * 2 - 1) * (box + 0.3)
+        ray_gt = (box - ray_xyz.abs()).min(dim=1).values.clamp(-0.3, 0.3).contiguous()
+        gt = torch.rand(1, H, W, 4, device=dev, generator=gen)
+        loss, sdf_loss = G.step(tsc, table, mlp, t(V), t(K), gt, ray_xyz, ray_gt, t(S.randns(N)))
+        torch.cuda.synchronize()
+        n_splat = G.R.flat_grad.numel()
+        outs.append(dict(loss=float(loss[0]), sdf_loss=float(sdf_loss[0]), splat=G.R.flat_grad.clone(), table=G.table_grad.clone(),
+                         mlp=G.mlp_grad.clone(), nnz=G.R.read_counts()["nnz"]))
+    a, b = outs
+    assert a["nnz"] == b["nnz"] and a["nnz"] > 100
+    assert abs(a["loss"] - b["loss"]) <= 1e-5 * abs(a["loss"])
+    assert abs(a["sdf_loss"] - b["sdf_loss"]) <= 1e-4 * abs(a["sdf_loss"]) and a["sdf_loss"] != 0.0
+    for k, tol in (("mlp", 1e-4), ("table", 3e-3), ("splat", 1e-3)):
+        x, y = a[k].double(), b[k].double()
+        assert float(x.abs().max()) > 0
+        rel = float((x - y).norm() / x.norm())
+        assert rel <= tol, f"{k}: {rel:.2e}"

@@ -301,6 +301,50 @@ def test_presort_footprint_cull_is_exact(oracle, N, W, H, scale):
         assert idx == sorted(idx), f"tile {t}: order changed"
 
 
+def test_fused_activations_a1_match_explicit_activations(oracle):
+    """Row a1 (NeuralGS::generate_gaussian, neural_gaussian.cpp:463-492) fused into the projection / SH kernels: rendering from the
+    RAW parameters (anchors + offsets, log-scales, logits, features_dc | features_rest) equals rendering from torch-activated
+    copies, and the gradients obey the chain rule of exp / sigmoid / cat."""
+    from gssdf_b200 import render
+    dev = _dev()
+    N, W, H, deg = 4000, 160, 96, 3
+    K = (deg + 1) ** 2
+    sc, V, Kc = small_scene(N, W, H, deg)
+    rn = S.randns(N)
+    rng = np.random.default_rng(4)
+    offsets = (0.01 * rng.standard_normal((N, 3))).astype(np.float32)
+    anchors = (sc["means"] - offsets).astype(np.float32)
+    logs = np.log(np.maximum(sc["scales"], 1e-8)).astype(np.float32)
+    op = np.clip(sc["opacities"], 1e-4, 1 - 1e-4)
+    logit = np.log(op / (1 - op)).astype(np.float32)
+    t = lambda a: _t(a, dev)
+    # explicit activations with torch (what the reference's ATen graph does)
+    means_t = t(anchors) + t(offsets)
+    scales_t, opac_t = torch.exp(t(logs)), torch.sigmoid(t(logit))
+    dc, rest = t(sc["sh"][:, :1].copy()), t(sc["sh"][:, 1:].copy())
+    sh_t = torch.cat([dc, rest], 1)
+    gt = torch.rand(1, H, W, 4, device=dev)
+    A = render.SplatRenderer(N, K, 1, W, H, dev, isect_cap=300000, sh_degree=deg)
+    la = A.step(dict(means=means_t, quats=t(sc["quats"]), scales=scales_t, opacities=opac_t, sh=sh_t), t(V), t(Kc), gt, t(rn))
+    B = render.SplatRenderer(N, K, 1, W, H, dev, isect_cap=300000, sh_degree=deg)
+    lb = B.step(dict(means=t(anchors), quats=t(sc["quats"]), scales=t(logs), opacities=t(logit), sh=dc,
+                     raw=dict(offsets=t(offsets), sh_rest=rest)), t(V), t(Kc), gt, t(rn))
+    torch.cuda.synchronize()
+    assert A.read_counts()["nnz"] == B.read_counts()["nnz"] > 100
+    torch.testing.assert_close(B.out_colors, A.out_colors, rtol=1e-5, atol=1e-6)
+    assert abs(float(la[0]) - float(lb[0])) <= 1e-5 * abs(float(la[0]))
+    tol = dict(rtol=2e-4, atol=0.0)
+    ref = {"means": A.v_means, "quats": A.v_quats, "scales": A.v_scales * scales_t, "opac": A.v_opac * opac_t * (1 - opac_t)}
+    got = {"means": B.v_means, "quats": B.v_quats, "scales": B.v_scales, "opac": B.v_opac}
+    for k in ref:
+        a_, b_ = ref[k].double(), got[k].double()
+        assert float(a_.abs().max()) > 0, k
+        assert float((a_ - b_).norm()) <= 2e-5 * float(a_.norm()), f"{k}: {float((a_ - b_).norm() / a_.norm()):.2e}"
+    v_dc, v_rest = B.v_sh.view(-1)[:N * 3].view(N, 1, 3), B.v_sh.view(-1)[N * 3:].view(N, K - 1, 3)
+    torch.testing.assert_close(v_dc, A.v_sh[:, :1], rtol=1e-4, atol=1e-9)
+    torch.testing.assert_close(v_rest, A.v_sh[:, 1:], rtol=1e-4, atol=1e-9)
+
+
 def test_error_conventions():
     """Reference wrappers throw on bad shapes / channel counts (GSC/rasterize_to_pixels.cpp:296-321); so do we."""
     from gssdf_b200 import ops
