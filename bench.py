@@ -260,7 +260,13 @@ def main():
 
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     sc_np = S.box_scene(N, deg, seed=0)  # replicated state: identical on every rank
-    sc = {k: t(v) for k, v in sc_np.items()}
+    sc_act = {k: t(v) for k, v in sc_np.items()}  # activated values (used once, for the ground-truth renders)
+    # the step runs on the RAW parameters of NeuralGS (anchors = centres, offsets = 0, scaling = log s, opacity =
+    # logit(o), features_dc | features_rest); row a1's activations are fused into the projection / SH kernels
+    op_ = np.clip(sc_np["opacities"], 1e-6, 1 - 1e-6)
+    sc = dict(means=sc_act["means"], quats=sc_act["quats"], scales=t(np.log(sc_np["scales"]).astype(np.float32)),
+              opacities=t(np.log(op_ / (1 - op_)).astype(np.float32)), sh=t(sc_np["sh"][:, :1].copy()),
+              raw=dict(offsets=torch.zeros(N, 3, device=dev), sh_rest=t(sc_np["sh"][:, 1:].copy()) if deg > 0 else None))
     K_sh = (deg + 1) ** 2
     sdf_cfg = dict(n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=2.0,
                    hidden_dim=32 if args.workload == "c1" else 64, n_hidden=1 if args.workload == "c1" else 3)
@@ -286,8 +292,8 @@ def main():
     cams = [S.camera(cam0 + i, W, H) for i in range(n_cams)]
     torch.manual_seed(1234 + rank)  # randns stream
     # ground truth: the same scene rendered with perturbed colours, produced once on the device
-    sc_gt = dict(sc)
-    sc_gt["sh"] = sc["sh"] + 0.1 * torch.randn(sc["sh"].shape, device=dev, generator=torch.Generator(dev).manual_seed(3))
+    sc_gt = dict(sc_act)
+    sc_gt["sh"] = sc_act["sh"] + 0.1 * torch.randn(sc_act["sh"].shape, device=dev, generator=torch.Generator(dev).manual_seed(3))
     gts = []
     randn_buf = torch.empty(N, 2, device=dev)
     for V, Kc in cams:

@@ -94,7 +94,8 @@ class SplatRenderer:
         C, W, H, cap = self.C, self.W, self.H, self.cap
         off, rest = (raw["offsets"], raw["sh_rest"]) if raw else (None, None)
         N, K = self.N, self.K
-        v_sh, v_rest = (self.v_sh.view(-1)[:N * 3].view(N, 1, 3), self.v_sh.view(-1)[N * 3:].view(N, K - 1, 3)) if raw else (self.v_sh, None)
+        v_sh, v_rest = ((self.v_sh.view(-1)[:N * 3].view(N, 1, 3), self.v_sh.view(-1)[N * 3:].view(N, K - 1, 3)) if rest is not None
+                        else (self.v_sh, None))
         self.loss.zero_()
         if zero_grads:
             self.flat_grad.zero_()
