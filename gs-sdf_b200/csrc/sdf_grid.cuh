@@ -150,6 +150,54 @@ __device__ __forceinline__ void encode_level_bwd(const __half2 *__restrict__ tab
     }
 }
 
+// Second-order pass of one (point, level) for the analytic eikonal / align losses (L depends on g = d sdf / d x):
+//   dfeat0/1 : d sdf / d feat of this level (the first backward's input cotangent, fp32 -> half -> x128 like the binding)
+//   cc[3]    : dL / d(dL/dx) in the units of x01 (cotangent of the first backward's input-gradient output)
+// Writes r[2] = (half)(sum_d dy_dx[f][d] * cc[d]) (kernel_grid_backward_input_backward_dLdoutput, grid.h:624-647) and scatters
+// the table gradient of kernel_grid_backward_input_backward_grid (grid.h:352-456): per grad_dim and corner pair
+// (half)(-+ scale * cc[gd] * w) * dL_dy_half, divided by the loss scale (TB/tcnn_binding.cpp:151-192). fp32 vector REDs.
+__device__ __forceinline__ void encode_level_bwd2(const __half2 *__restrict__ table, float *__restrict__ table_grad, const GridGeom &g,
+                                                  int lvl, const float x[3], float dfeat0, float dfeat1, const float cc[3], float r[2]) {
+    const uint32_t hs = g.offset[lvl + 1] - g.offset[lvl];
+    const LevelPos p = level_pos(x, g.scale[lvl]);
+    const __half2 gh = __hmul2(__floats2half2_rn(dfeat0, dfeat1), __float2half2_rn(128.f));
+    const __half2 *t = table + g.offset[lvl];
+    float *tg = table_grad ? table_grad + 2 * (size_t)g.offset[lvl] : nullptr;
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int gd = 0; gd < 3; ++gd) {
+        float acc0 = 0.f, acc1 = 0.f;
+        const float grad_in = g.scale[lvl] * cc[gd];
+#pragma unroll
+        for (int idx = 0; idx < 4; ++idx) {
+            float wd = g.scale[lvl], w = grad_in;  // same multiplication order as grid.h:186-201 (dy_dx) and :430-446 (grid gradient)
+            uint32_t c[3];
+#pragma unroll
+            for (int nd = 0; nd < 2; ++nd) {
+                const int d = nd >= gd ? nd + 1 : nd;
+                if ((idx & (1 << nd)) == 0) { wd *= 1.f - p.pos[d]; w *= 1.f - p.pos[d]; c[d] = p.pg[d]; }
+                else { wd *= p.pos[d]; w *= p.pos[d]; c[d] = p.pg[d] + 1; }
+            }
+            c[gd] = p.pg[gd];
+            const uint32_t il = grid_index(hs, g.res[lvl], c[0], c[1], c[2]);
+            c[gd] = p.pg[gd] + 1;
+            const uint32_t ir = grid_index(hs, g.res[lvl], c[0], c[1], c[2]);
+            const float2 l = __half22float2(__ldg(t + il)), rr = __half22float2(__ldg(t + ir));
+            acc0 += wd * (rr.x - l.x);
+            acc1 += wd * (rr.y - l.y);
+            if (tg) {
+                const float2 vl = __half22float2(__hmul2(__float2half2_rn(-w), gh)), vr = __half22float2(__hmul2(__float2half2_rn(w), gh));
+                if (vl.x != 0.f || vl.y != 0.f) atomicAdd(reinterpret_cast<float2 *>(tg + 2 * (size_t)il), make_float2(vl.x * (1.f / 128.f), vl.y * (1.f / 128.f)));
+                if (vr.x != 0.f || vr.y != 0.f) atomicAdd(reinterpret_cast<float2 *>(tg + 2 * (size_t)ir), make_float2(vr.x * (1.f / 128.f), vr.y * (1.f / 128.f)));
+            }
+        }
+        r0 += acc0 * cc[gd];
+        r1 += acc1 * cc[gd];
+    }
+    r[0] = __half2float(__float2half_rn(r0));
+    r[1] = __half2float(__float2half_rn(r1));
+}
+
 __device__ __forceinline__ void load_x(const gssdf_sdf_net &net, const float *__restrict__ x, int64_t gi, int64_t n, float delta,
                                        float out[3]) {
     const int64_t i = gi % n;

@@ -345,7 +345,7 @@ sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
 // ---------------------------------------------------------------------------------------------
 // backward: persistent, one CTA per SM, 128-point tiles
 // ---------------------------------------------------------------------------------------------
-constexpr size_t kBwdTcSmem = 16 * kGA0 + 3 * 16 * kGA + 16 * kGA + 16 * kGL + kWImg + sizeof(float) * (5 * 64 + 132 + 256 + 384 + 4 * 192) + 1024;
+constexpr size_t kBwdTcSmem = 16 * kGA0 + 3 * 16 * kGA + 16 * kGA + 16 * kGL + kWImg + sizeof(float) * (5 * 64 + 132 + 256 + 384 + 4 * 192 + 1024 + 384) + 1024;
 
 // FUSED = false: gssdf_sdf_bwd (cotangents v_sdf / v_y1 come from memory; evaluation index = variant * n + point).
 // FUSED = true : gssdf_sdf_train (forward -> losses -> backward in one pass, nothing but the gradients leaves the SM). A tile
@@ -355,6 +355,8 @@ struct TcLossArgs {
     const float *gt_sdf, *weights, *visibilities;
     SdfLossCfg cfg;
     float *loss_out;
+    int analytic;        // eikonal on the ANALYTIC gradient d sdf/dx (LocalMap::get_gradient(numerical = false), local_map.cpp:150-171)
+    float align_weight;  // |g_analytic - g_numerical.detach()|.mean() (neural_mapping.cpp:124-133); needs the 7-variant layout
 };
 
 template <bool FUSED>
@@ -373,6 +375,8 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
     float *s_seed = s_wout + 132;                // [128][2] v_sdf, v_y1
     float *s_dx = s_seed + 256;                  // [128][3]
     float *s_col = s_dx + 384;                   // [4 row quarters][192]: column sums (db: 64, dW_out: 128)
+    uint16_t *s_mask16 = reinterpret_cast<uint16_t *>(s_col + 4 * 192);  // [128 rows][4 layers][4 column quarters]: ReLU masks (analytic mode)
+    float *s_gnum = s_col + 4 * 192 + 1024;      // [128][3] numerical gradient of the tile's points (align loss)
     __shared__ __align__(8) uint64_t s_mbar[2];
     __shared__ uint32_t s_tmem;
 
@@ -385,6 +389,12 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
     const unsigned char *wimg = reinterpret_cast<const unsigned char *>(a.net.mlp_packed);
     const int V = max(a.n_variants, 1), PT = FUSED ? TM / V : TM;
     float loss_acc = 0.f;
+    const bool analytic = FUSED && lo.analytic != 0;
+    float acc2_0[4] = {0.f, 0.f, 0.f, 0.f}, acc2[3][8], acc2_wo = 0.f;  // second-order decoder gradients (analytic mode), per thread
+#pragma unroll
+    for (int l = 0; l < 3; ++l)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc2[l][e] = 0.f;
 
     if (warp == 0) {  // TMEM: D (64 columns) + one 64-column weight-gradient accumulator per hidden layer -> 512-column allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(512));
@@ -489,6 +499,12 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
             unsigned char *dst = (l < nh - 1) ? sAct + l * 16 * kGA : sG;
             store8(dst, l < nh - 1 ? sL : nullptr, row, col0, act);
             store8(dst, l < nh - 1 ? sL : nullptr, row, col0 + 8, act + 8);
+            if (analytic) {  // ReLU mask of z_{l+1}: kept until the second-order phase at the end of the tile
+                uint32_t bits = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) bits |= (act[j] > 0.f ? 1u : 0u) << j;
+                s_mask16[(row * 4 + l) * 4 + cq] = (uint16_t)bits;
+            }
             if (FUSED && l == nh - 1) {  // output layer (64 -> 2): this thread's 16-column share of both dot products
                 float p0 = 0.f, p1 = 0.f;
 #pragma unroll
@@ -518,7 +534,17 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
                 const int64_t i = base + tid;
                 float sv[7], v_s[7], v_y;
                 for (int v = 0; v < V; ++v) sv[v] = s_out[2 * (tid * V + v)];
-                loss_acc += sdf_point_loss(lo.cfg, (float)n_live, V, sv, s_out[2 * tid * V + 1], lo.gt_sdf != nullptr,
+                SdfLossCfg cfg1 = lo.cfg;
+                if (analytic) {  // the eikonal / align terms act on the analytic gradient: second-order phase below
+                    cfg1.eikonal_weight = 0.f;
+                    if (V == 7) {
+                        const float inv2d = 0.5f / lo.cfg.delta;
+                        s_gnum[tid * 3 + 0] = (sv[1] - sv[2]) * inv2d;
+                        s_gnum[tid * 3 + 1] = (sv[3] - sv[4]) * inv2d;
+                        s_gnum[tid * 3 + 2] = (sv[5] - sv[6]) * inv2d;
+                    }
+                }
+                loss_acc += sdf_point_loss(cfg1, (float)n_live, V, sv, s_out[2 * tid * V + 1], lo.gt_sdf != nullptr,
                                            lo.gt_sdf ? __ldg(lo.gt_sdf + i) : 0.f, lo.weights != nullptr, lo.weights ? __ldg(lo.weights + i) : 0.f,
                                            lo.visibilities != nullptr, lo.visibilities ? __ldg(lo.visibilities + i) : 0.f, v_s, v_y);
                 for (int v = 0; v < V; ++v) s_seed[2 * (tid * V + v)] = v_s[v];
@@ -663,6 +689,175 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
                     if (base + e / 3 < n_live) a.v_x[base * 3 + e] = s_dx[e] * sc;
             }
         }
+        if (analytic) {
+            // ---- 5b. second-order phase (CUDA cores; every operand buffer of the tile is idle now): gradient of the eikonal / align
+            //      losses, which are functions of g = d sdf / d x, w.r.t. decoder and table. Chains over the base rows:
+            //        u_nh = D_nh (.) w_out[0]; u_l = D_l (.) W_l^T u_{l+1}; dfeat = W_0^T u_1          (first backward, seed e_sdf)
+            //        g = dy_dx^T half(dfeat) (tcnn rounding points); c = dL/dg; r = half(dy_dx c)
+            //        q_1 = D_1 (.) W_0 r; q_{l+1} = D_{l+1} (.) W_l q_l                               (forward-like)
+            //        dL/dW_0 += u_1 (x) r; dL/dW_l += u_{l+1} (x) q_l; dL/dw_out[0] += q_nh; table: encode_level_bwd2
+            constexpr int CH = 32;
+            float *sW2 = reinterpret_cast<float *>(s_tc);  // [64][65]
+            float *sU = sW2 + 64 * 65;                     // [CH][4][64]  u_l at slot l - 1
+            float *sQ0 = sU + CH * 4 * 64, *sQ1 = sQ0 + CH * 64;  // [CH][64] ping / pong
+            float *sR = sQ1 + CH * 64, *sDf = sR + CH * 32;       // [CH][32]
+            float *sGx = sDf + CH * 32, *sCc = sGx + CH * 3;      // [CH][3]
+            const float isz = a.net.inv_size != 0.f ? a.net.inv_size : 1.f;
+            const float *Wg = a.net.mlp;
+            auto w_of = [&](int l) { return Wg + (l == 0 ? 0 : (size_t)HID * kFeat + HID + (size_t)(l - 1) * (HID * HID + HID)); };
+            auto mask_of = [&](int j, int l, int k) -> bool {  // ReLU'(z_l)[k] of base row j of the chunk, l = 1..nh
+                return (s_mask16[((j * V) * 4 + (l - 1)) * 4 + (k >> 4)] >> (k & 15)) & 1;
+            };
+            const int n_pts = (int)min((int64_t)PT, n_live - base);
+            for (int c0 = 0; c0 < n_pts; c0 += CH) {
+                const int nj = min(CH, n_pts - c0);
+                __syncthreads();
+                // (i) u_nh
+                for (int e = tid; e < CH * 64; e += NT) {
+                    const int j = e >> 6, k = e & 63;
+                    sU[(j * 4 + nh - 1) * 64 + k] = (j < nj && mask_of(c0 + j, nh, k)) ? s_wout[k] : 0.f;
+                }
+                // (ii) u_l, l = nh-1 .. 1
+                for (int l = nh - 1; l >= 1; --l) {
+                    __syncthreads();
+                    const float *W = w_of(l);
+                    for (int e = tid; e < 64 * 64; e += NT) sW2[(e >> 6) * 65 + (e & 63)] = __ldg(W + e);
+                    __syncthreads();
+                    const int k = tid & 63, jg = tid >> 6;
+#pragma unroll
+                    for (int jj = 0; jj < CH / 8; ++jj) {
+                        const int j = jg + 8 * jj;
+                        float sacc = 0.f;
+                        const float *un = sU + (j * 4 + l) * 64;
+#pragma unroll 8
+                        for (int o = 0; o < 64; ++o) sacc = fmaf(sW2[o * 65 + k], un[o], sacc);
+                        sU[(j * 4 + l - 1) * 64 + k] = (j < nj && mask_of(c0 + j, l, k)) ? sacc : 0.f;
+                    }
+                }
+                // (iii) dfeat = W_0^T u_1 ; W_0 [64][32] stays staged (stride 33) until q_1 is done
+                __syncthreads();
+                for (int e = tid; e < 64 * kFeat; e += NT) sW2[(e >> 5) * 33 + (e & 31)] = __ldg(Wg + e);
+                for (int e = tid; e < CH * 3; e += NT) sGx[e] = 0.f;
+                __syncthreads();
+                {
+                    const int k = tid & 31, jg = tid >> 5;
+#pragma unroll
+                    for (int jj = 0; jj < CH / 16; ++jj) {
+                        const int j = jg + 16 * jj;
+                        float sacc = 0.f;
+                        const float *un = sU + (j * 4 + 0) * 64;
+#pragma unroll 8
+                        for (int o = 0; o < 64; ++o) sacc = fmaf(sW2[o * 33 + k], un[o], sacc);
+                        sDf[j * 32 + k] = sacc;
+                    }
+                }
+                __syncthreads();
+                // (iv) pass A: g (x01 units) = sum over levels of the tcnn input gradient with cotangent dfeat
+                for (int task = tid; task < CH * kLevels; task += NT) {
+                    const int j = task % CH, lvl = task / CH;
+                    if (j < nj) {
+                        float x[3], dx[3] = {0.f, 0.f, 0.f};
+                        load_x(a.net, a.x, row_gi((c0 + j) * V), a.n, a.delta, x);
+                        encode_level_bwd(table, nullptr, g, lvl, x, sDf[j * 32 + 2 * lvl], sDf[j * 32 + 2 * lvl + 1], true, dx);
+                        atomicAdd(&sGx[j * 3 + 0], dx[0]);
+                        atomicAdd(&sGx[j * 3 + 1], dx[1]);
+                        atomicAdd(&sGx[j * 3 + 2], dx[2]);
+                    }
+                }
+                __syncthreads();
+                // (v) losses on the analytic gradient (world units) and their cotangent
+                if (tid < CH) {
+                    float cc[3] = {0.f, 0.f, 0.f};
+                    if (tid < nj) {
+                        const float gx = sGx[tid * 3] * isz, gy = sGx[tid * 3 + 1] * isz, gz = sGx[tid * 3 + 2] * isz;
+                        const float nl = (float)n_live;
+                        const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
+                        const float we = lo.cfg.eikonal_weight / nl;
+                        loss_acc += we * (nrm - 1.f) * (nrm - 1.f);
+                        const float ke = nrm > 0.f ? 2.f * (nrm - 1.f) / nrm * we : 0.f;
+                        cc[0] = ke * gx; cc[1] = ke * gy; cc[2] = ke * gz;
+                        if (lo.align_weight > 0.f && V == 7) {
+                            const float wa = lo.align_weight / (3.f * nl);
+                            const float *gn = s_gnum + (c0 + tid) * 3;
+                            const float d0 = gx - gn[0], d1 = gy - gn[1], d2 = gz - gn[2];
+                            loss_acc += wa * (fabsf(d0) + fabsf(d1) + fabsf(d2));
+                            cc[0] += d0 > 0.f ? wa : (d0 < 0.f ? -wa : 0.f);
+                            cc[1] += d1 > 0.f ? wa : (d1 < 0.f ? -wa : 0.f);
+                            cc[2] += d2 > 0.f ? wa : (d2 < 0.f ? -wa : 0.f);
+                        }
+                    }
+                    sCc[tid * 3] = cc[0] * isz; sCc[tid * 3 + 1] = cc[1] * isz; sCc[tid * 3 + 2] = cc[2] * isz;  // -> x01 units
+                }
+                __syncthreads();
+                // (vi) pass B: r = half(dy_dx c) and the second-order table gradient
+                for (int task = tid; task < CH * kLevels; task += NT) {
+                    const int j = task % CH, lvl = task / CH;
+                    float r[2] = {0.f, 0.f};
+                    if (j < nj) {
+                        float x[3];
+                        load_x(a.net, a.x, row_gi((c0 + j) * V), a.n, a.delta, x);
+                        encode_level_bwd2(table, a.table_grad, g, lvl, x, sDf[j * 32 + 2 * lvl], sDf[j * 32 + 2 * lvl + 1], sCc + j * 3, r);
+                    }
+                    sR[j * 32 + 2 * lvl] = r[0];
+                    sR[j * 32 + 2 * lvl + 1] = r[1];
+                }
+                __syncthreads();
+                // (vii) q-chain and the decoder's second-order gradients
+                {   // q_1 = D_1 (.) W_0 r ;  dL/dW_0[o][k] += u_1[o] r[k]
+                    const int o = tid & 63, jg = tid >> 6;
+#pragma unroll
+                    for (int jj = 0; jj < CH / 8; ++jj) {
+                        const int j = jg + 8 * jj;
+                        float sacc = 0.f;
+#pragma unroll 8
+                        for (int k = 0; k < kFeat; ++k) sacc = fmaf(sW2[o * 33 + k], sR[j * 32 + k], sacc);
+                        sQ0[j * 64 + o] = (j < nj && mask_of(c0 + j, 1, o)) ? sacc : 0.f;
+                    }
+                    if (a.mlp_grad) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int idx = tid + e * NT, oo = idx >> 5, kk = idx & 31;
+                            float sacc = 0.f;
+                            for (int j = 0; j < nj; ++j) sacc = fmaf(sU[(j * 4 + 0) * 64 + oo], sR[j * 32 + kk], sacc);
+                            acc2_0[e] += sacc;
+                        }
+                    }
+                }
+                float *qc = sQ0, *qn = sQ1;
+                for (int l = 1; l < nh; ++l) {
+                    __syncthreads();
+                    const float *W = w_of(l);
+                    for (int e = tid; e < 64 * 64; e += NT) sW2[(e >> 6) * 65 + (e & 63)] = __ldg(W + e);
+                    __syncthreads();
+                    const int o = tid & 63, jg = tid >> 6;
+#pragma unroll
+                    for (int jj = 0; jj < CH / 8; ++jj) {
+                        const int j = jg + 8 * jj;
+                        float sacc = 0.f;
+#pragma unroll 8
+                        for (int k = 0; k < 64; ++k) sacc = fmaf(sW2[o * 65 + k], qc[j * 64 + k], sacc);
+                        qn[j * 64 + o] = (j < nj && mask_of(c0 + j, l + 1, o)) ? sacc : 0.f;
+                    }
+                    if (a.mlp_grad) {  // dL/dW_l[o][k] += u_{l+1}[o] q_l[k]
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int idx = tid + e * NT, oo = idx >> 6, kk = idx & 63;
+                            float sacc = 0.f;
+                            for (int j = 0; j < nj; ++j) sacc = fmaf(sU[(j * 4 + l) * 64 + oo], qc[j * 64 + kk], sacc);
+                            acc2[l - 1][e] += sacc;
+                        }
+                    }
+                    float *t2 = qc; qc = qn; qn = t2;
+                }
+                __syncthreads();
+                if (a.mlp_grad && tid < 64) {  // dL/dw_out[0][k] += q_nh[k]
+                    float sacc = 0.f;
+                    for (int j = 0; j < nj; ++j) sacc += qc[j * 64 + tid];
+                    acc2_wo += sacc;
+                }
+            }
+            __syncthreads();
+        }
         first_tile = false;
 #undef LIVE_TC
     }
@@ -691,6 +886,18 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
         if (tid < HID) atomicAdd(G + tid, dwo0);
         else if (tid < 2 * HID) atomicAdd(G + tid, dwo1);
         else if (tid < 2 * HID + 2) atomicAdd(G + tid, dbo);
+    }
+    if (analytic && ok && a.mlp_grad) {  // second-order decoder gradients (no bias terms)
+        float *G = a.mlp_grad;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) atomicAdd(G + tid + e * NT, acc2_0[e]);  // W_0 [64][32]: index o * 32 + k == tid + e * NT
+        G += (size_t)HID * kFeat + HID;
+        for (int l = 1; l < nh; ++l) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(G + tid + e * NT, acc2[l - 1][e]);
+            G += (size_t)HID * HID + HID;
+        }
+        if (tid < 64) atomicAdd(G + tid, acc2_wo);
     }
     if (FUSED && lo.loss_out) {
         loss_acc = warp_sum(loss_acc);
@@ -778,7 +985,12 @@ extern "C" int gssdf_sdf_train(const gssdf_sdf_train_args *t, gssdf_stream_t str
     a.net = t->net; a.n = t->n; a.x = t->x; a.n_variants = t->n_variants; a.delta = t->delta; a.n_live = t->n_live;
     a.table_grad = t->table_grad; a.mlp_grad = t->mlp_grad; a.v_x = t->v_x;
     TcLossArgs lo{t->gt_sdf, t->weights, t->visibilities,
-                  SdfLossCfg{t->bce_isigma, t->bce_weight, t->eikonal_weight, t->gs_sdf_weight, t->delta, t->visible_thr}, t->loss_out};
+                  SdfLossCfg{t->bce_isigma, t->bce_weight, t->eikonal_weight, t->gs_sdf_weight, t->delta, t->visible_thr}, t->loss_out,
+                  t->eikonal_mode, t->align_weight};
+    GSSDF_REQUIRE(t->eikonal_mode == 0 || t->eikonal_mode == 1, GSSDF_EINVAL, "sdf_train: eikonal_mode must be 0 or 1");
+    GSSDF_REQUIRE(!(t->eikonal_mode == 1 && t->align_weight > 0.f) || t->n_variants == 7, GSSDF_EINVAL,
+                  "sdf_train: the align loss needs n_variants 7 (numerical gradient)");
+    GSSDF_REQUIRE(t->eikonal_mode == 1 || t->align_weight == 0.f, GSSDF_EINVAL, "sdf_train: align_weight needs eikonal_mode 1");
     const GridGeom g = make_grid(t->net);
     GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdTcSmem));
     const int pt = 128 / t->n_variants;

@@ -49,7 +49,7 @@ const char *gssdf_last_error(void);
 /* "gssdf_b200 <ver> sm_100a" */
 const char *gssdf_version(void);
 /* Argument structs grow between revisions: a binding compiled against this header must see the same number from the library. */
-#define GSSDF_ABI_REVISION 6
+#define GSSDF_ABI_REVISION 7
 int32_t gssdf_abi_revision(void);
 
 /* Device-side counters shared by the stages of one render. Zeroed by gssdf_project2dgs_fwd. */
@@ -466,6 +466,15 @@ typedef struct gssdf_sdf_train_args {
     float *table_grad;       /* [table_params] fp32 += or NULL; 8-byte aligned */
     float *mlp_grad;         /* [mlp_params]  fp32 += or NULL */
     float *v_x;              /* [n,3] overwritten (rows < n_live) or NULL */
+    int32_t eikonal_mode;    /* 0: eikonal on the 6-offset NUMERICAL gradient (k_numerical_grad branch, local_map.cpp:110-133; needs
+                                   n_variants 7).
+                                1: the reference default (config/base.yaml:13 numerical_grad: 0): eikonal on the ANALYTIC gradient
+                                   d sdf/dx obtained by back-propagating through decoder + encoding (local_map.cpp:150-171), whose own
+                                   gradient w.r.t. decoder / table is the double backward of tcnn_binding
+                                   (TB/tcnn_binding.cpp:151-192, grid.h:352-456,624-647). x carries no gradient from these terms
+                                   (both call sites pass detached points, neural_mapping.cpp:183,450). */
+    float align_weight;      /* mode 1 only: + align_weight * mean |g_analytic - g_numerical.detach()| (neural_mapping.cpp:124-133);
+                                needs n_variants 7 (the six offsets are evaluated forward-only); 0 disables it */
 } gssdf_sdf_train_args;
 int gssdf_sdf_train(const gssdf_sdf_train_args *a, gssdf_stream_t stream);
 

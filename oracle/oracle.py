@@ -275,6 +275,83 @@ def sdf_bwd(x, table, mlp_params, v_sdf, v_y1, hidden=64, n_hidden=3, **grid):
     return tg, d_mlp, dx
 
 
+def set_half_rounding(on):
+    """Test hook: switch the fp16 rounding points of the SDF oracle off to finite-difference the restated math."""
+    lib().oracle_set_half_rounding(C.c_int(1 if on else 0))
+
+
+def grid_corner_indices(x, L=16, F=2, log2_hashmap=19, base_res=32, per_level_scale=2.0):
+    x = _f32(x)
+    out = np.zeros((x.shape[0], L, 8), np.int64)
+    lib().oracle_grid_corner_indices(C.c_int64(x.shape[0]), _p(x), C.c_int(L), C.c_int(F), C.c_int(log2_hashmap), C.c_int(base_res),
+                                     C.c_float(per_level_scale), _p(out))
+    return out
+
+
+def hashgrid_bwd_bwd(x, dL_ddLdx, dL_dy, n_params, dy_dx, L=16, F=2, log2_hashmap=19, base_res=32, per_level_scale=2.0):
+    x, c, g, dy = _f32(x), _f32(dL_ddLdx), _f32(dL_dy), _f32(dy_dx)
+    n = x.shape[0]
+    tg = np.zeros(n_params, np.float64)
+    r = np.zeros((n, L * F), np.float32)
+    lib().oracle_hashgrid_bwd_bwd(C.c_int64(n), _p(x), _p(c), _p(g), C.c_int(L), C.c_int(F), C.c_int(log2_hashmap), C.c_int(base_res),
+                                  C.c_float(per_level_scale), _p(dy), _p(tg), _p(r))
+    return tg, r
+
+
+def _mlp_layers(mlp_params, widths):
+    Ws, bs, o = [], [], 0
+    p = np.asarray(mlp_params, np.float64)
+    for k, q in zip(widths[:-1], widths[1:]):
+        Ws.append(p[o:o + q * k].reshape(q, k)); o += q * k
+        bs.append(p[o:o + q]); o += q
+    return Ws, bs
+
+
+def sdf_grad_analytic(x, table, mlp_params, hidden=64, n_hidden=3, **grid):
+    """g = d sdf / d x through decoder + encoding, exactly as the autograd graph of LocalMap::get_gradient(numerical=false)
+    builds it (local_map.cpp:150-171): fp32/fp64 decoder backward, then the tcnn input gradient with its fp16 rounding points
+    (dL/dy -> half, x128, kernel_grid_backward_input grid.h:323-349). Returns g [n,3] (x in [0,1]^3 units)."""
+    n = len(x)
+    return sdf_bwd(x, table, mlp_params, np.ones(n, np.float32), np.zeros(n, np.float32), hidden, n_hidden, **grid)[2]
+
+
+def sdf_grad_analytic_bwd(x, table, mlp_params, c, hidden=64, n_hidden=3, **grid):
+    """Double backward: given c = dL/dg [n,3] (g from sdf_grad_analytic) return (table_grad, mlp_grad) = dL/d(table), dL/d(decoder).
+    Chain (TB/tcnn_binding.cpp:151-192 + torch autograd of the Linear/ReLU stack):
+      m_l : the first backward's chain with seed w_out[0]     (d sdf / d a_l, masked)     -> dfeat = W_0^T m_1
+      r   = half(dy_dx . c)                                   (grid.h:624-647)           -> cotangent of dfeat
+      q_l : forward-like chain  q_1 = D_1 (W_0 r), q_{l+1} = D_{l+1} (W_l q_l)
+      dL/dW_0 = m_1 (x) r, dL/dW_l = m_{l+1} (x) q_l, dL/dw_out[0] = q_last; biases get nothing;
+      table: kernel_grid_backward_input_backward_grid with dL_dy = dfeat (grid.h:352-456)."""
+    x = _f32(x)
+    n = len(x)
+    feat, dy = hashgrid_fwd(x, table, want_dy_dx=True, **grid)
+    widths = [feat.shape[1]] + [hidden] * (1 + n_hidden) + [2]
+    Ws, bs = _mlp_layers(mlp_params, widths)
+    nl = len(Ws) - 1  # hidden layers (with ReLU)
+    a, masks = feat.astype(np.float64), []
+    for l in range(nl):
+        z = a @ Ws[l].T + bs[l]
+        masks.append(z > 0)
+        a = np.maximum(z, 0)
+    m = [None] * (nl + 1)  # m[l], l = 1..nl : d sdf / d z_l
+    m[nl] = masks[nl - 1] * Ws[nl][0][None, :]
+    for l in range(nl - 1, 0, -1):
+        m[l] = masks[l - 1] * (m[l + 1] @ Ws[l])
+    dfeat = (m[1] @ Ws[0]).astype(np.float32)
+    tg, r = hashgrid_bwd_bwd(x, c, dfeat, len(table), dy, **grid)
+    r = r.astype(np.float64)
+    grads = []
+    q = r
+    for l in range(nl):
+        grads.append((m[l + 1].T @ q, np.zeros(widths[l + 1])))  # dW_l [out,in], db_l = 0
+        q = masks[l] * (q @ Ws[l].T)
+    gw_out = np.zeros_like(Ws[nl])
+    gw_out[0] = q.sum(0)
+    grads.append((gw_out, np.zeros(2)))
+    return tg, np.concatenate([np.concatenate([gw.ravel(), gb]) for gw, gb in grads])
+
+
 def sdf_losses(sdf, y1, n, n_variants, gt_sdf=None, weights=None, bce_isigma=1.0, bce_weight=1.0, eikonal_weight=0.1,
                gs_sdf_weight=1e-3, delta=0.05):
     """numpy (fp64) restatement of loss::sdf_loss / eikonal_loss / gs_sdf_loss (include/optimizer/loss.cpp:7-11,49-83) with the

@@ -52,7 +52,9 @@ static double h_to_f64(uint16_t h) {
     else v = ldexp(1.0 + man / 1024.0, exp - 15);
     return sign ? -v : v;
 }
-static double rh(double d) { return h_to_f64(f64_to_h(d)); } /* round a real to binary16 */
+static int g_half_rounding = 1; /* tests of the restated MATH (finite differences) switch the fp16 rounding points off */
+void oracle_set_half_rounding(int on) { g_half_rounding = on; }
+static double rh(double d) { return g_half_rounding ? h_to_f64(f64_to_h(d)) : d; } /* round a real to binary16 */
 
 void oracle_f32_to_f16_bits(int64_t n, const float *x, uint16_t *out) {
     for (int64_t i = 0; i < n; ++i) out[i] = f64_to_h((double)x[i]);
@@ -201,6 +203,89 @@ void oracle_hashgrid_bwd(int64_t n, const float *x, const float *dL_dfeat, int L
         if (dL_dx)
             for (int d = 0; d < 3; ++d) dL_dx[3 * i + d] = dx[d] / (float)loss_scale;
     }
+}
+
+/* Double backward of the encoding w.r.t. the TABLE (the eikonal / align losses are functions of the analytic gradient
+ * dsdf/dx): restates kernel_grid_backward_input_backward_grid (grid.h:352-456) as driven by
+ * TCNNModuleFunctionBackward::backward (TB/tcnn_binding.cpp:151-192).
+ *   dL_ddLdx[n,3] : cotangent of the first backward's dL/dx output (fp32)
+ *   dL_dy[n,L*F]  : the first backward's INPUT cotangent (fp32; rounded to half and x128 in half like the binding does)
+ * table_grad (fp64, accumulated): sum over grad_dim, the 4 corner pairs: (half)(+-weight) * dL_dy_half, / 128.
+ * Also returns dL_ddLdy[n,L*F] = (half)(sum_d dy_dx[k][d] * dL_ddLdx[d]) (kernel_grid_backward_input_backward_dLdoutput,
+ * grid.h:624-647) as fp32 values: the cotangent that flows back into the decoder's backward graph. */
+void oracle_hashgrid_bwd_bwd(int64_t n, const float *x, const float *dL_ddLdx, const float *dL_dy, int L, int F, int log2_hashmap,
+                             int base_res, float per_level_scale, const float *dy_dx, double *table_grad, float *dL_ddLdy) {
+    uint32_t off[33];
+    oracle_grid_setup(L, F, log2_hashmap, base_res, per_level_scale, off);
+    float l2 = log2f(per_level_scale);
+    const double loss_scale = 128.0;
+    for (int64_t i = 0; i < n; ++i) {
+        for (int lvl = 0; lvl < L; ++lvl) {
+            uint32_t hs = off[lvl + 1] - off[lvl];
+            float scale = grid_scale(lvl, l2, base_res);
+            uint32_t res = grid_resolution(scale);
+            float pos[3];
+            uint32_t pg[3];
+            for (int d = 0; d < 3; ++d) {
+                pos[d] = fmaf(scale, x[3 * i + d], 0.5f);
+                float tmp = floorf(pos[d]);
+                pg[d] = (uint32_t)(int)tmp;
+                pos[d] -= tmp;
+            }
+            double gh[8];
+            for (int f = 0; f < F; ++f) gh[f] = rh(rh((double)dL_dy[i * L * F + lvl * F + f]) * loss_scale);
+            if (table_grad)
+                for (int gd = 0; gd < 3; ++gd) {
+                    float grad_in = scale * dL_ddLdx[3 * i + gd] * 1.0f; /* pos_derivative == 1 (Linear) */
+                    for (int idx = 0; idx < 4; ++idx) {
+                        float w = grad_in;
+                        uint32_t pl[3];
+                        for (int nd = 0; nd < 2; ++nd) {
+                            int d = nd >= gd ? nd + 1 : nd;
+                            if ((idx & (1 << nd)) == 0) { w *= 1 - pos[d]; pl[d] = pg[d]; }
+                            else { w *= pos[d]; pl[d] = pg[d] + 1; }
+                        }
+                        pl[gd] = pg[gd];
+                        uint32_t il = grid_index(hs, res, pl) * F;
+                        pl[gd] = pg[gd] + 1;
+                        uint32_t ir = grid_index(hs, res, pl) * F;
+                        double wl = rh((double)-w), wr = rh((double)w);
+                        for (int f = 0; f < F; ++f) {
+                            table_grad[(size_t)off[lvl] * F + il + f] += rh(wl * gh[f]) / loss_scale;
+                            table_grad[(size_t)off[lvl] * F + ir + f] += rh(wr * gh[f]) / loss_scale;
+                        }
+                    }
+                }
+            if (dL_ddLdy)
+                for (int f = 0; f < F; ++f) {
+                    float r = 0;
+                    for (int d = 0; d < 3; ++d) r += dy_dx[((i * L + lvl) * F + f) * 3 + d] * dL_ddLdx[3 * i + d];
+                    dL_ddLdy[i * L * F + lvl * F + f] = (float)rh((double)r);
+                }
+        }
+    }
+}
+
+/* Test helper: parameter index (entry * F, i.e. of feature 0) of the 8 interpolation corners of every (point, level), in the corner
+ * order idx = 0..7 (bit d set -> +1 along dimension d) used by the kernels above. */
+void oracle_grid_corner_indices(int64_t n, const float *x, int L, int F, int log2_hashmap, int base_res, float per_level_scale,
+                                int64_t *out /* [n, L, 8] */) {
+    uint32_t off[33];
+    oracle_grid_setup(L, F, log2_hashmap, base_res, per_level_scale, off);
+    float l2 = log2f(per_level_scale);
+    for (int64_t i = 0; i < n; ++i)
+        for (int lvl = 0; lvl < L; ++lvl) {
+            uint32_t hs = off[lvl + 1] - off[lvl];
+            float scale = grid_scale(lvl, l2, base_res);
+            uint32_t res = grid_resolution(scale);
+            uint32_t pg[3];
+            for (int d = 0; d < 3; ++d) pg[d] = (uint32_t)(int)floorf(fmaf(scale, x[3 * i + d], 0.5f));
+            for (int idx = 0; idx < 8; ++idx) {
+                uint32_t pl[3];
+                for (int d = 0; d < 3; ++d) pl[d] = pg[d] + ((idx >> d) & 1);
+                out[(i * L + lvl) * 8 + idx] = ((int64_t)off[lvl] + grid_index(hs, res, pl)) * F;
+            }
+        }
 }
 
 /* ---- decoder MLP (local_map.cpp:29-42): widths[0..nl], fp64 arithmetic (the reference runs fp32 cuBLAS) ---- */

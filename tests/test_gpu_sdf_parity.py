@@ -324,3 +324,56 @@ def test_full_step_tensor_core_equals_cuda_core_path():
         assert float(x.abs().max()) > 0
         rel = float((x - y).norm() / x.norm())
         assert rel <= tol, f"{k}: {rel:.2e}"
+
+
+@pytest.mark.parametrize("align_w,n", [(0.1, 1500), (0.0, 1500)])
+def test_sdf_train_analytic_eikonal_double_backward(oracle, align_w, n):
+    """eikonal_mode 1 (the reference default): eikonal + align losses on the ANALYTIC gradient d sdf/dx and their double backward
+    to decoder / table, against the oracle chain (pinned to torch.autograd in tests/test_sdf_oracle.py) with tcnn's fp16
+    rounding points (dL/dy -> half x128, half corner products, half dL_ddLdy)."""
+    from gssdf_b200 import cabi
+    dev = _dev()
+    n_hidden, V, delta = 3, 7, 0.01
+    rng = np.random.default_rng(31)
+    n_params, _ = oracle.grid_setup()
+    table = rng.uniform(-2e-3, 2e-3, n_params).astype(np.float32)
+    mlp = _mlp(rng, 64, n_hidden)
+    x = rng.uniform(0.05, 0.95, (n, 3)).astype(np.float32)
+    gt = rng.uniform(-0.1, 0.1, n).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    tab, half, mlp_t, xt = t(table), torch.empty(n_params, dtype=torch.float16, device=dev), t(mlp), t(x)
+    cabi.sdf_table_to_half(tab, half)
+    net = _tc_net(cabi, half, mlp_t, n_hidden)
+    isg, bce_w, eik_w = 10.0, 1.0, 0.1
+    # ---- oracle
+    offs = np.array([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float32) * np.float32(delta)
+    pts = (x[None] + offs[:, None]).reshape(-1, 3).astype(np.float32)
+    r_sdf, r_y1, r_feat = oracle.sdf_fwd(pts, table, mlp, 64, n_hidden)
+    tie = _relu_ties(r_feat[:n], mlp, 64, n_hidden)  # base rows only take part in any backward
+    keep = ~tie
+    l1, v_s, v_y = oracle.sdf_losses(r_sdf, r_y1, n, 7, gt_sdf=gt, bce_isigma=isg, bce_weight=bce_w, eikonal_weight=0.0, delta=delta)
+    tg1, mg1, _ = oracle.sdf_bwd(pts, table, mlp, v_s.reshape(-1).astype(np.float32), v_y.reshape(-1).astype(np.float32), 64, n_hidden)
+    g = oracle.sdf_grad_analytic(x, table, mlp, 64, n_hidden).astype(np.float64)
+    s7 = r_sdf.reshape(7, n).astype(np.float64)
+    gnum = np.stack([s7[1] - s7[2], s7[3] - s7[4], s7[5] - s7[6]], 1) * (0.5 / delta)
+    nrm = np.linalg.norm(g, axis=1)
+    l2 = eik_w * np.mean((nrm - 1) ** 2) + align_w * np.mean(np.abs(g - gnum))
+    c = (eik_w / n) * (2 * (nrm - 1) / nrm)[:, None] * g + (align_w / (3 * n)) * np.sign(g - gnum)
+    tg2, mg2 = oracle.sdf_grad_analytic_bwd(x, table, mlp, c.astype(np.float32), 64, n_hidden)
+    # ---- GPU (ties cannot be removed from the analytic path by zeroing cotangents, so compare with a flip allowance instead)
+    loss = torch.zeros(1, device=dev)
+    tg, mg = torch.zeros(n_params, device=dev), torch.zeros(len(mlp), device=dev)
+    cabi.sdf_train(net, xt, V, delta, t(gt), None, isg, bce_w, eik_w, 0.0, loss, tg, mg, None, eikonal_mode=1, align_weight=align_w)
+    torch.cuda.synchronize()
+    assert keep.mean() > 0.98
+    assert abs(float(loss) - (l1 + l2)) <= 2e-3 * abs(l1 + l2), (float(loss), l1, l2)
+    r_mg, r_tg = mg1 + mg2, tg1 + tg2
+    mgc, tgc = mg.cpu().numpy().astype(np.float64), tg.cpu().numpy().astype(np.float64)
+    assert np.linalg.norm(mg2) > 1e-3 * np.linalg.norm(mg1)  # the second-order part is a visible share of the reference gradient
+    e_m, e_t = np.linalg.norm(mgc - r_mg) / np.linalg.norm(r_mg), np.linalg.norm(tgc - r_tg) / np.linalg.norm(r_tg)
+    assert e_m <= 2e-2, f"mlp grad {e_m:.2e}"
+    assert e_t <= 2e-2, f"table grad {e_t:.2e}"
+    # the second-order share alone (first-order part removed with the oracle's value)
+    e_m2 = np.linalg.norm((mgc - mg1) - mg2) / np.linalg.norm(mg2)
+    e_t2 = np.linalg.norm((tgc - tg1) - tg2) / np.linalg.norm(tg2)
+    assert e_m2 <= 5e-2 and e_t2 <= 5e-2, (e_m2, e_t2)

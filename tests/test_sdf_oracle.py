@@ -99,3 +99,62 @@ def test_sdf_chain_table_gradient(oracle):
         seg = per_level[off[lvl]:off[lvl + 1]].sum(0)
         np.testing.assert_allclose(seg, d_feat[:, 2 * lvl:2 * lvl + 2].sum(0), rtol=3e-3, atol=3e-4)  # fp16 rounding of w and g
     assert (tg != 0).sum() <= 200 * 16 * 8 * 2 and np.isfinite(dx).all() and np.abs(dx).max() > 0
+
+
+def test_analytic_gradient_double_backward_matches_torch_autograd(oracle):
+    """The closed-form chains of oracle.sdf_grad_analytic(_bwd) (first backward seeded with w_out[0]; r = dy_dx . c; forward-like
+    q-chain; outer products; kernel_grid_backward_input_backward_grid) against torch.autograd double backward of an independent
+    fp64 torch restatement (trilinear grid lookup + Linear/ReLU stack). fp16 rounding points switched off for this check."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(0)
+    n_params, _ = oracle.grid_setup()
+    table = rng.uniform(-1e-2, 1e-2, n_params).astype(np.float32)
+    dims, ps = [32, 64, 64, 64, 64, 2], []
+    for k, o in zip(dims[:-1], dims[1:]):
+        b = 1 / np.sqrt(k)
+        ps += [rng.uniform(-b, b, o * k), rng.uniform(-b, b, o)]
+    mlp = np.concatenate(ps).astype(np.float32)
+    n = 64
+    x = rng.uniform(0.05, 0.95, (n, 3)).astype(np.float32)
+    c = rng.standard_normal((n, 3)).astype(np.float32)
+    oracle.set_half_rounding(False)
+    try:
+        g = oracle.sdf_grad_analytic(x, table, mlp)
+        tg, mg = oracle.sdf_grad_analytic_bwd(x, table, mlp, c)
+    finally:
+        oracle.set_half_rounding(True)
+    # torch restatement
+    idx = torch.from_numpy(oracle.grid_corner_indices(x))  # [n,16,8]
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    tab = torch.tensor(table, dtype=torch.float64, requires_grad=True)
+    par = torch.tensor(mlp, dtype=torch.float64, requires_grad=True)
+    feats = []
+    for lvl in range(16):
+        scale = float(np.float32(np.exp2(np.float32(lvl)) * 32 - 1))
+        # the kernels compute pos = fmaf(scale, x, 0.5) in fp32 (one rounding): at the fine levels the fractional part keeps only
+        # a few bits, so the torch restatement must start from the same fp32 value (derivative: scale)
+        pos32 = (np.float64(np.float32(scale)) * x.astype(np.float64) + 0.5).astype(np.float32)
+        fr0 = torch.tensor((pos32 - np.floor(pos32)).astype(np.float64))
+        fr = fr0 + (xt - xt.detach()) * scale
+        f = 0
+        for corner in range(8):
+            w = 1
+            for d in range(3):
+                w = w * (fr[:, d] if (corner >> d) & 1 else 1 - fr[:, d])
+            e = idx[:, lvl, corner]
+            f = f + w[:, None] * torch.stack([tab[e], tab[e + 1]], 1)
+        feats.append(f)
+    a, o = torch.cat(feats, 1), 0
+    for li, (k, q) in enumerate(zip(dims[:-1], dims[1:])):
+        W, b = par[o:o + q * k].view(q, k), par[o + q * k:o + q * k + q]
+        o += q * k + q
+        a = a @ W.T + b
+        if li < len(dims) - 2:
+            a = torch.relu(a)
+    sdf = a[:, 0]
+    (gt,) = torch.autograd.grad(sdf.sum(), xt, create_graph=True)
+    assert np.allclose(gt.detach().numpy(), g, rtol=2e-4, atol=2e-4 * np.abs(g).max())
+    (gt * torch.tensor(c, dtype=torch.float64)).sum().backward()
+    r_mg, r_tg = par.grad.numpy(), tab.grad.numpy()
+    assert np.linalg.norm(mg - r_mg) <= 1e-4 * np.linalg.norm(r_mg), np.linalg.norm(mg - r_mg) / np.linalg.norm(r_mg)
+    assert np.linalg.norm(tg - r_tg) <= 1e-4 * np.linalg.norm(r_tg), np.linalg.norm(tg - r_tg) / np.linalg.norm(r_tg)
