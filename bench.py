@@ -153,14 +153,27 @@ def cpu_oracle_step(O, S, sc, V, K, W, H, deg, rn, gt):
     return float(loss), p["nnz"], len(flat), p, r
 
 
-def cpu_oracle_sdf(O, pts, table, mlp, hidden, n_hidden, gt=None, weights=None, delta=0.1):
-    """SDF stage on the oracle port: 7 evaluations per point, losses, backward (table + decoder + d/dx of the base point)."""
+def cpu_oracle_sdf(O, pts, table, mlp, hidden, n_hidden, gt=None, weights=None, delta=0.1, analytic=True, align_w=0.1):
+    """SDF stage on the oracle port: 7 evaluations per point, losses, backward (table + decoder + d/dx of the base point).
+    analytic: eikonal + align on the analytic gradient with its double backward (reference default), else the 6-offset eikonal."""
     n = len(pts)
     offs = np.array([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float32) * np.float32(delta)
     x01 = (((pts[None] + offs[:, None]).reshape(-1, 3)) / 14.0 + 0.5).astype(np.float32)
     sdf, y1, _ = O.sdf_fwd(x01, table, mlp, hidden, n_hidden)
-    loss, vs, vy = O.sdf_losses(sdf, y1, n, 7, gt, weights, 10.0, 1.0 if gt is not None else 0.0, 0.1, 1e-3, delta)
-    O.sdf_bwd(x01, table, mlp, vs, vy, hidden, n_hidden)
+    if not analytic:
+        loss, vs, vy = O.sdf_losses(sdf, y1, n, 7, gt, weights, 10.0, 1.0 if gt is not None else 0.0, 0.1, 1e-3, delta)
+        O.sdf_bwd(x01, table, mlp, vs, vy, hidden, n_hidden)
+        return loss
+    loss, vs, vy = O.sdf_losses(sdf, y1, n, 7, gt, weights, 10.0, 1.0 if gt is not None else 0.0, 0.0, 1e-3, delta)
+    vs, vy = np.asarray(vs).reshape(7, n)[0].astype(np.float32), np.asarray(vy).reshape(7, n)[0].astype(np.float32)
+    O.sdf_bwd(x01[:n], table, mlp, vs, vy, hidden, n_hidden)  # first order: only the base evaluations carry cotangents
+    g = O.sdf_grad_analytic(x01[:n], table, mlp, hidden, n_hidden).astype(np.float64) / 14.0  # world units
+    s7 = np.asarray(sdf, np.float64).reshape(7, n)
+    gnum = np.stack([s7[1] - s7[2], s7[3] - s7[4], s7[5] - s7[6]], 1) * (0.5 / delta)
+    nrm = np.maximum(np.linalg.norm(g, axis=1), 1e-30)
+    loss += 0.1 * np.mean((nrm - 1) ** 2) + align_w * np.mean(np.abs(g - gnum))
+    c = (0.1 / n) * (2 * (nrm - 1) / nrm)[:, None] * g + (align_w / (3 * n)) * np.sign(g - gnum)
+    O.sdf_grad_analytic_bwd(x01[:n], table, mlp, (c / 14.0).astype(np.float32), hidden, n_hidden)
     return loss
 
 
@@ -213,7 +226,7 @@ def run_cpu_sample(workload, steps, warmup, budget_s=25.0):
     value = (1.0 / dt) * frac  # sample steps/s scaled by the work fraction = full-workload-equivalent steps/s
     return dict(value=value, unit="step/s", cores=cores, kind="port",
                 sample=f"{done} oracle steps (C, OpenMP, fp32) of the workload at 1/{CPU_SAMPLE_DIV} linear resolution "
-                       f"({Ws}x{Hs}, {Ns} splats, nnz={nnz}, n_isects={I}, {n_ray}+{nnz} SDF points x7): {dt * 1e3:.0f} ms each; value = sample steps/s x {frac:.4f}"), W, H
+                       f"({Ws}x{Hs}, {Ns} splats, nnz={nnz}, n_isects={I}, {n_ray}+{nnz} SDF points x7, analytic eikonal + align with double backward): {dt * 1e3:.0f} ms each; value = sample steps/s x {frac:.4f}"), W, H
 
 
 def main():
@@ -224,6 +237,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p-1M", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eikonal", default="analytic", choices=["analytic", "numerical"],
+                    help="analytic: eikonal + align on d sdf/dx with double backward (reference default); numerical: 6-offset gradient")
     ap.add_argument("--distinct-cameras", action="store_true", help="N>1: rank r renders its own camera poses (adds load imbalance)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -271,7 +286,8 @@ def main():
     sdf_cfg = dict(n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=2.0,
                    hidden_dim=32 if args.workload == "c1" else 64, n_hidden=1 if args.workload == "c1" else 3)
     n_ray = 32768  # config/base.yaml:23 batch_pt_num
-    G = render.GsSdfStep(N, K_sh, W, H, dev, isect_cap, sdf_cfg, n_ray_samples=n_ray, sh_degree=deg, origin=(0.0, 0.0, 0.0), map_size=14.0)
+    G = render.GsSdfStep(N, K_sh, W, H, dev, isect_cap, sdf_cfg, n_ray_samples=n_ray, sh_degree=deg, origin=(0.0, 0.0, 0.0), map_size=14.0,
+                         eikonal_mode=(1 if args.eikonal == "analytic" and sdf_cfg["hidden_dim"] == 64 else 0))
     R = G.R
     gen = torch.Generator(dev).manual_seed(5)  # replicated parameters: same on every rank
     table = (torch.rand(G.n_table, device=dev, generator=gen) * 2 - 1) * 1e-4  # tcnn grid init U(+-1e-4) (grid.h:1059-1062)

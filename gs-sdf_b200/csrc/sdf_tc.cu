@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256) mlp_pack_kernel(const float *__restrict__
 __global__ void __launch_bounds__(kFwdTcThreads)
 sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
     constexpr int TM = 128, HID = 64;
-    extern __shared__ __align__(1024) unsigned char s_tc[];
+    extern __shared__ __align__(128) unsigned char s_tc[];  // (a larger alignment pads the static part and costs the L1 carve-out step)
     unsigned char *sA = s_tc;                    // 32 KB activations hi/mid (off_act); in place across layers
     unsigned char *sF = sA + 16 * kGA;           // 16 KB encoded features hi/mid (off_feat)
     unsigned char *sL = sF + 16 * kGA0;          // 16 KB activation lo (off_lo)
@@ -345,7 +345,14 @@ sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
 // ---------------------------------------------------------------------------------------------
 // backward: persistent, one CTA per SM, 128-point tiles
 // ---------------------------------------------------------------------------------------------
-constexpr size_t kBwdTcSmem = 16 * kGA0 + 3 * 16 * kGA + 16 * kGA + 16 * kGL + kWImg + sizeof(float) * (5 * 64 + 132 + 256 + 384 + 4 * 192 + 1024 + 384) + 1024;
+// Shared-memory budget: the SM's 256 KiB are split between shared memory and L1, and the carve-out comes in steps (.., 196, 228 KiB).
+// Staying under 196 KiB per CTA (incl. 1 KiB system reserve) keeps a 60 KiB L1 for the hash-grid gathers; at 228 KiB only 28 KiB
+// remain and the kernel ran 20 % slower. Both variants are sized to fit the 196 KiB step.
+constexpr size_t kBwdTcMain = 16 * kGA0 + 3 * 16 * kGA + 16 * kGA + 16 * kGL + kWImg;
+constexpr size_t kBwdTcMisc = sizeof(float) * (4 * 64 + 132 + 384 + 4 * 128);                    // bias, w_out, dx|seed, column sums
+constexpr size_t kBwdTcMiscAnalytic = 128 * 16 * sizeof(uint16_t) + 128 * 3 * sizeof(float) + 64;  // ReLU masks, numerical gradient, tile bases
+constexpr size_t bwd_tc_smem(bool analytic) { return kBwdTcMain + kBwdTcMisc + (analytic ? kBwdTcMiscAnalytic : 0); }
+static_assert(bwd_tc_smem(true) + 1024 + 128 <= 196 * 1024, "the analytic variant must fit the 196 KiB shared-memory carve-out");
 
 // FUSED = false: gssdf_sdf_bwd (cotangents v_sdf / v_y1 come from memory; evaluation index = variant * n + point).
 // FUSED = true : gssdf_sdf_train (forward -> losses -> backward in one pass, nothing but the gradients leaves the SM). A tile
@@ -359,24 +366,25 @@ struct TcLossArgs {
     float align_weight;  // |g_analytic - g_numerical.detach()|.mean() (neural_mapping.cpp:124-133); needs the 7-variant layout
 };
 
-template <bool FUSED>
-__global__ void __launch_bounds__(kBwdTcThreads)
+template <bool FUSED, bool ANALYTIC>
+__global__ void __launch_bounds__(kBwdTcThreads, 1)
 sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeom g, int64_t n_tiles) {
     constexpr int TM = 128, HID = 64, NT = kBwdTcThreads;
-    extern __shared__ __align__(1024) unsigned char s_tc[];
+    extern __shared__ __align__(128) unsigned char s_tc[];  // (a larger alignment pads the static part and costs the L1 carve-out step)
     unsigned char *sF = s_tc;                    // 16 KB a_0: encoded features hi/mid (off_feat); rows 64-127 of its stacked view alias
                                                  //       the next 8-point group / the start of a_1 (finite garbage, rows ignored)
     unsigned char *sAct = sF + 16 * kGA0;        // 3 x 32 KB a_1 .. a_3 hi/mid (off_act)
     unsigned char *sG = sAct + 3 * 16 * kGA;     // 32 KB: a_nh, then g_l for l = nh-1 .. 0, updated in place
     unsigned char *sL = sG + 16 * kGA;           // 16 KB activation lo (forward only); later fp32 dL/dfeat [128][33] (spills 512 B into sW)
     unsigned char *sW = sL + 16 * kGL;           // 24 KB weight image of the current layer
-    float *s_bias = reinterpret_cast<float *>(sW + kWImg);  // [5][64]
-    float *s_wout = s_bias + 5 * 64;             // [2][64] + [2]
-    float *s_seed = s_wout + 132;                // [128][2] v_sdf, v_y1
-    float *s_dx = s_seed + 256;                  // [128][3]
-    float *s_col = s_dx + 384;                   // [4 row quarters][192]: column sums (db: 64, dW_out: 128)
-    uint16_t *s_mask16 = reinterpret_cast<uint16_t *>(s_col + 4 * 192);  // [128 rows][4 layers][4 column quarters]: ReLU masks (analytic mode)
-    float *s_gnum = s_col + 4 * 192 + 1024;      // [128][3] numerical gradient of the tile's points (align loss)
+    float *s_bias = reinterpret_cast<float *>(sW + kWImg);  // [4][64]
+    float *s_wout = s_bias + 4 * 64;             // [2][64] + [2]
+    float *s_dx = s_wout + 132;                  // [128][3] dL/dx accumulators (step 5 / second-order phase) ...
+    float *s_seed = s_dx;                        // ... aliased by [128][2] v_sdf, v_y1 (live from the loss stage to step 3) + 8 b_out sums
+    float *s_col = s_dx + 384;                   // [4 row quarters][128]: column sums (db: 64 | dW_out: 2 x 64)
+    uint16_t *s_mask16 = reinterpret_cast<uint16_t *>(s_col + 4 * 128);  // ANALYTIC only: [128 slots][4 layers][4 column quarters] ReLU masks
+    float *s_gnum = s_col + 4 * 128 + 1024;      // ANALYTIC only: [128][3] numerical gradient of the pending points (align loss)
+    int64_t *s_tbase = reinterpret_cast<int64_t *>(s_gnum + 384);  // ANALYTIC only: first point of each tile of the pending batch [8]
     __shared__ __align__(8) uint64_t s_mbar[2];
     __shared__ uint32_t s_tmem;
 
@@ -389,12 +397,10 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
     const unsigned char *wimg = reinterpret_cast<const unsigned char *>(a.net.mlp_packed);
     const int V = max(a.n_variants, 1), PT = FUSED ? TM / V : TM;
     float loss_acc = 0.f;
-    const bool analytic = FUSED && lo.analytic != 0;
-    float acc2_0[4] = {0.f, 0.f, 0.f, 0.f}, acc2[3][8], acc2_wo = 0.f;  // second-order decoder gradients (analytic mode), per thread
-#pragma unroll
-    for (int l = 0; l < 3; ++l)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc2[l][e] = 0.f;
+    constexpr bool analytic = ANALYTIC;
+    static_assert(FUSED || !ANALYTIC, "the analytic eikonal path is part of the fused train kernel");
+    float acc2_wo = 0.f;  // second-order gradient of w_out[0] (thread (q == 0, lane < 16) owns column 16cq + lane)
+    int n_coll = 0;       // base points waiting for the second-order phase (slots 0 .. n_coll-1 of s_mask16 / s_cpt / s_gnum)
 
     if (warp == 0) {  // TMEM: D (64 columns) + one 64-column weight-gradient accumulator per hidden layer -> 512-column allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(512));
@@ -422,6 +428,218 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
     bool ok = true, first_tile = true;
     float dbias[4] = {0.f, 0.f, 0.f, 0.f};  // thread (q == 0, lane < 16) owns column 16cq + lane of every hidden layer's bias gradient
     float dwo0 = 0.f, dwo1 = 0.f, dbo = 0.f;
+
+
+    // ---- second-order phase (ANALYTIC): gradient of the eikonal / align losses -- functions of g = d sdf / d x -- w.r.t. decoder and
+    //      table, for the up to 128 pending base points, on the tensor cores with the machinery of the first-order backward:
+    //        u-chain  u_nh = D_nh (.) w_out[0]; u_l = D_l (.) (u_{l+1} W_l); dfeat = u_1 W_0      (the first backward seeded with e_sdf)
+    //        g = dy_dx^T half(dfeat) (tcnn rounding points); c = dL/dg; r = half(dy_dx c); table: encode_level_bwd2
+    //        q-chain  q_0 = r; q_{l+1} = D_{l+1} (.) (q_l W_l^T)                                   (forward-like, no bias)
+    //        dL/dW_l += u_{l+1} (x) q_l  : the SAME stacked dW GEMM, A = q_l parked where a_l lives, B = u_{l+1} where g_l lives,
+    //        accumulating into the same TMEM tiles as the first-order weight gradient; dL/dw_out[0] += colsum(q_nh); no bias terms.
+    //      The u-chain runs twice (first to get dfeat, then again to pair u_{l+1} with the stored q_l) so that only one gradient
+    //      buffer is live. ReLU masks D_l come from the bit masks captured in the forward epilogues.
+    auto second_order = [&]() {
+        const int nc = n_coll;
+        float *gf = reinterpret_cast<float *>(sL);  // dfeat [128][33] fp32
+        float *s_cc = s_col;                        // [128][3] dL/dg in x01 units
+        const float isz = a.net.inv_size != 0.f ? a.net.inv_size : 1.f;
+        __syncthreads();
+        for (int e = tid; e < (TM - nc) * 16; e += NT) s_mask16[nc * 16 + e] = 0;  // empty slots: all chains vanish
+        for (int e = tid; e < TM * 3; e += NT) s_dx[e] = 0.f;
+        __syncthreads();
+        auto seed_u = [&]() {  // u_nh into sG (this thread's row, 16 columns)
+            const uint32_t bits = s_mask16[(row * 4 + nh - 1) * 4 + cq];
+            float u[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) u[j] = ((bits >> j) & 1u) ? s_wout[col0 + j] : 0.f;
+            store8(sG, nullptr, row, col0, u);
+            store8(sG, nullptr, row, col0 + 8, u + 8);
+        };
+        auto load_w = [&](int l) {  // thread 0
+            mbar_arrive_expect_tx(&s_mbar[1], kWImg);
+            bulk_g2s(sW, wimg + (size_t)l * kWImg, kWImg, &s_mbar[1]);
+        };
+        auto issue_d = [&]() {  // D = G . W (A = sG K-major, B = weight image MN-major), thread 0
+            const uint32_t gB = smem_u32(sG), wB = smem_u32(sW);
+            uint32_t acc = 0;
+            for (int ks = 0; ks < HID / 16; ++ks) {
+                const uint64_t gh = make_desc(gB + ks * 256, 128, kGA), gm = make_desc(gB + 1024 + ks * 256, 128, kGA);
+                const uint64_t wh = make_desc(wB + ks * 2 * kGW, kGW, 128), wm = make_desc(wB + 1024 + ks * 2 * kGW, kGW, 128);
+                umma_bf16(tmD, gh, wh, kIdescBmn, acc); acc = 1;
+                umma_bf16(tmD, gh, wm, kIdescBmn, 1);
+                umma_bf16(tmD, gm, wh, kIdescBmn, 1);
+                umma_bf16(tmD, gm, wm, kIdescBmn, 1);
+            }
+        };
+        auto mask_store = [&](int l, unsigned char *dst) {  // dst[row][cols] = D_l (.) TMEM D   (l = 1..nh)
+            uint32_t v[16];
+            tmem_ld16(tmD + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, v);
+            const uint32_t bits = s_mask16[(row * 4 + l - 1) * 4 + cq];
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = ((bits >> j) & 1u) ? __uint_as_float(v[j]) : 0.f;
+            store8(dst, nullptr, row, col0, o);
+            store8(dst, nullptr, row, col0 + 8, o + 8);
+        };
+        // -- u-chain, pass 1: dfeat
+        seed_u();
+        if (tid == 0) { fence_proxy_async(); load_w(nh - 1); }
+        for (int l = nh - 1; l >= 0 && ok; --l) {
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                ok = mbar_wait_bounded(&s_mbar[1], ph_w); ph_w ^= 1;
+                tc_fence_after();
+                if (ok) issue_d();
+                umma_commit(&s_mbar[0]);
+            }
+            ok = mbar_wait_bounded(&s_mbar[0], ph_mma) && ok; ph_mma ^= 1;
+            if (!ok) return;
+            tc_fence_after();
+            if (tid == 0 && l > 0) load_w(l - 1);
+            if (l > 0) {
+                mask_store(l, sG);
+            } else if (cq < 2) {
+                uint32_t v[16];
+                tmem_ld16(tmD + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) gf[row * 33 + col0 + j] = __uint_as_float(v[j]);
+            }
+            tc_fence_before();
+        }
+        __syncthreads();
+        // -- pass A: g (x01 units) = tcnn input gradient with cotangent dfeat, summed over the levels
+#pragma unroll 1
+        for (int task = tid; task < TM * kLevels; task += NT) {
+            const int c = task % TM, lvl = task / TM;
+            if (c < nc) {
+                float x[3], dx[3] = {0.f, 0.f, 0.f};
+                load_x(a.net, a.x, s_tbase[c / PT] + c % PT, a.n, a.delta, x);
+                encode_level_bwd(table, nullptr, g, lvl, x, gf[c * 33 + 2 * lvl], gf[c * 33 + 2 * lvl + 1], true, dx);
+                atomicAdd(&s_dx[c * 3 + 0], dx[0]);
+                atomicAdd(&s_dx[c * 3 + 1], dx[1]);
+                atomicAdd(&s_dx[c * 3 + 2], dx[2]);
+            }
+        }
+        __syncthreads();
+        // -- losses on the analytic gradient (world units), cotangent back in x01 units
+        if (tid < TM) {
+            float cc[3] = {0.f, 0.f, 0.f};
+            if (tid < nc) {
+                const float gx = s_dx[tid * 3] * isz, gy = s_dx[tid * 3 + 1] * isz, gz = s_dx[tid * 3 + 2] * isz;
+                const float nl = (float)n_live;
+                const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
+                const float we = lo.cfg.eikonal_weight / nl;
+                loss_acc += we * (nrm - 1.f) * (nrm - 1.f);
+                const float ke = nrm > 0.f ? 2.f * (nrm - 1.f) / nrm * we : 0.f;
+                cc[0] = ke * gx; cc[1] = ke * gy; cc[2] = ke * gz;
+                if (lo.align_weight > 0.f && V == 7) {
+                    const float wa = lo.align_weight / (3.f * nl);
+                    const float *gn = s_gnum + tid * 3;
+                    const float d0 = gx - gn[0], d1 = gy - gn[1], d2 = gz - gn[2];
+                    loss_acc += wa * (fabsf(d0) + fabsf(d1) + fabsf(d2));
+                    cc[0] += d0 > 0.f ? wa : (d0 < 0.f ? -wa : 0.f);
+                    cc[1] += d1 > 0.f ? wa : (d1 < 0.f ? -wa : 0.f);
+                    cc[2] += d2 > 0.f ? wa : (d2 < 0.f ? -wa : 0.f);
+                }
+            }
+            s_cc[tid * 3] = cc[0] * isz; s_cc[tid * 3 + 1] = cc[1] * isz; s_cc[tid * 3 + 2] = cc[2] * isz;
+        }
+        __syncthreads();
+        // -- pass B: r = half(dy_dx c) -> q_0 (operand layout of the encoded features), second-order table gradient
+#pragma unroll 1
+        for (int task = tid; task < TM * kLevels; task += NT) {
+            const int c = task % TM, lvl = task / TM;
+            float r[2] = {0.f, 0.f};
+            if (c < nc) {
+                float x[3];
+                load_x(a.net, a.x, s_tbase[c / PT] + c % PT, a.n, a.delta, x);
+                encode_level_bwd2(table, a.table_grad, g, lvl, x, gf[c * 33 + 2 * lvl], gf[c * 33 + 2 * lvl + 1], s_cc + c * 3, r);
+            }
+            __nv_bfloat16 h0, m0, h1, m1;
+            split2(r[0], h0, m0);
+            split2(r[1], h1, m1);
+            *reinterpret_cast<__nv_bfloat162 *>(sF + off_feat(c, 2 * lvl, 0)) = __halves2bfloat162(h0, h1);
+            *reinterpret_cast<__nv_bfloat162 *>(sF + off_feat(c, 2 * lvl, 1)) = __halves2bfloat162(m0, m1);
+        }
+        if (!a.mlp_grad) { __syncthreads(); return; }
+        // -- q-chain (forward-like, 2-term split, no bias): q_l parked where the forward keeps a_l
+        if (tid == 0) { fence_proxy_async(); load_w(0); }
+        for (int l = 0; l < nh; ++l) {
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                ok = mbar_wait_bounded(&s_mbar[1], ph_w); ph_w ^= 1;
+                tc_fence_after();
+                if (ok) {
+                    const uint32_t aB = smem_u32(l == 0 ? sF : sAct + (l - 1) * 16 * kGA), wB = smem_u32(sW);
+                    const uint32_t ga = l == 0 ? kGA0 : kGA, am = l == 0 ? 512u : 1024u;
+                    uint32_t acc = 0;
+                    for (int ks = 0; ks < (l == 0 ? kFeat : HID) / 16; ++ks) {
+                        const uint32_t ko = ks * 256;
+                        const uint64_t ah = make_desc(aB + ko, 128, ga), amd = make_desc(aB + am + ko, 128, ga);
+                        const uint64_t wh = make_desc(wB + ko, 128, kGW), wm = make_desc(wB + 1024 + ko, 128, kGW);
+                        umma_bf16(tmD, ah, wh, kIdesc, acc); acc = 1;
+                        umma_bf16(tmD, ah, wm, kIdesc, 1);
+                        umma_bf16(tmD, amd, wh, kIdesc, 1);
+                        umma_bf16(tmD, amd, wm, kIdesc, 1);
+                    }
+                }
+                umma_commit(&s_mbar[0]);
+            }
+            ok = mbar_wait_bounded(&s_mbar[0], ph_mma) && ok; ph_mma ^= 1;
+            if (!ok) return;
+            tc_fence_after();
+            if (tid == 0 && (l + 1 < nh || nh > 1)) load_w(l + 1 < nh ? l + 1 : nh - 1);  // next q layer, or the first weights of the second u pass
+            if (l < nh - 1) {
+                mask_store(l + 1, sAct + l * 16 * kGA);
+            } else {  // q_nh is only needed for dL/dw_out[0] = its column sums
+                uint32_t v[16];
+                tmem_ld16(tmD + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, v);
+                const uint32_t bits = s_mask16[(row * 4 + nh - 1) * 4 + cq];
+                float c[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) c[j] = ((bits >> j) & 1u) ? __uint_as_float(v[j]) : 0.f;
+                const float sres = colsum16(c, lane);
+                if (lane < 16) s_col[q * 128 + col0 + lane] = sres;
+            }
+            tc_fence_before();
+        }
+        __syncthreads();
+        if (q == 0 && lane < 16) {
+            const int c = col0 + lane;
+            acc2_wo += s_col[c] + s_col[128 + c] + s_col[256 + c] + s_col[384 + c];
+        }
+        // -- u-chain, pass 2: dW_l += u_{l+1} (x) q_l on the way down
+        seed_u();
+        for (int l = nh - 1; l >= 0 && ok; --l) {
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                if (l > 0) { ok = mbar_wait_bounded(&s_mbar[1], ph_w); ph_w ^= 1; }
+                tc_fence_after();
+                if (ok) {
+                    const uint32_t gB = smem_u32(sG);
+                    const uint32_t aB = smem_u32(l == 0 ? sF : sAct + (l - 1) * 16 * kGA), ga = l == 0 ? kGA0 : kGA;
+                    for (int ks = 0; ks < TM / 16; ++ks) {
+                        const uint64_t ad = make_desc(aB + ks * 2 * ga, ga, 128);
+                        umma_bf16(tmW + 64 * l, ad, make_desc(gB + ks * 2 * kGA, kGA, 128), kIdescAmnBmn, 1);
+                        umma_bf16(tmW + 64 * l, ad, make_desc(gB + 1024 + ks * 2 * kGA, kGA, 128), kIdescAmnBmn, 1);
+                    }
+                    if (l > 0) issue_d();
+                }
+                umma_commit(&s_mbar[0]);
+            }
+            ok = mbar_wait_bounded(&s_mbar[0], ph_mma) && ok; ph_mma ^= 1;
+            if (!ok) return;
+            tc_fence_after();
+            if (tid == 0 && l > 1) load_w(l - 1);
+            if (l > 0) mask_store(l, sG);
+            tc_fence_before();
+        }
+        __syncthreads();
+    };
 
     for (int64_t tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
         const int64_t base = FUSED ? tile * PT : tile * TM;  // first point (FUSED) / first evaluation index of the tile
@@ -499,11 +717,14 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
             unsigned char *dst = (l < nh - 1) ? sAct + l * 16 * kGA : sG;
             store8(dst, l < nh - 1 ? sL : nullptr, row, col0, act);
             store8(dst, l < nh - 1 ? sL : nullptr, row, col0 + 8, act + 8);
-            if (analytic) {  // ReLU mask of z_{l+1}: kept until the second-order phase at the end of the tile
-                uint32_t bits = 0;
+            if (analytic) {  // ReLU mask of z_{l+1} of the BASE rows: kept in the pending batch for the second-order phase
+                const int jb = row / V;
+                if (row - jb * V == 0 && jb < PT && base + jb < n_live) {
+                    uint32_t bits = 0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) bits |= (act[j] > 0.f ? 1u : 0u) << j;
-                s_mask16[(row * 4 + l) * 4 + cq] = (uint16_t)bits;
+                    for (int j = 0; j < 16; ++j) bits |= (act[j] > 0.f ? 1u : 0u) << j;
+                    s_mask16[((n_coll + jb) * 4 + l) * 4 + cq] = (uint16_t)bits;
+                }
             }
             if (FUSED && l == nh - 1) {  // output layer (64 -> 2): this thread's 16-column share of both dot products
                 float p0 = 0.f, p1 = 0.f;
@@ -512,7 +733,7 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
                     p0 = fmaf(act[j], s_wout[col0 + j], p0);
                     p1 = fmaf(act[j], s_wout[HID + col0 + j], p1);
                 }
-                float *s_part = s_dx;  // [4 column quarters][128][2] over s_dx + s_col (both idle here)
+                float *s_part = reinterpret_cast<float *>(sL);  // [4 column quarters][128][2]; sL (activation lo) is idle after the last forward MMA
                 s_part[(cq * TM + row) * 2] = p0;
                 s_part[(cq * TM + row) * 2 + 1] = p1;
             }
@@ -520,7 +741,7 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
         }
         if (!ok) break;
         if (FUSED) {  // ---- 2b. network outputs -> per-point losses -> cotangent seeds
-            float *s_part = s_dx, *s_out = reinterpret_cast<float *>(sL);  // sL is idle after the last forward layer
+            float *s_part = reinterpret_cast<float *>(sL), *s_out = s_part + 4 * TM * 2;
             __syncthreads();
             if (tid < TM) {
                 s_out[2 * tid] = s_part[tid * 2] + s_part[(TM + tid) * 2] + s_part[(2 * TM + tid) * 2] + s_part[(3 * TM + tid) * 2] + s_wout[2 * HID];
@@ -537,11 +758,12 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
                 SdfLossCfg cfg1 = lo.cfg;
                 if (analytic) {  // the eikonal / align terms act on the analytic gradient: second-order phase below
                     cfg1.eikonal_weight = 0.f;
+                    if (tid == 0) s_tbase[n_coll / PT] = base;  // slots of a batch are filled PT per tile (only a CTA's last tile is partial)
                     if (V == 7) {
                         const float inv2d = 0.5f / lo.cfg.delta;
-                        s_gnum[tid * 3 + 0] = (sv[1] - sv[2]) * inv2d;
-                        s_gnum[tid * 3 + 1] = (sv[3] - sv[4]) * inv2d;
-                        s_gnum[tid * 3 + 2] = (sv[5] - sv[6]) * inv2d;
+                        s_gnum[(n_coll + tid) * 3 + 0] = (sv[1] - sv[2]) * inv2d;
+                        s_gnum[(n_coll + tid) * 3 + 1] = (sv[3] - sv[4]) * inv2d;
+                        s_gnum[(n_coll + tid) * 3 + 2] = (sv[5] - sv[6]) * inv2d;
                     }
                 }
                 loss_acc += sdf_point_loss(cfg1, (float)n_live, V, sv, s_out[2 * tid * V + 1], lo.gt_sdf != nullptr,
@@ -568,23 +790,23 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
                 for (int j = 0; j < 16; ++j) { c0[j] = v0 * an[j]; c1[j] = v1 * an[j]; }
                 const float s0 = colsum16(c0, lane), s1 = colsum16(c1, lane);
                 if (lane < 16) {
-                    s_col[q * 192 + 64 + col0 + lane] = s0;
-                    s_col[q * 192 + 128 + col0 + lane] = s1;
+                    s_col[q * 128 + col0 + lane] = s0;
+                    s_col[q * 128 + 64 + col0 + lane] = s1;
                 }
                 if (cq == 0) {
                     const float b0 = warp_sum(v0), b1 = warp_sum(v1);
-                    if (lane == 0) { s_col[q * 192 + 0] = b0; s_col[q * 192 + 1] = b1; }
+                    if (lane == 0) { s_dx[256 + 2 * q] = b0; s_dx[256 + 2 * q + 1] = b1; }  // (beyond the seeds)
                 }
             }
         }
         __syncthreads();
         if (a.mlp_grad) {
             if (tid < 2 * HID) {
-                const float s = s_col[64 + tid] + s_col[192 + 64 + tid] + s_col[384 + 64 + tid] + s_col[576 + 64 + tid];
+                const float s = s_col[tid] + s_col[128 + tid] + s_col[256 + tid] + s_col[384 + tid];
                 if (tid < HID) dwo0 += s; else dwo1 += s;
             } else if (tid < 2 * HID + 2) {
                 const int o = tid - 2 * HID;
-                dbo += s_col[o] + s_col[192 + o] + s_col[384 + o] + s_col[576 + o];
+                dbo += s_dx[256 + o] + s_dx[258 + o] + s_dx[260 + o] + s_dx[262 + o];
             }
         }
         // ---- 4. hidden layers, last to first
@@ -623,7 +845,7 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
                 load8_sum(sG, row, col0, c);
                 load8_sum(sG, row, col0 + 8, c + 8);
                 const float s = colsum16(c, lane);
-                if (lane < 16) s_col[q * 192 + col0 + lane] = s;
+                if (lane < 16) s_col[q * 128 + col0 + lane] = s;
             }
             ok = mbar_wait_bounded(&s_mbar[0], ph_mma) && ok;
             ph_mma ^= 1;
@@ -652,7 +874,7 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
             __syncthreads();
             if (a.mlp_grad && q == 0 && lane < 16) {
                 const int c = col0 + lane;
-                dbias[l] += s_col[c] + s_col[192 + c] + s_col[384 + c] + s_col[576 + c];
+                dbias[l] += s_col[c] + s_col[128 + c] + s_col[256 + c] + s_col[384 + c];
             }
         }
         if (!ok) break;
@@ -689,178 +911,19 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
                     if (base + e / 3 < n_live) a.v_x[base * 3 + e] = s_dx[e] * sc;
             }
         }
-        if (analytic) {
-            // ---- 5b. second-order phase (CUDA cores; every operand buffer of the tile is idle now): gradient of the eikonal / align
-            //      losses, which are functions of g = d sdf / d x, w.r.t. decoder and table. Chains over the base rows:
-            //        u_nh = D_nh (.) w_out[0]; u_l = D_l (.) W_l^T u_{l+1}; dfeat = W_0^T u_1          (first backward, seed e_sdf)
-            //        g = dy_dx^T half(dfeat) (tcnn rounding points); c = dL/dg; r = half(dy_dx c)
-            //        q_1 = D_1 (.) W_0 r; q_{l+1} = D_{l+1} (.) W_l q_l                               (forward-like)
-            //        dL/dW_0 += u_1 (x) r; dL/dW_l += u_{l+1} (x) q_l; dL/dw_out[0] += q_nh; table: encode_level_bwd2
-            constexpr int CH = 32;
-            float *sW2 = reinterpret_cast<float *>(s_tc);  // [64][65]
-            float *sU = sW2 + 64 * 65;                     // [CH][4][64]  u_l at slot l - 1
-            float *sQ0 = sU + CH * 4 * 64, *sQ1 = sQ0 + CH * 64;  // [CH][64] ping / pong
-            float *sR = sQ1 + CH * 64, *sDf = sR + CH * 32;       // [CH][32]
-            float *sGx = sDf + CH * 32, *sCc = sGx + CH * 3;      // [CH][3]
-            const float isz = a.net.inv_size != 0.f ? a.net.inv_size : 1.f;
-            const float *Wg = a.net.mlp;
-            auto w_of = [&](int l) { return Wg + (l == 0 ? 0 : (size_t)HID * kFeat + HID + (size_t)(l - 1) * (HID * HID + HID)); };
-            auto mask_of = [&](int j, int l, int k) -> bool {  // ReLU'(z_l)[k] of base row j of the chunk, l = 1..nh
-                return (s_mask16[((j * V) * 4 + (l - 1)) * 4 + (k >> 4)] >> (k & 15)) & 1;
-            };
-            const int n_pts = (int)min((int64_t)PT, n_live - base);
-            for (int c0 = 0; c0 < n_pts; c0 += CH) {
-                const int nj = min(CH, n_pts - c0);
-                __syncthreads();
-                // (i) u_nh
-                for (int e = tid; e < CH * 64; e += NT) {
-                    const int j = e >> 6, k = e & 63;
-                    sU[(j * 4 + nh - 1) * 64 + k] = (j < nj && mask_of(c0 + j, nh, k)) ? s_wout[k] : 0.f;
-                }
-                // (ii) u_l, l = nh-1 .. 1
-                for (int l = nh - 1; l >= 1; --l) {
-                    __syncthreads();
-                    const float *W = w_of(l);
-                    for (int e = tid; e < 64 * 64; e += NT) sW2[(e >> 6) * 65 + (e & 63)] = __ldg(W + e);
-                    __syncthreads();
-                    const int k = tid & 63, jg = tid >> 6;
-#pragma unroll
-                    for (int jj = 0; jj < CH / 8; ++jj) {
-                        const int j = jg + 8 * jj;
-                        float sacc = 0.f;
-                        const float *un = sU + (j * 4 + l) * 64;
-#pragma unroll 8
-                        for (int o = 0; o < 64; ++o) sacc = fmaf(sW2[o * 65 + k], un[o], sacc);
-                        sU[(j * 4 + l - 1) * 64 + k] = (j < nj && mask_of(c0 + j, l, k)) ? sacc : 0.f;
-                    }
-                }
-                // (iii) dfeat = W_0^T u_1 ; W_0 [64][32] stays staged (stride 33) until q_1 is done
-                __syncthreads();
-                for (int e = tid; e < 64 * kFeat; e += NT) sW2[(e >> 5) * 33 + (e & 31)] = __ldg(Wg + e);
-                for (int e = tid; e < CH * 3; e += NT) sGx[e] = 0.f;
-                __syncthreads();
-                {
-                    const int k = tid & 31, jg = tid >> 5;
-#pragma unroll
-                    for (int jj = 0; jj < CH / 16; ++jj) {
-                        const int j = jg + 16 * jj;
-                        float sacc = 0.f;
-                        const float *un = sU + (j * 4 + 0) * 64;
-#pragma unroll 8
-                        for (int o = 0; o < 64; ++o) sacc = fmaf(sW2[o * 33 + k], un[o], sacc);
-                        sDf[j * 32 + k] = sacc;
-                    }
-                }
-                __syncthreads();
-                // (iv) pass A: g (x01 units) = sum over levels of the tcnn input gradient with cotangent dfeat
-                for (int task = tid; task < CH * kLevels; task += NT) {
-                    const int j = task % CH, lvl = task / CH;
-                    if (j < nj) {
-                        float x[3], dx[3] = {0.f, 0.f, 0.f};
-                        load_x(a.net, a.x, row_gi((c0 + j) * V), a.n, a.delta, x);
-                        encode_level_bwd(table, nullptr, g, lvl, x, sDf[j * 32 + 2 * lvl], sDf[j * 32 + 2 * lvl + 1], true, dx);
-                        atomicAdd(&sGx[j * 3 + 0], dx[0]);
-                        atomicAdd(&sGx[j * 3 + 1], dx[1]);
-                        atomicAdd(&sGx[j * 3 + 2], dx[2]);
-                    }
-                }
-                __syncthreads();
-                // (v) losses on the analytic gradient (world units) and their cotangent
-                if (tid < CH) {
-                    float cc[3] = {0.f, 0.f, 0.f};
-                    if (tid < nj) {
-                        const float gx = sGx[tid * 3] * isz, gy = sGx[tid * 3 + 1] * isz, gz = sGx[tid * 3 + 2] * isz;
-                        const float nl = (float)n_live;
-                        const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
-                        const float we = lo.cfg.eikonal_weight / nl;
-                        loss_acc += we * (nrm - 1.f) * (nrm - 1.f);
-                        const float ke = nrm > 0.f ? 2.f * (nrm - 1.f) / nrm * we : 0.f;
-                        cc[0] = ke * gx; cc[1] = ke * gy; cc[2] = ke * gz;
-                        if (lo.align_weight > 0.f && V == 7) {
-                            const float wa = lo.align_weight / (3.f * nl);
-                            const float *gn = s_gnum + (c0 + tid) * 3;
-                            const float d0 = gx - gn[0], d1 = gy - gn[1], d2 = gz - gn[2];
-                            loss_acc += wa * (fabsf(d0) + fabsf(d1) + fabsf(d2));
-                            cc[0] += d0 > 0.f ? wa : (d0 < 0.f ? -wa : 0.f);
-                            cc[1] += d1 > 0.f ? wa : (d1 < 0.f ? -wa : 0.f);
-                            cc[2] += d2 > 0.f ? wa : (d2 < 0.f ? -wa : 0.f);
-                        }
-                    }
-                    sCc[tid * 3] = cc[0] * isz; sCc[tid * 3 + 1] = cc[1] * isz; sCc[tid * 3 + 2] = cc[2] * isz;  // -> x01 units
-                }
-                __syncthreads();
-                // (vi) pass B: r = half(dy_dx c) and the second-order table gradient
-                for (int task = tid; task < CH * kLevels; task += NT) {
-                    const int j = task % CH, lvl = task / CH;
-                    float r[2] = {0.f, 0.f};
-                    if (j < nj) {
-                        float x[3];
-                        load_x(a.net, a.x, row_gi((c0 + j) * V), a.n, a.delta, x);
-                        encode_level_bwd2(table, a.table_grad, g, lvl, x, sDf[j * 32 + 2 * lvl], sDf[j * 32 + 2 * lvl + 1], sCc + j * 3, r);
-                    }
-                    sR[j * 32 + 2 * lvl] = r[0];
-                    sR[j * 32 + 2 * lvl + 1] = r[1];
-                }
-                __syncthreads();
-                // (vii) q-chain and the decoder's second-order gradients
-                {   // q_1 = D_1 (.) W_0 r ;  dL/dW_0[o][k] += u_1[o] r[k]
-                    const int o = tid & 63, jg = tid >> 6;
-#pragma unroll
-                    for (int jj = 0; jj < CH / 8; ++jj) {
-                        const int j = jg + 8 * jj;
-                        float sacc = 0.f;
-#pragma unroll 8
-                        for (int k = 0; k < kFeat; ++k) sacc = fmaf(sW2[o * 33 + k], sR[j * 32 + k], sacc);
-                        sQ0[j * 64 + o] = (j < nj && mask_of(c0 + j, 1, o)) ? sacc : 0.f;
-                    }
-                    if (a.mlp_grad) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int idx = tid + e * NT, oo = idx >> 5, kk = idx & 31;
-                            float sacc = 0.f;
-                            for (int j = 0; j < nj; ++j) sacc = fmaf(sU[(j * 4 + 0) * 64 + oo], sR[j * 32 + kk], sacc);
-                            acc2_0[e] += sacc;
-                        }
-                    }
-                }
-                float *qc = sQ0, *qn = sQ1;
-                for (int l = 1; l < nh; ++l) {
-                    __syncthreads();
-                    const float *W = w_of(l);
-                    for (int e = tid; e < 64 * 64; e += NT) sW2[(e >> 6) * 65 + (e & 63)] = __ldg(W + e);
-                    __syncthreads();
-                    const int o = tid & 63, jg = tid >> 6;
-#pragma unroll
-                    for (int jj = 0; jj < CH / 8; ++jj) {
-                        const int j = jg + 8 * jj;
-                        float sacc = 0.f;
-#pragma unroll 8
-                        for (int k = 0; k < 64; ++k) sacc = fmaf(sW2[o * 65 + k], qc[j * 64 + k], sacc);
-                        qn[j * 64 + o] = (j < nj && mask_of(c0 + j, l + 1, o)) ? sacc : 0.f;
-                    }
-                    if (a.mlp_grad) {  // dL/dW_l[o][k] += u_{l+1}[o] q_l[k]
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int idx = tid + e * NT, oo = idx >> 6, kk = idx & 63;
-                            float sacc = 0.f;
-                            for (int j = 0; j < nj; ++j) sacc = fmaf(sU[(j * 4 + l) * 64 + oo], qc[j * 64 + kk], sacc);
-                            acc2[l - 1][e] += sacc;
-                        }
-                    }
-                    float *t2 = qc; qc = qn; qn = t2;
-                }
-                __syncthreads();
-                if (a.mlp_grad && tid < 64) {  // dL/dw_out[0][k] += q_nh[k]
-                    float sacc = 0.f;
-                    for (int j = 0; j < nj; ++j) sacc += qc[j * 64 + tid];
-                    acc2_wo += sacc;
-                }
-            }
-            __syncthreads();
-        }
         first_tile = false;
+        if (ANALYTIC) {  // the tile's base points join the pending second-order batch; run it when the next tile would not fit
+            n_coll += (int)min((int64_t)PT, n_live - base);
+            if (n_coll + PT > TM) {
+                second_order();
+                n_coll = 0;
+                if (!ok) break;
+            }
+        }
+
 #undef LIVE_TC
     }
+    if (ANALYTIC && ok && n_coll > 0) second_order();  // the last, partial batch
     __syncthreads();
     // ---- 6. read the weight-gradient accumulators out of TMEM once
     if (ok && a.mlp_grad && !first_tile) {
@@ -883,21 +946,10 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
             G += (size_t)HID * K + HID;
             __syncthreads();
         }
+        if (ANALYTIC && q == 0 && lane < 16) atomicAdd(G + col0 + lane, acc2_wo);  // second-order part of dL/dw_out[0]
         if (tid < HID) atomicAdd(G + tid, dwo0);
         else if (tid < 2 * HID) atomicAdd(G + tid, dwo1);
         else if (tid < 2 * HID + 2) atomicAdd(G + tid, dbo);
-    }
-    if (analytic && ok && a.mlp_grad) {  // second-order decoder gradients (no bias terms)
-        float *G = a.mlp_grad;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) atomicAdd(G + tid + e * NT, acc2_0[e]);  // W_0 [64][32]: index o * 32 + k == tid + e * NT
-        G += (size_t)HID * kFeat + HID;
-        for (int l = 1; l < nh; ++l) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(G + tid + e * NT, acc2[l - 1][e]);
-            G += (size_t)HID * HID + HID;
-        }
-        if (tid < 64) atomicAdd(G + tid, acc2_wo);
     }
     if (FUSED && lo.loss_out) {
         loss_acc = warp_sum(loss_acc);
@@ -957,13 +1009,13 @@ extern "C" int gssdf_sdf_fwd_tc_launch(const gssdf_sdf_fwd_args *a, const gssdf:
 extern "C" int gssdf_sdf_bwd_tc_launch(const gssdf_sdf_bwd_args *a, const gssdf::GridGeom *g, gssdf_stream_t stream) {
     int rc = check_tc("sdf_bwd", a->net);
     if (rc) return rc;
-    GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdTcSmem));
+    GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_tc_smem(false)));
     const int64_t n_tiles = (a->n * (a->n_variants > 1 ? a->n_variants : 1) + 127) / 128;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sms);
-    sdf_bwd_tc_kernel<false><<<grid, kBwdTcThreads, kBwdTcSmem, (cudaStream_t)stream>>>(*a, TcLossArgs{}, *g, n_tiles);
+    sdf_bwd_tc_kernel<false, false><<<grid, kBwdTcThreads, bwd_tc_smem(false), (cudaStream_t)stream>>>(*a, TcLossArgs{}, *g, n_tiles);
     GSSDF_LAUNCH_OK("sdf_bwd_tc_kernel");
     return GSSDF_OK;
 }
@@ -992,14 +1044,18 @@ extern "C" int gssdf_sdf_train(const gssdf_sdf_train_args *t, gssdf_stream_t str
                   "sdf_train: the align loss needs n_variants 7 (numerical gradient)");
     GSSDF_REQUIRE(t->eikonal_mode == 1 || t->align_weight == 0.f, GSSDF_EINVAL, "sdf_train: align_weight needs eikonal_mode 1");
     const GridGeom g = make_grid(t->net);
-    GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdTcSmem));
+    GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_tc_smem(false)));
+    GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_tc_smem(true)));
     const int pt = 128 / t->n_variants;
     const int64_t n_tiles = (t->n + pt - 1) / pt;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sms);
-    sdf_bwd_tc_kernel<true><<<grid, kBwdTcThreads, kBwdTcSmem, (cudaStream_t)stream>>>(a, lo, g, n_tiles);
+    if (t->eikonal_mode == 1)
+        sdf_bwd_tc_kernel<true, true><<<grid, kBwdTcThreads, bwd_tc_smem(true), (cudaStream_t)stream>>>(a, lo, g, n_tiles);
+    else
+        sdf_bwd_tc_kernel<true, false><<<grid, kBwdTcThreads, bwd_tc_smem(false), (cudaStream_t)stream>>>(a, lo, g, n_tiles);
     GSSDF_LAUNCH_OK("sdf_train_kernel");
     return GSSDF_OK;
 }

@@ -146,7 +146,8 @@ class GsSdfStep:
     """
 
     def __init__(self, N, K, W, H, device, isect_cap, sdf_net_cfg, n_ray_samples=32768, sh_degree=3, origin=(0.0, 0.0, 0.0),
-                 map_size=14.0, bce_sigma=0.1, delta=None, eikonal_weight=0.1, gs_sdf_weight=1e-3, visible_thr=0.1, mlp_mode=None):
+                 map_size=14.0, bce_sigma=0.1, delta=None, eikonal_weight=0.1, gs_sdf_weight=1e-3, visible_thr=0.1, mlp_mode=None,
+                 eikonal_mode=None, align_weight=0.1):
         self.R = SplatRenderer(N, K, 1, W, H, device, isect_cap, sh_degree=sh_degree)
         self.dev, self.N, self.n_ray = device, N, n_ray_samples
         self.cfg = dict(sdf_net_cfg)
@@ -161,6 +162,11 @@ class GsSdfStep:
         tc_ok = self.cfg.get("hidden_dim", 64) == 64 and self.cfg.get("n_hidden", 3) <= 3
         self.mlp_mode = (1 if tc_ok else 0) if mlp_mode is None else int(mlp_mode)
         self.mlp_packed = torch.empty(cabi.sdf_mlp_packed_bytes(probe), dtype=torch.uint8, device=device) if self.mlp_mode == 1 else None
+        # eikonal: 1 = on the analytic gradient + align loss (reference default, config/base.yaml:13,32; fused tensor-core kernel only),
+        # 0 = on the 6-offset numerical gradient (k_numerical_grad)
+        self.eik_mode = (1 if self.mlp_mode == 1 else 0) if eikonal_mode is None else int(eikonal_mode)
+        assert self.eik_mode == 0 or self.mlp_mode == 1, "the analytic eikonal path lives in the fused tensor-core kernel (mlp_mode 1)"
+        self.align_w = float(align_weight) if self.eik_mode == 1 else 0.0
         # flat gradient: [splat | (pad to an even offset: the table gradient takes 8-byte vector REDs) | table | mlp]
         n_splat = self.R.flat_grad.numel()
         t0 = (n_splat + 1) // 2 * 2
@@ -203,7 +209,7 @@ class GsSdfStep:
         # [A] SDF stage on the ray samples (tensor-core mode: forward + losses + backward fused in one kernel)
         if self.mlp_mode == 1:
             cabi.sdf_train(net, ray_xyz, 7, self.delta, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.sdf_loss,
-                           self.table_grad, self.mlp_grad, None)
+                           self.table_grad, self.mlp_grad, None, eikonal_mode=self.eik_mode, align_weight=self.align_w)
         else:
             cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, self.ray_y1, None, n_variants=7, delta=self.delta)
             cabi.sdf_loss(n_ray, 7, self.ray_sdf, self.ray_y1, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.delta, self.sdf_loss,
@@ -217,7 +223,7 @@ class GsSdfStep:
         if self.mlp_mode == 1:
             cabi.sdf_train(net, samples, 7, self.delta, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
                            self.sdf_loss, self.table_grad, self.mlp_grad, self.v_samples, visibilities=R.r["visibilities"],
-                           visible_thr=self.vis_thr, n_live=n_live)
+                           visible_thr=self.vis_thr, n_live=n_live, eikonal_mode=self.eik_mode, align_weight=self.align_w)
         else:
             cabi.sdf_fwd(net, samples, self.gs_sdf, self.gs_y1, None, n_variants=7, delta=self.delta, n_live=n_live)
             cabi.sdf_loss(cap, 7, self.gs_sdf, self.gs_y1, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w, self.delta,

@@ -298,7 +298,8 @@ def test_full_step_tensor_core_equals_cuda_core_path():
     n_ray = 4096
     outs = []
     for mode in (0, 1):
-        G = render.GsSdfStep(N, (deg + 1) ** 2, W, H, dev, 300000, cfg, n_ray_samples=n_ray, sh_degree=deg, map_size=14.0, mlp_mode=mode)
+        G = render.GsSdfStep(N, (deg + 1) ** 2, W, H, dev, 300000, cfg, n_ray_samples=n_ray, sh_degree=deg, map_size=14.0, mlp_mode=mode,
+                             eikonal_mode=0)
         gen.manual_seed(5)
         table = (torch.rand(G.n_table, device=dev, generator=gen) * 2 - 1) * 0.1
         chunks, dims = [], [32, 64, 64, 64, 64, 2]

@@ -47,4 +47,14 @@ for mode in (0, 1):
         s.record()
         for _ in range(10): cabi.sdf_fwd(net, xb, sd, y1, None, n_variants=7, delta=0.01)
         e.record(); torch.cuda.synchronize(); tf = s.elapsed_time(e) / 10
-        print(f"  {name}: fwd {tf:.3f} ms  bwd {tb:.3f} ms")
+        line = f"  {name}: fwd {tf:.3f} ms  bwd {tb:.3f} ms"
+        if mode == 1:  # fused forward + losses + backward (gssdf_sdf_train), numerical and analytic eikonal
+            gt_b = torch.rand(nb, device=dev) * 0.2 - 0.1
+            ls = torch.zeros(1, device=dev)
+            for em, aw in ((0, 0.0), (1, 0.1)):
+                for _ in range(3): cabi.sdf_train(net, xb, 7, 0.01, gt_b, None, 10.0, 1.0, 0.1, 0.0, ls, tg, mg, vxb, eikonal_mode=em, align_weight=aw)
+                s.record()
+                for _ in range(10): cabi.sdf_train(net, xb, 7, 0.01, gt_b, None, 10.0, 1.0, 0.1, 0.0, ls, tg, mg, vxb, eikonal_mode=em, align_weight=aw)
+                e.record(); torch.cuda.synchronize()
+                line += f"  train[eik={em}] {s.elapsed_time(e) / 10:.3f} ms"
+        print(line)
