@@ -363,7 +363,8 @@ struct TcLossArgs {
     SdfLossCfg cfg;
     float *loss_out;
     int analytic;        // eikonal on the ANALYTIC gradient d sdf/dx (LocalMap::get_gradient(numerical = false), local_map.cpp:150-171)
-    float align_weight;  // |g_analytic - g_numerical.detach()|.mean() (neural_mapping.cpp:124-133); needs the 7-variant layout
+    float align_weight;  // |g_analytic - g_numerical.detach()|.mean() (neural_mapping.cpp:124-133)
+    const float *sdf_variants;  // [7n] precomputed sdf of the 7 variants (V == 1) or NULL (V == 7: evaluated in the tile)
 };
 
 template <bool FUSED, bool ANALYTIC>
@@ -534,7 +535,7 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
                 loss_acc += we * (nrm - 1.f) * (nrm - 1.f);
                 const float ke = nrm > 0.f ? 2.f * (nrm - 1.f) / nrm * we : 0.f;
                 cc[0] = ke * gx; cc[1] = ke * gy; cc[2] = ke * gz;
-                if (lo.align_weight > 0.f && V == 7) {
+                if (lo.align_weight > 0.f && (V == 7 || lo.sdf_variants)) {
                     const float wa = lo.align_weight / (3.f * nl);
                     const float *gn = s_gnum + tid * 3;
                     const float d0 = gx - gn[0], d1 = gy - gn[1], d2 = gz - gn[2];
@@ -759,7 +760,10 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
                 if (analytic) {  // the eikonal / align terms act on the analytic gradient: second-order phase below
                     cfg1.eikonal_weight = 0.f;
                     if (tid == 0) s_tbase[n_coll / PT] = base;  // slots of a batch are filled PT per tile (only a CTA's last tile is partial)
-                    if (V == 7) {
+                    if (V == 1 && lo.sdf_variants) {
+                        for (int v = 1; v < 7; ++v) sv[v] = __ldg(lo.sdf_variants + (int64_t)v * a.n + i);
+                    }
+                    if (V == 7 || lo.sdf_variants) {
                         const float inv2d = 0.5f / lo.cfg.delta;
                         s_gnum[(n_coll + tid) * 3 + 0] = (sv[1] - sv[2]) * inv2d;
                         s_gnum[(n_coll + tid) * 3 + 1] = (sv[3] - sv[4]) * inv2d;
@@ -1038,10 +1042,11 @@ extern "C" int gssdf_sdf_train(const gssdf_sdf_train_args *t, gssdf_stream_t str
     a.table_grad = t->table_grad; a.mlp_grad = t->mlp_grad; a.v_x = t->v_x;
     TcLossArgs lo{t->gt_sdf, t->weights, t->visibilities,
                   SdfLossCfg{t->bce_isigma, t->bce_weight, t->eikonal_weight, t->gs_sdf_weight, t->delta, t->visible_thr}, t->loss_out,
-                  t->eikonal_mode, t->align_weight};
+                  t->eikonal_mode, t->align_weight, t->n_variants == 1 ? t->sdf_variants : nullptr};
     GSSDF_REQUIRE(t->eikonal_mode == 0 || t->eikonal_mode == 1, GSSDF_EINVAL, "sdf_train: eikonal_mode must be 0 or 1");
-    GSSDF_REQUIRE(!(t->eikonal_mode == 1 && t->align_weight > 0.f) || t->n_variants == 7, GSSDF_EINVAL,
-                  "sdf_train: the align loss needs n_variants 7 (numerical gradient)");
+    GSSDF_REQUIRE(!(t->eikonal_mode == 1 && t->align_weight > 0.f) || t->n_variants == 7 || t->sdf_variants, GSSDF_EINVAL,
+                  "sdf_train: the align loss needs the numerical gradient: n_variants 7 or sdf_variants");
+    GSSDF_REQUIRE(!t->sdf_variants || t->delta > 0.f, GSSDF_EINVAL, "sdf_train: sdf_variants needs the delta they were evaluated with");
     GSSDF_REQUIRE(t->eikonal_mode == 1 || t->align_weight == 0.f, GSSDF_EINVAL, "sdf_train: align_weight needs eikonal_mode 1");
     const GridGeom g = make_grid(t->net);
     GSSDF_CUDA_OK(cudaFuncSetAttribute(sdf_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_tc_smem(false)));

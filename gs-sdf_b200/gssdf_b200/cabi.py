@@ -242,11 +242,12 @@ def sdf_loss(n, n_variants, sdf, y1, gt_sdf, weights, bce_isigma, bce_weight, ei
 
 def sdf_train(net, x, n_variants, delta, gt_sdf, weights, bce_isigma, bce_weight, eikonal_weight, gs_sdf_weight, loss_out,
               table_grad=None, mlp_grad=None, v_x=None, visibilities=None, visible_thr=0.0, n_live=None, eikonal_mode=0,
-              align_weight=0.0):
+              align_weight=0.0, sdf_variants=None):
     """sdf_fwd + sdf_loss + sdf_bwd fused into one persistent tensor-core kernel (net.mlp_mode must be 1)."""
     a = make_args("gssdf_sdf_train_args", n=x.shape[0], x=x, n_variants=n_variants, delta=delta, n_live=n_live, gt_sdf=gt_sdf,
                   weights=weights, visibilities=visibilities, visible_thr=visible_thr, bce_isigma=bce_isigma, bce_weight=bce_weight,
                   eikonal_weight=eikonal_weight, gs_sdf_weight=gs_sdf_weight, loss_out=loss_out, table_grad=table_grad,
-                  mlp_grad=mlp_grad, v_x=v_x, eikonal_mode=eikonal_mode, align_weight=align_weight)
+                  mlp_grad=mlp_grad, v_x=v_x, eikonal_mode=eikonal_mode, align_weight=align_weight,
+                  sdf_variants=sdf_variants)
     a.net = net
     check(lib().gssdf_sdf_train(_lib.C.byref(a), _stream()))

@@ -181,7 +181,7 @@ class GsSdfStep:
         self.v_samples = e(cap, 3)
         self.sdf_loss = torch.zeros(1, **f32)
 
-    KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 4  # + table cast + decoder weight image + 2 fused sdf train kernels (mlp_mode 1)
+    KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 6  # + table cast + decoder weight image + 2 x (7-variant forward, fused train) (mlp_mode 1)
 
     def _rebind_splat_grads(self, n_splat):
         R, N, K = self.R, self.R.N, self.R.K
@@ -208,8 +208,16 @@ class GsSdfStep:
         self.sdf_loss.zero_()
         # [A] SDF stage on the ray samples (tensor-core mode: forward + losses + backward fused in one kernel)
         if self.mlp_mode == 1:
-            cabi.sdf_train(net, ray_xyz, 7, self.delta, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.sdf_loss,
-                           self.table_grad, self.mlp_grad, None, eikonal_mode=self.eik_mode, align_weight=self.align_w)
+            if self.eik_mode == 1:  # reference default: forward-only pass over the 7 variants (numerical gradient of the align loss),
+                                    # then forward + losses + backward + double backward on the base points only
+                if self.align_w > 0:
+                    cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, None, None, n_variants=7, delta=self.delta)
+                cabi.sdf_train(net, ray_xyz, 1, self.delta, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.sdf_loss,
+                               self.table_grad, self.mlp_grad, None, eikonal_mode=1, align_weight=self.align_w,
+                               sdf_variants=self.ray_sdf if self.align_w > 0 else None)
+            else:
+                cabi.sdf_train(net, ray_xyz, 7, self.delta, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.sdf_loss,
+                               self.table_grad, self.mlp_grad, None)
         else:
             cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, self.ray_y1, None, n_variants=7, delta=self.delta)
             cabi.sdf_loss(n_ray, 7, self.ray_sdf, self.ray_y1, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.delta, self.sdf_loss,
@@ -221,9 +229,17 @@ class GsSdfStep:
         # [C] coupling on the stochastic splat samples (rows < nnz, counted on the device)
         samples, n_live = R.p["samples"], R.counts  # counts[0] == nnz
         if self.mlp_mode == 1:
-            cabi.sdf_train(net, samples, 7, self.delta, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
-                           self.sdf_loss, self.table_grad, self.mlp_grad, self.v_samples, visibilities=R.r["visibilities"],
-                           visible_thr=self.vis_thr, n_live=n_live, eikonal_mode=self.eik_mode, align_weight=self.align_w)
+            if self.eik_mode == 1:
+                if self.align_w > 0:
+                    cabi.sdf_fwd(net, samples, self.gs_sdf, None, None, n_variants=7, delta=self.delta, n_live=n_live)
+                cabi.sdf_train(net, samples, 1, self.delta, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
+                               self.sdf_loss, self.table_grad, self.mlp_grad, self.v_samples, visibilities=R.r["visibilities"],
+                               visible_thr=self.vis_thr, n_live=n_live, eikonal_mode=1, align_weight=self.align_w,
+                               sdf_variants=self.gs_sdf if self.align_w > 0 else None)
+            else:
+                cabi.sdf_train(net, samples, 7, self.delta, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
+                               self.sdf_loss, self.table_grad, self.mlp_grad, self.v_samples, visibilities=R.r["visibilities"],
+                               visible_thr=self.vis_thr, n_live=n_live)
         else:
             cabi.sdf_fwd(net, samples, self.gs_sdf, self.gs_y1, None, n_variants=7, delta=self.delta, n_live=n_live)
             cabi.sdf_loss(cap, 7, self.gs_sdf, self.gs_y1, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w, self.delta,

@@ -49,7 +49,7 @@ const char *gssdf_last_error(void);
 /* "gssdf_b200 <ver> sm_100a" */
 const char *gssdf_version(void);
 /* Argument structs grow between revisions: a binding compiled against this header must see the same number from the library. */
-#define GSSDF_ABI_REVISION 7
+#define GSSDF_ABI_REVISION 8
 int32_t gssdf_abi_revision(void);
 
 /* Device-side counters shared by the stages of one render. Zeroed by gssdf_project2dgs_fwd. */
@@ -474,7 +474,11 @@ typedef struct gssdf_sdf_train_args {
                                    (TB/tcnn_binding.cpp:151-192, grid.h:352-456,624-647). x carries no gradient from these terms
                                    (both call sites pass detached points, neural_mapping.cpp:183,450). */
     float align_weight;      /* mode 1 only: + align_weight * mean |g_analytic - g_numerical.detach()| (neural_mapping.cpp:124-133);
-                                needs n_variants 7 (the six offsets are evaluated forward-only); 0 disables it */
+                                the numerical gradient comes either from n_variants 7 (the six offsets evaluated forward-only in the same
+                                tiles) or from sdf_variants; 0 disables it */
+    const float *sdf_variants; /* mode 1, n_variants 1: [7n] sdf values from gssdf_sdf_fwd(n_variants = 7, same x / delta) or NULL. The
+                                cheapest arrangement for the reference default: one forward-only pass over the 7n evaluations, then this
+                                kernel on the n base points only */
 } gssdf_sdf_train_args;
 int gssdf_sdf_train(const gssdf_sdf_train_args *a, gssdf_stream_t stream);
 

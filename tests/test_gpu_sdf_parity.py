@@ -365,7 +365,15 @@ def test_sdf_train_analytic_eikonal_double_backward(oracle, align_w, n):
     loss = torch.zeros(1, device=dev)
     tg, mg = torch.zeros(n_params, device=dev), torch.zeros(len(mlp), device=dev)
     cabi.sdf_train(net, xt, V, delta, t(gt), None, isg, bce_w, eik_w, 0.0, loss, tg, mg, None, eikonal_mode=1, align_weight=align_w)
+    # the split arrangement of the training step: forward-only pass over the 7 variants, then the fused kernel on the base points
+    loss_s = torch.zeros(1, device=dev)
+    tg_s, mg_s, sdf7 = torch.zeros(n_params, device=dev), torch.zeros(len(mlp), device=dev), torch.empty(7 * n, device=dev)
+    cabi.sdf_fwd(net, xt, sdf7, None, None, n_variants=7, delta=delta)
+    cabi.sdf_train(net, xt, 1, delta, t(gt), None, isg, bce_w, eik_w, 0.0, loss_s, tg_s, mg_s, None, eikonal_mode=1, align_weight=align_w,
+                   sdf_variants=sdf7 if align_w > 0 else None)
     torch.cuda.synchronize()
+    assert abs(float(loss_s) - float(loss)) <= 1e-5 * abs(float(loss))
+    assert float((mg_s - mg).norm()) <= 1e-4 * float(mg.norm()) and float((tg_s - tg).norm()) <= 2e-3 * float(tg.norm())
     assert keep.mean() > 0.98
     assert abs(float(loss) - (l1 + l2)) <= 2e-3 * abs(l1 + l2), (float(loss), l1, l2)
     r_mg, r_tg = mg1 + mg2, tg1 + tg2
