@@ -275,6 +275,11 @@ def sdf_bwd(x, table, mlp_params, v_sdf, v_y1, hidden=64, n_hidden=3, **grid):
     return tg, d_mlp, dx
 
 
+def set_threads(n):
+    """OpenMP threads of the oracle library (torchrun forces OMP_NUM_THREADS=1 into its ranks)."""
+    lib().oracle_set_threads(C.c_int(int(n)))
+
+
 def set_half_rounding(on):
     """Test hook: switch the fp16 rounding points of the SDF oracle off to finite-difference the restated math."""
     lib().oracle_set_half_rounding(C.c_int(1 if on else 0))

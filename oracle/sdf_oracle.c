@@ -52,6 +52,17 @@ static double h_to_f64(uint16_t h) {
     else v = ldexp(1.0 + man / 1024.0, exp - 15);
     return sign ? -v : v;
 }
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* torchrun exports OMP_NUM_THREADS=1 into every rank: the CPU baseline asks for the host's cores explicitly */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 static int g_half_rounding = 1; /* tests of the restated MATH (finite differences) switch the fp16 rounding points off */
 void oracle_set_half_rounding(int on) { g_half_rounding = on; }
 static double rh(double d) { return g_half_rounding ? h_to_f64(f64_to_h(d)) : d; } /* round a real to binary16 */
