@@ -247,7 +247,8 @@ def main():
     W, H, N, deg, isect_cap = WORKLOADS[args.workload]
     cfg = {"workload": f"{args.workload}: {W}x{H}, {N} splats, SH deg {deg}, synthetic box scene seed 0 (SURVEY 8d), tile 16, packed, "
                        f"1 camera/rank/step", "timing": "CUDA events; inputs (232 B/splat state + images) exceed the 126 MB L2, no flush",
-           "parallelism": f"image-parallel dp{world}, replicated splats, NCCL all-reduce of the flat gradient" if world > 1 else "single GPU"}
+           "parallelism": (f"image-parallel dp{world}, replicated state, 2 NCCL all-reduces/step: SDF segment under the render backward, splat "
+                           f"segment under the next step's SDF stage") if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -323,24 +324,33 @@ def main():
     loss_host = torch.empty(1).pin_memory()
 
     n_splat_grad = R.flat_grad.numel()
-    pending = []
+    pending, pending_splat = [], []
 
-    def reduce_sdf_grads(g):  # hash-table + decoder gradients are final after [C]: reduce them under the render backward
+    # Data-parallel gradient exchange, two NCCL all-reduces per step, both overlapped with compute that does not depend on them:
+    #   hash-table + decoder segment (61 MB): final after stage [C]  -> reduced under the render backward [D] of the same step
+    #   splat segment (236 MB)              : final after [D]        -> reduced under stage [A] of the NEXT step, which reads only SDF
+    #                                          parameters; it is waited for before the next render touches the splats (before_render)
+    def reduce_sdf_grads(g):
         pending.append(dist.all_reduce(g, async_op=True))
 
-    def reduce_rest():
-        dist.all_reduce(G.flat_grad[:n_splat_grad])  # splat gradients; the optimiser scales by 1/world
+    def before_render():
+        while pending_splat:
+            pending_splat.pop().wait()
+
+    def finish_step():
+        pending_splat.append(dist.all_reduce(G.flat_grad[:n_splat_grad], async_op=True))  # the optimiser scales by 1/world
         while pending:
             pending.pop().wait()
 
     hook = reduce_sdf_grads if world > 1 else None
+    pre = before_render if world > 1 else None
 
     def step_resident(i):
         V, Kc = dev_cams[i % n_cams]
         randn_buf.normal_()  # the reference draws randns on the device every render (Projection.cpp:728)
-        loss, _sdf_loss = G.step(sc, table, mlp, V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook)
+        loss, _sdf_loss = G.step(sc, table, mlp, V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook, before_render=pre)
         if world > 1:
-            reduce_rest()
+            finish_step()
         return loss
 
     # end-to-end path: every step's inputs (camera pose, intrinsics, ground-truth image) come from pinned HOST memory and the loss is
@@ -369,10 +379,10 @@ def main():
         cur = torch.cuda.current_stream()
         cur.wait_event(sl["ready"])
         randn_buf.normal_()
-        loss, _sdf_loss = G.step(sc, table, mlp, sl["V"], sl["K"], sl["gt"], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook)
+        loss, _sdf_loss = G.step(sc, table, mlp, sl["V"], sl["K"], sl["gt"], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook, before_render=pre)
         sl["free"].record(cur)
         if world > 1:
-            reduce_rest()
+            finish_step()
         loss_host.copy_(loss, non_blocking=True)
         cur.synchronize()  # the caller reads the loss every step (neural_mapping.cpp:505-514)
         return float(loss_host[0])
@@ -390,6 +400,8 @@ def main():
         ev0.record()
         for i in range(steps):
             fn(i)
+        if world > 1:
+            before_render()  # the last step's splat all-reduce belongs to the timed region
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -418,6 +430,8 @@ def main():
     for i in range(args.steps):
         R.prof_fwd, R.prof_bwd = prof_f[i], prof_b[i]
         step_resident(i)
+    if world > 1:
+        before_render()  # the last step's splat all-reduce belongs to the timed region
     ev1.record()
     barrier()
     fwd_ms = [a.elapsed_time(b) for a, b in prof_f]

@@ -194,9 +194,14 @@ class GsSdfStep:
     def refresh_table(self, table_f32):
         cabi.sdf_table_to_half(table_f32, self.table_half)
 
-    def step(self, scene, table_f32, mlp, viewmats, Ks, gt_image, ray_xyz, ray_gt_sdf, randns=None, on_sdf_grads_ready=None):
-        """on_sdf_grads_ready(table_and_mlp_grad): called once the hash-table / decoder gradients are final (after [C]) so a
-        data-parallel caller can start reducing them while the render backward [D] is still running."""
+    def step(self, scene, table_f32, mlp, viewmats, Ks, gt_image, ray_xyz, ray_gt_sdf, randns=None, on_sdf_grads_ready=None,
+             before_render=None):
+        """Hooks for a data-parallel caller (both optional):
+        on_sdf_grads_ready(table_and_mlp_grad): the hash-table / decoder gradients are final (after [C]) -> start reducing them while the
+            render backward [D] is still running.
+        before_render(): called after stage [A] and before anything touches the splat parameters or their gradient segment. Stage [A]
+            depends on the SDF parameters only, so the PREVIOUS step's splat-gradient all-reduce (and splat optimiser step) may still be
+            in flight while [A] runs; the caller waits for them here."""
         R, n_ray, cap = self.R, self.n_ray, self.R.cap
         # fp32 master -> fp16 shadow once per step (the optimiser moved the master; the reference casts on EVERY forward)
         cabi.sdf_table_to_half(table_f32, self.table_half)
@@ -204,7 +209,8 @@ class GsSdfStep:
             cabi.sdf_mlp_pack(cabi.sdf_net(self.table_half, mlp, **self.cfg), self.mlp_packed)
         net = cabi.sdf_net(self.table_half, mlp, origin=self.origin, inv_size=self.inv_size, mlp_mode=self.mlp_mode,
                            mlp_packed=self.mlp_packed, **self.cfg)
-        self.flat_grad.zero_()
+        t0 = self.table_grad.storage_offset()
+        self.flat_grad[t0:].zero_()  # table + decoder segment; the splat segment is cleared after before_render()
         self.sdf_loss.zero_()
         # [A] SDF stage on the ray samples (tensor-core mode: forward + losses + backward fused in one kernel)
         if self.mlp_mode == 1:
@@ -223,6 +229,9 @@ class GsSdfStep:
             cabi.sdf_loss(n_ray, 7, self.ray_sdf, self.ray_y1, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.delta, self.sdf_loss,
                           self.ray_vs, self.ray_vy)
             cabi.sdf_bwd(net, ray_xyz, self.ray_vs, self.ray_vy, self.table_grad, self.mlp_grad, None, n_variants=7, delta=self.delta)
+        if before_render is not None:
+            before_render()
+        self.flat_grad[:t0].zero_()
         # [B] render
         R.forward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, randns,
                   raw=scene.get("raw"))
