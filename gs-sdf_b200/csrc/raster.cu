@@ -170,6 +170,7 @@ __device__ __forceinline__ void issue_batch(Stage &st, uint64_t *bar, const floa
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+template <bool DISTORT>  // false: render_distort / render_Ts are not requested (GS-SDF never uses the distortion loss)
 __global__ void __launch_bounds__(kRasterThreads)
 raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restrict__ rec, const int2 *__restrict__ clist,
                       const int32_t *__restrict__ ccount, int tw, int th) {
@@ -244,11 +245,13 @@ raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restric
                 pc0 += r2.z * vis; pc1 += r2.w * vis; pc2 += r3.x * vis;
                 dout += depth * vis;
                 pn0 += r3.y * vis; pn1 += r3.z * vis; pn2 += r3.w * vis;
-                const float A = 1.f - T;
-                const float m = kFarN / (kFarN - kNearN) * (1.f - kNearN / depth);
-                distort += (m * m * A + M1 - 2.f * m * M2) * vis;
-                M1 += m * m * vis;
-                M2 += m * vis;
+                if (DISTORT) {
+                    const float A = 1.f - T;
+                    const float m = kFarN / (kFarN - kNearN) * (1.f - kNearN / depth);
+                    distort += (m * m * A + M1 - 2.f * m * M2) * vis;
+                    M1 += m * m * vis;
+                    M2 += m * vis;
+                }
                 if (T > 0.5f) { median_depth = depth; median_idx = sorted_idx; }
                 cur_idx = sorted_idx;
                 T = next_T;
@@ -281,7 +284,7 @@ raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restric
     if (inside) {
         a.render_depths[pix] = dout;
         a.render_alphas[pix] = 1.f - T;
-        reinterpret_cast<float2 *>(a.render_Ts)[pix] = make_float2(M1, M2);
+        if (DISTORT) reinterpret_cast<float2 *>(a.render_Ts)[pix] = make_float2(M1, M2);
         float b0 = 0.f, b1 = 0.f, b2 = 0.f;
         if (a.backgrounds) { b0 = a.backgrounds[3 * ti.cam]; b1 = a.backgrounds[3 * ti.cam + 1]; b2 = a.backgrounds[3 * ti.cam + 2]; }
         a.render_colors[3 * pix] = pc0 + T * b0;
@@ -291,7 +294,7 @@ raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restric
         a.render_normals[3 * pix + 1] = pn1;
         a.render_normals[3 * pix + 2] = pn2;
         a.last_ids[pix] = cur_idx;
-        a.render_distort[pix] = distort;
+        if (DISTORT) a.render_distort[pix] = distort;
         a.render_median[pix] = median_depth;
         a.median_ids[pix] = median_idx;
     }
@@ -689,7 +692,7 @@ extern "C" int gssdf_raster2dgs_fwd(const gssdf_raster2dgs_fwd_args *a, gssdf_st
     int rc = check_raster_common("raster2dgs_fwd", a->C, a->image_width, a->image_height, a->tile_size, a->channels);
     if (rc) return rc;
     GSSDF_REQUIRE(a->counts && a->offsets && a->render_colors && a->render_depths && a->render_alphas && a->render_normals &&
-                      a->render_distort && a->render_median && a->render_Ts && a->last_ids && a->median_ids,
+                      a->render_median && a->last_ids && a->median_ids && (a->render_distort != nullptr) == (a->render_Ts != nullptr),
                   GSSDF_EINVAL, "raster2dgs_fwd: null output / counts / offsets");
     GSSDF_REQUIRE(a->cap == 0 || (a->ray_transforms && a->colors && a->opacities && a->normals && a->flatten_ids && a->visibilities),
                   GSSDF_EINVAL, "raster2dgs_fwd: null splat input");
@@ -703,9 +706,13 @@ extern "C" int gssdf_raster2dgs_fwd(const gssdf_raster2dgs_fwd_args *a, gssdf_st
     rc = pack_and_cull("raster2dgs_fwd", w, a->counts, a->C, a->image_width, a->image_height, a->cap, a->ray_transforms, a->colors,
                        a->opacities, a->normals, a->offsets, a->flatten_ids, a->visibilities, 1, st);
     if (rc) return rc;
-    GSSDF_CUDA_OK(cudaFuncSetAttribute(raster2dgs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(Stage))));
+    GSSDF_CUDA_OK(cudaFuncSetAttribute(raster2dgs_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(Stage))));
+    GSSDF_CUDA_OK(cudaFuncSetAttribute(raster2dgs_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(Stage))));
     if (a->prof_start) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_start, st));
-    raster2dgs_fwd_kernel<<<a->C * tw * th, kRasterThreads, 2 * sizeof(Stage), st>>>(*a, w.rec, w.clist, w.ccount, tw, th);
+    if (a->render_distort)
+        raster2dgs_fwd_kernel<true><<<a->C * tw * th, kRasterThreads, 2 * sizeof(Stage), st>>>(*a, w.rec, w.clist, w.ccount, tw, th);
+    else
+        raster2dgs_fwd_kernel<false><<<a->C * tw * th, kRasterThreads, 2 * sizeof(Stage), st>>>(*a, w.rec, w.clist, w.ccount, tw, th);
     GSSDF_LAUNCH_OK("raster2dgs_fwd_kernel");
     if (a->prof_stop) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_stop, st));
     return GSSDF_OK;

@@ -240,6 +240,7 @@ sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
     const int64_t n_eval = a.n * max(a.n_variants, 1);
     const int64_t n_live = a.n_live ? min((int64_t)*a.n_live, a.n) : a.n;
     if (base % a.n >= n_live && base % a.n + TM <= a.n) return;  // CTA-uniform: the whole tile is beyond the live rows
+    if (a.skip_base_variant && base + TM <= a.n) return;           // CTA-uniform: only variant-0 evaluations in this tile
     const int tm = (int)min((int64_t)TM, n_eval - base);
     const __half2 *table = reinterpret_cast<const __half2 *>(a.net.table_half);
     const unsigned char *wimg = reinterpret_cast<const unsigned char *>(a.net.mlp_packed);

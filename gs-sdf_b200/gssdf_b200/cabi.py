@@ -134,7 +134,7 @@ def raster2dgs_fwd(Cn, W, H, tile_size, channels, cap, counts, means2d, ray_tran
                   colors=colors, opacities=opacities, normals=normals, backgrounds=backgrounds, offsets=offsets,
                   flatten_ids=flatten_ids, isect_cap=isect_cap, render_colors=out["render_colors"], render_depths=out["render_depths"],
                   render_alphas=out["render_alphas"], render_normals=out["render_normals"],
-                  render_distort=out["render_distort"], render_median=out["render_median"], render_Ts=out["render_Ts"],
+                  render_distort=out.get("render_distort"), render_median=out["render_median"], render_Ts=out.get("render_Ts"),
                   last_ids=out["last_ids"], median_ids=out["median_ids"], visibilities=out["visibilities"], workspace=w,
                   workspace_bytes=w.numel(), prof_start=prof[0].cuda_event if prof else None,
                   prof_stop=prof[1].cuda_event if prof else None)
@@ -218,8 +218,9 @@ def sdf_table_to_half(table_f32, table_f16):
                                         _lib.C.c_int64(table_f32.numel()), _stream()))
 
 
-def sdf_fwd(net, x, sdf, y1=None, feat=None, n_variants=1, delta=0.0, n_live=None):
-    a = make_args("gssdf_sdf_fwd_args", n=x.shape[0], x=x, sdf=sdf, y1=y1, feat=feat, n_variants=n_variants, delta=delta, n_live=n_live)
+def sdf_fwd(net, x, sdf, y1=None, feat=None, n_variants=1, delta=0.0, n_live=None, skip_base_variant=False):
+    a = make_args("gssdf_sdf_fwd_args", n=x.shape[0], x=x, sdf=sdf, y1=y1, feat=feat, n_variants=n_variants, delta=delta, n_live=n_live,
+                  skip_base_variant=int(bool(skip_base_variant)))
     a.net = net
     check(lib().gssdf_sdf_fwd(_lib.C.byref(a), _stream()))
 

@@ -36,10 +36,10 @@ class SplatRenderer:
         self.conics = e(cap, 8) if self.presort_cull else None
         self.flatten_ids = e(self.isect_cap, **i32)
         self.offsets = e(C, self.th, self.tw, **i32)
+        # no render_distort / render_Ts: the distortion loss is off in GS-SDF (distloss = false), the kernel then skips those terms
         self.r = dict(render_colors=e(C, H, W, 3), render_depths=e(C, H, W, 1), render_alphas=e(C, H, W, 1),
-                      render_normals=e(C, H, W, 3), render_distort=e(C, H, W, 1), render_median=e(C, H, W, 1),
-                      render_Ts=e(C, H, W, 2), last_ids=e(C, H, W, **i32), median_ids=e(C, H, W, **i32),
-                      visibilities=e(cap, 1))
+                      render_normals=e(C, H, W, 3), render_median=e(C, H, W, 1),
+                      last_ids=e(C, H, W, **i32), median_ids=e(C, H, W, **i32), visibilities=e(cap, 1))
         self.out_colors, self.out_normals = e(C, H, W, 4), e(C, H, W, 3)
         # cotangents
         self.v_out_colors, self.v_out_normals = e(C, H, W, 4), torch.zeros(C, H, W, 3, **f32)
@@ -105,7 +105,7 @@ class SplatRenderer:
                              self.v_r["normals"])
         cabi.raster2dgs_bwd(C, W, H, self.tile, 3, cap, self.counts, self.p["means2d"], self.p["ray_transforms"], self.colors,
                             self.p["pt_opacities"], self.p["normals"], None, self.offsets, self.flatten_ids,
-                            self.r["render_alphas"], self.r["render_Ts"], self.r["last_ids"], self.r["median_ids"],
+                            self.r["render_alphas"], None, self.r["last_ids"], self.r["median_ids"],
                             self.v_r["colors"], self.v_r["depths"], self.v_r["alphas"], self.v_r["normals"],
                             self.v_r["median"], self.g, self.raster_ws, prof=self.prof_bwd, isect_cap=self.isect_cap, reuse_fwd=True)
         cabi.view_colors_bwd(viewmats, means, sh, self.sh_degree, cap, self.counts, self.p["camera_ids"],
@@ -217,7 +217,7 @@ class GsSdfStep:
             if self.eik_mode == 1:  # reference default: forward-only pass over the 7 variants (numerical gradient of the align loss),
                                     # then forward + losses + backward + double backward on the base points only
                 if self.align_w > 0:
-                    cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, None, None, n_variants=7, delta=self.delta)
+                    cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, None, None, n_variants=7, delta=self.delta, skip_base_variant=True)
                 cabi.sdf_train(net, ray_xyz, 1, self.delta, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.sdf_loss,
                                self.table_grad, self.mlp_grad, None, eikonal_mode=1, align_weight=self.align_w,
                                sdf_variants=self.ray_sdf if self.align_w > 0 else None)
@@ -240,7 +240,7 @@ class GsSdfStep:
         if self.mlp_mode == 1:
             if self.eik_mode == 1:
                 if self.align_w > 0:
-                    cabi.sdf_fwd(net, samples, self.gs_sdf, None, None, n_variants=7, delta=self.delta, n_live=n_live)
+                    cabi.sdf_fwd(net, samples, self.gs_sdf, None, None, n_variants=7, delta=self.delta, n_live=n_live, skip_base_variant=True)
                 cabi.sdf_train(net, samples, 1, self.delta, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
                                self.sdf_loss, self.table_grad, self.mlp_grad, self.v_samples, visibilities=R.r["visibilities"],
                                visible_thr=self.vis_thr, n_live=n_live, eikonal_mode=1, align_weight=self.align_w,

@@ -49,7 +49,7 @@ const char *gssdf_last_error(void);
 /* "gssdf_b200 <ver> sm_100a" */
 const char *gssdf_version(void);
 /* Argument structs grow between revisions: a binding compiled against this header must see the same number from the library. */
-#define GSSDF_ABI_REVISION 8
+#define GSSDF_ABI_REVISION 9
 int32_t gssdf_abi_revision(void);
 
 /* Device-side counters shared by the stages of one render. Zeroed by gssdf_project2dgs_fwd. */
@@ -260,7 +260,8 @@ typedef struct gssdf_raster2dgs_fwd_args {
     float *render_normals;       /* [C,H,W,3] */
     float *render_distort;       /* [C,H,W,1] */
     float *render_median;        /* [C,H,W,1] */
-    float *render_Ts;            /* [C,H,W,2] saved for backward */
+    float *render_Ts;            /* [C,H,W,2] saved for the distortion backward. render_distort and render_Ts may BOTH be NULL: the
+                                    distortion terms are then not computed (GS-SDF: distloss = false, neural_gaussian.cpp:224) */
     int32_t *last_ids;           /* [C,H,W]   saved for backward */
     int32_t *median_ids;         /* [C,H,W]   saved for backward */
     float *visibilities;         /* [cap,1] */
@@ -409,6 +410,8 @@ typedef struct gssdf_sdf_fwd_args {
     float *sdf;       /* [n_variants*n] decoder output 0 */
     float *y1;        /* [n_variants*n] decoder output 1 (raw; isigma = 1 + softplus_100(y1) * k_bce_isigma) or NULL */
     float *feat;      /* [n_variants*n, L*F] encoding (fp16-exact values) or NULL */
+    int32_t skip_base_variant; /* 1 (n_variants 7): tiles that hold only variant-0 evaluations are skipped (their outputs stay untouched):
+                                  the caller needs the six offsets only (numerical gradient next to gssdf_sdf_train on the base points) */
 } gssdf_sdf_fwd_args;
 int gssdf_sdf_fwd(const gssdf_sdf_fwd_args *a, gssdf_stream_t stream);
 
