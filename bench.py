@@ -123,6 +123,24 @@ def ncu_traffic(kernel):
         return None
 
 
+def cpu_dssim(x, y, w):
+    """loss::dssim_loss on the host (numpy + scipy separable correlation, the reference's 11-tap window): w * (1 - mean SSIM) and d/dx."""
+    from scipy.ndimage import correlate1d
+    g = np.array([np.exp(-(np.floor((i - 11) / 2.0) ** 2) / 4.5) for i in range(11)], np.float32)
+    g = (g / g.sum()).astype(np.float64)
+    cv = lambda t, k: correlate1d(correlate1d(t, k, axis=0, mode="constant"), k, axis=1, mode="constant")
+    x, y = x.astype(np.float64), y.astype(np.float64)
+    mu1, mu2, s11, s22, s12 = cv(x, g), cv(y, g), cv(x * x, g), cv(y * y, g), cv(x * y, g)
+    A1, A2 = 2 * mu1 * mu2 + 1e-4, 2 * (s12 - mu1 * mu2) + 9e-4
+    B1, B2 = mu1 * mu1 + mu2 * mu2 + 1e-4, (s11 - mu1 * mu1) + (s22 - mu2 * mu2) + 9e-4
+    S = A1 * A2 / (B1 * B2)
+    dm = 2 * mu2 * (A2 - A1) / (B1 * B2) - S * (2 * mu1 / B1 - 2 * mu1 / B2)
+    d11, d12 = -S / B2, 2 * A1 / (B1 * B2)
+    gf = g[::-1].copy()
+    grad = (cv(dm, gf) + 2 * x * cv(d11, gf) + y * cv(d12, gf)) * (-w / S.size)
+    return w * (1 - S.mean()), grad.astype(np.float32)
+
+
 def cpu_oracle_step(O, S, sc, V, K, W, H, deg, rn, gt):
     """One hot-path step on the CPU oracle port (fp32 restatement, OpenMP)."""
     p = O.project2dgs_fwd(sc["means"], sc["quats"], sc["scales"], V, K, W, H, S.NEAR, S.FAR, 0.0, rn, "f32")
@@ -136,8 +154,13 @@ def cpu_oracle_step(O, S, sc, V, K, W, H, deg, rn, gt):
     out = np.concatenate([r["render_colors"], ed], -1)
     d = out - gt
     npx = W * H
-    loss = np.abs(d[..., :3]).sum() / (3 * npx) + 0.1 * np.abs(d[..., 3:]).sum() / npx
-    v_out = np.sign(d) * np.array([1 / (3 * npx)] * 3 + [0.1 / npx], np.float32)
+    # photometric loss of the step: 0.8 L1 + 0.2 (1 - SSIM) on rgb (config/base.yaml:35-36) + 0.1 L1 on the expected depth
+    loss = 0.8 * np.abs(d[..., :3]).sum() / (3 * npx) + 0.1 * np.abs(d[..., 3:]).sum() / npx
+    v_out = np.sign(d) * np.array([0.8 / (3 * npx)] * 3 + [0.1 / npx], np.float32)
+    for ch in range(3):
+        l_s, g_s = cpu_dssim(out[0, :, :, ch], gt[0, :, :, ch], 0.2 / 3)
+        loss += l_s
+        v_out[0, :, :, ch] += g_s
     fin = np.isfinite(r["render_depths"] / np.where(r["render_alphas"] == 0, np.nan, r["render_alphas"]))
     v_dep = np.where(fin, v_out[..., 3:] / np.where(fin, r["render_alphas"], 1), 0).astype(np.float32)
     v_alp = np.where(fin, -v_out[..., 3:] * r["render_depths"] / np.where(fin, r["render_alphas"], 1) ** 2, 0).astype(np.float32)

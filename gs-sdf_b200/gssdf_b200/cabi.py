@@ -252,3 +252,12 @@ def sdf_train(net, x, n_variants, delta, gt_sdf, weights, bce_isigma, bce_weight
                   sdf_variants=sdf_variants)
     a.net = net
     check(lib().gssdf_sdf_train(_lib.C.byref(a), _stream()))
+
+
+def dssim_loss(Cn, W, H, out_colors, gt, w_dssim, loss_out, v_out_colors, ws):
+    """loss_out += w_dssim * (1 - SSIM(rgb, gt_rgb)); v_out_colors[..., :3] += gradient (call after l1_loss)."""
+    need = lib().gssdf_dssim_workspace_bytes(Cn, W, H)
+    w = ws.get(need)
+    a = make_args("gssdf_dssim_loss_args", C=Cn, image_width=W, image_height=H, out_colors=out_colors, gt=gt, w_dssim=w_dssim,
+                  loss_out=loss_out, v_out_colors=v_out_colors, workspace=w, workspace_bytes=w.numel())
+    check(lib().gssdf_dssim_loss(_lib.C.byref(a), _stream()))

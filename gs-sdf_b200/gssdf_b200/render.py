@@ -60,6 +60,7 @@ class SplatRenderer:
         self.ws = cabi.Workspace(device)
         # dedicated raster workspace (records, conics, culled lists | gradient records): the backward reuses the forward's part
         self.raster_ws = cabi.Workspace(device)
+        self.loss_ws = cabi.Workspace(device)  # DSSIM derivative maps
         self.raster_ws.get(cabi.lib().gssdf_raster2dgs_bwd_workspace_bytes(C, W, H, cap, cabi._lib.C.c_int64(self.isect_cap)))
         self.prof_fwd = self.prof_bwd = None  # optional (start, stop) torch.cuda.Event pairs around the raster kernels
 
@@ -88,7 +89,7 @@ class SplatRenderer:
 
     # -- loss + backward -----------------------------------------------------------------------
     def backward(self, means, quats, scales, opacities, sh, viewmats, Ks, gt, randns=None, w_rgb=1.0, w_depth=0.1, v_samples=None,
-                 zero_grads=True, raw=None):
+                 zero_grads=True, raw=None, w_dssim=0.0):
         """With raw parameters the flat gradient holds dL/d(offsets|quats|log-scales|logits|features_dc|features_rest); the SH segment
         keeps its [N,K,3] size, laid out as dc [N,1,3] followed by rest [N,K-1,3]."""
         C, W, H, cap = self.C, self.W, self.H, self.cap
@@ -100,6 +101,8 @@ class SplatRenderer:
         if zero_grads:
             self.flat_grad.zero_()
         cabi.l1_loss(C, W, H, self.out_colors, gt, w_rgb, w_depth, self.loss, self.v_out_colors)
+        if w_dssim > 0:  # + w_dssim * (1 - SSIM(rgb, gt)) (loss::dssim_loss), gradient added to the colour cotangent
+            cabi.dssim_loss(C, W, H, self.out_colors, gt, w_dssim, self.loss, self.v_out_colors, self.loss_ws)
         cabi.render_post_bwd(C, W, H, viewmats, self.r["render_depths"], self.r["render_alphas"], self.v_out_colors,
                              self.v_out_normals, None, self.v_r["colors"], self.v_r["depths"], self.v_r["alphas"],
                              self.v_r["normals"])
@@ -147,13 +150,15 @@ class GsSdfStep:
 
     def __init__(self, N, K, W, H, device, isect_cap, sdf_net_cfg, n_ray_samples=32768, sh_degree=3, origin=(0.0, 0.0, 0.0),
                  map_size=14.0, bce_sigma=0.1, delta=None, eikonal_weight=0.1, gs_sdf_weight=1e-3, visible_thr=0.1, mlp_mode=None,
-                 eikonal_mode=None, align_weight=0.1):
+                 eikonal_mode=None, align_weight=0.1, rgb_weight=0.8, dssim_weight=0.2, depth_weight=0.1):
         self.R = SplatRenderer(N, K, 1, W, H, device, isect_cap, sh_degree=sh_degree)
         self.dev, self.N, self.n_ray = device, N, n_ray_samples
         self.cfg = dict(sdf_net_cfg)
         self.origin, self.inv_size = tuple(origin), 1.0 / map_size
         self.bce_isigma, self.delta = 1.0 / bce_sigma, (delta if delta is not None else bce_sigma)  # k_sample_std = k_bce_sigma
         self.eik_w, self.gs_sdf_w, self.vis_thr = eikonal_weight, gs_sdf_weight, visible_thr
+        # photometric loss: k_rgb_weight * L1 + k_dssim_weight * (1 - SSIM) (config/base.yaml:35-36) (+ an L1 on the expected depth)
+        self.rgb_w, self.dssim_w, self.depth_w = rgb_weight, dssim_weight, depth_weight
         f32 = dict(dtype=torch.float32, device=device)
         probe = cabi.sdf_net(torch.zeros(1, **f32), torch.zeros(1, **f32), **self.cfg)
         self.n_table, self.n_mlp = cabi.sdf_table_params(probe), cabi.sdf_mlp_params(probe)
@@ -181,7 +186,7 @@ class GsSdfStep:
         self.v_samples = e(cap, 3)
         self.sdf_loss = torch.zeros(1, **f32)
 
-    KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 6  # + table cast + decoder weight image + 2 x (7-variant forward, fused train) (mlp_mode 1)
+    KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 8  # + 2 DSSIM kernels + table cast + decoder weight image + 2 x (7-variant forward, fused train) (mlp_mode 1)
 
     def _rebind_splat_grads(self, n_splat):
         R, N, K = self.R, self.R.N, self.R.K
@@ -259,5 +264,6 @@ class GsSdfStep:
             on_sdf_grads_ready(self.flat_grad[self.table_grad.storage_offset():])
         # [D] photometric loss + backward of the render, with the coupling gradient entering through the samples
         loss = R.backward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, gt_image, randns,
-                          v_samples=self.v_samples, zero_grads=False, raw=scene.get("raw"))
+                          v_samples=self.v_samples, zero_grads=False, raw=scene.get("raw"), w_rgb=self.rgb_w, w_depth=self.depth_w,
+                          w_dssim=self.dssim_w)
         return loss, self.sdf_loss

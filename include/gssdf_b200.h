@@ -49,7 +49,7 @@ const char *gssdf_last_error(void);
 /* "gssdf_b200 <ver> sm_100a" */
 const char *gssdf_version(void);
 /* Argument structs grow between revisions: a binding compiled against this header must see the same number from the library. */
-#define GSSDF_ABI_REVISION 9
+#define GSSDF_ABI_REVISION 10
 int32_t gssdf_abi_revision(void);
 
 /* Device-side counters shared by the stages of one render. Zeroed by gssdf_project2dgs_fwd. */
@@ -353,6 +353,24 @@ typedef struct gssdf_l1_loss_args {
     float *v_out_colors;     /* [C,H,W,4] */
 } gssdf_l1_loss_args;
 int gssdf_l1_loss(const gssdf_l1_loss_args *a, gssdf_stream_t stream);
+
+/* f-1  DSSIM term of the photometric loss and its cotangent (loss::dssim_loss, include/optimizer/loss.cpp:37-47;
+ *     loss_utils::ssim, include/optimizer/loss_utils/loss_utils.cpp:5-113: 11-tap window of gaussian() -- NOT a centred Gaussian, see
+ *     loss.cu --, zero padding, C1 = 0.01^2, C2 = 0.03^2, mean over channels and pixels) on the rgb channels of the post-processed render:
+ *         loss_out[0] += w_dssim * (1 - mean SSIM(rgb, gt_rgb));   v_out_colors[..., 0:3] += d/d rgb   (call after gssdf_l1_loss,
+ *     which overwrites v_out_colors; k_rgb_weight / k_dssim_weight are w_rgb / w_dssim, neural_mapping.cpp:237-240). */
+typedef struct gssdf_dssim_loss_args {
+    int32_t C, image_width, image_height;
+    const float *out_colors; /* [C,H,W,4] */
+    const float *gt;         /* [C,H,W,4] */
+    float w_dssim;
+    float *loss_out;         /* device float[1], += */
+    float *v_out_colors;     /* [C,H,W,4] += (channels 0..2) or NULL (forward only) */
+    void *workspace;         /* >= gssdf_dssim_workspace_bytes (three derivative maps) */
+    size_t workspace_bytes;
+} gssdf_dssim_loss_args;
+size_t gssdf_dssim_workspace_bytes(int32_t C, int32_t image_width, int32_t image_height);
+int gssdf_dssim_loss(const gssdf_dssim_loss_args *a, gssdf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a9-a12  SDF branch: multiresolution hash-grid encoding + decoder MLP, first order.

@@ -422,3 +422,38 @@ def test_kernels_vs_reference_cuda_goldens(oracle):
             err = rel_l2(_np(go[k]), d[k])
             assert err <= max(3 * noise, 2e-4), f"raster bwd {k}: rel L2 {err:.2e} vs reference (its run-to-run spread {noise:.2e})"
         assert rel_l2(_np(go["v_densify"]), d["v_densify"]) < 5e-2
+
+
+@pytest.mark.parametrize("W,H,C", [(160, 96, 1), (37, 53, 2)])
+def test_dssim_loss_matches_reference_formula(W, H, C):
+    """f-1: loss::dssim_loss (loss.cpp:37-47, loss_utils.cpp:5-113) restated with torch conv2d in fp64 -- including the reference's
+    asymmetric 11-tap window exp(-floor((x - 11) / 2)^2 / (2 * 1.5^2)) -- vs the fused forward/backward tile kernels."""
+    from gssdf_b200 import cabi
+    dev = _dev()
+    g = torch.Generator(dev).manual_seed(W * H)
+    x = torch.rand(C, H, W, 4, device=dev, generator=g)
+    y = (x + 0.2 * torch.randn(C, H, W, 4, device=dev, generator=g)).clamp(0, 1).contiguous()
+    w_dssim = 0.2
+    # reference formula
+    win1 = torch.tensor([np.exp(-(np.floor((i - 11) / 2.0) ** 2) / (2 * 1.5 ** 2)) for i in range(11)], dtype=torch.float32)
+    win1 = (win1 / win1.sum()).double().to(dev)
+    win = (win1[:, None] @ win1[None, :])[None, None].expand(3, 1, 11, 11).contiguous()
+    xr = x[..., :3].double().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    yr = y[..., :3].double().permute(0, 3, 1, 2).contiguous()
+    conv = lambda t: torch.nn.functional.conv2d(t, win, padding=5, groups=3)
+    mu1, mu2 = conv(xr), conv(yr)
+    s1, s2, s12 = conv(xr * xr) - mu1 * mu1, conv(yr * yr) - mu2 * mu2, conv(xr * yr) - mu1 * mu2
+    ssim = ((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 * mu1 + mu2 * mu2 + 1e-4) * (s1 + s2 + 9e-4))
+    ref = w_dssim * (1 - ssim.mean())
+    ref.backward()
+    # kernels
+    loss = torch.zeros(1, device=dev)
+    v = torch.zeros(C, H, W, 4, device=dev)
+    v[..., 3] = 7.0
+    cabi.dssim_loss(C, W, H, x, y, w_dssim, loss, v, cabi.Workspace(dev))
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    got = v[..., :3].double().permute(0, 3, 1, 2)
+    assert float((v[..., 3] - 7.0).abs().max()) == 0.0  # the depth channel is untouched
+    err = float((got - xr.grad).abs().max())
+    assert err <= 1e-4 * float(xr.grad.abs().max()) + 1e-9, err
