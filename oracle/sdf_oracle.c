@@ -14,9 +14,13 @@
  *                                                  isigma = 1 + softplus_{beta=100}(y1) * k_bce_isigma
  * Deviation restated on purpose: the table gradient is accumulated in fp64 here (the reference accumulates it with
  * fp16 atomics, whose result is neither deterministic nor 1e-4 accurate); the per-term fp16 products are kept.
- * tiny-cuda-nn ships no tests and GS-SDF none: parity of this file is UNPINNED against reference outputs
- * (tcnn was not built here: 8+ minutes of template instantiation and its own cmake); it is pinned only against the
- * published algorithm + finite differences (tests/test_sdf_oracle.py).
+ * Pinning: tiny-cuda-nn ships no tests and GS-SDF none, and tcnn's runtime was not built here (its own cmake, minutes per
+ * TU). The grid KERNELS, however, are header templates: oracle/ref_tcnn_grid_driver.cu instantiates the reference's kernel_grid,
+ * kernel_grid_backward, kernel_grid_backward_input, kernel_grid_backward_input_backward_grid/_dLdoutput directly from grid.h; they were
+ * run on a B200 (oracle/gen_golden_tcnn.py -> tests/golden/tcnn_grid_ref.npz) and this file reproduces their outputs: encoded features
+ * bit-for-bit, dy_dx / dL/dx to fp32 rounding, table gradients to the accuracy of the reference's half atomics
+ * (tests/test_sdf_oracle.py::test_oracle_grid_matches_tiny_cuda_nn_kernels). The decoder (libtorch Linear/ReLU) and the
+ * second-order chains are pinned against torch.autograd (same file).
  */
 #include <math.h>
 #include <stdint.h>

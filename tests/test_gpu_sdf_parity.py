@@ -440,3 +440,30 @@ def test_sdf_train_small_and_ragged_batches(oracle, n, live):
     assert abs(float(lc) - float(ld)) <= 1e-5 * abs(float(lc)) and np.isfinite(float(lc))
     assert bool(torch.isfinite(tgc).all()) and bool(torch.isfinite(mgc).all())
     assert float((mgc - mgd).norm()) <= 1e-4 * float(mgc.norm()) and float((tgc - tgd).norm()) <= 2e-2 * float(tgc.norm())
+
+
+def test_cuda_features_match_tiny_cuda_nn_kernels(oracle):
+    """The CUDA encoder against the outputs of tiny-cuda-nn's own kernel_grid run on a B200 (tests/golden/tcnn_grid_ref.npz; level 0
+    dense incl. cube-face points, levels 1-15 hashed at log2_hashmap_size 16): bit-identical features, both arithmetic modes."""
+    import os
+    from gssdf_b200 import cabi
+    dev = _dev()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tcnn_grid_ref.npz"))
+    rng = np.random.default_rng(int(g["seed"]))
+    table = rng.uniform(-0.5, 0.5, int(g["n_params"])).astype(np.float32)
+    n = g["x"].shape[0]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    half, mlp_t, xt = torch.empty(len(table), dtype=torch.float16, device=dev), t(_mlp(np.random.default_rng(1), 64, 3)), t(g["x"])
+    cabi.sdf_table_to_half(t(table), half)
+    for mode in (0, 1):
+        net = cabi.sdf_net(half, mlp_t, log2_hashmap_size=int(g["cfg"][1]), hidden_dim=64, n_hidden=3)
+        if mode == 1:
+            packed = torch.empty(cabi.sdf_mlp_packed_bytes(net), dtype=torch.uint8, device=dev)
+            cabi.sdf_mlp_pack(net, packed)
+            _KEEP.append(packed)
+            net = cabi.sdf_net(half, mlp_t, log2_hashmap_size=int(g["cfg"][1]), hidden_dim=64, n_hidden=3, mlp_mode=1, mlp_packed=packed)
+        assert cabi.sdf_table_params(net) == len(table)
+        sdf, feat = torch.empty(n, device=dev), torch.empty(n, 32, device=dev)
+        cabi.sdf_fwd(net, xt, sdf, None, feat)
+        torch.cuda.synchronize()
+        assert np.array_equal(feat.cpu().numpy(), g["enc"]), f"mlp_mode {mode}"
