@@ -347,26 +347,17 @@ def main():
     loss_host = torch.empty(1).pin_memory()
 
     n_splat_grad = R.flat_grad.numel()
-    pending, pending_splat = [], []
-
-    # Data-parallel gradient exchange, two NCCL all-reduces per step, both overlapped with compute that does not depend on them:
-    #   hash-table + decoder segment (61 MB): final after stage [C]  -> reduced under the render backward [D] of the same step
-    #   splat segment (236 MB)              : final after [D]        -> reduced under stage [A] of the NEXT step, which reads only SDF
-    #                                          parameters; it is waited for before the next render touches the splats (before_render)
-    def reduce_sdf_grads(g):
-        pending.append(dist.all_reduce(g, async_op=True))
-
-    def before_render():
-        while pending_splat:
-            pending_splat.pop().wait()
+    # Data-parallel gradient exchange (gssdf_b200/parallel.py:GradientExchange): two NCCL all-reduces per step, both overlapped with
+    # compute that does not depend on them -- the hash-table + decoder segment (61 MB) under the render backward [D] of the same step,
+    # the splat segment (236 MB) under stage [A] of the NEXT step; the optimiser scales by 1/world
+    from gssdf_b200 import parallel
+    xchg = parallel.GradientExchange()
+    hook = xchg.on_sdf_grads_ready if world > 1 else None
+    pre = xchg.before_render if world > 1 else None
+    before_render = xchg.drain
 
     def finish_step():
-        pending_splat.append(dist.all_reduce(G.flat_grad[:n_splat_grad], async_op=True))  # the optimiser scales by 1/world
-        while pending:
-            pending.pop().wait()
-
-    hook = reduce_sdf_grads if world > 1 else None
-    pre = before_render if world > 1 else None
+        xchg.finish_step(G.flat_grad[:n_splat_grad])
 
     def step_resident(i):
         V, Kc = dev_cams[i % n_cams]

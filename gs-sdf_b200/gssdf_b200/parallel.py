@@ -46,3 +46,39 @@ def allreduce_densify_state(state):
         if k in state:
             dist.all_reduce(state[k], op=dist.ReduceOp.MAX)
     return state
+
+
+class GradientExchange:
+    """The step's two all-reduces, each overlapped with compute that does not depend on it:
+
+        sdf segment   (hash table + decoder): final after stage [C]  -> reduced under the render backward [D] of the same step
+        splat segment                        : final after [D]        -> reduced under stage [A] of the NEXT step (which reads SDF
+                                               parameters only); `before_render` waits for it before the splats are touched again
+
+    Plug the three methods into GsSdfStep.step(on_sdf_grads_ready=..., before_render=...) and call finish_step() after it; drain()
+    before reading the gradients / stopping a timer. Works with any torch.distributed backend (NCCL on GPUs, gloo in the CPU tests);
+    a no-op when torch.distributed is not initialised or the world size is 1."""
+
+    def __init__(self):
+        self.active = dist.is_initialized() and dist.get_world_size() > 1
+        self._sdf, self._splat = [], []
+
+    def on_sdf_grads_ready(self, sdf_segment):
+        if self.active:
+            self._sdf.append(dist.all_reduce(sdf_segment, op=dist.ReduceOp.SUM, async_op=True))
+
+    def before_render(self):
+        while self._splat:
+            self._splat.pop().wait()
+
+    def finish_step(self, splat_segment):
+        if not self.active:
+            return
+        self._splat.append(dist.all_reduce(splat_segment, op=dist.ReduceOp.SUM, async_op=True))
+        while self._sdf:
+            self._sdf.pop().wait()
+
+    def drain(self):
+        self.before_render()
+        while self._sdf:
+            self._sdf.pop().wait()

@@ -52,3 +52,51 @@ def test_single_process_is_identity():
     t = torch.ones(4)
     assert parallel.allreduce_flat_grad(t) is t and (t == 1).all()
     assert sorted(parallel.image_for_rank(s, 0, 1, 7) for s in range(7)) == list(range(7))
+
+
+def _xchg_worker(rank, world, port, out):
+    """Drives parallel.GradientExchange through three fake steps with the hook order of GsSdfStep.step: stage [A] (touches only the
+    SDF segment) -> before_render -> stages [B]-[C] -> on_sdf_grads_ready -> stage [D] (writes the splat segment) -> finish_step."""
+    import torch.distributed as dist
+
+    from gssdf_b200 import parallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_splat, n_sdf = 1000, 300
+    flat = torch.zeros(n_splat + n_sdf)
+    x = parallel.GradientExchange()
+    seen = []
+    for step in range(3):
+        flat[n_splat:].zero_()                       # step start: only the SDF segment is cleared
+        flat[n_splat:] += (rank + 1) * (step + 1)    # [A] + [C] write the SDF segment
+        x.before_render()                            # previous step's splat all-reduce must be complete here ...
+        if step > 0:
+            seen.append(float(flat[0]))              # ... so the reduced value of the previous step is visible
+        flat[:n_splat].zero_()
+        x.on_sdf_grads_ready(flat[n_splat:])
+        flat[:n_splat] += 10 * (rank + 1) + step     # [D] writes the splat segment
+        x.finish_step(flat[:n_splat])
+        seen.append(float(flat[n_splat]))            # the SDF segment is reduced when finish_step returns
+    x.drain()
+    seen.append(float(flat[0]))
+    out.put((rank, seen))
+    dist.destroy_process_group()
+
+
+def test_gradient_exchange_overlap_protocol_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_xchg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    # sums over ranks {1, 2}: sdf segment (1+2)*(step+1); splat segment 10*(1+2) + 2*step
+    expect = [3.0, 30.0, 6.0, 32.0, 9.0, 34.0]
+    for rank, seen in res:
+        assert seen == expect, (rank, seen)
