@@ -217,6 +217,11 @@ def run_cpu_sample(workload, steps, warmup, budget_s=25.0):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1 into its ranks: the CPU arm uses every host core
     O.set_threads(cores)
+    try:  # numpy's BLAS pool read OMP_NUM_THREADS=1 at import time under torchrun
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=cores)
+    except Exception:
+        pass
     rng = np.random.default_rng(5)
     n_table, _ = O.grid_setup()
     table = rng.uniform(-1e-4, 1e-4, n_table).astype(np.float32)

@@ -183,6 +183,7 @@ void oracle_hashgrid_bwd(int64_t n, const float *x, const float *dL_dfeat, int L
     oracle_grid_setup(L, F, log2_hashmap, base_res, per_level_scale, off);
     float l2 = log2f(per_level_scale);
     const double loss_scale = 128.0;
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
         float dx[3] = {0, 0, 0};
         for (int lvl = 0; lvl < L; ++lvl) {
@@ -209,7 +210,11 @@ void oracle_hashgrid_bwd(int64_t n, const float *x, const float *dL_dfeat, int L
                     }
                     uint32_t index = grid_index(hs, res, pl) * F;
                     double wh = rh((double)w);
-                    for (int f = 0; f < F; ++f) table_grad[(size_t)off[lvl] * F + index + f] += rh(wh * gh[f]) / loss_scale;
+                    for (int f = 0; f < F; ++f) {
+                        const double v = rh(wh * gh[f]) / loss_scale;
+#pragma omp atomic
+                        table_grad[(size_t)off[lvl] * F + index + f] += v;
+                    }
                 }
             if (dL_dx && dy_dx)
                 for (int f = 0; f < F; ++f)
@@ -234,6 +239,7 @@ void oracle_hashgrid_bwd_bwd(int64_t n, const float *x, const float *dL_ddLdx, c
     oracle_grid_setup(L, F, log2_hashmap, base_res, per_level_scale, off);
     float l2 = log2f(per_level_scale);
     const double loss_scale = 128.0;
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
         for (int lvl = 0; lvl < L; ++lvl) {
             uint32_t hs = off[lvl + 1] - off[lvl];
@@ -266,8 +272,11 @@ void oracle_hashgrid_bwd_bwd(int64_t n, const float *x, const float *dL_ddLdx, c
                         uint32_t ir = grid_index(hs, res, pl) * F;
                         double wl = rh((double)-w), wr = rh((double)w);
                         for (int f = 0; f < F; ++f) {
-                            table_grad[(size_t)off[lvl] * F + il + f] += rh(wl * gh[f]) / loss_scale;
-                            table_grad[(size_t)off[lvl] * F + ir + f] += rh(wr * gh[f]) / loss_scale;
+                            const double vl = rh(wl * gh[f]) / loss_scale, vr = rh(wr * gh[f]) / loss_scale;
+#pragma omp atomic
+                            table_grad[(size_t)off[lvl] * F + il + f] += vl;
+#pragma omp atomic
+                            table_grad[(size_t)off[lvl] * F + ir + f] += vr;
                         }
                     }
                 }
