@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgssdf_b200.so")
-SOURCES = ["api.cu", "project.cu", "sh.cu", "tiles.cu", "raster.cu", "sdf.cu", "sdf_tc.cu", "loss.cu"]
+SOURCES = ["api.cu", "project.cu", "sh.cu", "tiles.cu", "raster.cu", "sdf.cu", "sdf_tc.cu", "loss.cu", "grid_ops.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "--extended-lambda", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -45,14 +45,20 @@ def build_shim(force=False):
     import sysconfig
 
     import torch
-    srcs = [os.path.join(HERE, "shim", f) for f in ("gsplat_cpp_shim.cpp", "py_binding.cpp")]
+    srcs = [os.path.join(HERE, "shim", f) for f in ("gsplat_cpp_shim.cpp", "tcnn_binding_shim.cpp", "py_binding.cpp")]
     deps = srcs + [os.path.join(HERE, "shim", "include", "gsplat_cpp", h) for h in ("fully_fused_projection.h", "rasterize_to_pixels.h", "rendering.h")]
+    deps.append(os.path.join(HERE, "shim", "include", "tcnn_binding", "tcnn_binding.h"))
     deps.append(os.path.join(HERE, "..", "include", "gssdf_b200.h"))
     if not force and os.path.exists(SHIM_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(SHIM_OUT) for d in deps):
         return SHIM_OUT
     tdir = os.path.dirname(torch.__file__)
     inc = [f"-I{os.path.join(HERE, 'shim', 'include')}", f"-I{tdir}/include", f"-I{tdir}/include/torch/csrc/api/include",
            "-I/usr/local/cuda/include", f"-I{sysconfig.get_paths()['include']}"]
+    # nlohmann::json for the tcnn_binding twin: the reference gets it from tiny-cuda-nn/dependencies (json/json.hpp); this image carries
+    # the same single header under cudnn_frontend's third-party directory
+    import glob
+    js = glob.glob(os.path.join(sysconfig.get_paths()["purelib"], "include", "cudnn_frontend", "thirdparty"))
+    inc += [f"-I{p_}" for p_ in js]
     flags = ["-std=c++17", "-O2", "-fPIC", "-w", "-D_GLIBCXX_USE_CXX11_ABI=1", "-DTORCH_EXTENSION_NAME=gssdf_shim", "-DTORCH_API_INCLUDE_EXTENSION_H"]
     objs, procs = [], []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)

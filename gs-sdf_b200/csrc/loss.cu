@@ -183,3 +183,138 @@ extern "C" int gssdf_dssim_loss(const gssdf_dssim_loss_args *a, gssdf_stream_t s
     }
     return GSSDF_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// f-1 (rest): normal-consistency loss (include/neural_mapping/neural_mapping.cpp:243-266) between the rendered normals and the normals
+// of the rendered depth map (sensor::depth_to_normal, include/utils/sensor_utils/cameras.hpp:176-226), loss + both cotangents in one
+// tile kernel. A 32x8 pixel tile stages the world points P = dir_w * depth of its halo-2 neighbourhood in shared memory, evaluates the
+// stencil normal and dL/d(cross product) on the halo-1 ring, then every pixel GATHERS its depth gradient from its four neighbours'
+// stencils (deterministic; the autograd graph of the reference scatters through index/cat/cross/normalize backward kernels).
+// ---------------------------------------------------------------------------------------------------------------------------------
+namespace gssdf {
+
+constexpr int kNcX = 32, kNcY = 8;
+
+__global__ void __launch_bounds__(kNcX * kNcY) normal_consistency_kernel(const gssdf_normal_consistency_args a, float scale) {
+    __shared__ float sP[kNcY + 4][kNcX + 4][3];
+    __shared__ float sG[kNcY + 2][kNcX + 2][3];  // dL / d cross(a, b) of the stencil centred on the pixel
+    __shared__ float s_red[kNcX * kNcY / 32];
+    const int W = a.image_width, H = a.image_height, cam = blockIdx.z;
+    const int tid = threadIdx.y * kNcX + threadIdx.x;
+    const int bx = blockIdx.x * kNcX, by = blockIdx.y * kNcY;
+    const float *V = a.viewmats + 16 * cam, *K = a.Ks + 9 * cam;
+    const float ifx = 1.f / K[0], ify = 1.f / K[4], cx = K[2], cy = K[5];
+    const int64_t img = (int64_t)cam * H * W;
+    auto dir_w = [&](int gx, int gy, float d[3]) {  // rot * zdir with rot = R^T of the world->camera view matrix
+        const float zx = ((float)gx + 0.5f - cx) * ifx, zy = ((float)gy + 0.5f - cy) * ify;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) d[k] = V[0 * 4 + k] * zx + V[1 * 4 + k] * zy + V[2 * 4 + k];
+    };
+    for (int e = tid; e < (kNcY + 4) * (kNcX + 4); e += kNcX * kNcY) {
+        const int r = e / (kNcX + 4), c = e % (kNcX + 4), gx = bx + c - 2, gy = by + r - 2;
+        float p[3] = {0.f, 0.f, 0.f};
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+            float d[3];
+            dir_w(gx, gy, d);
+            const float z = __ldg(a.depth + (img + (int64_t)gy * W + gx) * a.depth_stride);
+            p[0] = d[0] * z; p[1] = d[1] * z; p[2] = d[2] * z;  // (+ pos: cancels in the differences)
+        }
+        sP[r][c][0] = p[0]; sP[r][c][1] = p[1]; sP[r][c][2] = p[2];
+    }
+    __syncthreads();
+    float part = 0.f;
+    for (int e = tid; e < (kNcY + 2) * (kNcX + 2); e += kNcX * kNcY) {
+        const int r = e / (kNcX + 2), c = e % (kNcX + 2), gx = bx + c - 1, gy = by + r - 1;
+        const bool own = r >= 1 && r <= kNcY && c >= 1 && c <= kNcX && gx < W && gy < H;  // this CTA's pixels (gx, gy >= 0 there)
+        float gc[3] = {0.f, 0.f, 0.f};
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+            const int64_t pix = img + (int64_t)gy * W + gx;
+            const float alpha = __ldg(a.render_alphas + pix);
+            float grn[3] = {0.f, 0.f, 0.f};
+            float dot = 0.f;
+            if (gx >= 1 && gx <= W - 2 && gy >= 1 && gy <= H - 2) {  // interior: depth_point_to_normal fills [1:-1, 1:-1]
+                const int pr = r + 1, pc = c + 1;
+                float va[3], vb[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { va[k] = sP[pr + 1][pc][k] - sP[pr - 1][pc][k]; vb[k] = sP[pr][pc + 1][k] - sP[pr][pc - 1][k]; }
+                const float cr[3] = {va[1] * vb[2] - va[2] * vb[1], va[2] * vb[0] - va[0] * vb[2], va[0] * vb[1] - va[1] * vb[0]};
+                const float nrm = sqrtf(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+                const float den = fmaxf(nrm, 1e-12f);  // F::normalize eps
+                const float n[3] = {cr[0] / den, cr[1] / den, cr[2] / den};
+                const float rn[3] = {__ldg(a.out_normals + 3 * pix), __ldg(a.out_normals + 3 * pix + 1), __ldg(a.out_normals + 3 * pix + 2)};
+                dot = alpha * (n[0] * rn[0] + n[1] * rn[1] + n[2] * rn[2]);
+                if (isfinite(dot)) {  // nan_to_num: value 0 and zero gradient where the product is not finite
+                    const float gd = -scale;  // d loss / d dot
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) grn[k] = gd * alpha * n[k];
+                    const float gn[3] = {gd * alpha * rn[0], gd * alpha * rn[1], gd * alpha * rn[2]};
+                    if (nrm > 1e-12f) {
+                        const float ng = n[0] * gn[0] + n[1] * gn[1] + n[2] * gn[2];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) gc[k] = (gn[k] - n[k] * ng) / nrm;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) gc[k] = gn[k] * 1e12f;
+                    }
+                } else {
+                    dot = 0.f;
+                }
+            }
+            if (own) {
+                part += scale * (alpha * alpha - dot);
+                if (a.v_out_normals) { a.v_out_normals[3 * pix] = grn[0]; a.v_out_normals[3 * pix + 1] = grn[1]; a.v_out_normals[3 * pix + 2] = grn[2]; }
+            }
+        }
+        sG[r][c][0] = gc[0]; sG[r][c][1] = gc[1]; sG[r][c][2] = gc[2];
+    }
+    __syncthreads();
+    const int gx = bx + threadIdx.x, gy = by + threadIdx.y;
+    if (a.v_depth && gx < W && gy < H) {
+        // P(p) enters: a of the stencil at (y-1, x) with +, at (y+1, x) with -; b of the stencil at (y, x-1) with +, at (y, x+1) with -.
+        // dL/da = b x gc, dL/db = gc x a.
+        float gP[3] = {0.f, 0.f, 0.f};
+        auto add = [&](int qr, int qc, bool is_a, float sign) {  // stencil centred on halo-2 cell (qr, qc) / halo-1 cell (qr-1, qc-1)
+            const float *g = sG[qr - 1][qc - 1];
+            float va[3], vb[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { va[k] = sP[qr + 1][qc][k] - sP[qr - 1][qc][k]; vb[k] = sP[qr][qc + 1][k] - sP[qr][qc - 1][k]; }
+            float o[3];
+            if (is_a) { o[0] = vb[1] * g[2] - vb[2] * g[1]; o[1] = vb[2] * g[0] - vb[0] * g[2]; o[2] = vb[0] * g[1] - vb[1] * g[0]; }
+            else      { o[0] = g[1] * va[2] - g[2] * va[1]; o[1] = g[2] * va[0] - g[0] * va[2]; o[2] = g[0] * va[1] - g[1] * va[0]; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gP[k] += sign * o[k];
+        };
+        const int pr = threadIdx.y + 2, pc = threadIdx.x + 2;
+        add(pr - 1, pc, true, 1.f);
+        add(pr + 1, pc, true, -1.f);
+        add(pr, pc - 1, false, 1.f);
+        add(pr, pc + 1, false, -1.f);
+        float d[3];
+        dir_w(gx, gy, d);
+        const float gz = gP[0] * d[0] + gP[1] * d[1] + gP[2] * d[2];
+        a.v_depth[(img + (int64_t)gy * W + gx) * a.v_depth_stride] += gz;
+    }
+    part = warp_sum(part);
+    if ((tid & 31) == 0) s_red[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int w = 0; w < kNcX * kNcY / 32; ++w) t += s_red[w];
+        atomicAdd(a.loss_out, t);
+    }
+}
+
+}  // namespace gssdf
+
+extern "C" int gssdf_normal_consistency_loss(const gssdf_normal_consistency_args *a, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "normal_consistency: null args");
+    GSSDF_REQUIRE(a->C > 0 && a->image_width > 0 && a->image_height > 0, GSSDF_EINVAL, "normal_consistency: bad image size");
+    GSSDF_REQUIRE(a->viewmats && a->Ks && a->depth && a->render_alphas && a->out_normals && a->loss_out, GSSDF_EINVAL,
+                  "normal_consistency: null pointer");
+    GSSDF_REQUIRE(a->depth_stride >= 1 && (!a->v_depth || a->v_depth_stride >= 1), GSSDF_EINVAL, "normal_consistency: bad stride");
+    const dim3 grid(cdiv(a->image_width, kNcX), cdiv(a->image_height, kNcY), a->C), block(kNcX, kNcY);
+    const double n = (double)a->C * a->image_width * a->image_height;
+    normal_consistency_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*a, (float)(a->weight / n));
+    GSSDF_LAUNCH_OK("normal_consistency_kernel");
+    return GSSDF_OK;
+}

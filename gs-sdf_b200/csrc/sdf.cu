@@ -415,7 +415,8 @@ __global__ void __launch_bounds__(256) sdf_loss_kernel(const gssdf_sdf_loss_args
         for (int v = 0; v < V; ++v) s[v] = a.sdf[v * n + i];
         part = sdf_point_loss(cfg, (float)nl, V, s, a.y1 ? a.y1[i] : 0.f, a.gt_sdf != nullptr, a.gt_sdf ? a.gt_sdf[i] : 0.f,
                               a.weights != nullptr, a.weights ? a.weights[i] : 0.f, a.visibilities != nullptr,
-                              a.visibilities ? a.visibilities[i] : 0.f, v_s, v_y);
+                              a.visibilities ? a.visibilities[i] : 0.f, v_s, v_y,
+                              sdf_gate(a.n_gate, a.valid_mask, a.visibilities, a.visible_thr, i));
         for (int v = 0; v < V; ++v) a.v_sdf[v * n + i] = v_s[v];
         if (a.v_y1) {
             a.v_y1[i] = v_y;

@@ -11,8 +11,25 @@ struct SdfLossCfg {
 
 // s[0] = sdf at the point, s[1..6] = sdf at +x,-x,+y,-y,+z,-z (V == 7). Returns the point's weighted loss contribution;
 // v_s[0..V) = dL/dsdf of each evaluation, v_y = dL/dy1 of the base evaluation. nl = number of live points (the means' divisor).
+// Gate (neural_mapping.cpp:428-437, only when the caller supplies n_gate): gated = the gate is in force, gate = this point passes it
+// (vis > visible_thr and inside the octree), ng = number of points that pass; the eikonal mean then divides by ng instead of nl and a
+// point that fails contributes nothing.
+struct SdfGate {
+    bool gated, gate;
+    float ng;
+};
+__device__ __forceinline__ SdfGate sdf_gate(const int32_t *n_gate, const uint8_t *valid_mask, const float *vis, float thr, int64_t i) {
+    SdfGate g{n_gate != nullptr, true, 1.f};
+    if (g.gated) {
+        g.ng = fmaxf((float)*n_gate, 1.f);
+        g.gate = (!vis || __ldg(vis + i) > thr) && (!valid_mask || valid_mask[i] != 0);
+    }
+    return g;
+}
+
 __device__ __forceinline__ float sdf_point_loss(const SdfLossCfg &c, float nl, int V, const float s[7], float y, bool has_gt, float gt,
-                                                bool has_w, float weight, bool has_vis, float vis, float v_s[7], float &v_y) {
+                                                bool has_w, float weight, bool has_vis, float vis, float v_s[7], float &v_y,
+                                                const SdfGate gt8 = SdfGate{false, true, 1.f}) {
     float part = 0.f, vs0 = 0.f;
     v_y = 0.f;
     if (has_gt) {
@@ -38,6 +55,7 @@ __device__ __forceinline__ float sdf_point_loss(const SdfLossCfg &c, float nl, i
     if (has_w) {
         float w = weight * c.gs_sdf_weight;
         if (has_vis) w = vis > c.visible_thr ? w * vis : 0.f;
+        if (gt8.gated && !gt8.gate) w = 0.f;
         part += 0.5f * w * s[0] * s[0];
         vs0 += w * s[0];
     }
@@ -45,7 +63,7 @@ __device__ __forceinline__ float sdf_point_loss(const SdfLossCfg &c, float nl, i
         const float inv2d = 0.5f / c.delta;
         const float gx = (s[1] - s[2]) * inv2d, gy = (s[3] - s[4]) * inv2d, gz = (s[5] - s[6]) * inv2d;
         const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
-        const float w = c.eikonal_weight / nl;
+        const float w = (gt8.gated && !gt8.gate) ? 0.f : c.eikonal_weight / (gt8.gated ? gt8.ng : nl);
         part += w * (nrm - 1.f) * (nrm - 1.f);
         const float k = nrm > 0.f ? 2.f * (nrm - 1.f) / nrm * w * inv2d : 0.f;
         v_s[1] = k * gx; v_s[2] = -k * gx;

@@ -366,6 +366,8 @@ struct TcLossArgs {
     int analytic;        // eikonal on the ANALYTIC gradient d sdf/dx (LocalMap::get_gradient(numerical = false), local_map.cpp:150-171)
     float align_weight;  // |g_analytic - g_numerical.detach()|.mean() (neural_mapping.cpp:124-133)
     const float *sdf_variants;  // [7n] precomputed sdf of the 7 variants (V == 1) or NULL (V == 7: evaluated in the tile)
+    const uint8_t *valid_mask;  // sample gate of the coupling site (see SdfGate), in force iff n_gate != NULL
+    const int32_t *n_gate;
 };
 
 template <bool FUSED, bool ANALYTIC>
@@ -528,9 +530,11 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
         // -- losses on the analytic gradient (world units), cotangent back in x01 units
         if (tid < TM) {
             float cc[3] = {0.f, 0.f, 0.f};
-            if (tid < nc) {
+            const SdfGate gate = tid < nc ? sdf_gate(lo.n_gate, lo.valid_mask, lo.visibilities, lo.cfg.visible_thr, s_tbase[tid / PT] + tid % PT)
+                                          : SdfGate{false, true, 1.f};
+            if (tid < nc && (!gate.gated || gate.gate)) {
                 const float gx = s_dx[tid * 3] * isz, gy = s_dx[tid * 3 + 1] * isz, gz = s_dx[tid * 3 + 2] * isz;
-                const float nl = (float)n_live;
+                const float nl = gate.gated ? gate.ng : (float)n_live;
                 const float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
                 const float we = lo.cfg.eikonal_weight / nl;
                 loss_acc += we * (nrm - 1.f) * (nrm - 1.f);
@@ -773,7 +777,8 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
                 }
                 loss_acc += sdf_point_loss(cfg1, (float)n_live, V, sv, s_out[2 * tid * V + 1], lo.gt_sdf != nullptr,
                                            lo.gt_sdf ? __ldg(lo.gt_sdf + i) : 0.f, lo.weights != nullptr, lo.weights ? __ldg(lo.weights + i) : 0.f,
-                                           lo.visibilities != nullptr, lo.visibilities ? __ldg(lo.visibilities + i) : 0.f, v_s, v_y);
+                                           lo.visibilities != nullptr, lo.visibilities ? __ldg(lo.visibilities + i) : 0.f, v_s, v_y,
+                                           sdf_gate(lo.n_gate, lo.valid_mask, lo.visibilities, lo.cfg.visible_thr, i));
                 for (int v = 0; v < V; ++v) s_seed[2 * (tid * V + v)] = v_s[v];
                 s_seed[2 * tid * V + 1] = v_y;
             }
@@ -1043,7 +1048,7 @@ extern "C" int gssdf_sdf_train(const gssdf_sdf_train_args *t, gssdf_stream_t str
     a.table_grad = t->table_grad; a.mlp_grad = t->mlp_grad; a.v_x = t->v_x;
     TcLossArgs lo{t->gt_sdf, t->weights, t->visibilities,
                   SdfLossCfg{t->bce_isigma, t->bce_weight, t->eikonal_weight, t->gs_sdf_weight, t->delta, t->visible_thr}, t->loss_out,
-                  t->eikonal_mode, t->align_weight, t->n_variants == 1 ? t->sdf_variants : nullptr};
+                  t->eikonal_mode, t->align_weight, t->n_variants == 1 ? t->sdf_variants : nullptr, t->valid_mask, t->n_gate};
     GSSDF_REQUIRE(t->eikonal_mode == 0 || t->eikonal_mode == 1, GSSDF_EINVAL, "sdf_train: eikonal_mode must be 0 or 1");
     GSSDF_REQUIRE(!(t->eikonal_mode == 1 && t->align_weight > 0.f) || t->n_variants == 7 || t->sdf_variants, GSSDF_EINVAL,
                   "sdf_train: the align loss needs the numerical gradient: n_variants 7 or sdf_variants");

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(_PKG))
 HEADER = os.path.join(ROOT, "include", "gssdf_b200.h")
 SO_PATH = os.path.join(os.path.dirname(_PKG), "libgssdf_b200.so")
 
-_SCALARS = {"int32_t": C.c_int32, "int64_t": C.c_int64, "uint32_t": C.c_uint32, "float": C.c_float,
+_SCALARS = {"uint8_t": C.c_uint8, "int32_t": C.c_int32, "int64_t": C.c_int64, "uint32_t": C.c_uint32, "float": C.c_float,
             "size_t": C.c_size_t, "int": C.c_int, "double": C.c_double}
 
 
@@ -24,6 +24,8 @@ def _strip_comments(src):
 def parse_header(path=HEADER):
     """Returns ({struct_name: [(field, ctype)]}, {func_name: (restype, n_args)})."""
     src = _strip_comments(open(path).read())
+    for m in re.finditer(r"#define\s+(GSSDF_\w+)\s+(\d+)\s*$", src, flags=re.M):  # integer macros used as array extents
+        src = re.sub(r"\[" + m.group(1) + r"\]", "[" + m.group(2) + "]", src)
     structs = {}
     ctypes_structs = {}
     for m in re.finditer(r"typedef\s+struct\s+(\w+)\s*\{(.*?)\}\s*(\w+)\s*;", src, flags=re.S):
@@ -41,7 +43,7 @@ def parse_header(path=HEADER):
                 if item.startswith("*"):
                     fields.append((item.lstrip("* "), C.c_void_p))
                 elif arr:
-                    fields.append((arr.group(1), _SCALARS[base] * int(arr.group(2))))
+                    fields.append((arr.group(1), (ctypes_structs.get(base) or _SCALARS[base]) * int(arr.group(2))))
                 elif base in ctypes_structs:  # nested struct by value
                     fields.append((item, ctypes_structs[base]))
                 else:
@@ -57,6 +59,21 @@ def parse_header(path=HEADER):
 
 _STRUCT_FIELDS, FUNCS, STRUCTS = parse_header()
 
+
+def _argtypes(args):
+    """ctypes argtypes of one prototype's parameter list: pointers, struct pointers and gssdf_stream_t -> c_void_p."""
+    args = args.strip()
+    if args in ("", "void"):
+        return []
+    out = []
+    for item in args.split(","):
+        item = " ".join(item.replace("const ", "").split())
+        if "*" in item or item.startswith("gssdf_stream_t"):
+            out.append(C.c_void_p)
+        else:
+            out.append(_SCALARS[item.split(" ")[0]])
+    return out
+
 _lib = None
 
 
@@ -71,6 +88,9 @@ def lib():
         for name, (ret, _args) in FUNCS.items():
             fn = getattr(L, name)  # raises AttributeError if a declared symbol is not exported
             fn.restype = {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "size_t": C.c_size_t, "const char *": C.c_char_p}[ret]
+            # typed arguments: an untyped Python int is passed as a 32-bit C int, which would truncate 64-bit handles
+            # (cudaStream_t of a non-default stream, device pointers, int64 sizes)
+            fn.argtypes = _argtypes(_args)
         m = re.search(r"#define\s+GSSDF_ABI_REVISION\s+(\d+)", open(HEADER).read())
         if m and L.gssdf_abi_revision() != int(m.group(1)):
             raise RuntimeError(f"{SO_PATH} was built against ABI revision {L.gssdf_abi_revision()}, the header says {m.group(1)}: "

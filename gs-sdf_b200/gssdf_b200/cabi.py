@@ -233,9 +233,9 @@ def sdf_bwd(net, x, v_sdf, v_y1=None, table_grad=None, mlp_grad=None, v_x=None, 
 
 
 def sdf_loss(n, n_variants, sdf, y1, gt_sdf, weights, bce_isigma, bce_weight, eikonal_weight, gs_sdf_weight, delta, loss_out, v_sdf, v_y1,
-             visibilities=None, visible_thr=0.0, n_live=None):
+             visibilities=None, visible_thr=0.0, n_live=None, valid_mask=None, n_gate=None):
     a = make_args("gssdf_sdf_loss_args", n=n, n_variants=n_variants, sdf=sdf, y1=y1, gt_sdf=gt_sdf, weights=weights,
-                  visibilities=visibilities, visible_thr=visible_thr, n_live=n_live,
+                  visibilities=visibilities, visible_thr=visible_thr, n_live=n_live, valid_mask=valid_mask, n_gate=n_gate,
                   bce_isigma=bce_isigma, bce_weight=bce_weight, eikonal_weight=eikonal_weight, gs_sdf_weight=gs_sdf_weight,
                   delta=delta, loss_out=loss_out, v_sdf=v_sdf, v_y1=v_y1)
     check(lib().gssdf_sdf_loss(_lib.C.byref(a), _stream()))
@@ -243,13 +243,13 @@ def sdf_loss(n, n_variants, sdf, y1, gt_sdf, weights, bce_isigma, bce_weight, ei
 
 def sdf_train(net, x, n_variants, delta, gt_sdf, weights, bce_isigma, bce_weight, eikonal_weight, gs_sdf_weight, loss_out,
               table_grad=None, mlp_grad=None, v_x=None, visibilities=None, visible_thr=0.0, n_live=None, eikonal_mode=0,
-              align_weight=0.0, sdf_variants=None):
+              align_weight=0.0, sdf_variants=None, valid_mask=None, n_gate=None):
     """sdf_fwd + sdf_loss + sdf_bwd fused into one persistent tensor-core kernel (net.mlp_mode must be 1)."""
     a = make_args("gssdf_sdf_train_args", n=x.shape[0], x=x, n_variants=n_variants, delta=delta, n_live=n_live, gt_sdf=gt_sdf,
                   weights=weights, visibilities=visibilities, visible_thr=visible_thr, bce_isigma=bce_isigma, bce_weight=bce_weight,
                   eikonal_weight=eikonal_weight, gs_sdf_weight=gs_sdf_weight, loss_out=loss_out, table_grad=table_grad,
                   mlp_grad=mlp_grad, v_x=v_x, eikonal_mode=eikonal_mode, align_weight=align_weight,
-                  sdf_variants=sdf_variants)
+                  sdf_variants=sdf_variants, valid_mask=valid_mask, n_gate=n_gate)
     a.net = net
     check(lib().gssdf_sdf_train(_lib.C.byref(a), _stream()))
 
@@ -261,3 +261,58 @@ def dssim_loss(Cn, W, H, out_colors, gt, w_dssim, loss_out, v_out_colors, ws):
     a = make_args("gssdf_dssim_loss_args", C=Cn, image_width=W, image_height=H, out_colors=out_colors, gt=gt, w_dssim=w_dssim,
                   loss_out=loss_out, v_out_colors=v_out_colors, workspace=w, workspace_bytes=w.numel())
     check(lib().gssdf_dssim_loss(_lib.C.byref(a), _stream()))
+
+
+# ---- operator-level hash grid (tcnn_binding twin), gate, optimiser, remaining loss terms ------------------------------------
+def hashgrid_fwd(net, x, feat):
+    a = make_args("gssdf_hashgrid_fwd_args", n=x.shape[0], x=x, feat=feat)
+    a.net = net
+    check(lib().gssdf_hashgrid_fwd(_lib.C.byref(a), _stream()))
+
+
+def hashgrid_bwd(net, x, dL_dy, table_grad=None, dL_dx=None):
+    a = make_args("gssdf_hashgrid_bwd_args", n=x.shape[0], x=x, dL_dy=dL_dy, table_grad=table_grad, dL_dx=dL_dx)
+    a.net = net
+    check(lib().gssdf_hashgrid_bwd(_lib.C.byref(a), _stream()))
+
+
+def hashgrid_bwdbwd(net, x, dL_ddLdx, dL_dy, table_grad=None, dL_ddLdy=None, dL_dx=None):
+    a = make_args("gssdf_hashgrid_bwdbwd_args", n=x.shape[0], x=x, dL_ddLdx=dL_ddLdx, dL_dy=dL_dy, table_grad=table_grad,
+                  dL_ddLdy=dL_ddLdy, dL_dx=dL_dx)
+    a.net = net
+    check(lib().gssdf_hashgrid_bwdbwd(_lib.C.byref(a), _stream()))
+
+
+def sdf_gate_count(n, n_gate, visibilities=None, visible_thr=0.0, valid_mask=None, n_live=None):
+    a = make_args("gssdf_sdf_gate_count_args", n=n, n_live=n_live, visibilities=visibilities, visible_thr=visible_thr,
+                  valid_mask=valid_mask, n_gate=n_gate)
+    check(lib().gssdf_sdf_gate_count(_lib.C.byref(a), _stream()))
+
+
+def normal_consistency_loss(Cn, W, H, viewmats, Ks, depth, depth_stride, render_alphas, out_normals, weight, loss_out, v_depth=None,
+                            v_depth_stride=1, v_out_normals=None):
+    """depth / v_depth are raw device pointers (int) or tensors: e.g. out_colors.data_ptr() + 12 with stride 4 for the ED channel."""
+    a = make_args("gssdf_normal_consistency_args", C=Cn, image_width=W, image_height=H, viewmats=viewmats, Ks=Ks, depth=depth,
+                  depth_stride=depth_stride, render_alphas=render_alphas, out_normals=out_normals, weight=weight, loss_out=loss_out,
+                  v_depth=v_depth, v_depth_stride=v_depth_stride, v_out_normals=v_out_normals)
+    check(lib().gssdf_normal_consistency_loss(_lib.C.byref(a), _stream()))
+
+
+def isotropic_loss(N, cap, counts, gaussian_ids, scales, raw_params, weight, loss_out, v_scales=None):
+    a = make_args("gssdf_isotropic_loss_args", N=N, cap=cap, counts=counts, gaussian_ids=gaussian_ids, scales=scales,
+                  raw_params=int(bool(raw_params)), weight=weight, loss_out=loss_out, v_scales=v_scales)
+    check(lib().gssdf_isotropic_loss(_lib.C.byref(a), _stream()))
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, groups, step, beta1=0.9, beta2=0.999, eps=1e-15, grad_scale=1.0, zero_grads=True,
+              table_half=None, net=None, mlp_packed=None):
+    """groups: list of (offset, count, lr, half_shadow). `net` (gssdf_sdf_net struct, kept alive by the caller) + mlp_packed: re-pack the
+    decoder's bf16 operand image after the update."""
+    a = make_args("gssdf_adam_args", params=params, grads=grads, exp_avg=exp_avg, exp_avg_sq=exp_avg_sq, n_groups=len(groups), step=step,
+                  beta1=beta1, beta2=beta2, eps=eps, grad_scale=grad_scale, zero_grads=int(bool(zero_grads)), table_half=table_half,
+                  mlp_packed=mlp_packed)
+    for i, (off, cnt, lr, hs) in enumerate(groups):
+        a.groups[i].offset, a.groups[i].count, a.groups[i].lr, a.groups[i].half_shadow = int(off), int(cnt), float(lr), int(bool(hs))
+    if net is not None:
+        a.net = _lib.C.cast(_lib.C.pointer(net), _lib.C.c_void_p)
+    check(lib().gssdf_adam_step(_lib.C.byref(a), _stream()))

@@ -49,7 +49,7 @@ const char *gssdf_last_error(void);
 /* "gssdf_b200 <ver> sm_100a" */
 const char *gssdf_version(void);
 /* Argument structs grow between revisions: a binding compiled against this header must see the same number from the library. */
-#define GSSDF_ABI_REVISION 10
+#define GSSDF_ABI_REVISION 11
 int32_t gssdf_abi_revision(void);
 
 /* Device-side counters shared by the stages of one render. Zeroed by gssdf_project2dgs_fwd. */
@@ -385,9 +385,10 @@ int gssdf_dssim_loss(const gssdf_dssim_loss_args *a, gssdf_stream_t stream);
  *     non-deterministic fp16 atomics). The fp16 shadow of the table is refreshed by
  *     gssdf_sdf_table_to_half once per optimiser step (the reference re-casts 61 MB on EVERY forward).
  *     Decoder parameters: torch::nn::Linear order, row-major W[out,in] then bias, layer after layer.
- *     Double backward (analytic eikonal through the encoding, grid.h:352-667) is not part of this ABI
- *     yet: the numerical-gradient regulariser (LocalMap::get_gradient numerical branch,
- *     local_map.cpp:110-147) is expressed with these two calls on the 6 offset points.
+ *     The analytic-eikonal double backward (grid.h:352-667) exists twice: fused into gssdf_sdf_train (eikonal_mode 1,
+ *     the throughput path) and as the operator-level gssdf_hashgrid_fwd/_bwd/_bwdbwd below (what the tcnn_binding twin's
+ *     autograd functions call); the numerical-gradient regulariser (LocalMap::get_gradient numerical branch,
+ *     local_map.cpp:110-147) is expressed with gssdf_sdf_fwd / _bwd on the 6 offset points (n_variants 7).
  * ------------------------------------------------------------------------------------------ */
 typedef struct gssdf_sdf_net {
     int32_t n_levels, n_features_per_level, log2_hashmap_size, base_resolution; /* 16, 2, 19, 32 */
@@ -465,6 +466,14 @@ typedef struct gssdf_sdf_loss_args {
     float bce_isigma, bce_weight, eikonal_weight, gs_sdf_weight, delta;
     float *loss_out;         /* device float[1] += */
     float *v_sdf, *v_y1;     /* [n_variants*n] */
+    /* Sample gate of the GS<->SDF coupling site (neural_mapping.cpp:428-437): the reference index_selects the samples with
+       `get_valid_mask(samples) & vis > k_visible_thr` BEFORE get_sdf / sdf_regularization, so eikonal (+ align) and the coupling term
+       act on that subset only and their means divide by its size. */
+    const uint8_t *valid_mask; /* [n] or NULL: 1 = inside the octree's occupied voxels (OctreeAS::query >= 0; gssdf_octree_query) */
+    const int32_t *n_gate;     /* device int32 or NULL: number of gated points (gssdf_sdf_gate_count). Non-NULL switches the gate on:
+                                  a point contributes to ANY term only if (visibilities == NULL || vis > visible_thr) && (valid_mask ==
+                                  NULL || valid_mask[i]); the eikonal / align means divide by *n_gate. NULL: round-1 behaviour (eikonal on
+                                  all live points, / n_live) -- the ray-sample site, where every point counts */
 } gssdf_sdf_loss_args;
 int gssdf_sdf_loss(const gssdf_sdf_loss_args *a, gssdf_stream_t stream);
 
@@ -500,8 +509,139 @@ typedef struct gssdf_sdf_train_args {
     const float *sdf_variants; /* mode 1, n_variants 1: [7n] sdf values from gssdf_sdf_fwd(n_variants = 7, same x / delta) or NULL. The
                                 cheapest arrangement for the reference default: one forward-only pass over the 7n evaluations, then this
                                 kernel on the n base points only */
+    const uint8_t *valid_mask; /* as in gssdf_sdf_loss_args */
+    const int32_t *n_gate;     /* as in gssdf_sdf_loss_args */
 } gssdf_sdf_train_args;
 int gssdf_sdf_train(const gssdf_sdf_train_args *a, gssdf_stream_t stream);
+
+/* Number of gated samples of the coupling site: *n_gate = #{ i < min(n, *n_live) : (visibilities == NULL || vis[i] > visible_thr) &&
+   (valid_mask == NULL || valid_mask[i]) }  (the `valid_mask.sum()` / `nonzero()` of neural_mapping.cpp:432-437, without the host sync). */
+typedef struct gssdf_sdf_gate_count_args {
+    int64_t n;
+    const int32_t *n_live;     /* device int32 or NULL */
+    const float *visibilities; /* [n] or NULL */
+    float visible_thr;
+    const uint8_t *valid_mask; /* [n] or NULL */
+    int32_t *n_gate;           /* device int32, overwritten */
+} gssdf_sdf_gate_count_args;
+int gssdf_sdf_gate_count(const gssdf_sdf_gate_count_args *a, gssdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a9/a12 operator level: the hash-grid encoding alone, with its first and second backward -- what the tcnn_binding twin
+ *     (shim/include/tcnn_binding/tcnn_binding.h: TCNNEncoding) binds in place of tcnn_binding::Module::fwd / bwd / bwd_bwd_input
+ *     (TB/bindings.cpp:76-257), i.e. tiny-cuda-nn's kernel_grid (grid.h:49-212), kernel_grid_backward (:215-320),
+ *     kernel_grid_backward_input (:323-349), kernel_grid_backward_input_backward_grid (:352-456), _backward_input (:458-622),
+ *     _backward_dLdoutput (:624-647) for <__half, 3 dims, 2 features, CoherentPrime, Linear>. Same fp16 rounding points as the binding:
+ *     table -> half, per-corner __hfma2, dL/dy -> half then x loss scale 128 in half, results / 128 (TB/tcnn_binding.cpp:122-192).
+ *     x is in [0,1]^3 (net.inv_size is ignored here: EncodingMap::encoding normalises before the call, encoding_map.cpp:31-60).
+ *     Only net.{n_levels, n_features_per_level, log2_hashmap_size, base_resolution, per_level_scale, table_half} are read.
+ *     No padding to 256 rows is needed (the binding pads for tcnn's batch granularity, TB/tcnn_binding.cpp:31-42).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gssdf_hashgrid_fwd_args {
+    gssdf_sdf_net net;
+    int64_t n;
+    const float *x;   /* [n,3] in [0,1]^3 */
+    float *feat;      /* [n, L*F] fp32 holding the encoder's fp16 values (the binding's `.to(kFloat32)`, TB/tcnn_binding.cpp:54-57) */
+} gssdf_hashgrid_fwd_args;
+int gssdf_hashgrid_fwd(const gssdf_hashgrid_fwd_args *a, gssdf_stream_t stream);
+
+typedef struct gssdf_hashgrid_bwd_args {
+    gssdf_sdf_net net;
+    int64_t n;
+    const float *x;      /* [n,3] */
+    const float *dL_dy;  /* [n, L*F] cotangent of feat */
+    float *table_grad;   /* [table_params] fp32 += or NULL; 8-byte aligned (the binding zero-fills a half buffer per call, grid.h:857-859) */
+    float *dL_dx;        /* [n,3] overwritten, or NULL */
+} gssdf_hashgrid_bwd_args;
+int gssdf_hashgrid_bwd(const gssdf_hashgrid_bwd_args *a, gssdf_stream_t stream);
+
+/* Backward of gssdf_hashgrid_bwd's dL_dx output (TCNNModuleFunctionBackward::backward, TB/tcnn_binding.cpp:151-192): given the
+   cotangent dL_ddLdx of dL_dx, produce the gradients w.r.t. the table, w.r.t. dL_dy and w.r.t. x. (The gradient of the first backward's
+   table_grad output is not supported -- neither is it in the reference, :156-160.) */
+typedef struct gssdf_hashgrid_bwdbwd_args {
+    gssdf_sdf_net net;
+    int64_t n;
+    const float *x;         /* [n,3] */
+    const float *dL_ddLdx;  /* [n,3] */
+    const float *dL_dy;     /* [n, L*F] the first backward's cotangent (needed for table_grad / dL_dx) */
+    float *table_grad;      /* [table_params] fp32 += or NULL */
+    float *dL_ddLdy;        /* [n, L*F] overwritten (fp16-rounded values), or NULL */
+    float *dL_dx;           /* [n,3] overwritten, or NULL: mixed second partials only (Linear interpolation: the Hessian diagonal is 0) */
+} gssdf_hashgrid_bwdbwd_args;
+int gssdf_hashgrid_bwdbwd(const gssdf_hashgrid_bwdbwd_args *a, gssdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f-1 (rest)  Normal-consistency loss and isotropic-scale regulariser of gs_train_batch_iter
+ *     (include/neural_mapping/neural_mapping.cpp:243-276).
+ *     normal consistency: depth_normal = normalize(cross(P[y+1,x]-P[y-1,x], P[y,x+1]-P[y,x-1])) on interior pixels, 0 on the border,
+ *       P = world point of the pixel centre (+0.5) at the rendered depth (sensor::depth_to_normal,
+ *       include/utils/sensor_utils/cameras.hpp:176-226); loss = w * mean_px( alpha^2 - nan_to_num(alpha * depth_normal . render_normal) )
+ *       with alpha detached. One kernel produces the loss and BOTH cotangents (dL/d depth through the 4-neighbour stencil, dL/d normal)
+ *       instead of ~25 ATen kernels + their autograd graph.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gssdf_normal_consistency_args {
+    int32_t C, image_width, image_height;
+    const float *viewmats;      /* [C,4,4] world->camera (the pose the reference passes is its inverse) */
+    const float *Ks;            /* [C,3,3] */
+    const float *depth;         /* [C,H,W,*] rendered depth, read at depth[pix * depth_stride] (out_colors + 3 with stride 4 = the expected
+                                   depth of "RGB+ED"; render_median with stride 1 when depth_type 1) */
+    int32_t depth_stride;
+    const float *render_alphas; /* [C,H,W,1] */
+    const float *out_normals;   /* [C,H,W,3] world-space rendered normals (render_post_fwd) */
+    float weight;               /* k_render_normal_weight */
+    float *loss_out;            /* device float[1] += */
+    float *v_depth;             /* [C,H,W,*] += at [pix * v_depth_stride] (v_out_colors + 3, stride 4), or NULL */
+    int32_t v_depth_stride;
+    float *v_out_normals;       /* [C,H,W,3] overwritten, or NULL */
+} gssdf_normal_consistency_args;
+int gssdf_normal_consistency_loss(const gssdf_normal_consistency_args *a, gssdf_stream_t stream);
+
+/* isotropic regulariser: scale = get_scale()[gaussian_ids][:, :2]; loss = w * mean |scale - mean(scale, -1)| (neural_mapping.cpp:268-276).
+   raw_params 1: `scales` holds log-scales (get_scale = exp) and v_scales is dL/d log-scale. */
+typedef struct gssdf_isotropic_loss_args {
+    int32_t N, cap;
+    const gssdf_counts *counts;   /* nnz */
+    const int64_t *gaussian_ids;  /* [cap] */
+    const float *scales;          /* [N,3] */
+    int32_t raw_params;
+    float weight;                 /* k_isotropic_weight */
+    float *loss_out;              /* device float[1] += */
+    float *v_scales;              /* [N,3] += (x, y components), or NULL */
+} gssdf_isotropic_loss_args;
+int gssdf_isotropic_loss(const gssdf_isotropic_loss_args *a, gssdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f-3 (first half)  Optimiser step.  Replaces `p_optimizer_->step()` = torch::optim::Adam over the 1 + 6 parameter groups
+ *     (include/neural_mapping/neural_mapping.cpp:466-469,825-829,855-858; include/neural_gaussian/neural_gaussian.cpp:426-449):
+ *     betas (0.9, 0.999), eps 1e-15, no weight decay, no amsgrad, one learning rate per group. ONE multi-tensor kernel over the flat
+ *     parameter / gradient / moment buffers:
+ *         g = grad * grad_scale;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *         p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)            (torch/csrc/api/src/optim/adam.cpp)
+ *     and in the same pass: the gradient is zeroed (replaces zero_grad), the fp16 shadow of the hash table is refreshed (replaces the
+ *     binding's per-forward 61 MB -> 30 MB cast, TB/tcnn_binding.cpp:49-52) and, when `net` is given, the decoder's bf16 operand image is
+ *     re-packed (second, 14 k-parameter launch).
+ * ------------------------------------------------------------------------------------------ */
+#define GSSDF_ADAM_MAX_GROUPS 16
+typedef struct gssdf_adam_group {
+    int64_t offset, count;   /* slice of the flat buffers */
+    float lr;
+    int32_t half_shadow;     /* 1: params of this group are mirrored to `table_half` (element i of the group -> table_half[i]) */
+} gssdf_adam_group;
+typedef struct gssdf_adam_args {
+    float *params;           /* flat fp32 parameters */
+    float *grads;            /* flat fp32 gradients (same indexing) */
+    float *exp_avg, *exp_avg_sq;
+    int32_t n_groups;
+    gssdf_adam_group groups[GSSDF_ADAM_MAX_GROUPS];
+    int32_t step;            /* t >= 1 (the reference keeps one step count per parameter; all parameters step together here) */
+    float beta1, beta2, eps; /* 0.9, 0.999, 1e-15 */
+    float grad_scale;        /* 1 / world_size after a gradient all-reduce(sum) under data parallelism, else 1 */
+    int32_t zero_grads;      /* 1: grads := 0 in the same pass */
+    void *table_half;        /* fp16 shadow (half_shadow groups) or NULL */
+    const gssdf_sdf_net *net; /* or NULL. Non-NULL (mlp_mode 1): net->mlp must point into `params`; gssdf_sdf_mlp_pack(net, mlp_packed) follows */
+    void *mlp_packed;
+} gssdf_adam_args;
+int gssdf_adam_step(const gssdf_adam_args *a, gssdf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -303,6 +303,15 @@ def hashgrid_bwd_bwd(x, dL_ddLdx, dL_dy, n_params, dy_dx, L=16, F=2, log2_hashma
     return tg, r
 
 
+def hashgrid_bwd_bwd_input(x, dL_ddLdx, dL_dy, table, L=16, F=2, log2_hashmap=19, base_res=32, per_level_scale=2.0):
+    """d(dL/dx)/dx contracted with dL_ddLdx (kernel_grid_backward_input_backward_input), loss scale removed."""
+    x, c, g, table = _f32(x), _f32(dL_ddLdx), _f32(dL_dy), _f32(table)
+    out = np.zeros((x.shape[0], 3), np.float32)
+    lib().oracle_hashgrid_bwd_bwd_input(C.c_int64(x.shape[0]), _p(x), _p(c), _p(g), _p(table), C.c_int(L), C.c_int(F), C.c_int(log2_hashmap),
+                                        C.c_int(base_res), C.c_float(per_level_scale), _p(out))
+    return out
+
+
 def _mlp_layers(mlp_params, widths):
     Ws, bs, o = [], [], 0
     p = np.asarray(mlp_params, np.float64)

@@ -68,4 +68,17 @@ int tcnn_ref_bwd_bwd(int n, int n_levels, int log2_hashmap, int base_res, float 
                   dy_dx, dL_dy, MatrixView<__half>(dL_ddLdy, n, 1));
     return (int)cudaDeviceSynchronize();
 }
+
+// double backward w.r.t. the input: dL_dx [n,3] fp32 (zero-filled here; still carries the loss scale of dL_dy), launch geometry of
+// GridEncodingTemplated::backward_backward_input_impl (grid.h:1003-1024)
+int tcnn_ref_bwd_bwd_input(int n, int n_levels, int log2_hashmap, int base_res, float pls, const float *x, const float *dL_ddLdx,
+                           const __half *dL_dy, const __half *grid, float *dL_dx) {
+    const GridOffsetTable off = make_offsets(n_levels, log2_hashmap, base_res, pls);
+    cudaMemset(dL_dx, 0, sizeof(float) * (size_t)n * 3);
+    const dim3 blocks = {div_round_up((uint32_t)n * 2 / 2, 256u), (uint32_t)n_levels, 1};
+    kernel_grid_backward_input_backward_input<__half, 3, 2, 2, HashType::CoherentPrime><<<blocks, 256>>>(
+        n, n_levels * 2, off, base_res, std::log2(pls), 1.0f, nullptr, InterpolationType::Linear, GridType::Hash,
+        MatrixView<const float>(dL_ddLdx, 1, 3), MatrixView<const float>(x, 1, 3), dL_dy, grid, MatrixView<float>(dL_dx, 1, 3));
+    return (int)cudaDeviceSynchronize();
+}
 }

@@ -290,6 +290,66 @@ void oracle_hashgrid_bwd_bwd(int64_t n, const float *x, const float *dL_ddLdx, c
     }
 }
 
+/* Double backward of the encoding w.r.t. the INPUT: restates kernel_grid_backward_input_backward_input (grid.h:458-622) for Linear
+ * interpolation (pos_derivative == 1, pos_2nd_derivative == 0: the Hessian diagonal vanishes, only the mixed partials remain,
+ * :558-559,584-618). dL_dx[n,3] (fp32, the reference accumulates the levels with float atomics) still carries the loss scale of dL_dy;
+ * the binding divides by it afterwards (TB/tcnn_binding.cpp:183-186) -- done here. table holds fp32 masters, read as half. */
+void oracle_hashgrid_bwd_bwd_input(int64_t n, const float *x, const float *dL_ddLdx, const float *dL_dy, const float *table, int L, int F,
+                                   int log2_hashmap, int base_res, float per_level_scale, float *dL_dx) {
+    uint32_t off[33];
+    oracle_grid_setup(L, F, log2_hashmap, base_res, per_level_scale, off);
+    float l2 = log2f(per_level_scale);
+    const double loss_scale = 128.0;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double acc[3] = {0, 0, 0};
+        for (int lvl = 0; lvl < L; ++lvl) {
+            uint32_t hs = off[lvl + 1] - off[lvl];
+            float scale = grid_scale(lvl, l2, base_res);
+            uint32_t res = grid_resolution(scale);
+            float pos[3];
+            uint32_t pg[3];
+            for (int d = 0; d < 3; ++d) {
+                pos[d] = fmaf(scale, x[3 * i + d], 0.5f);
+                float tmp = floorf(pos[d]);
+                pg[d] = (uint32_t)(int)tmp;
+                pos[d] -= tmp;
+            }
+            double gh[8];
+            for (int f = 0; f < F; ++f) gh[f] = rh(rh((double)dL_dy[i * L * F + lvl * F + f]) * loss_scale);
+            const float *tl = table + (size_t)off[lvl] * F;
+            for (int gd = 0; gd < 3; ++gd) {
+                float grad_out = 0;
+                for (int idx = 0; idx < 4; ++idx)
+                    for (int og = 0; og < 2; ++og) {
+                        int ro = og >= gd ? og + 1 : og; /* real_other_grad_dim */
+                        float w = scale * scale * dL_ddLdx[3 * i + ro] * 1.0f * 1.0f;
+                        uint32_t pl[3];
+                        for (int nd = 0; nd < 2; ++nd) {
+                            int d = nd >= ro ? nd + 1 : nd;
+                            if ((idx & (1 << nd)) == 0) {
+                                if (d != gd) w *= 1 - pos[d]; else w *= -1;
+                                pl[d] = pg[d];
+                            } else {
+                                if (d != gd) w *= pos[d];
+                                pl[d] = pg[d] + 1;
+                            }
+                        }
+                        for (int side = 0; side < 2; ++side) {
+                            pl[ro] = pg[ro] + side;
+                            uint32_t ix = grid_index(hs, res, pl) * F;
+                            float ww = side ? w : -w, s = 0;
+                            for (int f = 0; f < F; ++f) s += (float)rh((double)tl[ix + f]) * (float)gh[f] * ww;
+                            grad_out += s;
+                        }
+                    }
+                acc[gd] += (double)grad_out;
+            }
+        }
+        for (int d = 0; d < 3; ++d) dL_dx[3 * i + d] = (float)(acc[d] / loss_scale);
+    }
+}
+
 /* Test helper: parameter index (entry * F, i.e. of feature 0) of the 8 interpolation corners of every (point, level), in the corner
  * order idx = 0..7 (bit d set -> +1 along dimension d) used by the kernels above. */
 void oracle_grid_corner_indices(int64_t n, const float *x, int L, int F, int log2_hashmap, int base_res, float per_level_scale,
