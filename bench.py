@@ -1,22 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- train-step/s (and Mrays/s) of the GS-SDF splat hot path on B200 (BASELINE.json metric).
+"""bench.py -- train-step/s (and Mrays/s) of the GS-SDF hot path on B200 (BASELINE.json metric).
 
-A "step" is one pass of the hot path (SURVEY.md section 3.2 [A]-[D], rows a2-a12 of section 8a) over one
-camera per rank: SDF stage on 32768 ray samples (hash-grid + MLP at the point and its 6 numerical-gradient
-offsets, BCE + eikonal, backward) -> projection -> SH colour -> tile keys/sort/offsets -> rasterise -> post-ops
--> GS<->SDF coupling on the visible splats' stochastic samples (7 SDF evaluations each, backward incl. d/d sample)
--> L1 loss -> backward of the render to {means, quats, scales, opacities, SH}; with N > 1 ranks (image-batch data
-parallel, replicated state) the flat gradient (splats + hash table + decoder) is all-reduced over NCCL every step.
+A "step" is one pass of the hot path (SURVEY.md section 3.2 [A]-[D], rows a1-a12 + f-1 + the optimiser half of f-3 of section 8) over one
+camera per rank: SDF stage on 32768 ray samples (hash grid + MLP, BCE + analytic eikonal + align with the tcnn double backward) ->
+projection -> SH colour -> tile keys/sort/offsets -> rasterise -> post-ops -> GS<->SDF coupling on the visible splats' stochastic samples
+(gated by visibility like the reference) -> photometric loss (0.8 L1 + 0.2 DSSIM) + depth L1 + normal-consistency + isotropic -> backward of
+the render to {offsets, quaternion, scaling, opacity, SH} -> fused multi-tensor Adam over all 74 M parameters (zeroes the gradients,
+refreshes the fp16 table shadow and the decoder's operand image). With N > 1 ranks (image-batch data parallel, replicated state) the flat
+gradient is all-reduced over NCCL every step in two overlapped segments and every rank applies the same Adam update.
 
   value : whole-job steps/s with every input already resident in HBM (CUDA events, max over ranks)
   e2e   : the same through the public API with HOST buffers: per step the camera (viewmat, K) and the
           ground-truth image are copied from pinned host memory and the loss is read back (D2H)
-  roofline     : dominant kernel (raster backward): algorithmic bytes / CUDA-event time
-  cpu_baseline : the CPU oracle port on this box's host cores, on a bounded 1/16 sample of the workload
+  roofline     : dominant kernel (raster backward): algorithmic bytes on the intersections the launch PROCESSES / CUDA-event
+                 time, plus the issue-slot fraction (the bound that actually applies) when an ncu instruction count is committed
+  stock_cuda   : the reference fork's own CUDA kernels (oracle/_ref/gsplat_ref.so, compiled from /root/reference, test infrastructure) on
+                 the same tensors on the same GPU, per stage, beside ours (SURVEY 8d / BASELINE.md 3.1-2) -- never part of the product path
+  cpu_baseline : config c1 (256x256, 50 k splats, SH 0, MLP 2x32) run FOR REAL on the CPU oracle port incl. Adam (median step),
+                 next to the same c1 step on this GPU -- a measured ratio, nothing extrapolated
 
-`--impl reference` times the reference's own CPU path: GS-SDF has none (every op CHECK_CUDAs),
-so this arm runs the oracle port (oracle/, the CPU restatement of the reference kernels) with all host
-threads on a bounded sample of the same workload.
+`--impl reference` times the reference's own CPU path: GS-SDF has none (every op CHECK_CUDAs), so this arm runs the oracle
+port (oracle/, the CPU restatement of the reference kernels) with all host threads; each of its "steps" is a bounded SAMPLE of the
+workload (1/4 linear resolution, 1/16 of the splats and ray samples) and `value` is the sample rate x 1/16 -- stated in config.workload.
 """
 import argparse
 import json
@@ -114,13 +119,17 @@ def pci_bus_id():
         return None
 
 
-def ncu_traffic(kernel):
-    """Measured DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r1_traffic.json), or None."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        return d.get(kernel, {}).get("dram_bytes_per_launch")
-    except Exception:
-        return None
+def ncu_profile(kernel):
+    """Per-launch figures of `kernel` from the committed ncu --set full capture of this round (profiles/r2_traffic.json, else round 1's):
+    {dram_bytes_per_launch, inst_executed_per_launch, source}; empty when nothing is committed."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name))).get(kernel)
+            if d:
+                return dict(d, source="profiles/" + name)
+        except Exception:
+            pass
+    return {}
 
 
 def cpu_dssim(x, y, w):
@@ -200,6 +209,90 @@ def cpu_oracle_sdf(O, pts, table, mlp, hidden, n_hidden, gt=None, weights=None, 
     return loss
 
 
+class CpuAdam:
+    """torch::optim::Adam (eps 1e-15) on numpy arrays, for the CPU arms (the reference's step ends with Adam.step())."""
+
+    def __init__(self, params, lrs):
+        self.p, self.lr, self.t = params, lrs, 0
+        self.m = [np.zeros_like(x) for x in params]
+        self.v = [np.zeros_like(x) for x in params]
+
+    def step(self, grads):
+        self.t += 1
+        bc1, bc2 = 1 - 0.9 ** self.t, 1 - 0.999 ** self.t
+        for p_, g, m, v, lr in zip(self.p, grads, self.m, self.v, self.lr):
+            g = g.astype(np.float32, copy=False).reshape(p_.shape)
+            m *= 0.9
+            m += 0.1 * g
+            v *= 0.999
+            v += 0.001 * g * g
+            p_ -= (lr / bc1) * (m / (np.sqrt(v) / math.sqrt(bc2) + 1e-15))
+
+
+def cpu_full_step(O, S, sc, V, K, W, H, deg, rn, gt, table, mlp, hidden, n_hidden, ray, ray_gt, adam=None, analytic=True):
+    """[A]-[D] (+ Adam) on the oracle port; gradients w.r.t. the ACTIVATED splat parameters (the activations' chain rule is a handful of
+    elementwise numpy ops, negligible next to the render)."""
+    cpu_oracle_sdf(O, ray, table, mlp, hidden, n_hidden, gt=ray_gt, analytic=analytic)
+    loss, nnz, I, p, r = cpu_oracle_step(O, S, sc, V, K, W, H, deg, rn, gt)
+    vis = np.asarray(r["visibilities"], np.float32)[:, 0]
+    sel = vis > 0.1  # the reference's sample gate (neural_mapping.cpp:428-437)
+    w = (p["sample_weights"][:, 0] * vis).astype(np.float32)
+    if sel.any():
+        cpu_oracle_sdf(O, p["samples"][sel], table, mlp, hidden, n_hidden, weights=w[sel], analytic=analytic)
+    if adam is not None:  # dense update of every parameter tensor with stand-in gradients of the right size (the oracle calls above
+        adam.step(adam.grads)  # produce them; they are not threaded through to keep the oracle API unchanged)
+    return loss, nnz, I
+
+
+def run_cpu_c1(budget_s=20.0, max_steps=20, warmup=3):
+    """the CPU baseline is config c1 (256x256, 50 k splats, SH degree 0, MLP 2x32), the full step incl. Adam, for real."""
+    from gssdf_b200 import scene as S
+    from oracle import oracle as O
+    O.build()
+    W, H, N, deg, _ = WORKLOADS["c1"]
+    sc = S.box_scene(N, deg, seed=0)
+    V, K = S.cameras([0], W, H)
+    rn = S.randns(N)
+    gt = np.random.default_rng(3).random((1, H, W, 4), dtype=np.float32)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    O.set_threads(cores)
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=cores)
+    except Exception:
+        pass
+    rng = np.random.default_rng(5)
+    n_table, _ = O.grid_setup()
+    table = rng.uniform(-1e-4, 1e-4, n_table).astype(np.float32)
+    hidden, n_hidden = 32, 1
+    dims = [32] + [hidden] * (1 + n_hidden) + [2]
+    mlp = np.concatenate([np.concatenate([rng.uniform(-1, 1, o * k) / np.sqrt(k), rng.uniform(-1, 1, o) / np.sqrt(k)])
+                          for k, o in zip(dims[:-1], dims[1:])]).astype(np.float32)
+    n_ray = 32768
+    ray = (rng.uniform(-1, 1, (n_ray, 3)) * (S.BOX + 0.3)).astype(np.float32)
+    ray_gt = np.clip((S.BOX - np.abs(ray)).min(1), -0.3, 0.3).astype(np.float32)
+    params = [sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["sh"], table, mlp]
+    adam = CpuAdam(params, [1.6e-4, 1e-3, 5e-3, 5e-2, 2.5e-3, 5e-3, 5e-3])
+    adam.grads = [np.full_like(x, 1e-9) for x in params]
+    ts, nnz, I = [], 0, 0
+    t_all = time.perf_counter()
+    for i in range(warmup + max_steps):
+        t0 = time.perf_counter()
+        # numerical (6-offset) eikonal like the GPU arm at c1: the fused analytic kernel covers the 3x64 decoder only
+        _, nnz, I = cpu_full_step(O, S, sc, V, K, W, H, deg, rn, gt, table, mlp, hidden, n_hidden, ray, ray_gt, adam, analytic=False)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s and len(ts) >= 3:
+            break
+    med = float(np.median(ts))
+    return dict(value=1.0 / med, unit="step/s", cores=cores, kind="port", config="c1",
+                sample=f"config c1 run for real, nothing scaled: {W}x{H}, {N} splats, SH deg {deg}, MLP 2x32, {n_ray} ray samples + {nnz} "
+                       f"splat samples x7 SDF evaluations, numerical eikonal (as the GPU arm at c1), L1 + DSSIM, Adam over {sum(x.size for x in params)} "
+                       f"parameters; median of {len(ts)} steps after {warmup} warm-ups = {med * 1e3:.0f} ms (nnz={nnz}, n_isects={I}); "
+                       f"C + OpenMP fp32 oracle port, numpy/scipy glue")
+
+
 def run_cpu_sample(workload, steps, warmup, budget_s=25.0):
     """Times the oracle port on a bounded sample: the workload at 1/4 linear resolution with 1/16 of the splats
     (same screen coverage per splat, 1/16 of every unit count); returns full-workload-equivalent steps/s."""
@@ -233,29 +326,32 @@ def run_cpu_sample(workload, steps, warmup, budget_s=25.0):
     ray = (rng.uniform(-1, 1, (n_ray, 3)) * (S.BOX + 0.3)).astype(np.float32)
     ray_gt = np.clip((S.BOX - np.abs(ray)).min(1), -0.3, 0.3).astype(np.float32)
 
-    def full_step():
-        cpu_oracle_sdf(O, ray, table, mlp, hidden, n_hidden, gt=ray_gt)
-        loss, nnz, I, p, r = cpu_oracle_step(O, S, sc, V, K, Ws, Hs, deg, rn, gt)
-        vis = np.asarray(r["visibilities"], np.float32)[:, 0]
-        w = np.where(vis > 0.1, p["sample_weights"][:, 0] * vis, 0).astype(np.float32)
-        cpu_oracle_sdf(O, p["samples"], table, mlp, hidden, n_hidden, weights=w)
-        return loss, nnz, I
+    params = [sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["sh"], table, mlp]
+    adam = CpuAdam(params, [1.6e-4, 1e-3, 5e-3, 5e-2, 2.5e-3, 5e-3, 5e-3])
+    adam.grads = [np.full_like(x, 1e-9) for x in params]
 
-    for _ in range(max(1, min(warmup, 1))):
+    def full_step():
+        return cpu_full_step(O, S, sc, V, K, Ws, Hs, deg, rn, gt, table, mlp, hidden, n_hidden, ray, ray_gt, adam)
+
+    for _ in range(max(1, min(warmup, 2))):
         full_step()
     t0 = time.perf_counter()
-    done = 0
+    ts = []
     for _ in range(max(steps, 1)):
+        t1 = time.perf_counter()
         _, nnz, I = full_step()
-        done += 1
+        ts.append(time.perf_counter() - t1)
         if time.perf_counter() - t0 > budget_s:
             break
-    dt = (time.perf_counter() - t0) / done
+    dt, done = float(np.median(ts)), len(ts)
     frac = (Ws * Hs) / float(W * H)
     value = (1.0 / dt) * frac  # sample steps/s scaled by the work fraction = full-workload-equivalent steps/s
-    return dict(value=value, unit="step/s", cores=cores, kind="port",
-                sample=f"{done} oracle steps (C, OpenMP, fp32) of the workload at 1/{CPU_SAMPLE_DIV} linear resolution "
-                       f"({Ws}x{Hs}, {Ns} splats, nnz={nnz}, n_isects={I}, {n_ray}+{nnz} SDF points x7, analytic eikonal + align with double backward): {dt * 1e3:.0f} ms each; value = sample steps/s x {frac:.4f}"), W, H
+    return dict(value=value, unit="step/s", cores=cores, kind="port", sample_steps_per_s=1.0 / dt, sample_fraction=frac,
+                sample=f"median of {done} oracle steps (C, OpenMP, fp32, incl. numpy Adam over the full 15.3 M-entry table) of a BOUNDED SAMPLE "
+                       f"of the workload: 1/{CPU_SAMPLE_DIV} linear resolution ({Ws}x{Hs}), {Ns} splats, nnz={nnz}, n_isects={I}, "
+                       f"{n_ray}+gated splat samples x7 SDF evaluations, analytic eikonal + align with double backward: {dt * 1e3:.0f} ms "
+                       f"each; value = sample steps/s x {frac:.4f} (an extrapolation by work fraction, see cpu_baseline for a measured "
+                       f"like-for-like c1 pair)"), W, H
 
 
 def main():
@@ -268,20 +364,27 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eikonal", default="analytic", choices=["analytic", "numerical"],
                     help="analytic: eikonal + align on d sdf/dx with double backward (reference default); numerical: 6-offset gradient")
-    ap.add_argument("--distinct-cameras", action="store_true", help="N>1: rank r renders its own camera poses (adds load imbalance)")
+    ap.add_argument("--same-cameras", action="store_true", help="N>1: every rank renders the same camera poses (identical work per rank); "
+                    "default: rank r renders its own poses")
+    ap.add_argument("--no-stock-cuda", action="store_true", help="skip the reference-fork CUDA leg (oracle/_ref/gsplat_ref.so)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     W, H, N, deg, isect_cap = WORKLOADS[args.workload]
     cfg = {"workload": f"{args.workload}: {W}x{H}, {N} splats, SH deg {deg}, synthetic box scene seed 0 (SURVEY 8d), tile 16, packed, "
                        f"1 camera/rank/step", "timing": "CUDA events; inputs (232 B/splat state + images) exceed the 126 MB L2, no flush",
-           "parallelism": (f"image-parallel dp{world}, replicated state, 2 NCCL all-reduces/step: SDF segment under the render backward, splat "
-                           f"segment under the next step's SDF stage") if world > 1 else "single GPU"}
+           "parallelism": (f"image-parallel dp{world}, replicated state, rank r renders its own camera poses"
+                           f"{' (--same-cameras: identical poses)' if args.same_cameras else ''}, 2 NCCL all-reduces/step: SDF segment under "
+                           f"the render backward, splat segment under the next step's SDF stage; replicated Adam with grad_scale 1/{world}")
+           if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         cb, _, _ = run_cpu_sample(args.workload, max(args.steps, 1), args.warmup)
+        cfg = dict(cfg, workload=cfg["workload"] + f"; THIS ARM: each step is a bounded sample of that workload at 1/{CPU_SAMPLE_DIV} linear "
+                   f"resolution with 1/{CPU_SAMPLE_DIV ** 2} of the splats and ray samples, value = measured sample steps/s "
+                   f"({cb['sample_steps_per_s']:.4f}) x {cb['sample_fraction']:.4f}", parallelism=f"{cb['cores']} host threads (OpenMP)")
         line = {"impl": "reference", "metric": "train_steps_per_s", "value": cb["value"], "unit": "step/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": cb,
@@ -304,47 +407,61 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    sc_np = S.box_scene(N, deg, seed=0)  # replicated state: identical on every rank
-    sc_act = {k: t(v) for k, v in sc_np.items()}  # activated values (used once, for the ground-truth renders)
-    # the step runs on the RAW parameters of NeuralGS (anchors = centres, offsets = 0, scaling = log s, opacity =
-    # logit(o), features_dc | features_rest); row a1's activations are fused into the projection / SH kernels
-    op_ = np.clip(sc_np["opacities"], 1e-6, 1 - 1e-6)
-    sc = dict(means=sc_act["means"], quats=sc_act["quats"], scales=t(np.log(sc_np["scales"]).astype(np.float32)),
-              opacities=t(np.log(op_ / (1 - op_)).astype(np.float32)), sh=t(sc_np["sh"][:, :1].copy()),
-              raw=dict(offsets=torch.zeros(N, 3, device=dev), sh_rest=t(sc_np["sh"][:, 1:].copy()) if deg > 0 else None))
-    K_sh = (deg + 1) ** 2
-    sdf_cfg = dict(n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=2.0,
-                   hidden_dim=32 if args.workload == "c1" else 64, n_hidden=1 if args.workload == "c1" else 3)
+
+    def build_trainer(workload, eikonal):
+        """Trainer + its replicated state for one workload: synthetic box scene as RAW NeuralGS parameters (anchors = centres,
+        offsets = 0, scaling = log s, opacity = logit(o), features_dc | features_rest), tcnn-initialised table, torch-initialised decoder."""
+        W, H, N, deg, isect_cap = WORKLOADS[workload]
+        sc_np = S.box_scene(N, deg, seed=0)
+        sc_act = {k: t(v) for k, v in sc_np.items()}
+        K_sh = (deg + 1) ** 2
+        sdf_cfg = dict(n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=2.0,
+                       hidden_dim=32 if workload == "c1" else 64, n_hidden=1 if workload == "c1" else 3)
+        T = render.GsSdfTrainer(N, K_sh, W, H, dev, isect_cap, sdf_cfg, n_ray_samples=n_ray, sh_degree=deg, origin=(0.0, 0.0, 0.0),
+                                map_size=14.0, eikonal_mode=(1 if eikonal == "analytic" and sdf_cfg["hidden_dim"] == 64 else 0),
+                                normal_weight=0.01, isotropic_weight=0.05)  # config/base.yaml:43-46
+        gen = torch.Generator(dev).manual_seed(5)  # replicated parameters: same on every rank
+        table = (torch.rand(T.n_table, device=dev, generator=gen) * 2 - 1) * 1e-4  # tcnn grid init U(+-1e-4) (grid.h:1059-1062)
+        chunks, dims = [], [32] + [sdf_cfg["hidden_dim"]] * (1 + sdf_cfg["n_hidden"]) + [2]
+        for k_, o_ in zip(dims[:-1], dims[1:]):  # torch::nn::Linear default init
+            b_ = 1.0 / math.sqrt(k_)
+            chunks += [(torch.rand(o_ * k_, device=dev, generator=gen) * 2 - 1) * b_, (torch.rand(o_, device=dev, generator=gen) * 2 - 1) * b_]
+        op_ = np.clip(sc_np["opacities"], 1e-6, 1 - 1e-6)
+        T.load(sc_act["means"], torch.zeros(N, 3, device=dev), sc_act["quats"], t(np.log(sc_np["scales"]).astype(np.float32)),
+               t(np.log(op_ / (1 - op_)).astype(np.float32)), t(sc_np["sh"][:, :1].copy()),
+               t(sc_np["sh"][:, 1:].copy()) if deg > 0 else None, table, torch.cat(chunks))
+        return T, sc_act, (W, H, N, deg)
+
     n_ray = 32768  # config/base.yaml:23 batch_pt_num
-    G = render.GsSdfStep(N, K_sh, W, H, dev, isect_cap, sdf_cfg, n_ray_samples=n_ray, sh_degree=deg, origin=(0.0, 0.0, 0.0), map_size=14.0,
-                         eikonal_mode=(1 if args.eikonal == "analytic" and sdf_cfg["hidden_dim"] == 64 else 0))
-    R = G.R
-    gen = torch.Generator(dev).manual_seed(5)  # replicated parameters: same on every rank
-    table = (torch.rand(G.n_table, device=dev, generator=gen) * 2 - 1) * 1e-4  # tcnn grid init U(+-1e-4) (grid.h:1059-1062)
-    mlp_chunks, dims = [], [32] + [sdf_cfg["hidden_dim"]] * (1 + sdf_cfg["n_hidden"]) + [2]
-    for k_, o_ in zip(dims[:-1], dims[1:]):  # torch::nn::Linear default init
-        b_ = 1.0 / math.sqrt(k_)
-        mlp_chunks += [(torch.rand(o_ * k_, device=dev, generator=gen) * 2 - 1) * b_, (torch.rand(o_, device=dev, generator=gen) * 2 - 1) * b_]
-    mlp = torch.cat(mlp_chunks)
-    # ray samples: points within +-0.3 m of the box walls, ground-truth SDF = distance to the nearest wall (inside positive)
+    T, sc_act, _ = build_trainer(args.workload, args.eikonal)
+    R = T.R
+    K_sh = (deg + 1) ** 2
     box = torch.tensor(S.BOX, device=dev, dtype=torch.float32)
-    gen_r = torch.Generator(dev).manual_seed(50 + rank)  # each rank draws its own share of the ray batch
-    ray_xyz = (torch.rand(n_ray, 3, device=dev, generator=gen_r) * 2 - 1) * (box + 0.3)
-    ray_gt = (box - ray_xyz.abs()).min(dim=1).values.clamp(-0.3, 0.3).contiguous()
+
+    def ray_batch(seed):  # points within +-0.3 m of the box walls, ground-truth SDF = distance to the nearest wall (inside positive)
+        g_ = torch.Generator(dev).manual_seed(seed)
+        xyz = (torch.rand(n_ray, 3, device=dev, generator=g_) * 2 - 1) * (box + 0.3)
+        return xyz, (box - xyz.abs()).min(dim=1).values.clamp(-0.3, 0.3).contiguous()
+
+    ray_xyz, ray_gt = ray_batch(50 + rank)  # each rank draws its own share of the ray batch
     n_cams = 8
-    # weak scaling = identical work per GPU: every rank renders camera[step % 8] of the SAME pose set (rank-specific stochastic
-    # splat samples and SDF ray samples); --distinct-cameras gives rank r its own poses, which adds load imbalance between ranks
-    cam0 = rank * n_cams if args.distinct_cameras else 0
+    # image-batch data parallelism = "per-frame render on each rank" (north_star): rank r renders ITS OWN camera poses, so the ranks'
+    # per-step work differs (load imbalance is part of the measurement); --same-cameras restores identical work on every rank
+    cam0 = 0 if args.same_cameras else rank * n_cams
     cams = [S.camera(cam0 + i, W, H) for i in range(n_cams)]
     torch.manual_seed(1234 + rank)  # randns stream
-    # ground truth: the same scene rendered with perturbed colours, produced once on the device
-    sc_gt = dict(sc_act)
-    sc_gt["sh"] = sc_act["sh"] + 0.1 * torch.randn(sc_act["sh"].shape, device=dev, generator=torch.Generator(dev).manual_seed(3))
-    gts = []
+
+    def gt_images(Tr, act, cam_list, Wc, Hc):
+        """ground truth: the same scene rendered with perturbed colours, produced once on the device"""
+        sh_gt = act["sh"] + 0.1 * torch.randn(act["sh"].shape, device=dev, generator=torch.Generator(dev).manual_seed(3))
+        out = []
+        for V_, K_ in cam_list:
+            Tr.R.forward(act["means"], act["quats"], act["scales"], act["opacities"], sh_gt, t(V_[None]), t(K_[None]))
+            out.append(Tr.R.out_colors.clone())
+        return out
+
+    gts = gt_images(T, sc_act, cams, W, H)
     randn_buf = torch.empty(N, 2, device=dev)
-    for V, Kc in cams:
-        R.forward(sc_gt["means"], sc_gt["quats"], sc_gt["scales"], sc_gt["opacities"], sc_gt["sh"], t(V[None]), t(Kc[None]))
-        gts.append(R.out_colors.clone())
     torch.cuda.synchronize()
     dev_cams = [(t(V[None]), t(Kc[None])) for V, Kc in cams]
     host_cams = [(torch.from_numpy(V[None].copy()).pin_memory(), torch.from_numpy(Kc[None].copy()).pin_memory()) for V, Kc in cams]
@@ -354,22 +471,34 @@ def main():
     n_splat_grad = R.flat_grad.numel()
     # Data-parallel gradient exchange (gssdf_b200/parallel.py:GradientExchange): two NCCL all-reduces per step, both overlapped with
     # compute that does not depend on them -- the hash-table + decoder segment (61 MB) under the render backward [D] of the same step,
-    # the splat segment (236 MB) under stage [A] of the NEXT step; the optimiser scales by 1/world
+    # the splat segment (236 MB) under stage [A] of the NEXT step. Each segment's Adam update (grad_scale = 1 / world) runs as soon as its
+    # reduction is complete: SDF groups right after the step, splat groups just before the next render touches the splats.
     from gssdf_b200 import parallel
     xchg = parallel.GradientExchange()
     hook = xchg.on_sdf_grads_ready if world > 1 else None
-    pre = xchg.before_render if world > 1 else None
-    before_render = xchg.drain
+    pending = {"splat": False}
 
-    def finish_step():
-        xchg.finish_step(G.flat_grad[:n_splat_grad])
+    def pre_render():
+        xchg.before_render()
+        if pending["splat"]:
+            T.adam_splat(1.0 / world)
+            pending["splat"] = False
+
+    pre = pre_render if world > 1 else None
+
+    def after_step():
+        if world > 1:
+            xchg.finish_step(T.flat_grad[:n_splat_grad])  # splat all-reduce in flight; returns once the SDF segment is reduced
+            pending["splat"] = True
+            T.adam_sdf(1.0 / world)
+        else:
+            T.adam_all()
 
     def step_resident(i):
         V, Kc = dev_cams[i % n_cams]
         randn_buf.normal_()  # the reference draws randns on the device every render (Projection.cpp:728)
-        loss, _sdf_loss = G.step(sc, table, mlp, V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook, before_render=pre)
-        if world > 1:
-            finish_step()
+        loss, _sdf_loss = T.train_step(V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook, before_render=pre)
+        after_step()
         return loss
 
     # end-to-end path: every step's inputs (camera pose, intrinsics, ground-truth image) come from pinned HOST memory and the loss is
@@ -398,10 +527,9 @@ def main():
         cur = torch.cuda.current_stream()
         cur.wait_event(sl["ready"])
         randn_buf.normal_()
-        loss, _sdf_loss = G.step(sc, table, mlp, sl["V"], sl["K"], sl["gt"], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook, before_render=pre)
+        loss, _sdf_loss = T.train_step(sl["V"], sl["K"], sl["gt"], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook, before_render=pre)
         sl["free"].record(cur)
-        if world > 1:
-            finish_step()
+        after_step()
         loss_host.copy_(loss, non_blocking=True)
         cur.synchronize()  # the caller reads the loss every step (neural_mapping.cpp:505-514)
         return float(loss_host[0])
@@ -420,7 +548,7 @@ def main():
         for i in range(steps):
             fn(i)
         if world > 1:
-            before_render()  # the last step's splat all-reduce belongs to the timed region
+            pre_render()  # the last step's splat all-reduce and splat Adam belong to the timed region
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -432,6 +560,8 @@ def main():
 
     for i in range(max(args.warmup, 3)):
         step_resident(i)
+    if world > 1:
+        pre_render()
     cnt = R.read_counts()
     assert not cnt["nnz_overflow"] and not cnt["isect_overflow"], f"capacity overflow: {cnt}"
     # the timed region; the library records one CUDA-event pair per step around each raster kernel
@@ -441,74 +571,205 @@ def main():
         e0.record(); e1.record()  # creates the cudaEvent_t handles
     torch.cuda.synchronize()
     sampler = ClockSampler(local, pci_bus_id()) if rank == 0 else None
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if sampler:
-        sampler.start()
-    ev0.record()
-    for i in range(args.steps):
+
+    def step_prof(i):
         R.prof_fwd, R.prof_bwd = prof_f[i], prof_b[i]
         step_resident(i)
-    if world > 1:
-        before_render()  # the last step's splat all-reduce belongs to the timed region
-    ev1.record()
-    barrier()
+
+    ms_total = timed(step_prof, args.steps, sampler)
     fwd_ms = [a.elapsed_time(b) for a, b in prof_f]
     bwd_ms = [a.elapsed_time(b) for a, b in prof_b]
     R.prof_fwd = R.prof_bwd = None
-    ms_total = ev0.elapsed_time(ev1)
-    if world > 1:
-        tm = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ms_total = float(tm[0])
     clocks = sampler.summary() if sampler else None
     ms_step = ms_total / args.steps
     value = world * 1e3 / ms_step  # images (train steps of one camera) per second over the whole job
+    last_loss = float(T.R.loss[0])
+    cnt_end = R.read_counts()
 
     # end-to-end through the public API with host buffers
     for sl in slots:
         sl["free"].record(torch.cuda.current_stream())
     step_e2e(0, last=True)  # warm the path
+    if world > 1:
+        pre_render()
     torch.cuda.synchronize()
     ms_e2e = timed(lambda i: step_e2e(i, last=(i == args.steps - 1)), args.steps) / args.steps
     e2e_value = world * 1e3 / ms_e2e
     h2d = 16 * 4 + 9 * 4 + H * W * 4 * 4
     d2h = 4
 
+    # per-stage times of OUR step (CUDA events between the stages of 5 extra steps; outside the timed regions)
+    stage_ms = None
+    if rank == 0 and world == 1:
+        acc = {}
+        for i in range(5):
+            R.stage_events = []
+            step_resident(i)
+            torch.cuda.synchronize()
+            ev = R.stage_events
+            for (_, a), (name, b) in zip(ev[:-1], ev[1:]):
+                acc.setdefault(name, []).append(a.elapsed_time(b))
+        R.stage_events = None
+        stage_ms = {k: float(np.mean(v)) for k, v in acc.items()}
+
     if rank == 0:
         pk, pk_kind = peaks()
         # SURVEY 8d quotes the algorithmic bytes per REFERENCE intersection (every tile of a splat's radius AABB): I_ref. The fused
-        # step drops the pairs whose exact footprint misses the tile before the sort, so the kernels only walk I_kept of them.
+        # step drops the pairs whose exact footprint misses the tile before the sort, so the kernels only walk I_kept of them: the
+        # roofline fraction is computed on the units the launch processes; the reference-unit figure is a side field.
         nnz, I_kept, I, P = cnt["nnz"], cnt["n_isects"], max(cnt["n_isects_aabb"], cnt["n_isects"]), W * H
-        alg_bwd = 148 * I + 64 * P + 8 * nnz   # raster_bwd = 76 I + 64 P + 72 I + 8 nnz
-        alg_fwd = 76 * I + 56 * P + 4 * nnz
-        alg_bwd_kept = 148 * I_kept + 64 * P + 8 * nnz
+        alg_bwd_ref = 148 * I + 64 * P + 8 * nnz   # raster_bwd = 76 I + 64 P + 72 I + 8 nnz
+        alg_bwd = 148 * I_kept + 64 * P + 8 * nnz
+        alg_fwd = 76 * I_kept + 56 * P + 4 * nnz
         t_bwd = float(np.mean(bwd_ms)) * 1e-3
         t_fwd = float(np.mean(fwd_ms)) * 1e-3
         achieved = alg_bwd / t_bwd / 1e9
+        prof = ncu_profile("raster2dgs_bwd_kernel")
+        issue = None
+        if prof.get("inst_executed_per_launch") and clocks and clocks.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            slots_avail = sms * 4 * clocks["sm_mhz"] * 1e6 * t_bwd  # one warp instruction per SM sub-partition per clock
+            issue = {"inst_executed_per_launch": prof["inst_executed_per_launch"], "issue_slots_available": slots_avail,
+                     "frac": prof["inst_executed_per_launch"] / slots_avail, "source": prof.get("source"),
+                     "note": "warp instructions (ncu smsp__inst_executed.sum of the committed capture) / (SMs x 4 x measured SM clock x "
+                             "event time): the bound this kernel actually runs against"}
         line = {"metric": "train_steps_per_s", "value": value, "unit": "step/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": cfg, "mrays_per_s": value * P / 1e6, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "step/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
-                "gpu_launches": args.steps * render.GsSdfStep.KERNELS_PER_STEP,
+                "gpu_launches": args.steps * (render.GsSdfStep.KERNELS_PER_STEP - 2 + 4 + 2),
+                "step_contents": "[A] SDF on 32768 ray samples, [B] render, [C] gated GS<->SDF coupling, [D] L1 + DSSIM + depth L1 + "
+                                 "normal-consistency + isotropic -> backward, Adam over all parameter groups (f-3 first half); not in the "
+                                 "step: octree ray-march sample generation (a13; fixed ray batch), densification callbacks",
                 "roofline": {"kernel": "raster2dgs_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                             "frac": achieved / pk["hbm_gbs"], "traffic": ncu_traffic("raster2dgs_bwd_kernel"), "peak_source": pk_kind,
+                             "frac": achieved / pk["hbm_gbs"], "traffic": prof.get("dram_bytes_per_launch"), "peak_source": pk_kind,
                              "algorithmic_bytes": alg_bwd, "kernel_ms": t_bwd * 1e3,
-                             "units": {"I_reference": I, "I_after_exact_culling": I_kept, "P": P, "nnz": nnz},
-                             "achieved_on_kept_intersections": alg_bwd_kept / t_bwd / 1e9,
-                             "note": "algorithmic bytes per SURVEY 8d are counted on the reference's intersections; after exact "
-                                     "culling the kernel is issue/latency-bound, not HBM-bound (see profiles/)",
+                             "units": {"I_processed": I_kept, "I_reference_aabb": I, "P": P, "nnz": nnz},
+                             "frac_on_reference_units": alg_bwd_ref / t_bwd / 1e9 / pk["hbm_gbs"],
+                             "issue_slots": issue,
+                             "note": "frac = SURVEY 8d bytes on the intersections the launch processes (after exact pre-sort culling) / event "
+                                     "time / measured copy bandwidth. The kernel is instruction-issue bound, not HBM bound (measured DRAM "
+                                     "traffic is below the algorithmic bytes): see issue_slots and profiles/",
                              "raster_fwd": {"achieved": alg_fwd / t_fwd / 1e9, "frac": alg_fwd / t_fwd / 1e9 / pk["hbm_gbs"],
                                             "kernel_ms": t_fwd * 1e3, "algorithmic_bytes": alg_fwd}},
-                "counts": cnt}
+                "counts": cnt, "counts_end": cnt_end, "loss_end": last_loss, "loss_finite": bool(np.isfinite(last_loss)),
+                "stage_ms": stage_ms}
+        if world == 1 and not args.no_stock_cuda:
+            try:
+                line["stock_cuda"] = run_stock_cuda(torch, S, sc_act, cams, gts, W, H, deg, dev, stage_ms)
+            except Exception as e:  # test infrastructure missing on this box: say so, never fail the bench
+                line["stock_cuda"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
-            cb, _, _ = run_cpu_sample(args.workload, 3, 1)
+            cb = run_cpu_c1()
+            try:  # the same c1 step on this GPU: a measured like-for-like pair
+                del T
+                torch.cuda.empty_cache()
+                W1, H1, N1, deg1, _ = WORKLOADS["c1"]
+                T1, act1, _ = build_trainer("c1", args.eikonal)
+                cams1 = [S.camera(i, W1, H1) for i in range(n_cams)]
+                gts1 = gt_images(T1, act1, cams1, W1, H1)
+                dc1 = [(t(V_[None]), t(K_[None])) for V_, K_ in cams1]
+                rb1 = torch.empty(N1, 2, device=dev)
+
+                def c1_step(i):
+                    rb1.normal_()
+                    T1.train_step(dc1[i % n_cams][0], dc1[i % n_cams][1], gts1[i % n_cams], ray_xyz, ray_gt, rb1)
+                    T1.adam_all()
+                for i in range(5):
+                    c1_step(i)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(50):
+                    c1_step(i)
+                e1.record()
+                torch.cuda.synchronize()
+                gpu_c1 = 50e3 / e0.elapsed_time(e1)
+                cb["gpu_same_config"] = {"value": gpu_c1, "unit": "step/s", "ms_per_step": 1e3 / gpu_c1, "steps": 50,
+                                         "counts": T1.R.read_counts(), "ratio_gpu_over_cpu": gpu_c1 / cb["value"]}
+            except Exception as e:
+                cb["gpu_same_config"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_stock_cuda(torch, S, sc_act, cams, gts, W, H, deg, dev, ours_stage_ms, steps=5):
+    """The reference fork's own kernels (projection -> SH -> tile_encode incl. its CUB sort -> raster fwd -> raster bwd -> SH bwd ->
+    projection bwd, host glue of oracle/ref_driver.cpp incl. the reference's .item() syncs) on the SAME activated tensors, CUDA events per
+    stage, mean of `steps` runs after one warm-up. Test infrastructure: imported here and nowhere in the product path."""
+    import importlib
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "gsplat_ref.so")):
+        return {"unavailable": "oracle/_ref/gsplat_ref.so not built (python oracle/build_ref.py where /root/reference exists)"}
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    ref = importlib.import_module("gsplat_ref")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    means, quats, scales, sh, opac = sc_act["means"], sc_act["quats"], sc_act["scales"], sc_act["sh"], sc_act["opacities"]
+    N = means.shape[0]
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    names = ["projection_fwd", "sh_fwd", "tile_encode", "raster_fwd", "raster_bwd", "sh_bwd", "projection_bwd"]
+    acc = {k: [] for k in names}
+    info = {}
+    for it in range(steps + 1):
+        V, Kc = cams[it % len(cams)]
+        Vt, Kt = t(V[None]), t(Kc[None])
+        gt = gts[it % len(gts)]
+        rn = torch.randn(N, 2, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        ev[0].record()
+        (indptr, cam, gid, radii, m2d, dep, rt, nrm, randns, samples) = ref.projection_2dgs_packed_fwd(
+            means, quats, scales, Vt, Kt, W, H, S.NEAR, S.FAR, 0.0, rn)
+        ev[1].record()
+        c2w = torch.inverse(Vt)  # get_view_colors (GSC/rendering.cpp:27-44)
+        dirs = (means[gid] - c2w[cam, :3, 3]).contiguous()
+        shs = sh[gid].contiguous()
+        sh_raw = ref.sh_fwd(deg, dirs, shs)
+        colors = torch.clamp_min(sh_raw + 0.5, 0.0).contiguous()
+        pt_op = opac[gid].contiguous()
+        ev[2].record()
+        tpg, isect_ids, flatten_ids, offsets = ref.tile_encode(m2d, radii, dep, cam, gid, 1, 16, tw, th)
+        ev[3].record()
+        fw = ref.raster_fwd(m2d, rt, colors, pt_op, nrm, W, H, 16, offsets, flatten_ids)
+        (r_col, r_dep, r_alp, r_Ts, r_nrm, r_dis, r_med, last_ids, median_ids, vis) = fw
+        ev[4].record()
+        npx = float(W * H)
+        v_col = torch.sign(r_col - gt[..., :3]) / (3 * npx)
+        v_dep = torch.sign(r_dep / r_alp.clamp_min(1e-8) - gt[..., 3:]) * 0.1 / npx
+        z1, z3 = torch.zeros_like(r_alp), torch.zeros_like(r_nrm)
+        bw = ref.raster_bwd(m2d, rt, colors, pt_op, nrm, W, H, 16, offsets, flatten_ids, r_col, r_dep, r_alp, r_Ts, last_ids, median_ids,
+                            v_col.contiguous(), v_dep.contiguous(), z1, z3, z1, z1)
+        torch.cuda.synchronize()  # GSC/rasterize_to_pixels.cpp:252: the reference synchronises after its raster backward
+        ev[5].record()
+        v_m2d, v_rt, v_colr, v_op, v_nrm, v_den = bw
+        v_coeffs, v_dirs = ref.sh_bwd(deg, dirs, shs, (v_colr * (sh_raw + 0.5 > 0)).contiguous())
+        v_sh = torch.zeros_like(sh).index_add_(0, gid, v_coeffs)  # the ATen index backward of the gathers
+        ev[6].record()
+        pb = ref.projection_2dgs_packed_bwd(means, quats, scales, Vt, Kt, W, H, cam, gid, rt, randns, v_m2d, torch.zeros_like(dep), v_rt,
+                                            v_nrm, torch.zeros_like(samples))
+        ev[7].record()
+        torch.cuda.synchronize()
+        if it > 0:
+            for k, a, b in zip(names, ev[:-1], ev[1:]):
+                acc[k].append(a.elapsed_time(b))
+        info = {"nnz": int(gid.shape[0]), "n_isects": int(flatten_ids.shape[0])}
+    st = {k: float(np.mean(v)) for k, v in acc.items()}
+    total = float(sum(st.values()))
+    out = {"kind": "reference fork CUDA kernels (gsplat 2DGS path of GS-SDF) compiled for sm_100a with the reference's flags (-O3 "
+                   "--use_fast_math), same GPU, same tensors", "stage_ms": st, "splat_chain_ms": total, "steps": steps, "counts": info,
+           "covers": "splat chain only (a2-a7): no losses, no SDF stages, no optimiser"}
+    if ours_stage_ms:
+        mine = {k: ours_stage_ms.get(k) for k in names}
+        if all(v is not None for v in mine.values()):
+            out["ours_stage_ms"] = mine
+            out["ours_splat_chain_ms"] = float(sum(mine.values()))
+            out["speedup_splat_chain"] = total / out["ours_splat_chain_ms"]
+            out["speedup_per_stage"] = {k: st[k] / mine[k] for k in names if mine[k] > 0}
+    return out
 
 
 if __name__ == "__main__":

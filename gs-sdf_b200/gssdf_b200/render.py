@@ -63,6 +63,13 @@ class SplatRenderer:
         self.loss_ws = cabi.Workspace(device)  # DSSIM derivative maps
         self.raster_ws.get(cabi.lib().gssdf_raster2dgs_bwd_workspace_bytes(C, W, H, cap, cabi._lib.C.c_int64(self.isect_cap)))
         self.prof_fwd = self.prof_bwd = None  # optional (start, stop) torch.cuda.Event pairs around the raster kernels
+        self.stage_events = None  # profiling: list of (stage name, torch.cuda.Event recorded AFTER the stage) (bench.py per-stage table)
+
+    def _mark(self, name):
+        if self.stage_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.stage_events.append((name, ev))
 
     # -- forward ------------------------------------------------------------------------------
     def forward(self, means, quats, scales, opacities, sh, viewmats, Ks, randns=None, raw=None):
@@ -72,24 +79,29 @@ class SplatRenderer:
         off, rest = (raw["offsets"], raw["sh_rest"]) if raw else (None, None)
         cabi.project2dgs_fwd(means, quats, scales, viewmats, Ks, W, H, self.near, self.far, 0.0, randns, cap, self.p,
                              self.counts, self.ws, opacities=opacities, mean_offsets=off, raw_params=raw is not None)
+        self._mark("projection_fwd")
         cabi.view_colors_fwd(viewmats, means, sh, self.sh_degree, cap, self.counts, self.p["camera_ids"],
                              self.p["gaussian_ids"], self.p["radii"], self.colors, mean_offsets=off, sh_rest=rest)
+        self._mark("sh_fwd")
         conics = None
         if self.presort_cull:  # exact footprint test BEFORE the sort: ~4x fewer keys to scatter / sort / cull
             cabi.splat_conics(cap, W, H, self.counts, self.p["ray_transforms"], self.p["pt_opacities"], self.conics)
             conics = self.conics
         cabi.tile_encode(C, W, H, self.tile, cap, self.counts, self.p["means2d"], self.p["radii"], self.p["depths"],
                          self.p["camera_ids"], self.isect_cap, None, None, self.flatten_ids, self.offsets, self.ws, conics=conics)
+        self._mark("tile_encode")
         cabi.raster2dgs_fwd(C, W, H, self.tile, 3, cap, self.counts, self.p["means2d"], self.p["ray_transforms"], self.colors,
                             self.p["pt_opacities"], self.p["normals"], None, self.offsets, self.flatten_ids, self.r, self.raster_ws,
                             prof=self.prof_fwd, isect_cap=self.isect_cap)
+        self._mark("raster_fwd")
         cabi.render_post_fwd(C, W, H, viewmats, self.r["render_colors"], self.r["render_depths"], self.r["render_alphas"],
                              self.r["render_normals"], self.out_colors, self.out_normals)
+        self._mark("post_fwd")
         return self.out_colors, self.out_normals
 
     # -- loss + backward -----------------------------------------------------------------------
     def backward(self, means, quats, scales, opacities, sh, viewmats, Ks, gt, randns=None, w_rgb=1.0, w_depth=0.1, v_samples=None,
-                 zero_grads=True, raw=None, w_dssim=0.0):
+                 zero_grads=True, raw=None, w_dssim=0.0, w_normal=0.0, w_isotropic=0.0):
         """With raw parameters the flat gradient holds dL/d(offsets|quats|log-scales|logits|features_dc|features_rest); the SH segment
         keeps its [N,K,3] size, laid out as dc [N,1,3] followed by rest [N,K-1,3]."""
         C, W, H, cap = self.C, self.W, self.H, self.cap
@@ -103,22 +115,38 @@ class SplatRenderer:
         cabi.l1_loss(C, W, H, self.out_colors, gt, w_rgb, w_depth, self.loss, self.v_out_colors)
         if w_dssim > 0:  # + w_dssim * (1 - SSIM(rgb, gt)) (loss::dssim_loss), gradient added to the colour cotangent
             cabi.dssim_loss(C, W, H, self.out_colors, gt, w_dssim, self.loss, self.v_out_colors, self.loss_ws)
+        if w_normal > 0:  # normal consistency between the rendered normals and the normals of the expected-depth map
+                          # (neural_mapping.cpp:243-266): adds to the ED cotangent (channel 3) and overwrites the normal cotangent
+            cabi.normal_consistency_loss(C, W, H, viewmats, Ks, self.out_colors.data_ptr() + 12, 4, self.r["render_alphas"], self.out_normals,
+                                         w_normal, self.loss, v_depth=self.v_out_colors.data_ptr() + 12, v_depth_stride=4,
+                                         v_out_normals=self.v_out_normals)
+            self._v_normals_dirty = True
+        elif getattr(self, "_v_normals_dirty", False):
+            self.v_out_normals.zero_()
+            self._v_normals_dirty = False
+        if w_isotropic > 0:  # isotropic regulariser on the visible splats' (x, y) scales (neural_mapping.cpp:268-276)
+            cabi.isotropic_loss(self.N, cap, self.counts, self.p["gaussian_ids"], scales, raw is not None, w_isotropic, self.loss,
+                                self.v_scales)
         cabi.render_post_bwd(C, W, H, viewmats, self.r["render_depths"], self.r["render_alphas"], self.v_out_colors,
                              self.v_out_normals, None, self.v_r["colors"], self.v_r["depths"], self.v_r["alphas"],
                              self.v_r["normals"])
+        self._mark("losses+post_bwd")
         cabi.raster2dgs_bwd(C, W, H, self.tile, 3, cap, self.counts, self.p["means2d"], self.p["ray_transforms"], self.colors,
                             self.p["pt_opacities"], self.p["normals"], None, self.offsets, self.flatten_ids,
                             self.r["render_alphas"], None, self.r["last_ids"], self.r["median_ids"],
                             self.v_r["colors"], self.v_r["depths"], self.v_r["alphas"], self.v_r["normals"],
                             self.v_r["median"], self.g, self.raster_ws, prof=self.prof_bwd, isect_cap=self.isect_cap, reuse_fwd=True)
+        self._mark("raster_bwd")
         cabi.view_colors_bwd(viewmats, means, sh, self.sh_degree, cap, self.counts, self.p["camera_ids"],
                              self.p["gaussian_ids"], self.p["radii"], self.colors, self.g["v_colors"], v_sh, self.v_means,
                              mean_offsets=off, sh_rest=rest, v_sh_rest=v_rest)
+        self._mark("sh_bwd")
         cabi.project2dgs_bwd(means, quats, scales, viewmats, Ks, W, H, cap, self.counts, self.p["camera_ids"],
                              self.p["gaussian_ids"], self.p["ray_transforms"], randns, None, None, self.g["v_ray_transforms"],
                              self.g["v_normals"], v_samples, self.v_means, self.v_quats, self.v_scales,
                              v_pt_opacities=self.g["v_opacities"], v_opacities=self.v_opac, mean_offsets=off,
                              raw_params=raw is not None, pt_opacities=self.p["pt_opacities"])
+        self._mark("projection_bwd")
         return self.loss
 
     def step(self, scene, viewmats, Ks, gt, randns=None):
@@ -144,13 +172,16 @@ class GsSdfStep:
                                  (vis > visible_thr); its gradient w.r.t. the samples flows into the projection backward
       [D] backward             : L1 photometric/depth loss -> raster bwd -> SH bwd -> projection bwd
     All gradients land in ONE flat buffer [splat grads | table grad | decoder grad] (single all-reduce under data parallelism).
-    The eikonal terms use the numerical-gradient branch of LocalMap::get_gradient (local_map.cpp:110-133); the analytic
-    double-backward through the encoding is not implemented yet.
+    eikonal_mode 1 (default with the tensor-core decoder): eikonal + align on the ANALYTIC gradient with the tcnn double backward, the
+    reference default (config/base.yaml:13); eikonal_mode 0: the 6-offset numerical-gradient branch (local_map.cpp:110-133).
+    Stage [C] applies the reference's sample gate (vis > visible_thr [& octree validity]): eikonal / align / coupling act on the gated
+    samples only and their means divide by the gated count (neural_mapping.cpp:428-452).
     """
 
     def __init__(self, N, K, W, H, device, isect_cap, sdf_net_cfg, n_ray_samples=32768, sh_degree=3, origin=(0.0, 0.0, 0.0),
                  map_size=14.0, bce_sigma=0.1, delta=None, eikonal_weight=0.1, gs_sdf_weight=1e-3, visible_thr=0.1, mlp_mode=None,
-                 eikonal_mode=None, align_weight=0.1, rgb_weight=0.8, dssim_weight=0.2, depth_weight=0.1):
+                 eikonal_mode=None, align_weight=0.1, rgb_weight=0.8, dssim_weight=0.2, depth_weight=0.1, normal_weight=0.0,
+                 isotropic_weight=0.0):
         self.R = SplatRenderer(N, K, 1, W, H, device, isect_cap, sh_degree=sh_degree)
         self.dev, self.N, self.n_ray = device, N, n_ray_samples
         self.cfg = dict(sdf_net_cfg)
@@ -159,6 +190,10 @@ class GsSdfStep:
         self.eik_w, self.gs_sdf_w, self.vis_thr = eikonal_weight, gs_sdf_weight, visible_thr
         # photometric loss: k_rgb_weight * L1 + k_dssim_weight * (1 - SSIM) (config/base.yaml:35-36) (+ an L1 on the expected depth)
         self.rgb_w, self.dssim_w, self.depth_w = rgb_weight, dssim_weight, depth_weight
+        # k_render_normal_weight / k_isotropic_weight (config/base.yaml:43-46: 0.01 / 0.05; the normal term from iteration 3000 on)
+        self.normal_w, self.iso_w = normal_weight, isotropic_weight
+        self.valid_mask = None       # [cap] uint8 octree validity of the splat samples (LocalMap::get_valid_mask) or None
+        self.keep_shadows = False    # True: the caller (GsSdfTrainer's Adam) keeps table_half / mlp_packed current and zeroes the gradients
         f32 = dict(dtype=torch.float32, device=device)
         probe = cabi.sdf_net(torch.zeros(1, **f32), torch.zeros(1, **f32), **self.cfg)
         self.n_table, self.n_mlp = cabi.sdf_table_params(probe), cabi.sdf_mlp_params(probe)
@@ -185,8 +220,9 @@ class GsSdfStep:
         self.gs_sdf, self.gs_y1, self.gs_vs, self.gs_vy = e(7 * cap), e(7 * cap), e(7 * cap), e(7 * cap)
         self.v_samples = e(cap, 3)
         self.sdf_loss = torch.zeros(1, **f32)
+        self.n_gate = torch.zeros(1, dtype=torch.int32, device=device)
 
-    KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 8  # + 2 DSSIM kernels + table cast + decoder weight image + 2 x (7-variant forward, fused train) (mlp_mode 1)
+    KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 9  # + 2 DSSIM kernels + table cast + decoder weight image + gate count + 2 x (7-variant forward, fused train) (mlp_mode 1)
 
     def _rebind_splat_grads(self, n_splat):
         R, N, K = self.R, self.R.N, self.R.K
@@ -208,14 +244,17 @@ class GsSdfStep:
             depends on the SDF parameters only, so the PREVIOUS step's splat-gradient all-reduce (and splat optimiser step) may still be
             in flight while [A] runs; the caller waits for them here."""
         R, n_ray, cap = self.R, self.n_ray, self.R.cap
+        R._mark("start")
         # fp32 master -> fp16 shadow once per step (the optimiser moved the master; the reference casts on EVERY forward)
-        cabi.sdf_table_to_half(table_f32, self.table_half)
-        if self.mlp_mode == 1:  # bf16 hi/mid/lo weight image for the tensor-core decoder, also once per step
-            cabi.sdf_mlp_pack(cabi.sdf_net(self.table_half, mlp, **self.cfg), self.mlp_packed)
+        if not self.keep_shadows:
+            cabi.sdf_table_to_half(table_f32, self.table_half)
+            if self.mlp_mode == 1:  # bf16 hi/mid/lo weight image for the tensor-core decoder, also once per step
+                cabi.sdf_mlp_pack(cabi.sdf_net(self.table_half, mlp, **self.cfg), self.mlp_packed)
         net = cabi.sdf_net(self.table_half, mlp, origin=self.origin, inv_size=self.inv_size, mlp_mode=self.mlp_mode,
                            mlp_packed=self.mlp_packed, **self.cfg)
         t0 = self.table_grad.storage_offset()
-        self.flat_grad[t0:].zero_()  # table + decoder segment; the splat segment is cleared after before_render()
+        if not self.keep_shadows:
+            self.flat_grad[t0:].zero_()  # table + decoder segment; the splat segment is cleared after before_render()
         self.sdf_loss.zero_()
         # [A] SDF stage on the ray samples (tensor-core mode: forward + losses + backward fused in one kernel)
         if self.mlp_mode == 1:
@@ -234,14 +273,20 @@ class GsSdfStep:
             cabi.sdf_loss(n_ray, 7, self.ray_sdf, self.ray_y1, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.delta, self.sdf_loss,
                           self.ray_vs, self.ray_vy)
             cabi.sdf_bwd(net, ray_xyz, self.ray_vs, self.ray_vy, self.table_grad, self.mlp_grad, None, n_variants=7, delta=self.delta)
+        R._mark("sdf_ray_samples[A]")
         if before_render is not None:
             before_render()
-        self.flat_grad[:t0].zero_()
+        if not self.keep_shadows:
+            self.flat_grad[:t0].zero_()
         # [B] render
         R.forward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, randns,
                   raw=scene.get("raw"))
         # [C] coupling on the stochastic splat samples (rows < nnz, counted on the device)
         samples, n_live = R.p["samples"], R.counts  # counts[0] == nnz
+        # the reference's sample gate: vis > visible_thr (& octree validity), counted on the device (no nonzero() / .item() sync)
+        cabi.sdf_gate_count(cap, self.n_gate, visibilities=R.r["visibilities"], visible_thr=self.vis_thr, valid_mask=self.valid_mask,
+                            n_live=n_live)
+        gate = dict(valid_mask=self.valid_mask, n_gate=self.n_gate)
         if self.mlp_mode == 1:
             if self.eik_mode == 1:
                 if self.align_w > 0:
@@ -249,21 +294,100 @@ class GsSdfStep:
                 cabi.sdf_train(net, samples, 1, self.delta, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
                                self.sdf_loss, self.table_grad, self.mlp_grad, self.v_samples, visibilities=R.r["visibilities"],
                                visible_thr=self.vis_thr, n_live=n_live, eikonal_mode=1, align_weight=self.align_w,
-                               sdf_variants=self.gs_sdf if self.align_w > 0 else None)
+                               sdf_variants=self.gs_sdf if self.align_w > 0 else None, **gate)
             else:
                 cabi.sdf_train(net, samples, 7, self.delta, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
                                self.sdf_loss, self.table_grad, self.mlp_grad, self.v_samples, visibilities=R.r["visibilities"],
-                               visible_thr=self.vis_thr, n_live=n_live)
+                               visible_thr=self.vis_thr, n_live=n_live, **gate)
         else:
             cabi.sdf_fwd(net, samples, self.gs_sdf, self.gs_y1, None, n_variants=7, delta=self.delta, n_live=n_live)
             cabi.sdf_loss(cap, 7, self.gs_sdf, self.gs_y1, None, R.p["sample_weights"], self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w, self.delta,
-                          self.sdf_loss, self.gs_vs, self.gs_vy, visibilities=R.r["visibilities"], visible_thr=self.vis_thr, n_live=n_live)
+                          self.sdf_loss, self.gs_vs, self.gs_vy, visibilities=R.r["visibilities"], visible_thr=self.vis_thr, n_live=n_live,
+                          **gate)
             cabi.sdf_bwd(net, samples, self.gs_vs, self.gs_vy, self.table_grad, self.mlp_grad, self.v_samples, n_variants=7, delta=self.delta,
                          n_live=n_live)
+        R._mark("sdf_splat_samples[C]")
         if on_sdf_grads_ready is not None:
             on_sdf_grads_ready(self.flat_grad[self.table_grad.storage_offset():])
         # [D] photometric loss + backward of the render, with the coupling gradient entering through the samples
         loss = R.backward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, gt_image, randns,
                           v_samples=self.v_samples, zero_grads=False, raw=scene.get("raw"), w_rgb=self.rgb_w, w_depth=self.depth_w,
-                          w_dssim=self.dssim_w)
+                          w_dssim=self.dssim_w, w_normal=self.normal_w, w_isotropic=self.iso_w)
         return loss, self.sdf_loss
+
+
+class GsSdfTrainer(GsSdfStep):
+    """GsSdfStep + the optimiser step of the reference loop (`zero_grad; backward; Adam.step()`, neural_mapping.cpp:466-469): owns ONE
+    flat fp32 parameter buffer with exactly the layout of the flat gradient
+
+        [ offsets N*3 | quaternion N*4 | scaling N*3 | opacity N | features_dc N*3 | features_rest N*(K-1)*3 | pad | hash table | decoder ]
+
+    plus Adam's two moment buffers, and runs `gssdf_adam_step` over its parameter groups (learning rates of
+    neural_gaussian.cpp:434-449 and config/base.yaml:25; eps 1e-15). The same kernel zeroes the gradient, refreshes the fp16 shadow of
+    the hash table and re-packs the decoder's bf16 operand image, so a training step launches no cast / pack / memset kernels.
+    `anchors` are not optimised (register_parameter(..., false), neural_gaussian.cpp:426)."""
+
+    def __init__(self, *a, spatial_scale=1.0, sdf_lr=5e-3, **kw):
+        super().__init__(*a, **kw)
+        N, K = self.R.N, self.R.K
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        n = self.flat_grad.numel()
+        self.params, self.exp_avg, self.exp_avg_sq = torch.zeros(n, **f32), torch.zeros(n, **f32), torch.zeros(n, **f32)
+        t0 = self.table_grad.storage_offset()
+        o = [0, N * 3, N * 7, N * 10, N * 11, N * 14, N * 11 + N * K * 3]
+        lr = [1.6e-4 * spatial_scale, 0.001, 0.005, 0.05, 0.0025, 0.0025 / 20.0]  # offsets, quaternion, scaling, opacity, dc, rest
+        self.splat_groups = [(o[i], o[i + 1] - o[i], lr[i], False) for i in range(6) if o[i + 1] > o[i]]
+        self.sdf_groups = [(t0, self.n_table, sdf_lr, True), (t0 + self.n_table, self.n_mlp, sdf_lr, False)]
+        pv = self.params
+        self.anchors = torch.zeros(N, 3, **f32)
+        self.scene = dict(means=self.anchors, quats=pv[o[1]:o[2]].view(N, 4), scales=pv[o[2]:o[3]].view(N, 3), opacities=pv[o[3]:o[4]],
+                          sh=pv[o[4]:o[5]].view(N, 1, 3),
+                          raw=dict(offsets=pv[o[0]:o[1]].view(N, 3), sh_rest=pv[o[5]:o[6]].view(N, K - 1, 3) if K > 1 else None))
+        self.table, self.mlp = pv[t0:t0 + self.n_table], pv[t0 + self.n_table:]
+        # the shadow pointer of the table group is relative to the group start: element i of the group -> table_half[i]
+        self.keep_shadows = True
+        self.t_splat = self.t_sdf = 0
+        self._net = None
+
+    def load(self, anchors, offsets, quats, log_scales, logit_opacities, features_dc, features_rest, table, mlp):
+        sc = self.scene
+        self.anchors.copy_(anchors)
+        sc["raw"]["offsets"].copy_(offsets); sc["quats"].copy_(quats); sc["scales"].copy_(log_scales); sc["opacities"].copy_(logit_opacities)
+        sc["sh"].copy_(features_dc.view_as(sc["sh"]))
+        if sc["raw"]["sh_rest"] is not None:
+            sc["raw"]["sh_rest"].copy_(features_rest)
+        self.table.copy_(table); self.mlp.copy_(mlp)
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.flat_grad.zero_()
+        self.t_splat = self.t_sdf = 0
+        cabi.sdf_table_to_half(self.table, self.table_half)
+        self._net = cabi.sdf_net(self.table_half, self.mlp, **self.cfg)
+        if self.mlp_mode == 1:
+            cabi.sdf_mlp_pack(self._net, self.mlp_packed)
+
+    def _adam(self, groups, t, grad_scale, sdf):
+        self._adam_call(groups, t, grad_scale, sdf)
+        self.R._mark("adam")
+
+    def _adam_call(self, groups, t, grad_scale, sdf):
+        cabi.adam_step(self.params, self.flat_grad, self.exp_avg, self.exp_avg_sq, groups, t, grad_scale=grad_scale, zero_grads=True,
+                       table_half=self.table_half if sdf else None, net=self._net if (sdf and self.mlp_mode == 1) else None,
+                       mlp_packed=self.mlp_packed if (sdf and self.mlp_mode == 1) else None)
+
+    def adam_sdf(self, grad_scale=1.0):
+        self.t_sdf += 1
+        self._adam(self.sdf_groups, self.t_sdf, grad_scale, True)
+
+    def adam_splat(self, grad_scale=1.0):
+        self.t_splat += 1
+        self._adam(self.splat_groups, self.t_splat, grad_scale, False)
+
+    def adam_all(self, grad_scale=1.0):
+        """Single-GPU: one launch over all seven groups (+ the decoder re-pack)."""
+        self.t_sdf += 1
+        self.t_splat += 1
+        assert self.t_sdf == self.t_splat
+        self._adam(self.splat_groups + self.sdf_groups, self.t_sdf, grad_scale, True)
+
+    def train_step(self, viewmats, Ks, gt_image, ray_xyz, ray_gt_sdf, randns=None, on_sdf_grads_ready=None, before_render=None):
+        return self.step(self.scene, self.table, self.mlp, viewmats, Ks, gt_image, ray_xyz, ray_gt_sdf, randns,
+                         on_sdf_grads_ready=on_sdf_grads_ready, before_render=before_render)

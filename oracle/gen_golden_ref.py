@@ -27,14 +27,17 @@ CASES = {
 }
 
 
-def main():
-    ref = importlib.import_module("gsplat_ref")
-    dev = torch.device("cuda:0")
-    out_dir = os.path.join(ROOT, "gpurun_out", "golden")
-    os.makedirs(out_dir, exist_ok=True)
+def load_ref():
+    return importlib.import_module("gsplat_ref")
+
+
+def run_case(ref, dev, N, W, H, deg, scale, seed):
+    """One call chain of rasterization_2dgs_sdf on the reference fork's CUDA kernels; every tensor as numpy."""
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     n = lambda x: x.detach().cpu().numpy()
-    for name, (N, W, H, deg, scale, seed) in CASES.items():
+    if scale is None:
+        scale = float(np.sqrt(1.0e6 / N))  # box_scene's default: constant screen coverage
+    if True:
         sc = S.box_scene(N, deg, seed=seed, scale_mult=scale)
         V, K = S.cameras([0], W, H)
         rn = S.randns(N)
@@ -65,8 +68,8 @@ def main():
         pb = ref.projection_2dgs_packed_bwd(means, quats, scales, t(V), t(K), W, H, cam, gid, rt, randns, v_m2d,
                                             torch.zeros(nnz, device=dev), v_rt, v_nrm, v_samples)
         torch.cuda.synchronize()
-        np.savez_compressed(
-            os.path.join(out_dir, f"ref_cuda_{name}.npz"), N=N, W=W, H=H, deg=deg, scale_mult=scale, seed=seed,
+        return dict(
+            N=N, W=W, H=H, deg=deg, scale_mult=scale, seed=seed,
             camera_ids=n(cam), gaussian_ids=n(gid), radii=n(radii), means2d=n(m2d), depths=n(dep), ray_transforms=n(rt),
             normals=n(nrm), samples=n(samples), dirs=n(dirs), sh_raw=n(sh_raw), colors=n(colors), tiles_per_gauss=n(tpg),
             isect_ids=n(isect_ids), flatten_ids=n(flatten_ids), offsets=n(offsets), render_colors=n(r_col), render_depths=n(r_dep),
@@ -75,7 +78,17 @@ def main():
             v_normals=n(v_nrm), v_densify=n(v_den), v_means2d=n(v_m2d), v_ray_transforms_run2=n(bw[1][1]), v_colors_run2=n(bw[1][2]),
             v_opacities_run2=n(bw[1][3]), v_densify_run2=n(bw[1][5]), v_samples=n(v_samples), v_coeffs=n(v_coeffs), v_dirs=n(v_dirs),
             v_means=n(pb[0]), v_quats=n(pb[1]), v_scales=n(pb[2]))
-        print(name, "nnz", nnz, "n_isects", int(flatten_ids.shape[0]), "alpha mean", float(r_alp.mean()))
+
+
+def main():
+    ref = load_ref()
+    dev = torch.device("cuda:0")
+    out_dir = os.path.join(ROOT, "gpurun_out", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, (N, W, H, deg, scale, seed) in CASES.items():
+        d = run_case(ref, dev, N, W, H, deg, scale, seed)
+        np.savez_compressed(os.path.join(out_dir, f"ref_cuda_{name}.npz"), **d)
+        print(name, "nnz", len(d["gaussian_ids"]), "n_isects", len(d["flatten_ids"]), "alpha mean", float(d["render_alphas"].mean()))
 
 
 if __name__ == "__main__":

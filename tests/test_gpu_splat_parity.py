@@ -138,7 +138,10 @@ def _raster_inputs(oracle, N, W, H, deg, scale, seed=0):
     return sc, V, K, fw
 
 
-@pytest.mark.parametrize("N,W,H,scale", [(3000, 160, 96, 6.0), (12000, 200, 120, 3.0), (600, 50, 37, 30.0)])
+C1 = (50_000, 256, 256, None)  # BASELINE.json configs[0]: 256x256, 50 k splats (scale_mult None = constant screen coverage)
+
+
+@pytest.mark.parametrize("N,W,H,scale", [(3000, 160, 96, 6.0), (12000, 200, 120, 3.0), (600, 50, 37, 30.0), C1])
 def test_raster_fwd(oracle, N, W, H, scale):
     from gssdf_b200 import ops
     dev = _dev()
@@ -156,7 +159,7 @@ def test_raster_fwd(oracle, N, W, H, scale):
     assert ref["render_alphas"].mean() > 0.2  # the scene actually covers the image
 
 
-@pytest.mark.parametrize("N,W,H,scale", [(3000, 160, 96, 6.0), (12000, 200, 120, 3.0), (600, 50, 37, 30.0)])
+@pytest.mark.parametrize("N,W,H,scale", [(3000, 160, 96, 6.0), (12000, 200, 120, 3.0), (600, 50, 37, 30.0), C1])
 def test_raster_bwd(oracle, N, W, H, scale):
     """All raster gradients vs the fp64 oracle, using the oracle's own saved forward state so that the
     comparison isolates the backward kernel."""
@@ -186,13 +189,14 @@ def test_raster_bwd(oracle, N, W, H, scale):
         assert_close_frac(_np(out[name]), refv, 1e-4, 1e-5 * scale_, 5e-4, name)
 
 
-def test_render_end_to_end_autograd(oracle):
+@pytest.mark.parametrize("N,W,H,deg,scale", [(3000, 160, 96, 3, 6.0), (50_000, 256, 256, 0, None)])
+def test_render_end_to_end_autograd(oracle, N, W, H, deg, scale):
     """rasterization_2dgs_sdf (the caller, neural_gaussian.cpp:129-271) forward + backward through the mirror
-    API vs the fp64 oracle chain: checks that the four ops compose and every leaf gradient arrives."""
+    API vs the fp64 oracle chain: checks that the four ops compose and every leaf gradient arrives. Second case: BASELINE c1
+    (256x256, 50 k splats, SH degree 0) end to end."""
     from gssdf_b200 import ops
     dev = _dev()
-    N, W, H, deg = 3000, 160, 96, 3
-    sc, V, K = small_scene(N, W, H, deg)
+    sc, V, K = small_scene(N, W, H, deg, scale_mult=scale)
     rn = S.randns(N)
     fw = oracle_forward(oracle, sc, V, K, W, H, deg, rn, "f64")
     p, r = fw["p"], fw["r"]
@@ -366,15 +370,43 @@ def test_kernels_vs_reference_cuda_goldens(oracle):
     (both sides are fast-math fp32), gradients within the reference's own run-to-run spread."""
     import glob
     import os
-
-    from ref_cuda_checks import rel_l2, scene_of
-
-    from gssdf_b200 import cabi, ops
     dev = _dev()
     files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cuda_*.npz")))
     assert files, "reference CUDA goldens missing"
     for f in files:
-        d = np.load(f)
+        _check_vs_reference_cuda(np.load(f), dev, os.path.basename(f))
+
+
+@pytest.mark.parametrize("name,N,W,H,deg,scale", [("c1", 50_000, 256, 256, 0, None), ("c2", 500_000, 1200, 680, 3, None)])
+def test_kernels_vs_reference_cuda_live_at_baseline_configs(name, N, W, H, deg, scale):
+    """parity at BASELINE configs, not toy sizes. The reference fork's own CUDA kernels (oracle/_ref/gsplat_ref.so,
+    compiled from /root/reference by oracle/build_ref.py; it travels to the GPU box) are run HERE on the c1 (256x256, 50 k splats, SH 0)
+    and c2 (1200x680, 500 k splats, SH 3) scenes and our kernels are compared with their outputs on the same tensors: realistic tile depth
+    (c2: thousands of splats per tile, every sort tier), ints bit-exact, floats / gradients as in the golden test."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "oracle", "_ref", "gsplat_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/gsplat_ref.so not built (python oracle/build_ref.py in the build container)")
+    dev = _dev()
+    spec = importlib.util.spec_from_file_location("gen_golden_ref", os.path.join(root, "oracle", "gen_golden_ref.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    d = gen.run_case(gen.load_ref(), dev, N, W, H, deg, scale, 0)
+    tiles = np.diff(np.concatenate([d["offsets"].reshape(-1), [len(d["flatten_ids"])]]))
+    print(f"{name}: nnz {len(d['gaussian_ids'])}, n_isects {len(d['flatten_ids'])}, max splats per tile {tiles.max()}, mean {tiles.mean():.0f}")
+    if name == "c2":
+        assert tiles.max() > 2048, "the c2 scene is meant to exercise the larger sort tiers"
+    _check_vs_reference_cuda(d, dev, name)
+
+
+def _check_vs_reference_cuda(d, dev, label):
+    from ref_cuda_checks import rel_l2, scene_of
+
+    from gssdf_b200 import cabi, ops
+    if True:
         sc, V, K, N, W, H, deg = scene_of(d)
         rn = S.randns(N)
         nnz = len(d["gaussian_ids"])
@@ -383,6 +415,10 @@ def test_kernels_vs_reference_cuda_goldens(oracle):
                                               _t(K, dev), W, H, S.NEAR, S.FAR, 0.0, True, False, randns=_t(rn, dev))
         cam, gid, radii, m2d, dep, rt, nrm, smp, sw = [_np(o) for o in out]
         assert np.array_equal(gid, d["gaussian_ids"])
+        # radii = ceil(3.33 sqrt(mean2d^2 - temp)): both sides promote the sqrt to double (Projection2DGSPacked.cu:131-132) but the
+        # fp32 cancellation inside depends on the fma contraction of the two builds -> report the count, bound it
+        mism = int((radii != d["radii"]).any(1).sum())
+        print(f"{label}: radii differ from the reference CUDA kernels on {mism} of {len(radii)} visible splats ({mism / max(len(radii), 1):.2e})")
         assert (np.abs(radii - d["radii"]) <= np.maximum(1, 0.1 * d["radii"])).all() and (radii == d["radii"]).mean() > 0.95
         for k, a in (("means2d", m2d), ("depths", dep), ("ray_transforms", rt), ("normals", nrm), ("samples", smp)):
             assert_close_frac(a, d[k], 2e-4, 2e-4, 0.0, "proj " + k)
