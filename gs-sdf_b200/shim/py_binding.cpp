@@ -141,8 +141,9 @@ void bind_tcnn(pybind11::module &m) {
     py::class_<LocalMapReplay, std::shared_ptr<LocalMapReplay>>(m, "LocalMapReplay")
         .def(py::init<int, int, int, int, int, double, double>())
         .def("get_sdf", &LocalMapReplay::get_sdf)
-        .def("get_gradient_analytic", &LocalMapReplay::get_gradient_analytic)
-        .def("regularization", &LocalMapReplay::regularization)
+        // these run the autograd engine from C++ (torch::autograd::grad): the GIL must not be held
+        .def("get_gradient_analytic", &LocalMapReplay::get_gradient_analytic, py::call_guard<py::gil_scoped_release>())
+        .def("regularization", &LocalMapReplay::regularization, py::call_guard<py::gil_scoped_release>())
         .def("set_decoder", &LocalMapReplay::set_decoder)
         .def("decoder_grad", &LocalMapReplay::decoder_grad)
         .def("encoder_params", [](LocalMapReplay &s) { return s.p_encoder_tcnn_->params_; })

@@ -49,7 +49,7 @@ const char *gssdf_last_error(void);
 /* "gssdf_b200 <ver> sm_100a" */
 const char *gssdf_version(void);
 /* Argument structs grow between revisions: a binding compiled against this header must see the same number from the library. */
-#define GSSDF_ABI_REVISION 11
+#define GSSDF_ABI_REVISION 12
 int32_t gssdf_abi_revision(void);
 
 /* Device-side counters shared by the stages of one render. Zeroed by gssdf_project2dgs_fwd. */
@@ -642,6 +642,103 @@ typedef struct gssdf_adam_args {
     void *mlp_packed;
 } gssdf_adam_args;
 int gssdf_adam_step(const gssdf_adam_args *a, gssdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a13 / f-2  SDF sample generation: the octree acceleration structure of kaolin_wisp_cpp's OctreeAS (NVIDIA kaolin SPC: byte octree in
+ *     breadth-first order + exclusive sum of the child counts) and NeuralSLAM::sample on top of it.
+ *     KW = submodules/kaolin_wisp_cpp, KA = KW/submodules/kaolin/kaolin/csrc.
+ *     The reference traces rays level by level: per level a decide kernel, a CUB scan, a device->host copy of the count, an allocation and a
+ *     subdivide kernel (KA/render/spc/raytrace_cuda.cu:489-600), then ~25 ATen ops assemble the samples. Here every ray walks the octree
+ *     depth-first with a register stack in the reference's front-to-back child order (VOXEL_ORDER), which yields the SAME nugget sequence
+ *     (ray-major, children expanded in place), in two passes (count -> scan -> write) with device-side counts and no host sync.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gssdf_octree {
+    int32_t level;          /* depth of the octree = level of the occupancy leaves (OctreeAS::max_level_) */
+    int32_t n_nodes;        /* bytes in `octree` (nodes of levels 0 .. level-1) */
+    const uint8_t *octree;  /* device [n_nodes]  child masks, root first (kaolin::points_to_octree) */
+    const int32_t *exsum;   /* device [n_nodes+1] exclusive sum of popcount(octree) (kaolin::scan_octrees): child with inclusive bit count c of
+                               node i is node exsum[i] + c of the point hierarchy */
+    float origin[3];        /* SubMap::pos_W_M_ : world -> [-1,1]^3 is (x - origin) * 2 * inv_size (SubMap::xyz_to_m1p1_pts, sub_map.cpp:82-90) */
+    float inv_size;         /* k_map_size_inv; 0: coordinates are already in [-1,1]^3 */
+    float size;             /* k_map_size (scale_from_m1p1 = x * 0.5 * size) */
+} gssdf_octree;
+
+/* HOST function (initialisation path, no device work): spc_ops::unbatched_points_to_octree(points, level, sorted = false) +
+   wisp_spc_ops::octree_to_spc (KW/kaolin_wisp_cpp/spc_ops/spc_ops.cpp:70-80, KA/ops/spc/spc_cuda.cu:43-170, scan_octrees.cu,
+   generate_points.cu): quantised int16 points -> unique -> Morton sort -> bottom-up byte octree, exsum, point hierarchy, pyramid.
+   All pointers are HOST memory. Call with octree == NULL to obtain the sizes only. Returns GSSDF_ENOMEM if a capacity is too small. */
+typedef struct gssdf_octree_build_args {
+    int64_t n;               /* quantised points */
+    const int16_t *qpoints;  /* host [n,3] in [0, 2^level) (spc_ops::quantize_points) */
+    int32_t level;           /* 1 .. 15 */
+    int64_t node_cap, point_cap;
+    uint8_t *octree;         /* host [node_cap] or NULL */
+    int32_t *exsum;          /* host [node_cap+1] or NULL */
+    int16_t *points;         /* host [point_cap,3] point hierarchy or NULL */
+    int32_t *pyramid;        /* host [2, level+2] (counts | offsets) or NULL */
+    int64_t n_nodes, n_points; /* OUT */
+} gssdf_octree_build_args;
+int gssdf_octree_build_host(gssdf_octree_build_args *a);
+
+/* OctreeAS::query (KW/kaolin_wisp_cpp/octree_as/octree_as.cpp:49-89 -> kaolin::query_cuda, KA/ops/spc/query_cuda.cu:26-49, identify
+   KA/spc_utils.cuh:28-61) at the leaf level, and SubMap::get_valid_mask (sub_map.cpp:76-80) = pidx > -1. coords are WORLD points. */
+typedef struct gssdf_octree_query_args {
+    gssdf_octree tree;
+    int64_t n;
+    const float *coords;     /* [n,3] */
+    const int32_t *n_live;   /* device int32 or NULL */
+    int32_t *pidx;           /* [n] index into the point hierarchy or -1, or NULL */
+    uint8_t *valid;          /* [n] pidx > -1, or NULL */
+} gssdf_octree_query_args;
+int gssdf_octree_query(const gssdf_octree_query_args *a, gssdf_stream_t stream);
+
+/* OctreeAS::raytrace(origins, dirs, level = max, with_exit = true) (octree_as.cpp:91-122 -> kaolin::raytrace_cuda): all (ray, leaf voxel)
+   intersections with entry / exit depth, ray-major, front to back. origins are in [-1,1]^3 already when tree.inv_size == 0, else world. */
+typedef struct gssdf_octree_raytrace_args {
+    gssdf_octree tree;
+    int64_t n_rays;
+    const float *origins, *dirs;  /* [n_rays,3] */
+    int64_t cap;                  /* capacity of the outputs (nuggets) */
+    int32_t *ridx, *pidx;         /* [cap] */
+    float *depth;                 /* [cap,2] entry, exit */
+    int32_t *n_nuggets;           /* device int32[2]: count, overflow flag */
+    void *workspace;              /* >= gssdf_octree_raytrace_workspace_bytes(n_rays) */
+    size_t workspace_bytes;
+} gssdf_octree_raytrace_args;
+size_t gssdf_octree_raytrace_workspace_bytes(int64_t n_rays);
+int gssdf_octree_raytrace(const gssdf_octree_raytrace_args *a, gssdf_stream_t stream);
+
+/* NeuralSLAM::sample (include/neural_mapping/neural_mapping.cpp:73-104): LocalMap::sample (include/neural_net/local_map.cpp:449-509 =
+   OctreeAS::raymarch("voxel", voxel_sample_num) [octree_as.cpp:124-190, wisp_spc_ops.cpp:85-100] + utils::sample_free_pts
+   [include/utils/utils.cpp:368-393] + keep ray_sdf > 0) + utils::sample_surface_pts (utils.cpp:336-366) + truncation + the rays' own end
+   points + SubMap::get_inrange_mask (sub_map.cpp:37-45), as ONE call: packed samples in the reference's order
+   [voxel samples | free samples | surface samples | ray end points], each block filtered in place (stable).
+   The random draws are INPUTS (the reference calls torch::rand_like / randn): rand_voxel[nugget_cap * voxel_sample_num],
+   rand_free[n_rays * n_free], randn_surface[n_rays * n_surface], indexed like the reference's tensors. */
+typedef struct gssdf_sdf_sample_rays_args {
+    gssdf_octree tree;
+    int64_t n_rays;
+    const float *origin, *direction;  /* [n_rays,3] world */
+    const float *depth;               /* [n_rays] measured depth along the ray */
+    const float *xyz;                 /* [n_rays,3] measured end point */
+    int32_t voxel_sample_num;         /* 1 in GS-SDF (neural_mapping.cpp:82) */
+    int32_t n_free, n_surface;        /* k_free_sample_num (0 = no free samples), k_surface_sample_num */
+    float sample_std, truncated_dis;
+    float xyz_min[3], xyz_max[3];     /* in-range box already shrunk by padding + 1e-6 (sub_map.cpp:39-42) */
+    const float *rand_voxel, *rand_free, *randn_surface;
+    int64_t nugget_cap;               /* capacity for ray / voxel intersections */
+    int64_t cap;                      /* capacity of the packed outputs */
+    float *out_xyz;                   /* [cap,3] */
+    float *out_ray_sdf;               /* [cap] */
+    float *out_direction;             /* [cap,3] or NULL */
+    float *out_depth;                 /* [cap] or NULL */
+    int64_t *out_ridx;                /* [cap] or NULL */
+    int32_t *counts;                  /* device int32[4]: n_samples, n_nuggets, overflow flag (samples | nuggets), reserved */
+    void *workspace;                  /* >= gssdf_sdf_sample_rays_workspace_bytes(...) */
+    size_t workspace_bytes;
+} gssdf_sdf_sample_rays_args;
+size_t gssdf_sdf_sample_rays_workspace_bytes(int64_t n_rays, int64_t nugget_cap, int32_t voxel_sample_num, int32_t n_free, int32_t n_surface);
+int gssdf_sdf_sample_rays(const gssdf_sdf_sample_rays_args *a, gssdf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libgssdf_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("splat_oracle.c", "splat_oracle_impl.inc", "sdf_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("splat_oracle.c", "splat_oracle_impl.inc", "sdf_oracle.c", "octree_oracle.c", "Makefile")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s))
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"])
@@ -407,3 +407,119 @@ def sdf_losses(sdf, y1, n, n_variants, gt_sdf=None, weights=None, bce_isigma=1.0
             v_s[1 + 2 * k] = c * g[:, k]
             v_s[2 + 2 * k] = -c * g[:, k]
     return loss, v_s.reshape(-1), v_y.reshape(-1)
+
+
+# ---- octree acceleration structure (oracle/octree_oracle.c; restates NVIDIA kaolin's SPC ops as used by kaolin_wisp_cpp) -------------
+class Octree:
+    """octree bytes (root first), exsum [n_nodes+1], point hierarchy [n_points,3] int16, pyramid [2, level+2]."""
+
+    def __init__(self, octree, exsum, points, pyramid, level):
+        self.octree, self.exsum, self.points, self.pyramid, self.level = octree, exsum, points, pyramid, level
+
+
+def octree_from_bytes(octree_bytes, level):
+    """scan_octrees + generate_points for a given byte octree (what wisp_spc_ops::octree_to_spc does)."""
+    ob = np.ascontiguousarray(octree_bytes, np.uint8)
+    n = len(ob)
+    exsum = np.zeros(n + 1, np.int32)
+    lib().oracle_scan_octree(C.c_int64(n), _p(ob), _p(exsum))
+    n_points = int(exsum[n]) + 1
+    pts = np.zeros((n_points, 3), np.int16)
+    lib().oracle_generate_points(C.c_int64(n), _p(ob), _p(exsum), C.c_int64(n_points), _p(pts))
+    # pyramid from the tree itself: level sizes by walking the breadth-first layout
+    counts, start, size = [1], 0, 1
+    for _ in range(level):
+        nxt = int(np.unpackbits(ob[start:start + size]).sum()) if size else 0
+        counts.append(nxt)
+        start, size = start + size, nxt
+    pyr = np.zeros((2, level + 2), np.int32)
+    pyr[0, :level + 1] = counts
+    pyr[1, 1:] = np.cumsum(pyr[0, :level + 1])
+    return Octree(ob, exsum, pts, pyr, level)
+
+
+def octree_from_points(qpts, level):
+    """spc_ops::unbatched_points_to_octree(points, level, sorted=False) + octree_to_spc: quantised int16 points [n,3] -> Octree."""
+    q = np.ascontiguousarray(qpts, np.int16)
+    mort = np.zeros(len(q), np.uint64)
+    lib().oracle_points_to_sorted_morton.restype = C.c_int64
+    nu = lib().oracle_points_to_sorted_morton(C.c_int64(len(q)), _p(q), _p(mort))
+    ob = np.zeros(max(nu * max(level, 1), 1), np.uint8)
+    pyr = np.zeros((2, level + 2), np.int32)
+    lib().oracle_morton_to_octree.restype = C.c_int64
+    nn = lib().oracle_morton_to_octree(C.c_int64(nu), _p(mort), C.c_int(level), _p(ob), _p(pyr))
+    t = octree_from_bytes(ob[:nn], level)
+    assert np.array_equal(t.pyramid, pyr), (t.pyramid, pyr)
+    return t
+
+
+def quantize_points(x, level):
+    """spc_ops::quantize_points (spc_ops.cpp:6-15): [-1,1] floats -> int16 in [0, 2^level - 1]."""
+    res = 2 ** level
+    return np.floor(np.clip(res * (np.asarray(x, np.float32) + np.float32(1.0)) / np.float32(2.0), 0, res - 1)).astype(np.int16)
+
+
+def octree_query(t, coords, level=None):
+    c = _f32(coords)
+    out = np.zeros(len(c), np.int32)
+    lib().oracle_octree_query(C.c_int64(len(c)), _p(c), C.c_int(t.level if level is None else level), _p(t.octree), _p(t.exsum), _p(out))
+    return out
+
+
+def octree_raytrace(t, origins, dirs, level=None, depth_mode=2, cap=None):
+    """kaolin raytrace_cuda: (ridx, pidx, depth[k, depth_mode]) in the reference's nugget order (ray-major, front to back)."""
+    o, d = _f32(origins), _f32(dirs)
+    n = len(o)
+    cap = int(cap or max(64 * n, 1024))
+    ridx, pidx, dep = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros((cap, 2), np.float32)
+    dflat = np.zeros(cap * max(depth_mode, 1), np.float32)
+    lib().oracle_octree_raytrace.restype = C.c_int64
+    k = lib().oracle_octree_raytrace(C.c_int64(n), _p(o), _p(d), C.c_int(t.level if level is None else level), _p(t.octree), _p(t.exsum),
+                                     _p(t.points), C.c_int(depth_mode), C.c_int64(cap), _p(ridx), _p(pidx), _p(dflat))
+    assert k <= cap, "raise cap"
+    dep = dflat[:k * depth_mode].reshape(k, depth_mode) if depth_mode else np.zeros((k, 0), np.float32)
+    return ridx[:k].copy(), pidx[:k].copy(), dep.copy()
+
+
+def sdf_sample_generation(t, origin, direction, depth, xyz, pos_W_M, map_size, rand_voxel, rand_free, randn_surface, n_free, n_surface,
+                          sample_std, truncated_dis, xyz_min, xyz_max, sample_free=True):
+    """NeuralSLAM::sample (include/neural_mapping/neural_mapping.cpp:73-104) = LocalMap::sample (include/neural_net/local_map.cpp:449-509:
+    OctreeAS::raymarch('voxel', 1) -> kaolin raytrace + sample_from_depth_intervals, free samples, keep ray_sdf > 0) + sample_surface_pts
+    (include/utils/utils.cpp:336-366) + truncation + the rays' own end points + in-range filter (sub_map.cpp:37-45), in float32 numpy with the
+    reference's operation order. Random draws are INPUTS: rand_voxel[k] ~ U(0,1) per nugget, rand_free[n, n_free], randn_surface[n, n_surface].
+    Returns dict(xyz, direction, depth, ray_sdf, ridx) and the raytrace (ridx, pidx, depth intervals)."""
+    f = np.float32
+    origin, direction, depth, xyz = _f32(origin), _f32(direction), _f32(depth).reshape(-1, 1), _f32(xyz)
+    n = len(origin)
+    pos = _f32(pos_W_M).reshape(1, 3)
+    o_n = ((origin - pos) * f(2) * f(1.0 / map_size)).astype(f)  # xyz_to_m1p1_pts (sub_map.cpp:82-90)
+    ridx, pidx, iv = octree_raytrace(t, o_n, direction, depth_mode=2)
+    k = len(ridx)
+    steps = ((np.zeros(k, f) + rand_voxel[:k].astype(f)) * f(1.0)).astype(f)  # num_samples = 1: (arange(1) + rand) * (1 / 1)
+    ds = (iv[:, 0] + (iv[:, 1] - iv[:, 0]) * steps).astype(f)                 # sample_from_depth_intervals (wisp_spc_ops.cpp:85-100)
+    smp = (o_n[ridx] + direction[ridx] * ds[:, None]).astype(f)               # addcmul
+    S = dict(xyz=(smp * f(0.5) * f(map_size) + pos).astype(f), direction=direction[ridx], ridx=ridx.astype(np.int64))
+    dsw = (ds * f(0.5) * f(map_size)).astype(f)[:, None]                      # scale_from_m1p1
+    S["ray_sdf"] = (depth[ridx] - dsw).astype(f)
+    S["depth"] = dsw
+    if sample_free:  # utils::sample_free_pts (utils.cpp:368-393)
+        st = ((np.arange(n_free, dtype=f)[None].repeat(n, 0) + rand_free.astype(f)) * f(1.0 / n_free)).astype(f)
+        rr = np.arange(n).repeat(n_free)
+        dfree = (depth[rr] * st.reshape(-1, 1)).astype(f)
+        F = dict(xyz=(origin[rr] + direction[rr] * dfree).astype(f), direction=direction[rr], ridx=rr.astype(np.int64),
+                 ray_sdf=(depth[rr] - dfree).astype(f), depth=dfree)
+        S = {kk: np.concatenate([S[kk], F[kk]]) for kk in S}
+    keep = S["ray_sdf"][:, 0] > 0
+    S = {kk: v[keep] for kk, v in S.items()}
+    rs = (randn_surface.astype(f) * f(sample_std)).astype(f)  # sample_surface_pts
+    rr = np.arange(n).repeat(n_surface)
+    U = dict(xyz=(xyz[rr] - direction[rr] * rs.reshape(-1, 1)).astype(f), direction=direction[rr], ridx=rr.astype(np.int64),
+             ray_sdf=rs.reshape(-1, 1), depth=depth[rr])
+    S = {kk: np.concatenate([S[kk], U[kk]]) for kk in S}
+    big = np.abs(S["ray_sdf"]) > f(truncated_dis)
+    S["ray_sdf"] = np.where(big, np.sign(S["ray_sdf"]) * f(truncated_dis), S["ray_sdf"]).astype(f)
+    R = dict(xyz=xyz, direction=direction, ridx=np.arange(n, dtype=np.int64), ray_sdf=np.zeros((n, 1), f), depth=depth)
+    S = {kk: np.concatenate([S[kk], R[kk]]) for kk in S}
+    lo, hi = _f32(xyz_min).reshape(1, 3) + f(1e-6), _f32(xyz_max).reshape(1, 3) - f(1e-6)
+    inr = ((S["xyz"] < hi) & (S["xyz"] > lo)).all(1)
+    return {kk: v[inr] for kk, v in S.items()}, (ridx, pidx, iv)
