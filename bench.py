@@ -190,7 +190,7 @@ def cpu_oracle_sdf(O, pts, table, mlp, hidden, n_hidden, gt=None, weights=None, 
     analytic: eikonal + align on the analytic gradient with its double backward (reference default), else the 6-offset eikonal."""
     n = len(pts)
     offs = np.array([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float32) * np.float32(delta)
-    x01 = (((pts[None] + offs[:, None]).reshape(-1, 3)) / 14.0 + 0.5).astype(np.float32)
+    x01 = (((pts[None] + offs[:, None]).reshape(-1, 3)).astype(np.float32) * np.float32(1.0 / 14.0) + np.float32(0.5)).astype(np.float32)
     sdf, y1, _ = O.sdf_fwd(x01, table, mlp, hidden, n_hidden)
     if not analytic:
         loss, vs, vy = O.sdf_losses(sdf, y1, n, 7, gt, weights, 10.0, 1.0 if gt is not None else 0.0, 0.1, 1e-3, delta)
@@ -269,16 +269,26 @@ def run_cpu_c1(budget_s=20.0, max_steps=20, warmup=3):
     dims = [32] + [hidden] * (1 + n_hidden) + [2]
     mlp = np.concatenate([np.concatenate([rng.uniform(-1, 1, o * k) / np.sqrt(k), rng.uniform(-1, 1, o) / np.sqrt(k)])
                           for k, o in zip(dims[:-1], dims[1:])]).astype(np.float32)
-    n_ray = 32768
-    ray = (rng.uniform(-1, 1, (n_ray, 3)) * (S.BOX + 0.3)).astype(np.float32)
-    ray_gt = np.clip((S.BOX - np.abs(ray)).min(1), -0.3, 0.3).astype(np.float32)
+    # sample generation like the GPU arm: occupancy octree of the scene (level 8 over 14 m), 3277 depth rays per step through the
+    # kaolin-style level-by-level ray trace + NeuralSLAM::sample (oracle/octree_oracle.c, oracle.sdf_sample_generation)
+    n_rays, level, leaf = 3277, 8, 14.0 / 256
+    tree = O.octree_from_points(O.quantize_points(sc["means"] * np.float32(2.0 / 14.0), level), level)
+    ro = ((rng.uniform(0, 1, (1 << 16, 3)) - 0.5) * S.BOX).astype(np.float32)
+    rend = sc["means"][rng.integers(0, N, 1 << 16)]
+    rdep = np.linalg.norm(rend - ro, axis=1).astype(np.float32)
+    rdir = ((rend - ro) / rdep[:, None]).astype(np.float32)
     params = [sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["sh"], table, mlp]
     adam = CpuAdam(params, [1.6e-4, 1e-3, 5e-3, 5e-2, 2.5e-3, 5e-3, 5e-3])
     adam.grads = [np.full_like(x, 1e-9) for x in params]
-    ts, nnz, I = [], 0, 0
+    ts, nnz, I, n_ray = [], 0, 0, 0
     t_all = time.perf_counter()
     for i in range(warmup + max_steps):
         t0 = time.perf_counter()
+        k = (i * n_rays) % ((1 << 16) - n_rays)
+        smp, _ = O.sdf_sample_generation(tree, ro[k:k + n_rays], rdir[k:k + n_rays], rdep[k:k + n_rays], rend[k:k + n_rays], np.zeros(3), 14.0,
+                                         rng.uniform(0, 1, 64 * n_rays), rng.uniform(0, 1, (n_rays, 3)), rng.standard_normal((n_rays, 3)), 3, 3,
+                                         0.1, 3 * leaf, [-7.0] * 3, [7.0] * 3)
+        ray, ray_gt, n_ray = smp["xyz"], smp["ray_sdf"][:, 0].copy(), len(smp["xyz"])
         # numerical (6-offset) eikonal like the GPU arm at c1: the fused analytic kernel covers the 3x64 decoder only
         _, nnz, I = cpu_full_step(O, S, sc, V, K, W, H, deg, rn, gt, table, mlp, hidden, n_hidden, ray, ray_gt, adam, analytic=False)
         if i >= warmup:
@@ -287,7 +297,7 @@ def run_cpu_c1(budget_s=20.0, max_steps=20, warmup=3):
             break
     med = float(np.median(ts))
     return dict(value=1.0 / med, unit="step/s", cores=cores, kind="port", config="c1",
-                sample=f"config c1 run for real, nothing scaled: {W}x{H}, {N} splats, SH deg {deg}, MLP 2x32, {n_ray} ray samples + {nnz} "
+                sample=f"config c1 run for real, nothing scaled: {W}x{H}, {N} splats, SH deg {deg}, MLP 2x32, octree sample generation of {n_rays} rays -> {n_ray} ray samples + {nnz} "
                        f"splat samples x7 SDF evaluations, numerical eikonal (as the GPU arm at c1), L1 + DSSIM, Adam over {sum(x.size for x in params)} "
                        f"parameters; median of {len(ts)} steps after {warmup} warm-ups = {med * 1e3:.0f} ms (nnz={nnz}, n_isects={I}); "
                        f"C + OpenMP fp32 oracle port, numpy/scipy glue")
@@ -432,18 +442,40 @@ def main():
                t(sc_np["sh"][:, 1:].copy()) if deg > 0 else None, table, torch.cat(chunks))
         return T, sc_act, (W, H, N, deg)
 
-    n_ray = 32768  # config/base.yaml:23 batch_pt_num
+    # SDF ray samples (rows a13 / f-2): k_batch_num depth rays per step go through the octree ray-march + free / surface sampling of
+    # NeuralSLAM::sample; the reference adapts k_batch_num so that the batch holds ~k_batch_pt_num = 32768 points (neural_mapping.cpp:324-330)
+    # -- ~10 points per ray here. n_ray = capacity of the sample batch the SDF stage is sized for.
+    N_RAYS, n_ray, OCT_LEVEL, LEAF = 3277, 49152, 8, 14.0 / 256
+    from gssdf_b200 import octree as OT
+    box = torch.tensor(S.BOX, device=dev, dtype=torch.float32)
+
+    class Sampling:
+        """occupancy octree of the scene (leaf 5.5 cm, SubMap of 14 m like the SDF grid) + a device-resident pack of depth rays (sensor
+        positions inside the room looking at wall points: the stand-in for the dataset's train_depth_pack_) + the RaySampler"""
+
+        def __init__(self, T_, means, seed):
+            self.tree = OT.OctreeAS.from_quantized_points(OT.quantize_points(means * (2.0 / 14.0), OCT_LEVEL), OCT_LEVEL, dev,
+                                                          origin=(0.0, 0.0, 0.0), map_size=14.0)
+            g_ = torch.Generator(dev).manual_seed(seed)
+            self.n_pack = 1 << 18
+            self.o = ((torch.rand(self.n_pack, 3, device=dev, generator=g_) - 0.5) * box).contiguous()
+            self.end = means[torch.randint(0, means.shape[0], (self.n_pack,), device=dev, generator=g_)].contiguous()
+            self.depth = (self.end - self.o).norm(dim=1).contiguous()
+            self.dir = ((self.end - self.o) / self.depth[:, None]).contiguous()
+            self.rs = OT.RaySampler(self.tree, N_RAYS, dev, 1, 3, 3, sample_std=T_.delta, truncated_dis=3 * LEAF, xyz_min=(-7.0,) * 3,
+                                    xyz_max=(7.0,) * 3, nugget_cap=16 * N_RAYS, cap=n_ray)
+            T_.set_octree(self.tree)
+
+        def draw(self, i):
+            k = (i * N_RAYS) % (self.n_pack - N_RAYS)  # the reference indexes torch::rand rays of the pack (neural_mapping.cpp:145-156)
+            self.rs.draw()
+            self.rs.sample(self.o[k:k + N_RAYS], self.dir[k:k + N_RAYS], self.depth[k:k + N_RAYS], self.end[k:k + N_RAYS])
+            return self.rs.xyz, self.rs.ray_sdf, self.rs.counts
+
     T, sc_act, _ = build_trainer(args.workload, args.eikonal)
     R = T.R
     K_sh = (deg + 1) ** 2
-    box = torch.tensor(S.BOX, device=dev, dtype=torch.float32)
-
-    def ray_batch(seed):  # points within +-0.3 m of the box walls, ground-truth SDF = distance to the nearest wall (inside positive)
-        g_ = torch.Generator(dev).manual_seed(seed)
-        xyz = (torch.rand(n_ray, 3, device=dev, generator=g_) * 2 - 1) * (box + 0.3)
-        return xyz, (box - xyz.abs()).min(dim=1).values.clamp(-0.3, 0.3).contiguous()
-
-    ray_xyz, ray_gt = ray_batch(50 + rank)  # each rank draws its own share of the ray batch
+    SP = Sampling(T, sc_act["means"], 50 + rank)  # each rank draws its own rays
     n_cams = 8
     # image-batch data parallelism = "per-frame render on each rank" (north_star): rank r renders ITS OWN camera poses, so the ranks'
     # per-step work differs (load imbalance is part of the measurement); --same-cameras restores identical work on every rank
@@ -497,7 +529,9 @@ def main():
     def step_resident(i):
         V, Kc = dev_cams[i % n_cams]
         randn_buf.normal_()  # the reference draws randns on the device every render (Projection.cpp:728)
-        loss, _sdf_loss = T.train_step(V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook, before_render=pre)
+        ray_xyz, ray_gt, ray_cnt = SP.draw(i)
+        loss, _sdf_loss = T.train_step(V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook, before_render=pre,
+                                       ray_n_live=ray_cnt)
         after_step()
         return loss
 
@@ -527,7 +561,9 @@ def main():
         cur = torch.cuda.current_stream()
         cur.wait_event(sl["ready"])
         randn_buf.normal_()
-        loss, _sdf_loss = T.train_step(sl["V"], sl["K"], sl["gt"], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook, before_render=pre)
+        ray_xyz, ray_gt, ray_cnt = SP.draw(i)
+        loss, _sdf_loss = T.train_step(sl["V"], sl["K"], sl["gt"], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook, before_render=pre,
+                                       ray_n_live=ray_cnt)
         sl["free"].record(cur)
         after_step()
         loss_host.copy_(loss, non_blocking=True)
@@ -585,6 +621,9 @@ def main():
     value = world * 1e3 / ms_step  # images (train steps of one camera) per second over the whole job
     last_loss = float(T.R.loss[0])
     cnt_end = R.read_counts()
+    sdf_counts = {"ray_samples": int(SP.rs.counts[0]), "ray_voxel_hits": int(SP.rs.counts[1]), "sample_overflow": int(SP.rs.counts[2]),
+                  "rays": N_RAYS, "splat_samples_gated": int(T.n_gate[0]), "octree_nodes": SP.tree.n_nodes, "octree_level": OCT_LEVEL}
+    assert not sdf_counts["sample_overflow"], sdf_counts
 
     # end-to-end through the public API with host buffers
     for sl in slots:
@@ -638,10 +677,13 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": cfg, "mrays_per_s": value * P / 1e6, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "step/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
-                "gpu_launches": args.steps * (render.GsSdfStep.KERNELS_PER_STEP - 2 + 4 + 2),
-                "step_contents": "[A] SDF on 32768 ray samples, [B] render, [C] gated GS<->SDF coupling, [D] L1 + DSSIM + depth L1 + "
-                                 "normal-consistency + isotropic -> backward, Adam over all parameter groups (f-3 first half); not in the "
-                                 "step: octree ray-march sample generation (a13; fixed ray batch), densification callbacks",
+                # ours only (torch's RNG fills not counted): 30 of GsSdfStep - table cast - weight pack (now inside the Adam call) + normal-consistency
+                # + isotropic + Adam + weight pack + 6 sample-generation kernels + octree query
+                "gpu_launches": args.steps * (render.GsSdfStep.KERNELS_PER_STEP - 2 + 2 + 2 + 7),
+                "step_contents": "[A] octree ray-march sample generation of 3277 depth rays (~32 k points) + SDF stage on them, [B] render, [C] "
+                                 "GS<->SDF coupling gated by visibility and octree validity, [D] L1 + DSSIM + depth L1 + normal-consistency + "
+                                 "isotropic -> backward, Adam over all parameter groups (f-3 first half); not in the step: the every-100-"
+                                 "iterations densification callback (NeuralGS::train_callback)",
                 "roofline": {"kernel": "raster2dgs_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / pk["hbm_gbs"], "traffic": prof.get("dram_bytes_per_launch"), "peak_source": pk_kind,
                              "algorithmic_bytes": alg_bwd, "kernel_ms": t_bwd * 1e3,
@@ -653,7 +695,7 @@ def main():
                                      "traffic is below the algorithmic bytes): see issue_slots and profiles/",
                              "raster_fwd": {"achieved": alg_fwd / t_fwd / 1e9, "frac": alg_fwd / t_fwd / 1e9 / pk["hbm_gbs"],
                                             "kernel_ms": t_fwd * 1e3, "algorithmic_bytes": alg_fwd}},
-                "counts": cnt, "counts_end": cnt_end, "loss_end": last_loss, "loss_finite": bool(np.isfinite(last_loss)),
+                "counts": cnt, "counts_end": cnt_end, "sdf_counts": sdf_counts, "loss_end": last_loss, "loss_finite": bool(np.isfinite(last_loss)),
                 "stage_ms": stage_ms}
         if world == 1 and not args.no_stock_cuda:
             try:
@@ -667,6 +709,7 @@ def main():
                 torch.cuda.empty_cache()
                 W1, H1, N1, deg1, _ = WORKLOADS["c1"]
                 T1, act1, _ = build_trainer("c1", args.eikonal)
+                SP1 = Sampling(T1, act1["means"], 50)
                 cams1 = [S.camera(i, W1, H1) for i in range(n_cams)]
                 gts1 = gt_images(T1, act1, cams1, W1, H1)
                 dc1 = [(t(V_[None]), t(K_[None])) for V_, K_ in cams1]
@@ -674,7 +717,8 @@ def main():
 
                 def c1_step(i):
                     rb1.normal_()
-                    T1.train_step(dc1[i % n_cams][0], dc1[i % n_cams][1], gts1[i % n_cams], ray_xyz, ray_gt, rb1)
+                    rx, rg, rc = SP1.draw(i)
+                    T1.train_step(dc1[i % n_cams][0], dc1[i % n_cams][1], gts1[i % n_cams], rx, rg, rb1, ray_n_live=rc)
                     T1.adam_all()
                 for i in range(5):
                     c1_step(i)
@@ -700,7 +744,7 @@ def main():
 def run_stock_cuda(torch, S, sc_act, cams, gts, W, H, deg, dev, ours_stage_ms, steps=5):
     """The reference fork's own kernels (projection -> SH -> tile_encode incl. its CUB sort -> raster fwd -> raster bwd -> SH bwd ->
     projection bwd, host glue of oracle/ref_driver.cpp incl. the reference's .item() syncs) on the SAME activated tensors, CUDA events per
-    stage, mean of `steps` runs after one warm-up. Test infrastructure: imported here and nowhere in the product path."""
+    stage, median of `steps` runs after two warm-ups. Test infrastructure: imported here and nowhere in the product path."""
     import importlib
     ref_dir = os.path.join(ROOT, "oracle", "_ref")
     if not os.path.exists(os.path.join(ref_dir, "gsplat_ref.so")):
@@ -715,7 +759,8 @@ def run_stock_cuda(torch, S, sc_act, cams, gts, W, H, deg, dev, ours_stage_ms, s
     names = ["projection_fwd", "sh_fwd", "tile_encode", "raster_fwd", "raster_bwd", "sh_bwd", "projection_bwd"]
     acc = {k: [] for k in names}
     info = {}
-    for it in range(steps + 1):
+    warm = 2  # the first calls grow torch's caching allocator (cudaMalloc inside the stages)
+    for it in range(steps + warm):
         V, Kc = cams[it % len(cams)]
         Vt, Kt = t(V[None]), t(Kc[None])
         gt = gts[it % len(gts)]
@@ -753,11 +798,11 @@ def run_stock_cuda(torch, S, sc_act, cams, gts, W, H, deg, dev, ours_stage_ms, s
                                             v_nrm, torch.zeros_like(samples))
         ev[7].record()
         torch.cuda.synchronize()
-        if it > 0:
+        if it >= warm:
             for k, a, b in zip(names, ev[:-1], ev[1:]):
                 acc[k].append(a.elapsed_time(b))
         info = {"nnz": int(gid.shape[0]), "n_isects": int(flatten_ids.shape[0])}
-    st = {k: float(np.mean(v)) for k, v in acc.items()}
+    st = {k: float(np.median(v)) for k, v in acc.items()}  # median: a stray cudaMalloc in one run must not colour the stage table
     total = float(sum(st.values()))
     out = {"kind": "reference fork CUDA kernels (gsplat 2DGS path of GS-SDF) compiled for sm_100a with the reference's flags (-O3 "
                    "--use_fast_math), same GPU, same tensors", "stage_ms": st, "splat_chain_ms": total, "steps": steps, "counts": info,

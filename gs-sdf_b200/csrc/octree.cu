@@ -14,7 +14,7 @@
 // place is the depth-first leaf order). Two traversals (count, write) around one scan give packed outputs without any host sync; the
 // sample assembly is one candidate kernel + one scan + one stable compaction. The octree (a few hundred KB) is L1/L2 resident.
 // All float arithmetic that decides something (ray_aabb) follows the reference operation by operation (explicit fmaf where it has fmaf,
-// separately rounded mul / add where ATen runs separate kernels) so that hits, order and depths equal the CPU oracle's bit for bit.
+// separately rounded mul / add where ATen runs separate kernels) so that hits, order and depths are reproducible bit for bit by a CPU restatement of the reference.
 #include <algorithm>
 #include <vector>
 
@@ -234,6 +234,34 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int32_t *in, int32_t *
         *total_out = (int32_t)min((int64_t)s_carry, cap);
         if (s_carry > cap) *overflow = 1;
     }
+}
+
+// ---- gate compaction of the coupling site (neural_mapping.cpp:428-437) ---------------------------------------------------------------
+__global__ void __launch_bounds__(256) gate_flag_kernel(const gssdf_sdf_gate_compact_args a, int32_t *flags) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t nl = a.n_live ? min((int64_t)*a.n_live, a.n) : a.n;
+    if (i >= nl) return;
+    flags[i] = ((!a.visibilities || __ldg(a.visibilities + i) > a.visible_thr) && (!a.valid_mask || a.valid_mask[i] != 0)) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) gate_gather_kernel(const gssdf_sdf_gate_compact_args a, const int32_t *flags, const int32_t *pos) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t nl = a.n_live ? min((int64_t)*a.n_live, a.n) : a.n;
+    if (i >= nl || !flags[i]) return;
+    const int64_t j = pos[i];
+    a.index[j] = (int32_t)i;
+    a.x_out[3 * j] = __ldg(a.x + 3 * i); a.x_out[3 * j + 1] = __ldg(a.x + 3 * i + 1); a.x_out[3 * j + 2] = __ldg(a.x + 3 * i + 2);
+    if (a.w_out) a.w_out[j] = (a.weights ? __ldg(a.weights + i) : 1.f) * (a.visibilities ? __ldg(a.visibilities + i) : 1.f);
+}
+__global__ void __launch_bounds__(256) scatter_rows3_kernel(const gssdf_scatter_rows3_args a) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= (int64_t)*a.n_gate) return;
+    const int64_t r = a.index[j];
+    a.dst[3 * r] = a.src[3 * j]; a.dst[3 * r + 1] = a.src[3 * j + 1]; a.dst[3 * r + 2] = a.src[3 * j + 2];
+}
+__global__ void __launch_bounds__(256) zero_rows3_kernel(float *dst, int64_t n, const int32_t *n_live) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t nl = n_live ? min((int64_t)*n_live, n) : n;
+    if (e < 3 * nl) dst[e] = 0.f;
 }
 
 // ---- sample assembly -------------------------------------------------------------------------------------------------------------
@@ -527,5 +555,40 @@ extern "C" int gssdf_sdf_sample_rays(const gssdf_sdf_sample_rays_args *a, gssdf_
     GSSDF_LAUNCH_OK("scan_kernel");
     sample_write_kernel<<<cdiv(m_cap, 256), 256, 0, st>>>(*a, nug_ridx, nug_depth, flags, pos, m_cap);
     GSSDF_LAUNCH_OK("sample_write_kernel");
+    return GSSDF_OK;
+}
+
+extern "C" size_t gssdf_sdf_gate_compact_workspace_bytes(int64_t n) { return 2 * align_up((size_t)std::max<int64_t>(n, 1) * 4, 256); }
+
+extern "C" int gssdf_sdf_gate_compact(const gssdf_sdf_gate_compact_args *a, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(a != nullptr && a->n_gate != nullptr, GSSDF_EINVAL, "sdf_gate_compact: null args / n_gate");
+    GSSDF_REQUIRE(a->n >= 0 && a->n < ((int64_t)1 << 31), GSSDF_EINVAL, "sdf_gate_compact: bad n");
+    cudaStream_t st = (cudaStream_t)stream;
+    GSSDF_CUDA_OK(cudaMemsetAsync(a->n_gate, 0, sizeof(int32_t), st));
+    if (a->n == 0) return GSSDF_OK;
+    GSSDF_REQUIRE(a->x && a->index && a->x_out, GSSDF_EINVAL, "sdf_gate_compact: null pointer");
+    GSSDF_REQUIRE(a->workspace && a->workspace_bytes >= gssdf_sdf_gate_compact_workspace_bytes(a->n), GSSDF_ENOMEM, "sdf_gate_compact: workspace too small");
+    int32_t *flags = reinterpret_cast<int32_t *>(a->workspace);
+    int32_t *pos = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(a->workspace) + align_up((size_t)a->n * 4, 256));
+    int32_t *scratch_ovf = pos + a->n - 1;  // never read: the count cannot exceed n
+    gate_flag_kernel<<<cdiv(a->n, 256), 256, 0, st>>>(*a, flags);
+    GSSDF_LAUNCH_OK("gate_flag_kernel");
+    scan_kernel<<<1, 1024, 0, st>>>(flags, pos, a->n, a->n_live, a->n + 1, a->n_gate, scratch_ovf);
+    GSSDF_LAUNCH_OK("scan_kernel");
+    gate_gather_kernel<<<cdiv(a->n, 256), 256, 0, st>>>(*a, flags, pos);
+    GSSDF_LAUNCH_OK("gate_gather_kernel");
+    return GSSDF_OK;
+}
+
+extern "C" int gssdf_scatter_rows3(const gssdf_scatter_rows3_args *a, gssdf_stream_t stream) {
+    GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "scatter_rows3: null args");
+    GSSDF_REQUIRE(a->n >= 0, GSSDF_EINVAL, "scatter_rows3: negative n");
+    if (a->n == 0) return GSSDF_OK;
+    GSSDF_REQUIRE(a->index && a->n_gate && a->src && a->dst, GSSDF_EINVAL, "scatter_rows3: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    zero_rows3_kernel<<<cdiv(3 * a->n, 256), 256, 0, st>>>(a->dst, a->n, a->n_live);
+    GSSDF_LAUNCH_OK("zero_rows3_kernel");
+    scatter_rows3_kernel<<<cdiv(a->n, 256), 256, 0, st>>>(*a);
+    GSSDF_LAUNCH_OK("scatter_rows3_kernel");
     return GSSDF_OK;
 }

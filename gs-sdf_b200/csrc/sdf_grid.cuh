@@ -206,7 +206,10 @@ __device__ __forceinline__ void load_x(const gssdf_sdf_net &net, const float *__
     for (int d = 0; d < 3; ++d) {
         float v = __ldg(x + 3 * i + d);
         if (var > 0 && (var - 1) / 2 == d) v += ((var - 1) & 1) ? -delta : delta;
-        out[d] = net.inv_size != 0.f ? __fmaf_rn(v - net.origin[d], net.inv_size, 0.5f) : v;
+        // SubMap::xyz_to_zp1_pts = 0.5f * ((xyz - pos) * 2 * k_map_size_inv) + 0.5f as separate ATen ops (sub_map.cpp:82-97): the
+        // factors 2 and 0.5 are exact, so the value is fl(fl((x - pos) * inv) + 0.5) -- two roundings, NOT one fused multiply-add. The
+        // finest grid level magnifies a 1-ulp difference of the normalised coordinate to ~6 % of a cell, so this must match bit for bit.
+        out[d] = net.inv_size != 0.f ? __fadd_rn(__fmul_rn(__fsub_rn(v, net.origin[d]), net.inv_size), 0.5f) : v;
     }
 }
 

@@ -316,3 +316,16 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, groups, step, beta1=0.9, beta2
     if net is not None:
         a.net = _lib.C.cast(_lib.C.pointer(net), _lib.C.c_void_p)
     check(lib().gssdf_adam_step(_lib.C.byref(a), _stream()))
+
+
+def sdf_gate_compact(n, x, index, x_out, n_gate, ws, visibilities=None, visible_thr=0.0, valid_mask=None, weights=None, w_out=None, n_live=None):
+    """Stable compaction of the samples passing `vis > thr & valid` (the reference's index_select, neural_mapping.cpp:433-437)."""
+    w = ws.get(lib().gssdf_sdf_gate_compact_workspace_bytes(_lib.C.c_int64(n)))
+    a = make_args("gssdf_sdf_gate_compact_args", n=n, n_live=n_live, visibilities=visibilities, visible_thr=visible_thr, valid_mask=valid_mask,
+                  x=x, weights=weights, index=index, x_out=x_out, w_out=w_out, n_gate=n_gate, workspace=w, workspace_bytes=w.numel())
+    check(lib().gssdf_sdf_gate_compact(_lib.C.byref(a), _stream()))
+
+
+def scatter_rows3(n, index, n_gate, src, dst, n_live=None):
+    a = make_args("gssdf_scatter_rows3_args", n=n, n_live=n_live, index=index, n_gate=n_gate, src=src, dst=dst)
+    check(lib().gssdf_scatter_rows3(_lib.C.byref(a), _stream()))

@@ -193,6 +193,7 @@ class GsSdfStep:
         # k_render_normal_weight / k_isotropic_weight (config/base.yaml:43-46: 0.01 / 0.05; the normal term from iteration 3000 on)
         self.normal_w, self.iso_w = normal_weight, isotropic_weight
         self.valid_mask = None       # [cap] uint8 octree validity of the splat samples (LocalMap::get_valid_mask) or None
+        self.octree = None
         self.keep_shadows = False    # True: the caller (GsSdfTrainer's Adam) keeps table_half / mlp_packed current and zeroes the gradients
         f32 = dict(dtype=torch.float32, device=device)
         probe = cabi.sdf_net(torch.zeros(1, **f32), torch.zeros(1, **f32), **self.cfg)
@@ -221,6 +222,11 @@ class GsSdfStep:
         self.v_samples = e(cap, 3)
         self.sdf_loss = torch.zeros(1, **f32)
         self.n_gate = torch.zeros(1, dtype=torch.int32, device=device)
+        # compact copies of the gated splat samples (the reference's index_select, neural_mapping.cpp:433-437)
+        self.compact_gate = True
+        self.gate_idx = torch.empty(cap, dtype=torch.int32, device=device)
+        self.gate_x, self.gate_w, self.gate_vx = e(cap, 3), e(cap), e(cap, 3)
+        self.gate_ws = cabi.Workspace(device)
 
     KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 9  # + 2 DSSIM kernels + table cast + decoder weight image + gate count + 2 x (7-variant forward, fused train) (mlp_mode 1)
 
@@ -235,8 +241,14 @@ class GsSdfStep:
     def refresh_table(self, table_f32):
         cabi.sdf_table_to_half(table_f32, self.table_half)
 
+    def set_octree(self, octree):
+        """OctreeAS of the occupancy map: stage [C] then also gates the splat samples by LocalMap::get_valid_mask (neural_mapping.cpp:432)."""
+        self.octree = octree
+        self.valid_mask = torch.zeros(self.R.cap, dtype=torch.uint8, device=self.dev) if octree is not None else None
+
     def step(self, scene, table_f32, mlp, viewmats, Ks, gt_image, ray_xyz, ray_gt_sdf, randns=None, on_sdf_grads_ready=None,
-             before_render=None):
+             before_render=None, ray_n_live=None):
+        """ray_n_live: device int32 (e.g. RaySampler.counts): only the first *ray_n_live rows of ray_xyz / ray_gt_sdf are samples."""
         """Hooks for a data-parallel caller (both optional):
         on_sdf_grads_ready(table_and_mlp_grad): the hash-table / decoder gradients are final (after [C]) -> start reducing them while the
             render backward [D] is still running.
@@ -261,18 +273,19 @@ class GsSdfStep:
             if self.eik_mode == 1:  # reference default: forward-only pass over the 7 variants (numerical gradient of the align loss),
                                     # then forward + losses + backward + double backward on the base points only
                 if self.align_w > 0:
-                    cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, None, None, n_variants=7, delta=self.delta, skip_base_variant=True)
+                    cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, None, None, n_variants=7, delta=self.delta, skip_base_variant=True, n_live=ray_n_live)
                 cabi.sdf_train(net, ray_xyz, 1, self.delta, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.sdf_loss,
                                self.table_grad, self.mlp_grad, None, eikonal_mode=1, align_weight=self.align_w,
-                               sdf_variants=self.ray_sdf if self.align_w > 0 else None)
+                               sdf_variants=self.ray_sdf if self.align_w > 0 else None, n_live=ray_n_live)
             else:
                 cabi.sdf_train(net, ray_xyz, 7, self.delta, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.sdf_loss,
-                               self.table_grad, self.mlp_grad, None)
+                               self.table_grad, self.mlp_grad, None, n_live=ray_n_live)
         else:
-            cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, self.ray_y1, None, n_variants=7, delta=self.delta)
+            cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, self.ray_y1, None, n_variants=7, delta=self.delta, n_live=ray_n_live)
             cabi.sdf_loss(n_ray, 7, self.ray_sdf, self.ray_y1, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.delta, self.sdf_loss,
-                          self.ray_vs, self.ray_vy)
-            cabi.sdf_bwd(net, ray_xyz, self.ray_vs, self.ray_vy, self.table_grad, self.mlp_grad, None, n_variants=7, delta=self.delta)
+                          self.ray_vs, self.ray_vy, n_live=ray_n_live)
+            cabi.sdf_bwd(net, ray_xyz, self.ray_vs, self.ray_vy, self.table_grad, self.mlp_grad, None, n_variants=7, delta=self.delta,
+                         n_live=ray_n_live)
         R._mark("sdf_ray_samples[A]")
         if before_render is not None:
             before_render()
@@ -284,6 +297,31 @@ class GsSdfStep:
         # [C] coupling on the stochastic splat samples (rows < nnz, counted on the device)
         samples, n_live = R.p["samples"], R.counts  # counts[0] == nnz
         # the reference's sample gate: vis > visible_thr (& octree validity), counted on the device (no nonzero() / .item() sync)
+        if getattr(self, "octree", None) is not None:
+            self.octree.valid_mask(samples, self.valid_mask, n_live=n_live)
+        if self.compact_gate and self.mlp_mode == 1:
+            # like the reference: select the gated samples first, evaluate the SDF network on them only, scatter dL/d sample back
+            cabi.sdf_gate_compact(cap, samples, self.gate_idx, self.gate_x, self.n_gate, self.gate_ws, visibilities=R.r["visibilities"],
+                                  visible_thr=self.vis_thr, valid_mask=self.valid_mask, weights=R.p["sample_weights"], w_out=self.gate_w,
+                                  n_live=n_live)
+            if self.eik_mode == 1:
+                if self.align_w > 0:
+                    cabi.sdf_fwd(net, self.gate_x, self.gs_sdf, None, None, n_variants=7, delta=self.delta, n_live=self.n_gate,
+                                 skip_base_variant=True)
+                cabi.sdf_train(net, self.gate_x, 1, self.delta, None, self.gate_w, self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
+                               self.sdf_loss, self.table_grad, self.mlp_grad, self.gate_vx, n_live=self.n_gate, eikonal_mode=1,
+                               align_weight=self.align_w, sdf_variants=self.gs_sdf if self.align_w > 0 else None)
+            else:
+                cabi.sdf_train(net, self.gate_x, 7, self.delta, None, self.gate_w, self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
+                               self.sdf_loss, self.table_grad, self.mlp_grad, self.gate_vx, n_live=self.n_gate)
+            cabi.scatter_rows3(cap, self.gate_idx, self.n_gate, self.gate_vx, self.v_samples, n_live=n_live)
+            R._mark("sdf_splat_samples[C]")
+            if on_sdf_grads_ready is not None:
+                on_sdf_grads_ready(self.flat_grad[self.table_grad.storage_offset():])
+            loss = R.backward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, gt_image, randns,
+                              v_samples=self.v_samples, zero_grads=False, raw=scene.get("raw"), w_rgb=self.rgb_w, w_depth=self.depth_w,
+                              w_dssim=self.dssim_w, w_normal=self.normal_w, w_isotropic=self.iso_w)
+            return loss, self.sdf_loss
         cabi.sdf_gate_count(cap, self.n_gate, visibilities=R.r["visibilities"], visible_thr=self.vis_thr, valid_mask=self.valid_mask,
                             n_live=n_live)
         gate = dict(valid_mask=self.valid_mask, n_gate=self.n_gate)
@@ -388,6 +426,7 @@ class GsSdfTrainer(GsSdfStep):
         assert self.t_sdf == self.t_splat
         self._adam(self.splat_groups + self.sdf_groups, self.t_sdf, grad_scale, True)
 
-    def train_step(self, viewmats, Ks, gt_image, ray_xyz, ray_gt_sdf, randns=None, on_sdf_grads_ready=None, before_render=None):
+    def train_step(self, viewmats, Ks, gt_image, ray_xyz, ray_gt_sdf, randns=None, on_sdf_grads_ready=None, before_render=None,
+                   ray_n_live=None):
         return self.step(self.scene, self.table, self.mlp, viewmats, Ks, gt_image, ray_xyz, ray_gt_sdf, randns,
-                         on_sdf_grads_ready=on_sdf_grads_ready, before_render=before_render)
+                         on_sdf_grads_ready=on_sdf_grads_ready, before_render=before_render, ray_n_live=ray_n_live)

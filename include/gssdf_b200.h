@@ -526,6 +526,38 @@ typedef struct gssdf_sdf_gate_count_args {
 } gssdf_sdf_gate_count_args;
 int gssdf_sdf_gate_count(const gssdf_sdf_gate_count_args *a, gssdf_stream_t stream);
 
+/* The reference's `index_select` of the gated samples (neural_mapping.cpp:433-437) without its nonzero() / .item() host sync: stable
+   compaction of the rows that pass the gate. index[j] = j-th gated row (ascending), x_out[j] = x[index[j]], w_out[j] = weights[index[j]] *
+   visibilities[index[j]] (the coupling weight `gs_samples_gs_weights * gs_visibilities`, :426-427), *n_gate = count. The SDF kernels then
+   run on the compact arrays with n_live = n_gate -- like the reference, no work is spent on samples that fail the gate.
+   gssdf_scatter_rows3 is the backward of that index_select for dL/dx: dst[index[j]] = src[j], every other row < *n_live zero. */
+typedef struct gssdf_sdf_gate_compact_args {
+    int64_t n;
+    const int32_t *n_live;     /* device int32 or NULL */
+    const float *visibilities; /* [n] or NULL */
+    float visible_thr;
+    const uint8_t *valid_mask; /* [n] or NULL */
+    const float *x;            /* [n,3] */
+    const float *weights;      /* [n] or NULL (w_out = vis, or 1 without visibilities) */
+    int32_t *index;            /* [n] */
+    float *x_out;              /* [n,3] */
+    float *w_out;              /* [n] or NULL */
+    int32_t *n_gate;           /* device int32 */
+    void *workspace;           /* >= gssdf_sdf_gate_compact_workspace_bytes(n) */
+    size_t workspace_bytes;
+} gssdf_sdf_gate_compact_args;
+size_t gssdf_sdf_gate_compact_workspace_bytes(int64_t n);
+int gssdf_sdf_gate_compact(const gssdf_sdf_gate_compact_args *a, gssdf_stream_t stream);
+typedef struct gssdf_scatter_rows3_args {
+    int64_t n;                 /* rows of dst */
+    const int32_t *n_live;     /* device int32 or NULL: rows [0, min(n, *n_live)) of dst are written (zero unless indexed) */
+    const int32_t *index;      /* [*n_gate] */
+    const int32_t *n_gate;     /* device int32 */
+    const float *src;          /* [*n_gate, 3] */
+    float *dst;                /* [n,3] */
+} gssdf_scatter_rows3_args;
+int gssdf_scatter_rows3(const gssdf_scatter_rows3_args *a, gssdf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a9/a12 operator level: the hash-grid encoding alone, with its first and second backward -- what the tcnn_binding twin
  *     (shim/include/tcnn_binding/tcnn_binding.h: TCNNEncoding) binds in place of tcnn_binding::Module::fwd / bwd / bwd_bwd_input

@@ -92,9 +92,10 @@ def test_sdf_mirror_api_autograd_and_numerical_gradient(oracle):
     (sdf.square().sum() + isigma.sum()).backward()
     assert net.params_.grad is not None and net.decoder_.grad is not None and xyz.grad is not None
     assert torch.isfinite(net.params_.grad).all() and net.params_.grad.abs().sum() > 0
-    # same arithmetic as the kernel: fma(x - origin, inv_size, 0.5) in fp32 (the fp16 grid amplifies 1-ulp input changes)
+    # same arithmetic as the kernel and the reference (SubMap::xyz_to_zp1_pts as separate fp32 ops: fl(fl((x - pos) * inv) + 0.5));
+    # the fp16 grid amplifies 1-ulp input changes
     d32 = (xyz.detach().cpu().numpy() - np.array([0.5, -0.25, 0.1], np.float32)).astype(np.float32)
-    x01 = (d32.astype(np.float64) * np.float64(np.float32(1.0 / 14.0)) + 0.5).astype(np.float32)
+    x01 = ((d32 * np.float32(1.0 / 14.0)).astype(np.float32) + np.float32(0.5)).astype(np.float32)
     r_sdf, _, _ = oracle.sdf_fwd(x01, net.params_.detach().cpu().numpy(), net.decoder_.detach().cpu().numpy())
     assert_close_frac(sdf.detach().cpu().numpy()[:, 0], r_sdf, 2e-4, 2e-5, 2e-3, "sdf (world coords)")  # x01 rounding differs by an ulp
     g = net.get_gradient_numerical(xyz.detach(), 0.05)
