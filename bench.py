@@ -518,7 +518,11 @@ def main():
 
     pre = pre_render if world > 1 else None
 
+    from gssdf_b200 import densify
+    DEN = densify.Densifier(T, num_train_data=n_cams, sh_degree=deg)
+
     def after_step():
+        DEN.update_state()  # NeuralGS::update_state: per-iteration densification statistics (the every-100-iterations surgery is not timed)
         if world > 1:
             xchg.finish_step(T.flat_grad[:n_splat_grad])  # splat all-reduce in flight; returns once the SDF segment is reduced
             pending["splat"] = True
@@ -678,12 +682,12 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "step/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
                 # ours only (torch's RNG fills not counted): 30 of GsSdfStep - table cast - weight pack (now inside the Adam call) + normal-consistency
-                # + isotropic + Adam + weight pack + 6 sample-generation kernels + octree query
-                "gpu_launches": args.steps * (render.GsSdfStep.KERNELS_PER_STEP - 2 + 2 + 2 + 7),
+                # + isotropic + Adam + weight pack + 6 sample-generation kernels + octree query + gate compaction (3, replaces the gate count) + row scatter (2) + densify statistics
+                "gpu_launches": args.steps * (render.GsSdfStep.KERNELS_PER_STEP - 2 + 2 + 2 + 7 + 2 + 2 + 1),
                 "step_contents": "[A] octree ray-march sample generation of 3277 depth rays (~32 k points) + SDF stage on them, [B] render, [C] "
                                  "GS<->SDF coupling gated by visibility and octree validity, [D] L1 + DSSIM + depth L1 + normal-consistency + "
-                                 "isotropic -> backward, Adam over all parameter groups (f-3 first half); not in the step: the every-100-"
-                                 "iterations densification callback (NeuralGS::train_callback)",
+                                 "isotropic -> backward, Adam over all parameter groups, densification statistics (update_state); not in the "
+                                 "step: the every-100-iterations grow / split / prune surgery of NeuralGS::train_callback",
                 "roofline": {"kernel": "raster2dgs_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / pk["hbm_gbs"], "traffic": prof.get("dram_bytes_per_launch"), "peak_source": pk_kind,
                              "algorithmic_bytes": alg_bwd, "kernel_ms": t_bwd * 1e3,

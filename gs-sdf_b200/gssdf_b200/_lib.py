@@ -40,7 +40,10 @@ def parse_header(path=HEADER):
             for item in rest.split(","):
                 item = item.strip()
                 arr = re.match(r"(\w+)\[(\d+)\]$", item)
-                if item.startswith("*"):
+                parr = re.match(r"\*\s*(\w+)\[(\d+)\]$", item)
+                if parr:  # array of pointers
+                    fields.append((parr.group(1), C.c_void_p * int(parr.group(2))))
+                elif item.startswith("*"):
                     fields.append((item.lstrip("* "), C.c_void_p))
                 elif arr:
                     fields.append((arr.group(1), (ctypes_structs.get(base) or _SCALARS[base]) * int(arr.group(2))))

@@ -329,3 +329,28 @@ def sdf_gate_compact(n, x, index, x_out, n_gate, ws, visibilities=None, visible_
 def scatter_rows3(n, index, n_gate, src, dst, n_live=None):
     a = make_args("gssdf_scatter_rows3_args", n=n, n_live=n_live, index=index, n_gate=n_gate, src=src, dst=dst)
     check(lib().gssdf_scatter_rows3(_lib.C.byref(a), _stream()))
+
+
+def densify_update_state(N, cap, counts, gaussian_ids, v_densify, visibilities, radii, width, height, n_cameras, grad2d, count, vis, radii_state=None):
+    a = make_args("gssdf_densify_update_args", N=N, cap=cap, counts=counts, gaussian_ids=gaussian_ids, v_densify=v_densify, visibilities=visibilities,
+                  radii=radii, width=width, height=height, n_cameras=n_cameras, grad2d=grad2d, count=count, vis=vis, radii_state=radii_state)
+    check(lib().gssdf_densify_update_state(_lib.C.byref(a), _stream()))
+
+
+def densify_flags(N, offsets, quats, scaling, opacity, flags, grad2d=None, count=None, vis=None, radii_state=None, grow_grad2d=0.0, grow_scale3d=0.0,
+                  grow_scale2d=0.0, use_scale2d=False, prune_opa=0.0, prune_scale3d=float("inf")):
+    a = make_args("gssdf_densify_flags_args", N=N, offsets=offsets, quats=quats, scaling=scaling, opacity=opacity, grad2d=grad2d, count=count, vis=vis,
+                  radii_state=radii_state, grow_grad2d=grow_grad2d, grow_scale3d=grow_scale3d, grow_scale2d=grow_scale2d, use_scale2d=int(bool(use_scale2d)),
+                  prune_opa=prune_opa, prune_scale3d=prune_scale3d, flags=flags)
+    check(lib().gssdf_densify_flags(_lib.C.byref(a), _stream()))
+
+
+def densify_remap(n_new, K, stride_old, stride_new, src_row, mode, randn_row, randn, old, new, states_old=(), states_new=()):
+    """old / new: dict(params, exp_avg, exp_avg_sq, anchors)."""
+    a = make_args("gssdf_densify_remap_args", n_new=n_new, K=K, stride_old=stride_old, stride_new=stride_new, src_row=src_row, mode=mode,
+                  randn_row=randn_row, randn=randn, params_old=old["params"], exp_avg_old=old["exp_avg"], exp_avg_sq_old=old["exp_avg_sq"],
+                  anchors_old=old["anchors"], params_new=new["params"], exp_avg_new=new["exp_avg"], exp_avg_sq_new=new["exp_avg_sq"],
+                  anchors_new=new["anchors"], n_state=len(states_old))
+    for i, (so, sn) in enumerate(zip(states_old, states_new)):
+        a.state_old[i], a.state_new[i] = so.data_ptr(), sn.data_ptr()
+    check(lib().gssdf_densify_remap(_lib.C.byref(a), _stream()))

@@ -365,29 +365,44 @@ class GsSdfTrainer(GsSdfStep):
     the hash table and re-packs the decoder's bf16 operand image, so a training step launches no cast / pack / memset kernels.
     `anchors` are not optimised (register_parameter(..., false), neural_gaussian.cpp:426)."""
 
-    def __init__(self, *a, spatial_scale=1.0, sdf_lr=5e-3, **kw):
+    def __init__(self, *a, spatial_scale=1.0, sdf_lr=5e-3, n_live=None, **kw):
+        """The first positional argument N is the row CAPACITY of the splat buffers; n_live (default N) splats are in use. Densification
+        (gssdf_b200/densify.py) changes n_live between steps; every segment of the flat buffers keeps its capacity-based offset."""
         super().__init__(*a, **kw)
         N, K = self.R.N, self.R.K
         f32 = dict(dtype=torch.float32, device=self.dev)
         n = self.flat_grad.numel()
         self.params, self.exp_avg, self.exp_avg_sq = torch.zeros(n, **f32), torch.zeros(n, **f32), torch.zeros(n, **f32)
-        t0 = self.table_grad.storage_offset()
-        o = [0, N * 3, N * 7, N * 10, N * 11, N * 14, N * 11 + N * K * 3]
-        lr = [1.6e-4 * spatial_scale, 0.001, 0.005, 0.05, 0.0025, 0.0025 / 20.0]  # offsets, quaternion, scaling, opacity, dc, rest
-        self.splat_groups = [(o[i], o[i + 1] - o[i], lr[i], False) for i in range(6) if o[i + 1] > o[i]]
-        self.sdf_groups = [(t0, self.n_table, sdf_lr, True), (t0 + self.n_table, self.n_mlp, sdf_lr, False)]
-        pv = self.params
-        self.anchors = torch.zeros(N, 3, **f32)
-        self.scene = dict(means=self.anchors, quats=pv[o[1]:o[2]].view(N, 4), scales=pv[o[2]:o[3]].view(N, 3), opacities=pv[o[3]:o[4]],
-                          sh=pv[o[4]:o[5]].view(N, 1, 3),
-                          raw=dict(offsets=pv[o[0]:o[1]].view(N, 3), sh_rest=pv[o[5]:o[6]].view(N, K - 1, 3) if K > 1 else None))
-        self.table, self.mlp = pv[t0:t0 + self.n_table], pv[t0 + self.n_table:]
-        # the shadow pointer of the table group is relative to the group start: element i of the group -> table_half[i]
+        self.t0 = self.table_grad.storage_offset()
+        self.seg_off = [0, N * 3, N * 7, N * 10, N * 11, N * 14, N * 11 + N * K * 3]  # offsets|quaternion|scaling|opacity|dc|rest
+        self.seg_w = [3, 4, 3, 1, 3, 3 * (K - 1)]
+        self.lr = [1.6e-4 * spatial_scale, 0.001, 0.005, 0.05, 0.0025, 0.0025 / 20.0]  # neural_gaussian.cpp:434-449
+        self.sdf_lr = sdf_lr
+        self.anchors_buf = torch.zeros(N, 3, **f32)
         self.keep_shadows = True
         self.t_splat = self.t_sdf = 0
         self._net = None
+        self.N_cap = N
+        self.set_live(N if n_live is None else n_live)
+
+    def set_live(self, n_live):
+        """(Re)bind the parameter views and Adam groups to the first n_live rows of every segment."""
+        assert 0 <= n_live <= self.N_cap
+        self.N_live = n = int(n_live)
+        o, w, pv, K = self.seg_off, self.seg_w, self.params, self.R.K
+        v = lambda s_, *shape: pv[o[s_]:o[s_] + n * w[s_]].view(n, *shape)
+        self.anchors = self.anchors_buf[:n]
+        self.scene = dict(means=self.anchors, quats=v(1, 4), scales=v(2, 3), opacities=pv[o[3]:o[3] + n], sh=v(4, 1, 3),
+                          raw=dict(offsets=v(0, 3), sh_rest=v(5, K - 1, 3) if K > 1 else None))
+        self.splat_groups = [(o[i], n * w[i], self.lr[i], False) for i in range(6) if w[i] > 0 and n > 0]
+        t0 = self.t0
+        self.sdf_groups = [(t0, self.n_table, self.sdf_lr, True), (t0 + self.n_table, self.n_mlp, self.sdf_lr, False)]
+        self.table, self.mlp = pv[t0:t0 + self.n_table], pv[t0 + self.n_table:]
+        if self._net is not None:
+            self._net = cabi.sdf_net(self.table_half, self.mlp, **self.cfg)
 
     def load(self, anchors, offsets, quats, log_scales, logit_opacities, features_dc, features_rest, table, mlp):
+        self.set_live(anchors.shape[0])
         sc = self.scene
         self.anchors.copy_(anchors)
         sc["raw"]["offsets"].copy_(offsets); sc["quats"].copy_(quats); sc["scales"].copy_(log_scales); sc["opacities"].copy_(logit_opacities)

@@ -49,7 +49,7 @@ const char *gssdf_last_error(void);
 /* "gssdf_b200 <ver> sm_100a" */
 const char *gssdf_version(void);
 /* Argument structs grow between revisions: a binding compiled against this header must see the same number from the library. */
-#define GSSDF_ABI_REVISION 12
+#define GSSDF_ABI_REVISION 13
 int32_t gssdf_abi_revision(void);
 
 /* Device-side counters shared by the stages of one render. Zeroed by gssdf_project2dgs_fwd. */
@@ -674,6 +674,61 @@ typedef struct gssdf_adam_args {
     void *mlp_packed;
 } gssdf_adam_args;
 int gssdf_adam_step(const gssdf_adam_args *a, gssdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f-3 (second half)  Densification of NeuralGS (include/neural_gaussian/neural_gaussian.cpp:568-926).
+ *     update_state (:626-680) runs every iteration -> one fused kernel over the visible rows instead of ~12 ATen index kernels;
+ *     the grow / split / prune surgery (:690-905; include/optimizer/optimizer_utils/optimizer_utils.cpp:5-165 for the Adam moments)
+ *     runs every k_refine_every iterations -> one row-remap kernel that rebuilds parameters, both Adam moments, the anchors and the
+ *     statistics from a source-row map (the decisions themselves are a flag kernel + the caller's nonzero(), as in the reference).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gssdf_densify_update_args {
+    int32_t N, cap;
+    const gssdf_counts *counts;   /* nnz */
+    const int64_t *gaussian_ids;  /* [cap] */
+    const float *v_densify;       /* [cap,2] gradient of the `densify` carrier = info[key_for_gradient].grad() (neural_gaussian.cpp:562-564) */
+    const float *visibilities;    /* [cap] */
+    const int32_t *radii;         /* [cap,2] or NULL (k_refine_scale2d_stop_iter == 0) */
+    int32_t width, height, n_cameras;
+    float *grad2d, *count, *vis;  /* [N] state: += |grad * (W/2, H/2) * n_cameras|, += 1, max= visibility */
+    float *radii_state;           /* [N] max= max(radii) / max(W, H), or NULL */
+} gssdf_densify_update_args;
+int gssdf_densify_update_state(const gssdf_densify_update_args *a, gssdf_stream_t stream);
+
+/* Per-splat decision bits of grow_gs (:690-720), prune_gs (:842-876), prune_invisible_gs (:878-892), prune_nan_gs (:894-905). */
+enum { GSSDF_DENSIFY_DUPLI = 1, GSSDF_DENSIFY_SPLIT = 2, GSSDF_DENSIFY_PRUNE_OPA = 4, GSSDF_DENSIFY_PRUNE_SMALL = 8,
+       GSSDF_DENSIFY_PRUNE_BIG = 16, GSSDF_DENSIFY_PRUNE_NAN = 32, GSSDF_DENSIFY_PRUNE_INVISIBLE = 64 };
+typedef struct gssdf_densify_flags_args {
+    int32_t N;
+    const float *offsets, *quats, *scaling, *opacity;  /* raw parameters [N,3] [N,4] [N,3] [N] */
+    const float *grad2d, *count, *vis, *radii_state;   /* state (radii_state may be NULL) */
+    float grow_grad2d, grow_scale3d, grow_scale2d;     /* k_grow_grad2d, k_grow_scale3d * spatial_scale_, k_grow_scale2d */
+    int32_t use_scale2d;                               /* iter < k_refine_scale2d_stop_iter */
+    float prune_opa, prune_scale3d;                    /* k_prune_opa, k_prune_scale3d * original_spatial_scale_ */
+    uint8_t *flags;                                    /* [N] */
+} gssdf_densify_flags_args;
+int gssdf_densify_flags(const gssdf_densify_flags_args *a, gssdf_stream_t stream);
+
+/* Row remap of the flat buffers [offsets | quaternion | scaling | opacity | features_dc | features_rest] (segment stride = row capacity):
+   new row r takes its values from old row src_row[r]; mode[r] = 0 copies parameters AND Adam moments (index_select / rest rows),
+   1 copies parameters and zeroes the moments (duplicate, cat_tensors_to_optimizer), 2 is a split sample: offsets += R(q) (s*s*randn),
+   scaling = log(s / 1.6) with s = (exp(scaling).xy, 0) (split(), :764-790, einsum "nij,nj,bnj->bni" reproduced incl. its squared scale),
+   moments zeroed. randn row for mode 2 = randn_row[r]. State arrays are copied from the source row for every mode. */
+typedef struct gssdf_densify_remap_args {
+    int32_t n_new;            /* rows to write */
+    int32_t K;                /* SH bases per splat (features_dc + features_rest) */
+    int64_t stride_old, stride_new; /* row capacities of the old / new flat buffers (segment s starts at width-prefix(s) * stride) */
+    const int32_t *src_row;   /* [n_new] */
+    const uint8_t *mode;      /* [n_new] */
+    const int32_t *randn_row; /* [n_new] (read for mode 2) or NULL */
+    const float *randn;       /* [*,3] */
+    const float *params_old, *exp_avg_old, *exp_avg_sq_old, *anchors_old;
+    float *params_new, *exp_avg_new, *exp_avg_sq_new, *anchors_new;
+    int32_t n_state;          /* number of [N] state arrays (<= 4) */
+    const float *state_old[4];
+    float *state_new[4];
+} gssdf_densify_remap_args;
+int gssdf_densify_remap(const gssdf_densify_remap_args *a, gssdf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a13 / f-2  SDF sample generation: the octree acceleration structure of kaolin_wisp_cpp's OctreeAS (NVIDIA kaolin SPC: byte octree in
