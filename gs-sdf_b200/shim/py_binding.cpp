@@ -115,6 +115,24 @@ struct LocalMapReplay : torch::nn::Module {
             o += p.numel();
         }
     }
+    // export_checkpoint / load_checkpoint (neural_mapping.cpp:1331-1378): torch::save(local_map_ptr) = the module's own archive
+    // (named parameters `encoder_local_map`, `decoder.N.weight|bias`), written and read by libtorch itself
+    void save(const std::string &path) {
+        torch::serialize::OutputArchive ar;
+        torch::nn::Module::save(ar);
+        ar.save_to(path);
+    }
+    void load(const std::string &path) {
+        torch::serialize::InputArchive ar;
+        ar.load_from(path);
+        torch::nn::Module::load(ar);
+    }
+    std::vector<std::string> parameter_names() {
+        std::vector<std::string> n;
+        for (auto &kv : named_parameters()) n.push_back(kv.key());
+        return n;
+    }
+
     torch::Tensor decoder_grad() {
         std::vector<torch::Tensor> g;
         for (auto &p : decoder_->parameters()) g.push_back(p.grad().defined() ? p.grad().flatten() : torch::zeros({p.numel()}, p.options()));
@@ -145,6 +163,9 @@ void bind_tcnn(pybind11::module &m) {
         .def("get_gradient_analytic", &LocalMapReplay::get_gradient_analytic, py::call_guard<py::gil_scoped_release>())
         .def("regularization", &LocalMapReplay::regularization, py::call_guard<py::gil_scoped_release>())
         .def("set_decoder", &LocalMapReplay::set_decoder)
+        .def("save", &LocalMapReplay::save)
+        .def("load", &LocalMapReplay::load)
+        .def("parameter_names", &LocalMapReplay::parameter_names)
         .def("decoder_grad", &LocalMapReplay::decoder_grad)
         .def("encoder_params", [](LocalMapReplay &s) { return s.p_encoder_tcnn_->params_; })
         .def("zero_grad", [](LocalMapReplay &s) { s.zero_grad(); });
