@@ -354,3 +354,11 @@ def densify_remap(n_new, K, stride_old, stride_new, src_row, mode, randn_row, ra
     for i, (so, sn) in enumerate(zip(states_old, states_new)):
         a.state_old[i], a.state_new[i] = so.data_ptr(), sn.data_ptr()
     check(lib().gssdf_densify_remap(_lib.C.byref(a), _stream()))
+
+
+def l2_persist(tensor, hit_ratio=1.0):
+    """Keep `tensor` (e.g. the fp16 hash-table shadow) resident in L2 for kernels launched on the current stream (None clears the window)."""
+    if tensor is None:
+        check(lib().gssdf_l2_persist(None, 0, 1.0, _stream()))
+    else:
+        check(lib().gssdf_l2_persist(_lib.C.c_void_p(tensor.data_ptr()), tensor.numel() * tensor.element_size(), hit_ratio, _stream()))

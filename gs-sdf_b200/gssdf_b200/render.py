@@ -382,6 +382,7 @@ class GsSdfTrainer(GsSdfStep):
         self.keep_shadows = True
         self.t_splat = self.t_sdf = 0
         self._net = None
+        self.l2_persist = True
         self.N_cap = N
         self.set_live(N if n_live is None else n_live)
 
@@ -416,6 +417,8 @@ class GsSdfTrainer(GsSdfStep):
         self._net = cabi.sdf_net(self.table_half, self.mlp, **self.cfg)
         if self.mlp_mode == 1:
             cabi.sdf_mlp_pack(self._net, self.mlp_packed)
+        if self.l2_persist:  # the 30.5 MB fp16 table stays in L2 across the optimiser's streaming pass
+            cabi.l2_persist(self.table_half)
 
     def _adam(self, groups, t, grad_scale, sdf):
         self._adam_call(groups, t, grad_scale, sdf)

@@ -52,6 +52,13 @@ const char *gssdf_version(void);
 #define GSSDF_ABI_REVISION 13
 int32_t gssdf_abi_revision(void);
 
+/* L2 residency hint: marks [ptr, ptr+bytes) as a persisting access-policy window for kernels launched on `stream` from now on
+   and reserves that much of the device's persisting L2 carve-out (cudaLimitPersistingL2CacheSize, grown if needed, never shrunk).
+   Meant for the 30.5 MB fp16 hash-table shadow: the optimiser's 2.4 GB streaming pass would otherwise evict it between steps, and the
+   SDF kernels are bound by the latency of their table gathers. bytes == 0 clears the window of the stream. The only call of the library
+   that touches device-wide state; nothing else depends on it. */
+int gssdf_l2_persist(const void *ptr, size_t bytes, float hit_ratio, gssdf_stream_t stream);
+
 /* Device-side counters shared by the stages of one render. Zeroed by gssdf_project2dgs_fwd. */
 typedef struct gssdf_counts {
     int32_t nnz;            /* visible (camera, splat) pairs found by the projection            */
