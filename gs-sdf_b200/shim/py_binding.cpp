@@ -91,6 +91,19 @@ struct LocalMapReplay : torch::nn::Module {
         return gradients;
     }
 
+    // get_gradient(_xyz, delta, sdf, _heissian = true, numerical = false) (local_map.cpp:150-168): {gradients, hessian row sums}
+    std::vector<torch::Tensor> get_gradient_hessian_analytic(torch::Tensor _xyz) {
+        auto grad_mode = torch::GradMode::is_enabled();
+        torch::GradMode::set_enabled(true);
+        _xyz.requires_grad_(true);
+        auto _sdf = get_sdf(_xyz)[0];
+        auto d_output = torch::ones_like(_sdf);
+        auto gradients = torch::autograd::grad({_sdf}, {_xyz}, {d_output}, true, true)[0];
+        auto hessian = torch::autograd::grad({gradients}, {_xyz}, {torch::ones_like(gradients)}, true, true)[0];
+        torch::GradMode::set_enabled(grad_mode);
+        return {gradients, hessian};
+    }
+
     // sdf_regularization with the analytic gradient (neural_mapping.cpp:106-136): eikonal + align against the detached numerical gradient
     torch::Tensor regularization(const torch::Tensor &xyz, double delta, double eikonal_weight, double align_weight) {
         auto point_grad = get_gradient_analytic(xyz.detach().clone());
@@ -162,6 +175,7 @@ void bind_tcnn(pybind11::module &m) {
         // these run the autograd engine from C++ (torch::autograd::grad): the GIL must not be held
         .def("get_gradient_analytic", &LocalMapReplay::get_gradient_analytic, py::call_guard<py::gil_scoped_release>())
         .def("regularization", &LocalMapReplay::regularization, py::call_guard<py::gil_scoped_release>())
+        .def("get_gradient_hessian_analytic", &LocalMapReplay::get_gradient_hessian_analytic, py::call_guard<py::gil_scoped_release>())
         .def("set_decoder", &LocalMapReplay::set_decoder)
         .def("save", &LocalMapReplay::save)
         .def("load", &LocalMapReplay::load)

@@ -242,6 +242,17 @@ def test_tcnn_binding_twin_replays_local_map(oracle):
     f_l, f_t, f_m = abs(float(fl) - float(loss)) / abs(float(loss)), rel(tg.cpu().numpy(), enc_g), rel(mg.cpu().numpy(), dec_g)
     print(f"fused kernel vs tcnn twin: loss {f_l:.2e} table-grad {f_t:.2e} decoder-grad {f_m:.2e}")
     assert f_l <= 1e-4 and f_t <= 1e-3 and f_m <= 1e-3
+    # curvature branch of get_gradient (local_map.cpp:161-166): Hessian row sums = a second autograd.grad through the encoding's double
+    # backward (kernel_grid_backward_input_backward_input; the ReLU decoder is piecewise linear, so d(d sdf/d feat)/dx = 0 a.e.)
+    gh, hh = L.get_gradient_hessian_analytic(xt.clone())
+    widths = [32] + [hidden] * (1 + n_hidden) + [2]
+    r_feat = oracle.hashgrid_fwd(x01, table)
+    d_out = np.zeros((n, 2)); d_out[:, 0] = 1.0
+    dfeat, _ = oracle.mlp_bwd(r_feat, widths, mlp, d_out)
+    r_h = oracle.hashgrid_bwd_bwd_input(x01, np.ones((n, 3), np.float32), dfeat.astype(np.float32), table).astype(np.float64) / map_size ** 2
+    e_h = rel(hh.detach().cpu().numpy(), r_h)
+    print(f"tcnn twin: Hessian row sums vs oracle {e_h:.2e}")
+    assert rel(gh.detach().cpu().numpy(), r_g) <= 1e-4 and e_h <= 2e-3
     # unsupported configurations fail like tcnn's CHECK_THROW (std::runtime_error)
     with pytest.raises(RuntimeError):
         gssdf_shim.TCNNEncoding(3, json.dumps({"otype": "Grid", "type": "Dense"}), "e", 1337)
