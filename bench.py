@@ -44,9 +44,14 @@ WORKLOADS = {
     "1080p-1M": (1920, 1080, 1_000_000, 3, 40_000_000),   # the config BASELINE.json's metric is quoted on (c4 per GPU)
     "c2": (1200, 680, 500_000, 3, 24_000_000),
     "c3": (1920, 1080, 2_000_000, 3, 60_000_000),
+    "c5": (3840, 2160, 5_000_000, 3, 96_000_000),         # per GPU of the 8-GPU weak-scaling sweep
     "c1": (256, 256, 50_000, 0, 4_000_000),
     "tiny": (320, 192, 20_000, 3, 2_000_000),
 }
+# SDF sampling per workload: (rays per step, free samples per ray, surface samples per ray, capacity of the sample batch). Default: the
+# reference's k_batch_pt_num = 32768 points from ~3277 rays with 3 free + 3 surface samples (config/base.yaml:21-23). c5 asks for 64 rays x
+# 128 SDF samples per sampled pixel: 8192 rays x (124 free + 3 surface + voxel hits + the end point) ~ 1.07 M points per step.
+SDF_SAMPLING = {"default": (3277, 3, 3, 49152), "c5": (8192, 124, 3, 1_310_720)}
 CPU_SAMPLE_DIV = 4  # the CPU sample is the workload at 1/4 resolution per axis and 1/16 of the splats (1/16 of the work)
 
 
@@ -428,7 +433,8 @@ def main():
         K_sh = (deg + 1) ** 2
         sdf_cfg = dict(n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=2.0,
                        hidden_dim=32 if workload == "c1" else 64, n_hidden=1 if workload == "c1" else 3)
-        T = render.GsSdfTrainer(N, K_sh, W, H, dev, isect_cap, sdf_cfg, n_ray_samples=n_ray, sh_degree=deg, origin=(0.0, 0.0, 0.0),
+        T = render.GsSdfTrainer(N, K_sh, W, H, dev, isect_cap, sdf_cfg, n_ray_samples=SDF_SAMPLING.get(workload, SDF_SAMPLING["default"])[3],
+                                sh_degree=deg, origin=(0.0, 0.0, 0.0),
                                 map_size=14.0, eikonal_mode=(1 if eikonal == "analytic" and sdf_cfg["hidden_dim"] == 64 else 0),
                                 normal_weight=0.01, isotropic_weight=0.05)  # config/base.yaml:43-46
         T.l2_persist = not args.no_l2_persist
@@ -447,7 +453,8 @@ def main():
     # SDF ray samples (rows a13 / f-2): k_batch_num depth rays per step go through the octree ray-march + free / surface sampling of
     # NeuralSLAM::sample; the reference adapts k_batch_num so that the batch holds ~k_batch_pt_num = 32768 points (neural_mapping.cpp:324-330)
     # -- ~10 points per ray here. n_ray = capacity of the sample batch the SDF stage is sized for.
-    N_RAYS, n_ray, OCT_LEVEL, LEAF = 3277, 49152, 8, 14.0 / 256
+    OCT_LEVEL, LEAF = 8, 14.0 / 256
+    N_RAYS, N_FREE, N_SURF, n_ray = SDF_SAMPLING.get(args.workload, SDF_SAMPLING["default"])
     from gssdf_b200 import octree as OT
     box = torch.tensor(S.BOX, device=dev, dtype=torch.float32)
 
@@ -464,14 +471,17 @@ def main():
             self.end = means[torch.randint(0, means.shape[0], (self.n_pack,), device=dev, generator=g_)].contiguous()
             self.depth = (self.end - self.o).norm(dim=1).contiguous()
             self.dir = ((self.end - self.o) / self.depth[:, None]).contiguous()
-            self.rs = OT.RaySampler(self.tree, N_RAYS, dev, 1, 3, 3, sample_std=T_.delta, truncated_dis=3 * LEAF, xyz_min=(-7.0,) * 3,
-                                    xyz_max=(7.0,) * 3, nugget_cap=16 * N_RAYS, cap=n_ray)
+            nr_, nf_, ns_, cap_ = (N_RAYS, N_FREE, N_SURF, n_ray) if T_.n_ray == n_ray else SDF_SAMPLING["default"]
+            self.n_rays = nr_
+            self.rs = OT.RaySampler(self.tree, nr_, dev, 1, nf_, ns_, sample_std=T_.delta, truncated_dis=3 * LEAF, xyz_min=(-7.0,) * 3,
+                                    xyz_max=(7.0,) * 3, nugget_cap=16 * nr_, cap=cap_)
             T_.set_octree(self.tree)
 
         def draw(self, i):
-            k = (i * N_RAYS) % (self.n_pack - N_RAYS)  # the reference indexes torch::rand rays of the pack (neural_mapping.cpp:145-156)
+            nr_ = self.n_rays
+            k = (i * nr_) % (self.n_pack - nr_)  # the reference indexes torch::rand rays of the pack (neural_mapping.cpp:145-156)
             self.rs.draw()
-            self.rs.sample(self.o[k:k + N_RAYS], self.dir[k:k + N_RAYS], self.depth[k:k + N_RAYS], self.end[k:k + N_RAYS])
+            self.rs.sample(self.o[k:k + nr_], self.dir[k:k + nr_], self.depth[k:k + nr_], self.end[k:k + nr_])
             return self.rs.xyz, self.rs.ray_sdf, self.rs.counts
 
     T, sc_act, _ = build_trainer(args.workload, args.eikonal)

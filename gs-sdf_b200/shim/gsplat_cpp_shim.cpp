@@ -9,6 +9,7 @@
 #include <torch/torch.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <stdexcept>
 
 #include "../../include/gssdf_b200.h"
@@ -52,6 +53,23 @@ Tensor workspace(const Tensor &like, size_t bytes) {
     return torch::empty({(int64_t)std::max<size_t>(bytes, 256)}, like.options().dtype(torch::kUInt8));
 }
 
+// Opt-in (GSSDF_SHIM_PRESORT_CULL=1): exact footprint culling BEFORE the tile sort inside gsplat_cpp::tile_encode. tile_encode's reference
+// signature carries no ray transforms, so the projection leaves them here; tile_encode picks them up when it is handed the means2d tensor
+// of that same projection (rasterization_2dgs_sdf calls the two back to back, neural_gaussian.cpp:188-215). Opacities are not known at
+// that point: the conic is built for opacity 1 (alpha = o * exp(-r^2 / 2) <= exp(-r^2 / 2)), which only keeps extra pairs. The returned
+// lists are then per-tile SUBSETS of the reference's lists in the same order; every render output is unchanged.
+struct LastProjection {
+    const void *means2d_ptr = nullptr;
+    Tensor ray_transforms;
+    int width = 0, height = 0;
+};
+thread_local LastProjection g_last_projection;
+
+inline bool presort_cull_enabled() {
+    static const bool on = [] { const char *e = std::getenv("GSSDF_SHIM_PRESORT_CULL"); return e && e[0] == '1'; }();
+    return on;
+}
+
 // ---------------------------------------------------------------------------------------------
 struct Projection2DGS : public torch::autograd::Function<Projection2DGS> {
     static tensor_list forward(AutogradContext *ctx, const Tensor &means, const Tensor &quats, const Tensor &scales,
@@ -86,6 +104,7 @@ struct Projection2DGS : public torch::autograd::Function<Projection2DGS> {
         ctx->saved_data["height"] = height;
         ctx->saved_data["nnz"] = nnz;
         auto s = [&](const Tensor &t) { return t.slice(0, 0, nnz); };
+        if (presort_cull_enabled()) g_last_projection = LastProjection{means2d.data_ptr(), rt.slice(0, 0, nnz), width, height};
         tensor_list out = {s(camera_ids), s(gaussian_ids), s(radii), s(means2d), s(depths), s(rt), s(normals), s(samples), s(weights)};
         ctx->mark_non_differentiable({out[0], out[1], out[2]});
         return out;
@@ -175,7 +194,9 @@ struct Raster2DGS : public torch::autograd::Function<Raster2DGS> {
         Tensor rTs = torch::empty({C, height, width, 2}, f), last_ids = torch::empty({C, height, width}, i32), median_ids = torch::empty({C, height, width}, i32);
         Tensor vis = torch::zeros({std::max<int64_t>(nnz, 1), 1}, f);
         Tensor counts = new_counts(means2d, (int32_t)nnz, (int32_t)I);
-        Tensor ws = workspace(means2d, gssdf_raster2dgs_workspace_bytes((int32_t)C, width, height, (int32_t)nnz, I));
+        // sized for the backward (forward layout + gradient records) and kept in the autograd context: the backward reuses the packed
+        // records and the culled per-tile lists instead of rebuilding them
+        Tensor ws = workspace(means2d, gssdf_raster2dgs_bwd_workspace_bytes((int32_t)C, width, height, (int32_t)nnz, I));
         Tensor bg = bg_in.numel() > 0 ? bg_in.contiguous() : bg_in;
         gssdf_raster2dgs_fwd_args a{};
         a.C = (int32_t)C; a.image_width = width; a.image_height = height; a.tile_size = tile_size; a.channels = (int32_t)colors.size(-1);
@@ -188,7 +209,7 @@ struct Raster2DGS : public torch::autograd::Function<Raster2DGS> {
         a.last_ids = ptr<int32_t>(last_ids); a.median_ids = ptr<int32_t>(median_ids); a.visibilities = vis.data_ptr<float>();
         a.workspace = ws.data_ptr(); a.workspace_bytes = (size_t)ws.numel();
         check(gssdf_raster2dgs_fwd(&a, cur_stream()));
-        ctx->save_for_backward({means2d, rt, colors, opac, normals, offsets, flatten_ids, ra, rTs, last_ids, median_ids, counts, bg});  // bg: [C,3] or an empty tensor
+        ctx->save_for_backward({means2d, rt, colors, opac, normals, offsets, flatten_ids, ra, rTs, last_ids, median_ids, counts, bg, ws});  // bg: [C,3] or an empty tensor
         ctx->saved_data["dims"] = std::vector<int64_t>{width, height, tile_size, C, nnz, want_abs ? 1 : 0};
         Tensor visn = vis.slice(0, 0, nnz);
         ctx->mark_non_differentiable({visn});
@@ -212,13 +233,13 @@ struct Raster2DGS : public torch::autograd::Function<Raster2DGS> {
         Tensor v_abs = want_abs ? torch::zeros({nnz, 2}, f) : Tensor();
         if (nnz > 0 && flatten_ids.size(0) > 0) {
             const int64_t I = flatten_ids.size(0);
-            Tensor ws = workspace(means2d, gssdf_raster2dgs_bwd_workspace_bytes((int32_t)C, (int32_t)width, (int32_t)height, (int32_t)nnz, I));
+            Tensor ws = sv[13];
             gssdf_raster2dgs_bwd_args a{};
             a.C = (int32_t)C; a.image_width = (int32_t)width; a.image_height = (int32_t)height; a.tile_size = (int32_t)tile; a.channels = 3;
             a.cap = (int32_t)nnz; a.counts = reinterpret_cast<const gssdf_counts *>(counts.data_ptr<int32_t>());
             a.means2d = ptr<float>(means2d); a.ray_transforms = ptr<float>(rt); a.colors = ptr<float>(colors); a.opacities = ptr<float>(opac);
             a.normals = ptr<float>(normals); a.backgrounds = ptr<float>(bg); a.offsets = ptr<int32_t>(offsets); a.flatten_ids = ptr<int32_t>(flatten_ids);
-            a.isect_cap = I; a.reuse_fwd = 0;
+            a.isect_cap = I; a.reuse_fwd = 1;
             a.render_alphas = ptr<float>(ra); a.render_Ts = ptr<float>(rTs); a.last_ids = ptr<int32_t>(last_ids); a.median_ids = ptr<int32_t>(median_ids);
             a.v_render_colors = ptr<float>(vc); a.v_render_depths = ptr<float>(vd); a.v_render_alphas = ptr<float>(va);
             a.v_render_normals = ptr<float>(vn); a.v_render_median = ptr<float>(vm);
@@ -288,6 +309,19 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> tile_encode(const int &w
     Tensor m = means2d.contiguous(), r = radii.contiguous(), d = depths.contiguous(), c = camera_ids.contiguous();
     Tensor counts = new_counts(means2d, (int32_t)nnz, 0);
     Tensor tpg = torch::empty({nnz}, i32), offsets = torch::empty({camera_num, th, tw}, i32), dummy = torch::empty({1}, i32);
+    Tensor conics;
+    if (presort_cull_enabled() && tile_size == 16 && nnz > 0 && g_last_projection.means2d_ptr == means2d.data_ptr() &&
+        g_last_projection.ray_transforms.defined() && g_last_projection.ray_transforms.size(0) == nnz && g_last_projection.width == width &&
+        g_last_projection.height == height) {
+        conics = torch::empty({nnz, 8}, means2d.options());
+        Tensor ones = torch::ones({nnz}, means2d.options());
+        gssdf_splat_conics_args ca{};
+        ca.cap = (int32_t)nnz; ca.image_width = width; ca.image_height = height;
+        ca.counts = reinterpret_cast<const gssdf_counts *>(counts.data_ptr<int32_t>());
+        ca.ray_transforms = g_last_projection.ray_transforms.data_ptr<float>(); ca.opacities = ones.data_ptr<float>();
+        ca.conics = conics.data_ptr<float>();
+        check(gssdf_splat_conics(&ca, cur_stream()));
+    }
     auto run = [&](int64_t isect_cap, Tensor &flat) {
         Tensor ws = workspace(means2d, gssdf_tile_encode_workspace_bytes(camera_num, width, height, tile_size, isect_cap));
         gssdf_tile_encode_args a{};
@@ -296,6 +330,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> tile_encode(const int &w
         a.means2d = ptr<float>(m); a.radii = ptr<int32_t>(r); a.depths = ptr<float>(d); a.camera_ids = ptr<int64_t>(c);
         a.isect_cap = isect_cap; a.tiles_per_gauss = ptr<int32_t>(tpg); a.flatten_ids = flat.data_ptr<int32_t>();
         a.offsets = offsets.data_ptr<int32_t>(); a.workspace = ws.data_ptr(); a.workspace_bytes = (size_t)ws.numel();
+        a.conics = conics.defined() ? conics.data_ptr<float>() : nullptr;
         check(gssdf_tile_encode(&a, cur_stream()));
     };
     run(0, dummy);  // count pass
