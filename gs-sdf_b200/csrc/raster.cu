@@ -25,13 +25,16 @@
 //     minimum of the quadratic over a rectangle) and each warp only evaluates the splats whose ellipse
 //     touches its 8x4 pixels. Every culled (pixel, splat) pair is one the reference skips (alpha < 1/255),
 //     so results are unchanged; on the 1080p/1M workload 96% of the (warp, splat) iterations were such no-ops.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "conic.cuh"
 
 namespace gssdf {
 
 constexpr int kRasterThreads = 256;
-constexpr int kBatch = 256;  // splats per shared-memory stage
+constexpr int kBatch = 256;  // splats per shared-memory stage (forward)
+constexpr int kRasterBwdDefaultVariant = 0;
 constexpr float kNearN = 0.05f, kFarN = 100.f;  // hard-coded in the reference (Fwd.cu:368-369)
 constexpr float kAlphaThreshold = 1.f / 255.f;  // GSF/include/Common.h:53
 constexpr int kRecF4 = 4;                        // render record = 4 float4 = 64 B: M[9], opacity, rgb[3], normal[3]
@@ -303,22 +306,26 @@ raster2dgs_fwd_kernel(const gssdf_raster2dgs_fwd_args a, const float4 *__restric
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-struct __align__(16) BwdStage {
-    float4 rec[kBatch * kRecF4];
-    int ids[kBatch];
-    int meta[kBatch];
-    float grad[kBatch * 16];  // per-splat tile gradient record: rgb[3] n[3] u[3] v[3] w[3] opacity
-    float gabs[kBatch * 2];
+template <int BATCH>
+struct __align__(16) BwdStageT {
+    float4 rec[BATCH * kRecF4];
+    int ids[BATCH];
+    int meta[BATCH];
+    float grad[BATCH * 16];  // per-splat tile gradient record: rgb[3] n[3] u[3] v[3] w[3] opacity
+    float gabs[BATCH * 2];
 };
 
-__device__ __forceinline__ void issue_batch_bwd(BwdStage &st, uint64_t *bar, const float4 *__restrict__ rec,
+template <int BATCH>
+__device__ __forceinline__ void issue_batch_bwd(BwdStageT<BATCH> &st, uint64_t *bar, const float4 *__restrict__ rec,
                                                 const int2 *__restrict__ clist, int last, int n) {
     // batch covers culled-list entries last, last-1, ..., last-n+1 (slot t <-> entry last - t): back to front
     const int t = threadIdx.x;
+    if (t < BATCH) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) st.grad[k * kBatch + t] = 0.f;  // flat, conflict-free zero-fill of the [kBatch][16] records
-    st.gabs[t] = 0.f;
-    st.gabs[kBatch + t] = 0.f;
+        for (int k = 0; k < 16; ++k) st.grad[k * BATCH + t] = 0.f;  // flat, conflict-free zero-fill of the [BATCH][16] records
+        st.gabs[t] = 0.f;
+        st.gabs[BATCH + t] = 0.f;
+    }
     if (t < n) {
         const int2 e = clist[last - t];
         st.ids[t] = e.x;
@@ -330,10 +337,14 @@ __device__ __forceinline__ void issue_batch_bwd(BwdStage &st, uint64_t *bar, con
     }
 }
 
-template <bool ABS>
-__global__ void __launch_bounds__(kRasterThreads)
+// BATCH / MINB: splats per shared-memory stage and the CTAs per SM the register allocation is tuned for. <256, 3>: 72 KiB of shared
+// memory, 76 registers -> 3 CTAs (24 warps) per SM; <192, 4>: 54 KiB, <= 64 registers -> 4 CTAs (32 warps) per SM.
+template <bool ABS, int BATCH, int MINB>
+__global__ void __launch_bounds__(kRasterThreads, MINB)
 raster2dgs_bwd_kernel(const gssdf_raster2dgs_bwd_args a, const float4 *__restrict__ rec, const int2 *__restrict__ clist,
                       const int32_t *__restrict__ ccount, float *__restrict__ vrec, int tw, int th) {
+    constexpr int kBatch = BATCH;  // shadows the forward's batch size inside this kernel
+    using BwdStage = BwdStageT<BATCH>;
     extern __shared__ __align__(16) unsigned char s_raw[];
     BwdStage *s_stage = reinterpret_cast<BwdStage *>(s_raw);
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -743,16 +754,23 @@ extern "C" int gssdf_raster2dgs_bwd(const gssdf_raster2dgs_bwd_args *a, gssdf_st
         if (rc) return rc;
     }
     GSSDF_CUDA_OK(cudaMemsetAsync(w.vrec, 0, (size_t)a->cap * 64, st));
-    const size_t smem = 2 * sizeof(BwdStage);
     if (a->v_means2d_abs) GSSDF_CUDA_OK(cudaMemsetAsync(a->v_means2d_abs, 0, (size_t)a->cap * 2 * sizeof(float), st));
     if (a->prof_start) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_start, st));
-    if (a->v_means2d_abs) {
-        GSSDF_CUDA_OK(cudaFuncSetAttribute(raster2dgs_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        raster2dgs_bwd_kernel<true><<<a->C * tw * th, kRasterThreads, smem, st>>>(*a, w.rec, w.clist, w.ccount, reinterpret_cast<float *>(w.vrec), tw, th);
+    // occupancy variant (tuning knob, read once): GSSDF_RASTER_BWD_VARIANT=1 -> 192-splat stages, 4 CTAs / SM
+    static const int variant = [] { const char *e = getenv("GSSDF_RASTER_BWD_VARIANT"); return e ? atoi(e) : kRasterBwdDefaultVariant; }();
+    auto launch = [&](auto kern, size_t smem) -> int {
+        GSSDF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<a->C * tw * th, kRasterThreads, smem, st>>>(*a, w.rec, w.clist, w.ccount, reinterpret_cast<float *>(w.vrec), tw, th);
+        return GSSDF_OK;
+    };
+    if (variant == 1) {
+        rc = a->v_means2d_abs ? launch(raster2dgs_bwd_kernel<true, 192, 4>, 2 * sizeof(BwdStageT<192>))
+                              : launch(raster2dgs_bwd_kernel<false, 192, 4>, 2 * sizeof(BwdStageT<192>));
     } else {
-        GSSDF_CUDA_OK(cudaFuncSetAttribute(raster2dgs_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        raster2dgs_bwd_kernel<false><<<a->C * tw * th, kRasterThreads, smem, st>>>(*a, w.rec, w.clist, w.ccount, reinterpret_cast<float *>(w.vrec), tw, th);
+        rc = a->v_means2d_abs ? launch(raster2dgs_bwd_kernel<true, 256, 3>, 2 * sizeof(BwdStageT<256>))
+                              : launch(raster2dgs_bwd_kernel<false, 256, 3>, 2 * sizeof(BwdStageT<256>));
     }
+    if (rc) return rc;
     GSSDF_LAUNCH_OK("raster2dgs_bwd_kernel");
     if (a->prof_stop) GSSDF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->prof_stop, st));
     raster_bwd_finalize_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, w.vrec);
