@@ -517,38 +517,19 @@ def main():
     # compute that does not depend on them -- the hash-table + decoder segment (61 MB) under the render backward [D] of the same step,
     # the splat segment (236 MB) under stage [A] of the NEXT step. Each segment's Adam update (grad_scale = 1 / world) runs as soon as its
     # reduction is complete: SDF groups right after the step, splat groups just before the next render touches the splats.
-    from gssdf_b200 import parallel
-    xchg = parallel.GradientExchange()
-    hook = xchg.on_sdf_grads_ready if world > 1 else None
-    pending = {"splat": False}
-
-    def pre_render():
-        xchg.before_render()
-        if pending["splat"]:
-            T.adam_splat(1.0 / world)
-            pending["splat"] = False
-
-    pre = pre_render if world > 1 else None
-
-    from gssdf_b200 import densify
+    from gssdf_b200 import densify, parallel
+    DP = parallel.DataParallelStep(T, world)  # gssdf_b200/parallel.py: the step + its two overlapped all-reduces + per-segment Adam
     DEN = densify.Densifier(T, num_train_data=n_cams, sh_degree=deg)
 
-    def after_step():
-        DEN.update_state()  # NeuralGS::update_state: per-iteration densification statistics (the every-100-iterations surgery is not timed)
-        if world > 1:
-            xchg.finish_step(T.flat_grad[:n_splat_grad])  # splat all-reduce in flight; returns once the SDF segment is reduced
-            pending["splat"] = True
-            T.adam_sdf(1.0 / world)
-        else:
-            T.adam_all()
+    def pre_render():
+        DP.flush()
 
     def step_resident(i):
         V, Kc = dev_cams[i % n_cams]
         randn_buf.normal_()  # the reference draws randns on the device every render (Projection.cpp:728)
         ray_xyz, ray_gt, ray_cnt = SP.draw(i)
-        loss, _sdf_loss = T.train_step(V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook, before_render=pre,
-                                       ray_n_live=ray_cnt)
-        after_step()
+        loss, _sdf_loss = DP.step(V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf, ray_n_live=ray_cnt)
+        DEN.update_state()  # NeuralGS::update_state: per-iteration densification statistics (the every-100-iterations surgery is not timed)
         return loss
 
     # end-to-end path: every step's inputs (camera pose, intrinsics, ground-truth image) come from pinned HOST memory and the loss is
@@ -578,10 +559,9 @@ def main():
         cur.wait_event(sl["ready"])
         randn_buf.normal_()
         ray_xyz, ray_gt, ray_cnt = SP.draw(i)
-        loss, _sdf_loss = T.train_step(sl["V"], sl["K"], sl["gt"], ray_xyz, ray_gt, randn_buf, on_sdf_grads_ready=hook, before_render=pre,
-                                       ray_n_live=ray_cnt)
+        loss, _sdf_loss = DP.step(sl["V"], sl["K"], sl["gt"], ray_xyz, ray_gt, randn_buf, ray_n_live=ray_cnt)
         sl["free"].record(cur)
-        after_step()
+        DEN.update_state()
         loss_host.copy_(loss, non_blocking=True)
         cur.synchronize()  # the caller reads the loss every step (neural_mapping.cpp:505-514)
         return float(loss_host[0])

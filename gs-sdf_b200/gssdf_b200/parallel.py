@@ -82,3 +82,45 @@ class GradientExchange:
         self.before_render()
         while self._sdf:
             self._sdf.pop().wait()
+
+
+class DataParallelStep:
+    """One data-parallel training step around a trainer object (render.GsSdfTrainer, or any object with the same five members):
+
+        trainer.train_step(*args, on_sdf_grads_ready=..., before_render=..., **kw)   writes the flat gradient [splat segment | SDF segment]
+        trainer.flat_grad, trainer.t0                                               t0 = first element of the SDF segment
+        trainer.adam_sdf(grad_scale), trainer.adam_splat(grad_scale), trainer.adam_all(grad_scale)
+
+    Single process: train_step then adam_all. world > 1: the two all-reduces of GradientExchange, and each segment's Adam update (with
+    grad_scale = 1 / world: the reduced gradient is a sum of per-rank means) as soon as its reduction is complete -- SDF groups right
+    after the step, splat groups just before the next render touches the splats (the splat all-reduce runs under the next step's
+    sample generation + SDF stage). Every rank applies the same update to its replica. Call flush() before reading parameters or
+    stopping a timer: it completes the last step's splat update."""
+
+    def __init__(self, trainer, world=None):
+        self.T = trainer
+        self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        self.x = GradientExchange()
+        self._pending_splat = False
+
+    def _before_render(self):
+        self.x.before_render()
+        if self._pending_splat:
+            self.T.adam_splat(1.0 / self.world)
+            self._pending_splat = False
+
+    def step(self, *args, **kw):
+        T = self.T
+        if self.world <= 1:
+            out = T.train_step(*args, **kw)
+            T.adam_all(1.0)
+            return out
+        out = T.train_step(*args, on_sdf_grads_ready=self.x.on_sdf_grads_ready, before_render=self._before_render, **kw)
+        self.x.finish_step(T.flat_grad[:T.t0])  # splat all-reduce in flight; returns once the SDF segment is reduced
+        self._pending_splat = True
+        T.adam_sdf(1.0 / self.world)
+        return out
+
+    def flush(self):
+        if self.world > 1:
+            self._before_render()

@@ -100,3 +100,92 @@ def test_gradient_exchange_overlap_protocol_world2():
     expect = [3.0, 30.0, 6.0, 32.0, 9.0, 34.0]
     for rank, seen in res:
         assert seen == expect, (rank, seen)
+
+
+class _FakeTrainer:
+    """CPU stand-in with the five members parallel.DataParallelStep needs; 'Adam' is plain SGD so the expected result is easy to state."""
+
+    def __init__(self, rank, n_splat=64, n_sdf=24):
+        self.rank, self.t0 = rank, n_splat
+        self.flat_grad = torch.zeros(n_splat + n_sdf)
+        self.params = torch.zeros(n_splat + n_sdf)
+        self.calls = []
+
+    def train_step(self, step, on_sdf_grads_ready=None, before_render=None):
+        g = self.flat_grad
+        assert float(g[self.t0:].abs().max()) == 0.0, "the SDF segment must have been consumed (zeroed) by adam_sdf"
+        g[self.t0:] += (self.rank + 1) * (step + 1)                       # [A]: SDF stage on the ray samples
+        if before_render is not None:
+            before_render()                                               # previous splat all-reduce + splat Adam complete here
+        assert float(g[:self.t0].abs().max()) == 0.0, "the splat segment must have been consumed by adam_splat"
+        g[self.t0:] += 0.5 * (self.rank + 1)                              # [C]
+        if on_sdf_grads_ready is not None:
+            on_sdf_grads_ready(g[self.t0:])
+        g[:self.t0] += 10 * (self.rank + 1) + step                        # [D]
+        return step
+
+    def _sgd(self, sl, scale):
+        self.params[sl] -= 0.1 * scale * self.flat_grad[sl]
+        self.flat_grad[sl] = 0
+
+    def adam_sdf(self, scale=1.0):
+        self.calls.append("sdf")
+        self._sgd(slice(self.t0, None), scale)
+
+    def adam_splat(self, scale=1.0):
+        self.calls.append("splat")
+        self._sgd(slice(0, self.t0), scale)
+
+    def adam_all(self, scale=1.0):
+        self.calls.append("all")
+        self._sgd(slice(0, None), scale)
+
+
+def _dp_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    from gssdf_b200 import parallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    T = _FakeTrainer(rank)
+    DP = parallel.DataParallelStep(T)
+    for step in range(3):
+        DP.step(step)
+    DP.flush()
+    out.put((rank, T.params.clone(), list(T.calls)))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_step_matches_mean_gradient_world2():
+    """DataParallelStep on 2 gloo ranks == one process stepping with the rank-averaged gradient; both replicas end bit-identical."""
+    from gssdf_b200 import parallel
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    # single-process reference with the mean of the two ranks' gradients
+    ref = torch.zeros(64 + 24)
+    for step in range(3):
+        g = torch.zeros(64 + 24)
+        for rank in range(2):
+            g[64:] += ((rank + 1) * (step + 1) + 0.5 * (rank + 1)) / 2
+            g[:64] += (10 * (rank + 1) + step) / 2
+        ref -= 0.1 * g
+    for rank, params, calls in res:
+        assert torch.allclose(params, ref, rtol=1e-6, atol=1e-7), (rank, params[:2], ref[:2], params[-2:], ref[-2:])
+        assert calls == ["sdf", "splat", "sdf", "splat", "sdf", "splat"], calls
+    assert torch.equal(res[0][1], res[1][1])
+    # single process: one fused update per step
+    T = _FakeTrainer(0)
+    DP = parallel.DataParallelStep(T, world=1)
+    DP.step(0)
+    DP.flush()
+    assert T.calls == ["all"]
