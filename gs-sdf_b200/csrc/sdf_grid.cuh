@@ -98,6 +98,35 @@ __device__ __forceinline__ float2 encode_level(const __half2 *__restrict__ table
     return __half22float2(r);
 }
 
+// The 8 interpolation corners of one (point, level): table entry index and value, corner id bit d set <=> +1 along dimension d.
+// Every backward below needs exactly these 8 entries (the dy_dx finite differences of grid.h:170-211 pair them up along one dimension),
+// so they are gathered ONCE per pass instead of once per (gradient dimension, corner pair): 8 gathers / 8 index hashes instead of 24.
+struct Corners {
+    uint32_t idx[8];
+    float2 val[8];
+};
+__device__ __forceinline__ void load_corners(const __half2 *__restrict__ t, uint32_t hs, uint32_t res, const LevelPos &p, bool want_val, Corners &c) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        c.idx[k] = grid_index(hs, res, p.pg[0] + (k & 1), p.pg[1] + ((k >> 1) & 1), p.pg[2] + ((k >> 2) & 1));
+    if (want_val) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c.val[k] = __half22float2(__ldg(t + c.idx[k]));
+    }
+}
+// corner pair of (gradient dimension gd, combination idx of the two other dimensions): left has bit gd clear, right = left | 1 << gd;
+// wt = product of the other dimensions' interpolation weights (same multiplication order as grid.h:186-201)
+__device__ __forceinline__ int pair_left(int gd, int idx, const LevelPos &p, float &wt) {
+    int cl = 0;
+#pragma unroll
+    for (int nd = 0; nd < 2; ++nd) {
+        const int d = nd >= gd ? nd + 1 : nd;
+        if ((idx & (1 << nd)) == 0) wt *= 1.f - p.pos[d];
+        else { wt *= p.pos[d]; cl |= 1 << d; }
+    }
+    return cl;
+}
+
 // backward of one (point, level): scatter the table gradient (optional) and return dL/dx contribution (optional)
 __device__ __forceinline__ void encode_level_bwd(const __half2 *__restrict__ table, float *__restrict__ table_grad, const GridGeom &g,
                                                  int lvl, const float x[3], float g0, float g1, bool want_dx, float dx[3]) {
@@ -105,25 +134,22 @@ __device__ __forceinline__ void encode_level_bwd(const __half2 *__restrict__ tab
     const LevelPos p = level_pos(x, g.scale[lvl]);
     // binding rounding points: dL/dy -> half, x128 in half (TB/tcnn_binding.cpp:133)
     const __half2 gh = __hmul2(__floats2half2_rn(g0, g1), __float2half2_rn(128.f));
+    Corners c;
+    load_corners(table + g.offset[lvl], hs, g.res[lvl], p, want_dx, c);
     if (table_grad) {
         float *tg = table_grad + 2 * (size_t)g.offset[lvl];
 #pragma unroll
         for (int idx = 0; idx < 8; ++idx) {
             float wt = 1.f;
-            uint32_t c[3];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                if ((idx & (1 << d)) == 0) { wt *= 1.f - p.pos[d]; c[d] = p.pg[d]; }
-                else { wt *= p.pos[d]; c[d] = p.pg[d] + 1; }
-            }
+            for (int d = 0; d < 3; ++d) wt *= (idx & (1 << d)) == 0 ? 1.f - p.pos[d] : p.pos[d];
             const float2 v = __half22float2(__hmul2(__float2half2_rn(wt), gh));  // (GRAD_T)weight * grad, grid.h:247
-            const size_t e = 2 * (size_t)grid_index(hs, g.res[lvl], c[0], c[1], c[2]);
             // one 8-byte vector RED per corner (red.global.add.v2.f32, sm_90+); table_grad is 8-byte aligned (checked on the host)
-            if (v.x != 0.f || v.y != 0.f) atomicAdd(reinterpret_cast<float2 *>(tg + e), make_float2(v.x * (1.f / 128.f), v.y * (1.f / 128.f)));
+            if (v.x != 0.f || v.y != 0.f)
+                atomicAdd(reinterpret_cast<float2 *>(tg + 2 * (size_t)c.idx[idx]), make_float2(v.x * (1.f / 128.f), v.y * (1.f / 128.f)));
         }
     }
     if (want_dx) {  // dy_dx (grid.h:170-211) folded with kernel_grid_backward_input (:323-349)
-        const __half2 *t = table + g.offset[lvl];
         const float2 ghf = __half22float2(gh);
 #pragma unroll
         for (int gd = 0; gd < 3; ++gd) {
@@ -131,19 +157,9 @@ __device__ __forceinline__ void encode_level_bwd(const __half2 *__restrict__ tab
 #pragma unroll
             for (int idx = 0; idx < 4; ++idx) {
                 float wt = g.scale[lvl];
-                uint32_t c[3];
-#pragma unroll
-                for (int nd = 0; nd < 2; ++nd) {
-                    const int d = nd >= gd ? nd + 1 : nd;
-                    if ((idx & (1 << nd)) == 0) { wt *= 1.f - p.pos[d]; c[d] = p.pg[d]; }
-                    else { wt *= p.pos[d]; c[d] = p.pg[d] + 1; }
-                }
-                c[gd] = p.pg[gd];
-                const float2 l = __half22float2(__ldg(t + grid_index(hs, g.res[lvl], c[0], c[1], c[2])));
-                c[gd] = p.pg[gd] + 1;
-                const float2 r = __half22float2(__ldg(t + grid_index(hs, g.res[lvl], c[0], c[1], c[2])));
-                acc0 += wt * (r.x - l.x);
-                acc1 += wt * (r.y - l.y);
+                const int cl = pair_left(gd, idx, p, wt), cr = cl | (1 << gd);
+                acc0 += wt * (c.val[cr].x - c.val[cl].x);
+                acc1 += wt * (c.val[cr].y - c.val[cl].y);
             }
             dx[gd] = (ghf.x * acc0 + ghf.y * acc1) * (1.f / 128.f);
         }
@@ -155,14 +171,19 @@ __device__ __forceinline__ void encode_level_bwd(const __half2 *__restrict__ tab
 //   cc[3]    : dL / d(dL/dx) in the units of x01 (cotangent of the first backward's input-gradient output)
 // Writes r[2] = (half)(sum_d dy_dx[f][d] * cc[d]) (kernel_grid_backward_input_backward_dLdoutput, grid.h:624-647) and scatters
 // the table gradient of kernel_grid_backward_input_backward_grid (grid.h:352-456): per grad_dim and corner pair
-// (half)(-+ scale * cc[gd] * w) * dL_dy_half, divided by the loss scale (TB/tcnn_binding.cpp:151-192). fp32 vector REDs.
+// (half)(-+ scale * cc[gd] * w) * dL_dy_half, divided by the loss scale (TB/tcnn_binding.cpp:151-192). Every corner takes part in three
+// pairs (one per gradient dimension): its three half-rounded contributions are summed in fp32 and leave as ONE vector RED per corner
+// (8 instead of the reference's 24 half atomics per (point, level)).
 __device__ __forceinline__ void encode_level_bwd2(const __half2 *__restrict__ table, float *__restrict__ table_grad, const GridGeom &g,
                                                   int lvl, const float x[3], float dfeat0, float dfeat1, const float cc[3], float r[2]) {
     const uint32_t hs = g.offset[lvl + 1] - g.offset[lvl];
     const LevelPos p = level_pos(x, g.scale[lvl]);
     const __half2 gh = __hmul2(__floats2half2_rn(dfeat0, dfeat1), __float2half2_rn(128.f));
-    const __half2 *t = table + g.offset[lvl];
-    float *tg = table_grad ? table_grad + 2 * (size_t)g.offset[lvl] : nullptr;
+    Corners c;
+    load_corners(table + g.offset[lvl], hs, g.res[lvl], p, true, c);
+    float2 tacc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tacc[k] = make_float2(0.f, 0.f);
     float r0 = 0.f, r1 = 0.f;
 #pragma unroll
     for (int gd = 0; gd < 3; ++gd) {
@@ -171,28 +192,26 @@ __device__ __forceinline__ void encode_level_bwd2(const __half2 *__restrict__ ta
 #pragma unroll
         for (int idx = 0; idx < 4; ++idx) {
             float wd = g.scale[lvl], w = grad_in;  // same multiplication order as grid.h:186-201 (dy_dx) and :430-446 (grid gradient)
-            uint32_t c[3];
-#pragma unroll
-            for (int nd = 0; nd < 2; ++nd) {
-                const int d = nd >= gd ? nd + 1 : nd;
-                if ((idx & (1 << nd)) == 0) { wd *= 1.f - p.pos[d]; w *= 1.f - p.pos[d]; c[d] = p.pg[d]; }
-                else { wd *= p.pos[d]; w *= p.pos[d]; c[d] = p.pg[d] + 1; }
-            }
-            c[gd] = p.pg[gd];
-            const uint32_t il = grid_index(hs, g.res[lvl], c[0], c[1], c[2]);
-            c[gd] = p.pg[gd] + 1;
-            const uint32_t ir = grid_index(hs, g.res[lvl], c[0], c[1], c[2]);
-            const float2 l = __half22float2(__ldg(t + il)), rr = __half22float2(__ldg(t + ir));
-            acc0 += wd * (rr.x - l.x);
-            acc1 += wd * (rr.y - l.y);
-            if (tg) {
+            const int cl = pair_left(gd, idx, p, wd);
+            (void)pair_left(gd, idx, p, w);
+            const int cr = cl | (1 << gd);
+            acc0 += wd * (c.val[cr].x - c.val[cl].x);
+            acc1 += wd * (c.val[cr].y - c.val[cl].y);
+            if (table_grad) {
                 const float2 vl = __half22float2(__hmul2(__float2half2_rn(-w), gh)), vr = __half22float2(__hmul2(__float2half2_rn(w), gh));
-                if (vl.x != 0.f || vl.y != 0.f) atomicAdd(reinterpret_cast<float2 *>(tg + 2 * (size_t)il), make_float2(vl.x * (1.f / 128.f), vl.y * (1.f / 128.f)));
-                if (vr.x != 0.f || vr.y != 0.f) atomicAdd(reinterpret_cast<float2 *>(tg + 2 * (size_t)ir), make_float2(vr.x * (1.f / 128.f), vr.y * (1.f / 128.f)));
+                tacc[cl].x += vl.x; tacc[cl].y += vl.y;
+                tacc[cr].x += vr.x; tacc[cr].y += vr.y;
             }
         }
         r0 += acc0 * cc[gd];
         r1 += acc1 * cc[gd];
+    }
+    if (table_grad) {
+        float *tg = table_grad + 2 * (size_t)g.offset[lvl];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (tacc[k].x != 0.f || tacc[k].y != 0.f)
+                atomicAdd(reinterpret_cast<float2 *>(tg + 2 * (size_t)c.idx[k]), make_float2(tacc[k].x * (1.f / 128.f), tacc[k].y * (1.f / 128.f)));
     }
     r[0] = __half2float(__float2half_rn(r0));
     r[1] = __half2float(__float2half_rn(r1));
