@@ -514,16 +514,22 @@ sdf_bwd_tc_kernel(const gssdf_sdf_bwd_args a, const TcLossArgs lo, const GridGeo
         }
         __syncthreads();
         // -- pass A: g (x01 units) = tcnn input gradient with cotangent dfeat, summed over the levels
-#pragma unroll 1
-        for (int task = tid; task < TM * kLevels; task += NT) {
-            const int c = task % TM, lvl = task / TM;
+        {   // NT is a multiple of TM: a thread's tasks all belong to the same point c = tid % TM (levels tid / TM, + NT / TM, ...), so its
+            // level contributions are summed in registers and leave as 3 shared atomics per thread instead of 3 per (point, level)
+            static_assert(NT % TM == 0, "thread -> point mapping of the analytic pass");
+            const int c = tid % TM;
             if (c < nc) {
-                float x[3], dx[3] = {0.f, 0.f, 0.f};
+                float x[3], acc[3] = {0.f, 0.f, 0.f};
                 load_x(a.net, a.x, s_tbase[c / PT] + c % PT, a.n, a.delta, x);
-                encode_level_bwd(table, nullptr, g, lvl, x, gf[c * 33 + 2 * lvl], gf[c * 33 + 2 * lvl + 1], true, dx);
-                atomicAdd(&s_dx[c * 3 + 0], dx[0]);
-                atomicAdd(&s_dx[c * 3 + 1], dx[1]);
-                atomicAdd(&s_dx[c * 3 + 2], dx[2]);
+#pragma unroll 1
+                for (int lvl = tid / TM; lvl < kLevels; lvl += NT / TM) {
+                    float dx[3] = {0.f, 0.f, 0.f};
+                    encode_level_bwd(table, nullptr, g, lvl, x, gf[c * 33 + 2 * lvl], gf[c * 33 + 2 * lvl + 1], true, dx);
+                    acc[0] += dx[0]; acc[1] += dx[1]; acc[2] += dx[2];
+                }
+                atomicAdd(&s_dx[c * 3 + 0], acc[0]);
+                atomicAdd(&s_dx[c * 3 + 1], acc[1]);
+                atomicAdd(&s_dx[c * 3 + 2], acc[2]);
             }
         }
         __syncthreads();
