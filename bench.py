@@ -382,7 +382,7 @@ def main():
     ap.add_argument("--same-cameras", action="store_true", help="N>1: every rank renders the same camera poses (identical work per rank); "
                     "default: rank r renders its own poses")
     ap.add_argument("--no-stock-cuda", action="store_true", help="skip the reference-fork CUDA leg (oracle/_ref/gsplat_ref.so)")
-    ap.add_argument("--no-l2-persist", action="store_true", help="A/B: do not pin the fp16 hash-table shadow in L2")
+    ap.add_argument("--l2-persist", action="store_true", help="A/B: pin the fp16 hash-table shadow in L2 (gssdf_l2_persist); measured: no effect")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -437,7 +437,7 @@ def main():
                                 sh_degree=deg, origin=(0.0, 0.0, 0.0),
                                 map_size=14.0, eikonal_mode=(1 if eikonal == "analytic" and sdf_cfg["hidden_dim"] == 64 else 0),
                                 normal_weight=0.01, isotropic_weight=0.05)  # config/base.yaml:43-46
-        T.l2_persist = not args.no_l2_persist
+        T.l2_persist = args.l2_persist
         gen = torch.Generator(dev).manual_seed(5)  # replicated parameters: same on every rank
         table = (torch.rand(T.n_table, device=dev, generator=gen) * 2 - 1) * 1e-4  # tcnn grid init U(+-1e-4) (grid.h:1059-1062)
         chunks, dims = [], [32] + [sdf_cfg["hidden_dim"]] * (1 + sdf_cfg["n_hidden"]) + [2]

@@ -97,16 +97,47 @@ __device__ __forceinline__ void voxel_center(int x, int y, int z, int level, flo
     vc[2] = fmaf(r, fmaf(2.0f, (float)z, 1.0f), -1.0f);
 }
 
+// The octree is stored breadth-first, so a PREFIX of its node array is its top levels: the first `n_cached` nodes (child mask + exsum) are
+// staged in shared memory per CTA (the whole tree for the 12 k-node box scene = 60 KB), deeper nodes are read through L1/L2.
+struct TreeView {
+    const uint8_t *oct_s;
+    const int32_t *ex_s;
+    int n_cached;
+    const uint8_t *oct_g;
+    const int32_t *ex_g;
+    __device__ __forceinline__ unsigned bits(int node) const { return node < n_cached ? oct_s[node] : __ldg(oct_g + node); }
+    __device__ __forceinline__ int exsum(int node) const { return node < n_cached ? ex_s[node] : __ldg(ex_g + node); }
+};
+constexpr int kRayThreads = 32;           // one warp per CTA: a few thousand rays spread over (almost) every SM
+constexpr int kTreeCacheNodes = 32 * 1024;  // 160 KB of shared memory at most
+
+__device__ __forceinline__ TreeView stage_tree(const gssdf_octree &t, int n_cached, unsigned char *smem) {
+    int32_t *ex = reinterpret_cast<int32_t *>(smem);
+    uint8_t *oc = smem + (size_t)n_cached * 4;
+    for (int i = threadIdx.x; i < n_cached; i += blockDim.x) { ex[i] = __ldg(t.exsum + i); oc[i] = __ldg(t.octree + i); }
+    __syncthreads();
+    return TreeView{oc, ex, n_cached, t.octree, t.exsum};
+}
+
 // Depth-first traversal of one ray. emit(pidx, entry, exit) is called for every leaf-level hit in the reference's nugget order.
+// per-level traversal frames of the CTA's rays, in shared memory (indexed by the dynamic stack depth: registers cannot hold them, local
+// memory would put every push / pop through L1): [level][thread] -> conflict-free
+struct RayStack {
+    int ord[kMaxOctLevel][kRayThreads];        // node
+    uint32_t todo[kMaxOctLevel][kRayThreads];  // remaining children in visiting order (8 x 4 bits, 0xF = none)
+    short fx[kMaxOctLevel][kRayThreads], fy[kMaxOctLevel][kRayThreads], fz[kMaxOctLevel][kRayThreads];  // voxel coordinates
+};
+
 template <typename Emit>
-__device__ __forceinline__ void traverse(const gssdf_octree &t, const RayCtx &c, Emit emit) {
-    const int L = t.level;
-    // per-level frame: node, voxel coordinates, remaining children in visiting order (8 x 4 bits, 0xF = none)
-    int ord[kMaxOctLevel];
-    short fx[kMaxOctLevel], fy[kMaxOctLevel], fz[kMaxOctLevel];
-    uint32_t todo[kMaxOctLevel];
+__device__ __forceinline__ void traverse(const gssdf_octree &t, const TreeView &tv, RayStack &S, const RayCtx &c, Emit emit) {
+    const int L = t.level, me = threadIdx.x;
+#define ord(l) S.ord[l][me]
+#define todo(l) S.todo[l][me]
+#define fx(l) S.fx[l][me]
+#define fy(l) S.fy[l][me]
+#define fz(l) S.fz[l][me]
     auto open = [&](int lvl, int node, int x, int y, int z) {  // push a node whose voxel the ray touches (depth != 0)
-        const unsigned bits = __ldg(t.octree + node);
+        const unsigned bits = tv.bits(node);
         const float scale = 1.0f / (float)(1 << lvl);  // subdivide_cuda_kernel:226-237 (the 0.5 literals are doubles there)
         const double hx = (double)fmaf(0.5f, c.o[0], 0.5f) - (double)scale * ((double)x + 0.5);
         const double hy = (double)fmaf(0.5f, c.o[1], 0.5f) - (double)scale * ((double)y + 0.5);
@@ -120,7 +151,7 @@ __device__ __forceinline__ void traverse(const gssdf_octree &t, const RayCtx &c,
             if (bits & (1u << j)) { list |= j << (4 * k); ++k; }
         }
         for (; k < 8; ++k) list |= 0xFu << (4 * k);
-        ord[lvl] = node; fx[lvl] = (short)x; fy[lvl] = (short)y; fz[lvl] = (short)z; todo[lvl] = list;
+        ord(lvl) = node; fx(lvl) = (short)x; fy(lvl) = (short)y; fz(lvl) = (short)z; todo(lvl) = list;
     };
     {
         float vc[3], r;
@@ -135,12 +166,14 @@ __device__ __forceinline__ void traverse(const gssdf_octree &t, const RayCtx &c,
     }
     int top = 0;
     while (top >= 0) {
-        const unsigned j = todo[top] & 0xFu;
+        const uint32_t td = todo(top);
+        const unsigned j = td & 0xFu;
         if (j == 0xFu) { --top; continue; }
-        todo[top] = (todo[top] >> 4) | 0xF0000000u;
-        const unsigned bits = __ldg(t.octree + ord[top]);
-        const int child = __ldg(t.exsum + ord[top]) + __popc(bits & ((2u << j) - 1u));
-        const int x = (fx[top] << 1) | (int)((j >> 2) & 1u), y = (fy[top] << 1) | (int)((j >> 1) & 1u), z = (fz[top] << 1) | (int)(j & 1u);
+        todo(top) = (td >> 4) | 0xF0000000u;
+        const int node = ord(top);
+        const unsigned bits = tv.bits(node);
+        const int child = tv.exsum(node) + __popc(bits & ((2u << j) - 1u));
+        const int x = (fx(top) << 1) | (int)((j >> 2) & 1u), y = (fy(top) << 1) | (int)((j >> 1) & 1u), z = (fz(top) << 1) | (int)(j & 1u);
         float vc[3], r;
         voxel_center(x, y, z, top + 1, vc, r);
         if (top + 1 == L) {  // decide_cuda_kernel (with exit) :180-218
@@ -151,6 +184,11 @@ __device__ __forceinline__ void traverse(const gssdf_octree &t, const RayCtx &c,
             open(top, child, x, y, z);
         }
     }
+#undef ord
+#undef todo
+#undef fx
+#undef fy
+#undef fz
 }
 
 __device__ __forceinline__ RayCtx make_ray(const gssdf_octree &t, const float *origins, const float *dirs, int64_t i) {
@@ -167,22 +205,29 @@ __device__ __forceinline__ RayCtx make_ray(const gssdf_octree &t, const float *o
     return c;
 }
 
-__global__ void __launch_bounds__(128) ray_count_kernel(const gssdf_octree t, int64_t n, const float *origins, const float *dirs, int32_t *cnt) {
-    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+__global__ void __launch_bounds__(kRayThreads) ray_count_kernel(const gssdf_octree t, int n_cached, int64_t n, const float *origins, const float *dirs,
+                                                                int32_t *cnt) {
+    extern __shared__ __align__(16) unsigned char s_tree[];
+    __shared__ RayStack s_stack;
+    const TreeView tv = stage_tree(t, n_cached, s_tree);
+    const int64_t i = (int64_t)blockIdx.x * kRayThreads + threadIdx.x;
     if (i >= n) return;
     const RayCtx c = make_ray(t, origins, dirs, i);
     int k = 0;
-    traverse(t, c, [&](int, float, float) { ++k; });
+    traverse(t, tv, s_stack, c, [&](int, float, float) { ++k; });
     cnt[i] = k;
 }
 
-__global__ void __launch_bounds__(128) ray_write_kernel(const gssdf_octree t, int64_t n, const float *origins, const float *dirs, const int32_t *off,
-                                                        int64_t cap, int32_t *ridx, int32_t *pidx, float *depth) {
-    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+__global__ void __launch_bounds__(kRayThreads) ray_write_kernel(const gssdf_octree t, int n_cached, int64_t n, const float *origins, const float *dirs,
+                                                                const int32_t *off, int64_t cap, int32_t *ridx, int32_t *pidx, float *depth) {
+    extern __shared__ __align__(16) unsigned char s_tree[];
+    __shared__ RayStack s_stack;
+    const TreeView tv = stage_tree(t, n_cached, s_tree);
+    const int64_t i = (int64_t)blockIdx.x * kRayThreads + threadIdx.x;
     if (i >= n) return;
     const RayCtx c = make_ray(t, origins, dirs, i);
     int64_t pos = off[i];
-    traverse(t, c, [&](int p, float en, float ex) {
+    traverse(t, tv, s_stack, c, [&](int p, float en, float ex) {
         if (pos < cap) {
             ridx[pos] = (int32_t)i;
             if (pidx) pidx[pos] = p;
@@ -193,20 +238,28 @@ __global__ void __launch_bounds__(128) ray_write_kernel(const gssdf_octree t, in
     });
 }
 
-// exclusive scan of int32 counts by ONE CTA (n is a few thousand rays / ~1e5 candidates): out[i] = sum_{j<i} in[j]; total -> *total_out,
-// *overflow |= total > cap. (Also used for the keep flags of the sample assembly.)
+// exclusive scan of int32 counts by ONE CTA, 8 items per thread per sweep (8192 per sweep: a few thousand rays / ~1e5 candidates take
+// 1-20 sweeps): out[i] = sum_{j<i} in[j]; total -> *total_out (clamped to cap), *overflow = 1 if total > cap. Also used for the keep
+// flags of the sample assembly and the gate compaction.
 __global__ void __launch_bounds__(1024) scan_kernel(const int32_t *in, int32_t *out, int64_t n, const int32_t *n_dyn, int64_t cap, int32_t *total_out,
                                                     int32_t *overflow) {
+    constexpr int ITEMS = 8;
     __shared__ int32_t s_warp[32];
     __shared__ int32_t s_carry;
     if (n_dyn) n = min(n, (int64_t)*n_dyn);
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        const int32_t v = i < n ? in[i] : 0;
-        int32_t x = v;
+    for (int64_t base = 0; base < n; base += 1024 * ITEMS) {
+        const int64_t i0 = base + (int64_t)threadIdx.x * ITEMS;
+        int32_t v[ITEMS];
+        int32_t tsum = 0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            v[k] = i0 + k < n ? in[i0 + k] : 0;
+            tsum += v[k];
+        }
+        int32_t x = tsum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -225,7 +278,12 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int32_t *in, int32_t *
         }
         __syncthreads();
         const int32_t carry = s_carry, wpre = warp ? s_warp[warp - 1] : 0;
-        if (i < n) out[i] = carry + wpre + x - v;
+        int32_t run = carry + wpre + x - tsum;  // exclusive prefix of this thread's first item
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            if (i0 + k < n) out[i0 + k] = run;
+            run += v[k];
+        }
         __syncthreads();
         if (threadIdx.x == 1023) s_carry = carry + wpre + x;
         __syncthreads();
@@ -487,11 +545,15 @@ static int raytrace_impl(const gssdf_octree &tree, int64_t n_rays, const float *
     int32_t *cnt = ws, *off = ws + n_rays;
     GSSDF_CUDA_OK(cudaMemsetAsync(n_nuggets, 0, sizeof(int32_t), st));
     if (n_rays == 0 || tree.n_nodes == 0) return GSSDF_OK;
-    ray_count_kernel<<<cdiv(n_rays, 128), 128, 0, st>>>(tree, n_rays, origins, dirs, cnt);
+    const int n_cached = std::min(tree.n_nodes, kTreeCacheNodes);
+    const size_t smem = (size_t)n_cached * 5 + 16;
+    GSSDF_CUDA_OK(cudaFuncSetAttribute(ray_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTreeCacheNodes * 5 + 16));
+    GSSDF_CUDA_OK(cudaFuncSetAttribute(ray_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTreeCacheNodes * 5 + 16));
+    ray_count_kernel<<<cdiv(n_rays, kRayThreads), kRayThreads, smem, st>>>(tree, n_cached, n_rays, origins, dirs, cnt);
     GSSDF_LAUNCH_OK("ray_count_kernel");
     scan_kernel<<<1, 1024, 0, st>>>(cnt, off, n_rays, nullptr, cap, n_nuggets, overflow);
     GSSDF_LAUNCH_OK("scan_kernel");
-    ray_write_kernel<<<cdiv(n_rays, 128), 128, 0, st>>>(tree, n_rays, origins, dirs, off, cap, ridx, pidx, depth);
+    ray_write_kernel<<<cdiv(n_rays, kRayThreads), kRayThreads, smem, st>>>(tree, n_cached, n_rays, origins, dirs, off, cap, ridx, pidx, depth);
     GSSDF_LAUNCH_OK("ray_write_kernel");
     return GSSDF_OK;
 }

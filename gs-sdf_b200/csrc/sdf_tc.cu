@@ -217,10 +217,12 @@ __global__ void __launch_bounds__(256) mlp_pack_kernel(const float *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward: one CTA = one 128-point tile
+// forward: persistent CTAs (two per SM) walk the 128-point tiles. The layout stride n is a CAPACITY (the live count is a device value), so
+// most tiles of a launch can be dead: a dead tile costs one loop iteration here instead of a CTA launch, and TMEM allocation, barrier
+// initialisation and the bias loads happen once per CTA instead of once per tile.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFwdTcThreads)
-sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
+sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g, int64_t n_tiles) {
     constexpr int TM = 128, HID = 64;
     extern __shared__ __align__(128) unsigned char s_tc[];  // (a larger alignment pads the static part and costs the L1 carve-out step)
     unsigned char *sA = s_tc;                    // 32 KB activations hi/mid (off_act); in place across layers
@@ -236,12 +238,8 @@ sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, h = warp >> 2, row = 32 * q + lane;
     const int nh = 1 + a.net.n_hidden;
-    const int64_t base = (int64_t)blockIdx.x * TM;
     const int64_t n_eval = a.n * max(a.n_variants, 1);
     const int64_t n_live = a.n_live ? min((int64_t)*a.n_live, a.n) : a.n;
-    if (base % a.n >= n_live && base % a.n + TM <= a.n) return;  // CTA-uniform: the whole tile is beyond the live rows
-    if (a.skip_base_variant && base + TM <= a.n) return;           // CTA-uniform: only variant-0 evaluations in this tile
-    const int tm = (int)min((int64_t)TM, n_eval - base);
     const __half2 *table = reinterpret_cast<const __half2 *>(a.net.table_half);
     const unsigned char *wimg = reinterpret_cast<const unsigned char *>(a.net.mlp_packed);
 
@@ -253,8 +251,6 @@ sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
         mbar_init(&s_mbar[0], 1);
         mbar_init(&s_mbar[1], 1);
         fence_mbar_init();
-        mbar_arrive_expect_tx(&s_mbar[1], kWImg);
-        bulk_g2s(sW, wimg, kWImg, &s_mbar[1]);
     }
     {
         const float *W = a.net.mlp;
@@ -264,6 +260,21 @@ sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
             W += (size_t)HID * K + HID;
         }
         for (int e = tid; e < 2 * HID + 2; e += kFwdTcThreads) s_wout[e] = __ldg(W + e);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    bool ok = true;
+    uint32_t done_layers = 0;  // layers completed by this CTA so far: both barriers complete one phase per layer
+    for (int64_t tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+    const int64_t base = tile * TM;
+    if (base % a.n >= n_live && base % a.n + TM <= a.n) continue;  // CTA-uniform: the whole tile is beyond the live rows
+    if (a.skip_base_variant && base + TM <= a.n) continue;           // CTA-uniform: only variant-0 evaluations in this tile
+    const int tm = (int)min((int64_t)TM, n_eval - base);
+    if (tid == 0) {  // the previous tile's MMAs are complete (its last commit was waited for): sW is free
+        mbar_arrive_expect_tx(&s_mbar[1], kWImg);
+        bulk_g2s(sW, wimg, kWImg, &s_mbar[1]);
     }
     // 1. encode: 128 points x 16 levels -> features (global, optional) + A operand of layer 0. Branch-free batches of 4 (point,
     //    level) tasks per thread so that 32 table gathers are in flight before the first one is consumed.
@@ -289,21 +300,17 @@ sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
             *reinterpret_cast<__nv_bfloat162 *>(sF + off_feat(p, 2 * lvl, 1)) = __halves2bfloat162(m0, m1);
         }
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = s_tmem;
-    bool ok = true;
     for (int l = 0; l < nh; ++l) {
+        const uint32_t parity = (done_layers + (uint32_t)l) & 1u;
         fence_proxy_async();  // generic-proxy writes of the A operand -> visible to the tensor core
         __syncthreads();
         if (tid == 0) {
-            ok = mbar_wait_bounded(&s_mbar[1], (uint32_t)(l & 1));  // W_l has landed
+            ok = mbar_wait_bounded(&s_mbar[1], parity);  // W_l has landed
             tc_fence_after();
             if (ok) issue_forward_layer(tmem, l, smem_u32(l == 0 ? sF : sA), smem_u32(sL), smem_u32(sW));
             umma_commit(&s_mbar[0]);
         }
-        ok = mbar_wait_bounded(&s_mbar[0], (uint32_t)(l & 1)) && ok;
+        ok = mbar_wait_bounded(&s_mbar[0], parity) && ok;
         if (!ok) break;
         tc_fence_after();
         if (tid == 0 && l + 1 < nh) {  // the MMAs are done with sW: fetch the next layer while the epilogue runs
@@ -330,7 +337,8 @@ sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
         }
         tc_fence_before();
     }
-    __syncthreads();
+    done_layers += (uint32_t)nh;
+    ok = __syncthreads_and(ok);  // (thread 0's barrier waits decide for the CTA)
     if (ok && tid < TM) {
         const int p = tid;
         if (p < tm && (base + p) % a.n < n_live) {
@@ -338,6 +346,9 @@ sdf_fwd_tc_kernel(const gssdf_sdf_fwd_args a, const GridGeom g) {
             if (a.y1) a.y1[base + p] = s_part[p * 2 + 1] + s_part[(TM + p) * 2 + 1] + s_wout[2 * HID + 1];
         }
     }
+    __syncthreads();  // s_part / sF / sA are rewritten by the next tile
+    }  // tile loop
+    tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(64));
     if (!ok) __trap();  // the tensor core / copy engine never signalled: fail loudly rather than return garbage
@@ -1017,7 +1028,11 @@ extern "C" int gssdf_sdf_fwd_tc_launch(const gssdf_sdf_fwd_args *a, const gssdf:
         attr_set = true;
     }
     const int64_t n_tiles = (a->n * (a->n_variants > 1 ? a->n_variants : 1) + 127) / 128;
-    sdf_fwd_tc_kernel<<<(unsigned)n_tiles, kFwdTcThreads, smem, (cudaStream_t)stream>>>(*a, *g);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)2 * sms);  // two ~90 KiB CTAs fit one SM
+    sdf_fwd_tc_kernel<<<grid, kFwdTcThreads, smem, (cudaStream_t)stream>>>(*a, *g, n_tiles);
     GSSDF_LAUNCH_OK("sdf_fwd_tc_kernel");
     return GSSDF_OK;
 }

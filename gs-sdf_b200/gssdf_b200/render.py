@@ -382,7 +382,7 @@ class GsSdfTrainer(GsSdfStep):
         self.keep_shadows = True
         self.t_splat = self.t_sdf = 0
         self._net = None
-        self.l2_persist = True
+        self.l2_persist = False  # A/B on B200: no measurable effect (the 30.5 MB table stays in the 126 MB L2 anyway), so off by default
         self.N_cap = N
         self.set_live(N if n_live is None else n_live)
 

@@ -125,6 +125,9 @@ def test_update_state_grow_prune_reset_match_reference_functions():
     for k in ("grad2d", "count", "vis"):
         assert torch.allclose(D.state[k][:N], ref_state[k], rtol=1e-6, atol=0), k
     # ---- grow (duplicate + split) with the same randn stream
+    # (from here on the restatement starts from the kernel's statistics -- equal to the torch ones to fp32 rounding, checked above -- so that
+    #  both sides take identical decisions and the surgery itself is compared bit for bit)
+    ref_state = {k: D.state[k][:N].clone() for k in ref_state}
     ref = RefGS(T.anchors.clone(), snap(T.params), snap(T.exp_avg), snap(T.exp_avg_sq), {k: v.clone() for k, v in ref_state.items()})
     D.grow_grad2d, D.grow_scale3d = 2e-4, 0.015
     gen_ref = torch.Generator(dev).manual_seed(11)
