@@ -33,7 +33,9 @@ def build(verbose=False, force=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on " + s)
-    subprocess.check_call([nvcc, "-shared", "-o", OUT] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart"])
+    # link next to the target and rename: a concurrent reader (e.g. a gpurun snapshot) never sees a half-written library
+    subprocess.check_call([nvcc, "-shared", "-o", OUT + ".tmp"] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart"])
+    os.replace(OUT + ".tmp", OUT)
     return OUT
 
 
@@ -72,9 +74,10 @@ def build_shim(force=False):
         if p.returncode:
             sys.stderr.write(out)
             raise RuntimeError("g++ failed on " + s_)
-    subprocess.check_call(["/usr/bin/g++", "-shared", "-o", SHIM_OUT] + objs +
+    subprocess.check_call(["/usr/bin/g++", "-shared", "-o", SHIM_OUT + ".tmp"] + objs +
                           [f"-L{HERE}", "-l:libgssdf_b200.so", f"-L{tdir}/lib", "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda",
                            "-ltorch_python", "-L/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{tdir}/lib", "-Wl,-rpath,$ORIGIN"])
+    os.replace(SHIM_OUT + ".tmp", SHIM_OUT)
     return SHIM_OUT
 
 

@@ -15,6 +15,8 @@
 //   4. tile_sort    : one CTA per tile sorts its bin in shared memory (all-ascending bitonic
 //                     network); since the key is unique, ascending order IS the reference order
 //                     (sorted by depth bits, ties in emission = packed-index order).
+#include <algorithm>
+
 #include "common.cuh"
 #include "conic.cuh"
 
@@ -249,12 +251,14 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long *v, int n) {
 template <int S, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 tile_sort_kernel(const TileGeom g, const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys,
-                 int lo, int hi, int64_t isect_cap, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
+                 int lo, int hi, int64_t isect_cap, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids, int n_bins) {
     extern __shared__ __align__(16) unsigned long long s_keys[];
-    const int bin = blockIdx.x;
+    // grid-stride over the bins: the two large tiers are launched with one CTA per SM and usually find no bin of their size at all
+    // (a dedicated CTA per bin cost 50 us per step in launches that exit immediately)
+    for (int bin = blockIdx.x; bin < n_bins; bin += gridDim.x) {
     const int64_t rs = min((int64_t)bin_start[bin], isect_cap), re = min((int64_t)bin_start[bin + 1], isect_cap);
     const int n = (int)(re - rs);
-    if (n <= lo || n > hi) return;
+    if (n <= lo || n > hi) continue;  // CTA-uniform
     unsigned long long *v;
     if (n <= S) {
         for (int i = threadIdx.x; i < n; i += THREADS) s_keys[i] = keys[rs + i];
@@ -270,6 +274,8 @@ tile_sort_kernel(const TileGeom g, const int32_t *__restrict__ bin_start, unsign
         const unsigned long long k = v[i];
         flatten_ids[rs + i] = (int32_t)(uint32_t)(k & 0xffffffffull);
         if (isect_ids) isect_ids[rs + i] = hi_bits | (long long)(k >> 32);
+    }
+    __syncthreads();  // s_keys is reused by the next bin
     }
 }
 
@@ -337,12 +343,15 @@ extern "C" int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t
     constexpr int S0 = 2048, S1 = 8192, S2 = 28672;
     GSSDF_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<S1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1 * 8));
     GSSDF_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<S2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2 * 8));
-    tile_sort_kernel<S0, 256><<<bins, 256, S0 * 8, st>>>(g, bin_start, keys, 0, S0, a->isect_cap, a->isect_ids, a->flatten_ids);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    tile_sort_kernel<S0, 256><<<bins, 256, S0 * 8, st>>>(g, bin_start, keys, 0, S0, a->isect_cap, a->isect_ids, a->flatten_ids, bins);
     GSSDF_LAUNCH_OK("tile_sort_kernel<2048>");
-    tile_sort_kernel<S1, 512><<<bins, 512, S1 * 8, st>>>(g, bin_start, keys, S0, S1, a->isect_cap, a->isect_ids, a->flatten_ids);
+    tile_sort_kernel<S1, 512><<<std::min(bins, 2 * sms), 512, S1 * 8, st>>>(g, bin_start, keys, S0, S1, a->isect_cap, a->isect_ids, a->flatten_ids, bins);
     GSSDF_LAUNCH_OK("tile_sort_kernel<8192>");
-    tile_sort_kernel<S2, 1024><<<bins, 1024, S2 * 8, st>>>(g, bin_start, keys, S1, 0x7fffffff, a->isect_cap, a->isect_ids,
-                                                          a->flatten_ids);
+    tile_sort_kernel<S2, 1024><<<std::min(bins, sms), 1024, S2 * 8, st>>>(g, bin_start, keys, S1, 0x7fffffff, a->isect_cap, a->isect_ids,
+                                                                         a->flatten_ids, bins);
     GSSDF_LAUNCH_OK("tile_sort_kernel<28672>");
     return GSSDF_OK;
 }
