@@ -108,13 +108,15 @@ struct TreeView {
     __device__ __forceinline__ unsigned bits(int node) const { return node < n_cached ? oct_s[node] : __ldg(oct_g + node); }
     __device__ __forceinline__ int exsum(int node) const { return node < n_cached ? ex_s[node] : __ldg(ex_g + node); }
 };
-constexpr int kRayThreads = 32;           // one warp per CTA: a few thousand rays spread over (almost) every SM
-constexpr int kTreeCacheNodes = 32 * 1024;  // 160 KB of shared memory at most
+constexpr int kRayThreads = 64;          // two warps per CTA: a few thousand rays spread over a third of the SMs
+constexpr int kTreeCacheNodes = 4096;    // top of the tree (every ray walks it): 20 KB, staged in ~64 pipelined load rounds per CTA;
+                                         // deeper nodes are touched by few rays each and come through L1 / L2
 
 __device__ __forceinline__ TreeView stage_tree(const gssdf_octree &t, int n_cached, unsigned char *smem) {
     int32_t *ex = reinterpret_cast<int32_t *>(smem);
     uint8_t *oc = smem + (size_t)n_cached * 4;
-    for (int i = threadIdx.x; i < n_cached; i += blockDim.x) { ex[i] = __ldg(t.exsum + i); oc[i] = __ldg(t.octree + i); }
+#pragma unroll 8
+    for (int i = threadIdx.x; i < n_cached; i += kRayThreads) { ex[i] = __ldg(t.exsum + i); oc[i] = __ldg(t.octree + i); }
     __syncthreads();
     return TreeView{oc, ex, n_cached, t.octree, t.exsum};
 }
