@@ -526,10 +526,12 @@ def main():
 
     def step_resident(i):
         V, Kc = dev_cams[i % n_cams]
+        R._mark("step_begin")
         randn_buf.normal_()  # the reference draws randns on the device every render (Projection.cpp:728)
         ray_xyz, ray_gt, ray_cnt = SP.draw(i)
         loss, _sdf_loss = DP.step(V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf, ray_n_live=ray_cnt)
         DEN.update_state()  # NeuralGS::update_state: per-iteration densification statistics (the every-100-iterations surgery is not timed)
+        R._mark("densify_stats")
         return loss
 
     # end-to-end path: every step's inputs (camera pose, intrinsics, ground-truth image) come from pinned HOST memory and the loss is
@@ -645,7 +647,7 @@ def main():
             for (_, a), (name, b) in zip(ev[:-1], ev[1:]):
                 acc.setdefault(name, []).append(a.elapsed_time(b))
         R.stage_events = None
-        stage_ms = {k: float(np.mean(v)) for k, v in acc.items()}
+        stage_ms = {("rng+sample_generation[A0]" if k == "start" else k): float(np.mean(v)) for k, v in acc.items()}
 
     if rank == 0:
         pk, pk_kind = peaks()
