@@ -207,8 +207,18 @@ __device__ __forceinline__ RayCtx make_ray(const gssdf_octree &t, const float *o
     return c;
 }
 
+// ONE traversal per ray in the common case: the count pass also parks the first kStageHits hits of every ray in a per-ray staging slot;
+// after the scan the write pass copies them to their packed positions and re-traverses only the rays with more hits than slots (a ray
+// grazing a wall). A depth ray of the bench scene hits 2.4 leaf voxels on average.
+constexpr int kStageHits = 16;
+struct __align__(16) StagedHit {
+    int32_t pidx;
+    float entry, exit;
+    int32_t pad;
+};
+
 __global__ void __launch_bounds__(kRayThreads) ray_count_kernel(const gssdf_octree t, int n_cached, int64_t n, const float *origins, const float *dirs,
-                                                                int32_t *cnt) {
+                                                                int32_t *cnt, StagedHit *stage) {
     extern __shared__ __align__(16) unsigned char s_tree[];
     __shared__ RayStack s_stack;
     const TreeView tv = stage_tree(t, n_cached, s_tree);
@@ -216,20 +226,28 @@ __global__ void __launch_bounds__(kRayThreads) ray_count_kernel(const gssdf_octr
     if (i >= n) return;
     const RayCtx c = make_ray(t, origins, dirs, i);
     int k = 0;
-    traverse(t, tv, s_stack, c, [&](int, float, float) { ++k; });
+    StagedHit *mine = stage + i * kStageHits;
+    traverse(t, tv, s_stack, c, [&](int p, float en, float ex) {
+        if (k < kStageHits) mine[k] = StagedHit{p, en, ex, 0};
+        ++k;
+    });
     cnt[i] = k;
 }
 
 __global__ void __launch_bounds__(kRayThreads) ray_write_kernel(const gssdf_octree t, int n_cached, int64_t n, const float *origins, const float *dirs,
-                                                                const int32_t *off, int64_t cap, int32_t *ridx, int32_t *pidx, float *depth) {
+                                                                const int32_t *cnt, const int32_t *off, const StagedHit *stage, int64_t cap,
+                                                                int32_t *ridx, int32_t *pidx, float *depth) {
     extern __shared__ __align__(16) unsigned char s_tree[];
     __shared__ RayStack s_stack;
-    const TreeView tv = stage_tree(t, n_cached, s_tree);
     const int64_t i = (int64_t)blockIdx.x * kRayThreads + threadIdx.x;
+    const int k = i < n ? cnt[i] : 0;
+    const bool redo = k > kStageHits;
+    // CTA-uniform: the octree prefix is only staged when one of this CTA's rays has to be traversed again
+    TreeView tv{nullptr, nullptr, 0, t.octree, t.exsum};
+    if (__syncthreads_or(redo)) tv = stage_tree(t, n_cached, s_tree);
     if (i >= n) return;
-    const RayCtx c = make_ray(t, origins, dirs, i);
     int64_t pos = off[i];
-    traverse(t, tv, s_stack, c, [&](int p, float en, float ex) {
+    auto put = [&](int p, float en, float ex) {
         if (pos < cap) {
             ridx[pos] = (int32_t)i;
             if (pidx) pidx[pos] = p;
@@ -237,7 +255,14 @@ __global__ void __launch_bounds__(kRayThreads) ray_write_kernel(const gssdf_octr
             depth[2 * pos + 1] = ex;
         }
         ++pos;
-    });
+    };
+    if (!redo) {
+        const StagedHit *mine = stage + i * kStageHits;
+        for (int j = 0; j < k; ++j) { const StagedHit h = mine[j]; put(h.pidx, h.entry, h.exit); }
+    } else {
+        const RayCtx c = make_ray(t, origins, dirs, i);
+        traverse(t, tv, s_stack, c, put);
+    }
 }
 
 // exclusive scan of int32 counts by ONE CTA, 8 items per thread per sweep (8192 per sweep: a few thousand rays / ~1e5 candidates take
@@ -293,6 +318,52 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int32_t *in, int32_t *
     if (threadIdx.x == 0) {
         *total_out = (int32_t)min((int64_t)s_carry, cap);
         if (s_carry > cap) *overflow = 1;
+    }
+}
+
+// Large inputs (the gate compaction scans ~150 k flags, the sample assembly ~75 k): three parallel launches instead of ~20 dependent sweeps
+// of one CTA: per-chunk sums -> single-CTA scan of the (few) chunk sums -> per-chunk local scan + carry.
+constexpr int kScanChunk = 4096;
+__global__ void __launch_bounds__(512) scan_chunk_sum_kernel(const int32_t *in, int32_t *sums, int64_t n, const int32_t *n_dyn) {
+    if (n_dyn) n = min(n, (int64_t)*n_dyn);
+    const int64_t base = (int64_t)blockIdx.x * kScanChunk;
+    int32_t v = 0;
+    for (int k = threadIdx.x; k < kScanChunk; k += 512) v += base + k < n ? in[base + k] : 0;
+    v = __reduce_add_sync(0xffffffffu, v);
+    __shared__ int32_t s[16];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t t = 0;
+        for (int w = 0; w < 16; ++w) t += s[w];
+        sums[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(512) scan_chunk_apply_kernel(const int32_t *in, int32_t *out, const int32_t *chunk_off, int64_t n, const int32_t *n_dyn) {
+    if (n_dyn) n = min(n, (int64_t)*n_dyn);
+    const int64_t base = (int64_t)blockIdx.x * kScanChunk;
+    if (base >= n) return;
+    __shared__ int32_t s_warp[16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i0 = base + (int64_t)threadIdx.x * 8;
+    int32_t v[8], tsum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] = i0 + k < n ? in[i0 + k] : 0; tsum += v[k]; }
+    int32_t x = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    int32_t wpre = 0;
+    for (int w = 0; w < warp; ++w) wpre += s_warp[w];
+    int32_t run = chunk_off[blockIdx.x] + wpre + x - tsum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (i0 + k < n) out[i0 + k] = run;
+        run += v[k];
     }
 }
 
@@ -517,6 +588,26 @@ extern "C" int gssdf_octree_build_host(gssdf_octree_build_args *a) {
     return GSSDF_OK;
 }
 
+// exclusive scan of in[0..n) (n bounded on the device by *n_dyn): out, total (clamped to cap) and overflow flag. `sums` = scratch of
+// 2 * (n / kScanChunk + 1) int32 (only used for large n).
+static int run_scan(const int32_t *in, int32_t *out, int64_t n, const int32_t *n_dyn, int64_t cap, int32_t *total, int32_t *overflow, int32_t *sums,
+                    cudaStream_t st) {
+    if (n <= 4 * 8192 || !sums) {
+        scan_kernel<<<1, 1024, 0, st>>>(in, out, n, n_dyn, cap, total, overflow);
+        GSSDF_LAUNCH_OK("scan_kernel");
+        return GSSDF_OK;
+    }
+    const int chunks = cdiv(n, kScanChunk);
+    scan_chunk_sum_kernel<<<chunks, 512, 0, st>>>(in, sums, n, n_dyn);
+    GSSDF_LAUNCH_OK("scan_chunk_sum_kernel");
+    scan_kernel<<<1, 1024, 0, st>>>(sums, sums + chunks, chunks, nullptr, cap, total, overflow);
+    GSSDF_LAUNCH_OK("scan_kernel");
+    scan_chunk_apply_kernel<<<chunks, 512, 0, st>>>(in, out, sums + chunks, n, n_dyn);
+    GSSDF_LAUNCH_OK("scan_chunk_apply_kernel");
+    return GSSDF_OK;
+}
+static size_t scan_scratch_bytes(int64_t n) { return align_up((size_t)(2 * (n / kScanChunk + 2)) * 4, 256); }
+
 static int check_tree(const char *who, const gssdf_octree &t) {
     GSSDF_REQUIRE(t.level >= 0 && t.level <= kMaxOctLevel, GSSDF_EINVAL, "%s: octree level out of range", who);
     GSSDF_REQUIRE(t.n_nodes >= 0 && (t.n_nodes == 0 || (t.octree && t.exsum)), GSSDF_EINVAL, "%s: octree / exsum null", who);
@@ -540,22 +631,27 @@ extern "C" int gssdf_octree_query(const gssdf_octree_query_args *a, gssdf_stream
     return GSSDF_OK;
 }
 
-extern "C" size_t gssdf_octree_raytrace_workspace_bytes(int64_t n_rays) { return align_up((size_t)std::max<int64_t>(n_rays, 1) * 8, 256); }
+static size_t ray_ws_bytes(int64_t n_rays) {  // [cnt | off] + the staging slots
+    const size_t n = (size_t)std::max<int64_t>(n_rays, 1);
+    return align_up(n * 8, 256) + align_up(n * kStageHits * sizeof(StagedHit), 256);
+}
+extern "C" size_t gssdf_octree_raytrace_workspace_bytes(int64_t n_rays) { return ray_ws_bytes(n_rays); }
 
 static int raytrace_impl(const gssdf_octree &tree, int64_t n_rays, const float *origins, const float *dirs, int64_t cap, int32_t *ridx, int32_t *pidx,
                          float *depth, int32_t *n_nuggets, int32_t *overflow, int32_t *ws, cudaStream_t st) {
     int32_t *cnt = ws, *off = ws + n_rays;
+    StagedHit *stage = reinterpret_cast<StagedHit *>(reinterpret_cast<unsigned char *>(ws) + align_up((size_t)std::max<int64_t>(n_rays, 1) * 8, 256));
     GSSDF_CUDA_OK(cudaMemsetAsync(n_nuggets, 0, sizeof(int32_t), st));
     if (n_rays == 0 || tree.n_nodes == 0) return GSSDF_OK;
     const int n_cached = std::min(tree.n_nodes, kTreeCacheNodes);
     const size_t smem = (size_t)n_cached * 5 + 16;
     GSSDF_CUDA_OK(cudaFuncSetAttribute(ray_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTreeCacheNodes * 5 + 16));
     GSSDF_CUDA_OK(cudaFuncSetAttribute(ray_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTreeCacheNodes * 5 + 16));
-    ray_count_kernel<<<cdiv(n_rays, kRayThreads), kRayThreads, smem, st>>>(tree, n_cached, n_rays, origins, dirs, cnt);
+    ray_count_kernel<<<cdiv(n_rays, kRayThreads), kRayThreads, smem, st>>>(tree, n_cached, n_rays, origins, dirs, cnt, stage);
     GSSDF_LAUNCH_OK("ray_count_kernel");
     scan_kernel<<<1, 1024, 0, st>>>(cnt, off, n_rays, nullptr, cap, n_nuggets, overflow);
     GSSDF_LAUNCH_OK("scan_kernel");
-    ray_write_kernel<<<cdiv(n_rays, kRayThreads), kRayThreads, smem, st>>>(tree, n_cached, n_rays, origins, dirs, off, cap, ridx, pidx, depth);
+    ray_write_kernel<<<cdiv(n_rays, kRayThreads), kRayThreads, smem, st>>>(tree, n_cached, n_rays, origins, dirs, cnt, off, stage, cap, ridx, pidx, depth);
     GSSDF_LAUNCH_OK("ray_write_kernel");
     return GSSDF_OK;
 }
@@ -579,9 +675,9 @@ static int64_t sample_cand_cap(int64_t n_rays, int64_t nugget_cap, int ns, int n
 
 extern "C" size_t gssdf_sdf_sample_rays_workspace_bytes(int64_t n_rays, int64_t nugget_cap, int32_t ns, int32_t n_free, int32_t n_surface) {
     const int64_t m = sample_cand_cap(n_rays, nugget_cap, ns, n_free, n_surface);
-    // [cnt | off] per ray, nuggets (ridx, depth x2), flags + positions per candidate
-    return align_up((size_t)std::max<int64_t>(n_rays, 1) * 8, 256) + align_up((size_t)nugget_cap * 4, 256) + align_up((size_t)nugget_cap * 8, 256) +
-           2 * align_up((size_t)m * 4, 256);
+    // ray traversal scratch, nuggets (ridx, depth x2), flags + positions per candidate, scan scratch
+    return ray_ws_bytes(n_rays) + align_up((size_t)nugget_cap * 4, 256) + align_up((size_t)nugget_cap * 8, 256) + 2 * align_up((size_t)m * 4, 256) +
+           scan_scratch_bytes(m);
 }
 
 extern "C" int gssdf_sdf_sample_rays(const gssdf_sdf_sample_rays_args *a, gssdf_stream_t stream) {
@@ -603,7 +699,7 @@ extern "C" int gssdf_sdf_sample_rays(const gssdf_sdf_sample_rays_args *a, gssdf_
     GSSDF_REQUIRE(m_cap < ((int64_t)1 << 31), GSSDF_EINVAL, "sdf_sample_rays: too many candidates for one call");
     unsigned char *w = reinterpret_cast<unsigned char *>(a->workspace);
     int32_t *ray_ws = reinterpret_cast<int32_t *>(w);
-    w += align_up((size_t)std::max<int64_t>(a->n_rays, 1) * 8, 256);
+    w += ray_ws_bytes(a->n_rays);
     int32_t *nug_ridx = reinterpret_cast<int32_t *>(w);
     w += align_up((size_t)a->nugget_cap * 4, 256);
     float *nug_depth = reinterpret_cast<float *>(w);
@@ -611,18 +707,22 @@ extern "C" int gssdf_sdf_sample_rays(const gssdf_sdf_sample_rays_args *a, gssdf_
     int32_t *flags = reinterpret_cast<int32_t *>(w);
     w += align_up((size_t)m_cap * 4, 256);
     int32_t *pos = reinterpret_cast<int32_t *>(w);
+    w += align_up((size_t)m_cap * 4, 256);
+    int32_t *scan_scratch = reinterpret_cast<int32_t *>(w);
     rc = raytrace_impl(a->tree, a->n_rays, a->origin, a->direction, a->nugget_cap, nug_ridx, nullptr, nug_depth, a->counts + 1, a->counts + 2, ray_ws, st);
     if (rc) return rc;
     sample_flag_kernel<<<cdiv(m_cap, 256), 256, 0, st>>>(*a, nug_ridx, nug_depth, flags, m_cap);
     GSSDF_LAUNCH_OK("sample_flag_kernel");
-    scan_kernel<<<1, 1024, 0, st>>>(flags, pos, m_cap, nullptr, a->cap, a->counts, a->counts + 2);
-    GSSDF_LAUNCH_OK("scan_kernel");
+    rc = run_scan(flags, pos, m_cap, nullptr, a->cap, a->counts, a->counts + 2, scan_scratch, st);
+    if (rc) return rc;
     sample_write_kernel<<<cdiv(m_cap, 256), 256, 0, st>>>(*a, nug_ridx, nug_depth, flags, pos, m_cap);
     GSSDF_LAUNCH_OK("sample_write_kernel");
     return GSSDF_OK;
 }
 
-extern "C" size_t gssdf_sdf_gate_compact_workspace_bytes(int64_t n) { return 2 * align_up((size_t)std::max<int64_t>(n, 1) * 4, 256); }
+extern "C" size_t gssdf_sdf_gate_compact_workspace_bytes(int64_t n) {
+    return 2 * align_up((size_t)std::max<int64_t>(n, 1) * 4, 256) + scan_scratch_bytes(n) + 256;
+}
 
 extern "C" int gssdf_sdf_gate_compact(const gssdf_sdf_gate_compact_args *a, gssdf_stream_t stream) {
     GSSDF_REQUIRE(a != nullptr && a->n_gate != nullptr, GSSDF_EINVAL, "sdf_gate_compact: null args / n_gate");
@@ -634,11 +734,15 @@ extern "C" int gssdf_sdf_gate_compact(const gssdf_sdf_gate_compact_args *a, gssd
     GSSDF_REQUIRE(a->workspace && a->workspace_bytes >= gssdf_sdf_gate_compact_workspace_bytes(a->n), GSSDF_ENOMEM, "sdf_gate_compact: workspace too small");
     int32_t *flags = reinterpret_cast<int32_t *>(a->workspace);
     int32_t *pos = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(a->workspace) + align_up((size_t)a->n * 4, 256));
-    int32_t *scratch_ovf = pos + a->n - 1;  // never read: the count cannot exceed n
+    unsigned char *tail = reinterpret_cast<unsigned char *>(a->workspace) + 2 * align_up((size_t)a->n * 4, 256);
+    int32_t *scratch_ovf = reinterpret_cast<int32_t *>(tail);  // never set: the count cannot exceed n
+    int32_t *scan_scratch = reinterpret_cast<int32_t *>(tail + 256);
     gate_flag_kernel<<<cdiv(a->n, 256), 256, 0, st>>>(*a, flags);
     GSSDF_LAUNCH_OK("gate_flag_kernel");
-    scan_kernel<<<1, 1024, 0, st>>>(flags, pos, a->n, a->n_live, a->n + 1, a->n_gate, scratch_ovf);
-    GSSDF_LAUNCH_OK("scan_kernel");
+    {
+        const int rc2 = run_scan(flags, pos, a->n, a->n_live, a->n + 1, a->n_gate, scratch_ovf, scan_scratch, st);
+        if (rc2) return rc2;
+    }
     gate_gather_kernel<<<cdiv(a->n, 256), 256, 0, st>>>(*a, flags, pos);
     GSSDF_LAUNCH_OK("gate_gather_kernel");
     return GSSDF_OK;
