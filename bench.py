@@ -382,6 +382,9 @@ def main():
     ap.add_argument("--same-cameras", action="store_true", help="N>1: every rank renders the same camera poses (identical work per rank); "
                     "default: rank r renders its own poses")
     ap.add_argument("--no-stock-cuda", action="store_true", help="skip the reference-fork CUDA leg (oracle/_ref/gsplat_ref.so)")
+    ap.add_argument("--overlap", type=int, default=0, choices=[0, 1, 2, 3],
+                    help="schedule of the SDF-only work (sample generation, [A], [C]): 0 = in line on one stream, 1 = on a second stream beside the "
+                         "render (equal priority), 2 = second stream at high priority, 3 = render stream at high priority")
     ap.add_argument("--l2-persist", action="store_true", help="A/B: pin the fp16 hash-table shadow in L2 (gssdf_l2_persist); measured: no effect")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -392,7 +395,9 @@ def main():
            "parallelism": (f"image-parallel dp{world}, replicated state, rank r renders its own camera poses"
                            f"{' (--same-cameras: identical poses)' if args.same_cameras else ''}, 2 NCCL all-reduces/step: SDF segment under "
                            f"the render backward, splat segment under the next step's SDF stage; replicated Adam with grad_scale 1/{world}")
-           if world > 1 else "single GPU"}
+           if world > 1 else "single GPU",
+           "schedule": ["one stream, stages in line", "SDF-only work (sample generation, [A], [C]) on a second stream beside the render",
+                        "SDF-only work on a second, high-priority stream", "render on a high-priority stream, SDF-only work on a second stream"][args.overlap]}
 
     if args.impl == "reference":
         if rank != 0:
@@ -438,6 +443,8 @@ def main():
                                 map_size=14.0, eikonal_mode=(1 if eikonal == "analytic" and sdf_cfg["hidden_dim"] == 64 else 0),
                                 normal_weight=0.01, isotropic_weight=0.05)  # config/base.yaml:43-46
         T.l2_persist = args.l2_persist
+        T.overlap = args.overlap > 0 and T.mlp_mode == 1
+        T.sdf_stream_priority = -1 if args.overlap == 2 else 0
         gen = torch.Generator(dev).manual_seed(5)  # replicated parameters: same on every rank
         table = (torch.rand(T.n_table, device=dev, generator=gen) * 2 - 1) * 1e-4  # tcnn grid init U(+-1e-4) (grid.h:1059-1062)
         chunks, dims = [], [32] + [sdf_cfg["hidden_dim"]] * (1 + sdf_cfg["n_hidden"]) + [2]
@@ -484,6 +491,8 @@ def main():
             self.rs.sample(self.o[k:k + nr_], self.dir[k:k + nr_], self.depth[k:k + nr_], self.end[k:k + nr_])
             return self.rs.xyz, self.rs.ray_sdf, self.rs.counts
 
+    if args.overlap == 3:  # everything below is enqueued on a high-priority stream; the SDF stream keeps the default priority
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
     T, sc_act, _ = build_trainer(args.workload, args.eikonal)
     R = T.R
     K_sh = (deg + 1) ** 2
@@ -528,7 +537,8 @@ def main():
         V, Kc = dev_cams[i % n_cams]
         R._mark("step_begin")
         randn_buf.normal_()  # the reference draws randns on the device every render (Projection.cpp:728)
-        ray_xyz, ray_gt, ray_cnt = SP.draw(i)
+        with T.sdf_stage():
+            ray_xyz, ray_gt, ray_cnt = SP.draw(i)
         loss, _sdf_loss = DP.step(V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf, ray_n_live=ray_cnt)
         DEN.update_state()  # NeuralGS::update_state: per-iteration densification statistics (the every-100-iterations surgery is not timed)
         R._mark("densify_stats")
@@ -560,7 +570,8 @@ def main():
         cur = torch.cuda.current_stream()
         cur.wait_event(sl["ready"])
         randn_buf.normal_()
-        ray_xyz, ray_gt, ray_cnt = SP.draw(i)
+        with T.sdf_stage():
+            ray_xyz, ray_gt, ray_cnt = SP.draw(i)
         loss, _sdf_loss = DP.step(sl["V"], sl["K"], sl["gt"], ray_xyz, ray_gt, randn_buf, ray_n_live=ray_cnt)
         sl["free"].record(cur)
         DEN.update_state()
@@ -639,6 +650,7 @@ def main():
     stage_ms = None
     if rank == 0 and world == 1:
         acc = {}
+        T.overlap = False  # the per-stage table is taken with the stages in line on one stream (event differences are meaningless otherwise)
         for i in range(5):
             R.stage_events = []
             step_resident(i)
@@ -647,6 +659,7 @@ def main():
             for (_, a), (name, b) in zip(ev[:-1], ev[1:]):
                 acc.setdefault(name, []).append(a.elapsed_time(b))
         R.stage_events = None
+        T.overlap = args.overlap > 0 and T.mlp_mode == 1
         stage_ms = {("rng+sample_generation[A0]" if k == "start" else k): float(np.mean(v)) for k, v in acc.items()}
 
     if rank == 0:

@@ -8,6 +8,7 @@ sized by capacity (cap = C*N rows, isect_cap chosen by the caller) and overflow 
 All gradients land in ONE flat fp32 buffer (means|quats|scales|opacities|sh) so that data-parallel
 training is a single NCCL all-reduce.
 """
+import contextlib
 import math
 
 import torch
@@ -101,7 +102,7 @@ class SplatRenderer:
 
     # -- loss + backward -----------------------------------------------------------------------
     def backward(self, means, quats, scales, opacities, sh, viewmats, Ks, gt, randns=None, w_rgb=1.0, w_depth=0.1, v_samples=None,
-                 zero_grads=True, raw=None, w_dssim=0.0, w_normal=0.0, w_isotropic=0.0):
+                 zero_grads=True, raw=None, w_dssim=0.0, w_normal=0.0, w_isotropic=0.0, before_projection_bwd=None):
         """With raw parameters the flat gradient holds dL/d(offsets|quats|log-scales|logits|features_dc|features_rest); the SH segment
         keeps its [N,K,3] size, laid out as dc [N,1,3] followed by rest [N,K-1,3]."""
         C, W, H, cap = self.C, self.W, self.H, self.cap
@@ -141,6 +142,8 @@ class SplatRenderer:
                              self.p["gaussian_ids"], self.p["radii"], self.colors, self.g["v_colors"], v_sh, self.v_means,
                              mean_offsets=off, sh_rest=rest, v_sh_rest=v_rest)
         self._mark("sh_bwd")
+        if before_projection_bwd is not None:  # v_samples may be produced on another stream (GsSdfStep.overlap)
+            before_projection_bwd()
         cabi.project2dgs_bwd(means, quats, scales, viewmats, Ks, W, H, cap, self.counts, self.p["camera_ids"],
                              self.p["gaussian_ids"], self.p["ray_transforms"], randns, None, None, self.g["v_ray_transforms"],
                              self.g["v_normals"], v_samples, self.v_means, self.v_quats, self.v_scales,
@@ -227,6 +230,27 @@ class GsSdfStep:
         self.gate_idx = torch.empty(cap, dtype=torch.int32, device=device)
         self.gate_x, self.gate_w, self.gate_vx = e(cap, 3), e(cap), e(cap, 3)
         self.gate_ws = cabi.Workspace(device)
+        # overlap: the SDF-only work of a step (sample generation, [A], [C]) is enqueued on a second stream and runs concurrently with the
+        # render: [A] beside projection .. raster forward, [C] (which needs the forward's visibilities) beside losses .. SH backward; the
+        # projection backward waits for [C]'s dL/d sample. Same kernels, same results; only the schedule changes.
+        self.overlap = False
+        self.sdf_stream_priority = 0
+        self._side = None
+        self._ev_fwd, self._ev_c = torch.cuda.Event(), torch.cuda.Event()
+
+    @contextlib.contextmanager
+    def sdf_stage(self):
+        """Stream context for work that touches SDF-side state only (ray sample generation, stage [A]). Without `overlap` it is the
+        caller's stream; with it, the second stream, ordered after everything the caller's stream has enqueued so far (the previous step's
+        optimiser update included)."""
+        if not self.overlap:
+            yield
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev, priority=self.sdf_stream_priority)
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            yield
 
     KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 9  # + 2 DSSIM kernels + table cast + decoder weight image + gate count + 2 x (7-variant forward, fused train) (mlp_mode 1)
 
@@ -246,6 +270,27 @@ class GsSdfStep:
         self.octree = octree
         self.valid_mask = torch.zeros(self.R.cap, dtype=torch.uint8, device=self.dev) if octree is not None else None
 
+    def _coupling_compact(self, net, samples, n_live, on_sdf_grads_ready):
+        """[C] like the reference: select the gated samples first, evaluate the SDF network on them only, scatter dL/d sample back"""
+        R, cap = self.R, self.R.cap
+        cabi.sdf_gate_compact(cap, samples, self.gate_idx, self.gate_x, self.n_gate, self.gate_ws, visibilities=R.r["visibilities"],
+                              visible_thr=self.vis_thr, valid_mask=self.valid_mask, weights=R.p["sample_weights"], w_out=self.gate_w,
+                              n_live=n_live)
+        if self.eik_mode == 1:
+            if self.align_w > 0:
+                cabi.sdf_fwd(net, self.gate_x, self.gs_sdf, None, None, n_variants=7, delta=self.delta, n_live=self.n_gate,
+                             skip_base_variant=True)
+            cabi.sdf_train(net, self.gate_x, 1, self.delta, None, self.gate_w, self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
+                           self.sdf_loss, self.table_grad, self.mlp_grad, self.gate_vx, n_live=self.n_gate, eikonal_mode=1,
+                           align_weight=self.align_w, sdf_variants=self.gs_sdf if self.align_w > 0 else None)
+        else:
+            cabi.sdf_train(net, self.gate_x, 7, self.delta, None, self.gate_w, self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
+                           self.sdf_loss, self.table_grad, self.mlp_grad, self.gate_vx, n_live=self.n_gate)
+        cabi.scatter_rows3(cap, self.gate_idx, self.n_gate, self.gate_vx, self.v_samples, n_live=n_live)
+        R._mark("sdf_splat_samples[C]")
+        if on_sdf_grads_ready is not None:  # (NCCL orders itself after the stream that is current here)
+            on_sdf_grads_ready(self.flat_grad[self.table_grad.storage_offset():])
+
     def step(self, scene, table_f32, mlp, viewmats, Ks, gt_image, ray_xyz, ray_gt_sdf, randns=None, on_sdf_grads_ready=None,
              before_render=None, ray_n_live=None):
         """ray_n_live: device int32 (e.g. RaySampler.counts): only the first *ray_n_live rows of ray_xyz / ray_gt_sdf are samples."""
@@ -257,36 +302,37 @@ class GsSdfStep:
             in flight while [A] runs; the caller waits for them here."""
         R, n_ray, cap = self.R, self.n_ray, self.R.cap
         R._mark("start")
-        # fp32 master -> fp16 shadow once per step (the optimiser moved the master; the reference casts on EVERY forward)
-        if not self.keep_shadows:
-            cabi.sdf_table_to_half(table_f32, self.table_half)
-            if self.mlp_mode == 1:  # bf16 hi/mid/lo weight image for the tensor-core decoder, also once per step
-                cabi.sdf_mlp_pack(cabi.sdf_net(self.table_half, mlp, **self.cfg), self.mlp_packed)
-        net = cabi.sdf_net(self.table_half, mlp, origin=self.origin, inv_size=self.inv_size, mlp_mode=self.mlp_mode,
-                           mlp_packed=self.mlp_packed, **self.cfg)
-        t0 = self.table_grad.storage_offset()
-        if not self.keep_shadows:
-            self.flat_grad[t0:].zero_()  # table + decoder segment; the splat segment is cleared after before_render()
-        self.sdf_loss.zero_()
-        # [A] SDF stage on the ray samples (tensor-core mode: forward + losses + backward fused in one kernel)
-        if self.mlp_mode == 1:
-            if self.eik_mode == 1:  # reference default: forward-only pass over the 7 variants (numerical gradient of the align loss),
-                                    # then forward + losses + backward + double backward on the base points only
-                if self.align_w > 0:
-                    cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, None, None, n_variants=7, delta=self.delta, skip_base_variant=True, n_live=ray_n_live)
-                cabi.sdf_train(net, ray_xyz, 1, self.delta, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.sdf_loss,
-                               self.table_grad, self.mlp_grad, None, eikonal_mode=1, align_weight=self.align_w,
-                               sdf_variants=self.ray_sdf if self.align_w > 0 else None, n_live=ray_n_live)
+        with self.sdf_stage():
+            # fp32 master -> fp16 shadow once per step (the optimiser moved the master; the reference casts on EVERY forward)
+            if not self.keep_shadows:
+                cabi.sdf_table_to_half(table_f32, self.table_half)
+                if self.mlp_mode == 1:  # bf16 hi/mid/lo weight image for the tensor-core decoder, also once per step
+                    cabi.sdf_mlp_pack(cabi.sdf_net(self.table_half, mlp, **self.cfg), self.mlp_packed)
+            net = cabi.sdf_net(self.table_half, mlp, origin=self.origin, inv_size=self.inv_size, mlp_mode=self.mlp_mode,
+                               mlp_packed=self.mlp_packed, **self.cfg)
+            t0 = self.table_grad.storage_offset()
+            if not self.keep_shadows:
+                self.flat_grad[t0:].zero_()  # table + decoder segment; the splat segment is cleared after before_render()
+            self.sdf_loss.zero_()
+            # [A] SDF stage on the ray samples (tensor-core mode: forward + losses + backward fused in one kernel)
+            if self.mlp_mode == 1:
+                if self.eik_mode == 1:  # reference default: forward-only pass over the 7 variants (numerical gradient of the align loss),
+                                        # then forward + losses + backward + double backward on the base points only
+                    if self.align_w > 0:
+                        cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, None, None, n_variants=7, delta=self.delta, skip_base_variant=True, n_live=ray_n_live)
+                    cabi.sdf_train(net, ray_xyz, 1, self.delta, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.sdf_loss,
+                                   self.table_grad, self.mlp_grad, None, eikonal_mode=1, align_weight=self.align_w,
+                                   sdf_variants=self.ray_sdf if self.align_w > 0 else None, n_live=ray_n_live)
+                else:
+                    cabi.sdf_train(net, ray_xyz, 7, self.delta, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.sdf_loss,
+                                   self.table_grad, self.mlp_grad, None, n_live=ray_n_live)
             else:
-                cabi.sdf_train(net, ray_xyz, 7, self.delta, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.sdf_loss,
-                               self.table_grad, self.mlp_grad, None, n_live=ray_n_live)
-        else:
-            cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, self.ray_y1, None, n_variants=7, delta=self.delta, n_live=ray_n_live)
-            cabi.sdf_loss(n_ray, 7, self.ray_sdf, self.ray_y1, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.delta, self.sdf_loss,
-                          self.ray_vs, self.ray_vy, n_live=ray_n_live)
-            cabi.sdf_bwd(net, ray_xyz, self.ray_vs, self.ray_vy, self.table_grad, self.mlp_grad, None, n_variants=7, delta=self.delta,
-                         n_live=ray_n_live)
-        R._mark("sdf_ray_samples[A]")
+                cabi.sdf_fwd(net, ray_xyz, self.ray_sdf, self.ray_y1, None, n_variants=7, delta=self.delta, n_live=ray_n_live)
+                cabi.sdf_loss(n_ray, 7, self.ray_sdf, self.ray_y1, ray_gt_sdf, None, self.bce_isigma, 1.0, self.eik_w, 0.0, self.delta, self.sdf_loss,
+                              self.ray_vs, self.ray_vy, n_live=ray_n_live)
+                cabi.sdf_bwd(net, ray_xyz, self.ray_vs, self.ray_vy, self.table_grad, self.mlp_grad, None, n_variants=7, delta=self.delta,
+                             n_live=ray_n_live)
+            R._mark("sdf_ray_samples[A]")
         if before_render is not None:
             before_render()
         if not self.keep_shadows:
@@ -297,30 +343,23 @@ class GsSdfStep:
         # [C] coupling on the stochastic splat samples (rows < nnz, counted on the device)
         samples, n_live = R.p["samples"], R.counts  # counts[0] == nnz
         # the reference's sample gate: vis > visible_thr (& octree validity), counted on the device (no nonzero() / .item() sync)
-        if getattr(self, "octree", None) is not None:
-            self.octree.valid_mask(samples, self.valid_mask, n_live=n_live)
+        side = self._side if self.overlap else None
+        assert side is None or (self.compact_gate and self.mlp_mode == 1), "overlap needs the compact-gate tensor-core path"
+        if side is not None:  # [C] needs the forward's visibilities / samples: the second stream picks up after the raster forward
+            self._ev_fwd.record()
+            side.wait_event(self._ev_fwd)
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            if getattr(self, "octree", None) is not None:
+                self.octree.valid_mask(samples, self.valid_mask, n_live=n_live)
+            if self.compact_gate and self.mlp_mode == 1:
+                self._coupling_compact(net, samples, n_live, on_sdf_grads_ready)
+                if side is not None:
+                    self._ev_c.record(side)
         if self.compact_gate and self.mlp_mode == 1:
-            # like the reference: select the gated samples first, evaluate the SDF network on them only, scatter dL/d sample back
-            cabi.sdf_gate_compact(cap, samples, self.gate_idx, self.gate_x, self.n_gate, self.gate_ws, visibilities=R.r["visibilities"],
-                                  visible_thr=self.vis_thr, valid_mask=self.valid_mask, weights=R.p["sample_weights"], w_out=self.gate_w,
-                                  n_live=n_live)
-            if self.eik_mode == 1:
-                if self.align_w > 0:
-                    cabi.sdf_fwd(net, self.gate_x, self.gs_sdf, None, None, n_variants=7, delta=self.delta, n_live=self.n_gate,
-                                 skip_base_variant=True)
-                cabi.sdf_train(net, self.gate_x, 1, self.delta, None, self.gate_w, self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
-                               self.sdf_loss, self.table_grad, self.mlp_grad, self.gate_vx, n_live=self.n_gate, eikonal_mode=1,
-                               align_weight=self.align_w, sdf_variants=self.gs_sdf if self.align_w > 0 else None)
-            else:
-                cabi.sdf_train(net, self.gate_x, 7, self.delta, None, self.gate_w, self.bce_isigma, 0.0, self.eik_w, self.gs_sdf_w,
-                               self.sdf_loss, self.table_grad, self.mlp_grad, self.gate_vx, n_live=self.n_gate)
-            cabi.scatter_rows3(cap, self.gate_idx, self.n_gate, self.gate_vx, self.v_samples, n_live=n_live)
-            R._mark("sdf_splat_samples[C]")
-            if on_sdf_grads_ready is not None:
-                on_sdf_grads_ready(self.flat_grad[self.table_grad.storage_offset():])
+            wait_c = (lambda: torch.cuda.current_stream().wait_event(self._ev_c)) if side is not None else None
             loss = R.backward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, gt_image, randns,
                               v_samples=self.v_samples, zero_grads=False, raw=scene.get("raw"), w_rgb=self.rgb_w, w_depth=self.depth_w,
-                              w_dssim=self.dssim_w, w_normal=self.normal_w, w_isotropic=self.iso_w)
+                              w_dssim=self.dssim_w, w_normal=self.normal_w, w_isotropic=self.iso_w, before_projection_bwd=wait_c)
             return loss, self.sdf_loss
         cabi.sdf_gate_count(cap, self.n_gate, visibilities=R.r["visibilities"], visible_thr=self.vis_thr, valid_mask=self.valid_mask,
                             n_live=n_live)

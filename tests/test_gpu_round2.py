@@ -576,3 +576,56 @@ def test_local_map_checkpoint_archive_round_trip(tmp_path):
     # the archive is a regular TorchScript-style zip: python can open it too
     m = torch.jit.load(path, map_location="cpu")
     assert dict(m.named_parameters())["encoder_local_map"].shape == A.encoder_params().shape
+
+
+def test_two_stream_schedule_equals_in_line_schedule():
+    """GsSdfStep.overlap only changes WHERE the SDF-only work is enqueued (a second stream beside the render); losses and the flat gradient
+    must agree with the in-line schedule up to the order of the float atomics, over several consecutive steps with Adam in between."""
+    from gssdf_b200 import octree as OT, render, scene as S
+    dev = _dev()
+    rng = np.random.default_rng(5)
+    W, H, N, deg = 160, 96, 4000, 3
+    sc = S.box_scene(N, deg, seed=0)
+    V, K = S.camera(0, W, H)
+    cfg = dict(n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=2.0, hidden_dim=64, n_hidden=3)
+    table = (rng.uniform(-1, 1, 16 * 2 * (1 << 19)).astype(np.float32)) * 2e-4
+    out = {}
+    for overlap in (False, True):
+        torch.manual_seed(11)
+        T = render.GsSdfTrainer(N, (deg + 1) ** 2, W, H, dev, 300000, cfg, n_ray_samples=8192, sh_degree=deg, map_size=14.0,
+                                normal_weight=0.01, isotropic_weight=0.05)
+        T.overlap = overlap
+        probe = T.n_mlp
+        mlp = torch.from_numpy(np.random.default_rng(6).uniform(-0.2, 0.2, probe).astype(np.float32)).to(dev)
+        op_ = np.clip(sc["opacities"], 1e-6, 1 - 1e-6)
+        T.load(_t(sc["means"], dev), torch.zeros(N, 3, device=dev), _t(sc["quats"], dev), _t(np.log(sc["scales"]), dev),
+               _t(np.log(op_ / (1 - op_)), dev), _t(sc["sh"][:, :1].copy(), dev), _t(sc["sh"][:, 1:].copy(), dev), _t(table[:T.n_table], dev), mlp)
+        q = OT.quantize_points(_t(sc["means"], dev) * (2.0 / 14.0), 6)
+        tree = OT.OctreeAS.from_quantized_points(q, 6, dev, map_size=14.0)
+        T.set_octree(tree)
+        n_rays = 500
+        r2 = np.random.default_rng(7)
+        ro = (r2.uniform(-0.5, 0.5, (n_rays, 3)) * S.BOX).astype(np.float32)
+        rend = sc["means"][r2.integers(0, N, n_rays)].astype(np.float32)
+        rdep = np.linalg.norm(rend - ro, axis=1).astype(np.float32)
+        rdir = ((rend - ro) / rdep[:, None]).astype(np.float32)
+        RS = OT.RaySampler(tree, n_rays, dev, 1, 3, 3, 0.1, 0.3, nugget_cap=64 * n_rays, cap=8192)
+        gt = torch.rand(1, H, W, 4, device=dev, generator=torch.Generator(dev).manual_seed(3))
+        rn = torch.randn(N, 2, device=dev, generator=torch.Generator(dev).manual_seed(4))
+        gen = torch.Generator(dev).manual_seed(9)
+        rec = []
+        for it in range(3):
+            with T.sdf_stage():
+                RS.rand_voxel.uniform_(generator=gen); RS.rand_free.uniform_(generator=gen); RS.randn_surface.normal_(generator=gen)
+                RS.sample(_t(ro, dev), _t(rdir, dev), _t(rdep, dev), _t(rend, dev))
+            loss, sdf_loss = T.train_step(_t(V[None], dev), _t(K[None], dev), gt, RS.xyz, RS.ray_sdf, rn, ray_n_live=RS.counts)
+            torch.cuda.synchronize()
+            rec.append((float(loss), float(sdf_loss), T.flat_grad.clone(), int(T.n_gate[0]), int(RS.counts[0])))
+            T.adam_all()
+        torch.cuda.synchronize()
+        out[overlap] = (rec, T.params.clone())
+    for (l0, s0, g0, n0, c0), (l1, s1, g1, n1, c1) in zip(out[False][0], out[True][0]):
+        assert n0 == n1 and c0 == c1 and n0 > 0 and c0 > 0
+        assert abs(l0 - l1) <= 1e-5 * abs(l0) and abs(s0 - s1) <= 1e-4 * abs(s0), (l0, l1, s0, s1)
+        assert rel(g1.cpu().numpy(), g0.cpu().numpy()) < 1e-4
+    assert float((out[False][1] - out[True][1]).abs().max()) < 1e-3
