@@ -108,8 +108,10 @@ struct TreeView {
     __device__ __forceinline__ unsigned bits(int node) const { return node < n_cached ? oct_s[node] : __ldg(oct_g + node); }
     __device__ __forceinline__ int exsum(int node) const { return node < n_cached ? ex_s[node] : __ldg(ex_g + node); }
 };
-constexpr int kRayThreads = 64;          // two warps per CTA: a few thousand rays spread over a third of the SMs
-constexpr int kTreeCacheNodes = 4096;    // top of the tree (every ray walks it): 20 KB, staged in ~64 pipelined load rounds per CTA;
+constexpr int kRayLanes = 8;             // lanes per ray: one per child of the node being opened
+constexpr int kRayThreads = 256;         // 32 rays per CTA
+constexpr int kRaysPerCta = kRayThreads / kRayLanes;
+constexpr int kTreeCacheNodes = 4096;    // top of the tree (every ray walks it): 20 KB, staged in 16 pipelined load rounds per CTA;
                                          // deeper nodes are touched by few rays each and come through L1 / L2
 
 __device__ __forceinline__ TreeView stage_tree(const gssdf_octree &t, int n_cached, unsigned char *smem) {
@@ -121,76 +123,84 @@ __device__ __forceinline__ TreeView stage_tree(const gssdf_octree &t, int n_cach
     return TreeView{oc, ex, n_cached, t.octree, t.exsum};
 }
 
-// Depth-first traversal of one ray. emit(pidx, entry, exit) is called for every leaf-level hit in the reference's nugget order.
-// per-level traversal frames of the CTA's rays, in shared memory (indexed by the dynamic stack depth: registers cannot hold them, local
-// memory would put every push / pop through L1): [level][thread] -> conflict-free
+// Depth-first traversal of one ray by EIGHT lanes: when a node is opened, lane g tests the g-th child in the reference's front-to-back
+// visiting order (existence bit, then ray_aabb), a ballot over the eight lanes gives the hit children, and the lanes descend together
+// into the first of them. Frames of nodes with hit children still to visit live in shared memory, [slot][ray] (indexed by the dynamic
+// stack depth: registers cannot hold them); every lane of the ray writes the same value. At the leaf level the hit lanes call
+// emit(position in the ray's nugget list, pidx, entry, exit) -- the positions follow the reference's nugget order. Returns the number
+// of nuggets of the ray.
 struct RayStack {
-    int ord[kMaxOctLevel][kRayThreads];        // node
-    uint32_t todo[kMaxOctLevel][kRayThreads];  // remaining children in visiting order (8 x 4 bits, 0xF = none)
-    short fx[kMaxOctLevel][kRayThreads], fy[kMaxOctLevel][kRayThreads], fz[kMaxOctLevel][kRayThreads];  // voxel coordinates
+    int node[kMaxOctLevel][kRaysPerCta];
+    short x[kMaxOctLevel][kRaysPerCta], y[kMaxOctLevel][kRaysPerCta], z[kMaxOctLevel][kRaysPerCta];
+    uint8_t lvl[kMaxOctLevel][kRaysPerCta], code[kMaxOctLevel][kRaysPerCta], todo[kMaxOctLevel][kRaysPerCta];
 };
 
 template <typename Emit>
-__device__ __forceinline__ void traverse(const gssdf_octree &t, const TreeView &tv, RayStack &S, const RayCtx &c, Emit emit) {
-    const int L = t.level, me = threadIdx.x;
-#define ord(l) S.ord[l][me]
-#define todo(l) S.todo[l][me]
-#define fx(l) S.fx[l][me]
-#define fy(l) S.fy[l][me]
-#define fz(l) S.fz[l][me]
-    auto open = [&](int lvl, int node, int x, int y, int z) {  // push a node whose voxel the ray touches (depth != 0)
-        const unsigned bits = tv.bits(node);
-        const float scale = 1.0f / (float)(1 << lvl);  // subdivide_cuda_kernel:226-237 (the 0.5 literals are doubles there)
-        const double hx = (double)fmaf(0.5f, c.o[0], 0.5f) - (double)scale * ((double)x + 0.5);
-        const double hy = (double)fmaf(0.5f, c.o[1], 0.5f) - (double)scale * ((double)y + 0.5);
-        const double hz = (double)fmaf(0.5f, c.o[2], 0.5f) - (double)scale * ((double)z + 0.5);
-        const int code = ((float)hx > 0.f ? 4 : 0) + ((float)hy > 0.f ? 2 : 0) + ((float)hz > 0.f ? 1 : 0);
-        uint32_t list = 0;
-        int k = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const unsigned j = c_voxel_order[code][i];
-            if (bits & (1u << j)) { list |= j << (4 * k); ++k; }
-        }
-        for (; k < 8; ++k) list |= 0xFu << (4 * k);
-        ord(lvl) = node; fx(lvl) = (short)x; fy(lvl) = (short)y; fz(lvl) = (short)z; todo(lvl) = list;
-    };
+__device__ __forceinline__ int traverse(const gssdf_octree &t, const TreeView &tv, RayStack &S, const RayCtx &c, Emit emit) {
+    const int L = t.level, me = threadIdx.x / kRayLanes;
+    const unsigned g = threadIdx.x % kRayLanes, shift = (threadIdx.x & 31u) & ~7u, gmask = 0xFFu << shift;
     {
         float vc[3], r;
         voxel_center(0, 0, 0, 0, vc, r);
         if (L == 0) {
             const float en = ray_aabb(c.o, c.d, c.inv, c.sgn, vc, r), ex = ray_aabb(c.o, c.d, c.inv, c.sgx, vc, r);
-            if (en > 0.f && ex > 0.f) emit(0, en, ex);
-            return;
+            if (!(en > 0.f && ex > 0.f)) return 0;
+            if (g == 0) emit(0, 0, en, ex);
+            return 1;
         }
-        if (ray_aabb(c.o, c.d, c.inv, c.sgn, vc, r) == 0.0f) return;
-        open(0, 0, 0, 0, 0);
+        if (ray_aabb(c.o, c.d, c.inv, c.sgn, vc, r) == 0.0f) return 0;
     }
-    int top = 0;
-    while (top >= 0) {
-        const uint32_t td = todo(top);
-        const unsigned j = td & 0xFu;
-        if (j == 0xFu) { --top; continue; }
-        todo(top) = (td >> 4) | 0xF0000000u;
-        const int node = ord(top);
+    int hits = 0, sp = 0, lvl = 0, node = 0, x = 0, y = 0, z = 0;
+    unsigned code = 0, todo = 0;
+    auto open = [&]() {  // test the eight children of (lvl, node, x, y, z): todo = hit children (bit i = i-th in visiting order)
         const unsigned bits = tv.bits(node);
-        const int child = tv.exsum(node) + __popc(bits & ((2u << j) - 1u));
-        const int x = (fx(top) << 1) | (int)((j >> 2) & 1u), y = (fy(top) << 1) | (int)((j >> 1) & 1u), z = (fz(top) << 1) | (int)(j & 1u);
+        const float scale = 1.0f / (float)(1 << lvl);  // subdivide_cuda_kernel:226-237 (the 0.5 literals are doubles there)
+        const double hx = (double)fmaf(0.5f, c.o[0], 0.5f) - (double)scale * ((double)x + 0.5);
+        const double hy = (double)fmaf(0.5f, c.o[1], 0.5f) - (double)scale * ((double)y + 0.5);
+        const double hz = (double)fmaf(0.5f, c.o[2], 0.5f) - (double)scale * ((double)z + 0.5);
+        code = ((float)hx > 0.f ? 4u : 0u) + ((float)hy > 0.f ? 2u : 0u) + ((float)hz > 0.f ? 1u : 0u);
+        const unsigned j = c_voxel_order[code][g];
         float vc[3], r;
-        voxel_center(x, y, z, top + 1, vc, r);
-        if (top + 1 == L) {  // decide_cuda_kernel (with exit) :180-218
-            const float en = ray_aabb(c.o, c.d, c.inv, c.sgn, vc, r), ex = ray_aabb(c.o, c.d, c.inv, c.sgx, vc, r);
-            if (en > 0.0f && ex > 0.0f) emit(child, en, ex);
-        } else if (ray_aabb(c.o, c.d, c.inv, c.sgn, vc, r) != 0.0f) {  // decide_cuda_kernel :78-130
-            ++top;
-            open(top, child, x, y, z);
+        voxel_center((x << 1) | (int)((j >> 2) & 1u), (y << 1) | (int)((j >> 1) & 1u), (z << 1) | (int)(j & 1u), lvl + 1, vc, r);
+        bool hit = (bits >> j) & 1u;
+        if (lvl + 1 == L) {  // decide_cuda_kernel (with exit) :180-218
+            float en = 0.f, ex = 0.f;
+            if (hit) {
+                en = ray_aabb(c.o, c.d, c.inv, c.sgn, vc, r);
+                ex = ray_aabb(c.o, c.d, c.inv, c.sgx, vc, r);
+                hit = en > 0.0f && ex > 0.0f;
+            }
+            const unsigned m = (__ballot_sync(gmask, hit) >> shift) & 0xFFu;
+            if (hit) emit(hits + __popc(m & ((1u << g) - 1u)), tv.exsum(node) + __popc(bits & ((2u << j) - 1u)), en, ex);
+            hits += __popc(m);
+            todo = 0;
+        } else {  // decide_cuda_kernel :78-130
+            if (hit) hit = ray_aabb(c.o, c.d, c.inv, c.sgn, vc, r) != 0.0f;
+            todo = (__ballot_sync(gmask, hit) >> shift) & 0xFFu;
         }
+    };
+    open();
+    while (true) {
+        if (todo == 0) {
+            if (--sp < 0) break;
+            node = S.node[sp][me]; x = S.x[sp][me]; y = S.y[sp][me]; z = S.z[sp][me];
+            lvl = S.lvl[sp][me]; code = S.code[sp][me]; todo = S.todo[sp][me];
+            continue;
+        }
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        if (todo != 0) {  // this node is returned to
+            S.node[sp][me] = node; S.x[sp][me] = (short)x; S.y[sp][me] = (short)y; S.z[sp][me] = (short)z;
+            S.lvl[sp][me] = (uint8_t)lvl; S.code[sp][me] = (uint8_t)code; S.todo[sp][me] = (uint8_t)todo;
+            ++sp;
+        }
+        const unsigned j = c_voxel_order[code][i];
+        node = tv.exsum(node) + __popc(tv.bits(node) & ((2u << j) - 1u));
+        x = (x << 1) | (int)((j >> 2) & 1u); y = (y << 1) | (int)((j >> 1) & 1u); z = (z << 1) | (int)(j & 1u);
+        ++lvl;
+        open();
     }
-#undef ord
-#undef todo
-#undef fx
-#undef fy
-#undef fz
+    return hits;
 }
 
 __device__ __forceinline__ RayCtx make_ray(const gssdf_octree &t, const float *origins, const float *dirs, int64_t i) {
@@ -222,16 +232,14 @@ __global__ void __launch_bounds__(kRayThreads) ray_count_kernel(const gssdf_octr
     extern __shared__ __align__(16) unsigned char s_tree[];
     __shared__ RayStack s_stack;
     const TreeView tv = stage_tree(t, n_cached, s_tree);
-    const int64_t i = (int64_t)blockIdx.x * kRayThreads + threadIdx.x;
-    if (i >= n) return;
+    const int64_t i = (int64_t)blockIdx.x * kRaysPerCta + threadIdx.x / kRayLanes;
+    if (i >= n) return;  // (all eight lanes of a ray leave together)
     const RayCtx c = make_ray(t, origins, dirs, i);
-    int k = 0;
     StagedHit *mine = stage + i * kStageHits;
-    traverse(t, tv, s_stack, c, [&](int p, float en, float ex) {
-        if (k < kStageHits) mine[k] = StagedHit{p, en, ex, 0};
-        ++k;
+    const int k = traverse(t, tv, s_stack, c, [&](int pos, int p, float en, float ex) {
+        if (pos < kStageHits) mine[pos] = StagedHit{p, en, ex, 0};
     });
-    cnt[i] = k;
+    if (threadIdx.x % kRayLanes == 0) cnt[i] = k;
 }
 
 __global__ void __launch_bounds__(kRayThreads) ray_write_kernel(const gssdf_octree t, int n_cached, int64_t n, const float *origins, const float *dirs,
@@ -239,26 +247,27 @@ __global__ void __launch_bounds__(kRayThreads) ray_write_kernel(const gssdf_octr
                                                                 int32_t *ridx, int32_t *pidx, float *depth) {
     extern __shared__ __align__(16) unsigned char s_tree[];
     __shared__ RayStack s_stack;
-    const int64_t i = (int64_t)blockIdx.x * kRayThreads + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * kRaysPerCta + threadIdx.x / kRayLanes;
+    const int g = threadIdx.x % kRayLanes;
     const int k = i < n ? cnt[i] : 0;
     const bool redo = k > kStageHits;
     // CTA-uniform: the octree prefix is only staged when one of this CTA's rays has to be traversed again
     TreeView tv{nullptr, nullptr, 0, t.octree, t.exsum};
     if (__syncthreads_or(redo)) tv = stage_tree(t, n_cached, s_tree);
     if (i >= n) return;
-    int64_t pos = off[i];
-    auto put = [&](int p, float en, float ex) {
+    const int64_t base = off[i];
+    auto put = [&](int at, int p, float en, float ex) {
+        const int64_t pos = base + at;
         if (pos < cap) {
             ridx[pos] = (int32_t)i;
             if (pidx) pidx[pos] = p;
             depth[2 * pos] = en;
             depth[2 * pos + 1] = ex;
         }
-        ++pos;
     };
     if (!redo) {
         const StagedHit *mine = stage + i * kStageHits;
-        for (int j = 0; j < k; ++j) { const StagedHit h = mine[j]; put(h.pidx, h.entry, h.exit); }
+        for (int j = g; j < k; j += kRayLanes) { const StagedHit h = mine[j]; put(j, h.pidx, h.entry, h.exit); }
     } else {
         const RayCtx c = make_ray(t, origins, dirs, i);
         traverse(t, tv, s_stack, c, put);
@@ -647,11 +656,11 @@ static int raytrace_impl(const gssdf_octree &tree, int64_t n_rays, const float *
     const size_t smem = (size_t)n_cached * 5 + 16;
     GSSDF_CUDA_OK(cudaFuncSetAttribute(ray_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTreeCacheNodes * 5 + 16));
     GSSDF_CUDA_OK(cudaFuncSetAttribute(ray_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTreeCacheNodes * 5 + 16));
-    ray_count_kernel<<<cdiv(n_rays, kRayThreads), kRayThreads, smem, st>>>(tree, n_cached, n_rays, origins, dirs, cnt, stage);
+    ray_count_kernel<<<cdiv(n_rays, kRaysPerCta), kRayThreads, smem, st>>>(tree, n_cached, n_rays, origins, dirs, cnt, stage);
     GSSDF_LAUNCH_OK("ray_count_kernel");
     scan_kernel<<<1, 1024, 0, st>>>(cnt, off, n_rays, nullptr, cap, n_nuggets, overflow);
     GSSDF_LAUNCH_OK("scan_kernel");
-    ray_write_kernel<<<cdiv(n_rays, kRayThreads), kRayThreads, smem, st>>>(tree, n_cached, n_rays, origins, dirs, cnt, off, stage, cap, ridx, pidx, depth);
+    ray_write_kernel<<<cdiv(n_rays, kRaysPerCta), kRayThreads, smem, st>>>(tree, n_cached, n_rays, origins, dirs, cnt, off, stage, cap, ridx, pidx, depth);
     GSSDF_LAUNCH_OK("ray_write_kernel");
     return GSSDF_OK;
 }
