@@ -118,3 +118,33 @@ def test_query_raytrace_and_samples_vs_oracle(oracle, level, n_pts, n_rays):
     S2.draw()
     c2 = S2.sample(_t(origin, dev), _t(direction, dev), _t(depth, dev), _t(end, dev)).tolist()
     assert c2[2] == 1 and c2[0] <= 50 and c2[1] <= 10
+
+
+def test_raytrace_grazing_rays_overflow_and_empty(oracle):
+    """Rays running along a wall cross dozens of leaf voxels: more than the per-ray staging slots of the count pass, so the write pass
+    traverses them a second time; nugget order / indices / depths stay bit-exact. Also: capacity overflow is flagged, zero rays are legal."""
+    from gssdf_b200 import octree as OT
+    dev = _dev()
+    rng = np.random.default_rng(3)
+    level, map_size, n_pts = 8, 14.0, 150000
+    surf = _room(rng, n_pts)
+    q = oracle.quantize_points(surf * np.float32(2 / map_size), level)
+    ref = oracle.octree_from_points(q, level)
+    t = OT.OctreeAS.from_quantized_points(q, level, dev, origin=(0.0, 0.0, 0.0), map_size=map_size)
+    n_rays = 600
+    origin = np.stack([np.full(n_rays, -2.9), rng.uniform(-1.9, 1.9, n_rays), rng.uniform(-1.4, 1.4, n_rays)], 1).astype(np.float32)
+    origin[:300, 1] = 1.99  # inside the y = +2 wall's voxel layer, marching along x
+    direction = np.tile(np.array([[1.0, 0.0, 0.0]], np.float32), (n_rays, 1))
+    direction[300:] += rng.normal(0, 0.2, (300, 3)).astype(np.float32)
+    direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+    direction = direction.astype(np.float32)
+    o_n = ((origin - np.float32(0)) * np.float32(2) * np.float32(1 / map_size)).astype(np.float32)
+    rr, rp, rd = oracle.octree_raytrace(ref, o_n, direction, depth_mode=2)
+    per_ray = np.bincount(rr, minlength=n_rays)
+    assert per_ray.max() > 40 and (per_ray <= 16).sum() > 100, (per_ray.max(), (per_ray <= 16).sum())
+    gr, gp, gd = t.raytrace(_t(origin, dev), _t(direction, dev), cap=len(rr) + 7)
+    assert np.array_equal(gr.cpu().numpy(), rr) and np.array_equal(gp.cpu().numpy(), rp) and np.array_equal(gd.cpu().numpy(), rd)
+    with pytest.raises(RuntimeError, match="capacity"):
+        t.raytrace(_t(origin, dev), _t(direction, dev), cap=len(rr) - 1)
+    e_r, e_p, e_d = t.raytrace(torch.empty(0, 3, device=dev), torch.empty(0, 3, device=dev))
+    assert len(e_r) == 0 and len(e_p) == 0 and tuple(e_d.shape) == (0, 2)
