@@ -629,3 +629,28 @@ def test_two_stream_schedule_equals_in_line_schedule():
         assert abs(l0 - l1) <= 1e-5 * abs(l0) and abs(s0 - s1) <= 1e-4 * abs(s0), (l0, l1, s0, s1)
         assert rel(g1.cpu().numpy(), g0.cpu().numpy()) < 1e-4
     assert float((out[False][1] - out[True][1]).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("n,live,p_keep", [(100000, 91000, 0.4), (40000, 40000, 1.0), (40000, 40000, 0.0), (70000, 0, 0.5), (1, 1, 1.0),
+                                           (32769, 32769, 0.5), (4096 * 9, 4096 * 9 - 1, 0.5)])
+def test_gate_compaction_sizes_and_degenerate_masks(n, live, p_keep):
+    """flag -> scan -> gather at sizes on both sides of the single-CTA / chunked scan switch, with all / none / no live rows."""
+    from gssdf_b200 import cabi
+    dev = _dev()
+    rng = np.random.default_rng(n + live)
+    x = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    vis = np.where(rng.uniform(0, 1, n) < p_keep, 0.5, 0.01).astype(np.float32)
+    sel = np.flatnonzero(vis[:live] > 0.1)
+    n_live = torch.tensor([live], dtype=torch.int32, device=dev)
+    idx, xo = torch.full((n,), -7, dtype=torch.int32, device=dev), torch.zeros(n, 3, device=dev)
+    ng = torch.full((1,), -1, dtype=torch.int32, device=dev)
+    cabi.sdf_gate_compact(n, _t(x, dev), idx, xo, ng, cabi.Workspace(dev), visibilities=_t(vis, dev), visible_thr=0.1, n_live=n_live)
+    k = int(ng)
+    assert k == len(sel)
+    assert np.array_equal(idx[:k].cpu().numpy(), sel) and np.array_equal(xo[:k].cpu().numpy(), x[sel])
+    src, dst = torch.randn(n, 3, device=dev), torch.full((n, 3), 5.0, device=dev)
+    cabi.scatter_rows3(n, idx, ng, src, dst, n_live=n_live)
+    ref = np.full((n, 3), 5.0, np.float32)
+    ref[:live] = 0
+    ref[sel] = src[:k].cpu().numpy()
+    assert np.array_equal(dst.cpu().numpy(), ref)
