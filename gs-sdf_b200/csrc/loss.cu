@@ -7,16 +7,21 @@
 // (loss_utils.cpp:6-14), an asymmetric 11-tap profile, reproduced here bit-for-bit in intent (the backward therefore uses the
 // flipped taps).
 //
-// B200 design: two tile kernels instead of ~40 ATen launches. Forward: a 16x16 pixel tile of one channel stages a 26x26 halo of x and
-// y in shared memory, runs the separable window over the five products, evaluates the SSIM value and its three partial derivatives
-// (w.r.t. mu_x, E[x^2], E[xy]) and stores only those three maps. Backward: the same tiling convolves the three maps with the flipped
-// window and emits dL/dx = conv(Dm) + 2 x conv(D11) + y conv(D12) straight into the colour cotangent. HBM traffic ~ 9 floats per
-// channel-pixel in total.
+// B200 design: two streaming kernels instead of ~40 ATen launches. A WARP owns a strip of 32 image columns of one colour channel and
+// marches down a band of rows: per input row it stages the 42 strip + halo values of x and y in a private shared-memory row (the only
+// shared memory used; no CTA-wide barrier anywhere), every lane runs the horizontal 11-tap pass of the five products for its column
+// (22 conflict-free shared loads), and the vertical pass lives in REGISTERS as a ring of 11 x 5 partial sums -- one input row updates the
+// eleven pending output rows, the oldest of which is then complete: SSIM value, its three partial derivatives (w.r.t. mu_x, E[x^2],
+// E[xy]) -> three maps. The backward marches the same way over the three maps with the flipped window and emits
+// dL/dx = conv(Dm) + 2 x conv(D11) + y conv(D12) into the colour cotangent. (The first version tiled 16x16 pixels with both passes
+// through shared memory: ~180 shared-memory wavefronts per channel-pixel incl. 2-way bank conflicts and seven barriers per tile,
+// 0.17 ms per direction at 1080p; this one needs 29.)
 #include "common.cuh"
 
 namespace gssdf {
 
-constexpr int kWin = 11, kHalf = 5, kT = 16, kHalo = kT + 2 * kHalf;  // 26
+constexpr int kWin = 11, kHalf = 5, kStrip = 32, kRowW = kStrip + 2 * kHalf;  // 42
+constexpr int kSsimWarps = 4;                                                 // strips per CTA (independent warps)
 
 struct SsimWindow {
     float w[kWin];
@@ -35,124 +40,162 @@ static SsimWindow make_window() {  // loss_utils.cpp:6-14 (float tensor, normali
     return g;
 }
 
-__global__ void __launch_bounds__(256)
-dssim_fwd_kernel(const gssdf_dssim_loss_args a, const SsimWindow win, float *__restrict__ maps, float scale_loss) {
-    __shared__ float sx[3][kHalo][kHalo + 1], sy[3][kHalo][kHalo + 1];  // the three colour channels of the 26x26 halo
-    __shared__ float hq[5][kHalo][kT + 1];
-    __shared__ float s_red[8];
-    const int W = a.image_width, H = a.image_height, cam = blockIdx.z;
-    const int x0 = blockIdx.x * kT - kHalf, y0 = blockIdx.y * kT - kHalf;
+__device__ __forceinline__ float chan(const float4 &v, int ch) { return ch == 0 ? v.x : (ch == 1 ? v.y : v.z); }
+
+// grid (strips / kSsimWarps, bands, C * 3); band_h rows per band
+__global__ void __launch_bounds__(kSsimWarps * 32)
+dssim_fwd_kernel(const gssdf_dssim_loss_args a, const SsimWindow win, float *__restrict__ maps, float scale_loss, int band_h) {
+    __shared__ float s_row[kSsimWarps][2][2][kRowW + 2];  // [warp][buffer][x | y][column]
+    const int W = a.image_width, H = a.image_height;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x0 = (blockIdx.x * kSsimWarps + warp) * kStrip;
+    if (x0 >= W) return;  // (whole warp; no CTA-wide barrier below)
+    const int cam = blockIdx.z / 3, ch = blockIdx.z % 3;
+    const int y0 = blockIdx.y * band_h, y1 = min(y0 + band_h, H);
     const float4 *X = reinterpret_cast<const float4 *>(a.out_colors) + (int64_t)cam * H * W;
     const float4 *Y = reinterpret_cast<const float4 *>(a.gt) + (int64_t)cam * H * W;
-    for (int e = threadIdx.x; e < kHalo * kHalo; e += 256) {
-        const int r = e / kHalo, c = e % kHalo, yy = y0 + r, xx = x0 + c;
-        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;  // conv2d zero padding
-        const float4 xv = in ? __ldg(X + (int64_t)yy * W + xx) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 yv = in ? __ldg(Y + (int64_t)yy * W + xx) : make_float4(0.f, 0.f, 0.f, 0.f);
-        sx[0][r][c] = xv.x; sx[1][r][c] = xv.y; sx[2][r][c] = xv.z;
-        sy[0][r][c] = yv.x; sy[1][r][c] = yv.y; sy[2][r][c] = yv.z;
-    }
-    const int lx = threadIdx.x % kT, ly = threadIdx.x / kT;
-    const int px = blockIdx.x * kT + lx, py = blockIdx.y * kT + ly;
     const int64_t P = (int64_t)H * W, CP = (int64_t)a.C * 3 * P;
+    const int64_t map_base = ((int64_t)cam * 3 + ch) * P;
+    const int px = x0 + lane;
+    // lane l stages columns x0 - 5 + l and (l < 10) x0 + 27 + l of the current row
+    const int ca = x0 - kHalf + lane, cb = x0 - kHalf + 32 + lane;
+    const bool ina = ca >= 0 && ca < W, inb = lane < 2 * kHalf && cb < W;
+    auto fetch = [&](int yy, float &xa, float &ya, float &xb, float &yb) {
+        xa = ya = xb = yb = 0.f;  // conv2d zero padding
+        if (yy < 0 || yy >= H) return;
+        if (ina) { xa = chan(__ldg(X + (int64_t)yy * W + ca), ch); ya = chan(__ldg(Y + (int64_t)yy * W + ca), ch); }
+        if (inb) { xb = chan(__ldg(X + (int64_t)yy * W + cb), ch); yb = chan(__ldg(Y + (int64_t)yy * W + cb), ch); }
+    };
+    float acc[kWin][5];
+#pragma unroll
+    for (int k = 0; k < kWin; ++k)
+#pragma unroll
+        for (int q = 0; q < 5; ++q) acc[k][q] = 0.f;
     float part = 0.f;
-    for (int ch = 0; ch < 3; ++ch) {
-        __syncthreads();  // halo staged (ch == 0) / hq of the previous channel consumed
-        for (int e = threadIdx.x; e < kHalo * kT; e += 256) {  // horizontal pass of the five products
-            const int r = e / kT, c = e % kT;
-            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, q4 = 0.f;
+    float xa, ya, xb, yb;
+    fetch(y0 - kHalf, xa, ya, xb, yb);
+    const int n_in = (y1 - y0) + 2 * kHalf;  // input rows y0 - 5 .. y1 + 4
+    for (int base = 0; base < n_in; base += kWin) {
 #pragma unroll
-            for (int t = 0; t < kWin; ++t) {
-                const float xv = sx[ch][r][c + t], yv = sy[ch][r][c + t], w = win.w[t];
-                q0 += w * xv; q1 += w * yv; q2 += w * xv * xv; q3 += w * yv * yv; q4 += w * xv * yv;
-            }
-            hq[0][r][c] = q0; hq[1][r][c] = q1; hq[2][r][c] = q2; hq[3][r][c] = q3; hq[4][r][c] = q4;
-        }
-        __syncthreads();
-        if (px < W && py < H) {
-            float mu1 = 0.f, mu2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+        for (int j = 0; j < kWin; ++j) {
+            const int i = base + j;  // input row y0 - 5 + i feeds the output rows y0 + i - 10 .. y0 + i
+            if (i < n_in) {          // warp-uniform
+                float(*buf)[kRowW + 2] = s_row[warp][i & 1];
+                buf[0][lane] = xa; buf[1][lane] = ya;
+                if (lane < 2 * kHalf) { buf[0][32 + lane] = xb; buf[1][32 + lane] = yb; }
+                __syncwarp();
+                fetch(y0 - kHalf + i + 1, xa, ya, xb, yb);  // next row in flight during this row's arithmetic
+                float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, h4 = 0.f;
 #pragma unroll
-            for (int t = 0; t < kWin; ++t) {
-                const float w = win.w[t];
-                mu1 += w * hq[0][ly + t][lx]; mu2 += w * hq[1][ly + t][lx];
-                s11 += w * hq[2][ly + t][lx]; s22 += w * hq[3][ly + t][lx]; s12 += w * hq[4][ly + t][lx];
+                for (int t = 0; t < kWin; ++t) {
+                    const float xv = buf[0][lane + t], yv = buf[1][lane + t], w = win.w[t];
+                    h0 += w * xv; h1 += w * yv; h2 += w * xv * xv; h3 += w * yv * yv; h4 += w * xv * yv;
+                }
+#pragma unroll
+                for (int t = 0; t < kWin; ++t) {  // output row (i - t): tap t
+                    const int k = (j - t + kWin) % kWin;
+                    const float w = win.w[t];
+                    acc[k][0] += w * h0; acc[k][1] += w * h1; acc[k][2] += w * h2; acc[k][3] += w * h3; acc[k][4] += w * h4;
+                }
+                // output row o = i - 10 is complete (its slot is the one tap 10 just touched)
+                const int k_out = (j - (kWin - 1) + kWin) % kWin;
+                const int py = y0 + i - (kWin - 1);
+                if (i >= kWin - 1 && py < y1 && px < W) {
+                    const float mu1 = acc[k_out][0], mu2 = acc[k_out][1], s11 = acc[k_out][2], s22 = acc[k_out][3], s12 = acc[k_out][4];
+                    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+                    const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+                    const float sig1 = s11 - mu1_sq, sig2 = s22 - mu2_sq, sig12 = s12 - mu12;
+                    const float A1 = 2.f * mu12 + C1, A2 = 2.f * sig12 + C2, B1 = mu1_sq + mu2_sq + C1, B2 = sig1 + sig2 + C2;
+                    const float inv = 1.f / (B1 * B2);
+                    const float S = A1 * A2 * inv;
+                    part += S;
+                    // partial derivatives of S w.r.t. the three windowed moments that depend on x: mu1, s11 = E[x^2], s12 = E[xy]
+                    const float dm = (2.f * mu2 * (A2 - A1)) * inv - S * (2.f * mu1 / B1 - 2.f * mu1 / B2);
+                    const int64_t o = map_base + (int64_t)py * W + px;
+                    maps[o] = dm; maps[CP + o] = -S / B2; maps[2 * CP + o] = 2.f * A1 * inv;
+                }
+#pragma unroll
+                for (int q = 0; q < 5; ++q) acc[k_out][q] = 0.f;
             }
-            const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-            const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
-            const float sig1 = s11 - mu1_sq, sig2 = s22 - mu2_sq, sig12 = s12 - mu12;
-            const float A1 = 2.f * mu12 + C1, A2 = 2.f * sig12 + C2, B1 = mu1_sq + mu2_sq + C1, B2 = sig1 + sig2 + C2;
-            const float inv = 1.f / (B1 * B2);
-            const float S = A1 * A2 * inv;
-            part += S;
-            // partial derivatives of S w.r.t. the three windowed moments that depend on x: mu1, s11 = E[x^2], s12 = E[xy]
-            const float dm = (2.f * mu2 * (A2 - A1)) * inv - S * (2.f * mu1 / B1 - 2.f * mu1 / B2);
-            const int64_t o = ((int64_t)cam * 3 + ch) * P + (int64_t)py * W + px;
-            maps[o] = dm; maps[CP + o] = -S / B2; maps[2 * CP + o] = 2.f * A1 * inv;
         }
     }
     part = warp_sum(part);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int w = 0; w < 8; ++w) s += s_red[w];
-        s *= -scale_loss;                                                        // - w / N * sum S
-        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) s += a.w_dssim;  // + w * 1
+    if (lane == 0) {
+        float s = -scale_loss * part;                                                         // - w / N * sum S
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 0) s += a.w_dssim;  // + w * 1
         atomicAdd(a.loss_out, s);
     }
 }
 
-__global__ void __launch_bounds__(256)
-dssim_bwd_kernel(const gssdf_dssim_loss_args a, const SsimWindow win, const float *__restrict__ maps, float scale_grad) {
-    __shared__ float sm[3][kHalo][kHalo + 1];
-    __shared__ float hq[3][kHalo][kT + 1];
-    const int W = a.image_width, H = a.image_height, cam = blockIdx.z;
-    const int x0 = blockIdx.x * kT - kHalf, y0 = blockIdx.y * kT - kHalf;
+__global__ void __launch_bounds__(kSsimWarps * 32)
+dssim_bwd_kernel(const gssdf_dssim_loss_args a, const SsimWindow win, const float *__restrict__ maps, float scale_grad, int band_h) {
+    __shared__ float s_row[kSsimWarps][2][3][kRowW + 2];  // [warp][buffer][map][column]
+    const int W = a.image_width, H = a.image_height;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x0 = (blockIdx.x * kSsimWarps + warp) * kStrip;
+    if (x0 >= W) return;
+    const int cam = blockIdx.z / 3, ch = blockIdx.z % 3;
+    const int y0 = blockIdx.y * band_h, y1 = min(y0 + band_h, H);
     const int64_t P = (int64_t)H * W, CP = (int64_t)a.C * 3 * P;
-    const int lx = threadIdx.x % kT, ly = threadIdx.x / kT;
-    const int px = blockIdx.x * kT + lx, py = blockIdx.y * kT + ly;
-    const bool inside = px < W && py < H;
-    const int64_t pix = ((int64_t)cam * H + py) * W + px;
-    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv = xv, gv = xv;
-    if (inside) {
-        xv = __ldg(reinterpret_cast<const float4 *>(a.out_colors) + pix);
-        yv = __ldg(reinterpret_cast<const float4 *>(a.gt) + pix);
-        gv = reinterpret_cast<const float4 *>(a.v_out_colors)[pix];
-    }
-    float grad[3];
-    for (int ch = 0; ch < 3; ++ch) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < kHalo * kHalo; e += 256) {
-            const int r = e / kHalo, c = e % kHalo, yy = y0 + r, xx = x0 + c;
-            const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
-            const int64_t o = ((int64_t)cam * 3 + ch) * P + (int64_t)yy * W + xx;
+    const float *M = maps + ((int64_t)cam * 3 + ch) * P;
+    const int px = x0 + lane;
+    const int ca = x0 - kHalf + lane, cb = x0 - kHalf + 32 + lane;
+    const bool ina = ca >= 0 && ca < W, inb = lane < 2 * kHalf && cb < W;
+    auto fetch = [&](int yy, float (&va)[3], float (&vb)[3]) {
 #pragma unroll
-            for (int m = 0; m < 3; ++m) sm[m][r][c] = in ? __ldg(maps + m * CP + o) : 0.f;
+        for (int m = 0; m < 3; ++m) va[m] = vb[m] = 0.f;
+        if (yy < 0 || yy >= H) return;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            if (ina) va[m] = __ldg(M + m * CP + (int64_t)yy * W + ca);
+            if (inb) vb[m] = __ldg(M + m * CP + (int64_t)yy * W + cb);
         }
-        __syncthreads();
-        // adjoint of a correlation with taps w[t] at offset t - 5 = correlation with the FLIPPED taps w[10 - t]
-        for (int e = threadIdx.x; e < kHalo * kT; e += 256) {
-            const int r = e / kT, c = e % kT;
-            float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+    };
+    float acc[kWin][3];
 #pragma unroll
-            for (int t = 0; t < kWin; ++t) {
-                const float w = win.w[kWin - 1 - t];
-                q0 += w * sm[0][r][c + t]; q1 += w * sm[1][r][c + t]; q2 += w * sm[2][r][c + t];
+    for (int k = 0; k < kWin; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
+    float va[3], vb[3];
+    fetch(y0 - kHalf, va, vb);
+    const float *Xc = a.out_colors + (int64_t)cam * P * 4 + ch, *Yc = a.gt + (int64_t)cam * P * 4 + ch;
+    float *Vc = a.v_out_colors + (int64_t)cam * P * 4 + ch;
+    const int n_in = (y1 - y0) + 2 * kHalf;
+    for (int base = 0; base < n_in; base += kWin) {
+#pragma unroll
+        for (int j = 0; j < kWin; ++j) {
+            const int i = base + j;
+            if (i < n_in) {
+                float(*buf)[kRowW + 2] = s_row[warp][i & 1];
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    buf[m][lane] = va[m];
+                    if (lane < 2 * kHalf) buf[m][32 + lane] = vb[m];
+                }
+                __syncwarp();
+                fetch(y0 - kHalf + i + 1, va, vb);
+                // adjoint of a correlation with taps w[t] at offset t - 5 = correlation with the FLIPPED taps w[10 - t]
+                float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+                for (int t = 0; t < kWin; ++t) {
+                    const float w = win.w[kWin - 1 - t];
+                    h0 += w * buf[0][lane + t]; h1 += w * buf[1][lane + t]; h2 += w * buf[2][lane + t];
+                }
+#pragma unroll
+                for (int t = 0; t < kWin; ++t) {
+                    const int k = (j - t + kWin) % kWin;
+                    const float w = win.w[kWin - 1 - t];
+                    acc[k][0] += w * h0; acc[k][1] += w * h1; acc[k][2] += w * h2;
+                }
+                const int k_out = (j - (kWin - 1) + kWin) % kWin;
+                const int py = y0 + i - (kWin - 1);
+                if (i >= kWin - 1 && py < y1 && px < W) {
+                    const int64_t pix = ((int64_t)py * W + px) * 4;  // one owner per (pixel, channel): plain read-modify-write, depth untouched
+                    const float xc = __ldg(Xc + pix), yc = __ldg(Yc + pix);
+                    Vc[pix] += scale_grad * (acc[k_out][0] + 2.f * xc * acc[k_out][1] + yc * acc[k_out][2]);
+                }
+                acc[k_out][0] = acc[k_out][1] = acc[k_out][2] = 0.f;
             }
-            hq[0][r][c] = q0; hq[1][r][c] = q1; hq[2][r][c] = q2;
         }
-        __syncthreads();
-        float cA = 0.f, cB = 0.f, cC = 0.f;
-#pragma unroll
-        for (int t = 0; t < kWin; ++t) {
-            const float w = win.w[kWin - 1 - t];
-            cA += w * hq[0][ly + t][lx]; cB += w * hq[1][ly + t][lx]; cC += w * hq[2][ly + t][lx];
-        }
-        const float xc = ch == 0 ? xv.x : (ch == 1 ? xv.y : xv.z), yc = ch == 0 ? yv.x : (ch == 1 ? yv.y : yv.z);
-        grad[ch] = scale_grad * (cA + 2.f * xc * cB + yc * cC);
     }
-    if (inside)  // one thread per pixel: plain read-modify-write of the colour cotangent, depth channel untouched
-        reinterpret_cast<float4 *>(a.v_out_colors)[pix] = make_float4(gv.x + grad[0], gv.y + grad[1], gv.z + grad[2], gv.w);
 }
 
 }  // namespace gssdf
@@ -164,6 +207,24 @@ extern "C" size_t gssdf_dssim_workspace_bytes(int32_t C, int32_t W, int32_t H) {
     return (size_t)9 * C * W * H * sizeof(float);
 }
 
+// rows per band: a warp's cost is (band + 10) row steps, the launch runs ceil(warp tasks / resident warps) rounds of them
+static int ssim_band_height(const void *kernel, int W, int H, int C) {
+    int dev = 0, sms = 148, per_sm = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSsimWarps * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    const int64_t slots = (int64_t)sms * per_sm;  // resident CTAs
+    const int64_t per_band = (int64_t)cdiv(cdiv(W, kStrip), kSsimWarps) * 3 * C;
+    int best = 32;
+    int64_t best_cost = INT64_MAX;
+    for (int band = 16; band <= 128; band += 8) {
+        const int64_t ctas = per_band * cdiv(H, band);
+        const int64_t cost = cdiv(ctas, slots) * (band + 2 * kHalf);
+        if (cost < best_cost) { best_cost = cost; best = band; }
+    }
+    return best;
+}
+
 extern "C" int gssdf_dssim_loss(const gssdf_dssim_loss_args *a, gssdf_stream_t stream) {
     GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "dssim_loss: null args");
     GSSDF_REQUIRE(a->C > 0 && a->image_width > 0 && a->image_height > 0, GSSDF_EINVAL, "dssim_loss: bad image size");
@@ -171,14 +232,18 @@ extern "C" int gssdf_dssim_loss(const gssdf_dssim_loss_args *a, gssdf_stream_t s
     GSSDF_REQUIRE(a->workspace && a->workspace_bytes >= gssdf_dssim_workspace_bytes(a->C, a->image_width, a->image_height), GSSDF_ENOMEM,
                   "dssim_loss: workspace too small");
     static const SsimWindow win = make_window();
-    const dim3 grid(cdiv(a->image_width, kT), cdiv(a->image_height, kT), a->C);
     const double n = (double)a->C * 3.0 * a->image_width * a->image_height;
     float *maps = reinterpret_cast<float *>(a->workspace);
     cudaStream_t st = (cudaStream_t)stream;
-    dssim_fwd_kernel<<<grid, 256, 0, st>>>(*a, win, maps, (float)(a->w_dssim / n));
-    GSSDF_LAUNCH_OK("dssim_fwd_kernel");
+    const int gx = cdiv(cdiv(a->image_width, kStrip), kSsimWarps);
+    {
+        const int band = ssim_band_height((const void *)dssim_fwd_kernel, a->image_width, a->image_height, a->C);
+        dssim_fwd_kernel<<<dim3(gx, cdiv(a->image_height, band), a->C * 3), kSsimWarps * 32, 0, st>>>(*a, win, maps, (float)(a->w_dssim / n), band);
+        GSSDF_LAUNCH_OK("dssim_fwd_kernel");
+    }
     if (a->v_out_colors) {
-        dssim_bwd_kernel<<<grid, 256, 0, st>>>(*a, win, maps, (float)(-a->w_dssim / n));
+        const int band = ssim_band_height((const void *)dssim_bwd_kernel, a->image_width, a->image_height, a->C);
+        dssim_bwd_kernel<<<dim3(gx, cdiv(a->image_height, band), a->C * 3), kSsimWarps * 32, 0, st>>>(*a, win, maps, (float)(-a->w_dssim / n), band);
         GSSDF_LAUNCH_OK("dssim_bwd_kernel");
     }
     return GSSDF_OK;

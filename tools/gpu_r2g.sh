@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call G: 8-lane ray traversal + two-stream schedule A/B + ncu --set full of the mid-size kernels
-timeout 900 python -m pytest tests/test_gpu_octree.py tests/test_gpu_round2.py -q -m gpu -x > gpurun_out/r2g_tests.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_octree.py tests/test_gpu_round2.py tests/test_gpu_splat_parity.py -q -m gpu -x > gpurun_out/r2g_tests.log 2>&1
 rc=$?
 tail -5 gpurun_out/r2g_tests.log
 if [ $rc -ne 0 ]; then echo "tests failed: stopping"; grep -n "Error\|assert" gpurun_out/r2g_tests.log | head -20; exit 1; fi
