@@ -207,19 +207,20 @@ extern "C" size_t gssdf_dssim_workspace_bytes(int32_t C, int32_t W, int32_t H) {
     return (size_t)9 * C * W * H * sizeof(float);
 }
 
-// rows per band: a warp's cost is (band + 10) row steps, the launch runs ceil(warp tasks / resident warps) rounds of them
-static int ssim_band_height(const void *kernel, int W, int H, int C) {
-    int dev = 0, sms = 148, per_sm = 4;
+// rows per band. The kernels are throughput-bound per SM, so the launch costs ~ ceil(CTAs / SMs) x (band + 10) row steps of one CTA;
+// a taller band amortises the 10 halo rows, a shorter one balances the SMs. At least ~4 CTAs (16 warps) per SM are kept for latency
+// hiding when the image is large enough.
+static int ssim_band_height(int W, int H, int C) {
+    int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSsimWarps * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-    const int64_t slots = (int64_t)sms * per_sm;  // resident CTAs
     const int64_t per_band = (int64_t)cdiv(cdiv(W, kStrip), kSsimWarps) * 3 * C;
-    int best = 32;
+    int best = 16;
     int64_t best_cost = INT64_MAX;
     for (int band = 16; band <= 128; band += 8) {
         const int64_t ctas = per_band * cdiv(H, band);
-        const int64_t cost = cdiv(ctas, slots) * (band + 2 * kHalf);
+        if (band > 16 && ctas < 4 * (int64_t)sms) break;
+        const int64_t cost = cdiv(ctas, (int64_t)sms) * (band + 2 * kHalf);
         if (cost < best_cost) { best_cost = cost; best = band; }
     }
     return best;
@@ -237,12 +238,12 @@ extern "C" int gssdf_dssim_loss(const gssdf_dssim_loss_args *a, gssdf_stream_t s
     cudaStream_t st = (cudaStream_t)stream;
     const int gx = cdiv(cdiv(a->image_width, kStrip), kSsimWarps);
     {
-        const int band = ssim_band_height((const void *)dssim_fwd_kernel, a->image_width, a->image_height, a->C);
+        const int band = ssim_band_height(a->image_width, a->image_height, a->C);
         dssim_fwd_kernel<<<dim3(gx, cdiv(a->image_height, band), a->C * 3), kSsimWarps * 32, 0, st>>>(*a, win, maps, (float)(a->w_dssim / n), band);
         GSSDF_LAUNCH_OK("dssim_fwd_kernel");
     }
     if (a->v_out_colors) {
-        const int band = ssim_band_height((const void *)dssim_bwd_kernel, a->image_width, a->image_height, a->C);
+        const int band = ssim_band_height(a->image_width, a->image_height, a->C);
         dssim_bwd_kernel<<<dim3(gx, cdiv(a->image_height, band), a->C * 3), kSsimWarps * 32, 0, st>>>(*a, win, maps, (float)(-a->w_dssim / n), band);
         GSSDF_LAUNCH_OK("dssim_bwd_kernel");
     }
