@@ -382,7 +382,7 @@ def main():
     ap.add_argument("--same-cameras", action="store_true", help="N>1: every rank renders the same camera poses (identical work per rank); "
                     "default: rank r renders its own poses")
     ap.add_argument("--no-stock-cuda", action="store_true", help="skip the reference-fork CUDA leg (oracle/_ref/gsplat_ref.so)")
-    ap.add_argument("--overlap", type=int, default=0, choices=[0, 1, 2, 3],
+    ap.add_argument("--overlap", type=int, default=1, choices=[0, 1, 2, 3],
                     help="schedule of the SDF-only work (sample generation, [A], [C]): 0 = in line on one stream, 1 = on a second stream beside the "
                          "render (equal priority), 2 = second stream at high priority, 3 = render stream at high priority")
     ap.add_argument("--l2-persist", action="store_true", help="A/B: pin the fp16 hash-table shadow in L2 (gssdf_l2_persist); measured: no effect")

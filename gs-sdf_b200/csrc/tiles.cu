@@ -60,14 +60,53 @@ __device__ __forceinline__ bool shrink_rect(const gssdf_tile_encode_args &a, int
     return x0 < x1 && y0 < y1;
 }
 
+// Warp-cooperative walk of a large rect (>= 256 tiles) of splat `bidx` in culled mode: 8x8-tile super-blocks are tested against the
+// splat's conic first (same min-over-rectangle routine, looser tolerance -> a superset of the per-tile test), and only the ones it
+// touches are descended into. f(i, x, y) still applies the exact per-tile test, so the set of (splat, tile) pairs that pass is unchanged.
+template <typename F>
+__device__ __forceinline__ void walk_super_blocks(int bidx, uint32_t bx0, uint32_t by0, uint32_t bw, uint32_t bh, const float4 *__restrict__ conic,
+                                                  F &&f) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t sw = (bw + 7) >> 3, sh = (bh + 7) >> 3, nsb = sw * sh;
+    const float4 g0 = __ldg(conic + kConicF4 * (int64_t)bidx), g1 = __ldg(conic + kConicF4 * (int64_t)bidx + 1);
+    for (uint32_t s0 = 0; s0 < nsb; s0 += 32) {
+        const uint32_t sb = s0 + lane;
+        bool hit = false;
+        if (sb < nsb) {
+            const uint32_t sx = (sb % sw) * 8, sy = (sb / sw) * 8;
+            const uint32_t ex = min(sx + 8, bw), ey = min(sy + 8, bh);
+            hit = rect_hit(g0, g1, (bx0 + sx) * 16.f + 0.5f, (by0 + sy) * 16.f + 0.5f, (ex - sx) * 16.f - 1.f, (ey - sy) * 16.f - 1.f, 1e-4f);
+        }
+        unsigned hm = __ballot_sync(0xffffffffu, hit);
+        while (hm) {
+            const uint32_t sb2 = s0 + (__ffs(hm) - 1);
+            hm &= hm - 1;
+            const uint32_t sx = (sb2 % sw) * 8, sy = (sb2 / sw) * 8;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const uint32_t x = sx + (lane & 7), y = sy + (lane >> 3) + 4 * t;
+                if (x < bw && y < bh) f(bidx, bx0 + x, by0 + y);
+            }
+        }
+    }
+}
+
+// The large rects of the culled mode are not walked by the warp that finds them (a warp holding several screen-filling splats would
+// decide the kernel's duration: one wave of CTAs, 36 % of the issue slots used) but queued -- one aggregated atomic per warp -- for
+// tile_big_kernel, whose warps pull them from the queue one at a time.
+struct BigQueue {
+    int32_t *count;     // number of queued splats (device counter), or nullptr: walk in place
+    int32_t *items;     // [cap]
+    int64_t cap;        // = isect_cap: more queued splats than intersection slots cannot happen without an intersection overflow
+    int32_t *overflow;  // -> gssdf_counts::isect_overflow, raised if it happens all the same
+    bool append;        // false: the queue was filled by an earlier pass, just skip the large rects
+};
+
 // Visit every tile of every splat's rect. Small rects are walked by their own thread; rects with
 // >= 32 tiles are walked cooperatively by the warp (a screen-filling splat touches ~8k tiles).
-// Culled mode (conic != NULL): the cooperative walk first tests 8x8-tile super-blocks against the splat's conic (same
-// min-over-rectangle routine, looser tolerance -> a superset of the per-tile test), and only descends into the ones it touches.
-// f(i, x, y) still applies the exact per-tile test, so the set of visited (splat, tile) pairs that pass is unchanged.
 template <typename F>
 __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, int idx,
-                                              const float4 *__restrict__ conic, F &&f) {
+                                              const float4 *__restrict__ conic, const BigQueue &q, F &&f) {
     const uint32_t w = has ? x1 - x0 : 0, h = has ? y1 - y0 : 0;
     const uint32_t cnt = w * h;
     const bool big = cnt >= 32;
@@ -77,6 +116,20 @@ __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0
     }
     unsigned m = __ballot_sync(0xffffffffu, big);
     const int lane = threadIdx.x & 31;
+    if (conic && q.count) {  // warp-uniform
+        const unsigned mq = __ballot_sync(0xffffffffu, cnt >= 256);
+        if (mq && q.append) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(q.count, __popc(mq));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (cnt >= 256) {
+                const int64_t slot = (int64_t)base + __popc(mq & ((1u << lane) - 1u));
+                if (slot < q.cap) q.items[slot] = idx;
+                else *q.overflow = 1;
+            }
+        }
+        m &= ~mq;
+    }
     while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
@@ -84,28 +137,7 @@ __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0
         const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bcnt = __shfl_sync(0xffffffffu, cnt, src);
         const int bidx = __shfl_sync(0xffffffffu, idx, src);
         if (conic && bcnt >= 256) {
-            const uint32_t bh = bcnt / bw, sw = (bw + 7) >> 3, sh = (bh + 7) >> 3, nsb = sw * sh;
-            const float4 g0 = __ldg(conic + kConicF4 * (int64_t)bidx), g1 = __ldg(conic + kConicF4 * (int64_t)bidx + 1);
-            for (uint32_t s0 = 0; s0 < nsb; s0 += 32) {
-                const uint32_t sb = s0 + lane;
-                bool hit = false;
-                if (sb < nsb) {
-                    const uint32_t sx = (sb % sw) * 8, sy = (sb / sw) * 8;
-                    const uint32_t ex = min(sx + 8, bw), ey = min(sy + 8, bh);
-                    hit = rect_hit(g0, g1, (bx0 + sx) * 16.f + 0.5f, (by0 + sy) * 16.f + 0.5f, (ex - sx) * 16.f - 1.f, (ey - sy) * 16.f - 1.f, 1e-4f);
-                }
-                unsigned hm = __ballot_sync(0xffffffffu, hit);
-                while (hm) {
-                    const uint32_t sb2 = s0 + (__ffs(hm) - 1);
-                    hm &= hm - 1;
-                    const uint32_t sx = (sb2 % sw) * 8, sy = (sb2 / sw) * 8;
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        const uint32_t x = sx + (lane & 7), y = sy + (lane >> 3) + 4 * t;
-                        if (x < bw && y < bh) f(bidx, bx0 + x, by0 + y);
-                    }
-                }
-            }
+            walk_super_blocks(bidx, bx0, by0, bw, bcnt / bw, conic, f);
         } else {
 #pragma unroll 4
             for (uint32_t t = lane; t < bcnt; t += 32) f(bidx, bx0 + t % bw, by0 + t / bw);  // unrolled: 4 atomics in flight per lane
@@ -113,8 +145,53 @@ __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0
     }
 }
 
+__device__ __forceinline__ void count_tile(const gssdf_tile_encode_args &a, const TileGeom &g, int32_t *__restrict__ hist,
+                                           const float4 *__restrict__ conic, int i, uint32_t x, uint32_t y) {
+    if (conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f)) return;
+    const int64_t cid = a.camera_ids ? a.camera_ids[i] : 0;
+    atomicAdd(hist + cid * g.n_tiles + y * g.tw + x, 1);
+    if (conic && a.tiles_per_gauss) atomicAdd(a.tiles_per_gauss + i, 1);  // culled mode: count the survivors
+}
+
+__device__ __forceinline__ void scatter_tile(const gssdf_tile_encode_args &a, const TileGeom &g, int32_t *__restrict__ hist,
+                                             const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys,
+                                             const float4 *__restrict__ conic, int i, uint32_t x, uint32_t y) {
+    if (conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f))
+        return;  // the same test, on the same inputs, as in the count pass
+    const int64_t cid = a.camera_ids ? a.camera_ids[i] : 0;
+    const int64_t bin = cid * g.n_tiles + y * g.tw + x;
+    const int slot = atomicSub(hist + bin, 1) - 1;  // fills the bin back to front
+    const int64_t pos = (int64_t)bin_start[bin] + slot;
+    if (pos < a.isect_cap) keys[pos] = ((unsigned long long)__float_as_uint(a.depths[i]) << 32) | (unsigned long long)(uint32_t)i;
+}
+
+// the queued large rects (culled mode): every warp pulls one splat at a time. SCATTER = false: count pass, true: scatter pass
+template <bool SCATTER>
+__global__ void __launch_bounds__(128)
+tile_big_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist, const int32_t *__restrict__ bin_start,
+                unsigned long long *__restrict__ keys, const int32_t *__restrict__ n_items, const int32_t *__restrict__ items,
+                int32_t *__restrict__ cursor) {
+    const int lane = threadIdx.x & 31;
+    const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
+    const int n = (int)min((int64_t)*n_items, a.isect_cap);
+    while (true) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(cursor, 1);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= n) break;
+        const int idx = items[it];
+        uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+        tile_rect(a, g, idx, x0, y0, x1, y1);   // (queued splats passed both tests)
+        shrink_rect(a, idx, x0, y0, x1, y1);
+        if (SCATTER)
+            walk_super_blocks(idx, x0, y0, x1 - x0, y1 - y0, conic, [&](int i, uint32_t x, uint32_t y) { scatter_tile(a, g, hist, bin_start, keys, conic, i, x, y); });
+        else
+            walk_super_blocks(idx, x0, y0, x1 - x0, y1 - y0, conic, [&](int i, uint32_t x, uint32_t y) { count_tile(a, g, hist, conic, i, x, y); });
+    }
+}
+
 __global__ void __launch_bounds__(256)
-tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist) {
+tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist, const BigQueue q) {
     const int nnz = a.counts->nnz;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = idx < nnz;
@@ -130,30 +207,30 @@ tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__r
     has = has && shrink_rect(a, idx, x0, y0, x1, y1);
     if (in && a.tiles_per_gauss && !a.conics) a.tiles_per_gauss[idx] = has ? (int32_t)((y1 - y0) * (x1 - x0)) : 0;
     const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
-    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) {
-        if (conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f))
-            return;
-        const int64_t cid = a.camera_ids ? a.camera_ids[i] : 0;
-        atomicAdd(hist + cid * g.n_tiles + y * g.tw + x, 1);
-        if (conic && a.tiles_per_gauss) atomicAdd(a.tiles_per_gauss + i, 1);  // culled mode: count the survivors
-    });
+    for_each_tile(has, x0, y0, x1, y1, idx, conic, q, [&](int i, uint32_t x, uint32_t y) { count_tile(a, g, hist, conic, i, x, y); });
 }
 
 // exclusive scan of hist[n] -> offsets[n] (int32 output tensor) and bin_start[n+1]; hist is left
 // intact (the scatter pass counts it down). Single CTA.
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(const int32_t *__restrict__ hist, int32_t *__restrict__ offsets, int32_t *__restrict__ bin_start,
-                 int n, gssdf_counts *counts, int64_t isect_cap) {
+                 int n, gssdf_counts *counts, int64_t isect_cap, int32_t *__restrict__ big, int t1, int t2) {
+    // big: [count of bins with t1 < size <= t2 | count of bins with size > t2 | ids of the first kind [n] | ids of the second kind [n]]:
+    // the two large sort tiers walk these (usually empty) lists instead of all bins
     __shared__ int s_warp[32];
     __shared__ int s_carry, s_max;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_carry = 0; s_max = 0; }
+    if (tid == 0) { s_carry = 0; s_max = 0; big[0] = 0; big[1] = 0; }
     __syncthreads();
     int local_max = 0;
     for (int base = 0; base < n; base += 1024) {
         const int i = base + tid;
         const int v = i < n ? hist[i] : 0;
         local_max = max(local_max, v);
+        if (v > t1) {
+            const int kind = v > t2 ? 1 : 0;
+            big[2 + kind * n + atomicAdd(big + kind, 1)] = i;
+        }
         int x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -185,32 +262,22 @@ tile_scan_kernel(const int32_t *__restrict__ hist, int32_t *__restrict__ offsets
         const int total = s_carry;
         bin_start[n] = total;
         counts->n_isects = (int32_t)min((int64_t)total, isect_cap);
-        counts->isect_overflow = (int64_t)total > isect_cap ? 1 : 0;
+        if ((int64_t)total > isect_cap) counts->isect_overflow = 1;  // (cleared by the host call; the queueing pass may have raised it)
         counts->max_tile_count = s_max;
     }
 }
 
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist,
-                    const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys) {
+                    const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys, const BigQueue q) {
     const int nnz = a.counts->nnz;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = idx < nnz;
     uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     bool has = in && tile_rect(a, g, idx, x0, y0, x1, y1);
     has = has && shrink_rect(a, idx, x0, y0, x1, y1);
-    const int64_t cap = a.isect_cap;
     const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
-    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) {
-        if (conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f))
-            return;  // the same test, on the same inputs, as in tile_count_kernel
-        const int64_t cid = a.camera_ids ? a.camera_ids[i] : 0;
-        const int64_t bin = cid * g.n_tiles + y * g.tw + x;
-        const int slot = atomicSub(hist + bin, 1) - 1;  // fills the bin back to front
-        const int64_t pos = (int64_t)bin_start[bin] + slot;
-        if (pos < cap)
-            keys[pos] = ((unsigned long long)__float_as_uint(a.depths[i]) << 32) | (unsigned long long)(uint32_t)i;
-    });
+    for_each_tile(has, x0, y0, x1, y1, idx, conic, q, [&](int i, uint32_t x, uint32_t y) { scatter_tile(a, g, hist, bin_start, keys, conic, i, x, y); });
 }
 
 // All-ascending bitonic network over v[0..n) (virtual +inf padding beyond n): flip step then
@@ -251,11 +318,15 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long *v, int n) {
 template <int S, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 tile_sort_kernel(const TileGeom g, const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys,
-                 int lo, int hi, int64_t isect_cap, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids, int n_bins) {
+                 int lo, int hi, int64_t isect_cap, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids, int n_bins,
+                 const int32_t *__restrict__ bin_list, const int32_t *__restrict__ n_list) {
     extern __shared__ __align__(16) unsigned long long s_keys[];
-    // grid-stride over the bins: the two large tiers are launched with one CTA per SM and usually find no bin of their size at all
-    // (a dedicated CTA per bin cost 50 us per step in launches that exit immediately)
-    for (int bin = blockIdx.x; bin < n_bins; bin += gridDim.x) {
+    // the first tier runs one CTA per bin; the two large tiers are launched with a CTA or two per SM and walk the list of bins of
+    // their size written by tile_scan_kernel (usually empty: a CTA per bin cost 50 us per step in launches that exit immediately,
+    // a grid-stride loop over all bins still 45 us)
+    const int n_iter = bin_list ? *n_list : n_bins;
+    for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
+    const int bin = bin_list ? bin_list[it] : it;
     const int64_t rs = min((int64_t)bin_start[bin], isect_cap), re = min((int64_t)bin_start[bin + 1], isect_cap);
     const int n = (int)(re - rs);
     if (n <= lo || n > hi) continue;  // CTA-uniform
@@ -299,7 +370,8 @@ extern "C" size_t gssdf_tile_encode_workspace_bytes(int32_t C, int32_t W, int32_
     if (tile_size <= 0) return 0;
     const TileGeom g = make_geom(W, H, tile_size);
     const size_t bins = (size_t)(C > 0 ? C : 1) * g.n_tiles;
-    return align_up(bins * 4, 256) + align_up((bins + 1) * 4, 256) + align_up((size_t)(isect_cap > 0 ? isect_cap : 1) * 8, 256);
+    return align_up(bins * 4, 256) + align_up((bins + 1) * 4, 256) + align_up((size_t)(isect_cap > 0 ? isect_cap : 1) * 8, 256) +
+           align_up((2 * bins + 2) * 4, 256) + 256 + align_up((size_t)(isect_cap > 0 ? isect_cap : 1) * 4, 256);
 }
 
 extern "C" int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t stream) {
@@ -323,35 +395,56 @@ extern "C" int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t
     int32_t *bin_start = reinterpret_cast<int32_t *>(ws);
     ws += align_up((size_t)(bins + 1) * 4, 256);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws);
+    ws += align_up((size_t)(a->isect_cap > 0 ? a->isect_cap : 1) * 8, 256);
+    int32_t *big = reinterpret_cast<int32_t *>(ws);
+    ws += align_up((size_t)(2 * bins + 2) * 4, 256);
+    int32_t *qctr = reinterpret_cast<int32_t *>(ws);  // [queued splats | cursor of the count pass | cursor of the scatter pass]
+    ws += 256;
+    int32_t *qitems = reinterpret_cast<int32_t *>(ws);
+    constexpr int S0 = 2048, S1 = 8192, S2 = 28672;
+    const bool queue = a->conics != nullptr && a->isect_cap > 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    BigQueue q{queue ? qctr : nullptr, qitems, a->isect_cap, &a->counts->isect_overflow, true};
 
     GSSDF_REQUIRE(!a->conics || (a->tile_size == 16 && ((uintptr_t)a->conics & 15) == 0), GSSDF_EINVAL,
                   "tile_encode: footprint culling (conics) needs tile_size 16 and a 16-byte aligned conic array");
     GSSDF_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)bins * 4, st));
     GSSDF_CUDA_OK(cudaMemsetAsync(&a->counts->n_isects_aabb, 0, 4, st));
+    GSSDF_CUDA_OK(cudaMemsetAsync(&a->counts->isect_overflow, 0, 4, st));
     if (a->conics && a->tiles_per_gauss && a->cap > 0) GSSDF_CUDA_OK(cudaMemsetAsync(a->tiles_per_gauss, 0, (size_t)a->cap * 4, st));
     if (a->cap > 0) {
         GSSDF_REQUIRE(a->means2d && a->radii && a->depths && a->flatten_ids, GSSDF_EINVAL, "tile_encode: null input/output");
-        tile_count_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist);
+        if (queue) GSSDF_CUDA_OK(cudaMemsetAsync(qctr, 0, 16, st));
+        tile_count_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist, q);
         GSSDF_LAUNCH_OK("tile_count_kernel");
+        if (queue) {
+            tile_big_kernel<false><<<4 * sms, 128, 0, st>>>(*a, g, hist, nullptr, nullptr, qctr, qitems, qctr + 1);
+            GSSDF_LAUNCH_OK("tile_big_kernel<count>");
+        }
     }
-    tile_scan_kernel<<<1, 1024, 0, st>>>(hist, a->offsets, bin_start, bins, a->counts, a->isect_cap);
+    tile_scan_kernel<<<1, 1024, 0, st>>>(hist, a->offsets, bin_start, bins, a->counts, a->isect_cap, big, S0, S1);
     GSSDF_LAUNCH_OK("tile_scan_kernel");
     if (a->cap == 0 || a->isect_cap == 0) return GSSDF_OK;
-    tile_scatter_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist, bin_start, keys);
+    q.append = false;
+    tile_scatter_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist, bin_start, keys, q);
     GSSDF_LAUNCH_OK("tile_scatter_kernel");
+    if (queue) {
+        tile_big_kernel<true><<<4 * sms, 128, 0, st>>>(*a, g, hist, bin_start, keys, qctr, qitems, qctr + 2);
+        GSSDF_LAUNCH_OK("tile_big_kernel<scatter>");
+    }
 
-    constexpr int S0 = 2048, S1 = 8192, S2 = 28672;
     GSSDF_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<S1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1 * 8));
     GSSDF_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<S2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2 * 8));
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    tile_sort_kernel<S0, 256><<<bins, 256, S0 * 8, st>>>(g, bin_start, keys, 0, S0, a->isect_cap, a->isect_ids, a->flatten_ids, bins);
+    tile_sort_kernel<S0, 256><<<bins, 256, S0 * 8, st>>>(g, bin_start, keys, 0, S0, a->isect_cap, a->isect_ids, a->flatten_ids, bins, nullptr, nullptr);
     GSSDF_LAUNCH_OK("tile_sort_kernel<2048>");
-    tile_sort_kernel<S1, 512><<<std::min(bins, 2 * sms), 512, S1 * 8, st>>>(g, bin_start, keys, S0, S1, a->isect_cap, a->isect_ids, a->flatten_ids, bins);
+    // (list mode: every listed bin is sorted whatever its size after clamping to isect_cap)
+    tile_sort_kernel<S1, 512><<<std::min(bins, 2 * sms), 512, S1 * 8, st>>>(g, bin_start, keys, 0, S1, a->isect_cap, a->isect_ids, a->flatten_ids, bins,
+                                                                           big + 2, big);
     GSSDF_LAUNCH_OK("tile_sort_kernel<8192>");
-    tile_sort_kernel<S2, 1024><<<std::min(bins, sms), 1024, S2 * 8, st>>>(g, bin_start, keys, S1, 0x7fffffff, a->isect_cap, a->isect_ids,
-                                                                         a->flatten_ids, bins);
+    tile_sort_kernel<S2, 1024><<<std::min(bins, sms), 1024, S2 * 8, st>>>(g, bin_start, keys, 0, 0x7fffffff, a->isect_cap, a->isect_ids,
+                                                                         a->flatten_ids, bins, big + 2 + bins, big + 1);
     GSSDF_LAUNCH_OK("tile_sort_kernel<28672>");
     return GSSDF_OK;
 }
