@@ -40,8 +40,6 @@ static SsimWindow make_window() {  // loss_utils.cpp:6-14 (float tensor, normali
     return g;
 }
 
-__device__ __forceinline__ float chan(const float4 &v, int ch) { return ch == 0 ? v.x : (ch == 1 ? v.y : v.z); }
-
 // grid (strips / kSsimWarps, bands, C * 3); band_h rows per band
 __global__ void __launch_bounds__(kSsimWarps * 32)
 dssim_fwd_kernel(const gssdf_dssim_loss_args a, const SsimWindow win, float *__restrict__ maps, float scale_loss, int band_h) {
@@ -52,8 +50,10 @@ dssim_fwd_kernel(const gssdf_dssim_loss_args a, const SsimWindow win, float *__r
     if (x0 >= W) return;  // (whole warp; no CTA-wide barrier below)
     const int cam = blockIdx.z / 3, ch = blockIdx.z % 3;
     const int y0 = blockIdx.y * band_h, y1 = min(y0 + band_h, H);
-    const float4 *X = reinterpret_cast<const float4 *>(a.out_colors) + (int64_t)cam * H * W;
-    const float4 *Y = reinterpret_cast<const float4 *>(a.gt) + (int64_t)cam * H * W;
+    // channel ch of pixel p is the scalar at 4 p + ch: loaded as a scalar so that nothing has to wait for the load before the next row
+    // step consumes it (a float4 load + component select stalled every warp once per row: long_scoreboard was the top stall)
+    const float *X = a.out_colors + (int64_t)cam * H * W * 4 + ch;
+    const float *Y = a.gt + (int64_t)cam * H * W * 4 + ch;
     const int64_t P = (int64_t)H * W, CP = (int64_t)a.C * 3 * P;
     const int64_t map_base = ((int64_t)cam * 3 + ch) * P;
     const int px = x0 + lane;
@@ -63,8 +63,8 @@ dssim_fwd_kernel(const gssdf_dssim_loss_args a, const SsimWindow win, float *__r
     auto fetch = [&](int yy, float &xa, float &ya, float &xb, float &yb) {
         xa = ya = xb = yb = 0.f;  // conv2d zero padding
         if (yy < 0 || yy >= H) return;
-        if (ina) { xa = chan(__ldg(X + (int64_t)yy * W + ca), ch); ya = chan(__ldg(Y + (int64_t)yy * W + ca), ch); }
-        if (inb) { xb = chan(__ldg(X + (int64_t)yy * W + cb), ch); yb = chan(__ldg(Y + (int64_t)yy * W + cb), ch); }
+        if (ina) { xa = __ldg(X + ((int64_t)yy * W + ca) * 4); ya = __ldg(Y + ((int64_t)yy * W + ca) * 4); }
+        if (inb) { xb = __ldg(X + ((int64_t)yy * W + cb) * 4); yb = __ldg(Y + ((int64_t)yy * W + cb) * 4); }
     };
     float acc[kWin][5];
 #pragma unroll
@@ -158,6 +158,14 @@ dssim_bwd_kernel(const gssdf_dssim_loss_args a, const SsimWindow win, const floa
     fetch(y0 - kHalf, va, vb);
     const float *Xc = a.out_colors + (int64_t)cam * P * 4 + ch, *Yc = a.gt + (int64_t)cam * P * 4 + ch;
     float *Vc = a.v_out_colors + (int64_t)cam * P * 4 + ch;
+    // x, y and the cotangent of the output row completed by the NEXT row step are loaded one step ahead as well
+    float xc = 0.f, yc = 0.f, vc = 0.f;
+    auto fetch_out = [&](int py) {
+        if (py >= y0 && py < y1 && px < W) {
+            const int64_t pix = ((int64_t)py * W + px) * 4;
+            xc = __ldg(Xc + pix); yc = __ldg(Yc + pix); vc = Vc[pix];
+        }
+    };
     const int n_in = (y1 - y0) + 2 * kHalf;
     for (int base = 0; base < n_in; base += kWin) {
 #pragma unroll
@@ -187,12 +195,11 @@ dssim_bwd_kernel(const gssdf_dssim_loss_args a, const SsimWindow win, const floa
                 }
                 const int k_out = (j - (kWin - 1) + kWin) % kWin;
                 const int py = y0 + i - (kWin - 1);
-                if (i >= kWin - 1 && py < y1 && px < W) {
-                    const int64_t pix = ((int64_t)py * W + px) * 4;  // one owner per (pixel, channel): plain read-modify-write, depth untouched
-                    const float xc = __ldg(Xc + pix), yc = __ldg(Yc + pix);
-                    Vc[pix] += scale_grad * (acc[k_out][0] + 2.f * xc * acc[k_out][1] + yc * acc[k_out][2]);
+                if (i >= kWin - 1 && py < y1 && px < W) {  // one owner per (pixel, channel): plain read-modify-write, depth untouched
+                    Vc[((int64_t)py * W + px) * 4] = vc + scale_grad * (acc[k_out][0] + 2.f * xc * acc[k_out][1] + yc * acc[k_out][2]);
                 }
                 acc[k_out][0] = acc[k_out][1] = acc[k_out][2] = 0.f;
+                fetch_out(py + 1);
             }
         }
     }
@@ -207,21 +214,23 @@ extern "C" size_t gssdf_dssim_workspace_bytes(int32_t C, int32_t W, int32_t H) {
     return (size_t)9 * C * W * H * sizeof(float);
 }
 
-// rows per band. The kernels are throughput-bound per SM, so the launch costs ~ ceil(CTAs / SMs) x (band + 10) row steps of one CTA;
-// a taller band amortises the 10 halo rows, a shorter one balances the SMs. At least ~4 CTAs (16 warps) per SM are kept for latency
-// hiding when the image is large enough.
-static int ssim_band_height(int W, int H, int C) {
-    int dev = 0, sms = 148;
+// rows per band: a warp marches (band + 10) row steps and the launch takes ceil(CTAs / resident CTAs) rounds of them (the kernels
+// run at the latency of a row step, not at an SM throughput limit: ncu, profiles/): a taller band amortises the 10 halo rows, a
+// partial last round wastes most of a round. Ties go to the shorter band.
+static int ssim_band_height(const void *kernel, int W, int H, int C) {
+    int dev = 0, sms = 148, per_sm = 4;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSsimWarps * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    const int64_t slots = (int64_t)sms * per_sm;
     const int64_t per_band = (int64_t)cdiv(cdiv(W, kStrip), kSsimWarps) * 3 * C;
     int best = 16;
     int64_t best_cost = INT64_MAX;
     for (int band = 16; band <= 128; band += 8) {
         const int64_t ctas = per_band * cdiv(H, band);
-        if (band > 16 && ctas < 4 * (int64_t)sms) break;
-        const int64_t cost = cdiv(ctas, (int64_t)sms) * (band + 2 * kHalf);
+        const int64_t cost = cdiv(ctas, slots) * (band + 2 * kHalf);
         if (cost < best_cost) { best_cost = cost; best = band; }
+        if (ctas <= slots / 2) break;  // fewer CTAs than half the slots: taller bands only lose parallelism
     }
     return best;
 }
@@ -238,12 +247,12 @@ extern "C" int gssdf_dssim_loss(const gssdf_dssim_loss_args *a, gssdf_stream_t s
     cudaStream_t st = (cudaStream_t)stream;
     const int gx = cdiv(cdiv(a->image_width, kStrip), kSsimWarps);
     {
-        const int band = ssim_band_height(a->image_width, a->image_height, a->C);
+        const int band = ssim_band_height((const void *)dssim_fwd_kernel, a->image_width, a->image_height, a->C);
         dssim_fwd_kernel<<<dim3(gx, cdiv(a->image_height, band), a->C * 3), kSsimWarps * 32, 0, st>>>(*a, win, maps, (float)(a->w_dssim / n), band);
         GSSDF_LAUNCH_OK("dssim_fwd_kernel");
     }
     if (a->v_out_colors) {
-        const int band = ssim_band_height(a->image_width, a->image_height, a->C);
+        const int band = ssim_band_height((const void *)dssim_bwd_kernel, a->image_width, a->image_height, a->C);
         dssim_bwd_kernel<<<dim3(gx, cdiv(a->image_height, band), a->C * 3), kSsimWarps * 32, 0, st>>>(*a, win, maps, (float)(-a->w_dssim / n), band);
         GSSDF_LAUNCH_OK("dssim_bwd_kernel");
     }
