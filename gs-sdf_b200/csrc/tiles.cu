@@ -91,22 +91,11 @@ __device__ __forceinline__ void walk_super_blocks(int bidx, uint32_t bx0, uint32
     }
 }
 
-// The large rects of the culled mode are not walked by the warp that finds them (a warp holding several screen-filling splats would
-// decide the kernel's duration: one wave of CTAs, 36 % of the issue slots used) but queued -- one aggregated atomic per warp -- for
-// tile_big_kernel, whose warps pull them from the queue one at a time.
-struct BigQueue {
-    int32_t *count;     // number of queued splats (device counter), or nullptr: walk in place
-    int32_t *items;     // [cap]
-    int64_t cap;        // = isect_cap: more queued splats than intersection slots cannot happen without an intersection overflow
-    int32_t *overflow;  // -> gssdf_counts::isect_overflow, raised if it happens all the same
-    bool append;        // false: the queue was filled by an earlier pass, just skip the large rects
-};
-
 // Visit every tile of every splat's rect. Small rects are walked by their own thread; rects with
 // >= 32 tiles are walked cooperatively by the warp (a screen-filling splat touches ~8k tiles).
 template <typename F>
 __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, int idx,
-                                              const float4 *__restrict__ conic, const BigQueue &q, F &&f) {
+                                              const float4 *__restrict__ conic, F &&f) {
     const uint32_t w = has ? x1 - x0 : 0, h = has ? y1 - y0 : 0;
     const uint32_t cnt = w * h;
     const bool big = cnt >= 32;
@@ -116,20 +105,6 @@ __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0
     }
     unsigned m = __ballot_sync(0xffffffffu, big);
     const int lane = threadIdx.x & 31;
-    if (conic && q.count) {  // warp-uniform
-        const unsigned mq = __ballot_sync(0xffffffffu, cnt >= 256);
-        if (mq && q.append) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(q.count, __popc(mq));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (cnt >= 256) {
-                const int64_t slot = (int64_t)base + __popc(mq & ((1u << lane) - 1u));
-                if (slot < q.cap) q.items[slot] = idx;
-                else *q.overflow = 1;
-            }
-        }
-        m &= ~mq;
-    }
     while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
@@ -165,33 +140,8 @@ __device__ __forceinline__ void scatter_tile(const gssdf_tile_encode_args &a, co
     if (pos < a.isect_cap) keys[pos] = ((unsigned long long)__float_as_uint(a.depths[i]) << 32) | (unsigned long long)(uint32_t)i;
 }
 
-// the queued large rects (culled mode): every warp pulls one splat at a time. SCATTER = false: count pass, true: scatter pass
-template <bool SCATTER>
-__global__ void __launch_bounds__(128)
-tile_big_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist, const int32_t *__restrict__ bin_start,
-                unsigned long long *__restrict__ keys, const int32_t *__restrict__ n_items, const int32_t *__restrict__ items,
-                int32_t *__restrict__ cursor) {
-    const int lane = threadIdx.x & 31;
-    const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
-    const int n = (int)min((int64_t)*n_items, a.isect_cap);
-    while (true) {
-        int it = 0;
-        if (lane == 0) it = atomicAdd(cursor, 1);
-        it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= n) break;
-        const int idx = items[it];
-        uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-        tile_rect(a, g, idx, x0, y0, x1, y1);   // (queued splats passed both tests)
-        shrink_rect(a, idx, x0, y0, x1, y1);
-        if (SCATTER)
-            walk_super_blocks(idx, x0, y0, x1 - x0, y1 - y0, conic, [&](int i, uint32_t x, uint32_t y) { scatter_tile(a, g, hist, bin_start, keys, conic, i, x, y); });
-        else
-            walk_super_blocks(idx, x0, y0, x1 - x0, y1 - y0, conic, [&](int i, uint32_t x, uint32_t y) { count_tile(a, g, hist, conic, i, x, y); });
-    }
-}
-
 __global__ void __launch_bounds__(256)
-tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist, const BigQueue q) {
+tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist) {
     const int nnz = a.counts->nnz;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = idx < nnz;
@@ -207,7 +157,7 @@ tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__r
     has = has && shrink_rect(a, idx, x0, y0, x1, y1);
     if (in && a.tiles_per_gauss && !a.conics) a.tiles_per_gauss[idx] = has ? (int32_t)((y1 - y0) * (x1 - x0)) : 0;
     const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
-    for_each_tile(has, x0, y0, x1, y1, idx, conic, q, [&](int i, uint32_t x, uint32_t y) { count_tile(a, g, hist, conic, i, x, y); });
+    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) { count_tile(a, g, hist, conic, i, x, y); });
 }
 
 // exclusive scan of hist[n] -> offsets[n] (int32 output tensor) and bin_start[n+1]; hist is left
@@ -262,14 +212,14 @@ tile_scan_kernel(const int32_t *__restrict__ hist, int32_t *__restrict__ offsets
         const int total = s_carry;
         bin_start[n] = total;
         counts->n_isects = (int32_t)min((int64_t)total, isect_cap);
-        if ((int64_t)total > isect_cap) counts->isect_overflow = 1;  // (cleared by the host call; the queueing pass may have raised it)
+        counts->isect_overflow = (int64_t)total > isect_cap ? 1 : 0;
         counts->max_tile_count = s_max;
     }
 }
 
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist,
-                    const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys, const BigQueue q) {
+                    const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys) {
     const int nnz = a.counts->nnz;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = idx < nnz;
@@ -277,7 +227,7 @@ tile_scatter_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *_
     bool has = in && tile_rect(a, g, idx, x0, y0, x1, y1);
     has = has && shrink_rect(a, idx, x0, y0, x1, y1);
     const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
-    for_each_tile(has, x0, y0, x1, y1, idx, conic, q, [&](int i, uint32_t x, uint32_t y) { scatter_tile(a, g, hist, bin_start, keys, conic, i, x, y); });
+    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) { scatter_tile(a, g, hist, bin_start, keys, conic, i, x, y); });
 }
 
 // All-ascending bitonic network over v[0..n) (virtual +inf padding beyond n): flip step then
@@ -371,7 +321,7 @@ extern "C" size_t gssdf_tile_encode_workspace_bytes(int32_t C, int32_t W, int32_
     const TileGeom g = make_geom(W, H, tile_size);
     const size_t bins = (size_t)(C > 0 ? C : 1) * g.n_tiles;
     return align_up(bins * 4, 256) + align_up((bins + 1) * 4, 256) + align_up((size_t)(isect_cap > 0 ? isect_cap : 1) * 8, 256) +
-           align_up((2 * bins + 2) * 4, 256) + 256 + align_up((size_t)(isect_cap > 0 ? isect_cap : 1) * 4, 256);
+           align_up((2 * bins + 2) * 4, 256);
 }
 
 extern "C" int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t stream) {
@@ -397,43 +347,26 @@ extern "C" int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws);
     ws += align_up((size_t)(a->isect_cap > 0 ? a->isect_cap : 1) * 8, 256);
     int32_t *big = reinterpret_cast<int32_t *>(ws);
-    ws += align_up((size_t)(2 * bins + 2) * 4, 256);
-    int32_t *qctr = reinterpret_cast<int32_t *>(ws);  // [queued splats | cursor of the count pass | cursor of the scatter pass]
-    ws += 256;
-    int32_t *qitems = reinterpret_cast<int32_t *>(ws);
     constexpr int S0 = 2048, S1 = 8192, S2 = 28672;
-    const bool queue = a->conics != nullptr && a->isect_cap > 0;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    BigQueue q{queue ? qctr : nullptr, qitems, a->isect_cap, &a->counts->isect_overflow, true};
 
     GSSDF_REQUIRE(!a->conics || (a->tile_size == 16 && ((uintptr_t)a->conics & 15) == 0), GSSDF_EINVAL,
                   "tile_encode: footprint culling (conics) needs tile_size 16 and a 16-byte aligned conic array");
     GSSDF_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)bins * 4, st));
     GSSDF_CUDA_OK(cudaMemsetAsync(&a->counts->n_isects_aabb, 0, 4, st));
-    GSSDF_CUDA_OK(cudaMemsetAsync(&a->counts->isect_overflow, 0, 4, st));
     if (a->conics && a->tiles_per_gauss && a->cap > 0) GSSDF_CUDA_OK(cudaMemsetAsync(a->tiles_per_gauss, 0, (size_t)a->cap * 4, st));
     if (a->cap > 0) {
         GSSDF_REQUIRE(a->means2d && a->radii && a->depths && a->flatten_ids, GSSDF_EINVAL, "tile_encode: null input/output");
-        if (queue) GSSDF_CUDA_OK(cudaMemsetAsync(qctr, 0, 16, st));
-        tile_count_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist, q);
+        tile_count_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist);
         GSSDF_LAUNCH_OK("tile_count_kernel");
-        if (queue) {
-            tile_big_kernel<false><<<4 * sms, 128, 0, st>>>(*a, g, hist, nullptr, nullptr, qctr, qitems, qctr + 1);
-            GSSDF_LAUNCH_OK("tile_big_kernel<count>");
-        }
     }
     tile_scan_kernel<<<1, 1024, 0, st>>>(hist, a->offsets, bin_start, bins, a->counts, a->isect_cap, big, S0, S1);
     GSSDF_LAUNCH_OK("tile_scan_kernel");
     if (a->cap == 0 || a->isect_cap == 0) return GSSDF_OK;
-    q.append = false;
-    tile_scatter_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist, bin_start, keys, q);
+    tile_scatter_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist, bin_start, keys);
     GSSDF_LAUNCH_OK("tile_scatter_kernel");
-    if (queue) {
-        tile_big_kernel<true><<<4 * sms, 128, 0, st>>>(*a, g, hist, bin_start, keys, qctr, qitems, qctr + 2);
-        GSSDF_LAUNCH_OK("tile_big_kernel<scatter>");
-    }
 
     GSSDF_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<S1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1 * 8));
     GSSDF_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<S2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2 * 8));
