@@ -95,11 +95,11 @@ __device__ __forceinline__ void walk_super_blocks(int bidx, uint32_t bx0, uint32
 // >= 32 tiles are walked cooperatively by the warp (a screen-filling splat touches ~8k tiles).
 template <typename F>
 __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, int idx,
-                                              const float4 *__restrict__ conic, F &&f) {
+                                              const float4 *__restrict__ conic, F &&f, bool do_small = true) {
     const uint32_t w = has ? x1 - x0 : 0, h = has ? y1 - y0 : 0;
     const uint32_t cnt = w * h;
     const bool big = cnt >= 32;
-    if (has && !big) {
+    if (has && !big && do_small) {
         for (uint32_t y = y0; y < y1; ++y)
             for (uint32_t x = x0; x < x1; ++x) f(idx, x, y);
     }
@@ -120,18 +120,20 @@ __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0
     }
 }
 
-__device__ __forceinline__ void count_tile(const gssdf_tile_encode_args &a, const TileGeom &g, int32_t *__restrict__ hist,
+__device__ __forceinline__ bool count_tile(const gssdf_tile_encode_args &a, const TileGeom &g, int32_t *__restrict__ hist,
                                            const float4 *__restrict__ conic, int i, uint32_t x, uint32_t y) {
-    if (conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f)) return;
+    if (conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f))
+        return false;
     const int64_t cid = a.camera_ids ? a.camera_ids[i] : 0;
     atomicAdd(hist + cid * g.n_tiles + y * g.tw + x, 1);
     if (conic && a.tiles_per_gauss) atomicAdd(a.tiles_per_gauss + i, 1);  // culled mode: count the survivors
+    return true;
 }
 
 __device__ __forceinline__ void scatter_tile(const gssdf_tile_encode_args &a, const TileGeom &g, int32_t *__restrict__ hist,
                                              const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys,
-                                             const float4 *__restrict__ conic, int i, uint32_t x, uint32_t y) {
-    if (conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f))
+                                             const float4 *__restrict__ conic, int i, uint32_t x, uint32_t y, bool test = true) {
+    if (test && conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f))
         return;  // the same test, on the same inputs, as in the count pass
     const int64_t cid = a.camera_ids ? a.camera_ids[i] : 0;
     const int64_t bin = cid * g.n_tiles + y * g.tw + x;
@@ -141,7 +143,7 @@ __device__ __forceinline__ void scatter_tile(const gssdf_tile_encode_args &a, co
 }
 
 __global__ void __launch_bounds__(256)
-tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist) {
+tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist, uint32_t *__restrict__ small_mask) {
     const int nnz = a.counts->nnz;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = idx < nnz;
@@ -157,7 +159,19 @@ tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__r
     has = has && shrink_rect(a, idx, x0, y0, x1, y1);
     if (in && a.tiles_per_gauss && !a.conics) a.tiles_per_gauss[idx] = has ? (int32_t)((y1 - y0) * (x1 - x0)) : 0;
     const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
-    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) { count_tile(a, g, hist, conic, i, x, y); });
+    if (small_mask) {
+        // culled mode: a rect of fewer than 32 tiles (walked by its own thread) leaves the outcome of its tile tests as one bit per tile
+        // for the scatter pass, which then neither repeats the tests nor visits the tiles that failed
+        uint32_t mk = 0u;
+        if (has && (x1 - x0) * (y1 - y0) < 32u) {
+            uint32_t t = 0;
+            for (uint32_t y = y0; y < y1; ++y)
+                for (uint32_t x = x0; x < x1; ++x, ++t)
+                    if (count_tile(a, g, hist, conic, idx, x, y)) mk |= 1u << t;
+        }
+        if (in) small_mask[idx] = mk;
+    }
+    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) { count_tile(a, g, hist, conic, i, x, y); }, small_mask == nullptr);
 }
 
 // exclusive scan of hist[n] -> offsets[n] (int32 output tensor) and bin_start[n+1]; hist is left
@@ -219,7 +233,7 @@ tile_scan_kernel(const int32_t *__restrict__ hist, int32_t *__restrict__ offsets
 
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist,
-                    const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys) {
+                    const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys, const uint32_t *__restrict__ small_mask) {
     const int nnz = a.counts->nnz;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = idx < nnz;
@@ -227,7 +241,18 @@ tile_scatter_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *_
     bool has = in && tile_rect(a, g, idx, x0, y0, x1, y1);
     has = has && shrink_rect(a, idx, x0, y0, x1, y1);
     const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
-    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) { scatter_tile(a, g, hist, bin_start, keys, conic, i, x, y); });
+    if (small_mask && has && (x1 - x0) * (y1 - y0) < 32u) {
+        uint32_t mk = small_mask[idx];
+        const uint32_t w = x1 - x0;
+        while (mk) {
+            const uint32_t t = (uint32_t)__ffs(mk) - 1u;
+            mk &= mk - 1u;
+            const uint32_t ty = t / w;
+            scatter_tile(a, g, hist, bin_start, keys, conic, idx, x0 + (t - ty * w), y0 + ty, false);
+        }
+    }
+    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) { scatter_tile(a, g, hist, bin_start, keys, conic, i, x, y); },
+                  small_mask == nullptr);
 }
 
 // All-ascending bitonic network over v[0..n) (virtual +inf padding beyond n): flip step then half-cleaners. Works on shared or global
@@ -398,18 +423,21 @@ extern "C" int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t
 
     GSSDF_REQUIRE(!a->conics || (a->tile_size == 16 && ((uintptr_t)a->conics & 15) == 0), GSSDF_EINVAL,
                   "tile_encode: footprint culling (conics) needs tile_size 16 and a 16-byte aligned conic array");
+    // culled mode: the per-splat tile-test masks of the small rects travel from the count to the scatter pass in the flatten_ids output
+    // buffer, which nothing reads or writes before the sort kernels fill it (needs one int32 per packed row)
+    uint32_t *small_mask = (a->conics && a->flatten_ids && (int64_t)a->cap <= a->isect_cap) ? reinterpret_cast<uint32_t *>(a->flatten_ids) : nullptr;
     GSSDF_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)bins * 4, st));
     GSSDF_CUDA_OK(cudaMemsetAsync(&a->counts->n_isects_aabb, 0, 4, st));
     if (a->conics && a->tiles_per_gauss && a->cap > 0) GSSDF_CUDA_OK(cudaMemsetAsync(a->tiles_per_gauss, 0, (size_t)a->cap * 4, st));
     if (a->cap > 0) {
         GSSDF_REQUIRE(a->means2d && a->radii && a->depths && a->flatten_ids, GSSDF_EINVAL, "tile_encode: null input/output");
-        tile_count_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist);
+        tile_count_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist, small_mask);
         GSSDF_LAUNCH_OK("tile_count_kernel");
     }
     tile_scan_kernel<<<1, 1024, 0, st>>>(hist, a->offsets, bin_start, bins, a->counts, a->isect_cap, big, S0, S1);
     GSSDF_LAUNCH_OK("tile_scan_kernel");
     if (a->cap == 0 || a->isect_cap == 0) return GSSDF_OK;
-    tile_scatter_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist, bin_start, keys);
+    tile_scatter_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist, bin_start, keys, small_mask);
     GSSDF_LAUNCH_OK("tile_scatter_kernel");
 
     GSSDF_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<S1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1 * 8));
