@@ -178,22 +178,22 @@ tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__r
 // intact (the scatter pass counts it down). Single CTA.
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(const int32_t *__restrict__ hist, int32_t *__restrict__ offsets, int32_t *__restrict__ bin_start,
-                 int n, gssdf_counts *counts, int64_t isect_cap, int32_t *__restrict__ big, int t1, int t2) {
-    // big: [count of bins with t1 < size <= t2 | count of bins with size > t2 | ids of the first kind [n] | ids of the second kind [n]]:
-    // the two large sort tiers walk these (usually empty) lists instead of all bins
+                 int n, gssdf_counts *counts, int64_t isect_cap, int32_t *__restrict__ big, int t0, int t1, int t2) {
+    // big: [counts of the bins with t0 < size <= t1, t1 < size <= t2, t2 < size | pad | ids of the first kind [n] | second [n] | third [n]]:
+    // the three larger sort tiers walk these lists (the last two usually empty) instead of all bins
     __shared__ int s_warp[32];
     __shared__ int s_carry, s_max;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_carry = 0; s_max = 0; big[0] = 0; big[1] = 0; }
+    if (tid == 0) { s_carry = 0; s_max = 0; big[0] = 0; big[1] = 0; big[2] = 0; }
     __syncthreads();
     int local_max = 0;
     for (int base = 0; base < n; base += 1024) {
         const int i = base + tid;
         const int v = i < n ? hist[i] : 0;
         local_max = max(local_max, v);
-        if (v > t1) {
-            const int kind = v > t2 ? 1 : 0;
-            big[2 + kind * n + atomicAdd(big + kind, 1)] = i;
+        if (v > t0) {
+            const int kind = v > t2 ? 2 : (v > t1 ? 1 : 0);
+            big[4 + kind * n + atomicAdd(big + kind, 1)] = i;
         }
         int x = v;
 #pragma unroll
@@ -390,7 +390,7 @@ extern "C" size_t gssdf_tile_encode_workspace_bytes(int32_t C, int32_t W, int32_
     const TileGeom g = make_geom(W, H, tile_size);
     const size_t bins = (size_t)(C > 0 ? C : 1) * g.n_tiles;
     return align_up(bins * 4, 256) + align_up((bins + 1) * 4, 256) + align_up((size_t)(isect_cap > 0 ? isect_cap : 1) * 8, 256) +
-           align_up((2 * bins + 2) * 4, 256);
+           align_up((3 * bins + 4) * 4, 256);
 }
 
 extern "C" int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t stream) {
@@ -416,7 +416,7 @@ extern "C" int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws);
     ws += align_up((size_t)(a->isect_cap > 0 ? a->isect_cap : 1) * 8, 256);
     int32_t *big = reinterpret_cast<int32_t *>(ws);
-    constexpr int S0 = 2048, S1 = 8192, S2 = 28672;
+    constexpr int SS = 256, S0 = 2048, S1 = 8192, S2 = 28672;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -434,7 +434,7 @@ extern "C" int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t
         tile_count_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist, small_mask);
         GSSDF_LAUNCH_OK("tile_count_kernel");
     }
-    tile_scan_kernel<<<1, 1024, 0, st>>>(hist, a->offsets, bin_start, bins, a->counts, a->isect_cap, big, S0, S1);
+    tile_scan_kernel<<<1, 1024, 0, st>>>(hist, a->offsets, bin_start, bins, a->counts, a->isect_cap, big, SS, S0, S1);
     GSSDF_LAUNCH_OK("tile_scan_kernel");
     if (a->cap == 0 || a->isect_cap == 0) return GSSDF_OK;
     tile_scatter_kernel<<<cdiv(a->cap, 256), 256, 0, st>>>(*a, g, hist, bin_start, keys, small_mask);
@@ -442,14 +442,19 @@ extern "C" int gssdf_tile_encode(const gssdf_tile_encode_args *a, gssdf_stream_t
 
     GSSDF_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<S1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1 * 8));
     GSSDF_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<S2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2 * 8));
-    tile_sort_kernel<S0, 256><<<bins, 256, S0 * 8, st>>>(g, bin_start, keys, 0, S0, a->isect_cap, a->isect_ids, a->flatten_ids, bins, nullptr, nullptr);
-    GSSDF_LAUNCH_OK("tile_sort_kernel<2048>");
+    // most bins hold a few hundred keys: one 64-thread CTA each (32 resident per SM hide the load -> sort -> store latency chain that a
+    // 256-thread CTA per bin, 8 per SM, exposed); the larger tiers walk the bin lists written by tile_scan_kernel.
     // (list mode: every listed bin is sorted whatever its size after clamping to isect_cap)
+    tile_sort_kernel<SS, 64><<<bins, 64, SS * 8, st>>>(g, bin_start, keys, 0, SS, a->isect_cap, a->isect_ids, a->flatten_ids, bins, nullptr, nullptr);
+    GSSDF_LAUNCH_OK("tile_sort_kernel<256>");
+    tile_sort_kernel<S0, 256><<<std::min(bins, 8 * sms), 256, S0 * 8, st>>>(g, bin_start, keys, 0, S0, a->isect_cap, a->isect_ids, a->flatten_ids, bins,
+                                                                           big + 4, big);
+    GSSDF_LAUNCH_OK("tile_sort_kernel<2048>");
     tile_sort_kernel<S1, 512><<<std::min(bins, 2 * sms), 512, S1 * 8, st>>>(g, bin_start, keys, 0, S1, a->isect_cap, a->isect_ids, a->flatten_ids, bins,
-                                                                           big + 2, big);
+                                                                           big + 4 + bins, big + 1);
     GSSDF_LAUNCH_OK("tile_sort_kernel<8192>");
     tile_sort_kernel<S2, 1024><<<std::min(bins, sms), 1024, S2 * 8, st>>>(g, bin_start, keys, 0, 0x7fffffff, a->isect_cap, a->isect_ids,
-                                                                         a->flatten_ids, bins, big + 2 + bins, big + 1);
+                                                                         a->flatten_ids, bins, big + 4 + 2 * bins, big + 2);
     GSSDF_LAUNCH_OK("tile_sort_kernel<28672>");
     return GSSDF_OK;
 }
