@@ -105,7 +105,12 @@ __device__ __forceinline__ float conic_min_rect(const Conic &q, float x0, float 
     return m;
 }
 
-// 8-bit warp mask of record t for the tile whose first pixel centre is (ox, oy) (global pixel coordinates)
+// 8-bit warp mask of a splat for the tile whose first pixel centre is (ox, oy) (global pixel coordinates): bit w is set if the footprint
+// conic reaches the 8x4-pixel block w (x half = w & 1, y quarter = w >> 1). The eight block rectangles share their boundaries
+// (x in {-m, 7.5, 15 + m}, y in {-m, 3.5, 7.5, 11.5, 15 + m}: each contains the pixel centres of its block plus the margin m, a
+// superset of the separate rectangles), so the minimum of Q over all of them comes from ONE pass over the 3 x 5 grid points, the 3
+// vertical and 5 horizontal grid lines (one critical point per line, which lies in exactly one segment) and the interior critical
+// point: ~280 instructions instead of nine independent conic_min_rect evaluations (~1100). Same closed form as conic_min_rect.
 __device__ __forceinline__ unsigned cull_mask(const float4 g0, const float4 g1, float ox, float oy) {
     // shift the conic to tile-local coordinates (x = ox + x')
     Conic q;
@@ -116,12 +121,52 @@ __device__ __forceinline__ unsigned cull_mask(const float4 g0, const float4 g1, 
     // every term of the normalised form is <= 1 over the image: fp32 evaluation error < ~1e-6
     const float tol = 4e-6f;
     const float m = 0.05f;  // margin in pixels
-    if (!(conic_min_rect(q, -m, 15.f + m, -m, 15.f + m) <= tol)) return 0u;
+    const float X[3] = {-m, 7.5f, 15.f + m}, Y[5] = {-m, 3.5f, 7.5f, 11.5f, 15.f + m};
     unsigned mask = 0u;
+    // grid points: a hit at (ix, iy) marks the (up to four) blocks around it
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        const float x0 = (w & 1) * 8.f, y0 = (w >> 1) * 4.f;
-        if (conic_min_rect(q, x0 - m, x0 + 7.f + m, y0 - m, y0 + 3.f + m) <= tol) mask |= 1u << w;
+    for (int iy = 0; iy < 5; ++iy) {
+        const float ty = (q.c * Y[iy] + 2.f * q.e) * Y[iy] + q.f, by = 2.f * (q.b * Y[iy] + q.d);
+#pragma unroll
+        for (int ix = 0; ix < 3; ++ix) {
+            const unsigned cols = (ix >= 1 ? 1u << (ix - 1) : 0u) | (ix <= 1 ? 1u << ix : 0u);
+            const unsigned around = (iy >= 1 ? cols << (2 * (iy - 1)) : 0u) | (iy <= 3 ? cols << (2 * iy) : 0u);
+            if ((q.a * X[ix] + by) * X[ix] + ty <= tol) mask |= around;
+        }
+    }
+    if (q.c > 0.f) {  // vertical grid lines: minimise over y
+        const float rc = 1.f / q.c;
+#pragma unroll
+        for (int ix = 0; ix < 3; ++ix) {
+            const float ys = -(q.b * X[ix] + q.e) * rc;
+            if (ys > Y[0] && ys < Y[4] && conic_eval(q, X[ix], ys) <= tol) {
+                const int iy = (ys > Y[1]) + (ys > Y[2]) + (ys > Y[3]);
+                const unsigned cols = (ix >= 1 ? 1u << (ix - 1) : 0u) | (ix <= 1 ? 1u << ix : 0u);
+                mask |= cols << (2 * iy);
+                // (ys exactly on a horizontal grid line: the two segments meet at a grid point already evaluated above)
+            }
+        }
+    }
+    if (q.a > 0.f) {  // horizontal grid lines: minimise over x
+        const float ra = 1.f / q.a;
+#pragma unroll
+        for (int iy = 0; iy < 5; ++iy) {
+            const float xs = -(q.b * Y[iy] + q.d) * ra;
+            if (xs > X[0] && xs < X[2] && conic_eval(q, xs, Y[iy]) <= tol) {
+                const int ix = xs > X[1] ? 1 : 0;
+                const unsigned rows = (iy >= 1 ? 1u << (2 * (iy - 1)) : 0u) | (iy <= 3 ? 1u << (2 * iy) : 0u);
+                mask |= rows << ix;
+            }
+        }
+    }
+    const float det = q.a * q.c - q.b * q.b;
+    if (q.a > 0.f && det > 0.f) {  // interior minimum (ellipse centre)
+        const float rd = 1.f / det;
+        const float cx = -(q.c * q.d - q.b * q.e) * rd, cy = -(q.a * q.e - q.b * q.d) * rd;
+        if (cx > X[0] && cx < X[2] && cy > Y[0] && cy < Y[4] && conic_eval(q, cx, cy) <= tol) {
+            const int ix = cx > X[1] ? 1 : 0, iy = (cy > Y[1]) + (cy > Y[2]) + (cy > Y[3]);
+            mask |= 1u << (2 * iy + ix);
+        }
     }
     return mask;
 }
