@@ -160,14 +160,18 @@ tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__r
     if (in && a.tiles_per_gauss && !a.conics) a.tiles_per_gauss[idx] = has ? (int32_t)((y1 - y0) * (x1 - x0)) : 0;
     const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
     if (small_mask) {
-        // culled mode: a rect of fewer than 32 tiles (walked by its own thread) leaves the outcome of its tile tests as one bit per tile
-        // for the scatter pass, which then neither repeats the tests nor visits the tiles that failed
+        // culled mode: a rect of fewer than 32 tiles is tested by its own thread for all its tiles at once (small_rect_mask) and leaves
+        // the outcome as one bit per tile for the scatter pass, which then neither repeats the tests nor visits the tiles that failed
         uint32_t mk = 0u;
         if (has && (x1 - x0) * (y1 - y0) < 32u) {
-            uint32_t t = 0;
-            for (uint32_t y = y0; y < y1; ++y)
-                for (uint32_t x = x0; x < x1; ++x, ++t)
-                    if (count_tile(a, g, hist, conic, idx, x, y)) mk |= 1u << t;
+            const uint32_t w = x1 - x0;
+            mk = small_rect_mask(__ldg(conic + kConicF4 * (int64_t)idx), __ldg(conic + kConicF4 * (int64_t)idx + 1), x0, y0, w, y1 - y0);
+            int32_t *row = hist + (a.camera_ids ? a.camera_ids[idx] : 0) * g.n_tiles;
+            for (uint32_t m2 = mk; m2; m2 &= m2 - 1u) {
+                const uint32_t t = (uint32_t)__ffs(m2) - 1u, ty = t / w;
+                atomicAdd(row + (y0 + ty) * g.tw + x0 + (t - ty * w), 1);
+            }
+            if (a.tiles_per_gauss && mk) atomicAdd(a.tiles_per_gauss + idx, __popc(mk));  // (zeroed by the host call)
         }
         if (in) small_mask[idx] = mk;
     }
