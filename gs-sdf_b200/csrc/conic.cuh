@@ -106,11 +106,10 @@ __device__ __forceinline__ float conic_min_rect(const Conic &q, float x0, float 
 }
 
 // 8-bit warp mask of a splat for the tile whose first pixel centre is (ox, oy) (global pixel coordinates): bit w is set if the footprint
-// conic reaches the 8x4-pixel block w (x half = w & 1, y quarter = w >> 1). The eight block rectangles share their boundaries
-// (x in {-m, 7.5, 15 + m}, y in {-m, 3.5, 7.5, 11.5, 15 + m}: each contains the pixel centres of its block plus the margin m, a
-// superset of the separate rectangles), so the minimum of Q over all of them comes from ONE pass over the 3 x 5 grid points, the 3
-// vertical and 5 horizontal grid lines (one critical point per line, which lies in exactly one segment) and the interior critical
-// point: ~280 instructions instead of nine independent conic_min_rect evaluations (~1100). Same closed form as conic_min_rect.
+// conic reaches the 8x4-pixel block w (x half = w & 1, y quarter = w >> 1), i.e. min Q over [x0 - m, x0 + 7 + m] x [y0 - m, y0 + 3 + m]
+// <= tol. All eight minima come from ONE pass over the 4 x 8 grid of the blocks' corner coordinates: the 32 grid points (each belongs to
+// one block), the critical point of each of the 4 vertical and 8 horizontal grid lines (it lies in at most one block's edge) and the
+// conic centre -- ~350 instructions instead of nine independent conic_min_rect evaluations (~1100), same closed form, same masks.
 __device__ __forceinline__ unsigned cull_mask(const float4 g0, const float4 g1, float ox, float oy) {
     // shift the conic to tile-local coordinates (x = ox + x')
     Conic q;
@@ -121,41 +120,38 @@ __device__ __forceinline__ unsigned cull_mask(const float4 g0, const float4 g1, 
     // every term of the normalised form is <= 1 over the image: fp32 evaluation error < ~1e-6
     const float tol = 4e-6f;
     const float m = 0.05f;  // margin in pixels
-    const float X[3] = {-m, 7.5f, 15.f + m}, Y[5] = {-m, 3.5f, 7.5f, 11.5f, 15.f + m};
+    const float X[4] = {-m, 7.f + m, 8.f - m, 15.f + m};
+    const float Y[8] = {-m, 3.f + m, 4.f - m, 7.f + m, 8.f - m, 11.f + m, 12.f - m, 15.f + m};
     unsigned mask = 0u;
-    // grid points: a hit at (ix, iy) marks the (up to four) blocks around it
 #pragma unroll
-    for (int iy = 0; iy < 5; ++iy) {
+    for (int iy = 0; iy < 8; ++iy) {  // grid points = block corners
         const float ty = (q.c * Y[iy] + 2.f * q.e) * Y[iy] + q.f, by = 2.f * (q.b * Y[iy] + q.d);
 #pragma unroll
-        for (int ix = 0; ix < 3; ++ix) {
-            const unsigned cols = (ix >= 1 ? 1u << (ix - 1) : 0u) | (ix <= 1 ? 1u << ix : 0u);
-            const unsigned around = (iy >= 1 ? cols << (2 * (iy - 1)) : 0u) | (iy <= 3 ? cols << (2 * iy) : 0u);
-            if ((q.a * X[ix] + by) * X[ix] + ty <= tol) mask |= around;
-        }
+        for (int ix = 0; ix < 4; ++ix)
+            if ((q.a * X[ix] + by) * X[ix] + ty <= tol) mask |= 1u << ((iy >> 1) * 2 + (ix >> 1));
     }
-    if (q.c > 0.f) {  // vertical grid lines: minimise over y
+    // position of a coordinate among the block intervals: even k = inside interval k / 2, odd = in the gap between two blocks
+    auto ky_of = [&](float y) { return (y > Y[1]) + (y > Y[2]) + (y > Y[3]) + (y > Y[4]) + (y > Y[5]) + (y > Y[6]); };
+    auto kx_of = [&](float x) { return (x > X[1]) + (x > X[2]); };
+    if (q.c > 0.f) {  // vertical block edges x = X[ix]: minimise over y
         const float rc = 1.f / q.c;
 #pragma unroll
-        for (int ix = 0; ix < 3; ++ix) {
+        for (int ix = 0; ix < 4; ++ix) {
             const float ys = -(q.b * X[ix] + q.e) * rc;
-            if (ys > Y[0] && ys < Y[4] && conic_eval(q, X[ix], ys) <= tol) {
-                const int iy = (ys > Y[1]) + (ys > Y[2]) + (ys > Y[3]);
-                const unsigned cols = (ix >= 1 ? 1u << (ix - 1) : 0u) | (ix <= 1 ? 1u << ix : 0u);
-                mask |= cols << (2 * iy);
-                // (ys exactly on a horizontal grid line: the two segments meet at a grid point already evaluated above)
+            if (ys > Y[0] && ys < Y[7]) {
+                const int k = ky_of(ys);
+                if (!(k & 1) && conic_eval(q, X[ix], ys) <= tol) mask |= 1u << ((k >> 1) * 2 + (ix >> 1));
             }
         }
     }
-    if (q.a > 0.f) {  // horizontal grid lines: minimise over x
+    if (q.a > 0.f) {  // horizontal block edges y = Y[iy]: minimise over x
         const float ra = 1.f / q.a;
 #pragma unroll
-        for (int iy = 0; iy < 5; ++iy) {
+        for (int iy = 0; iy < 8; ++iy) {
             const float xs = -(q.b * Y[iy] + q.d) * ra;
-            if (xs > X[0] && xs < X[2] && conic_eval(q, xs, Y[iy]) <= tol) {
-                const int ix = xs > X[1] ? 1 : 0;
-                const unsigned rows = (iy >= 1 ? 1u << (2 * (iy - 1)) : 0u) | (iy <= 3 ? 1u << (2 * iy) : 0u);
-                mask |= rows << ix;
+            if (xs > X[0] && xs < X[3]) {
+                const int k = kx_of(xs);
+                if (k != 1 && conic_eval(q, xs, Y[iy]) <= tol) mask |= 1u << ((iy >> 1) * 2 + (k >> 1));
             }
         }
     }
@@ -163,9 +159,9 @@ __device__ __forceinline__ unsigned cull_mask(const float4 g0, const float4 g1, 
     if (q.a > 0.f && det > 0.f) {  // interior minimum (ellipse centre)
         const float rd = 1.f / det;
         const float cx = -(q.c * q.d - q.b * q.e) * rd, cy = -(q.a * q.e - q.b * q.d) * rd;
-        if (cx > X[0] && cx < X[2] && cy > Y[0] && cy < Y[4] && conic_eval(q, cx, cy) <= tol) {
-            const int ix = cx > X[1] ? 1 : 0, iy = (cy > Y[1]) + (cy > Y[2]) + (cy > Y[3]);
-            mask |= 1u << (2 * iy + ix);
+        if (cx > X[0] && cx < X[3] && cy > Y[0] && cy < Y[7]) {
+            const int kx = kx_of(cx), ky = ky_of(cy);
+            if (kx != 1 && !(ky & 1) && conic_eval(q, cx, cy) <= tol) mask |= 1u << ((ky >> 1) * 2 + (kx >> 1));
         }
     }
     return mask;
