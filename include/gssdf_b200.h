@@ -220,7 +220,9 @@ typedef struct gssdf_tile_encode_args {
     size_t workspace_bytes;
     const float *conics;         /* NULL: reference-identical lists (every tile of the splat's radius AABB).
                                     [cap,8] from gssdf_splat_conics (tile_size must be 16): a (splat, tile) pair is dropped BEFORE the
-                                    sort when the splat's exact alpha >= 1/255 footprint misses the tile. tiles_per_gauss / offsets /
+                                    sort when the splat's exact alpha >= 1/255 footprint misses the tile's 16x16-pixel square (a few
+                                    pairs whose footprint only reaches the half-pixel rim between pixel centres and tile edge are
+                                    kept; the raster stage drops them). tiles_per_gauss / offsets /
                                     flatten_ids / n_isects then describe the culled lists: per tile a subset of the reference's list in
                                     the same order; every render output is unchanged (the dropped pairs cannot pass the kernel's
                                     alpha test anywhere in the tile). Used by the fused training step. */
