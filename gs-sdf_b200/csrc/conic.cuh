@@ -78,8 +78,7 @@ __device__ __forceinline__ float conic_eval(const Conic &q, float x, float y) {
 }
 
 // minimum of Q over the rectangle [x0,x1] x [y0,y1] (any conic type): corners, edge critical points, interior
-// critical point. Exact up to fp32 rounding, which the caller's tolerance absorbs. This is the closed form; cull_mask and
-// small_rect_mask below evaluate it for a whole grid of rectangles in one pass (shared points, one critical point per grid line).
+// critical point. Exact up to fp32 rounding, which the caller's tolerance absorbs.
 __device__ __forceinline__ float conic_min_rect(const Conic &q, float x0, float x1, float y0, float y1) {
     float m = fminf(fminf(conic_eval(q, x0, y0), conic_eval(q, x1, y0)), fminf(conic_eval(q, x0, y1), conic_eval(q, x1, y1)));
     if (q.c > 0.f) {  // edges x = const: minimise over y
@@ -169,9 +168,23 @@ __device__ __forceinline__ unsigned cull_mask(const float4 g0, const float4 g1, 
 }
 
 
+// does the conic touch the pixel-centre rectangle [ox, ox + wpx] x [oy, oy + hpx] (global pixel coordinates, + 0.05 px)?
+__device__ __forceinline__ bool rect_hit(const float4 g0, const float4 g1, float ox, float oy, float wpx, float hpx, float tol) {
+    Conic q;  // shifted to rectangle-local coordinates (x = ox + x')
+    q.a = g0.x; q.b = g0.y; q.c = g0.z;
+    q.d = g0.x * ox + g0.y * oy + g0.w;
+    q.e = g0.y * ox + g0.z * oy + g1.x;
+    q.f = (g0.x * ox + 2.f * (g0.y * oy + g0.w)) * ox + (g0.z * oy + 2.f * g1.x) * oy + g1.y;
+    return conic_min_rect(q, -0.05f, wpx + 0.05f, -0.05f, hpx + 0.05f) <= tol;
+}
+// tile-level test (the first line of cull_mask): the 16x16 tile whose first pixel centre is (ox, oy)
+__device__ __forceinline__ bool tile_hit(const float4 g0, const float4 g1, float ox, float oy) {
+    return rect_hit(g0, g1, ox, oy, 15.f, 15.f, 4e-6f);
+}
+
 // All tiles of a small tile rect (w x h < 32 tiles, first tile (x0, y0)) at once: bit j * w + i is set if the footprint conic reaches
 // tile (x0 + i, y0 + j). The tiles are taken with shared boundaries on the pixel-edge grid (x = 16 (x0 + i), y = 16 (y0 + j)): each
-// such square contains its tile's pixel centres plus the 0.05 px margin of cull_mask, so the result is a superset of per-tile tests, and
+// such square contains its tile's pixel centres plus the margin used by tile_hit, so the result is a superset of the per-tile tests, and
 // the minimum of Q over every square comes from one pass over the (w + 1) x (h + 1) grid points, one critical point per grid line and
 // the conic centre -- a few hundred instructions for a 20-tile rect instead of 20 x ~120.
 __device__ __forceinline__ uint32_t small_rect_mask(const float4 g0, const float4 g1, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h) {

@@ -60,14 +60,46 @@ __device__ __forceinline__ bool shrink_rect(const gssdf_tile_encode_args &a, int
     return x0 < x1 && y0 < y1;
 }
 
-// Reference mode (no conics): visit every tile of every splat's rect. Small rects are walked by their own thread; rects with
+// Warp-cooperative walk of a large rect (>= 256 tiles) of splat `bidx` in culled mode: 8x8-tile super-blocks are tested against the
+// splat's conic first (same min-over-rectangle routine, looser tolerance -> a superset of the per-tile test), and only the ones it
+// touches are descended into. f(i, x, y) still applies the exact per-tile test, so the set of (splat, tile) pairs that pass is unchanged.
+template <typename F>
+__device__ __forceinline__ void walk_super_blocks(int bidx, uint32_t bx0, uint32_t by0, uint32_t bw, uint32_t bh, const float4 *__restrict__ conic,
+                                                  F &&f) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t sw = (bw + 7) >> 3, sh = (bh + 7) >> 3, nsb = sw * sh;
+    const float4 g0 = __ldg(conic + kConicF4 * (int64_t)bidx), g1 = __ldg(conic + kConicF4 * (int64_t)bidx + 1);
+    for (uint32_t s0 = 0; s0 < nsb; s0 += 32) {
+        const uint32_t sb = s0 + lane;
+        bool hit = false;
+        if (sb < nsb) {
+            const uint32_t sx = (sb % sw) * 8, sy = (sb / sw) * 8;
+            const uint32_t ex = min(sx + 8, bw), ey = min(sy + 8, bh);
+            hit = rect_hit(g0, g1, (bx0 + sx) * 16.f + 0.5f, (by0 + sy) * 16.f + 0.5f, (ex - sx) * 16.f - 1.f, (ey - sy) * 16.f - 1.f, 1e-4f);
+        }
+        unsigned hm = __ballot_sync(0xffffffffu, hit);
+        while (hm) {
+            const uint32_t sb2 = s0 + (__ffs(hm) - 1);
+            hm &= hm - 1;
+            const uint32_t sx = (sb2 % sw) * 8, sy = (sb2 / sw) * 8;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const uint32_t x = sx + (lane & 7), y = sy + (lane >> 3) + 4 * t;
+                if (x < bw && y < bh) f(bidx, bx0 + x, by0 + y);
+            }
+        }
+    }
+}
+
+// Visit every tile of every splat's rect. Small rects are walked by their own thread; rects with
 // >= 32 tiles are walked cooperatively by the warp (a screen-filling splat touches ~8k tiles).
 template <typename F>
-__device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, int idx, F &&f) {
+__device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, int idx,
+                                              const float4 *__restrict__ conic, F &&f, bool do_small = true) {
     const uint32_t w = has ? x1 - x0 : 0, h = has ? y1 - y0 : 0;
     const uint32_t cnt = w * h;
     const bool big = cnt >= 32;
-    if (has && !big) {
+    if (has && !big && do_small) {
         for (uint32_t y = y0; y < y1; ++y)
             for (uint32_t x = x0; x < x1; ++x) f(idx, x, y);
     }
@@ -79,54 +111,30 @@ __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0
         const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
         const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bcnt = __shfl_sync(0xffffffffu, cnt, src);
         const int bidx = __shfl_sync(0xffffffffu, idx, src);
+        if (conic && bcnt >= 256) {
+            walk_super_blocks(bidx, bx0, by0, bw, bcnt / bw, conic, f);
+        } else {
 #pragma unroll 4
-        for (uint32_t t = lane; t < bcnt; t += 32) f(bidx, bx0 + t % bw, by0 + t / bw);  // unrolled: 4 atomics in flight per lane
-    }
-}
-
-// Culled mode: the tiles of a rect that the splat's footprint conic reaches. small_rect_mask (conic.cuh) decides up to 31 tiles in one
-// pass, so a rect of fewer than 32 tiles is one call by its own thread (`small_bits`: the count pass stores the outcome, the scatter pass
-// reads it back) and a larger rect is cut into sub-rects of at most 5 x 6 tiles that the lanes of the warp take one each. emit(i, x, y)
-// is called for every kept tile. Both passes make the same calls on the same inputs, so they agree on every tile.
-constexpr uint32_t kSubW = 5, kSubH = 6;
-template <typename Emit>
-__device__ __forceinline__ void emit_mask(uint32_t mk, int idx, uint32_t x0, uint32_t y0, uint32_t w, Emit &&emit) {
-    for (; mk; mk &= mk - 1u) {
-        const uint32_t t = (uint32_t)__ffs(mk) - 1u, ty = t / w;
-        emit(idx, x0 + (t - ty * w), y0 + ty);
-    }
-}
-template <typename Emit>
-__device__ __forceinline__ void culled_large_rects(bool large, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, int idx,
-                                                   const float4 *__restrict__ conic, Emit &&emit) {
-    unsigned m = __ballot_sync(0xffffffffu, large);
-    const uint32_t lane = threadIdx.x & 31;
-    while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-        const uint32_t bw = __shfl_sync(0xffffffffu, x1, src) - bx0, bh = __shfl_sync(0xffffffffu, y1, src) - by0;
-        const int bidx = __shfl_sync(0xffffffffu, idx, src);
-        const float4 g0 = __ldg(conic + kConicF4 * (int64_t)bidx), g1 = __ldg(conic + kConicF4 * (int64_t)bidx + 1);
-        const uint32_t ta = (bw + kSubW - 1) / kSubW, nt = ta * ((bh + kSubH - 1) / kSubH);
-        for (uint32_t t = lane; t < nt; t += 32) {  // (no warp-level operation inside: the lanes run freely)
-            const uint32_t sx = (t % ta) * kSubW, sy = (t / ta) * kSubH;
-            const uint32_t sw = min(kSubW, bw - sx), sh = min(kSubH, bh - sy);
-            emit_mask(small_rect_mask(g0, g1, bx0 + sx, by0 + sy, sw, sh), bidx, bx0 + sx, by0 + sy, sw, emit);
+            for (uint32_t t = lane; t < bcnt; t += 32) f(bidx, bx0 + t % bw, by0 + t / bw);  // unrolled: 4 atomics in flight per lane
         }
     }
 }
 
-__device__ __forceinline__ void count_tile(const gssdf_tile_encode_args &a, const TileGeom &g, int32_t *__restrict__ hist, bool survivors, int i,
-                                           uint32_t x, uint32_t y) {
+__device__ __forceinline__ bool count_tile(const gssdf_tile_encode_args &a, const TileGeom &g, int32_t *__restrict__ hist,
+                                           const float4 *__restrict__ conic, int i, uint32_t x, uint32_t y) {
+    if (conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f))
+        return false;
     const int64_t cid = a.camera_ids ? a.camera_ids[i] : 0;
     atomicAdd(hist + cid * g.n_tiles + y * g.tw + x, 1);
-    if (survivors) atomicAdd(a.tiles_per_gauss + i, 1);  // culled mode: count the survivors (zeroed by the host call)
+    if (conic && a.tiles_per_gauss) atomicAdd(a.tiles_per_gauss + i, 1);  // culled mode: count the survivors
+    return true;
 }
 
 __device__ __forceinline__ void scatter_tile(const gssdf_tile_encode_args &a, const TileGeom &g, int32_t *__restrict__ hist,
-                                             const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys, int i, uint32_t x,
-                                             uint32_t y) {
+                                             const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys,
+                                             const float4 *__restrict__ conic, int i, uint32_t x, uint32_t y, bool test = true) {
+    if (test && conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f))
+        return;  // the same test, on the same inputs, as in the count pass
     const int64_t cid = a.camera_ids ? a.camera_ids[i] : 0;
     const int64_t bin = cid * g.n_tiles + y * g.tw + x;
     const int slot = atomicSub(hist + bin, 1) - 1;  // fills the bin back to front
@@ -135,7 +143,7 @@ __device__ __forceinline__ void scatter_tile(const gssdf_tile_encode_args &a, co
 }
 
 __global__ void __launch_bounds__(256)
-tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist, uint32_t *__restrict__ small_bits) {
+tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist, uint32_t *__restrict__ small_mask) {
     const int nnz = a.counts->nnz;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = idx < nnz;
@@ -151,20 +159,23 @@ tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__r
     has = has && shrink_rect(a, idx, x0, y0, x1, y1);
     if (in && a.tiles_per_gauss && !a.conics) a.tiles_per_gauss[idx] = has ? (int32_t)((y1 - y0) * (x1 - x0)) : 0;
     const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
-    if (!conic) {
-        for_each_tile(has, x0, y0, x1, y1, idx, [&](int i, uint32_t x, uint32_t y) { count_tile(a, g, hist, false, i, x, y); });
-        return;
+    if (small_mask) {
+        // culled mode: a rect of fewer than 32 tiles is tested by its own thread for all its tiles at once (small_rect_mask) and leaves
+        // the outcome as one bit per tile for the scatter pass, which then neither repeats the tests nor visits the tiles that failed
+        uint32_t mk = 0u;
+        if (has && (x1 - x0) * (y1 - y0) < 32u) {
+            const uint32_t w = x1 - x0;
+            mk = small_rect_mask(__ldg(conic + kConicF4 * (int64_t)idx), __ldg(conic + kConicF4 * (int64_t)idx + 1), x0, y0, w, y1 - y0);
+            int32_t *row = hist + (a.camera_ids ? a.camera_ids[idx] : 0) * g.n_tiles;
+            for (uint32_t m2 = mk; m2; m2 &= m2 - 1u) {
+                const uint32_t t = (uint32_t)__ffs(m2) - 1u, ty = t / w;
+                atomicAdd(row + (y0 + ty) * g.tw + x0 + (t - ty * w), 1);
+            }
+            if (a.tiles_per_gauss && mk) atomicAdd(a.tiles_per_gauss + idx, __popc(mk));  // (zeroed by the host call)
+        }
+        if (in) small_mask[idx] = mk;
     }
-    const bool survivors = a.tiles_per_gauss != nullptr;
-    auto emit = [&](int i, uint32_t x, uint32_t y) { count_tile(a, g, hist, survivors, i, x, y); };
-    const bool small = has && (x1 - x0) * (y1 - y0) < 32u;
-    uint32_t mk = 0u;
-    if (small) {
-        mk = small_rect_mask(__ldg(conic + kConicF4 * (int64_t)idx), __ldg(conic + kConicF4 * (int64_t)idx + 1), x0, y0, x1 - x0, y1 - y0);
-        emit_mask(mk, idx, x0, y0, x1 - x0, emit);
-    }
-    if (small_bits && in) small_bits[idx] = mk;
-    culled_large_rects(has && !small, x0, y0, x1, y1, idx, conic, emit);
+    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) { count_tile(a, g, hist, conic, i, x, y); }, small_mask == nullptr);
 }
 
 // exclusive scan of hist[n] -> offsets[n] (int32 output tensor) and bin_start[n+1]; hist is left
@@ -226,7 +237,7 @@ tile_scan_kernel(const int32_t *__restrict__ hist, int32_t *__restrict__ offsets
 
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist,
-                    const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys, const uint32_t *__restrict__ small_bits) {
+                    const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys, const uint32_t *__restrict__ small_mask) {
     const int nnz = a.counts->nnz;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = idx < nnz;
@@ -234,19 +245,18 @@ tile_scatter_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *_
     bool has = in && tile_rect(a, g, idx, x0, y0, x1, y1);
     has = has && shrink_rect(a, idx, x0, y0, x1, y1);
     const float4 *conic = reinterpret_cast<const float4 *>(a.conics);
-    auto emit = [&](int i, uint32_t x, uint32_t y) { scatter_tile(a, g, hist, bin_start, keys, i, x, y); };
-    if (!conic) {
-        for_each_tile(has, x0, y0, x1, y1, idx, emit);
-        return;
+    if (small_mask && has && (x1 - x0) * (y1 - y0) < 32u) {
+        uint32_t mk = small_mask[idx];
+        const uint32_t w = x1 - x0;
+        while (mk) {
+            const uint32_t t = (uint32_t)__ffs(mk) - 1u;
+            mk &= mk - 1u;
+            const uint32_t ty = t / w;
+            scatter_tile(a, g, hist, bin_start, keys, conic, idx, x0 + (t - ty * w), y0 + ty, false);
+        }
     }
-    const bool small = has && (x1 - x0) * (y1 - y0) < 32u;
-    if (small) {  // the count pass left its decisions, unless there was no room to keep them
-        const uint32_t mk = small_bits ? small_bits[idx]
-                                       : small_rect_mask(__ldg(conic + kConicF4 * (int64_t)idx), __ldg(conic + kConicF4 * (int64_t)idx + 1), x0, y0,
-                                                         x1 - x0, y1 - y0);
-        emit_mask(mk, idx, x0, y0, x1 - x0, emit);
-    }
-    culled_large_rects(has && !small, x0, y0, x1, y1, idx, conic, emit);
+    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) { scatter_tile(a, g, hist, bin_start, keys, conic, i, x, y); },
+                  small_mask == nullptr);
 }
 
 // All-ascending bitonic network over v[0..n) (virtual +inf padding beyond n): flip step then half-cleaners. Works on shared or global
