@@ -173,21 +173,3 @@ def test_grid_pass_over_tile_rects_is_a_superset_of_per_tile_tests():
                 kept += o
                 extra += bool(n and not o)
     assert kept > 10000 and extra < 0.05 * kept
-
-
-def test_sub_rect_split_of_large_rects_covers_every_kept_tile():
-    rng = np.random.default_rng(2)
-    for _ in range(150):
-        w, h = int(rng.integers(6, 25)), int(rng.integers(6, 16))
-        x0, y0 = int(rng.integers(0, 90)), int(rng.integers(0, 50))
-        q = random_conic(rng, 16 * x0 + rng.uniform(-10, 16 * w + 10), 16 * y0 + rng.uniform(-10, 16 * h + 10), rng.uniform(0.5, 600), 1000.0)
-        got = set()
-        ta = (w + 4) // 5
-        for t in range(ta * ((h + 5) // 6)):  # culled_large_rects of tiles.cu
-            sx, sy = (t % ta) * 5, (t // ta) * 6
-            sw, sh = min(5, w - sx), min(6, h - sy)
-            mk = small_rect_mask(q, x0 + sx, y0 + sy, sw, sh)
-            got |= {(x0 + sx + tt % sw, y0 + sy + tt // sw) for tt in range(sw * sh) if (mk >> tt) & 1}
-        for j in range(h):
-            for i in range(w):
-                assert (x0 + i, y0 + j) in got or not tile_test(q, x0 + i, y0 + j)
