@@ -647,20 +647,24 @@ def main():
     d2h = 4
 
     # per-stage times of OUR step (CUDA events between the stages of 5 extra steps; outside the timed regions)
+    # (world > 1: every rank runs the extra steps -- they contain collectives -- and rank 0 reports; the waits for the two all-reduces
+    # then show up inside the stage that issues them: the splat segment's in projection_fwd, the SDF segment's in adam)
     stage_ms = None
-    if rank == 0 and world == 1:
+    if True:
         acc = {}
         T.overlap = False  # the per-stage table is taken with the stages in line on one stream (event differences are meaningless otherwise)
         for i in range(5):
-            R.stage_events = []
+            R.stage_events = [] if rank == 0 else None
             step_resident(i)
+            if world > 1:
+                pre_render()
             torch.cuda.synchronize()
-            ev = R.stage_events
+            ev = R.stage_events or []
             for (_, a), (name, b) in zip(ev[:-1], ev[1:]):
                 acc.setdefault(name, []).append(a.elapsed_time(b))
         R.stage_events = None
         T.overlap = args.overlap > 0 and T.mlp_mode == 1
-        stage_ms = {("rng+sample_generation[A0]" if k == "start" else k): float(np.mean(v)) for k, v in acc.items()}
+        stage_ms = {("rng+sample_generation[A0]" if k == "start" else k): float(np.mean(v)) for k, v in acc.items()} if rank == 0 else None
 
     if rank == 0:
         pk, pk_kind = peaks()

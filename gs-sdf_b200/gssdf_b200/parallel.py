@@ -103,8 +103,14 @@ class DataParallelStep:
         self.x = GradientExchange()
         self._pending_splat = False
 
+    def _mark(self, name):
+        R = getattr(self.T, "R", None)
+        if R is not None and hasattr(R, "_mark"):
+            R._mark(name)  # profiling hook of the renderer (bench.py's per-stage table); no-op unless enabled
+
     def _before_render(self):
         self.x.before_render()
+        self._mark("wait_splat_allreduce")
         if self._pending_splat:
             self.T.adam_splat(1.0 / self.world)
             self._pending_splat = False
@@ -117,6 +123,7 @@ class DataParallelStep:
             return out
         out = T.train_step(*args, on_sdf_grads_ready=self.x.on_sdf_grads_ready, before_render=self._before_render, **kw)
         self.x.finish_step(T.flat_grad[:T.t0])  # splat all-reduce in flight; returns once the SDF segment is reduced
+        self._mark("wait_sdf_allreduce")
         self._pending_splat = True
         T.adam_sdf(1.0 / self.world)
         return out

@@ -459,9 +459,9 @@ class GsSdfTrainer(GsSdfStep):
         if self.l2_persist:  # the 30.5 MB fp16 table stays in L2 across the optimiser's streaming pass
             cabi.l2_persist(self.table_half)
 
-    def _adam(self, groups, t, grad_scale, sdf):
+    def _adam(self, groups, t, grad_scale, sdf, mark="adam"):
         self._adam_call(groups, t, grad_scale, sdf)
-        self.R._mark("adam")
+        self.R._mark(mark)
 
     def _adam_call(self, groups, t, grad_scale, sdf):
         cabi.adam_step(self.params, self.flat_grad, self.exp_avg, self.exp_avg_sq, groups, t, grad_scale=grad_scale, zero_grads=True,
@@ -470,11 +470,11 @@ class GsSdfTrainer(GsSdfStep):
 
     def adam_sdf(self, grad_scale=1.0):
         self.t_sdf += 1
-        self._adam(self.sdf_groups, self.t_sdf, grad_scale, True)
+        self._adam(self.sdf_groups, self.t_sdf, grad_scale, True, "adam_sdf")
 
     def adam_splat(self, grad_scale=1.0):
         self.t_splat += 1
-        self._adam(self.splat_groups, self.t_splat, grad_scale, False)
+        self._adam(self.splat_groups, self.t_splat, grad_scale, False, "adam_splat")
 
     def adam_all(self, grad_scale=1.0):
         """Single-GPU: one launch over all seven groups (+ the decoder re-pack)."""
