@@ -385,6 +385,7 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1, 2, 3],
                     help="schedule of the SDF-only work (sample generation, [A], [C]): 0 = in line on one stream, 1 = on a second stream beside the "
                          "render (equal priority), 2 = second stream at high priority, 3 = render stream at high priority")
+    ap.add_argument("--nccl-high-priority", action="store_true", help="A/B (N > 1): run NCCL's kernels on a high-priority stream")
     ap.add_argument("--l2-persist", action="store_true", help="A/B: pin the fp16 hash-table shadow in L2 (gssdf_l2_persist); measured: no effect")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -425,7 +426,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        opts = None
+        if args.nccl_high_priority:  # NCCL's kernels on a high-priority stream: their CTAs are placed as soon as any CTA slot frees up
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
