@@ -91,141 +91,17 @@ __device__ __forceinline__ void walk_super_blocks(int bidx, uint32_t bx0, uint32
     }
 }
 
-// The same walk with grid passes (conic.cuh, small_rect_mask) at both levels, shared by the lanes of the warp: level 1 decides all 8x8-tile
-// super-blocks of the rect from its (sw + 1) x (sh + 1) super-block corner points, one critical point per super-block grid line and the
-// conic centre (flags in `s_hit`, one byte per super-block, per-warp scratch); level 2 decides the up to 64 tiles of a hit super-block
-// the same way on its 9 x 9 tile corner points (a 64-bit mask OR-reduced over the warp). ~50 instructions per lane for level 1 and
-// ~70 per hit super-block instead of 4 x 120 and 2 x 120 (+ the per-tile closed form). Tiles are taken as pixel-edge squares like the
-// small rects (superset of the pixel-centre squares). g(i, x, y) is called for every kept tile and does NOT test.
-constexpr int kMaxSuper = 1024;  // super-blocks of the largest rect handled this way (a 4K image has 30 x 17 = 510)
-__device__ __forceinline__ Conic conic_at(const float4 g0, const float4 g1, float ox, float oy) {  // coordinates local to (ox, oy)
-    Conic q;
-    q.a = g0.x; q.b = g0.y; q.c = g0.z;
-    q.d = g0.x * ox + g0.y * oy + g0.w;
-    q.e = g0.y * ox + g0.z * oy + g1.x;
-    q.f = (g0.x * ox + 2.f * (g0.y * oy + g0.w)) * ox + (g0.z * oy + 2.f * g1.x) * oy + g1.y;
-    return q;
-}
-template <typename G>
-__device__ __forceinline__ void walk_super_blocks_grid(int bidx, uint32_t bx0, uint32_t by0, uint32_t bw, uint32_t bh,
-                                                       const float4 *__restrict__ conic, uint8_t *s_hit, G &&g) {
-    const int lane = threadIdx.x & 31;
-    const int sw = (int)((bw + 7) >> 3), sh = (int)((bh + 7) >> 3), nsb = sw * sh;
-    const float4 g0 = __ldg(conic + kConicF4 * (int64_t)bidx), g1 = __ldg(conic + kConicF4 * (int64_t)bidx + 1);
-    for (int sidx = lane; sidx < nsb; sidx += 32) s_hit[sidx] = 0;
-    __syncwarp();
-    {   // level 1: super-blocks (the last column / row may be narrower: its far edge is the rect's edge)
-        const Conic q = conic_at(g0, g1, 16.f * (float)bx0, 16.f * (float)by0);
-        const float tol = 1e-4f, XW = 16.f * (float)bw, YH = 16.f * (float)bh;
-        auto X1 = [&](int i) { return fminf(128.f * (float)i, XW); };
-        auto Y1 = [&](int j) { return fminf(128.f * (float)j, YH); };
-        auto mark = [&](int i, int j) {
-            if (i >= 0 && i < sw && j >= 0 && j < sh) s_hit[j * sw + i] = 1;
-        };
-        const int np = (sw + 1) * (sh + 1);
-        for (int pnt = lane; pnt < np; pnt += 32) {
-            const int i = pnt % (sw + 1), j = pnt / (sw + 1);
-            if (conic_eval(q, X1(i), Y1(j)) <= tol) { mark(i - 1, j - 1); mark(i, j - 1); mark(i - 1, j); mark(i, j); }
-        }
-        if (q.c > 0.f) {
-            const float rc = 1.f / q.c;
-            for (int i = lane; i <= sw; i += 32) {
-                const float X = X1(i), ys = -(q.b * X + q.e) * rc;
-                if (ys > 0.f && ys < YH && conic_eval(q, X, ys) <= tol) {
-                    const int j = min((int)(ys * (1.f / 128.f)), sh - 1);
-                    mark(i - 1, j); mark(i, j);
-                }
-            }
-        }
-        if (q.a > 0.f) {
-            const float ra = 1.f / q.a;
-            for (int j = lane; j <= sh; j += 32) {
-                const float Y = Y1(j), xs = -(q.b * Y + q.d) * ra;
-                if (xs > 0.f && xs < XW && conic_eval(q, xs, Y) <= tol) {
-                    const int i = min((int)(xs * (1.f / 128.f)), sw - 1);
-                    mark(i, j - 1); mark(i, j);
-                }
-            }
-        }
-        const float det = q.a * q.c - q.b * q.b;
-        if (lane == 0 && q.a > 0.f && det > 0.f) {
-            const float rd = 1.f / det;
-            const float cx = -(q.c * q.d - q.b * q.e) * rd, cy = -(q.a * q.e - q.b * q.d) * rd;
-            if (cx > 0.f && cx < XW && cy > 0.f && cy < YH && conic_eval(q, cx, cy) <= tol)
-                mark(min((int)(cx * (1.f / 128.f)), sw - 1), min((int)(cy * (1.f / 128.f)), sh - 1));
-        }
-    }
-    __syncwarp();
-    for (int s0 = 0; s0 < nsb; s0 += 32) {
-        unsigned hm = __ballot_sync(0xffffffffu, s0 + lane < nsb && s_hit[s0 + lane] != 0);
-        while (hm) {  // level 2: the tiles of one hit super-block
-            const int sb = s0 + (__ffs(hm) - 1);
-            hm &= hm - 1;
-            const uint32_t sx = (uint32_t)(sb % sw) * 8u, sy = (uint32_t)(sb / sw) * 8u;
-            const int ew = (int)min(8u, bw - sx), eh = (int)min(8u, bh - sy);
-            const Conic q = conic_at(g0, g1, 16.f * (float)(bx0 + sx), 16.f * (float)(by0 + sy));
-            const float tol = 4e-6f, XW = 16.f * (float)ew, YH = 16.f * (float)eh;
-            uint32_t lo = 0u, hi = 0u;
-            auto mark = [&](int i, int j) {
-                if (i >= 0 && i < ew && j >= 0 && j < eh) {
-                    const int b = j * 8 + i;
-                    if (b < 32) lo |= 1u << b; else hi |= 1u << (b - 32);
-                }
-            };
-            const int np = (ew + 1) * (eh + 1);
-            for (int pnt = lane; pnt < np; pnt += 32) {
-                const int i = pnt % (ew + 1), j = pnt / (ew + 1);
-                if (conic_eval(q, 16.f * (float)i, 16.f * (float)j) <= tol) { mark(i - 1, j - 1); mark(i, j - 1); mark(i - 1, j); mark(i, j); }
-            }
-            {   // one grid line (or the centre) per lane: lanes 0..ew vertical, ew+1..ew+eh+1 horizontal, the next one the centre
-                const int l = lane;
-                if (l <= ew) {
-                    if (q.c > 0.f) {
-                        const float X = 16.f * (float)l, ys = -(q.b * X + q.e) / q.c;
-                        if (ys > 0.f && ys < YH && conic_eval(q, X, ys) <= tol) {
-                            const int j = min((int)(ys * 0.0625f), eh - 1);
-                            mark(l - 1, j); mark(l, j);
-                        }
-                    }
-                } else if (l <= ew + eh + 1) {
-                    if (q.a > 0.f) {
-                        const int j = l - ew - 1;
-                        const float Y = 16.f * (float)j, xs = -(q.b * Y + q.d) / q.a;
-                        if (xs > 0.f && xs < XW && conic_eval(q, xs, Y) <= tol) {
-                            const int i = min((int)(xs * 0.0625f), ew - 1);
-                            mark(i, j - 1); mark(i, j);
-                        }
-                    }
-                } else if (l == ew + eh + 2) {
-                    const float det = q.a * q.c - q.b * q.b;
-                    if (q.a > 0.f && det > 0.f) {
-                        const float rd = 1.f / det;
-                        const float cx = -(q.c * q.d - q.b * q.e) * rd, cy = -(q.a * q.e - q.b * q.d) * rd;
-                        if (cx > 0.f && cx < XW && cy > 0.f && cy < YH && conic_eval(q, cx, cy) <= tol)
-                            mark(min((int)(cx * 0.0625f), ew - 1), min((int)(cy * 0.0625f), eh - 1));
-                    }
-                }
-            }
-            lo = __reduce_or_sync(0xffffffffu, lo);
-            hi = __reduce_or_sync(0xffffffffu, hi);
-            if ((lo >> lane) & 1u) g(bidx, bx0 + sx + (lane & 7), by0 + sy + (lane >> 3));
-            if ((hi >> lane) & 1u) g(bidx, bx0 + sx + (lane & 7), by0 + sy + 4 + (lane >> 3));
-        }
-    }
-    __syncwarp();  // s_hit is reused by the warp's next large rect
-}
-
 // Visit every tile of every splat's rect. Small rects are walked by their own thread; rects with
 // >= 32 tiles are walked cooperatively by the warp (a screen-filling splat touches ~8k tiles).
 template <typename F>
 __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, int idx,
-                                              const float4 *__restrict__ conic, F &&f, bool do_small = true, uint8_t *s_hit = nullptr) {
+                                              const float4 *__restrict__ conic, F &&f, bool do_small = true) {
     const uint32_t w = has ? x1 - x0 : 0, h = has ? y1 - y0 : 0;
     const uint32_t cnt = w * h;
     const bool big = cnt >= 32;
     if (has && !big && do_small) {
         for (uint32_t y = y0; y < y1; ++y)
-            for (uint32_t x = x0; x < x1; ++x) f(idx, x, y, true);
+            for (uint32_t x = x0; x < x1; ++x) f(idx, x, y);
     }
     unsigned m = __ballot_sync(0xffffffffu, big);
     const int lane = threadIdx.x & 31;
@@ -236,21 +112,17 @@ __device__ __forceinline__ void for_each_tile(bool has, uint32_t x0, uint32_t y0
         const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bcnt = __shfl_sync(0xffffffffu, cnt, src);
         const int bidx = __shfl_sync(0xffffffffu, idx, src);
         if (conic && bcnt >= 256) {
-            const uint32_t bh = bcnt / bw;
-            if (s_hit && ((bw + 7) >> 3) * ((bh + 7) >> 3) <= (uint32_t)kMaxSuper)
-                walk_super_blocks_grid(bidx, bx0, by0, bw, bh, conic, s_hit, [&](int i, uint32_t x, uint32_t y) { f(i, x, y, false); });
-            else
-                walk_super_blocks(bidx, bx0, by0, bw, bh, conic, [&](int i, uint32_t x, uint32_t y) { f(i, x, y, true); });
+            walk_super_blocks(bidx, bx0, by0, bw, bcnt / bw, conic, f);
         } else {
 #pragma unroll 4
-            for (uint32_t t = lane; t < bcnt; t += 32) f(bidx, bx0 + t % bw, by0 + t / bw, true);  // unrolled: 4 atomics in flight per lane
+            for (uint32_t t = lane; t < bcnt; t += 32) f(bidx, bx0 + t % bw, by0 + t / bw);  // unrolled: 4 atomics in flight per lane
         }
     }
 }
 
 __device__ __forceinline__ bool count_tile(const gssdf_tile_encode_args &a, const TileGeom &g, int32_t *__restrict__ hist,
-                                           const float4 *__restrict__ conic, int i, uint32_t x, uint32_t y, bool test = true) {
-    if (test && conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f))
+                                           const float4 *__restrict__ conic, int i, uint32_t x, uint32_t y) {
+    if (conic && !tile_hit(__ldg(conic + kConicF4 * (int64_t)i), __ldg(conic + kConicF4 * (int64_t)i + 1), x * 16.f + 0.5f, y * 16.f + 0.5f))
         return false;
     const int64_t cid = a.camera_ids ? a.camera_ids[i] : 0;
     atomicAdd(hist + cid * g.n_tiles + y * g.tw + x, 1);
@@ -272,7 +144,6 @@ __device__ __forceinline__ void scatter_tile(const gssdf_tile_encode_args &a, co
 
 __global__ void __launch_bounds__(256)
 tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist, uint32_t *__restrict__ small_mask) {
-    __shared__ uint8_t s_hit[8][kMaxSuper];  // per-warp super-block flags of walk_super_blocks_grid
     const int nnz = a.counts->nnz;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = idx < nnz;
@@ -304,8 +175,7 @@ tile_count_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__r
         }
         if (in) small_mask[idx] = mk;
     }
-    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y, bool test) { count_tile(a, g, hist, conic, i, x, y, test); },
-                  small_mask == nullptr, s_hit[threadIdx.x >> 5]);
+    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) { count_tile(a, g, hist, conic, i, x, y); }, small_mask == nullptr);
 }
 
 // exclusive scan of hist[n] -> offsets[n] (int32 output tensor) and bin_start[n+1]; hist is left
@@ -368,7 +238,6 @@ tile_scan_kernel(const int32_t *__restrict__ hist, int32_t *__restrict__ offsets
 __global__ void __launch_bounds__(256)
 tile_scatter_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *__restrict__ hist,
                     const int32_t *__restrict__ bin_start, unsigned long long *__restrict__ keys, const uint32_t *__restrict__ small_mask) {
-    __shared__ uint8_t s_hit[8][kMaxSuper];
     const int nnz = a.counts->nnz;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = idx < nnz;
@@ -386,9 +255,8 @@ tile_scatter_kernel(const gssdf_tile_encode_args a, const TileGeom g, int32_t *_
             scatter_tile(a, g, hist, bin_start, keys, conic, idx, x0 + (t - ty * w), y0 + ty, false);
         }
     }
-    for_each_tile(has, x0, y0, x1, y1, idx, conic,
-                  [&](int i, uint32_t x, uint32_t y, bool test) { scatter_tile(a, g, hist, bin_start, keys, conic, i, x, y, test); }, small_mask == nullptr,
-                  s_hit[threadIdx.x >> 5]);
+    for_each_tile(has, x0, y0, x1, y1, idx, conic, [&](int i, uint32_t x, uint32_t y) { scatter_tile(a, g, hist, bin_start, keys, conic, i, x, y); },
+                  small_mask == nullptr);
 }
 
 // All-ascending bitonic network over v[0..n) (virtual +inf padding beyond n): flip step then half-cleaners. Works on shared or global
