@@ -379,8 +379,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eikonal", default="analytic", choices=["analytic", "numerical"],
                     help="analytic: eikonal + align on d sdf/dx with double backward (reference default); numerical: 6-offset gradient")
-    ap.add_argument("--same-cameras", action="store_true", help="N>1: every rank renders the same camera poses (identical work per rank); "
-                    "default: rank r renders its own poses")
+    ap.add_argument("--same-cameras", action="store_true", help="N>1: every rank renders the same camera pose at every step (no load imbalance); "
+                    "default: one shared pool of poses, rank r a fixed number of poses ahead in the cycle")
     ap.add_argument("--no-stock-cuda", action="store_true", help="skip the reference-fork CUDA leg (oracle/_ref/gsplat_ref.so)")
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1, 2, 3],
                     help="schedule of the SDF-only work (sample generation, [A], [C]): 0 = in line on one stream, 1 = on a second stream beside the "
@@ -393,8 +393,8 @@ def main():
     W, H, N, deg, isect_cap = WORKLOADS[args.workload]
     cfg = {"workload": f"{args.workload}: {W}x{H}, {N} splats, SH deg {deg}, synthetic box scene seed 0 (SURVEY 8d), tile 16, packed, "
                        f"1 camera/rank/step", "timing": "CUDA events; inputs (232 B/splat state + images) exceed the 126 MB L2, no flush",
-           "parallelism": (f"image-parallel dp{world}, replicated state, rank r renders its own camera poses"
-                           f"{' (--same-cameras: identical poses)' if args.same_cameras else ''}, 2 NCCL all-reduces/step: SDF segment under "
+           "parallelism": (f"image-parallel dp{world}, replicated state, one pool of 8 camera poses, rank r renders pose (step + r * {max(8 // world, 1)}) mod 8"
+                           f"{' (--same-cameras: the same pose on every rank)' if args.same_cameras else ''}, 2 NCCL all-reduces/step: SDF segment under "
                            f"the render backward, splat segment under the next step's SDF stage; replicated Adam with grad_scale 1/{world}")
            if world > 1 else "single GPU",
            "schedule": ["one stream, stages in line", "SDF-only work (sample generation, [A], [C]) on a second stream beside the render",
@@ -502,10 +502,13 @@ def main():
     K_sh = (deg + 1) ** 2
     SP = Sampling(T, sc_act["means"], 50 + rank)  # each rank draws its own rays
     n_cams = 8
-    # image-batch data parallelism = "per-frame render on each rank" (north_star): rank r renders ITS OWN camera poses, so the ranks'
-    # per-step work differs (load imbalance is part of the measurement); --same-cameras restores identical work on every rank
-    cam0 = 0 if args.same_cameras else rank * n_cams
-    cams = [S.camera(cam0 + i, W, H) for i in range(n_cams)]
+    # image-batch data parallelism = "per-frame render on each rank" (north_star): every rank draws from the SAME pool of camera poses
+    # (like ranks sharing one dataset), rank r being cam_shift poses ahead in the cycle -- at every step the ranks render different poses,
+    # so the per-step load imbalance of real training is part of the measurement, while the work per rank averaged over the cycle is the
+    # same for every rank and every N (weak scaling). --same-cameras: identical pose at every step on every rank (no imbalance).
+    cam_shift = 0 if (args.same_cameras or world == 1) else rank * max(n_cams // world, 1)
+    cam_of = lambda i: (i + cam_shift) % n_cams
+    cams = [S.camera(i, W, H) for i in range(n_cams)]
     torch.manual_seed(1234 + rank)  # randns stream
 
     def gt_images(Tr, act, cam_list, Wc, Hc):
@@ -538,12 +541,12 @@ def main():
         DP.flush()
 
     def step_resident(i):
-        V, Kc = dev_cams[i % n_cams]
+        V, Kc = dev_cams[cam_of(i)]
         R._mark("step_begin")
         randn_buf.normal_()  # the reference draws randns on the device every render (Projection.cpp:728)
         with T.sdf_stage():
             ray_xyz, ray_gt, ray_cnt = SP.draw(i)
-        loss, _sdf_loss = DP.step(V, Kc, gts[i % n_cams], ray_xyz, ray_gt, randn_buf, ray_n_live=ray_cnt)
+        loss, _sdf_loss = DP.step(V, Kc, gts[cam_of(i)], ray_xyz, ray_gt, randn_buf, ray_n_live=ray_cnt)
         DEN.update_state()  # NeuralGS::update_state: per-iteration densification statistics (the every-100-iterations surgery is not timed)
         R._mark("densify_stats")
         return loss
@@ -559,10 +562,10 @@ def main():
         sl = slots[i % 2]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(sl["free"])  # the step that last used this slot has finished with it
-            hv, hk = host_cams[i % n_cams]
+            hv, hk = host_cams[cam_of(i)]
             sl["V"].copy_(hv, non_blocking=True)
             sl["K"].copy_(hk, non_blocking=True)
-            sl["gt"].copy_(host_gts[i % n_cams], non_blocking=True)
+            sl["gt"].copy_(host_gts[cam_of(i)], non_blocking=True)
             sl["ready"].record(copy_stream)
 
     def step_e2e(i, last=False):
