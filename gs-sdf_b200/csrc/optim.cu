@@ -147,3 +147,69 @@ extern "C" int gssdf_isotropic_loss(const gssdf_isotropic_loss_args *a, gssdf_st
     GSSDF_LAUNCH_OK("isotropic_kernel");
     return GSSDF_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// (e) sparse exchange of the splat gradient under data parallelism: gather the visible rows of every segment of the flat gradient
+// into packed rows [id | seg 0 | seg 1 | ...] and add a peer's packed rows back into the flat gradient. One thread per packed float;
+// consecutive threads walk a packed row, so the packed side is fully coalesced and the flat side is coalesced within a segment.
+namespace gssdf {
+
+struct RowsPlan {
+    int32_t start[GSSDF_ROWS_MAX_SEGMENTS + 1];  // first packed column of every segment (column 0 = the row id)
+    int32_t stride;
+};
+
+template <bool PACK>
+__global__ void __launch_bounds__(256) rows_kernel(const gssdf_rows_args a, const RowsPlan plan) {
+    const int64_t n = min((int64_t)*a.n_rows, a.cap_rows);
+    const int64_t total = n * plan.stride;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = e / plan.stride;
+        const int c = (int)(e - k * plan.stride);
+        if (c == 0) {
+            if (PACK) a.packed[e] = __int_as_float((int32_t)a.row_ids[k]);
+            continue;
+        }
+        const int64_t row = PACK ? a.row_ids[k] : (int64_t)__float_as_int(a.packed[k * plan.stride]);
+        int s = 0;
+#pragma unroll
+        for (int i = 1; i < GSSDF_ROWS_MAX_SEGMENTS; ++i) s += (i < a.n_segments && c >= plan.start[i]) ? 1 : 0;
+        float *f = a.flat + a.segments[s].offset + row * a.segments[s].width + (c - plan.start[s]);
+        if (PACK) {
+            a.packed[e] = *f;
+            if (a.zero_source) *f = 0.f;
+        } else {
+            atomicAdd(f, a.packed[e]);
+        }
+    }
+}
+
+}  // namespace gssdf
+
+static int rows_launch(const gssdf_rows_args *a, gssdf_stream_t stream, bool pack, const char *who) {
+    GSSDF_REQUIRE(a != nullptr, GSSDF_EINVAL, "%s: null args", who);
+    GSSDF_REQUIRE(a->n_segments > 0 && a->n_segments <= GSSDF_ROWS_MAX_SEGMENTS && a->cap_rows >= 0, GSSDF_EINVAL, "%s: bad segment count / capacity", who);
+    if (a->cap_rows == 0) return GSSDF_OK;
+    GSSDF_REQUIRE(a->n_rows && a->flat && a->packed && (!pack || a->row_ids), GSSDF_EINVAL, "%s: null pointer", who);
+    RowsPlan plan;
+    int32_t c = 1;
+    for (int i = 0; i < a->n_segments; ++i) {
+        GSSDF_REQUIRE(a->segments[i].width > 0 && a->segments[i].offset >= 0, GSSDF_EINVAL, "%s: bad segment %d", who, i);
+        plan.start[i] = c;
+        c += a->segments[i].width;
+    }
+    for (int i = a->n_segments; i <= GSSDF_ROWS_MAX_SEGMENTS; ++i) plan.start[i] = c;
+    plan.stride = c;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = cdiv(a->cap_rows * (int64_t)c, (int64_t)256);
+    const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * 16);  // grid-stride: the live row count is on the device
+    if (pack) gssdf::rows_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(*a, plan);
+    else gssdf::rows_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*a, plan);
+    GSSDF_LAUNCH_OK(pack ? "rows_kernel<pack>" : "rows_kernel<unpack>");
+    return GSSDF_OK;
+}
+
+extern "C" int gssdf_rows_pack(const gssdf_rows_args *a, gssdf_stream_t stream) { return rows_launch(a, stream, true, "rows_pack"); }
+extern "C" int gssdf_rows_unpack_add(const gssdf_rows_args *a, gssdf_stream_t stream) { return rows_launch(a, stream, false, "rows_unpack_add"); }

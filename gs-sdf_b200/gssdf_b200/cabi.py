@@ -318,6 +318,29 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, groups, step, beta1=0.9, beta2
     check(lib().gssdf_adam_step(_lib.C.byref(a), _stream()))
 
 
+def _rows_args(segments, cap_rows, n_rows, row_ids, flat, packed, zero_source=False):
+    a = make_args("gssdf_rows_args", n_segments=len(segments), zero_source=int(bool(zero_source)), cap_rows=cap_rows, n_rows=n_rows,
+                  row_ids=row_ids, flat=flat, packed=packed)
+    for i, (off, width) in enumerate(segments):
+        a.segments[i].offset, a.segments[i].width = int(off), int(width)
+    return a
+
+
+def rows_stride(segments):
+    return 1 + sum(int(w) for _, w in segments)
+
+
+def rows_pack(segments, cap_rows, n_rows, row_ids, flat, packed, zero_source=False):
+    """segments: list of (offset, width) into `flat`. packed[k] = [id | flat rows row_ids[k] of every segment], k < *n_rows (device int32);
+    zero_source: the packed elements of `flat` are cleared."""
+    check(lib().gssdf_rows_pack(_lib.C.byref(_rows_args(segments, cap_rows, n_rows, row_ids, flat, packed, zero_source)), _stream()))
+
+
+def rows_unpack_add(segments, cap_rows, n_rows, flat, packed):
+    """flat rows += packed rows (the ids travel in column 0 of the packed rows)."""
+    check(lib().gssdf_rows_unpack_add(_lib.C.byref(_rows_args(segments, cap_rows, n_rows, None, flat, packed)), _stream()))
+
+
 def sdf_gate_compact(n, x, index, x_out, n_gate, ws, visibilities=None, visible_thr=0.0, valid_mask=None, weights=None, w_out=None, n_live=None):
     """Stable compaction of the samples passing `vis > thr & valid` (the reference's index_select, neural_mapping.cpp:433-437)."""
     w = ws.get(lib().gssdf_sdf_gate_compact_workspace_bytes(_lib.C.c_int64(n)))

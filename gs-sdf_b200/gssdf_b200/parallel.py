@@ -72,9 +72,11 @@ class GradientExchange:
             self._splat.pop().wait()
 
     def finish_step(self, splat_segment):
+        """splat_segment None: the caller exchanges the splat gradient itself (SparseRowExchange)"""
         if not self.active:
             return
-        self._splat.append(dist.all_reduce(splat_segment, op=dist.ReduceOp.SUM, async_op=True))
+        if splat_segment is not None:
+            self._splat.append(dist.all_reduce(splat_segment, op=dist.ReduceOp.SUM, async_op=True))
         while self._sdf:
             self._sdf.pop().wait()
 
@@ -82,6 +84,61 @@ class GradientExchange:
         self.before_render()
         while self._sdf:
             self._sdf.pop().wait()
+
+
+class SparseRowExchange:
+    """Exchange of the splat-gradient segment by its VISIBLE rows (CUDA trainers, one camera per rank and step). Only the rows of the
+    splats a rank's frame sees carry a gradient, so instead of all-reducing the dense [N x 59] segment the ranks all-gather
+
+        packed[k] = [row id | offsets | quaternion | scaling | opacity | features_dc | features_rest]   k < nnz(rank)
+
+    (gssdf_rows_pack, which also clears those rows locally) and every rank adds ALL ranks' packed rows, its own included, in rank order
+    (gssdf_rows_unpack_add): the same sum on every rank, bit for bit, like after an all-reduce. The row counts differ per rank and step;
+    they are exchanged first (one int32 per rank), read on the host while the render backward is still queued on the device, and the
+    all-gather is sized to the largest count. use_sparse() falls back to the dense all-reduce when the gathered rows would not be
+    clearly smaller than the dense segment (large world sizes, most splats visible)."""
+
+    def __init__(self, trainer, world, rank):
+        from . import cabi
+        self.cabi, self.T, self.world, self.rank = cabi, trainer, world, rank
+        N = trainer.N_cap
+        self.segments = [(trainer.seg_off[i], trainer.seg_w[i]) for i in range(6) if trainer.seg_w[i] > 0]
+        self.stride = cabi.rows_stride(self.segments)
+        dev = trainer.flat_grad.device
+        self.cnt_all = torch.zeros(world, dtype=torch.int32, device=dev)
+        self.cnt_host = torch.zeros(world, dtype=torch.int32).pin_memory()
+        self.cnt_ev = torch.cuda.Event()
+        self.dense_bytes = trainer.t0 * 4
+        self.pack = self.gath = None
+        self.rows = 0
+        self._N = N
+
+    def start_counts(self):
+        """enqueue: all-gather of the ranks' visible-row counts -> pinned host (call once the step's projection has been enqueued)"""
+        dist.all_gather_into_tensor(self.cnt_all, self.T.R.counts[0:1])
+        self.cnt_host.copy_(self.cnt_all, non_blocking=True)
+        self.cnt_ev.record()
+
+    def use_sparse(self):
+        """host: wait for the counts (the device still has the render backward queued) and size this step's exchange"""
+        self.cnt_ev.synchronize()
+        rows = (int(self.cnt_host.max()) + 4095) // 4096 * 4096
+        self.rows = min(max(rows, 4096), self._N)
+        return self.world * self.rows * self.stride * 4 <= 0.6 * self.dense_bytes
+
+    def launch(self):
+        T, rows, st = self.T, self.rows, self.stride
+        if self.pack is None or self.pack.numel() < rows * st:
+            cap = min(int(rows * 1.25), self._N)
+            self.pack = torch.empty(cap * st, dtype=torch.float32, device=T.flat_grad.device)
+            self.gath = torch.empty(self.world * cap * st, dtype=torch.float32, device=T.flat_grad.device)
+        self.cabi.rows_pack(self.segments, rows, T.R.counts[0:1], T.R.p["gaussian_ids"], T.flat_grad, self.pack, zero_source=True)
+        return dist.all_gather_into_tensor(self.gath[:self.world * rows * st], self.pack[:rows * st], async_op=True)
+
+    def add_all(self):
+        rows, st = self.rows, self.stride
+        for p in range(self.world):  # rank order on every rank: identical sums
+            self.cabi.rows_unpack_add(self.segments, rows, self.cnt_all[p:p + 1], self.T.flat_grad, self.gath[p * rows * st:(p + 1) * rows * st])
 
 
 class DataParallelStep:
@@ -97,11 +154,20 @@ class DataParallelStep:
     sample generation + SDF stage). Every rank applies the same update to its replica. Call flush() before reading parameters or
     stopping a timer: it completes the last step's splat update."""
 
-    def __init__(self, trainer, world=None):
+    def __init__(self, trainer, world=None, sparse_rows=True):
+        """sparse_rows: exchange the splat segment by its visible rows when that is clearly smaller than the dense all-reduce (CUDA
+        trainers with one camera per step; see SparseRowExchange)."""
         self.T = trainer
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         self.x = GradientExchange()
         self._pending_splat = False
+        self.sparse = None
+        fg = getattr(trainer, "flat_grad", None)
+        if (sparse_rows and self.world > 1 and dist.is_initialized() and fg is not None and fg.is_cuda and hasattr(trainer, "seg_off")
+                and getattr(getattr(trainer, "R", None), "C", 0) == 1):
+            self.sparse = SparseRowExchange(trainer, self.world, dist.get_rank())
+        self._sparse_work = None
+        self.sparse_steps = self.dense_steps = 0
 
     def _mark(self, name):
         R = getattr(self.T, "R", None)
@@ -110,6 +176,10 @@ class DataParallelStep:
 
     def _before_render(self):
         self.x.before_render()
+        if self._sparse_work is not None:
+            self._sparse_work.wait()
+            self._sparse_work = None
+            self.sparse.add_all()
         self._mark("wait_splat_allreduce")
         if self._pending_splat:
             self.T.adam_splat(1.0 / self.world)
@@ -121,12 +191,23 @@ class DataParallelStep:
             out = T.train_step(*args, **kw)
             T.adam_all(1.0)
             return out
-        out = T.train_step(*args, on_sdf_grads_ready=self.x.on_sdf_grads_ready, before_render=self._before_render, **kw)
-        self.x.finish_step(T.flat_grad[:T.t0])  # splat all-reduce in flight; returns once the SDF segment is reduced
+        out = T.train_step(*args, on_sdf_grads_ready=self._on_sdf_grads_ready, before_render=self._before_render, **kw)
+        if self.sparse is not None and self.sparse.use_sparse():
+            self._sparse_work = self.sparse.launch()  # visible rows in flight
+            self.x.finish_step(None)                  # returns once the SDF segment is reduced
+            self.sparse_steps += 1
+        else:
+            self.x.finish_step(T.flat_grad[:T.t0])  # splat all-reduce in flight; returns once the SDF segment is reduced
+            self.dense_steps += 1
         self._mark("wait_sdf_allreduce")
         self._pending_splat = True
         T.adam_sdf(1.0 / self.world)
         return out
+
+    def _on_sdf_grads_ready(self, sdf_segment):
+        self.x.on_sdf_grads_ready(sdf_segment)
+        if self.sparse is not None:
+            self.sparse.start_counts()
 
     def flush(self):
         if self.world > 1:

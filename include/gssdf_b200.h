@@ -49,7 +49,7 @@ const char *gssdf_last_error(void);
 /* "gssdf_b200 <ver> sm_100a" */
 const char *gssdf_version(void);
 /* Argument structs grow between revisions: a binding compiled against this header must see the same number from the library. */
-#define GSSDF_ABI_REVISION 13
+#define GSSDF_ABI_REVISION 14
 int32_t gssdf_abi_revision(void);
 
 /* L2 residency hint: marks [ptr, ptr+bytes) as a persisting access-policy window for kernels launched on `stream` from now on
@@ -683,6 +683,33 @@ typedef struct gssdf_adam_args {
     void *mlp_packed;
 } gssdf_adam_args;
 int gssdf_adam_step(const gssdf_adam_args *a, gssdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (e) data parallelism: sparse exchange of the splat gradient. Only the rows of the VISIBLE splats of a rank's frame carry a gradient
+ *     (15 % of the rows in the bench scene), so for small world sizes the ranks exchange those rows instead of all-reducing the dense
+ *     [N x 59] segment: gssdf_rows_pack gathers row row_ids[k] of every segment of the flat buffer into one packed row
+ *     [id | segment 0 | segment 1 | ...] (k < *n_rows), the packed rows travel with one all-gather, and gssdf_rows_unpack_add adds a
+ *     peer's packed rows into the local flat gradient. The sum over ranks is the same as the dense all-reduce's (zero rows add nothing).
+ *     No reference counterpart (the reference trains on one GPU).
+ * ------------------------------------------------------------------------------------------ */
+#define GSSDF_ROWS_MAX_SEGMENTS 8
+typedef struct gssdf_row_segment {
+    int64_t offset;          /* first element of the segment in the flat buffer */
+    int32_t width, pad_;     /* floats per row */
+} gssdf_row_segment;
+typedef struct gssdf_rows_args {
+    int32_t n_segments;
+    int32_t zero_source;     /* pack only: 1 = the packed elements of `flat` are zeroed (every rank then adds ALL ranks' packed rows, its own
+                                included, in rank order: the replicas stay bit-identical, like after an all-reduce) */
+    gssdf_row_segment segments[GSSDF_ROWS_MAX_SEGMENTS];
+    int64_t cap_rows;        /* rows allocated in `packed`; row stride = 1 + sum of the segment widths (floats) */
+    const int32_t *n_rows;   /* device int32: rows [0, min(*n_rows, cap_rows)) are packed / unpacked */
+    const int64_t *row_ids;  /* pack: [>= *n_rows] row of the flat segments that packed row k comes from (gaussian_ids); unpack: unused */
+    float *flat;             /* pack: read; unpack: += (atomic: a row may occur more than once with several cameras) */
+    float *packed;           /* [cap_rows, stride]; column 0 holds the row id (int32 bit pattern). pack: written; unpack: read */
+} gssdf_rows_args;
+int gssdf_rows_pack(const gssdf_rows_args *a, gssdf_stream_t stream);
+int gssdf_rows_unpack_add(const gssdf_rows_args *a, gssdf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * f-3 (second half)  Densification of NeuralGS (include/neural_gaussian/neural_gaussian.cpp:568-926).

@@ -654,3 +654,53 @@ def test_gate_compaction_sizes_and_degenerate_masks(n, live, p_keep):
     ref[:live] = 0
     ref[sel] = src[:k].cpu().numpy()
     assert np.array_equal(dst.cpu().numpy(), ref)
+
+
+def test_rows_pack_unpack_equal_index_ops():
+    """(e) gssdf_rows_pack / gssdf_rows_unpack_add == torch index_select / index_add over the six splat segments, with a device-side row
+    count, zero_source, and duplicate rows on the unpack side."""
+    from gssdf_b200 import cabi
+    dev = _dev()
+    g = torch.Generator(dev).manual_seed(3)
+    N, widths = 5000, [3, 4, 3, 1, 3, 45]
+    offs = [0]
+    for w in widths:
+        offs.append(offs[-1] + N * w)
+    flat = torch.randn(offs[-1] + 7, device=dev, generator=g)
+    segments = list(zip(offs[:-1], widths))
+    stride = cabi.rows_stride(segments)
+    assert stride == 60
+    ids = torch.randperm(N, device=dev, generator=g)[:1800].to(torch.int64)
+    n_rows = torch.tensor([1500], dtype=torch.int32, device=dev)
+    cap_rows = 1700
+    packed = torch.full((cap_rows, stride), 7.5, device=dev)
+    src = flat.clone()
+    cabi.rows_pack(segments, cap_rows, n_rows, ids, flat, packed, zero_source=True)
+    torch.cuda.synchronize()
+    live = ids[:1500]
+    assert torch.equal(packed[:1500, 0].view(torch.int32).to(torch.int64), live)
+    col = 1
+    for (o, w) in segments:
+        seg = src[o:o + N * w].view(N, w)
+        assert torch.equal(packed[:1500, col:col + w], seg[live])
+        now = flat[o:o + N * w].view(N, w)
+        assert float(now[live].abs().max()) == 0.0  # zero_source
+        keep = torch.ones(N, dtype=torch.bool, device=dev)
+        keep[live] = False
+        assert torch.equal(now[keep], seg[keep])
+        col += w
+    assert float((packed[1500:] - 7.5).abs().max()) == 0.0 and torch.equal(flat[offs[-1]:], src[offs[-1]:])
+    # unpack twice (two "ranks" with the same rows) + a duplicate row inside one packed batch
+    packed[1499] = packed[0]
+    dst = torch.zeros_like(flat)
+    cabi.rows_unpack_add(segments, cap_rows, n_rows, dst, packed)
+    cabi.rows_unpack_add(segments, cap_rows, n_rows, dst, packed)
+    torch.cuda.synchronize()
+    col = 1
+    for (o, w) in segments:
+        want = torch.zeros(N, w, device=dev)
+        want.index_add_(0, packed[:1500, 0].view(torch.int32).to(torch.int64), packed[:1500, col:col + w])
+        assert torch.allclose(dst[o:o + N * w].view(N, w), 2 * want, rtol=1e-6, atol=1e-6)
+        col += w
+    # empty batch
+    cabi.rows_unpack_add(segments, cap_rows, torch.zeros(1, dtype=torch.int32, device=dev), dst, packed)
