@@ -385,6 +385,7 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1, 2, 3],
                     help="schedule of the SDF-only work (sample generation, [A], [C]): 0 = in line on one stream, 1 = on a second stream beside the "
                          "render (equal priority), 2 = second stream at high priority, 3 = render stream at high priority")
+    ap.add_argument("--dense-allreduce", action="store_true", help="A/B (N > 1): always all-reduce the dense splat segment (no sparse row exchange)")
     ap.add_argument("--nccl-high-priority", action="store_true", help="A/B (N > 1): run NCCL's kernels on a high-priority stream")
     ap.add_argument("--l2-persist", action="store_true", help="A/B: pin the fp16 hash-table shadow in L2 (gssdf_l2_persist); measured: no effect")
     args = ap.parse_args()
@@ -394,8 +395,10 @@ def main():
     cfg = {"workload": f"{args.workload}: {W}x{H}, {N} splats, SH deg {deg}, synthetic box scene seed 0 (SURVEY 8d), tile 16, packed, "
                        f"1 camera/rank/step", "timing": "CUDA events; inputs (232 B/splat state + images) exceed the 126 MB L2, no flush",
            "parallelism": (f"image-parallel dp{world}, replicated state, one pool of 8 camera poses, rank r renders pose (step + r * {max(8 // world, 1)}) mod 8"
-                           f"{' (--same-cameras: the same pose on every rank)' if args.same_cameras else ''}, 2 NCCL all-reduces/step: SDF segment under "
-                           f"the render backward, splat segment under the next step's SDF stage; replicated Adam with grad_scale 1/{world}")
+                           f"{' (--same-cameras: the same pose on every rank)' if args.same_cameras else ''}, 2 NCCL exchanges/step: SDF segment (all-reduce) under "
+                           f"the render backward; splat segment after the backward, as an all-gather of the ranks' visible rows when that is clearly "
+                           f"smaller than the dense all-reduce{' (--dense-allreduce: always dense)' if args.dense_allreduce else ''}; replicated Adam "
+                           f"with grad_scale 1/{world}")
            if world > 1 else "single GPU",
            "schedule": ["one stream, stages in line", "SDF-only work (sample generation, [A], [C]) on a second stream beside the render",
                         "SDF-only work on a second, high-priority stream", "render on a high-priority stream, SDF-only work on a second stream"][args.overlap]}
@@ -534,7 +537,8 @@ def main():
     # the splat segment (236 MB) under stage [A] of the NEXT step. Each segment's Adam update (grad_scale = 1 / world) runs as soon as its
     # reduction is complete: SDF groups right after the step, splat groups just before the next render touches the splats.
     from gssdf_b200 import densify, parallel
-    DP = parallel.DataParallelStep(T, world)  # gssdf_b200/parallel.py: the step + its two overlapped all-reduces + per-segment Adam
+    # gssdf_b200/parallel.py: the step + its two overlapped exchanges + per-segment Adam (splat segment: visible rows when that is smaller)
+    DP = parallel.DataParallelStep(T, world, sparse_rows=not args.dense_allreduce)
     DEN = densify.Densifier(T, num_train_data=n_cams, sh_degree=deg)
 
     def pre_render():
@@ -717,6 +721,7 @@ def main():
                                      "traffic is below the algorithmic bytes): see issue_slots and profiles/",
                              "raster_fwd": {"achieved": alg_fwd / t_fwd / 1e9, "frac": alg_fwd / t_fwd / 1e9 / pk["hbm_gbs"],
                                             "kernel_ms": t_fwd * 1e3, "algorithmic_bytes": alg_fwd}},
+                "splat_exchange_steps": {"visible_rows": DP.sparse_steps, "dense_allreduce": DP.dense_steps} if world > 1 else None,
                 "counts": cnt, "counts_end": cnt_end, "sdf_counts": sdf_counts, "loss_end": last_loss, "loss_finite": bool(np.isfinite(last_loss)),
                 "stage_ms": stage_ms}
         if world == 1 and not args.no_stock_cuda:

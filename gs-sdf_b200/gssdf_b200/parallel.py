@@ -98,8 +98,9 @@ class SparseRowExchange:
     all-gather is sized to the largest count. use_sparse() falls back to the dense all-reduce when the gathered rows would not be
     clearly smaller than the dense segment (large world sizes, most splats visible)."""
 
-    def __init__(self, trainer, world, rank):
+    def __init__(self, trainer, world, rank, always=False):
         from . import cabi
+        self.always = always
         self.cabi, self.T, self.world, self.rank = cabi, trainer, world, rank
         N = trainer.N_cap
         self.segments = [(trainer.seg_off[i], trainer.seg_w[i]) for i in range(6) if trainer.seg_w[i] > 0]
@@ -122,9 +123,9 @@ class SparseRowExchange:
     def use_sparse(self):
         """host: wait for the counts (the device still has the render backward queued) and size this step's exchange"""
         self.cnt_ev.synchronize()
-        rows = (int(self.cnt_host.max()) + 4095) // 4096 * 4096
-        self.rows = min(max(rows, 4096), self._N)
-        return self.world * self.rows * self.stride * 4 <= 0.6 * self.dense_bytes
+        rows = (int(self.cnt_host.max()) + 255) // 256 * 256
+        self.rows = min(max(rows, 256), self._N)
+        return self.always or self.world * self.rows * self.stride * 4 <= 0.6 * self.dense_bytes
 
     def launch(self):
         T, rows, st = self.T, self.rows, self.stride
@@ -155,8 +156,8 @@ class DataParallelStep:
     stopping a timer: it completes the last step's splat update."""
 
     def __init__(self, trainer, world=None, sparse_rows=True):
-        """sparse_rows: exchange the splat segment by its visible rows when that is clearly smaller than the dense all-reduce (CUDA
-        trainers with one camera per step; see SparseRowExchange)."""
+        """sparse_rows: True = exchange the splat segment by its visible rows when that is clearly smaller than the dense all-reduce (CUDA
+        trainers with one camera per step; see SparseRowExchange), "always" = whenever possible, False = dense all-reduce only."""
         self.T = trainer
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         self.x = GradientExchange()
@@ -165,7 +166,7 @@ class DataParallelStep:
         fg = getattr(trainer, "flat_grad", None)
         if (sparse_rows and self.world > 1 and dist.is_initialized() and fg is not None and fg.is_cuda and hasattr(trainer, "seg_off")
                 and getattr(getattr(trainer, "R", None), "C", 0) == 1):
-            self.sparse = SparseRowExchange(trainer, self.world, dist.get_rank())
+            self.sparse = SparseRowExchange(trainer, self.world, dist.get_rank(), always=(sparse_rows == "always"))
         self._sparse_work = None
         self.sparse_steps = self.dense_steps = 0
 
