@@ -75,7 +75,13 @@ def test_sparse_row_exchange_equals_dense_allreduce_world2():
         pytest.skip("needs two GPUs")
     sparse, dense = _run("always"), _run(False)
     assert sparse[0][2] == 3 and sparse[0][3] == 0 and dense[0][2] == 0 and dense[0][3] == 3
-    assert torch.equal(sparse[0][1], sparse[1][1]), "replicas diverged under the sparse exchange"
-    assert torch.equal(dense[0][1], dense[1][1])
-    d = (sparse[0][1] - dense[0][1]).abs().max()
-    assert float(d) <= 1e-6, float(d)  # same sums; the hash-table REDs of the SDF kernels are order-dependent at the 1e-7 level
+    t0 = 4000 * 59  # splat segment | (pad) | hash table | decoder
+    gap = lambda a, b: (float((a[:t0] - b[:t0]).abs().max()), float((a[t0:] - b[t0:]).abs().max()))
+    report = dict(sparse_replicas=gap(sparse[0][1], sparse[1][1]), dense_replicas=gap(dense[0][1], dense[1][1]),
+                  sparse_vs_dense=gap(sparse[0][1], dense[0][1]))
+    print(report)
+    # the SDF segment is all-reduced in both runs: bit-identical replicas. The hash-table REDs of the SDF kernels are order-dependent at
+    # the 1e-7 level, so two RUNS agree to rounding only.
+    assert report["dense_replicas"] == (0.0, 0.0), report
+    assert report["sparse_replicas"] == (0.0, 0.0), report
+    assert max(report["sparse_vs_dense"]) <= 1e-6, report
