@@ -705,7 +705,8 @@ def main():
                         "ms_per_step": ms_e2e},
                 # ours only (torch's RNG fills not counted): 30 of GsSdfStep - table cast - weight pack (now inside the Adam call) + normal-consistency
                 # + isotropic + Adam + weight pack + 6 sample-generation kernels + octree query + gate compaction (3, replaces the gate count) + row scatter (2) + densify statistics
-                "gpu_launches": args.steps * (render.GsSdfStep.KERNELS_PER_STEP - 2 + 2 + 2 + 7 + 2 + 2 + 1),
+                # (N > 1 with the sparse exchange: + row pack + one row unpack per rank; NCCL's own kernels are not ours)
+                "gpu_launches": args.steps * (render.GsSdfStep.KERNELS_PER_STEP - 2 + 2 + 2 + 7 + 2 + 2 + 1 + ((1 + world) if DP.sparse_steps else 0)),
                 "step_contents": "[A] octree ray-march sample generation of 3277 depth rays (~32 k points) + SDF stage on them, [B] render, [C] "
                                  "GS<->SDF coupling gated by visibility and octree validity, [D] L1 + DSSIM + depth L1 + normal-consistency + "
                                  "isotropic -> backward, Adam over all parameter groups, densification statistics (update_state); not in the "
