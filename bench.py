@@ -397,7 +397,7 @@ def main():
            "parallelism": (f"image-parallel dp{world}, replicated state, one pool of 8 camera poses, rank r renders pose (step + r * {max(8 // world, 1)}) mod 8"
                            f"{' (--same-cameras: the same pose on every rank)' if args.same_cameras else ''}, 2 NCCL exchanges/step: SDF segment (all-reduce) under "
                            f"the render backward; splat segment after the backward, as an all-gather of the ranks' visible rows when they are "
-                           f"smaller than the dense segment, else a dense all-reduce{' (--dense-allreduce: always dense)' if args.dense_allreduce else ''}; replicated Adam "
+                           f"less than half the dense segment, else a dense all-reduce{' (--dense-allreduce: always dense)' if args.dense_allreduce else ''}; replicated Adam "
                            f"with grad_scale 1/{world}")
            if world > 1 else "single GPU",
            "schedule": ["one stream, stages in line", "SDF-only work (sample generation, [A], [C]) on a second stream beside the render",

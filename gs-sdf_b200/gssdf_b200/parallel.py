@@ -95,8 +95,8 @@ class SparseRowExchange:
     (gssdf_rows_pack, which also clears those rows locally) and every rank adds ALL ranks' packed rows, its own included, in rank order
     (gssdf_rows_unpack_add): the same sum on every rank, bit for bit, like after an all-reduce. The row counts differ per rank and step;
     they are exchanged first (one int32 per rank), read on the host while the render backward is still queued on the device, and the
-    all-gather is sized to the largest count. use_sparse() falls back to the dense all-reduce when the gathered rows would be larger
-    than the dense segment (large world sizes, most splats visible)."""
+    all-gather is sized to the largest count. use_sparse() falls back to the dense all-reduce unless the gathered rows are less than half
+    the dense segment (larger world sizes, most splats visible)."""
 
     def __init__(self, trainer, world, rank, always=False):
         from . import cabi
@@ -125,9 +125,10 @@ class SparseRowExchange:
         self.cnt_ev.synchronize()
         rows = (int(self.cnt_host.max()) + 255) // 256 * 256
         self.rows = min(max(rows, 256), self._N)
-        # an all-gather delivers (world - 1) / world of the gathered bytes to every rank, a ring all-reduce moves about twice the dense
-        # segment: the rows win while the gathered rows are no larger than the dense segment
-        return self.always or self.world * self.rows * self.stride * 4 <= self.dense_bytes
+        # measured on B200 / NVLink 5 (profiles/r2y_*.json): at 2 ranks (gathered rows = 0.31 x the dense segment) the rows win (4.68 vs
+        # 4.77 ms / step); at 4 ranks (0.62 x) the shorter wait is eaten by the pack / unpack launches and the host read of the counts
+        # (5.09 vs 5.05 ms): sparse only while the gathered rows are clearly smaller
+        return self.always or self.world * self.rows * self.stride * 4 <= 0.5 * self.dense_bytes
 
     def launch(self):
         T, rows, st = self.T, self.rows, self.stride
@@ -158,7 +159,7 @@ class DataParallelStep:
     stopping a timer: it completes the last step's splat update."""
 
     def __init__(self, trainer, world=None, sparse_rows=True):
-        """sparse_rows: True = exchange the splat segment by its visible rows when the gathered rows are smaller than the dense segment (CUDA
+        """sparse_rows: True = exchange the splat segment by its visible rows when the gathered rows are less than half the dense segment (CUDA
         trainers with one camera per step; see SparseRowExchange), "always" = whenever possible, False = dense all-reduce only."""
         self.T = trainer
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
