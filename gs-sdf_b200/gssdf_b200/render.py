@@ -352,9 +352,11 @@ class GsSdfStep:
             if getattr(self, "octree", None) is not None:
                 self.octree.valid_mask(samples, self.valid_mask, n_live=n_live)
             if self.compact_gate and self.mlp_mode == 1:
-                self._coupling_compact(net, samples, n_live, on_sdf_grads_ready)
+                self._coupling_compact(net, samples, n_live, None)
                 if side is not None:
-                    self._ev_c.record(side)
+                    self._ev_c.record(side)  # dL/d sample is ready: all the projection backward waits for
+                if on_sdf_grads_ready is not None:  # the hash-table / decoder gradients are final (NCCL, or the caller's SDF optimiser
+                    on_sdf_grads_ready(self.flat_grad[self.table_grad.storage_offset():])  # step, order themselves after the stream current here)
         if self.compact_gate and self.mlp_mode == 1:
             wait_c = (lambda: torch.cuda.current_stream().wait_event(self._ev_c)) if side is not None else None
             loss = R.backward(scene["means"], scene["quats"], scene["scales"], scene["opacities"], scene["sh"], viewmats, Ks, gt_image, randns,
