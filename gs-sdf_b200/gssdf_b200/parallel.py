@@ -192,15 +192,6 @@ class DataParallelStep:
     def step(self, *args, **kw):
         T = self.T
         if self.world <= 1:
-            if getattr(T, "overlap", False):
-                # two-stream schedule: the SDF groups step on the SDF stream as soon as [C] has produced their gradients -- a
-                # bandwidth-bound pass beside the issue-bound raster backward -- and only the splat groups step after the backward
-                out = T.train_step(*args, on_sdf_grads_ready=lambda seg: T.adam_sdf(1.0), **kw)
-                side = getattr(T, "_side", None)
-                if side is not None:
-                    torch.cuda.current_stream().wait_stream(side)  # the step's work is complete on the caller's stream
-                T.adam_splat(1.0)
-                return out
             out = T.train_step(*args, **kw)
             T.adam_all(1.0)
             return out

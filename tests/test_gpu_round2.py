@@ -624,7 +624,7 @@ def test_two_stream_schedule_equals_in_line_schedule():
                 torch.cuda.synchronize()
                 rec.append((float(loss), float(sdf_loss), T.flat_grad.clone(), int(T.n_gate[0]), int(RS.counts[0])))
                 T.adam_all()
-            else:       # the way bench.py drives it: with two streams the SDF groups step on the SDF stream right after [C]
+            else:       # the way bench.py drives it
                 loss, sdf_loss = DP.step(_t(V[None], dev), _t(K[None], dev), gt, RS.xyz, RS.ray_sdf, rn, ray_n_live=RS.counts)
                 torch.cuda.synchronize()
                 rec.append((float(loss), float(sdf_loss), None, int(T.n_gate[0]), int(RS.counts[0])))
