@@ -24,20 +24,36 @@ def _worker(rank, world, port, out):
     out.put((rank, imgs, float(flat[0]), st["grad2d"].tolist(), st["count"].tolist(), st["vis"].tolist(), st["radii"].tolist()))
     dist.destroy_process_group()
 
+def _launch_world2(worker, sort_key=None, attempts=3):
+    """two spawned gloo ranks on a free local port -> their queue outputs, sorted. The port is found by bind-and-release, so another
+    process can take it before the ranks rendezvous: retry with a new port if a rank dies or never reports."""
+    import queue as _queue
+    last = None
+    for _ in range(attempts):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        try:
+            res = [q.get(timeout=120) for _ in procs]
+            for p in procs:
+                p.join(timeout=60)
+            return sorted(res, key=sort_key)
+        except _queue.Empty as e:
+            last = e
+            for p in procs:
+                p.kill()
+                p.join(timeout=10)
+    raise AssertionError(f"no result from the gloo ranks after {attempts} attempts: {last!r}")
+
 
 def test_data_parallel_host_logic_world2():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted(q.get(timeout=120) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
+    res = _launch_world2(_worker)
         assert p.exitcode == 0
     (r0, im0, f0, g0, c0, v0, rad0), (r1, im1, f1, g1, c1, v1, rad1) = res
     # same epoch permutation on both ranks, disjoint images inside an epoch (5 steps x 2 ranks = the 10 images once each)
@@ -84,18 +100,7 @@ def _xchg_worker(rank, world, port, out):
 
 
 def test_gradient_exchange_overlap_protocol_world2():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_xchg_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted(q.get(timeout=120) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
+    res = _launch_world2(_xchg_worker)
     # sums over ranks {1, 2}: sdf segment (1+2)*(step+1); splat segment 10*(1+2) + 2*step
     expect = [3.0, 30.0, 6.0, 32.0, 9.0, 34.0]
     for rank, seen in res:
@@ -159,18 +164,7 @@ def _dp_worker(rank, world, port, out):
 def test_data_parallel_step_matches_mean_gradient_world2():
     """DataParallelStep on 2 gloo ranks == one process stepping with the rank-averaged gradient; both replicas end bit-identical."""
     from gssdf_b200 import parallel
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted((q.get(timeout=120) for _ in procs), key=lambda r: r[0])
-    for p in procs:
-        p.join(timeout=60)
+    res = _launch_world2(_dp_worker, sort_key=lambda r: r[0])
     # single-process reference with the mean of the two ranks' gradients
     ref = torch.zeros(64 + 24)
     for step in range(3):
