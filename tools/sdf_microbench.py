@@ -1,8 +1,7 @@
-import sys, numpy as np, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/gs-sdf_b200"); sys.path.insert(0, "/root/repo/tests")
-from oracle import oracle as O
+"""Timing of the stand-alone SDF kernels on the two batch shapes of the training step (correctness lives in tests/test_gpu_sdf_parity.py)."""
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gs-sdf_b200"))
 from gssdf_b200 import cabi
-O.build()
 dev = torch.device("cuda:0")
 def _mlp(rng, hidden, n_hidden, in_dim=32):
     dims = [in_dim] + [hidden] * (1 + n_hidden) + [2]; ps = []
@@ -11,15 +10,13 @@ def _mlp(rng, hidden, n_hidden, in_dim=32):
     return np.concatenate(ps).astype(np.float32)
 n, n_hidden = 40000, 3
 rng = np.random.default_rng(7 * n + 3)
-n_params, _ = O.grid_setup()
+n_params = cabi.sdf_table_params(cabi.sdf_net(torch.zeros(1, device=dev), torch.zeros(1, device=dev)))
 table = rng.uniform(-0.5, 0.5, n_params).astype(np.float32); mlp = _mlp(rng, 64, n_hidden)
 x = rng.uniform(0.02, 0.98, (n, 3)).astype(np.float32)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 tab, half, mlp_t, xt = t(table), torch.empty(n_params, dtype=torch.float16, device=dev), t(mlp), t(x)
 cabi.sdf_table_to_half(tab, half)
 v_sdf, v_y1 = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
-r_tg, r_mg, r_vx = O.sdf_bwd(x, table, mlp, v_sdf, v_y1, 64, n_hidden)
-sizes = [("W0", 64*32), ("b0", 64)] + sum([[(f"W{i}", 64*64), (f"b{i}", 64)] for i in range(1, 1+n_hidden)], []) + [("Wo", 128), ("bo", 2)]
 for mode in (0, 1):
     probe = cabi.sdf_net(half, mlp_t, hidden_dim=64, n_hidden=n_hidden)
     packed = torch.empty(cabi.sdf_mlp_packed_bytes(probe), dtype=torch.uint8, device=dev)
@@ -27,10 +24,7 @@ for mode in (0, 1):
     net = cabi.sdf_net(half, mlp_t, hidden_dim=64, n_hidden=n_hidden, mlp_mode=mode, mlp_packed=packed if mode else None)
     tg, mg, vx = torch.zeros(n_params, device=dev), torch.zeros(len(mlp), device=dev), torch.empty(n, 3, device=dev)
     cabi.sdf_bwd(net, xt, t(v_sdf), t(v_y1), tg, mg, vx); torch.cuda.synchronize()
-    m = mg.cpu().numpy(); o = 0
-    print("mode", mode, "L2 rel", np.linalg.norm(m - r_mg) / np.linalg.norm(r_mg))
-    for name, sz in sizes:
-        d = np.abs(m[o:o+sz] - r_mg[o:o+sz]); print(f"  {name}: max|ref| {np.abs(r_mg[o:o+sz]).max():.3e} max err {d.max():.3e} at {d.argmax()}"); o += sz
+    print("mlp_mode", mode)
     # timing on the two shapes of the training step (bench.py 1080p-1M): ray samples 32768 x 7 variants (no dL/dx) and splat
     # samples 152864 x 7 variants (dL/dx through variant 0)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
