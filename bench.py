@@ -385,6 +385,8 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1, 2, 3],
                     help="schedule of the SDF-only work (sample generation, [A], [C]): 0 = in line on one stream, 1 = on a second stream beside the "
                          "render (equal priority), 2 = second stream at high priority, 3 = render stream at high priority")
+    ap.add_argument("--no-cover", action="store_true", help="A/B (N > 1, two-stream schedule): keep sample generation + [A] on the second stream "
+                    "even while a dense all-reduce is in flight")
     ap.add_argument("--dense-allreduce", action="store_true", help="A/B (N > 1): always all-reduce the dense splat segment (no sparse row exchange)")
     ap.add_argument("--nccl-high-priority", action="store_true", help="A/B (N > 1): run NCCL's kernels on a high-priority stream")
     ap.add_argument("--l2-persist", action="store_true", help="A/B: pin the fp16 hash-table shadow in L2 (gssdf_l2_persist); measured: no effect")
@@ -539,6 +541,7 @@ def main():
     from gssdf_b200 import densify, parallel
     # gssdf_b200/parallel.py: the step + its two overlapped exchanges + per-segment Adam (splat segment: visible rows when that is smaller)
     DP = parallel.DataParallelStep(T, world, sparse_rows=not args.dense_allreduce)
+    DP.cover_dense_exchange = not args.no_cover
     DEN = densify.Densifier(T, num_train_data=n_cams, sh_degree=deg)
 
     def pre_render():

@@ -172,6 +172,7 @@ class DataParallelStep:
             self.sparse = SparseRowExchange(trainer, self.world, dist.get_rank(), always=(sparse_rows == "always"))
         self._sparse_work = None
         self.sparse_steps = self.dense_steps = 0
+        self.cover_dense_exchange = True
 
     def _mark(self, name):
         R = getattr(self.T, "R", None)
@@ -204,6 +205,10 @@ class DataParallelStep:
             self.x.finish_step(T.flat_grad[:T.t0])  # splat all-reduce in flight; returns once the SDF segment is reduced
             self.dense_steps += 1
         self._mark("wait_sdf_allreduce")
+        if self.cover_dense_exchange and hasattr(T, "overlap_ray_stage"):
+            # two-stream schedule: with the dense all-reduce in flight the next step's sample generation + [A] stay on the caller's stream,
+            # ahead of the wait for it; with the (short) row exchange they go to the second stream like on a single GPU
+            T.overlap_ray_stage = self._sparse_work is not None
         self._pending_splat = True
         T.adam_sdf(1.0 / self.world)
         return out

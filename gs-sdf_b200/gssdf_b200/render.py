@@ -234,6 +234,10 @@ class GsSdfStep:
         # render: [A] beside projection .. raster forward, [C] (which needs the forward's visibilities) beside losses .. SH backward; the
         # projection backward waits for [C]'s dL/d sample. Same kernels, same results; only the schedule changes.
         self.overlap = False
+        # with `overlap`: False keeps sample generation + [A] on the caller's stream (ahead of the render) and only [C] goes to the second
+        # stream -- what a data-parallel caller wants while a dense gradient all-reduce of the previous step is still in flight, which
+        # [A] then covers (parallel.DataParallelStep sets it per step)
+        self.overlap_ray_stage = True
         self.sdf_stream_priority = 0
         self._side = None
         self._ev_fwd, self._ev_c = torch.cuda.Event(), torch.cuda.Event()
@@ -243,14 +247,18 @@ class GsSdfStep:
         """Stream context for work that touches SDF-side state only (ray sample generation, stage [A]). Without `overlap` it is the
         caller's stream; with it, the second stream, ordered after everything the caller's stream has enqueued so far (the previous step's
         optimiser update included)."""
-        if not self.overlap:
+        if not (self.overlap and self.overlap_ray_stage):
             yield
             return
+        side = self._side_stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            yield
+
+    def _side_stream(self):
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.dev, priority=self.sdf_stream_priority)
-        self._side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self._side):
-            yield
+        return self._side
 
     KERNELS_PER_STEP = SplatRenderer.KERNELS_PER_STEP + 9  # + 2 DSSIM kernels + table cast + decoder weight image + gate count + 2 x (7-variant forward, fused train) (mlp_mode 1)
 
@@ -343,7 +351,7 @@ class GsSdfStep:
         # [C] coupling on the stochastic splat samples (rows < nnz, counted on the device)
         samples, n_live = R.p["samples"], R.counts  # counts[0] == nnz
         # the reference's sample gate: vis > visible_thr (& octree validity), counted on the device (no nonzero() / .item() sync)
-        side = self._side if self.overlap else None
+        side = self._side_stream() if self.overlap else None
         assert side is None or (self.compact_gate and self.mlp_mode == 1), "overlap needs the compact-gate tensor-core path"
         if side is not None:  # [C] needs the forward's visibilities / samples: the second stream picks up after the raster forward
             self._ev_fwd.record()

@@ -590,11 +590,12 @@ def test_two_stream_schedule_equals_in_line_schedule():
     cfg = dict(n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=2.0, hidden_dim=64, n_hidden=3)
     table = (rng.uniform(-1, 1, 16 * 2 * (1 << 19)).astype(np.float32)) * 2e-4
     out = {}
-    for overlap in (False, True):
+    for overlap in (False, True, "coupling only"):
         torch.manual_seed(11)
         T = render.GsSdfTrainer(N, (deg + 1) ** 2, W, H, dev, 300000, cfg, n_ray_samples=8192, sh_degree=deg, map_size=14.0,
                                 normal_weight=0.01, isotropic_weight=0.05)
-        T.overlap = overlap
+        T.overlap = bool(overlap)
+        T.overlap_ray_stage = overlap is True  # "coupling only": sample generation + [A] stay on the caller's stream
         probe = T.n_mlp
         mlp = torch.from_numpy(np.random.default_rng(6).uniform(-0.2, 0.2, probe).astype(np.float32)).to(dev)
         op_ = np.clip(sc["opacities"], 1e-6, 1 - 1e-6)
@@ -631,12 +632,13 @@ def test_two_stream_schedule_equals_in_line_schedule():
                 assert float(T.flat_grad.abs().max()) == 0.0 and T.t_sdf == T.t_splat == it + 1
         torch.cuda.synchronize()
         out[overlap] = (rec, T.params.clone())
-    for (l0, s0, g0, n0, c0), (l1, s1, g1, n1, c1) in zip(out[False][0], out[True][0]):
-        assert n0 == n1 and c0 == c1 and n0 > 0 and c0 > 0
-        assert abs(l0 - l1) <= 1e-5 * abs(l0) and abs(s0 - s1) <= 1e-4 * abs(s0), (l0, l1, s0, s1)
-        if g0 is not None:
-            assert rel(g1.cpu().numpy(), g0.cpu().numpy()) < 1e-4
-    assert float((out[False][1] - out[True][1]).abs().max()) < 1e-3
+    for other in (True, "coupling only"):
+        for (l0, s0, g0, n0, c0), (l1, s1, g1, n1, c1) in zip(out[False][0], out[other][0]):
+            assert n0 == n1 and c0 == c1 and n0 > 0 and c0 > 0
+            assert abs(l0 - l1) <= 1e-5 * abs(l0) and abs(s0 - s1) <= 1e-4 * abs(s0), (l0, l1, s0, s1)
+            if g0 is not None:
+                assert rel(g1.cpu().numpy(), g0.cpu().numpy()) < 1e-4
+        assert float((out[False][1] - out[other][1]).abs().max()) < 1e-3
 
 
 @pytest.mark.parametrize("n,live,p_keep", [(100000, 91000, 0.4), (40000, 40000, 1.0), (40000, 40000, 0.0), (70000, 0, 0.5), (1, 1, 1.0),
