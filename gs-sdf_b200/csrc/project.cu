@@ -20,17 +20,35 @@ struct Cam {
     float fx, fy, cx, cy;
 };
 
+// The fp32 operation STRUCTURE below (which product of a sum is rounded on its own, which one is fused into an FMA, the approximate
+// reciprocal) is the one nvcc gives the reference's GLM expressions under its build flags (-O3 --use_fast_math), read off the SASS of
+// oracle/_ref/gsplat_ref.so. `radii = ceil(3.33 sqrt(mean2d^2 - temp))` sits behind a catastrophic cancellation, so anything else
+// changes the integer radius of ~1 % of the splats and with it the chained tile lists (tests/test_gpu_splat_parity.py reports the count).
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float dot3_left(float a0, float b0, float a1, float b1, float a2, float b2) {
+    // a0 b0 + a1 b1 + a2 b2 as the reference build evaluates glm's  m[0] * v.x + m[1] * v.y + m[2] * v.z :
+    // the MIDDLE product is rounded, the first and the last are fused
+    return fma_(a2, b2, fma_(a0, b0, mul_(a1, b1)));
+}
+
 __device__ __forceinline__ void quat_to_rotmat(const float4 qv, float q[9]) {
     // Utils.cuh:142-164 ; q is the row-major rotation matrix
     float w = qv.x, x = qv.y, y = qv.z, z = qv.w;
-    float inv_norm = rsqrtf(x * x + y * y + z * z + w * w);
-    x *= inv_norm; y *= inv_norm; z *= inv_norm; w *= inv_norm;
-    float x2 = x * x, y2 = y * y, z2 = z * z;
-    float xy = x * y, xz = x * z, yz = y * z;
-    float wx = w * x, wy = w * y, wz = w * z;
-    q[0] = 1.f - 2.f * (y2 + z2); q[3] = 2.f * (xy + wz);       q[6] = 2.f * (xz - wy);
-    q[1] = 2.f * (xy - wz);       q[4] = 1.f - 2.f * (x2 + z2); q[7] = 2.f * (yz + wx);
-    q[2] = 2.f * (xz + wy);       q[5] = 2.f * (yz - wx);       q[8] = 1.f - 2.f * (x2 + y2);
+    const float inv_norm = rsqrtf(fma_(w, w, fma_(z, z, fma_(x, x, mul_(y, y)))));
+    x = mul_(x, inv_norm); y = mul_(y, inv_norm); z = mul_(z, inv_norm); w = mul_(w, inv_norm);
+    const float z2 = mul_(z, z), y2 = mul_(y, y);
+    const float wx = mul_(x, w), wy = mul_(y, w), wz = mul_(z, w);
+    const float y2z2 = __fadd_rn(y2, z2), x2z2 = fma_(x, x, z2), x2y2 = fma_(x, x, y2);
+    auto twice = [](float v) { return __fadd_rn(v, v); };
+    q[0] = __fsub_rn(1.f, twice(y2z2));   q[3] = twice(fma_(x, y, wz));        q[6] = twice(fma_(x, z, -wy));
+    q[1] = twice(fma_(x, y, -wz));        q[4] = __fsub_rn(1.f, twice(x2z2));  q[7] = twice(fma_(y, z, wx));
+    q[2] = twice(fma_(x, z, wy));         q[5] = twice(fma_(y, z, -wx));       q[8] = __fsub_rn(1.f, twice(x2y2));
 }
 
 struct ProjOut {
@@ -51,7 +69,7 @@ __device__ __forceinline__ bool project_one(const Cam &cam, const float mean[3],
     float mc[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
-        mc[r] = R[r * 3 + 0] * mean[0] + R[r * 3 + 1] * mean[1] + R[r * 3 + 2] * mean[2] + cam.t[r];
+        mc[r] = __fadd_rn(dot3_left(R[r * 3 + 0], mean[0], R[r * 3 + 1], mean[1], R[r * 3 + 2], mean[2]), cam.t[r]);
     if (mc[2] < near_plane || mc[2] > far_plane) return false;
 
     float q[9];
@@ -59,8 +77,8 @@ __device__ __forceinline__ bool project_one(const Cam &cam, const float mean[3],
     float RSw[9];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        RSw[r * 3 + 0] = q[r * 3 + 0] * scale[0];
-        RSw[r * 3 + 1] = q[r * 3 + 1] * scale[1];
+        RSw[r * 3 + 0] = mul_(q[r * 3 + 0], scale[0]);
+        RSw[r * 3 + 1] = mul_(q[r * 3 + 1], scale[1]);
         RSw[r * 3 + 2] = q[r * 3 + 2];
     }
     float RSc[9];
@@ -68,7 +86,7 @@ __device__ __forceinline__ bool project_one(const Cam &cam, const float mean[3],
     for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-            RSc[r * 3 + c] = R[r * 3 + 0] * RSw[0 + c] + R[r * 3 + 1] * RSw[3 + c] + R[r * 3 + 2] * RSw[6 + c];
+            RSc[r * 3 + c] = dot3_left(R[r * 3 + 0], RSw[0 + c], R[r * 3 + 1], RSw[3 + c], R[r * 3 + 2], RSw[6 + c]);
     // WH = [RSc.col0 | RSc.col1 | mean_c] ; M = K * WH (rows u, v, w)
     float WH[9];
 #pragma unroll
@@ -76,20 +94,23 @@ __device__ __forceinline__ bool project_one(const Cam &cam, const float mean[3],
     float *M = o.M;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        M[0 + c] = cam.fx * WH[0 + c] + cam.cx * WH[6 + c];
-        M[3 + c] = cam.fy * WH[3 + c] + cam.cy * WH[6 + c];
+        M[0 + c] = fma_(cam.cx, WH[6 + c], mul_(cam.fx, WH[0 + c]));  // transpose(WH) * K with K's zeros: (fx a + 0 b) + cx c
+        M[3 + c] = fma_(cam.cy, WH[6 + c], mul_(cam.fy, WH[3 + c]));
         M[6 + c] = WH[6 + c];
     }
-    const float distance = (M[6] * M[6] + M[7] * M[7]) - M[8] * M[8];
+    const float distance = fma_(-M[8], M[8], fma_(M[7], M[7], mul_(M[6], M[6])));
     bool valid = distance != 0.0f;
-    const float fi = 1.0f / distance;
-    const float f0 = fi, f1 = fi, f2 = -fi;
-    o.mean2d[0] = (f0 * M[0] * M[6] + f1 * M[1] * M[7]) + f2 * M[2] * M[8];
-    o.mean2d[1] = (f0 * M[3] * M[6] + f1 * M[4] * M[7]) + f2 * M[5] * M[8];
-    const float tmp0 = (f0 * M[0] * M[0] + f1 * M[1] * M[1]) + f2 * M[2] * M[2];
-    const float tmp1 = (f0 * M[3] * M[3] + f1 * M[4] * M[4]) + f2 * M[5] * M[5];
-    const float he0 = o.mean2d[0] * o.mean2d[0] - tmp0;
-    const float he1 = o.mean2d[1] * o.mean2d[1] - tmp1;
+    const float fi = rcp_approx(distance);  // 1 / distance under --use_fast_math
+    float he[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {  // f * M_a with f = (1, 1, -1) / distance, then the sums with M2 and with M_a
+        const float *Ma = M + 3 * a;
+        const float g0 = mul_(Ma[0], fi), g1 = mul_(Ma[1], fi), g2 = mul_(Ma[2], -fi);
+        o.mean2d[a] = fma_(M[8], g2, fma_(M[7], g1, mul_(M[6], g0)));
+        const float tmp = fma_(Ma[2], g2, fma_(Ma[1], g1, mul_(Ma[0], g0)));
+        he[a] = fma_(o.mean2d[a], o.mean2d[a], -tmp);
+    }
+    const float he0 = he[0], he1 = he[1];
     // the reference evaluates max(1e-4, he) and the sqrt in double (Projection2DGSPacked.cu:131-132)
     const float rx = (float)ceil((double)3.33f * sqrt(fmax(1e-4, (double)he0)));
     const float ry = (float)ceil((double)3.33f * sqrt(fmax(1e-4, (double)he1)));
