@@ -633,9 +633,12 @@ def test_two_stream_schedule_equals_in_line_schedule():
         torch.cuda.synchronize()
         out[overlap] = (rec, T.params.clone())
     for other in (True, "coupling only"):
-        for (l0, s0, g0, n0, c0), (l1, s1, g1, n1, c1) in zip(out[False][0], out[other][0]):
+        for k, ((l0, s0, g0, n0, c0), (l1, s1, g1, n1, c1)) in enumerate(zip(out[False][0], out[other][0])):
             assert n0 == n1 and c0 == c1 and n0 > 0 and c0 > 0
-            assert abs(l0 - l1) <= 1e-5 * abs(l0) and abs(s0 - s1) <= 1e-4 * abs(s0), (l0, l1, s0, s1)
+            # the same step on the same parameters agrees to the order of the float REDs; every Adam step (eps 1e-15: a sign-like update
+            # on near-zero gradients) then amplifies that run-to-run noise a little, whatever the schedule
+            tol = 1e-4 if k == 0 else 2e-3
+            assert abs(l0 - l1) <= 0.1 * tol * abs(l0) and abs(s0 - s1) <= tol * abs(s0), (k, l0, l1, s0, s1)
             if g0 is not None:
                 assert rel(g1.cpu().numpy(), g0.cpu().numpy()) < 1e-4
         assert float((out[False][1] - out[other][1]).abs().max()) < 1e-3
