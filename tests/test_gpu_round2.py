@@ -641,7 +641,10 @@ def test_two_stream_schedule_equals_in_line_schedule():
             assert abs(l0 - l1) <= 0.1 * tol * abs(l0) and abs(s0 - s1) <= tol * abs(s0), (k, l0, l1, s0, s1)
             if g0 is not None:
                 assert rel(g1.cpu().numpy(), g0.cpu().numpy()) < 1e-4
-        assert float((out[False][1] - out[other][1]).abs().max()) < 1e-3
+        # parameters after four optimiser steps: equal up to that noise (a sign-like Adam update of a near-zero gradient may flip: a few
+        # entries move by ~ lr per step the other way)
+        pa, pb = out[False][1].cpu().numpy(), out[other][1].cpu().numpy()
+        assert rel(pb, pa) < 1e-3 and float(np.abs(pa - pb).max()) < 0.05, (rel(pb, pa), float(np.abs(pa - pb).max()))
 
 
 @pytest.mark.parametrize("n,live,p_keep", [(100000, 91000, 0.4), (40000, 40000, 1.0), (40000, 40000, 0.0), (70000, 0, 0.5), (1, 1, 1.0),
