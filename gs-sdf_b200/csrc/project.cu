@@ -22,7 +22,7 @@ struct Cam {
 
 // The fp32 operation STRUCTURE below (which product of a sum is rounded on its own, which one is fused into an FMA, the approximate
 // reciprocal) is the one nvcc gives the reference's GLM expressions under its build flags (-O3 --use_fast_math), read off the SASS of
-// oracle/_ref/gsplat_ref.so. `radii = ceil(3.33 sqrt(mean2d^2 - temp))` sits behind a catastrophic cancellation, so anything else
+// the reference kernels compiled with those flags. `radii = ceil(3.33 sqrt(mean2d^2 - temp))` sits behind a catastrophic cancellation, so anything else
 // changes the integer radius of ~1 % of the splats and with it the chained tile lists (tests/test_gpu_splat_parity.py reports the count).
 __device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
